@@ -1,0 +1,138 @@
+/*
+ * zotmer_b200.h -- C ABI of libzot_b200.so, the B200 (sm_100a) implementation of zotmer's k-mer hot path.
+ *
+ * The reference (drtconway/zotmer) is pure Python and has no FFI; the seam this library fills is
+ * "zotmer/commands + zotmer/library  ->  per-k-mer work", i.e. every place where the reference runs
+ * an interpreter loop over k-mers.  Each entry point below names the reference call site(s) it
+ * replaces (paths relative to the reference root).  The Python binding a maintainer would add is
+ * zotmer_b200/_native.py (ctypes); INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 (ZB_OK) or a negative ZB_E_* code; zb_last_error() gives the message
+ *     of the last failure on the calling thread.  No exception crosses this boundary.
+ *   - the caller owns every host buffer; handles (zb_set*, zb_kmerizer*) own device memory until
+ *     the matching *_free / *_close.  Sizes are obtained first (two-call pattern), then fetched.
+ *   - plain pointers and sizes only.  `*_dev` variants take DEVICE pointers on the handle's device
+ *     (used by bench.py for the HBM-resident measurement and by the multi-GPU exchange).
+ *   - one host thread drives one device context; calls on one handle must not be concurrent.
+ *   - k-mer encoding is the reference's: A=0 C=1 G=2 T/U=3, first base most significant, k <= 32
+ *     (zotmer/library/basics.py:42-59).  A "counted set" is a strictly ascending u64 k-mer array
+ *     with a parallel u32 count array (kmerize.py:373-374 `array('L')`/`array('I')`).
+ */
+#ifndef ZOTMER_B200_H
+#define ZOTMER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZB_OK 0
+#define ZB_E_CUDA (-1)     /* a CUDA runtime call failed */
+#define ZB_E_ARG (-2)      /* bad argument (k out of 1..32, null pointer, ...) */
+#define ZB_E_RANGE (-3)    /* value does not fit: codec64 payload > 60 bits (codec64.py:93-99 IndexError),
+                              count > 2^32-1 (kmerize.py:374 array('I') OverflowError) */
+#define ZB_E_FORMAT (-4)   /* corrupt codec64 stream (files.py:58 / codec64.py:128 KeyError) */
+#define ZB_E_NOMEM (-5)
+#define ZB_E_NOGPU (-6)    /* no CUDA device: this library has no CPU path */
+
+typedef struct zb_set zb_set;             /* device-resident counted k-mer set */
+typedef struct zb_kmerizer zb_kmerizer;   /* streaming kmerize+count state */
+
+const char* zb_last_error(void);
+int zb_version(void);
+int zb_device_count(int* n);
+/* number of kernels this library has launched on `device` from the calling thread (bench "gpu_launches") */
+int zb_launch_count(int device, uint64_t* n);
+int zb_device_sync(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * kmerize + count          replaces zotmer/commands/kmerize.py:463-545
+ *   reads()/readFasta/readFastq (library/reads.py:35-125, file.py:19-52), kmersList(K,seq,True)
+ *   (basics.py:303-347), the acgt tally (kmerize.py:492-493), KmerAccumulator2.addList/flush
+ *   (kmerize.py:401-424), radix_sort (misc.py:400-424) and merge() (kmerize.py:41-132).
+ *
+ * feed(): `raw` is the text of ONE input file, or a record-aligned piece of it (a piece must start
+ * at the first byte of a record line group / '>' header line and is parsed exactly as a whole file
+ * would be: FASTA per file.py:19-36, 4-line FASTQ per file.py:38-52 incl. the dropped trailing
+ * partial record).  n < 2^31.  Every window of k consecutive AaCcGgTtUu bytes inside one record
+ * contributes the forward k-mer AND its reverse complement (both=True).
+ * finish(): sorts, counts and returns the both-strand counted set; the kmerizer can be closed after.
+ * ------------------------------------------------------------------------------------------ */
+int zb_kmerize_open(int k, int device, zb_kmerizer** out);
+int zb_kmerize_feed(zb_kmerizer* h, const uint8_t* raw, size_t n, int is_fasta);
+int zb_kmerize_feed_dev(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is_fasta);
+/* pre-parsed input: one code per base (0..3 = ACGT, 4 = break) -- used by the synthetic read generator */
+int zb_kmerize_feed_codes_dev(zb_kmerizer* h, const uint8_t* d_codes, size_t n, uint64_t n_records);
+int zb_kmerize_finish(zb_kmerizer* h, zb_set** result, uint64_t* n_records);
+int zb_kmerize_close(zb_kmerizer* h);
+/* multi-GPU (hash-range all-to-all): extract canonical k-mers of everything fed so far WITHOUT
+ * counting, bucketed by owner = (mix64(kmer) >> 32) * nranks >> 32.  bucket_counts[nranks] (host)
+ * receives the sizes; d_keys (device, capacity >= zb_kmerize_pending) the keys grouped by owner. */
+int zb_kmerize_pending(zb_kmerizer* h, uint64_t* n_keys);
+int zb_kmerize_take_bucketed_dev(zb_kmerizer* h, int nranks, uint64_t* d_keys, uint64_t* bucket_counts);
+/* count canonical keys received from peers (device array, any order) into the kmerizer */
+int zb_kmerize_add_canonical_dev(zb_kmerizer* h, const uint64_t* d_keys, size_t n);
+
+/* ------------------------------------------------------------------------------------------
+ * counted sets
+ * ------------------------------------------------------------------------------------------ */
+/* upload a sorted, duplicate-free set; counts may be NULL (all 1) -- readKmersAndCounts result, files.py:219-227 */
+int zb_set_from_host(int device, const uint64_t* kmers, const uint32_t* counts, size_t n, zb_set** out);
+int zb_set_size(const zb_set* s, size_t* n);
+int zb_set_fetch(const zb_set* s, uint64_t* kmers, uint32_t* counts); /* either may be NULL */
+int zb_set_dev_ptrs(const zb_set* s, const uint64_t** d_kmers, const uint32_t** d_counts);
+int zb_set_free(zb_set* s);
+
+/* hist = {count: number of k-mers} with distinct counts in order of FIRST OCCURRENCE along the
+ * sorted set (the reference's dict insertion order -> JSON key order; kmerize.py:544-545,
+ * merge.py:158); acgt_weighted[x&3] += count (kmerize.py:492-493 == merge.py:159);
+ * acgt_plain[x&3] += 1 (merge.py:88-92, the 2-input path).  Fills min(hist_cap, *n_hist) entries; retry when *n_hist > hist_cap. */
+int zb_set_stats(const zb_set* s, uint64_t acgt_weighted[4], uint64_t acgt_plain[4], uint64_t* total_count,
+                 uint64_t* hist_vals, uint64_t* hist_freqs, size_t hist_cap, size_t* n_hist);
+
+/* N-way union with counts summed -- merge.py:26-86 (merge) + :127-163 (mergeNinto) */
+int zb_merge(int nsets, zb_set* const* sets, zb_set** out);
+/* keep cmin <= count (and count <= cmax when cmax > 0) -- trim.py:54-62 */
+int zb_trim(const zb_set* s, uint64_t cmin, uint64_t cmax, zb_set** out);
+/* y = x >> shift_bits, adjacent duplicates dropped, counts discarded -- commands/dist.py:36-49 (Measure.prep) */
+int zb_project(const zb_set* s, int shift_bits, zb_set** out);
+/* (|X n Y|, |X \ Y|, |Y \ X|) for each listed pair -- library/dist.py:241-265 (split), jaccard.py:31-54.
+ * abc holds 3*npairs u64.  All sets must live on the same device. */
+int zb_pairs_abc(int nsets, zb_set* const* sets, const uint32_t* I, const uint32_t* J, size_t npairs, uint64_t* abc);
+
+/* ------------------------------------------------------------------------------------------
+ * stream codec             replaces zotmer/library/codec64.py:82-150 + files.py:85-110 (delta)
+ * host arrays in, host arrays out; the work runs on `device`.
+ * encode: words must hold n entries (worst case one value per word).  ZB_E_RANGE when a value
+ * (or, with delta, a gap) needs more than 60 bits.
+ * decode: two-call -- out == NULL returns the value count in *n.
+ * ------------------------------------------------------------------------------------------ */
+int zb_encode_u64_stream(int device, const uint64_t* vals, size_t n, int delta, uint64_t* words, size_t* n_words);
+int zb_decode_u64_stream(int device, const uint64_t* words, size_t n_words, int delta, uint64_t* out, size_t* n);
+/* device-resident forms: encode a set straight to its two file streams / build a set from them
+ * (writeKmersAndCounts2 files.py:209-217, readKmersAndCounts files.py:219-227) */
+int zb_set_encode(const zb_set* s, uint64_t* kmer_words, size_t* n_kmer_words, uint64_t* count_words, size_t* n_count_words);
+int zb_set_encode_sizes(const zb_set* s, size_t* n_kmer_words, size_t* n_count_words);
+int zb_set_from_streams(int device, const uint64_t* kmer_words, size_t n_kmer_words,
+                        const uint64_t* count_words, size_t n_count_words, zb_set** out);
+
+/* ------------------------------------------------------------------------------------------
+ * diagnostics: stage-level entry points for tests/ and bench.py (kernel isolation and timing).
+ * Not part of the drop-in surface; host arrays in/out.
+ * ------------------------------------------------------------------------------------------ */
+/* sort keys (and optional u32 payload) in place; max_bits 8..11 = digit width cap; times `iters` sorts */
+int zb_dbg_sort_u64(int device, uint64_t* keys, uint32_t* vals, size_t n, int key_bits, int max_bits, int iters,
+                    float* ms_per_sort);
+/* text -> dense base codes (codes must hold n + 64 bytes) */
+int zb_dbg_parse(int device, const uint8_t* raw, size_t n, int is_fasta, uint8_t* codes, size_t* n_codes,
+                 uint64_t* n_records);
+/* dense base codes -> canonical k-mers in unspecified order (keys must hold n entries) */
+int zb_dbg_extract(int device, int k, const uint8_t* codes, size_t n, uint64_t* keys, size_t* n_keys);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,370 @@
+"""
+GPU parity tests (run on the B200 box: pytest -m gpu).  Every check goes through the C ABI
+(zotmer_b200/_native.py -> libzot_b200.so) and compares with the oracle (oracle/) on the same
+seeded inputs, or with the committed golden fixtures produced by the reference itself.
+Bit-exact: everything on this path is integer work.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import c_oracle as co
+from oracle import zot_oracle as zo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from zotmer_b200 import _native
+    assert _native.device_count() >= 1, "no CUDA device"
+    return _native
+
+
+def g(name):
+    return os.path.join(GOLDEN, name)
+
+
+def rd(name):
+    with open(g(name), "rb") as f:
+        return f.read()
+
+
+def rnd_dna(rng, n):
+    return np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)].tobytes()
+
+
+def make_fastq(rng, genome, nreads, L, err=0.01, pn=0.002):
+    out = []
+    G = np.frombuffer(genome, np.uint8)
+    comp = np.zeros(256, np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    for i in range(nreads):
+        p = int(rng.integers(0, len(G) - L))
+        s = G[p:p + L].copy()
+        if rng.random() < 0.5:
+            s = comp[s[::-1]]
+        e = rng.random(L) < err
+        s[e] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(e.sum()))]
+        nn = rng.random(L) < pn
+        s[nn] = ord("N")
+        out.append(b"@r%d\n%s\n+\n%s\n" % (i, s.tobytes(), b"I" * L))
+    return b"".join(out)
+
+
+def make_fasta(rng, n, width=80, nrec=3):
+    out = []
+    for r in range(nrec):
+        s = rnd_dna(rng, n // nrec)
+        out.append(b">rec%d\n" % r + b"\n".join(s[i:i + width] for i in range(0, len(s), width)) + b"\n")
+    return b"".join(out)
+
+
+# ----------------------------------------------------------------------------- radix sort
+@pytest.mark.parametrize("n", [1, 5, 4095, 4096, 4097, 100000, 1 << 20, 3000001])
+@pytest.mark.parametrize("bits,maxbits", [(50, 8), (64, 8), (62, 10), (50, 10), (10, 8), (50, 11), (33, 9)])
+def test_sort_keys(nat, n, bits, maxbits):
+    rng = np.random.default_rng(n * 131 + bits)
+    keys = rng.integers(0, 2 ** 63, n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, n, dtype=np.uint64)
+    if bits < 64:
+        keys &= np.uint64((1 << bits) - 1)
+    out, _, _ = nat.dbg_sort(keys, None, bits, maxbits)
+    assert np.array_equal(out, np.sort(keys))
+
+
+@pytest.mark.parametrize("n", [7, 4097, 250000])
+def test_sort_pairs_stable(nat, n):
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 50, n, dtype=np.uint64)  # many duplicates: stability is visible through the payload
+    vals = np.arange(n, dtype=np.uint32)
+    out, v, _ = nat.dbg_sort(keys, vals, 50, 8)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(out, keys[order])
+    assert np.array_equal(v, vals[order])
+
+
+def test_sort_skewed(nat):
+    n = 500000
+    rng = np.random.default_rng(3)
+    keys = np.zeros(n, np.uint64)
+    keys[rng.integers(0, n, 1000)] = rng.integers(0, 2 ** 50, 1000, dtype=np.uint64)
+    out, _, _ = nat.dbg_sort(keys, None, 50, 8)
+    assert np.array_equal(out, np.sort(keys))
+    keys[:] = np.uint64(2 ** 64 - 1)
+    out, _, _ = nat.dbg_sort(keys, None, 64, 8)
+    assert np.array_equal(out, keys)
+
+
+# ----------------------------------------------------------------------------- parse
+def expected_fasta_codes(data):
+    out = bytearray()
+    recs = zo.read_fasta(data)
+    for _, seq in recs:
+        out.append(4)
+        out.extend(4 if zo.NUC[b] is None else zo.NUC[b] for b in seq)
+    return bytes(out), len(recs)
+
+
+def kmers_from_codes(codes, k):
+    """canonical k-mers of a code stream (python, small inputs)"""
+    out = []
+    x = 0
+    run = 0
+    msk = (1 << (2 * k)) - 1
+    for c in codes:
+        if c > 3:
+            run = 0
+            x = 0
+            continue
+        x = ((x << 2) | int(c)) & msk
+        run += 1
+        if run >= k:
+            out.append(min(x, zo.rc(k, x)))
+    return sorted(out)
+
+
+@pytest.mark.parametrize("name", ["g1.fa", "kat6.fa", "s0.fa", "j.fa", "empty.fa"])
+def test_parse_fasta_golden_inputs(nat, name):
+    data = rd(name)
+    codes, nrec = nat.dbg_parse(data, True)
+    exp, enrec = expected_fasta_codes(data)
+    assert nrec == enrec
+    assert codes.tobytes() == exp
+
+
+def test_parse_fasta_fuzz(nat):
+    import random
+    rng = random.Random(11)
+    alphabets = [b"ACGT\n", b"ACGTN \n\r\t>", b"AC >\n", b" \n>", b"ACGTacgtnN>\n\r \t\x0b\x0c-", b"A\n"]
+    for it in range(150):
+        al = rng.choice(alphabets)
+        n = rng.choice([1, 15, 16, 17, 100, 4095, 4096, 4097, 16383, 16384, 16385, 40000, 70000])
+        w = [rng.choice([1, 1, 1, 5, 20]) for _ in al]
+        data = bytes(rng.choices(al, weights=w, k=n))
+        if rng.random() < 0.5:
+            data = b">h\n" + data
+        codes, nrec = nat.dbg_parse(data, True)
+        exp, enrec = expected_fasta_codes(data)
+        assert nrec == enrec, it
+        assert codes.tobytes() == exp, it
+
+
+def test_parse_fasta_long_lines_and_blank_runs(nat):
+    rng = np.random.default_rng(4)
+    one_line = b">single line chromosome\n" + rnd_dna(rng, 300000) + b"\n"
+    blanks = b">a\nACGTACGTAC" + b" \n" * 30000 + b"GTACGTACGT\n>b  " + b"x" * 50000 + b"\nAC" + b" " * 40000 + b"GT\n"
+    for data in (one_line, blanks, one_line + blanks):
+        codes, nrec = nat.dbg_parse(data, True)
+        exp, enrec = expected_fasta_codes(data)
+        assert nrec == enrec
+        assert codes.tobytes() == exp
+
+
+@pytest.mark.parametrize("name", ["r1.fq", "r2.fq"])
+def test_parse_fastq_golden_inputs(nat, name):
+    data = rd(name)
+    codes, nrec = nat.dbg_parse(data, False)
+    recs = zo.read_fastq(data)
+    assert nrec == len(recs)
+    for k in (8, 25):
+        exp = sorted(min(x, zo.rc(k, x)) for r in recs for x in zo.kmers_list(k, r[1], False))
+        assert kmers_from_codes(codes, k) == exp
+
+
+def test_parse_fastq_edge_cases(nat):
+    cases = [b"", b"\n", b"@a\nACGT\n+\nIIII", b"@a\nACGT\n+\nIIII\n", b"@a\nACGT\n+\nIIII\n@b\nACGT\n+\n",
+             b"@a\nACGT\n+\nIIII\n@b\nACGT", b"\n\n\n\n\n\n\n\n", b"@a\r\nAC GT\r\n+\r\nIIII\r\n" * 3,
+             b"@a\nACGTACGTAC\n+\nIIIIIIIIII\n" * 5000 + b"@tail\nACGTACGT\n"]
+    for data in cases:
+        codes, nrec = nat.dbg_parse(data, False)
+        recs = zo.read_fastq(data)
+        assert nrec == len(recs), data[:40]
+        exp = sorted(min(x, zo.rc(4, x)) for r in recs for x in zo.kmers_list(4, r[1], False))
+        assert kmers_from_codes(codes, 4) == exp, data[:40]
+
+
+# ----------------------------------------------------------------------------- extract
+@pytest.mark.parametrize("k", [1, 2, 5, 16, 25, 31, 32])
+def test_extract(nat, k):
+    rng = np.random.default_rng(k)
+    for n in (0, 1, 31, 32, 33, 4095, 4096, 4097, 20000):
+        codes = rng.integers(0, 4, n, dtype=np.uint8)
+        codes[rng.random(n) < 0.01] = 4
+        got = np.sort(nat.dbg_extract(k, codes))
+        assert [int(x) for x in got] == kmers_from_codes(codes, k), (k, n)
+
+
+# ----------------------------------------------------------------------------- kmerize end to end
+KMERIZE = [(5, "kat6.k5", ["kat6.fa"]), (5, "g1.k5", ["g1.fa"]), (16, "g1.k16", ["g1.fa"]), (25, "g1.k25", ["g1.fa"]),
+           (30, "g1.k30", ["g1.fa"]), (31, "g1.k31", ["g1.fa"]), (32, "g1.k32", ["g1.fa"]),
+           (8, "r1.k8", ["r1.fq"]), (25, "r1.k25", ["r1.fq"]), (31, "r1.k31", ["r1.fq"]),
+           (21, "r2.k21", ["r2.fq"]), (25, "mix.k25", ["s0.fa", "r1.fq", "s1.fa"])]
+
+
+def run_kmerize(nat, k, inputs):
+    km = nat.Kmerizer(k)
+    for data, is_fa in inputs:
+        km.feed(data, is_fa)
+    s, nr = km.finish()
+    km.close()
+    return s, nr
+
+
+@pytest.mark.parametrize("k,out,ins", KMERIZE)
+def test_kmerize_golden(nat, k, out, ins):
+    z = zo.CasketReader(g(out))
+    xs, cs = zo.read_kmers_and_counts(z)
+    s, nr = run_kmerize(nat, k, [(rd(i), zo.is_fasta(i)) for i in ins])
+    ks, cc = s.fetch()
+    assert nr == z.meta["reads"]
+    assert [int(x) for x in ks] == xs
+    assert [int(c) for c in cc] == cs
+    st = s.stats()
+    assert [(str(v), f) for v, f in st["hist"]] == list(z.meta["hist"].items())
+    n = float(sum(st["acgt_weighted"]))
+    assert [a / n for a in st["acgt_weighted"]] == z.meta["acgt"]
+    kw, cw = s.encode()
+    assert kw.tobytes() == z.blob("kmers") and cw.tobytes() == z.blob("counts")
+
+
+@pytest.mark.parametrize("k", [25, 31, 12])
+def test_kmerize_fastq_vs_c_oracle(nat, k):
+    rng = np.random.default_rng(100 + k)
+    genome = rnd_dna(rng, 200000)
+    fq = make_fastq(rng, genome, 20000, 150)
+    s, nr = run_kmerize(nat, k, [(fq, False)])
+    ks, cc = s.fetch()
+    ek, ec, eacgt, enr = co.kmerize(k, [(fq, False)])
+    assert nr == enr
+    assert np.array_equal(ks, ek) and np.array_equal(cc, ec)
+    st = s.stats()
+    assert st["acgt_weighted"] == eacgt
+    assert st["hist"] == co.hist(ec.astype(np.uint64))
+
+
+@pytest.mark.parametrize("k", [25, 32, 6])
+def test_kmerize_fasta_vs_c_oracle(nat, k):
+    rng = np.random.default_rng(200 + k)
+    fa = make_fasta(rng, 1500000)
+    s, nr = run_kmerize(nat, k, [(fa, True)])
+    ks, cc = s.fetch()
+    ek, ec, eacgt, enr = co.kmerize(k, [(fa, True)])
+    assert nr == enr
+    assert np.array_equal(ks, ek) and np.array_equal(cc, ec)
+    assert s.stats()["acgt_weighted"] == eacgt
+
+
+def test_kmerize_batched_flush(nat, monkeypatch):
+    """small ZB_MAX_PENDING forces several sort+count+merge rounds; the result must not change"""
+    rng = np.random.default_rng(7)
+    genome = rnd_dna(rng, 50000)
+    fq = make_fastq(rng, genome, 8000, 100)
+    monkeypatch.setenv("ZB_MAX_PENDING", "65536")
+    s, nr = run_kmerize(nat, 21, [(fq, False), (fq[:len(fq) // 2 - (len(fq) // 2) % 1], False)])
+    monkeypatch.delenv("ZB_MAX_PENDING")
+    ks, cc = s.fetch()
+    ek, ec, _, enr = co.kmerize(21, [(fq, False), (fq[:len(fq) // 2], False)])
+    assert nr == enr
+    assert np.array_equal(ks, ek) and np.array_equal(cc, ec)
+
+
+def test_kmerize_palindromes_even_k(nat):
+    pal = b"ACGTTGCAAGCTTGCAACGT"
+    fa = b">p\n" + pal * 50 + b"\n>q\n" + b"AT" * 100 + b"\n"
+    for k in (2, 4, 8, 20):
+        s, _ = run_kmerize(nat, k, [(fa, True)])
+        ks, cc = s.fetch()
+        ek, ec, _, _ = co.kmerize(k, [(fa, True)])
+        assert np.array_equal(ks, ek) and np.array_equal(cc, ec), k
+
+
+def test_kmerize_empty(nat):
+    s, nr = run_kmerize(nat, 25, [(b">nothing\nACGT\n", True)])
+    assert len(s) == 0 and nr == 1
+    assert s.stats()["total"] == 0
+
+
+# ----------------------------------------------------------------------------- set algebra
+def random_set(rng, n, bits=50, maxc=5):
+    k = np.unique(rng.integers(0, 2 ** bits, n, dtype=np.uint64))
+    c = rng.integers(1, maxc + 1, len(k), dtype=np.uint32)
+    return k, c
+
+
+@pytest.mark.parametrize("sizes", [[0, 0], [1, 0], [10, 10, 10], [5000, 3, 70000], [100000] * 5, [4096, 4096], [30000] * 9])
+def test_merge(nat, sizes):
+    rng = np.random.default_rng(sum(sizes) + len(sizes))
+    sets = [random_set(rng, n, bits=18) for n in sizes]  # 18 bits: plenty of shared k-mers
+    hs = [nat.KmerSet.from_arrays(k, c) for k, c in sets]
+    m = nat.merge(hs)
+    mk, mc = m.fetch()
+    ek, ec = co.merge([(k, c.astype(np.uint64)) for k, c in sets])
+    assert np.array_equal(mk, ek) and np.array_equal(mc.astype(np.uint64), ec)
+    st = m.stats()
+    assert st["hist"] == co.hist(ec)
+    assert st["acgt_weighted"] == [int(ec[(ek & np.uint64(3)) == np.uint64(b)].sum()) for b in range(4)]
+    assert st["acgt_plain"] == [int(((ek & np.uint64(3)) == np.uint64(b)).sum()) for b in range(4)]
+
+
+def test_stats_large_counts(nat):
+    rng = np.random.default_rng(5)
+    k, _ = random_set(rng, 50000)
+    c = rng.integers(1, 100000, len(k), dtype=np.uint32)
+    c[100] = 4000000000
+    s = nat.KmerSet.from_arrays(k, c)
+    assert s.stats()["hist"] == co.hist(c.astype(np.uint64))
+
+
+@pytest.mark.parametrize("cmin,cmax", [(1, 0), (2, 0), (2, 3), (6, 0), (3, 3)])
+def test_trim(nat, cmin, cmax):
+    rng = np.random.default_rng(cmin * 10 + cmax)
+    for n in (0, 1, 4095, 4097, 200000):
+        k, c = random_set(rng, n)
+        s = nat.KmerSet.from_arrays(k, c)
+        t = s.trim(cmin, cmax)
+        tk, tc = t.fetch()
+        ek, ec = co.trim(k, c.astype(np.uint64), cmin, cmax)
+        assert np.array_equal(tk, ek) and np.array_equal(tc.astype(np.uint64), ec)
+
+
+@pytest.mark.parametrize("shift", [0, 2, 26, 40])
+def test_project(nat, shift):
+    rng = np.random.default_rng(shift)
+    for n in (0, 1, 5000, 300000):
+        k, c = random_set(rng, n)
+        p = nat.KmerSet.from_arrays(k, c).project(shift)
+        assert np.array_equal(p.fetch(counts=False), co.project(k, shift))
+
+
+def test_pairs_abc(nat):
+    rng = np.random.default_rng(9)
+    base, _ = random_set(rng, 60000, bits=20)
+    sets = []
+    for i, n in enumerate([0, 1, 50, 4096, 8191, 30000, 60000]):
+        pick = np.sort(rng.choice(len(base), min(n, len(base)), replace=False))
+        sets.append(base[pick])
+    sets.append(np.array([2 ** 64 - 1], np.uint64))
+    sets.append(np.array([5, 2 ** 64 - 1], np.uint64))
+    hs = [nat.KmerSet.from_arrays(k) for k in sets]
+    I, J = np.triu_indices(len(sets), 1)
+    abc = nat.pairs_abc(hs, I, J)
+    for p in range(len(I)):
+        assert tuple(int(v) for v in abc[p]) == co.split(sets[I[p]], sets[J[p]]), (I[p], J[p])
+
+
+def test_codec_streams(nat):
+    rng = np.random.default_rng(12)
+    for n in (0, 1, 6, 7, 1000, 100000):
+        v = (rng.integers(0, 2 ** 62, n, dtype=np.uint64) >> rng.integers(2, 62, n).astype(np.uint64))
+        w = nat.encode_stream(v, False)
+        assert np.array_equal(w, co.encode(v, False))
+        assert np.array_equal(nat.decode_stream(w, False), v)
+        s = np.sort(v)
+        w = nat.encode_stream(s, True)
+        assert np.array_equal(w, co.encode(s, True))
+        assert np.array_equal(nat.decode_stream(w, True), s)
+    with pytest.raises(IndexError):
+        nat.encode_stream(np.array([2 ** 61], np.uint64))

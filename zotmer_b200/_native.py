@@ -1,0 +1,315 @@
+"""
+ctypes binding of libzot_b200.so (include/zotmer_b200.h) -- the only door between the Python host
+layer (zotmer_b200/commands, zotmer_b200/library) and the sm_100a kernels.
+
+There is NO CPU fallback: if the shared library is missing, or no CUDA device is present when a
+compute entry point is called, the call raises.  The library is built in-tree by
+`python -c "import __graft_entry__ as g; g.build()"` (or `make -C zotmer_b200/csrc`).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzot_b200.so")
+
+ZB_OK = 0
+ZB_E_CUDA, ZB_E_ARG, ZB_E_RANGE, ZB_E_FORMAT, ZB_E_NOMEM, ZB_E_NOGPU = -1, -2, -3, -4, -5, -6
+
+u64p = C.POINTER(C.c_uint64)
+u32p = C.POINTER(C.c_uint32)
+vp = C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol declared in include/zotmer_b200.h
+SIGNATURES = {
+    "zb_last_error": (C.c_char_p, []),
+    "zb_version": (C.c_int, []),
+    "zb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "zb_launch_count": (C.c_int, [C.c_int, u64p]),
+    "zb_device_sync": (C.c_int, [C.c_int]),
+    "zb_kmerize_open": (C.c_int, [C.c_int, C.c_int, C.POINTER(vp)]),
+    "zb_kmerize_feed": (C.c_int, [vp, vp, C.c_size_t, C.c_int]),
+    "zb_kmerize_feed_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_int]),
+    "zb_kmerize_feed_codes_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_uint64]),
+    "zb_kmerize_finish": (C.c_int, [vp, C.POINTER(vp), u64p]),
+    "zb_kmerize_close": (C.c_int, [vp]),
+    "zb_kmerize_pending": (C.c_int, [vp, u64p]),
+    "zb_kmerize_take_bucketed_dev": (C.c_int, [vp, C.c_int, vp, u64p]),
+    "zb_kmerize_add_canonical_dev": (C.c_int, [vp, vp, C.c_size_t]),
+    "zb_set_from_host": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.POINTER(vp)]),
+    "zb_set_size": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
+    "zb_set_fetch": (C.c_int, [vp, vp, vp]),
+    "zb_set_dev_ptrs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
+    "zb_set_free": (C.c_int, [vp]),
+    "zb_set_stats": (C.c_int, [vp, u64p, u64p, u64p, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "zb_merge": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp)]),
+    "zb_trim": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
+    "zb_project": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "zb_pairs_abc": (C.c_int, [C.c_int, C.POINTER(vp), vp, vp, C.c_size_t, vp]),
+    "zb_encode_u64_stream": (C.c_int, [C.c_int, vp, C.c_size_t, C.c_int, vp, C.POINTER(C.c_size_t)]),
+    "zb_decode_u64_stream": (C.c_int, [C.c_int, vp, C.c_size_t, C.c_int, vp, C.POINTER(C.c_size_t)]),
+    "zb_set_encode": (C.c_int, [vp, vp, C.POINTER(C.c_size_t), vp, C.POINTER(C.c_size_t)]),
+    "zb_set_encode_sizes": (C.c_int, [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "zb_set_from_streams": (C.c_int, [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(vp)]),
+    "zb_dbg_sort_u64": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "zb_dbg_parse": (C.c_int, [C.c_int, vp, C.c_size_t, C.c_int, vp, C.POINTER(C.c_size_t), u64p]),
+    "zb_dbg_extract": (C.c_int, [C.c_int, C.c_int, vp, C.c_size_t, vp, C.POINTER(C.c_size_t)]),
+}
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "libzot_b200: %s (code %d)" % (msg, code))
+        self.code = code
+
+
+def lib():
+    """Load libzot_b200.so; fails loudly when it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s not found: build it with `make -C zotmer_b200/csrc` "
+                              "(zotmer_b200 has no CPU path)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for nm, (res, args) in SIGNATURES.items():
+            fn = getattr(L, nm)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != ZB_OK:
+        msg = lib().zb_last_error().decode("utf-8", "replace")
+        if rc == ZB_E_RANGE:
+            # the reference raises IndexError (codec64.py:93-99) / OverflowError here
+            raise IndexError(msg)
+        if rc == ZB_E_FORMAT:
+            raise AssertionError(msg)  # files.py:58,182 asserts
+        raise NativeError(rc, msg)
+
+
+def device_count():
+    n = C.c_int(0)
+    _check(lib().zb_device_count(C.byref(n)))
+    return n.value
+
+
+def launch_count(device=0):
+    n = C.c_uint64(0)
+    _check(lib().zb_launch_count(device, C.byref(n)))
+    return n.value
+
+
+def _ptr(a):
+    return a.ctypes.data_as(vp) if a is not None and len(a) else None
+
+
+class KmerSet(object):
+    """Device-resident counted k-mer set (sorted u64 k-mers + u32 counts)."""
+
+    def __init__(self, handle, device):
+        self.h = vp(handle) if not isinstance(handle, vp) else handle
+        self.device = device
+
+    @staticmethod
+    def from_arrays(kmers, counts=None, device=0):
+        k = np.ascontiguousarray(kmers, dtype=np.uint64)
+        c = None if counts is None else np.ascontiguousarray(counts, dtype=np.uint32)
+        if c is not None and len(c) != len(k):
+            raise AssertionError("k-mer and count arrays differ in length")  # files.py:182
+        h = vp()
+        _check(lib().zb_set_from_host(device, _ptr(k), _ptr(c) if c is not None else None, len(k), C.byref(h)))
+        return KmerSet(h, device)
+
+    @staticmethod
+    def from_streams(kmer_words, count_words=None, device=0):
+        kw = np.ascontiguousarray(kmer_words, dtype=np.uint64)
+        cw = None if count_words is None else np.ascontiguousarray(count_words, dtype=np.uint64)
+        h = vp()
+        _check(lib().zb_set_from_streams(device, _ptr(kw), len(kw), _ptr(cw) if cw is not None else None,
+                                         0 if cw is None else len(cw), C.byref(h)))
+        return KmerSet(h, device)
+
+    def __len__(self):
+        n = C.c_size_t(0)
+        _check(lib().zb_set_size(self.h, C.byref(n)))
+        return n.value
+
+    def fetch(self, counts=True):
+        n = len(self)
+        k = np.empty(n, np.uint64)
+        c = np.empty(n, np.uint32) if counts else None
+        _check(lib().zb_set_fetch(self.h, _ptr(k), _ptr(c) if counts else None))
+        return (k, c) if counts else k
+
+    def dev_ptrs(self):
+        a, b = vp(), vp()
+        _check(lib().zb_set_dev_ptrs(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def stats(self):
+        """-> dict(acgt_weighted, acgt_plain, total, hist=[(count, n_kmers)] in first-occurrence order)"""
+        aw = (C.c_uint64 * 4)()
+        ap = (C.c_uint64 * 4)()
+        tot = C.c_uint64(0)
+        nh = C.c_size_t(0)
+        cap = 4096
+        while True:
+            hv = np.empty(cap, np.uint64)
+            hf = np.empty(cap, np.uint64)
+            _check(lib().zb_set_stats(self.h, aw, ap, C.byref(tot), _ptr(hv), _ptr(hf), cap, C.byref(nh)))
+            if nh.value <= cap:
+                break
+            cap = nh.value
+        return {"acgt_weighted": [int(x) for x in aw], "acgt_plain": [int(x) for x in ap], "total": int(tot.value),
+                "hist": [(int(hv[i]), int(hf[i])) for i in range(nh.value)]}
+
+    def trim(self, cmin, cmax=0):
+        h = vp()
+        _check(lib().zb_trim(self.h, int(cmin), int(cmax), C.byref(h)))
+        return KmerSet(h, self.device)
+
+    def project(self, shift_bits):
+        h = vp()
+        _check(lib().zb_project(self.h, int(shift_bits), C.byref(h)))
+        return KmerSet(h, self.device)
+
+    def encode(self):
+        """-> (kmer stream words, count stream words) exactly as the reference writes them."""
+        nk, nc = C.c_size_t(0), C.c_size_t(0)
+        _check(lib().zb_set_encode_sizes(self.h, C.byref(nk), C.byref(nc)))
+        kw = np.empty(max(nk.value, 1), np.uint64)
+        cw = np.empty(max(nc.value, 1), np.uint64)
+        _check(lib().zb_set_encode(self.h, _ptr(kw), C.byref(nk), _ptr(cw), C.byref(nc)))
+        return kw[:nk.value], cw[:nc.value]
+
+    def free(self):
+        if self.h is not None and self.h.value:
+            lib().zb_set_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def merge(sets):
+    arr = (vp * len(sets))(*[s.h for s in sets])
+    h = vp()
+    _check(lib().zb_merge(len(sets), arr, C.byref(h)))
+    return KmerSet(h, sets[0].device)
+
+
+def pairs_abc(sets, I, J):
+    """(|X n Y|, |X \\ Y|, |Y \\ X|) for each pair (I[p], J[p]) -> uint64 array [npairs, 3]"""
+    I = np.ascontiguousarray(I, dtype=np.uint32)
+    J = np.ascontiguousarray(J, dtype=np.uint32)
+    assert len(I) == len(J)
+    arr = (vp * len(sets))(*[s.h for s in sets])
+    out = np.zeros((len(I), 3), np.uint64)
+    _check(lib().zb_pairs_abc(len(sets), arr, _ptr(I), _ptr(J), len(I), _ptr(out.reshape(-1)) if len(I) else None))
+    return out
+
+
+class Kmerizer(object):
+    """Streaming kmerize+count (zb_kmerize_*)."""
+
+    def __init__(self, k, device=0):
+        self.h = vp()
+        self.device = device
+        self.k = k
+        _check(lib().zb_kmerize_open(int(k), device, C.byref(self.h)))
+
+    def feed(self, data, is_fasta):
+        """data: bytes / bytearray / memoryview / uint8 ndarray holding a whole file or a record-aligned piece."""
+        a = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+        if len(a):
+            _check(lib().zb_kmerize_feed(self.h, _ptr(a), len(a), 1 if is_fasta else 0))
+
+    def feed_dev(self, dptr, n, is_fasta):
+        _check(lib().zb_kmerize_feed_dev(self.h, vp(dptr), n, 1 if is_fasta else 0))
+
+    def feed_codes_dev(self, dptr, n, n_records):
+        _check(lib().zb_kmerize_feed_codes_dev(self.h, vp(dptr), n, n_records))
+
+    def pending(self):
+        n = C.c_uint64(0)
+        _check(lib().zb_kmerize_pending(self.h, C.byref(n)))
+        return n.value
+
+    def take_bucketed_dev(self, nranks, dptr):
+        cnt = (C.c_uint64 * nranks)()
+        _check(lib().zb_kmerize_take_bucketed_dev(self.h, nranks, vp(dptr), cnt))
+        return [int(x) for x in cnt]
+
+    def add_canonical_dev(self, dptr, n):
+        _check(lib().zb_kmerize_add_canonical_dev(self.h, vp(dptr), n))
+
+    def finish(self):
+        """-> (KmerSet with both strands, number of records)"""
+        s = vp()
+        nr = C.c_uint64(0)
+        _check(lib().zb_kmerize_finish(self.h, C.byref(s), C.byref(nr)))
+        return KmerSet(s, self.device), nr.value
+
+    def close(self):
+        if self.h is not None and self.h.value:
+            lib().zb_kmerize_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def encode_stream(vals, delta=False, device=0):
+    v = np.ascontiguousarray(vals, dtype=np.uint64)
+    w = np.empty(max(len(v), 1), np.uint64)
+    nw = C.c_size_t(0)
+    _check(lib().zb_encode_u64_stream(device, _ptr(v), len(v), 1 if delta else 0, _ptr(w), C.byref(nw)))
+    return w[:nw.value]
+
+
+def decode_stream(words, delta=False, device=0):
+    w = np.ascontiguousarray(words, dtype=np.uint64)
+    n = C.c_size_t(0)
+    _check(lib().zb_decode_u64_stream(device, _ptr(w), len(w), 1 if delta else 0, None, C.byref(n)))
+    out = np.empty(max(n.value, 1), np.uint64)
+    _check(lib().zb_decode_u64_stream(device, _ptr(w), len(w), 1 if delta else 0, _ptr(out), C.byref(n)))
+    return out[:n.value]
+
+
+# ---- diagnostics (tests / bench) -------------------------------------------------------------
+def dbg_sort(keys, vals=None, key_bits=64, max_bits=8, iters=1, device=0):
+    k = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+    v = None if vals is None else np.ascontiguousarray(vals, dtype=np.uint32).copy()
+    ms = C.c_float(0)
+    _check(lib().zb_dbg_sort_u64(device, _ptr(k), _ptr(v) if v is not None else None, len(k), key_bits, max_bits,
+                                 iters, C.byref(ms)))
+    return k, v, ms.value
+
+
+def dbg_parse(data, is_fasta, device=0):
+    a = np.frombuffer(bytes(data), dtype=np.uint8)
+    codes = np.empty(len(a) + 64, np.uint8)
+    n = C.c_size_t(0)
+    nr = C.c_uint64(0)
+    _check(lib().zb_dbg_parse(device, _ptr(a), len(a), 1 if is_fasta else 0, _ptr(codes), C.byref(n), C.byref(nr)))
+    return codes[:n.value].copy(), nr.value
+
+
+def dbg_extract(k, codes, device=0):
+    c = np.ascontiguousarray(codes, dtype=np.uint8)
+    keys = np.empty(max(len(c), 1), np.uint64)
+    n = C.c_size_t(0)
+    _check(lib().zb_dbg_extract(device, k, _ptr(c), len(c), _ptr(keys), C.byref(n)))
+    return keys[:n.value].copy()

@@ -1,0 +1,622 @@
+// api.cu -- the C ABI (include/zotmer_b200.h): handles, memory, orchestration of the kernels.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "kernels.h"
+
+namespace zb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+static std::mutex g_ctx_mu;
+static std::map<int, Ctx*> g_ctx;  // one context per device (calls on a device are serialised by the caller)
+
+Ctx* ctx_for(int device) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device available (%s): libzot_b200 has no CPU path", cudaGetErrorString(e));
+        throw Fail{ZB_E_NOGPU};
+    }
+    if (device < 0 || device >= ndev) ZB_FAIL(ZB_E_ARG, "device %d out of range (have %d)", device, ndev);
+    ZB_CUDA(cudaSetDevice(device));
+    auto it = g_ctx.find(device);
+    if (it != g_ctx.end()) return it->second;
+    Ctx* c = new Ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    ZB_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    ZB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    ZB_CUDA(cudaDeviceGetDefaultMemPool(&c->pool, device));
+    uint64_t keep = ~0ull;  // never give pages back: batches reuse them
+    ZB_CUDA(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    ZB_CUDA(cudaMallocHost((void**)&c->h_scalars, 64 * sizeof(uint64_t)));
+    g_ctx[device] = c;
+    return c;
+}
+
+}  // namespace zb
+
+using namespace zb;
+
+struct zb_set {
+    Ctx* c;
+    DBuf<uint64_t> k;
+    DBuf<uint32_t> cnt;
+    size_t n;
+};
+
+struct zb_kmerizer {
+    Ctx* c;
+    int k;
+    DBuf<uint64_t> pending;              // canonical keys not yet counted
+    size_t pending_cap = 0;
+    size_t pending_upper = 0;            // host-side upper bound of the device counter
+    DBuf<unsigned long long> d_count;    // [0] number of pending keys
+    DBuf<uint64_t> acc_k;                // counted canonical run accumulated so far
+    DBuf<uint32_t> acc_c;
+    size_t acc_n = 0;
+    uint64_t n_records = 0;
+    size_t max_pending = (size_t)1 << 29;
+};
+
+#define ZB_TRY try {
+#define ZB_CATCH                                   \
+    }                                              \
+    catch (const zb::Fail& f) { return f.code; }   \
+    catch (const std::bad_alloc&) {                \
+        zb::set_error("out of host memory");       \
+        return ZB_E_NOMEM;                         \
+    }                                              \
+    return ZB_OK;
+
+static size_t read_pending_count(zb_kmerizer* h) {
+    Ctx* c = h->c;
+    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, h->d_count.get(), 8, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    return (size_t)c->h_scalars[0];
+}
+
+static void ensure_pending(zb_kmerizer* h, size_t need_total) {
+    if (need_total <= h->pending_cap) return;
+    Ctx* c = h->c;
+    size_t ncap = std::max(need_total, h->pending_cap * 2);
+    DBuf<uint64_t> nb(c, ncap);
+    if (h->pending_upper) {
+        size_t have = read_pending_count(h);
+        ZB_CUDA(cudaMemcpyAsync(nb.get(), h->pending.get(), have * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    h->pending = std::move(nb);
+    h->pending_cap = ncap;
+}
+
+// count the pending canonical keys and fold them into the accumulated run
+static void flush_pending(zb_kmerizer* h) {
+    Ctx* c = h->c;
+    if (h->pending_upper == 0) return;
+    const size_t n = read_pending_count(h);
+    h->pending_upper = 0;
+    ZB_CUDA(cudaMemsetAsync(h->d_count.get(), 0, 8, c->stream));
+    if (n == 0) return;
+    DBuf<uint64_t> tmp(c, n);
+    const int which = radix_sort(c, h->pending.get(), tmp.get(), nullptr, nullptr, n, 2 * h->k);
+    const uint64_t* sorted = which ? tmp.get() : h->pending.get();
+    uint64_t* other = which ? h->pending.get() : tmp.get();
+    DBuf<uint32_t> dc(c, n);
+    const size_t nd = reduce_by_key(c, sorted, nullptr, n, other, dc.get());  // distinct keys -> `other`
+    if (h->acc_n == 0) {
+        h->acc_k.alloc(c, nd);
+        h->acc_c.alloc(c, nd);
+        ZB_CUDA(cudaMemcpyAsync(h->acc_k.get(), other, nd * 8, cudaMemcpyDeviceToDevice, c->stream));
+        ZB_CUDA(cudaMemcpyAsync(h->acc_c.get(), dc.get(), nd * 4, cudaMemcpyDeviceToDevice, c->stream));
+        h->acc_n = nd;
+    } else {
+        const size_t tot = h->acc_n + nd;
+        DBuf<uint64_t> mk(c, tot);
+        DBuf<uint32_t> mc(c, tot);
+        merge_pairs(c, h->acc_k.get(), h->acc_c.get(), h->acc_n, other, dc.get(), nd, mk.get(), mc.get());
+        DBuf<uint64_t> rk(c, tot);
+        DBuf<uint32_t> rc(c, tot);
+        const size_t nn = reduce_by_key(c, mk.get(), mc.get(), tot, rk.get(), rc.get());
+        h->acc_k = std::move(rk);
+        h->acc_c = std::move(rc);
+        h->acc_n = nn;
+    }
+}
+
+// extraction of a parsed code stream (device buffer with 32-byte front pad and tile tail pad)
+static void extract_codes(zb_kmerizer* h, const uint8_t* codes, size_t n_codes) {
+    Ctx* c = h->c;
+    size_t off = 0;
+    while (off < n_codes) {
+        if (h->pending_upper >= h->max_pending) flush_pending(h);
+        size_t room = h->max_pending - h->pending_upper;
+        size_t len = std::min(n_codes - off, std::max<size_t>(room, EXTRACT_TILE));
+        if (len < n_codes - off) len = (len / EXTRACT_TILE) * EXTRACT_TILE;  // slices end on tile boundaries
+        // a slice may overshoot into the next tile: bound by whole tiles
+        const size_t upper = div_up(len, EXTRACT_TILE) * EXTRACT_TILE;
+        ensure_pending(h, h->pending_upper + upper);
+        extract_canonical(c, h->k, codes + off, len, h->pending.get(), h->d_count.get());
+        h->pending_upper += upper;
+        off += len;
+    }
+}
+
+static void feed_dev_impl(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is_fasta) {
+    Ctx* c = h->c;
+    if (n == 0) return;
+    if (n >= ((size_t)1 << 31)) ZB_FAIL(ZB_E_ARG, "feed: piece of %zu bytes; split the input at record boundaries below 2 GiB", n);
+    if (((uintptr_t)d_raw & 15) != 0) ZB_FAIL(ZB_E_ARG, "feed_dev: device pointer must be 16-byte aligned");
+    const size_t cap = 32 + n + 2 * EXTRACT_TILE + 64;
+    DBuf<uint8_t> codes(c, cap);
+    uint8_t* cd = codes.get() + 32;
+    ZB_CUDA(cudaMemsetAsync(codes.get(), 4, 32, c->stream));
+    size_t n_codes = 0;
+    uint64_t n_rec = 0;
+    if (is_fasta) parse_fasta(c, d_raw, n, cd, &n_codes, &n_rec);
+    else parse_fastq(c, d_raw, n, cd, &n_codes, &n_rec);
+    h->n_records += n_rec;
+    if (n_codes == 0) return;
+    const size_t padded = div_up(n_codes, EXTRACT_TILE) * EXTRACT_TILE + 32;
+    ZB_CUDA(cudaMemsetAsync(cd + n_codes, 4, padded - n_codes, c->stream));
+    extract_codes(h, cd, n_codes);
+}
+
+static zb_set* new_set(Ctx* c, size_t n) {
+    zb_set* s = new zb_set();
+    s->c = c;
+    s->n = n;
+    s->k.alloc(c, n);
+    s->cnt.alloc(c, n);
+    return s;
+}
+
+extern "C" {
+
+const char* zb_last_error(void) { return zb::g_err; }
+int zb_version(void) { return 100; }
+
+int zb_device_count(int* n) {
+    int nd = 0;
+    cudaError_t e = cudaGetDeviceCount(&nd);
+    if (e != cudaSuccess) nd = 0;
+    if (n) *n = nd;
+    return ZB_OK;
+}
+
+int zb_launch_count(int device, uint64_t* n) {
+    ZB_TRY
+    *n = ctx_for(device)->launches;
+    ZB_CATCH
+}
+
+int zb_device_sync(int device) {
+    ZB_TRY
+    Ctx* c = ctx_for(device);
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    ZB_CATCH
+}
+
+// ------------------------------------------------------------------------------- kmerize
+int zb_kmerize_open(int k, int device, zb_kmerizer** out) {
+    ZB_TRY
+    if (!out) ZB_FAIL(ZB_E_ARG, "null out");
+    if (k < 1 || k > 32) ZB_FAIL(ZB_E_ARG, "k=%d outside 1..32 (k-mers are packed into 64 bits)", k);
+    Ctx* c = ctx_for(device);
+    zb_kmerizer* h = new zb_kmerizer();
+    h->c = c;
+    h->k = k;
+    h->d_count.alloc(c, 2);
+    ZB_CUDA(cudaMemsetAsync(h->d_count.get(), 0, 16, c->stream));
+    if (const char* e = getenv("ZB_MAX_PENDING")) {
+        size_t v = strtoull(e, nullptr, 10);
+        if (v >= (size_t)EXTRACT_TILE && v < ((size_t)1 << 30)) h->max_pending = v;
+    }
+    *out = h;
+    ZB_CATCH
+}
+
+int zb_kmerize_feed_dev(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is_fasta) {
+    ZB_TRY
+    if (!h) ZB_FAIL(ZB_E_ARG, "null handle");
+    ZB_CUDA(cudaSetDevice(h->c->device));
+    feed_dev_impl(h, d_raw, n, is_fasta);
+    ZB_CATCH
+}
+
+int zb_kmerize_feed(zb_kmerizer* h, const uint8_t* raw, size_t n, int is_fasta) {
+    ZB_TRY
+    if (!h) ZB_FAIL(ZB_E_ARG, "null handle");
+    if (n == 0) return ZB_OK;
+    if (!raw) ZB_FAIL(ZB_E_ARG, "null input");
+    Ctx* c = h->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    DBuf<uint8_t> d(c, n + 16);
+    ZB_CUDA(cudaMemcpyAsync(d.get(), raw, n, cudaMemcpyHostToDevice, c->stream));
+    feed_dev_impl(h, d.get(), n, is_fasta);
+    ZB_CATCH
+}
+
+int zb_kmerize_feed_codes_dev(zb_kmerizer* h, const uint8_t* d_codes, size_t n, uint64_t n_records) {
+    ZB_TRY
+    if (!h) ZB_FAIL(ZB_E_ARG, "null handle");
+    Ctx* c = h->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    if (n == 0) { h->n_records += n_records; return ZB_OK; }
+    const size_t padded = div_up(n, EXTRACT_TILE) * EXTRACT_TILE + 32;
+    DBuf<uint8_t> codes(c, 32 + padded);
+    ZB_CUDA(cudaMemsetAsync(codes.get(), 4, 32, c->stream));
+    ZB_CUDA(cudaMemcpyAsync(codes.get() + 32, d_codes, n, cudaMemcpyDeviceToDevice, c->stream));
+    ZB_CUDA(cudaMemsetAsync(codes.get() + 32 + n, 4, padded - n, c->stream));
+    extract_codes(h, codes.get() + 32, n);
+    h->n_records += n_records;
+    ZB_CATCH
+}
+
+int zb_kmerize_finish(zb_kmerizer* h, zb_set** result, uint64_t* n_records) {
+    ZB_TRY
+    if (!h || !result) ZB_FAIL(ZB_E_ARG, "null argument");
+    Ctx* c = h->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    flush_pending(h);
+    h->pending.release();
+    h->pending_cap = 0;
+    const size_t n = h->acc_n;
+    // both strands: mirror the canonical run, sort the mirrored half, merge
+    DBuf<uint64_t> rk(c, n), rk2(c, n);
+    DBuf<uint32_t> rc(c, n), rc2(c, n);
+    const size_t nm = mirror_keys(c, h->k, h->acc_k.get(), h->acc_c.get(), n, rk.get(), rc.get());
+    const int which = radix_sort(c, rk.get(), rk2.get(), rc.get(), rc2.get(), nm, 2 * h->k);
+    zb_set* s = new_set(c, n + nm);
+    merge_pairs(c, h->acc_k.get(), h->acc_c.get(), n, which ? rk2.get() : rk.get(), which ? rc2.get() : rc.get(), nm,
+                s->k.get(), s->cnt.get());
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    h->acc_k.release();
+    h->acc_c.release();
+    h->acc_n = 0;
+    if (n_records) *n_records = h->n_records;
+    *result = s;
+    ZB_CATCH
+}
+
+int zb_kmerize_close(zb_kmerizer* h) {
+    ZB_TRY
+    if (h) {
+        cudaSetDevice(h->c->device);
+        delete h;
+    }
+    ZB_CATCH
+}
+
+int zb_kmerize_pending(zb_kmerizer* h, uint64_t* n_keys) {
+    ZB_TRY
+    if (!h || !n_keys) ZB_FAIL(ZB_E_ARG, "null argument");
+    ZB_CUDA(cudaSetDevice(h->c->device));
+    *n_keys = h->pending_upper ? read_pending_count(h) : 0;
+    ZB_CATCH
+}
+
+int zb_kmerize_take_bucketed_dev(zb_kmerizer* h, int nranks, uint64_t* d_keys, uint64_t* bucket_counts) {
+    ZB_TRY
+    if (!h || !bucket_counts || nranks < 1 || nranks > 64) ZB_FAIL(ZB_E_ARG, "bad argument");
+    Ctx* c = h->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    const size_t n = h->pending_upper ? read_pending_count(h) : 0;
+    DBuf<unsigned long long> cnt(c, 128);
+    ZB_CUDA(cudaMemsetAsync(cnt.get(), 0, 128 * 8, c->stream));
+    bucket_count(c, h->pending.get(), n, nranks, cnt.get());
+    std::vector<unsigned long long> hc(64, 0), start(64, 0);
+    ZB_CUDA(cudaMemcpyAsync(hc.data(), cnt.get(), 64 * 8, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    unsigned long long s = 0;
+    for (int r = 0; r < nranks; r++) { start[r] = s; s += hc[r]; bucket_counts[r] = hc[r]; }
+    ZB_CUDA(cudaMemcpyAsync(cnt.get() + 64, start.data(), 64 * 8, cudaMemcpyHostToDevice, c->stream));
+    if (n && !d_keys) ZB_FAIL(ZB_E_ARG, "null d_keys");
+    bucket_scatter(c, h->pending.get(), n, nranks, cnt.get() + 64, d_keys);
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    h->pending_upper = 0;
+    ZB_CUDA(cudaMemsetAsync(h->d_count.get(), 0, 8, c->stream));
+    ZB_CATCH
+}
+
+int zb_kmerize_add_canonical_dev(zb_kmerizer* h, const uint64_t* d_keys, size_t n) {
+    ZB_TRY
+    if (!h) ZB_FAIL(ZB_E_ARG, "null handle");
+    Ctx* c = h->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    size_t off = 0;
+    while (off < n) {
+        size_t have = h->pending_upper ? read_pending_count(h) : 0;
+        if (have >= h->max_pending) { flush_pending(h); have = 0; }
+        const size_t len = std::min(n - off, h->max_pending - have);
+        ensure_pending(h, have + len);
+        ZB_CUDA(cudaMemcpyAsync(h->pending.get() + have, d_keys + off, len * 8, cudaMemcpyDeviceToDevice, c->stream));
+        const unsigned long long nc = have + len;
+        c->h_scalars[8] = nc;
+        ZB_CUDA(cudaMemcpyAsync(h->d_count.get(), c->h_scalars + 8, 8, cudaMemcpyHostToDevice, c->stream));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+        h->pending_upper = (size_t)nc;
+        off += len;
+    }
+    ZB_CATCH
+}
+
+// ------------------------------------------------------------------------------- sets
+int zb_set_from_host(int device, const uint64_t* kmers, const uint32_t* counts, size_t n, zb_set** out) {
+    ZB_TRY
+    if (!out || (n && !kmers)) ZB_FAIL(ZB_E_ARG, "null argument");
+    Ctx* c = ctx_for(device);
+    zb_set* s = new_set(c, n);
+    if (n) {
+        ZB_CUDA(cudaMemcpyAsync(s->k.get(), kmers, n * 8, cudaMemcpyHostToDevice, c->stream));
+        if (counts) {
+            ZB_CUDA(cudaMemcpyAsync(s->cnt.get(), counts, n * 4, cudaMemcpyHostToDevice, c->stream));
+        } else {
+            std::vector<uint32_t> ones(std::min<size_t>(n, 1 << 20), 1u);
+            for (size_t o = 0; o < n; o += ones.size())
+                ZB_CUDA(cudaMemcpyAsync(s->cnt.get() + o, ones.data(), std::min(ones.size(), n - o) * 4,
+                                        cudaMemcpyHostToDevice, c->stream));
+        }
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    *out = s;
+    ZB_CATCH
+}
+
+int zb_set_size(const zb_set* s, size_t* n) {
+    if (!s || !n) { zb::set_error("null argument"); return ZB_E_ARG; }
+    *n = s->n;
+    return ZB_OK;
+}
+
+int zb_set_fetch(const zb_set* s, uint64_t* kmers, uint32_t* counts) {
+    ZB_TRY
+    if (!s) ZB_FAIL(ZB_E_ARG, "null set");
+    Ctx* c = s->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    if (s->n && kmers) ZB_CUDA(cudaMemcpyAsync(kmers, s->k.get(), s->n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (s->n && counts) ZB_CUDA(cudaMemcpyAsync(counts, s->cnt.get(), s->n * 4, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    ZB_CATCH
+}
+
+int zb_set_dev_ptrs(const zb_set* s, const uint64_t** d_kmers, const uint32_t** d_counts) {
+    if (!s) { zb::set_error("null set"); return ZB_E_ARG; }
+    if (d_kmers) *d_kmers = s->k.get();
+    if (d_counts) *d_counts = s->cnt.get();
+    return ZB_OK;
+}
+
+int zb_set_free(zb_set* s) {
+    ZB_TRY
+    if (s) {
+        cudaSetDevice(s->c->device);
+        delete s;
+    }
+    ZB_CATCH
+}
+
+int zb_set_stats(const zb_set* s, uint64_t acgt_weighted[4], uint64_t acgt_plain[4], uint64_t* total_count,
+                 uint64_t* hist_vals, uint64_t* hist_freqs, size_t hist_cap, size_t* n_hist) {
+    ZB_TRY
+    if (!s) ZB_FAIL(ZB_E_ARG, "null set");
+    Ctx* c = s->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    uint64_t aw[4], ap[4], tot;
+    std::vector<std::pair<uint64_t, uint64_t>> hist;
+    set_stats(c, s->k.get(), s->cnt.get(), s->n, aw, ap, &tot, &hist);
+    for (int q = 0; q < 4; q++) {
+        if (acgt_weighted) acgt_weighted[q] = aw[q];
+        if (acgt_plain) acgt_plain[q] = ap[q];
+    }
+    if (total_count) *total_count = tot;
+    if (n_hist) *n_hist = hist.size();
+    if (hist_cap) {  // fills min(hist_cap, *n_hist) entries; the caller retries when *n_hist > hist_cap
+        for (size_t i = 0; i < hist.size() && i < hist_cap; i++) {
+            if (hist_vals) hist_vals[i] = hist[i].first;
+            if (hist_freqs) hist_freqs[i] = hist[i].second;
+        }
+    }
+    ZB_CATCH
+}
+
+int zb_merge(int nsets, zb_set* const* sets, zb_set** out) {
+    ZB_TRY
+    if (nsets < 1 || !sets || !out) ZB_FAIL(ZB_E_ARG, "bad argument");
+    Ctx* c = sets[0]->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    for (int i = 0; i < nsets; i++)
+        if (!sets[i] || sets[i]->c != c) ZB_FAIL(ZB_E_ARG, "sets must live on one device");
+    // pairwise tree; every level is merge-path + reduce-by-key (counts summed)
+    struct Run { const uint64_t* k; const uint32_t* c; size_t n; DBuf<uint64_t> ok; DBuf<uint32_t> oc; };
+    std::vector<Run> cur(nsets);
+    for (int i = 0; i < nsets; i++) { cur[i].k = sets[i]->k.get(); cur[i].c = sets[i]->cnt.get(); cur[i].n = sets[i]->n; }
+    while (cur.size() > 1) {
+        std::vector<Run> nxt((cur.size() + 1) / 2);
+        for (size_t i = 0; i + 1 < cur.size(); i += 2) {
+            Run& a = cur[i];
+            Run& b = cur[i + 1];
+            const size_t tot = a.n + b.n;
+            DBuf<uint64_t> mk(c, tot);
+            DBuf<uint32_t> mc(c, tot);
+            merge_pairs(c, a.k, a.c, a.n, b.k, b.c, b.n, mk.get(), mc.get());
+            Run& r = nxt[i / 2];
+            r.ok.alloc(c, tot);
+            r.oc.alloc(c, tot);
+            r.n = reduce_by_key(c, mk.get(), mc.get(), tot, r.ok.get(), r.oc.get());
+            r.k = r.ok.get();
+            r.c = r.oc.get();
+            a.ok.release(); a.oc.release(); b.ok.release(); b.oc.release();
+        }
+        if (cur.size() & 1) nxt.back() = std::move(cur.back());
+        cur = std::move(nxt);
+    }
+    zb_set* s = new_set(c, cur[0].n);
+    if (cur[0].n) {
+        ZB_CUDA(cudaMemcpyAsync(s->k.get(), cur[0].k, cur[0].n * 8, cudaMemcpyDeviceToDevice, c->stream));
+        ZB_CUDA(cudaMemcpyAsync(s->cnt.get(), cur[0].c, cur[0].n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    *out = s;
+    ZB_CATCH
+}
+
+int zb_trim(const zb_set* s, uint64_t cmin, uint64_t cmax, zb_set** out) {
+    ZB_TRY
+    if (!s || !out) ZB_FAIL(ZB_E_ARG, "null argument");
+    Ctx* c = s->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    zb_set* r = new_set(c, s->n);
+    r->n = trim_pairs(c, s->k.get(), s->cnt.get(), s->n, cmin, cmax, r->k.get(), r->cnt.get());
+    *out = r;
+    ZB_CATCH
+}
+
+int zb_project(const zb_set* s, int shift_bits, zb_set** out) {
+    ZB_TRY
+    if (!s || !out || shift_bits < 0 || shift_bits > 63) ZB_FAIL(ZB_E_ARG, "bad argument");
+    Ctx* c = s->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    zb_set* r = new zb_set();
+    r->c = c;
+    r->k.alloc(c, s->n);
+    r->n = project_keys(c, s->k.get(), s->n, shift_bits, r->k.get());
+    *out = r;
+    ZB_CATCH
+}
+
+int zb_pairs_abc(int nsets, zb_set* const* sets, const uint32_t* I, const uint32_t* J, size_t npairs, uint64_t* abc) {
+    ZB_TRY
+    if (nsets < 1 || !sets || (npairs && (!I || !J || !abc))) ZB_FAIL(ZB_E_ARG, "bad argument");
+    Ctx* c = sets[0]->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    std::vector<SetRef> refs(nsets);
+    for (int i = 0; i < nsets; i++) {
+        if (!sets[i] || sets[i]->c != c) ZB_FAIL(ZB_E_ARG, "sets must live on one device");
+        refs[i].k = sets[i]->k.get();
+        refs[i].n = sets[i]->n;
+    }
+    DBuf<SetRef> d_refs(c, nsets);
+    ZB_CUDA(cudaMemcpyAsync(d_refs.get(), refs.data(), nsets * sizeof(SetRef), cudaMemcpyHostToDevice, c->stream));
+    const size_t TILE = 4096;
+    size_t p0 = 0;
+    while (p0 < npairs) {
+        // batch pairs so that one launch stays below 2^30 CTAs
+        std::vector<uint64_t> tstart;
+        tstart.push_back(0);
+        size_t p1 = p0;
+        while (p1 < npairs) {
+            if (I[p1] >= (uint32_t)nsets || J[p1] >= (uint32_t)nsets) ZB_FAIL(ZB_E_ARG, "pair index out of range");
+            const uint64_t t = div_up(refs[I[p1]].n + refs[J[p1]].n, TILE);
+            if (tstart.back() + t > (1ull << 30) && p1 > p0) break;
+            tstart.push_back(tstart.back() + t);
+            p1++;
+        }
+        const size_t np = p1 - p0;
+        DBuf<uint64_t> d_abc(c, 3 * np + np + 1);
+        DBuf<uint32_t> d_ij(c, 2 * np);
+        ZB_CUDA(cudaMemsetAsync(d_abc.get(), 0, 3 * np * 8, c->stream));
+        ZB_CUDA(cudaMemcpyAsync(d_abc.get() + 3 * np, tstart.data(), (np + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        ZB_CUDA(cudaMemcpyAsync(d_ij.get(), I + p0, np * 4, cudaMemcpyHostToDevice, c->stream));
+        ZB_CUDA(cudaMemcpyAsync(d_ij.get() + np, J + p0, np * 4, cudaMemcpyHostToDevice, c->stream));
+        pairs_abc(c, d_refs.get(), d_ij.get(), d_ij.get() + np, np, d_abc.get(), tstart.back());
+        ZB_CUDA(cudaMemcpyAsync(abc + 3 * p0, d_abc.get(), 3 * np * 8, cudaMemcpyDeviceToHost, c->stream));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+        for (size_t p = p0; p < p1; p++) {
+            const uint64_t a = abc[3 * p];
+            abc[3 * p + 1] = refs[I[p]].n - a;
+            abc[3 * p + 2] = refs[J[p]].n - a;
+        }
+        p0 = p1;
+    }
+    ZB_CATCH
+}
+
+// ------------------------------------------------------------------------------- diagnostics
+// Stage-level entry points used by tests/ and bench.py (kernel isolation); not part of the drop-in surface.
+int zb_dbg_sort_u64(int device, uint64_t* keys, uint32_t* vals, size_t n, int key_bits, int max_bits, int iters,
+                    float* ms_per_sort) {
+    ZB_TRY
+    Ctx* c = ctx_for(device);
+    const int saved = g_sort_max_bits;
+    if (max_bits >= 8 && max_bits <= 11) g_sort_max_bits = max_bits;
+    DBuf<uint64_t> a(c, n), b(c, n), src(c, n);
+    DBuf<uint32_t> va, vb, vsrc;
+    if (vals) { va.alloc(c, n); vb.alloc(c, n); vsrc.alloc(c, n); }
+    ZB_CUDA(cudaMemcpyAsync(src.get(), keys, n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (vals) ZB_CUDA(cudaMemcpyAsync(vsrc.get(), vals, n * 4, cudaMemcpyHostToDevice, c->stream));
+    cudaEvent_t e0, e1;
+    ZB_CUDA(cudaEventCreate(&e0));
+    ZB_CUDA(cudaEventCreate(&e1));
+    int which = 0;
+    float total_ms = 0;
+    if (iters < 1) iters = 1;
+    for (int it = 0; it < iters; it++) {
+        ZB_CUDA(cudaMemcpyAsync(a.get(), src.get(), n * 8, cudaMemcpyDeviceToDevice, c->stream));
+        if (vals) ZB_CUDA(cudaMemcpyAsync(va.get(), vsrc.get(), n * 4, cudaMemcpyDeviceToDevice, c->stream));
+        ZB_CUDA(cudaEventRecord(e0, c->stream));
+        which = radix_sort(c, a.get(), b.get(), vals ? va.get() : nullptr, vals ? vb.get() : nullptr, n, key_bits);
+        ZB_CUDA(cudaEventRecord(e1, c->stream));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        ZB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (it > 0 || iters == 1) total_ms += ms;
+    }
+    g_sort_max_bits = saved;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_per_sort) *ms_per_sort = total_ms / (float)(iters > 1 ? iters - 1 : 1);
+    ZB_CUDA(cudaMemcpyAsync(keys, which ? b.get() : a.get(), n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (vals) ZB_CUDA(cudaMemcpyAsync(vals, which ? vb.get() : va.get(), n * 4, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    ZB_CATCH
+}
+
+int zb_dbg_parse(int device, const uint8_t* raw, size_t n, int is_fasta, uint8_t* codes, size_t* n_codes,
+                 uint64_t* n_records) {
+    ZB_TRY
+    Ctx* c = ctx_for(device);
+    DBuf<uint8_t> d(c, n + 16), cd(c, n + 64);
+    ZB_CUDA(cudaMemcpyAsync(d.get(), raw, n, cudaMemcpyHostToDevice, c->stream));
+    if (is_fasta) parse_fasta(c, d.get(), n, cd.get(), n_codes, n_records);
+    else parse_fastq(c, d.get(), n, cd.get(), n_codes, n_records);
+    if (codes && *n_codes) ZB_CUDA(cudaMemcpyAsync(codes, cd.get(), *n_codes, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    ZB_CATCH
+}
+
+int zb_dbg_extract(int device, int k, const uint8_t* codes, size_t n, uint64_t* keys, size_t* n_keys) {
+    ZB_TRY
+    Ctx* c = ctx_for(device);
+    if (k < 1 || k > 32) ZB_FAIL(ZB_E_ARG, "k out of range");
+    const size_t padded = div_up(n, EXTRACT_TILE) * EXTRACT_TILE + 32;
+    DBuf<uint8_t> cd(c, 32 + padded);
+    DBuf<uint64_t> out(c, padded);
+    DBuf<unsigned long long> cnt(c, 1);
+    ZB_CUDA(cudaMemsetAsync(cd.get(), 4, 32 + padded, c->stream));
+    ZB_CUDA(cudaMemsetAsync(cnt.get(), 0, 8, c->stream));
+    if (n) ZB_CUDA(cudaMemcpyAsync(cd.get() + 32, codes, n, cudaMemcpyHostToDevice, c->stream));
+    extract_canonical(c, k, cd.get() + 32, n, out.get(), cnt.get());
+    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, cnt.get(), 8, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    *n_keys = (size_t)c->h_scalars[0];
+    if (keys && *n_keys) ZB_CUDA(cudaMemcpy(keys, out.get(), *n_keys * 8, cudaMemcpyDeviceToHost));
+    ZB_CATCH
+}
+
+}  // extern "C"

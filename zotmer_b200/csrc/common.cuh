@@ -1,0 +1,233 @@
+// common.cuh -- shared host/device helpers for the zotmer_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/zotmer_b200.h"
+
+namespace zb {
+
+// ----------------------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+
+struct Fail {
+    int code;
+};
+
+#define ZB_CUDA(expr)                                                                             \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            zb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            throw zb::Fail{ZB_E_CUDA};                                                            \
+        }                                                                                         \
+    } while (0)
+
+#define ZB_FAIL(code, ...)            \
+    do {                              \
+        zb::set_error(__VA_ARGS__);   \
+        throw zb::Fail{code};         \
+    } while (0)
+
+// ----------------------------------------------------------------------------- device context
+// One context per (host thread, device): a stream, a stream-ordered memory pool that keeps its
+// pages (so repeated batches do not pay cudaMalloc), and a few scratch scalars in pinned memory.
+struct Ctx {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;
+    uint64_t* h_scalars = nullptr;  // pinned, 64 x u64
+    uint64_t launches = 0;          // kernels launched through this context (bench "gpu_launches")
+};
+
+Ctx* ctx_for(int device);
+
+inline void* dalloc(Ctx* c, size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    ZB_CUDA(cudaMallocAsync(&p, bytes, c->stream));
+    return p;
+}
+inline void dfree(Ctx* c, void* p) {
+    if (p) cudaFreeAsync(p, c->stream);
+}
+
+// RAII device buffer bound to a context's stream/pool
+template <typename T>
+struct DBuf {
+    Ctx* c = nullptr;
+    T* p = nullptr;
+    size_t n = 0;
+    DBuf() {}
+    DBuf(Ctx* c_, size_t n_) : c(c_), n(n_) { p = (T*)dalloc(c, n * sizeof(T)); }
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    DBuf(DBuf&& o) noexcept : c(o.c), p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DBuf& operator=(DBuf&& o) noexcept {
+        if (this != &o) { release(); c = o.c; p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DBuf() { release(); }
+    void release() { if (p) { dfree(c, p); p = nullptr; n = 0; } }
+    void alloc(Ctx* c_, size_t n_) { release(); c = c_; n = n_; p = (T*)dalloc(c, n * sizeof(T)); }
+    T* get() const { return p; }
+};
+
+#define ZB_LAUNCH_CHECK(c)                       \
+    do {                                         \
+        (c)->launches++;                         \
+        ZB_CUDA(cudaGetLastError());             \
+    } while (0)
+
+static inline size_t div_up(size_t a, size_t b) { return (a + b - 1) / b; }
+
+// ----------------------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// streaming (read-once) 128-bit load / store that do not pollute L1
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan(T v) {
+    const unsigned l = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T t = __shfl_up_sync(0xffffffffu, v, o);
+        if (l >= (unsigned)o) v += t;
+    }
+    return v;
+}
+
+// Block-wide exclusive scan of one value per thread.  THREADS multiple of 32, <= 1024.
+// `smem` needs THREADS/32 + 1 elements.  Returns exclusive prefix; *total gets the block sum.
+template <int THREADS, typename T>
+__device__ __forceinline__ T block_excl_scan(T v, T* smem, T* total) {
+    const unsigned l = lane_id(), w = threadIdx.x >> 5;
+    T inc = warp_incl_scan(v);
+    if (l == 31) smem[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        T x = (l < THREADS / 32) ? smem[l] : T(0);
+        T xi = warp_incl_scan(x);
+        if (l < THREADS / 32) smem[l] = xi - x;
+        if (l == 31) smem[THREADS / 32] = xi;
+    }
+    __syncthreads();
+    T r = smem[w] + inc - v;
+    *total = smem[THREADS / 32];
+    __syncthreads();
+    return r;
+}
+
+// ---- chained scan ("decoupled look-back") over tiles, one 64-bit status word per tile.
+// status: bits 63..62 = 0 invalid / 1 tile aggregate / 2 inclusive prefix; bits 61..0 value.
+// The status array must be zeroed before the launch and tile ids must be handed out in launch
+// order (atomic ticket) so that every predecessor of a running tile is itself running or done.
+// Call with ALL 32 lanes of one warp; returns the exclusive prefix of `agg` in every lane.
+#define ZB_ST_AGG (1ull << 62)
+#define ZB_ST_PFX (2ull << 62)
+#define ZB_ST_VAL ((1ull << 62) - 1)
+__device__ __forceinline__ uint64_t lookback_u64(uint64_t* status, uint32_t tile, uint64_t agg) {
+    const unsigned l = lane_id();
+    if (tile == 0) {
+        if (l == 0) st_volatile_u64(status, ZB_ST_PFX | agg);
+        return 0;
+    }
+    if (l == 0) st_volatile_u64(status + tile, ZB_ST_AGG | agg);
+    uint64_t excl = 0;
+    int64_t base = (int64_t)tile - 1;
+    while (true) {
+        int64_t idx = base - (int64_t)l;
+        uint64_t v;
+        unsigned inval, haspfx;
+        do {
+            v = (idx >= 0) ? ld_volatile_u64(status + idx) : ZB_ST_PFX;
+            inval = __ballot_sync(0xffffffffu, (v >> 62) == 0);
+            haspfx = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+            // only lanes up to (and including) the nearest inclusive prefix matter
+            unsigned need = haspfx ? ((2u << (__ffs(haspfx) - 1)) - 1u) : 0xffffffffu;
+            inval &= need;
+        } while (inval);
+        int firstp = haspfx ? (__ffs(haspfx) - 1) : 32;
+        uint64_t contrib = ((int)l <= firstp) ? (v & ZB_ST_VAL) : 0ull;
+        excl += warp_sum(contrib);
+        if (firstp < 32) break;
+        base -= 32;
+    }
+    if (l == 0) st_volatile_u64(status + tile, ZB_ST_PFX | (excl + agg));
+    return excl;
+}
+
+// ---- 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP) completing on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// bytes and both addresses must be multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+#endif  // __CUDACC__
+
+}  // namespace zb

@@ -1,0 +1,199 @@
+// extract.cu -- 2-bit packing and canonical k-mer extraction from a dense base-code stream.
+//
+// Replaces zotmer/library/basics.py:303-347 (kmersList(K, seq, True)): every window of k consecutive
+// valid bases yields the forward k-mer x and its reverse complement xb.  Because count(x) ==
+// count(rc(x)) for every k-mer the reference ever emits, the device counts only the CANONICAL key
+// min(x, xb) (half the sort volume) and mirrors the distinct result afterwards (setops.cu
+// mirror_keys); the emitted set is the reference's both-strand multiset, bit for bit.
+//
+// Input layout (produced by parse.cu): one byte per base, 0..3 = A C G T/U, 4 = break (invalid byte
+// or record boundary), preceded by 32 break bytes and padded with break bytes to a whole tile.
+// One CTA handles 4096 codes: a single 1-D bulk async copy (TMA, UBLKCP) brings the tile plus its
+// 32-code halo into shared memory; each thread packs 16 codes into a little-endian 2-bit word and a
+// 16-bit invalid mask; neighbours' words come from shared memory; all 16 windows of a thread are
+// then plain shifts of a 96-bit register window (no per-base rolling, no divergence).
+#include "kernels.h"
+
+namespace zb {
+
+static constexpr int EX_THREADS = 256;
+static constexpr int EX_PER = 16;
+static_assert(EX_THREADS * EX_PER == EXTRACT_TILE, "tile shape");
+
+__device__ __forceinline__ uint64_t rev2_64(uint64_t x) {
+    uint64_t y = __brevll(x);
+    return ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
+}
+
+// 4 byte codes (0..4) -> 8 bits of 2-bit codes (first byte lowest) and 4 invalid bits
+__device__ __forceinline__ void pack4(uint32_t v, uint32_t& w, uint32_t& m) {
+    uint32_t t = v & 0x03030303u;
+    t = (t | (t >> 6)) & 0x000f000fu;
+    t = (t | (t >> 12)) & 0xffu;
+    uint32_t u = (v >> 2) & 0x01010101u;
+    u = (u | (u >> 7) | (u >> 14) | (u >> 21)) & 0xfu;
+    w = t;
+    m = u;
+}
+__device__ __forceinline__ void pack16(uint4 c, uint32_t& w, uint32_t& m) {
+    uint32_t w0, w1, w2, w3, m0, m1, m2, m3;
+    pack4(c.x, w0, m0);
+    pack4(c.y, w1, m1);
+    pack4(c.z, w2, m2);
+    pack4(c.w, w3, m3);
+    w = w0 | (w1 << 8) | (w2 << 16) | (w3 << 24);
+    m = m0 | (m1 << 4) | (m2 << 8) | (m3 << 12);
+}
+
+__global__ void __launch_bounds__(EX_THREADS)
+extract_kernel(int k, const uint8_t* __restrict__ codes, uint64_t* __restrict__ out,
+               unsigned long long* __restrict__ counter) {
+    __shared__ __align__(128) uint8_t s_codes[EXTRACT_TILE + 32];
+    __shared__ uint32_t s_w[EX_THREADS + 2];
+    __shared__ uint32_t s_m[EX_THREADS + 2];
+    __shared__ __align__(16) uint64_t s_keys[EXTRACT_TILE];
+    __shared__ uint32_t s_scan[EX_THREADS / 32 + 1];
+    __shared__ unsigned long long s_base;
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const unsigned tid = threadIdx.x;
+    const uint8_t* src = codes + (size_t)blockIdx.x * EXTRACT_TILE - 32;  // 16-byte aligned by construction
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&s_bar, EXTRACT_TILE + 32);
+        bulk_g2s(s_codes, src, EXTRACT_TILE + 32, &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+
+    uint32_t w, m;
+    pack16(*reinterpret_cast<const uint4*>(s_codes + 32 + tid * 16), w, m);
+    s_w[tid + 2] = w;
+    s_m[tid + 2] = m;
+    if (tid < 2) {
+        uint32_t hw, hm;
+        pack16(*reinterpret_cast<const uint4*>(s_codes + tid * 16), hw, hm);
+        s_w[tid] = hw;
+        s_m[tid] = hm;
+    }
+    __syncthreads();
+    const uint32_t w2 = s_w[tid], w1 = s_w[tid + 1];  // bases -32..-17, -16..-1 relative to my first base
+    const uint32_t m2 = s_m[tid], m1 = s_m[tid + 1];
+
+    // 96-bit little-endian window: base i of the 48 sits at bits [2i, 2i+2)
+    const uint64_t lo = ((uint64_t)w1 << 32) | w2;
+    const uint64_t hi = w;
+    const int s = 2 * (33 - k);  // 2..64: uniform pre-shift so that window j starts at bit 2j
+    uint64_t plo, phi;
+    if (s >= 64) { plo = hi; phi = 0; }
+    else { plo = (lo >> s) | (hi << (64 - s)); phi = hi >> s; }
+    const uint64_t inv48 = ((uint64_t)m << 32) | ((uint64_t)m1 << 16) | m2;
+    const uint64_t pinv = inv48 >> (33 - k);
+    const uint64_t kmask = (k == 32) ? 0xffffffffull : ((1ull << k) - 1ull);
+    const uint64_t msk = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    const int fsh = 64 - 2 * k;
+
+    uint64_t key[EX_PER];
+    uint32_t vbits = 0;
+#pragma unroll
+    for (int j = 0; j < EX_PER; j++) {
+        const uint64_t win = (j == 0) ? plo : ((plo >> (2 * j)) | (phi << (64 - 2 * j)));
+        const bool ok = ((pinv >> j) & kmask) == 0;
+        const uint64_t rcv = (~win) & msk;          // reverse complement: complement of the LE window
+        const uint64_t fwd = rev2_64(win) >> fsh;   // forward: first base most significant
+        key[j] = fwd < rcv ? fwd : rcv;
+        vbits |= (ok ? 1u : 0u) << j;
+    }
+    uint32_t tot;
+    uint32_t off = block_excl_scan<EX_THREADS, uint32_t>(__popc(vbits), s_scan, &tot);
+#pragma unroll
+    for (int j = 0; j < EX_PER; j++) {
+        if ((vbits >> j) & 1u) s_keys[off++] = key[j];
+    }
+    if (tid == 0) s_base = tot ? atomicAdd(counter, (unsigned long long)tot) : 0ull;
+    __syncthreads();
+    const unsigned long long base = s_base;
+    for (uint32_t i = tid; i < tot; i += EX_THREADS) out[base + i] = s_keys[i];
+}
+
+void extract_canonical(Ctx* c, int k, const uint8_t* codes, size_t n, uint64_t* out, unsigned long long* d_count) {
+    if (n == 0) return;
+    const unsigned tiles = (unsigned)div_up(n, EXTRACT_TILE);
+    extract_kernel<<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count);
+    ZB_LAUNCH_CHECK(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU routing: owner(key) = floor(mix64(key) * nranks / 2^64) -- the high bits of an
+// invertible 64-bit mix, so ownership is uniform even for low-complexity sequence.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+__device__ __forceinline__ int owner_of(uint64_t key, int nranks) {
+    return (int)__umul64hi(mix64(key), (uint64_t)nranks);
+}
+
+__global__ void __launch_bounds__(256)
+bucket_count_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int sc[64];
+    if (threadIdx.x < 64) sc[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&sc[owner_of(keys[i], nranks)], 1u);
+    __syncthreads();
+    if (threadIdx.x < nranks && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sc[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256)
+bucket_scatter_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, unsigned long long* __restrict__ cursor,
+                      uint64_t* __restrict__ out) {
+    // per-CTA: count per owner, reserve ranges with one atomic per owner, then place.
+    __shared__ unsigned int sc[64];
+    __shared__ unsigned long long sb[64];
+    constexpr int PER = 8;
+    const uint64_t base = (uint64_t)blockIdx.x * blockDim.x * PER;
+    if (threadIdx.x < 64) sc[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t kx[PER];
+    int ow[PER];
+    unsigned int rk[PER];
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        const uint64_t i = base + (uint64_t)j * blockDim.x + threadIdx.x;
+        ow[j] = -1;
+        if (i < n) {
+            kx[j] = keys[i];
+            ow[j] = owner_of(kx[j], nranks);
+            rk[j] = atomicAdd(&sc[ow[j]], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < nranks) sb[threadIdx.x] = sc[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], (unsigned long long)sc[threadIdx.x]) : 0ull;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; j++)
+        if (ow[j] >= 0) out[sb[ow[j]] + rk[j]] = kx[j];
+}
+
+void bucket_count(Ctx* c, const uint64_t* keys, size_t n, int nranks, unsigned long long* d_counts) {
+    if (n == 0) return;
+    if (nranks > 64) ZB_FAIL(ZB_E_ARG, "bucket_count: nranks > 64");
+    int blocks = (int)std::min<size_t>((size_t)c->sm_count * 8, div_up(n, 256));
+    bucket_count_kernel<<<blocks, 256, 0, c->stream>>>(keys, n, nranks, d_counts);
+    ZB_LAUNCH_CHECK(c);
+}
+
+void bucket_scatter(Ctx* c, const uint64_t* keys, size_t n, int nranks, unsigned long long* d_cursor, uint64_t* out) {
+    if (n == 0) return;
+    bucket_scatter_kernel<<<(unsigned)div_up(n, 256 * 8), 256, 0, c->stream>>>(keys, n, nranks, d_cursor, out);
+    ZB_LAUNCH_CHECK(c);
+}
+
+}  // namespace zb

@@ -1,0 +1,67 @@
+// kernels.h -- internal host-side entry points of the CUDA translation units (not part of the C ABI).
+#pragma once
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+
+namespace zb {
+
+// ---- sort.cu ---------------------------------------------------------------------------------
+// LSD radix sort ("onesweep": one upfront multi-digit histogram, then one chained-scan scatter
+// pass per digit) of n < 2^30 u64 keys whose significant bits are [0, key_bits).  Buffers are
+// ping-ponged; returns 0 or 1 = which of (k0,v0)/(k1,v1) holds the sorted result.  v0/v1 may be
+// null (keys only).  Replaces zotmer/library/misc.py:400-424 (radix_sort).
+int radix_sort(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits);
+extern int g_sort_max_bits;  // digit width cap (8..11), tunable from bench via ZB_SORT_BITS
+
+// ---- setops.cu -------------------------------------------------------------------------------
+// Run-length count of a sorted key array (optionally weighted by `w`): distinct keys + counts.
+// Replaces kmerize.py:41-132 (merge with an empty left run) / KmerAccumulator2.flush :412-424.
+// Returns the number of distinct keys (synchronises the stream).  Fails with ZB_E_RANGE if a count
+// exceeds 2^32-1.
+size_t reduce_by_key(Ctx* c, const uint64_t* keys, const uint32_t* w, size_t n, uint64_t* out_k, uint32_t* out_c);
+// Merge two sorted (key,count) lists keeping duplicates adjacent (merge-path), n = na + nb outputs.
+void merge_pairs(Ctx* c, const uint64_t* ak, const uint32_t* ac, size_t na, const uint64_t* bk, const uint32_t* bc,
+                 size_t nb, uint64_t* ok, uint32_t* oc);
+// Both-strand expansion of a canonical counted set (kmerize.py both=True semantics):
+// writes rc(k, x) for every non-palindromic x (+ its count) and doubles palindrome counts in place.
+// Returns number of mirrored keys written.
+size_t mirror_keys(Ctx* c, int k, const uint64_t* ck, uint32_t* cc, size_t n, uint64_t* rk, uint32_t* rcnt);
+// Compaction cmin <= count (<= cmax when cmax > 0); returns kept count.  trim.py:54-62.
+size_t trim_pairs(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, uint64_t cmin, uint64_t cmax,
+                  uint64_t* ok, uint32_t* oc);
+// y = x >> shift with adjacent duplicates dropped.  commands/dist.py:36-49.
+size_t project_keys(Ctx* c, const uint64_t* k, size_t n, int shift, uint64_t* ok);
+// Histogram of counts in first-occurrence order + acgt tallies.  kmerize.py:544-545, merge.py:158-159.
+void set_stats(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, uint64_t acgt_w[4], uint64_t acgt_p[4],
+               uint64_t* total, std::vector<std::pair<uint64_t, uint64_t>>* hist_first_order);
+// Intersection / difference cardinalities for a batch of pairs.  library/dist.py:241-265.
+struct SetRef {
+    const uint64_t* k;
+    uint64_t n;
+};
+void pairs_abc(Ctx* c, const SetRef* d_sets, const uint32_t* d_I, const uint32_t* d_J, size_t npairs, uint64_t* d_abc,
+               uint64_t total_work);
+
+// ---- parse.cu --------------------------------------------------------------------------------
+// Raw FASTA/FASTQ bytes (device) -> dense base codes (0..3, 4 = break).  `codes` must have room for
+// n + 64 bytes.  Returns number of codes written and the number of records (synchronises).
+// Replaces file.py:19-52 (readFasta/readFastq) as used by reads.py:86-125.
+void parse_fastq(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n_codes, uint64_t* n_records);
+void parse_fasta(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n_codes, uint64_t* n_records);
+
+// ---- extract.cu ------------------------------------------------------------------------------
+// codes: device pointer to a buffer laid out as [32 bytes of 4][n codes][padding of 4 up to a
+// multiple of EXTRACT_TILE + 16]; pointer passed is to the first real code.  Appends the canonical
+// k-mer (min(x, rc x)) of every valid window to out[*d_count ...] (unordered within the batch).
+// basics.py:303-347.
+static const int EXTRACT_TILE = 4096;
+void extract_canonical(Ctx* c, int k, const uint8_t* codes, size_t n, uint64_t* out, unsigned long long* d_count);
+// multi-GPU: same, but also tallies owner-bucket sizes (owner = mix64(key) range partition).
+void bucket_count(Ctx* c, const uint64_t* keys, size_t n, int nranks, unsigned long long* d_bucket_counts);
+void bucket_scatter(Ctx* c, const uint64_t* keys, size_t n, int nranks, unsigned long long* d_bucket_cursor,
+                    uint64_t* out);
+
+}  // namespace zb

@@ -1,0 +1,386 @@
+// parse.cu -- FASTQ / FASTA text -> dense base-code stream, entirely on the device.
+//
+// Replaces zotmer/library/file.py:19-36 (readFasta), :38-52 (readFastq) as driven by
+// zotmer/library/reads.py:86-125.  Output: one byte per sequence character that the reference's
+// k-mer extractor would see, 0..3 for AaCcGgTtUu (basics.py:42-46), 4 for anything else, plus one
+// 4 ("break") between records so that no window spans two records.
+//
+// FASTQ semantics reproduced: lines are split at '\n' only; every 4 lines form a record, line 1 of
+// each group is the sequence; a trailing group of fewer than 4 lines is dropped (file.py:51 is never
+// true); strip() only removes bytes that are invalid bases anyway, so it needs no special handling.
+//
+// FASTA semantics reproduced: a line whose first non-blank byte is '>' starts a record; everything
+// before the first header is ignored; sequence lines are strip()ped and JOINED, i.e. a maximal
+// whitespace run that contains a '\n' (or touches either end of the file) vanishes, while a
+// whitespace run inside a line is an ordinary invalid byte.  Whitespace = " \t\n\r\v\f" (py2 strip).
+//
+// Both kernels are single-pass: chained scans ("decoupled look-back") carry the line number / the
+// line state and the output offset from tile to tile.
+#include "kernels.h"
+#include "fasta_rules.cuh"
+
+namespace zb {
+
+static constexpr int PA_THREADS = 256;
+static constexpr int PA_ROWS = 4;
+static constexpr int PA_TILE = PA_THREADS * 16 * PA_ROWS;  // 16 KB of text per CTA
+static constexpr int PA_WARPS = PA_THREADS / 32;
+
+__device__ __forceinline__ uint4 load16(const uint8_t* raw, uint64_t off, uint64_t n, uint32_t fill) {
+    uint4 v;
+    if (off + 16 <= n) {
+        v = *reinterpret_cast<const uint4*>(raw + off);
+    } else {
+        uint32_t w[4] = {fill, fill, fill, fill};
+        for (int b = 0; b < 16; b++)
+            if (off + b < n) w[b >> 2] = (w[b >> 2] & ~(0xffu << (8 * (b & 3)))) | ((uint32_t)raw[off + b] << (8 * (b & 3)));
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return v;
+}
+__device__ __forceinline__ uint32_t count_eq(const uint4& v, uint32_t pat) {
+    return (__popc(__vcmpeq4(v.x, pat)) + __popc(__vcmpeq4(v.y, pat)) + __popc(__vcmpeq4(v.z, pat)) +
+            __popc(__vcmpeq4(v.w, pat))) >> 3;
+}
+
+// exclusive scan, in position order, over the [ROWS][WARPS] cells held in shared memory (by warp 0)
+__device__ __forceinline__ uint32_t cells_excl_scan(uint32_t* cells /*[ROWS*WARPS]*/) {
+    // ROWS*WARPS == 32: one cell per lane
+    static_assert(PA_ROWS * PA_WARPS == 32, "cell grid");
+    const unsigned l = lane_id();
+    const uint32_t v = cells[l];
+    const uint32_t inc = warp_incl_scan(v);
+    cells[l] = inc - v;
+    return __shfl_sync(0xffffffffu, inc, 31);
+}
+
+// ------------------------------------------------------------------------------------- FASTQ
+__global__ void __launch_bounds__(256) count_newlines_kernel(const uint8_t* __restrict__ raw, uint64_t n,
+                                                            unsigned long long* __restrict__ out) {
+    unsigned long long c = 0;
+    const uint64_t chunks = (n + 15) / 16;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < chunks; q += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 v = load16(raw, q * 16, n, 0);
+        c += count_eq(v, 0x0a0a0a0au);
+    }
+    c = warp_sum(c);
+    if (lane_id() == 0 && c) atomicAdd(out, c);
+}
+
+__global__ void __launch_bounds__(PA_THREADS)
+fastq_kernel(const uint8_t* __restrict__ raw, uint64_t n, const unsigned long long* __restrict__ n_newlines,
+             uint8_t* __restrict__ codes, uint64_t* __restrict__ st_lines, uint64_t* __restrict__ st_out,
+             uint32_t* __restrict__ ticket, uint64_t* __restrict__ total_out) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_nl[PA_ROWS * PA_WARPS];
+    __shared__ uint32_t s_em[PA_ROWS * PA_WARPS];
+    __shared__ uint64_t s_pref[2];
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t base = (uint64_t)tile * PA_TILE;
+    // complete records only: lines = newlines (+1 if the text does not end in '\n')
+    const uint64_t lines = *n_newlines + ((n > 0 && raw[n - 1] != '\n') ? 1 : 0);
+    const uint64_t max_line = (lines >> 2) << 2;
+
+    uint4 v[PA_ROWS];
+    uint32_t nlx[PA_ROWS];  // newlines before my 16 bytes inside the tile
+#pragma unroll
+    for (int r = 0; r < PA_ROWS; r++) {
+        const uint64_t off = base + (uint64_t)r * (PA_THREADS * 16) + tid * 16;
+        v[r] = (off < n) ? load16(raw, off, n, 0) : make_uint4(0, 0, 0, 0);
+        const uint32_t c = count_eq(v[r], 0x0a0a0a0au);
+        const uint32_t inc = warp_incl_scan(c);
+        nlx[r] = inc - c;
+        if (lane == 31) s_nl[r * PA_WARPS + warp] = inc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t tot = cells_excl_scan(s_nl);
+        const uint64_t p = lookback_u64(st_lines, tile, tot);
+        if (lane == 0) s_pref[0] = p;
+    }
+    __syncthreads();
+    const uint64_t line0 = s_pref[0];
+
+    uint64_t acc[PA_ROWS];
+    uint32_t cnt[PA_ROWS], emx[PA_ROWS];
+#pragma unroll
+    for (int r = 0; r < PA_ROWS; r++) {
+        const uint64_t off = base + (uint64_t)r * (PA_THREADS * 16) + tid * 16;
+        uint64_t line = line0 + s_nl[r * PA_WARPS + warp] + nlx[r];
+        uint64_t a = 0;
+        uint32_t m = 0;
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            const uint32_t ch = byte_of(v[r], b);
+            const bool in = off + b < n;
+            const bool seq = in && ((line & 3) == 1) && (line < max_line);
+            if (seq) {
+                a |= (uint64_t)code_of(ch) << (4 * m);
+                m++;
+            }
+            line += (ch == '\n') ? 1 : 0;
+        }
+        acc[r] = a;
+        cnt[r] = m;
+        const uint32_t inc = warp_incl_scan(m);
+        emx[r] = inc - m;
+        if (lane == 31) s_em[r * PA_WARPS + warp] = inc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t tot = cells_excl_scan(s_em);
+        const uint64_t p = lookback_u64(st_out, tile, tot);
+        if (lane == 0) {
+            s_pref[1] = p;
+            if (base + PA_TILE >= n) *total_out = p + tot;
+        }
+    }
+    __syncthreads();
+    const uint64_t out0 = s_pref[1];
+#pragma unroll
+    for (int r = 0; r < PA_ROWS; r++) {
+        uint64_t o = out0 + s_em[r * PA_WARPS + warp] + emx[r];
+        uint64_t a = acc[r];
+        for (uint32_t q = 0; q < cnt[r]; q++) {
+            codes[o + q] = (uint8_t)(a & 0xf);
+            a >>= 4;
+        }
+    }
+}
+
+void parse_fastq(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n_codes, uint64_t* n_records) {
+    *n_codes = 0;
+    *n_records = 0;
+    if (n == 0) return;
+    const uint32_t tiles = (uint32_t)div_up(n, PA_TILE);
+    DBuf<uint64_t> st(c, (size_t)tiles * 2 + 4);
+    ZB_CUDA(cudaMemsetAsync(st.get(), 0, ((size_t)tiles * 2 + 4) * 8, c->stream));
+    uint64_t* st_lines = st.get();
+    uint64_t* st_out = st.get() + tiles;
+    unsigned long long* nnl = reinterpret_cast<unsigned long long*>(st.get() + 2 * (size_t)tiles);
+    uint64_t* total = st.get() + 2 * (size_t)tiles + 1;
+    uint32_t* ticket = reinterpret_cast<uint32_t*>(st.get() + 2 * (size_t)tiles + 2);
+    int blocks = (int)std::min<size_t>((size_t)c->sm_count * 8, div_up(n, 256 * 16));
+    count_newlines_kernel<<<blocks, 256, 0, c->stream>>>(raw, n, nnl);
+    ZB_LAUNCH_CHECK(c);
+    fastq_kernel<<<tiles, PA_THREADS, 0, c->stream>>>(raw, n, nnl, codes, st_lines, st_out, ticket, total);
+    ZB_LAUNCH_CHECK(c);
+    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, nnl, 16, cudaMemcpyDeviceToHost, c->stream));
+    uint8_t last = 0;
+    ZB_CUDA(cudaMemcpyAsync(&last, raw + n - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    const uint64_t lines = c->h_scalars[0] + (last != '\n' ? 1 : 0);
+    *n_records = lines / 4;
+    *n_codes = (size_t)c->h_scalars[1];
+}
+
+// ------------------------------------------------------------------------------------- FASTA
+// (line-state rules: fasta_rules.cuh)
+#define FST_AGG 0x40000000u
+#define FST_PFX 0x80000000u
+
+__global__ void __launch_bounds__(PA_THREADS)
+fasta_kernel(const uint8_t* __restrict__ raw, uint64_t n, uint8_t* __restrict__ codes, uint32_t* __restrict__ st_state,
+             uint64_t* __restrict__ st_out, uint32_t* __restrict__ ticket, uint64_t* __restrict__ total_out,
+             unsigned long long* __restrict__ n_records) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_cell[PA_ROWS * PA_WARPS];   // inclusive transfer map per (row, warp), then exclusive
+    __shared__ uint32_t s_bcell[PA_ROWS * PA_WARPS];  // backward (gb, pb) per cell
+    __shared__ uint32_t s_em[PA_ROWS * PA_WARPS];
+    __shared__ uint32_t s_in;    // tile entry state (f,h,s)
+    __shared__ uint32_t s_bin;   // B carry entering the tile from the right
+    __shared__ uint64_t s_pref;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t base = (uint64_t)tile * PA_TILE;
+
+    FaMasks mk[PA_ROWS];
+    uint4 v[PA_ROWS];
+    uint32_t texcl[PA_ROWS];  // composition of the pieces before mine inside my warp-row
+    uint32_t bexcl[PA_ROWS];  // backward: composition of the pieces after mine inside my warp-row (bit0=gb, bit1=pb)
+#pragma unroll
+    for (int r = 0; r < PA_ROWS; r++) {
+        const uint64_t off = base + (uint64_t)r * (PA_THREADS * 16) + tid * 16;
+        // bytes past the end behave like blanks touching the end of the text
+        v[r] = (off < n) ? load16(raw, off, n, 0x20202020u) : make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
+        mk[r] = fa_masks(v[r]);
+        const uint32_t t = fa_summary(mk[r]);
+        // forward inclusive scan by composition
+        uint32_t inc = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (unsigned)o) inc = fa_compose(u, inc);
+        }
+        uint32_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
+        texcl[r] = (lane == 0) ? FA_IDENT : ex;
+        if (lane == 31) s_cell[r * PA_WARPS + warp] = inc;
+        // backward: b_left = gb | pb & b_right ; gb = leading blank run holds '\n', pb = all blank & no '\n'
+        const FaPiece p0 = fa_piece(mk[r], false, false, false);
+        uint32_t bs = ((p0.B & 1u) ? 1u : 0u) | (((t & FA_PF) ? 1u : 0u) << 1);
+        uint32_t binc = bs;  // inclusive from the right
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_down_sync(0xffffffffu, binc, o);
+            if (lane + o < 32) {
+                // mine (left) then u (right):  g = g1 | p1&g2 ; p = p1&p2
+                const uint32_t g = (binc & 1u) | (((binc >> 1) & 1u) & (u & 1u));
+                const uint32_t pp = ((binc >> 1) & 1u) & ((u >> 1) & 1u);
+                binc = g | (pp << 1);
+            }
+        }
+        uint32_t bex = __shfl_down_sync(0xffffffffu, binc, 1);
+        bexcl[r] = (lane == 31) ? 2u : bex;  // identity = (g=0,p=1)
+        if (lane == 0) s_bcell[r * PA_WARPS + warp] = binc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // ---- forward: scan the 32 cells, then chain with the previous tiles
+        const uint32_t t = s_cell[lane];
+        uint32_t inc = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (unsigned)o) inc = fa_compose(u, inc);
+        }
+        const uint32_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
+        s_cell[lane] = (lane == 0) ? FA_IDENT : ex;
+        const uint32_t tile_map = __shfl_sync(0xffffffffu, inc, 31);
+        // ---- backward cells
+        const uint32_t bt = s_bcell[lane];
+        uint32_t binc = bt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_down_sync(0xffffffffu, binc, o);
+            if (lane + o < 32) {
+                const uint32_t g = (binc & 1u) | (((binc >> 1) & 1u) & (u & 1u));
+                const uint32_t pp = ((binc >> 1) & 1u) & ((u >> 1) & 1u);
+                binc = g | (pp << 1);
+            }
+        }
+        const uint32_t bex = __shfl_down_sync(0xffffffffu, binc, 1);
+        s_bcell[lane] = (lane == 31) ? 2u : bex;
+        if (lane == 0) {
+            // chained look-back with function composition (sequential walk; predecessors resolve fast)
+            uint32_t st_in;
+            if (tile == 0) {
+                st_in = 1u;  // f = 1 at the start of the text, no header yet
+            } else {
+                st_volatile_u32(st_state + tile, FST_AGG | tile_map);
+                uint32_t comp = FA_IDENT;
+                int64_t p = (int64_t)tile - 1;
+                while (true) {
+                    uint32_t x;
+                    do { x = ld_volatile_u32(st_state + p); } while ((x & (FST_AGG | FST_PFX)) == 0);
+                    if (x & FST_PFX) { st_in = fa_apply(comp, x & 7u); break; }
+                    comp = fa_compose(x & 0x7fu, comp);
+                    p--;
+                }
+            }
+            st_volatile_u32(st_state + tile, FST_PFX | fa_apply(tile_map, st_in));
+            s_in = st_in;
+            // ---- B carry from the right of the tile: does the blank run that starts right after the
+            // tile reach a '\n' or the end of the text?  Direct forward scan (runs are short).
+            uint64_t q = base + PA_TILE;
+            uint32_t bin = 1u;
+            while (q < n) {
+                const uint8_t ch = raw[q];
+                if (ch == '\n') { bin = 1u; break; }
+                if (!(ch == ' ' || (ch >= 9 && ch <= 13))) { bin = 0u; break; }
+                q++;
+            }
+            s_bin = bin;
+        }
+    }
+    __syncthreads();
+    const uint32_t tile_in = s_in;
+    const uint32_t tile_bin = s_bin;
+
+    uint64_t acc[PA_ROWS];
+    uint32_t cnt[PA_ROWS], emx[PA_ROWS];
+    uint32_t nrec = 0;
+#pragma unroll
+    for (int r = 0; r < PA_ROWS; r++) {
+        const uint64_t off = base + (uint64_t)r * (PA_THREADS * 16) + tid * 16;
+        const uint32_t st = fa_apply(fa_compose(s_cell[r * PA_WARPS + warp], texcl[r]), tile_in);
+        // backward carry: my right neighbours inside the warp-row, then the cells to the right, then the tile's
+        const uint32_t bc = s_bcell[r * PA_WARPS + warp];
+        const uint32_t bright_cells = (bc & 1u) | (((bc >> 1) & 1u) & tile_bin);
+        const uint32_t b_in = (bexcl[r] & 1u) | (((bexcl[r] >> 1) & 1u) & bright_cells);
+        const FaPiece p = fa_piece(mk[r], st & 1u, st & 2u, b_in);
+        // bytes that come after the first header: everything if s already set, else from the first HS bit on
+        uint32_t live = (st & 4u) ? 0xffffu : (p.HS ? (0xffffu & ~((p.HS & (0u - p.HS)) - 1u)) : 0u);
+        const uint32_t skip = mk[r].W & (p.F | p.B);
+        // emit: header start -> one break; header text -> nothing; vanished blanks -> nothing; else code
+        const uint32_t emit = live & ((p.HS) | (~p.HIN & ~skip & 0xffffu));
+        uint64_t a = 0;
+        uint32_t m = 0;
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            const bool in = off + b < n;
+            if (in && ((emit >> b) & 1u)) {
+                const uint32_t cd = ((p.HS >> b) & 1u) ? 4u : code_of(byte_of(v[r], b));
+                a |= (uint64_t)cd << (4 * m);
+                m++;
+            }
+        }
+        // records: header starts inside the text
+        uint32_t hs_valid = p.HS;
+        if (off + 16 > n) hs_valid &= (off < n) ? ((1u << (n - off)) - 1u) : 0u;
+        nrec += __popc(hs_valid);
+        acc[r] = a;
+        cnt[r] = m;
+        const uint32_t inc = warp_incl_scan(m);
+        emx[r] = inc - m;
+        if (lane == 31) s_em[r * PA_WARPS + warp] = inc;
+    }
+    nrec = warp_sum(nrec);
+    if (lane == 0 && nrec) atomicAdd(n_records, (unsigned long long)nrec);
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t tot = cells_excl_scan(s_em);
+        const uint64_t p = lookback_u64(st_out, tile, tot);
+        if (lane == 0) {
+            s_pref = p;
+            if (base + PA_TILE >= n) *total_out = p + tot;
+        }
+    }
+    __syncthreads();
+    const uint64_t out0 = s_pref;
+#pragma unroll
+    for (int r = 0; r < PA_ROWS; r++) {
+        uint64_t o = out0 + s_em[r * PA_WARPS + warp] + emx[r];
+        uint64_t a = acc[r];
+        for (uint32_t q = 0; q < cnt[r]; q++) {
+            codes[o + q] = (uint8_t)(a & 0xf);
+            a >>= 4;
+        }
+    }
+}
+
+void parse_fasta(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n_codes, uint64_t* n_records) {
+    *n_codes = 0;
+    *n_records = 0;
+    if (n == 0) return;
+    const uint32_t tiles = (uint32_t)div_up(n, PA_TILE);
+    DBuf<uint64_t> st(c, (size_t)tiles * 2 + 4);
+    ZB_CUDA(cudaMemsetAsync(st.get(), 0, ((size_t)tiles * 2 + 4) * 8, c->stream));
+    uint64_t* st_out = st.get();
+    uint32_t* st_state = reinterpret_cast<uint32_t*>(st.get() + tiles);
+    uint64_t* total = st.get() + 2 * (size_t)tiles;
+    unsigned long long* nrec = reinterpret_cast<unsigned long long*>(st.get() + 2 * (size_t)tiles + 1);
+    uint32_t* ticket = reinterpret_cast<uint32_t*>(st.get() + 2 * (size_t)tiles + 2);
+    fasta_kernel<<<tiles, PA_THREADS, 0, c->stream>>>(raw, n, codes, st_state, st_out, ticket, total, nrec);
+    ZB_LAUNCH_CHECK(c);
+    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, total, 16, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    *n_codes = (size_t)c->h_scalars[0];
+    *n_records = c->h_scalars[1];
+}
+
+}  // namespace zb

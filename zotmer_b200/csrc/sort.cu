@@ -1,0 +1,303 @@
+// sort.cu -- hand-written LSD radix sort for u64 k-mer keys (optionally with a u32 payload).
+//
+// Replaces zotmer/library/misc.py:400-424 (radix_sort: MSD buckets + list.sort) -- the result is the
+// same ascending order.  Design ("onesweep"): one upfront kernel reads the keys once and builds the
+// histograms of ALL digits; then one kernel per digit does load -> in-tile stable ranking (warp
+// match + per-warp counters) -> chained scan across tiles (decoupled look-back, one status word per
+// (tile, bin)) -> shared-memory staged scatter.  Per pass every key is read once and written once:
+// 16 B/key/pass (+4 B with payload), the HBM floor for an out-of-place LSD pass.
+//
+// Digits: the 2k significant key bits are split EVENLY over ceil(2k / maxbits) passes so that every
+// digit is fully populated (k=25: 50 bits -> 7 x (8,7,7,7,7,7,7) at maxbits=8, or 5 x 10 at 10).
+#include <vector>
+
+#include "kernels.h"
+
+namespace zb {
+
+int g_sort_max_bits = 8;
+
+static constexpr int SORT_THREADS = 256;
+static constexpr int SORT_WARPS = SORT_THREADS / 32;
+static constexpr int SORT_ITEMS = 16;
+static constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys = 32 KB
+static constexpr int MAX_PASSES = 8;
+
+struct SortPlan {
+    int passes;
+    int shift[MAX_PASSES];
+    int bits[MAX_PASSES];
+};
+
+// ------------------------------------------------------------------------------- histogram
+// All digits of all passes in one read of the keys.  Shared-memory bins, one RED per key per pass.
+template <int BINS>
+__global__ void __launch_bounds__(512) sort_hist_kernel(const uint64_t* __restrict__ keys, size_t n, SortPlan plan,
+                                                        uint32_t* __restrict__ ghist /*[passes][BINS]*/) {
+    extern __shared__ uint32_t sh[];  // [passes][BINS]
+    const int total = plan.passes * BINS;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 2;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += stride) {
+        uint64_t a, b;
+        bool two = (i + 1 < n);
+        if (two) {
+            ulonglong2 v = *reinterpret_cast<const ulonglong2*>(keys + i);
+            a = v.x; b = v.y;
+        } else {
+            a = keys[i]; b = 0;
+        }
+#pragma unroll
+        for (int p = 0; p < MAX_PASSES; p++) {
+            if (p < plan.passes) {
+                const uint32_t m = (1u << plan.bits[p]) - 1u;
+                atomicAdd(&sh[p * BINS + ((uint32_t)(a >> plan.shift[p]) & m)], 1u);
+                if (two) atomicAdd(&sh[p * BINS + ((uint32_t)(b >> plan.shift[p]) & m)], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        uint32_t v = sh[i];
+        if (v) atomicAdd(&ghist[i], v);
+    }
+}
+
+// exclusive scan of each pass's histogram -> global start of each bin.  One block per pass.
+template <int BINS>
+__global__ void __launch_bounds__(BINS > 1024 ? 1024 : BINS) sort_scan_kernel(uint32_t* __restrict__ ghist) {
+    constexpr int T = BINS > 1024 ? 1024 : BINS;
+    constexpr int PER = BINS / T;
+    __shared__ uint32_t sm[T / 32 + 1];
+    uint32_t* h = ghist + (size_t)blockIdx.x * BINS;
+    uint32_t v[PER];
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { v[i] = h[threadIdx.x * PER + i]; s += v[i]; }
+    uint32_t tot;
+    uint32_t ex = block_excl_scan<T, uint32_t>(s, sm, &tot);
+#pragma unroll
+    for (int i = 0; i < PER; i++) { h[threadIdx.x * PER + i] = ex; ex += v[i]; }
+}
+
+// ------------------------------------------------------------------------------- onesweep pass
+#define ST32_AGG 0x40000000u
+#define ST32_PFX 0x80000000u
+#define ST32_VAL 0x3fffffffu
+
+template <int BINS, bool HAS_VALS>
+__global__ void __launch_bounds__(SORT_THREADS, (BINS <= 256 ? 3 : 2))
+onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const uint32_t* __restrict__ vin,
+                uint32_t* __restrict__ vout, uint32_t n, int shift, int bits,
+                const uint32_t* __restrict__ bin_start /*[BINS] global exclusive*/,
+                uint32_t* __restrict__ status /*[tiles][BINS], zeroed*/, uint32_t* __restrict__ ticket) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw);                       // [TILE]
+    uint32_t* svals = reinterpret_cast<uint32_t*>(skeys + SORT_TILE);              // [TILE] (if HAS_VALS)
+    uint32_t* whist = svals + (HAS_VALS ? SORT_TILE : 0);                          // [WARPS][BINS]
+    uint32_t* s_binstart = whist + SORT_WARPS * BINS;                              // [BINS] start inside the tile
+    uint32_t* s_goff = s_binstart + BINS;                                          // [BINS] global pos - tile pos
+    __shared__ uint32_t s_scan[SORT_THREADS / 32 + 1];
+    __shared__ uint32_t s_tile;
+
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t dmask = (1u << bits) - 1u;
+    const int nbins = 1 << bits;
+
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < SORT_WARPS * BINS; i += SORT_THREADS) whist[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t tile_base = tile * SORT_TILE;
+    const uint32_t n_valid = min((uint32_t)SORT_TILE, n - tile_base);
+
+    // ---- load, warp-striped: item j of lane l sits at warp_base + j*32 + l
+    uint64_t key[SORT_ITEMS];
+    const uint32_t wbase = warp * (32 * SORT_ITEMS);
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; j++) {
+        uint32_t idx = wbase + j * 32 + lane;
+        key[j] = (idx < n_valid) ? __ldg(kin + tile_base + idx) : ~0ull;
+    }
+
+    // ---- stable rank inside the warp: lanes holding the same digit form a group, the lowest lane
+    // bumps the warp's counter of that digit by the group size.
+    uint16_t rnk[SORT_ITEMS];
+    uint32_t* myhist = whist + warp * BINS;
+    const unsigned lt = lanemask_lt();
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; j++) {
+        const uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
+        const unsigned m = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(m) - 1;
+        uint32_t old = 0;
+        if ((int)lane == leader) {
+            old = myhist[d];
+            myhist[d] = old + __popc(m);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rnk[j] = (uint16_t)(old + __popc(m & lt));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per digit: exclusive prefix over warps, tile count
+    constexpr int PER = (BINS + SORT_THREADS - 1) / SORT_THREADS;  // digits per thread (blocked)
+    uint32_t cnt[PER];
+    uint32_t csum = 0;
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+        const int d = tid * PER + q;
+        uint32_t s = 0;
+        if (d < nbins) {
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; w++) {
+                uint32_t c = whist[w * BINS + d];
+                whist[w * BINS + d] = s;
+                s += c;
+            }
+        }
+        cnt[q] = s;
+        csum += s;
+    }
+    uint32_t tot;
+    uint32_t ex = block_excl_scan<SORT_THREADS, uint32_t>(csum, s_scan, &tot);
+
+    // ---- chained scan across tiles, one status word per (tile, digit)
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+        const int d = tid * PER + q;
+        if (d < nbins) {
+            s_binstart[d] = ex;
+            uint32_t* st = status + (size_t)tile * BINS + d;
+            uint32_t excl = 0;
+            if (tile == 0) {
+                st_volatile_u32(st, ST32_PFX | cnt[q]);
+            } else {
+                st_volatile_u32(st, ST32_AGG | cnt[q]);
+                const uint32_t* p = st - BINS;
+                while (true) {
+                    uint32_t v;
+                    do { v = ld_volatile_u32(p); } while ((v & (ST32_AGG | ST32_PFX)) == 0);
+                    excl += v & ST32_VAL;
+                    if (v & ST32_PFX) break;
+                    p -= BINS;
+                }
+                st_volatile_u32(st, ST32_PFX | (excl + cnt[q]));
+            }
+            s_goff[d] = bin_start[d] + excl - ex;
+            ex += cnt[q];
+        }
+    }
+    __syncthreads();
+
+    // ---- place into tile-sorted order in shared memory
+    uint16_t pos[SORT_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; j++) {
+        const uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
+        const uint32_t p = s_binstart[d] + myhist[d] + rnk[j];
+        pos[j] = (uint16_t)p;
+        skeys[p] = key[j];
+    }
+    if (HAS_VALS) {
+#pragma unroll
+        for (int j = 0; j < SORT_ITEMS; j++) {
+            uint32_t idx = wbase + j * 32 + lane;
+            svals[pos[j]] = (idx < n_valid) ? __ldg(vin + tile_base + idx) : 0u;
+        }
+    }
+    __syncthreads();
+
+    // ---- coalesced-by-bin scatter: consecutive threads write consecutive keys of a bin
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; j++) {
+        const uint32_t i = j * SORT_THREADS + tid;
+        if (i < n_valid) {
+            const uint64_t kx = skeys[i];
+            const uint32_t d = (uint32_t)(kx >> shift) & dmask;
+            const uint32_t g = s_goff[d] + i;
+            kout[g] = kx;
+            if (HAS_VALS) vout[g] = svals[i];
+        }
+    }
+}
+
+template <int BINS>
+static size_t onesweep_smem(bool vals) {
+    return (size_t)SORT_TILE * 8 + (vals ? (size_t)SORT_TILE * 4 : 0) + (size_t)SORT_WARPS * BINS * 4 + 2 * BINS * 4;
+}
+
+template <int BINS>
+static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
+                           int maxbits) {
+    SortPlan plan;
+    plan.passes = (key_bits + maxbits - 1) / maxbits;
+    if (plan.passes < 1) plan.passes = 1;
+    if (plan.passes > MAX_PASSES) ZB_FAIL(ZB_E_ARG, "radix_sort: %d passes needed (max %d)", plan.passes, MAX_PASSES);
+    {
+        int base = key_bits / plan.passes, rem = key_bits % plan.passes, sh = 0;
+        for (int p = 0; p < plan.passes; p++) {
+            plan.bits[p] = base + (p < rem ? 1 : 0);
+            if (plan.bits[p] < 1) plan.bits[p] = 1;
+            plan.shift[p] = sh;
+            sh += plan.bits[p];
+        }
+    }
+    const bool vals = (v0 != nullptr);
+    const uint32_t tiles = (uint32_t)div_up(n, SORT_TILE);
+    DBuf<uint32_t> ghist(c, (size_t)plan.passes * BINS);
+    DBuf<uint32_t> status(c, (size_t)tiles * BINS);
+    DBuf<uint32_t> ticket(c, MAX_PASSES);
+    ZB_CUDA(cudaMemsetAsync(ghist.get(), 0, (size_t)plan.passes * BINS * 4, c->stream));
+    ZB_CUDA(cudaMemsetAsync(ticket.get(), 0, MAX_PASSES * 4, c->stream));
+
+    {
+        int blocks = (int)std::min<size_t>((size_t)c->sm_count * 4, div_up(n, 512 * 2 * 4));
+        if (blocks < 1) blocks = 1;
+        size_t sm = (size_t)plan.passes * BINS * 4;
+        if (sm > 48 * 1024)
+            ZB_CUDA(cudaFuncSetAttribute(sort_hist_kernel<BINS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        sort_hist_kernel<BINS><<<blocks, 512, sm, c->stream>>>(k0, n, plan, ghist.get());
+        ZB_LAUNCH_CHECK(c);
+        sort_scan_kernel<BINS><<<plan.passes, (BINS > 1024 ? 1024 : BINS), 0, c->stream>>>(ghist.get());
+        ZB_LAUNCH_CHECK(c);
+    }
+    size_t sm = onesweep_smem<BINS>(vals);
+    if (vals)
+        ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    else
+        ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    uint64_t* kb[2] = {k0, k1};
+    uint32_t* vb[2] = {v0, v1};
+    int cur = 0;
+    for (int p = 0; p < plan.passes; p++) {
+        ZB_CUDA(cudaMemsetAsync(status.get(), 0, (size_t)tiles * BINS * 4, c->stream));
+        if (vals)
+            onesweep_kernel<BINS, true><<<tiles, SORT_THREADS, sm, c->stream>>>(
+                kb[cur], kb[cur ^ 1], vb[cur], vb[cur ^ 1], (uint32_t)n, plan.shift[p], plan.bits[p],
+                ghist.get() + (size_t)p * BINS, status.get(), ticket.get() + p);
+        else
+            onesweep_kernel<BINS, false><<<tiles, SORT_THREADS, sm, c->stream>>>(
+                kb[cur], kb[cur ^ 1], nullptr, nullptr, (uint32_t)n, plan.shift[p], plan.bits[p],
+                ghist.get() + (size_t)p * BINS, status.get(), ticket.get() + p);
+        ZB_LAUNCH_CHECK(c);
+        cur ^= 1;
+    }
+    return cur;
+}
+
+int radix_sort(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits) {
+    if (n == 0) return 0;
+    if (n >= (1ull << 30)) ZB_FAIL(ZB_E_ARG, "radix_sort: n=%zu exceeds 2^30 keys per batch", n);
+    if (key_bits < 1) key_bits = 1;
+    if (key_bits > 64) key_bits = 64;
+    int mb = g_sort_max_bits;
+    if (mb <= 8) return radix_sort_impl<256>(c, k0, k1, v0, v1, n, key_bits, 8);
+    if (mb == 9) return radix_sort_impl<512>(c, k0, k1, v0, v1, n, key_bits, 9);
+    if (mb == 10) return radix_sort_impl<1024>(c, k0, k1, v0, v1, n, key_bits, 10);
+    return radix_sort_impl<2048>(c, k0, k1, v0, v1, n, key_bits, 11);
+}
+
+}  // namespace zb
