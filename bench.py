@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""
+bench.py -- measures BASELINE.json's metric "kmerize+count Gbases/s" on the configuration it is
+quoted on: synthetic 30x 150 bp Illumina-like FASTQ of a 5 Mbp genome (1,000,000 reads, 150 Mbases),
+kmerize+count at k=25 followed by zot trim at min-count 2.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch (the whole read set of a rank):
+  value : inputs resident in HBM (raw FASTQ text on the device) -> parse, extract, sort, count,
+          mirror, trim, all through the C ABI (zb_kmerize_feed_dev ... zb_trim); device-timed.
+  e2e   : the same through the host-buffer C ABI (zb_kmerize_feed from pinned host memory, results
+          fetched back to pinned host memory), H2D and D2H inside the timed region.
+N > 1 (weak scaling): every rank kmerizes its own 1M-read shard of the same genome, routes each
+canonical k-mer to its owner rank (high bits of a 64-bit mix) with one NCCL all-to-all over NVLink,
+and sorts/counts/trims its disjoint key range locally.
+--impl reference: the reference's own algorithm (pure Python, single thread, as the reference is)
+timed on a bounded sample of the same workload on the host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+K = 25
+READ_LEN = 150
+READS_PER_RANK = int(os.environ.get("ZB_BENCH_READS", 1000000))
+GENOME = 5000000
+METRIC = "kmerize+count Gbases/s"
+UNIT = "Gbases/s"
+# algorithmic bytes per input base of kmerize+count at k=25 on this workload
+# (1 + 2*W*8*(3+2P) + 12*d with W=0.84, P=7, d~0.3) and per key per radix pass (8 read + 8 write)
+BYTES_PER_BASE = 233.0
+BYTES_PER_KEY_PASS = 16.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_reads(rank, nreads):
+    from tools import synth
+    g = synth.genome(GENOME, seed=17)
+    return synth.fastq_array(g, nreads, L=READ_LEN, seed=18 + 1000 * rank).reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    """The reference's own CPU path (pure Python, single thread): oracle port timed on a bounded sample."""
+    if rank != 0:
+        return
+    from oracle import zot_oracle as zo
+    sample_reads = int(os.environ.get("ZB_REF_SAMPLE_READS", 4000))
+    fq = make_reads(0, READS_PER_RANK)[:sample_reads * 315].tobytes()
+    bases = sample_reads * READ_LEN
+
+    def step():
+        xs, cs, h, acgt, nr = zo.kmerize_core(K, [("reads.fq", fq)])
+        zo.words_to_bytes(zo.encode(zo.delta(xs)))       # the reference writes the set (54 % of its time)
+        zo.words_to_bytes(zo.encode(cs))
+        tx, tc = zo.trim_core(xs, cs, 2, None)
+        zo.words_to_bytes(zo.encode(zo.delta(tx)))
+        zo.words_to_bytes(zo.encode(tc))
+        return len(xs)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = bases / dt / 1e9
+    sample = "first %d of the %d reads (%d bases) per step; CPython %s, 1 thread" % (
+        sample_reads, READS_PER_RANK, bases, sys.version.split()[0])
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n):
+    return {"workload": "config[1]: synthetic 30x 150bp FASTQ of a 5 Mbp genome, %d reads per GPU, kmerize+count k=25 "
+                        "then trim min-count 2" % READS_PER_RANK,
+            "k": K, "reads_per_gpu": READS_PER_RANK, "read_len": READ_LEN, "bases_per_gpu": READS_PER_RANK * READ_LEN,
+            "parallelism": "1 GPU" if n == 1 else "%d GPUs: reads sharded, hash-range all-to-all of canonical k-mers" % n,
+            "l2": "inputs (315 MB of text, 1 GB of keys per GPU) are larger than the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+def step_device(nat, dev, d_ptr, nbytes, dist_ctx):
+    """one step with inputs resident in HBM -> (trimmed set, full set)"""
+    km = nat.Kmerizer(K, dev)
+    km.feed_dev(d_ptr, nbytes, False)
+    if dist_ctx is not None:
+        exchange(nat, km, dist_ctx)
+    s, nr = km.finish()
+    km.close()
+    t = s.trim(2)
+    return s, t
+
+
+def exchange(nat, km, ctx):
+    """route every pending canonical k-mer to its owner rank: sizes first, then one all-to-all of keys"""
+    import torch
+    import torch.distributed as dist
+    world, dev = ctx["world"], ctx["dev"]
+    n = km.pending()
+    send = ctx["send"]
+    if send.numel() < max(n, 1):
+        send = ctx["send"] = torch.empty(int(n * 1.1) + 16, dtype=torch.int64, device="cuda:%d" % dev)
+    counts = km.take_bucketed_dev(world, send.data_ptr())
+    cin = torch.tensor(counts, dtype=torch.int64, device="cuda:%d" % dev)
+    cout = torch.empty_like(cin)
+    dist.all_to_all_single(cout, cin)
+    recv_counts = [int(x) for x in cout.tolist()]
+    nrecv = sum(recv_counts)
+    recv = ctx["recv"]
+    if recv.numel() < max(nrecv, 1):
+        recv = ctx["recv"] = torch.empty(int(nrecv * 1.1) + 16, dtype=torch.int64, device="cuda:%d" % dev)
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    dist.all_to_all_single(recv[:nrecv], send[:n], recv_counts, counts)
+    t1.record()
+    torch.cuda.synchronize(dev)
+    ctx["a2a_ms"].append(t0.elapsed_time(t1))
+    ctx["a2a_bytes"].append(8 * (n - counts[ctx["rank"]]))
+    km.add_canonical_dev(recv.data_ptr(), nrecv)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from zotmer_b200 import _native as nat
+    if nat.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (zotmer_b200 has no CPU path)")
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    dist_ctx = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % dev))
+        dist_ctx = {"world": world, "rank": rank, "dev": dev, "a2a_ms": [], "a2a_bytes": [],
+                    "send": torch.empty(16, dtype=torch.int64, device="cuda:%d" % dev),
+                    "recv": torch.empty(16, dtype=torch.int64, device="cuda:%d" % dev)}
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        nat.device_sync(dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    fq = make_reads(rank, READS_PER_RANK)
+    nbytes = fq.nbytes
+    bases = READS_PER_RANK * READ_LEN
+    d_in = torch.from_numpy(fq).to("cuda:%d" % dev)
+    pinned_in = torch.from_numpy(fq).pin_memory()
+    h_in = pinned_in.numpy()
+
+    # ---------------- device-resident: warm-up, then K timed steps
+    n_trim = n_full = 0
+    for _ in range(args.warmup):
+        s, t = step_device(nat, dev, d_in.data_ptr(), nbytes, dist_ctx)
+        n_full, n_trim = len(s), len(t)
+        s.free(); t.free()
+    if dist_ctx is not None:
+        dist_ctx["a2a_ms"].clear(); dist_ctx["a2a_bytes"].clear()
+    sampler = ClockSampler(dev)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    nat.dbg_profile(True, dev)
+    launches0 = nat.launch_count(dev)
+    nat.timer_start(dev)
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        s, t = step_device(nat, dev, d_in.data_ptr(), nbytes, dist_ctx)
+        s.free(); t.free()
+    ms_dev = nat.timer_stop(dev)
+    barrier()
+    wall_ms = (time.perf_counter() - w0) * 1e3
+    launches = nat.launch_count(dev) - launches0
+    prof = nat.dbg_profile(False, dev)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- end to end through host buffers (pinned in, pinned out)
+    out_k = torch.empty(max(n_trim, 1), dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+    out_c = torch.empty(max(n_trim, 1), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+
+    def step_e2e():
+        km = nat.Kmerizer(K, dev)
+        km.feed(h_in, False)
+        if dist_ctx is not None:
+            exchange(nat, km, dist_ctx)
+        s, nr = km.finish()
+        km.close()
+        t = s.trim(2)
+        st = s.stats()
+        k_, c_ = t.fetch(out_k=out_k, out_c=out_c)
+        s.free(); t.free()
+        return len(k_), st
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        nk, st = step_e2e()
+    barrier()
+    e2e_ms = (time.perf_counter() - e0) * 1e3 / args.steps
+
+    # ---------------- reduce over ranks (max time), aggregate throughput
+    per_step_ms = ms_dev / args.steps   # CUDA events on the library stream around the K steps
+    vals = [per_step_ms, e2e_ms, float(launches)]
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor(vals[:2], dtype=torch.float64, device="cuda:%d" % dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        per_step_ms, e2e_ms = float(tt[0]), float(tt[1])
+        tl = torch.tensor([float(launches)], dtype=torch.float64, device="cuda:%d" % dev)
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+        launches = int(tl[0])
+    if rank != 0:
+        return
+    total_bases = bases * world
+    value = total_bases / (per_step_ms * 1e-3) / 1e9
+    e2e = total_bases / (e2e_ms * 1e-3) / 1e9
+
+    peak, peak_kind = load_peaks()
+    # dominant kernel: one onesweep radix pass over the canonical keys of this rank
+    sp = prof.get("sort_pass_keys", (0.0, 0))
+    pass_ms = sp[0] / sp[1] if sp[1] else None
+    roofline = None
+    stage_ms = {k: round(v[0] / args.steps, 4) for k, v in prof.items()}
+    keys_per_step = stage_keys(nat, dev, d_in, nbytes) if pass_ms else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "onesweep_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    if pass_ms and keys_per_step:
+        achieved = BYTES_PER_KEY_PASS * keys_per_step / (pass_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "onesweep_kernel (one LSD radix pass, 16 B/key)", "achieved": achieved,
+                    "peak": peak, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)", "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic,
+                    "launch_ms": pass_ms, "keys_per_launch": keys_per_step,
+                    "pipeline_achieved": BYTES_PER_BASE * bases / (per_step_ms * 1e-3) / 1e9,
+                    "pipeline_frac": BYTES_PER_BASE * bases / (per_step_ms * 1e-3) / 1e9 / peak,
+                    "pipeline_bytes_per_base": BYTES_PER_BASE,
+                    "stage_ms_per_step": stage_ms}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic", "config": workload_config(world),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nk * 12),
+                "ms_per_step": e2e_ms, "result": "trimmed (k-mer u64, count u32) arrays + count histogram of the full set"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "result": {"distinct_kmers": int(n_full), "after_trim": int(n_trim)},
+    }
+    if dist_ctx is not None and dist_ctx["a2a_ms"]:
+        a_ms = float(np.mean(dist_ctx["a2a_ms"]))
+        a_b = float(np.mean(dist_ctx["a2a_bytes"]))
+        line["nvlink"] = {"all_to_all_ms": a_ms, "bytes_sent_per_gpu": a_b, "GBps_per_gpu_out": a_b / a_ms / 1e6,
+                          "peak_GBps_per_direction": 900.0, "measured_peer_copy_GBps": 770.0}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line))
+
+
+def stage_keys(nat, dev, d_in, nbytes):
+    """number of canonical keys one step sorts (valid windows of the rank's reads)"""
+    km = nat.Kmerizer(K, dev)
+    km.feed_dev(d_in.data_ptr(), nbytes, False)
+    n = km.pending()
+    km.close()
+    return int(n)
+
+
+def cpu_baseline():
+    """oracle port of the reference (pure Python, 1 thread) on a bounded sample of the same reads"""
+    from oracle import zot_oracle as zo
+    sample_reads = int(os.environ.get("ZB_CPU_SAMPLE_READS", 12000))
+    fq = make_reads(0, READS_PER_RANK)[:sample_reads * 315].tobytes()
+    t0 = time.perf_counter()
+    xs, cs, h, acgt, nr = zo.kmerize_core(K, [("reads.fq", fq)])
+    zo.words_to_bytes(zo.encode(zo.delta(xs)))
+    zo.words_to_bytes(zo.encode(cs))
+    tx, tc = zo.trim_core(xs, cs, 2, None)
+    zo.words_to_bytes(zo.encode(zo.delta(tx)))
+    zo.words_to_bytes(zo.encode(tc))
+    dt = time.perf_counter() - t0
+    return {"value": sample_reads * READ_LEN / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "first %d of the %d reads (%.1f Mbases, %.1f s): kmerize+count, codec64 encode, trim; CPython %s "
+                      "single thread (the reference has no parallelism); host has %d cores" % (
+                          sample_reads, READS_PER_RANK, sample_reads * READ_LEN / 1e6, dt, sys.version.split()[0],
+                          os.cpu_count())}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -131,6 +131,11 @@ int zb_dbg_parse(int device, const uint8_t* raw, size_t n, int is_fasta, uint8_t
                  uint64_t* n_records);
 /* dense base codes -> canonical k-mers in unspecified order (keys must hold n entries) */
 int zb_dbg_extract(int device, int k, const uint8_t* codes, size_t n, uint64_t* keys, size_t* n_keys);
+/* per-stage device timing (CUDA events on the library stream): turn on/off; `report` receives
+ * "stage total_ms calls" lines for everything run since it was switched on */
+int zb_dbg_profile(int device, int on, char* report, size_t cap);
+/* CUDA-event timer on the library stream: op 0 records the start, op 1 records the stop and returns ms */
+int zb_dbg_timer(int device, int op, float* ms);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,199 @@
+"""
+CPU-only tests of the host layer: the C-ABI library loads and exports every symbol the header
+declares (no compute calls without a GPU), the docopt-compatible parser, the casket container against
+the reference-written golden files, the metadata-only commands, and the no-CPU-fallback rule.
+"""
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+
+def g(name):
+    return os.path.join(GOLDEN, name)
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "zotmer_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(zb_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from zotmer_b200 import _native
+    L = _native.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(L, s), s
+        assert s in _native.SIGNATURES, "binding missing for " + s
+    assert set(_native.SIGNATURES) == set(syms)
+    assert L.zb_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    from zotmer_b200 import _native
+    if _native.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_native.NativeError) as ei:
+        _native.Kmerizer(25)
+    assert ei.value.code == _native.ZB_E_NOGPU
+    with pytest.raises(_native.NativeError):
+        _native.KmerSet.from_arrays(np.array([1, 2, 3], np.uint64))
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for dp, _, fns in os.walk(os.path.join(ROOT, "zotmer_b200")):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dp, fn), errors="replace").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|libzot_oracle|zot_oracle", txt, re.M):
+                    bad.append(fn)
+    assert bad == []
+
+
+def test_docopt_mini_grammars():
+    from zotmer_b200 import docopt_mini as d
+    from zotmer_b200 import cli
+    from zotmer_b200.commands import kmerize, dist, jaccard, trim, merge, hist
+    o = d.docopt(kmerize.__doc__, ["kmerize", "-m", "5", "-v", "25", "out.k25", "a.fa", "b.fq"])
+    assert o["-m"] == "5" and o["-v"] is True and o["-D"] is None and o["<k>"] == "25"
+    assert o["<output>"] == "out.k25" and o["<input>"] == ["a.fa", "b.fq"]
+    o = d.docopt(dist.__doc__, ["dist", "-M", "jaccard.qual", "-M", "*.qual", "25", "a", "b"])
+    assert o["-M"] == ["jaccard.qual", "*.qual"] and o["<k>"] == "25" and o["<input>"] == ["a", "b"]
+    assert d.docopt(dist.__doc__, ["dist", "25", "a"])["-M"] == []
+    o = d.docopt(jaccard.__doc__, ["jaccard", "-ap", "0.9", "a", "b"])
+    assert o["-a"] is True and o["-b"] is False and o["-p"] == "0.9"
+    o = d.docopt(trim.__doc__, ["trim", "o", "i"])
+    assert o["-c"] == "0" and o["-C"] == "0" and o["<input>"] == "i"
+    assert d.docopt(trim.__doc__, ["trim", "-c", "2", "o", "i"])["-c"] == "2"
+    assert d.docopt(merge.__doc__, ["merge", "o", "i"])["<input>"] == ["i"]
+    assert d.docopt(hist.__doc__, ["hist", "x", "y"])["<input>"] == ["x", "y"]
+    o = d.docopt(cli.__doc__, ["kmerize", "-m", "5", "25", "o", "i"], options_first=True, version="v")
+    assert o["<command>"] == "kmerize" and o["<args>"] == ["-m", "5", "25", "o", "i"]
+    with pytest.raises(SystemExit):
+        d.docopt(trim.__doc__, ["trim", "o"])
+    with pytest.raises(SystemExit):
+        d.docopt(kmerize.__doc__, ["kmerize", "--bogus", "25", "o", "i"])
+
+
+def test_casket_reads_reference_files_and_rewrites_identically(tmp_path):
+    from zotmer_b200.library.kmers import kmers
+    for name in ("kat6.k5", "r1_c2.k25", "m2.k25", "m5.k25"):
+        with kmers(g(name), "r") as z:
+            meta = z.meta
+            blobs = {nm: z.open(nm).read() for nm in ("kmers", "counts")}
+            toc_order = list(z.toc.keys())
+        assert toc_order == ["kmers", "counts", "__meta__"]
+        o = tmp_path / name
+        with kmers(str(o), "w") as w:
+            with w.add_stream("kmers") as f:
+                f.write(blobs["kmers"])
+            w.add_content("counts", blobs["counts"])
+            w.meta = meta
+        assert o.read_bytes() == open(g(name), "rb").read()
+
+
+def test_casket_missing_entry_keyerror():
+    from zotmer_b200.library.casket import casket
+    with casket(g("kat6.k5"), "r") as z:
+        with pytest.raises(KeyError):
+            z.open("nope")
+        assert z.list() == [("__meta__", 176), ("counts", 8), ("kmers", 8)]
+
+
+def test_hist_and_info_commands(in_golden_dir, capsys):
+    from zotmer_b200 import cli
+    cli.main(["hist", "g1.k25", "r1.k25", "r1_c2.k25", "m5.k25", "m2.k25"])
+    assert capsys.readouterr().out == open(g("hist.txt")).read()
+    cli.main(["info", "kat6.k5", "m3.k25"])
+    assert capsys.readouterr().out == open(g("info.txt")).read()
+
+
+def test_cli_help_and_unknown_command(capsys):
+    from zotmer_b200 import cli
+    cli.main(["help"])
+    out = capsys.readouterr().out
+    for c in ("kmerize", "merge", "dist", "jaccard", "trim", "hist", "info", "dump"):
+        assert "\t" + c in out
+    cli.main(["help", "trim"])
+    assert "zot trim [-c CUTOFF] <output> <input>" in capsys.readouterr().out
+    cli.main(["frobnicate"])
+    assert "unable to load command `frobnicate'" in capsys.readouterr().err
+
+
+def test_reads_rules_and_pieces():
+    from zotmer_b200.library.reads import isFasta, pieces
+    assert isFasta("a.fa") and isFasta("a.fasta.gz") and isFasta("x.fna.bz2") and isFasta("y.fas")
+    assert not isFasta("a.fq") and not isFasta("a.fastq.gz") and not isFasta("-") and not isFasta("a.fa.txt")
+    fq = b"".join(b"@r%d\nACGT\n+\nIIII\n" % i for i in range(1000))
+    ps = [bytes(p) for p in pieces(fq, False, max_piece=1000)]
+    assert b"".join(ps) == fq and len(ps) > 10
+    assert all(p.count(b"\n") % 4 == 0 and p[:1] == b"@" for p in ps)
+    fa = b"".join(b">s%d\nACGTACGTAC\nGGG\n" % i for i in range(500))
+    ps = [bytes(p) for p in pieces(fa, True, max_piece=777)]
+    assert b"".join(ps) == fa and all(p[:1] == b">" for p in ps)
+
+
+def test_host_formulas_match_reference_vectors():
+    from zotmer_b200.library import dist as D
+    from zotmer_b200.library import basics as B
+    from zotmer_b200.commands import jaccard as J
+    kat = json.load(open(g("kat.json")))
+    for e in kat["split"]:
+        if "jaccard" not in e:
+            continue
+        a, b, c = e["split"]
+        for nm in ("brayCurtis", "chord", "hellinger", "jaccard", "kulczynski", "ochiai", "sorensen", "whittaker"):
+            assert float(getattr(D, nm)(a, b, c)).hex() == e["m_" + nm]
+    for e in kat["beta"]:
+        assert float(J.logIx(e["p"], e["m"], e["n"])).hex() == e["logIx"]
+        assert float(J.quantBeta(0.05, e["m"], e["n"])).hex() == e["q05"]
+        assert float(J.quantBeta(0.95, e["m"], e["n"])).hex() == e["q95"]
+    for e in kat["render"]:
+        assert B.render(e["k"], int(e["x"])) == e["out"]
+        assert B.renderMany(e["k"], np.array([int(e["x"])], np.uint64)) == [e["out"]]
+    for e in kat["rc"]:
+        assert str(B.rc(e["k"], int(e["x"]))) == e["out"]
+    for e in kat["murmer"]:
+        assert str(B.murmer(int(e["x"]), e["s"])) == e["out"]
+
+
+def test_fasta_line_rules_host_build(tmp_path):
+    """the byte-classification rules of the FASTA parse kernel, compiled for the host and fuzzed
+    against the oracle's read_fasta (zotmer_b200/csrc/fasta_rules.cuh)"""
+    import random
+    from oracle import zot_oracle as zo
+    exe = str(tmp_path / "parse_rules_host")
+    subprocess.check_call(["g++", "-O1", "-o", exe, os.path.join(ROOT, "tests", "host", "parse_rules_host.cpp")])
+
+    def expected(data):
+        out = bytearray()
+        recs = zo.read_fasta(data)
+        for _, seq in recs:
+            out.append(4)
+            out.extend(4 if zo.NUC[b] is None else zo.NUC[b] for b in seq)
+        return bytes(out), len(recs)
+
+    rng = random.Random(5)
+    cases = [open(g("g1.fa"), "rb").read(), open(g("kat6.fa"), "rb").read(), b"", b"ACGT", b">", b">a",
+             b"\n\n  \n>x\nAC GT\n \n\nAC\n"]
+    alphabets = [b"ACGT\n", b"ACGTN \n\r\t>", b"AC >\n", b" \n>", b"ACGTacgtnN>\n\r \t\x0b\x0c-", b"A\n"]
+    for it in range(400):
+        al = rng.choice(alphabets)
+        n = rng.choice([0, 1, 2, 15, 16, 17, 31, 32, 33, 50, 100, 200, 500])
+        data = bytes(rng.choices(al, weights=[rng.choice([1, 1, 1, 5, 20]) for _ in al], k=n))
+        cases.append((b">h\n" + data) if rng.random() < 0.5 else data)
+    fa, co = str(tmp_path / "t.fa"), str(tmp_path / "t.codes")
+    for data in cases:
+        open(fa, "wb").write(data)
+        r = subprocess.run([exe, fa, co], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        exp, nrec = expected(data)
+        assert open(co, "rb").read() == exp and int(r.stdout) == nrec

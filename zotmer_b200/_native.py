@@ -55,6 +55,8 @@ SIGNATURES = {
     "zb_dbg_sort_u64": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "zb_dbg_parse": (C.c_int, [C.c_int, vp, C.c_size_t, C.c_int, vp, C.POINTER(C.c_size_t), u64p]),
     "zb_dbg_extract": (C.c_int, [C.c_int, C.c_int, vp, C.c_size_t, vp, C.POINTER(C.c_size_t)]),
+    "zb_dbg_profile": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
+    "zb_dbg_timer": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float)]),
 }
 
 _lib = None
@@ -140,10 +142,13 @@ class KmerSet(object):
         _check(lib().zb_set_size(self.h, C.byref(n)))
         return n.value
 
-    def fetch(self, counts=True):
+    def fetch(self, counts=True, out_k=None, out_c=None):
+        """copy to host; out_k/out_c may be preallocated (e.g. pinned) arrays of sufficient size"""
         n = len(self)
-        k = np.empty(n, np.uint64)
-        c = np.empty(n, np.uint32) if counts else None
+        k = np.empty(n, np.uint64) if out_k is None else out_k[:n]
+        c = None
+        if counts:
+            c = np.empty(n, np.uint32) if out_c is None else out_c[:n]
         _check(lib().zb_set_fetch(self.h, _ptr(k), _ptr(c) if counts else None))
         return (k, c) if counts else k
 
@@ -313,3 +318,28 @@ def dbg_extract(k, codes, device=0):
     n = C.c_size_t(0)
     _check(lib().zb_dbg_extract(device, k, _ptr(c), len(c), _ptr(keys), C.byref(n)))
     return keys[:n.value].copy()
+
+
+def dbg_profile(on, device=0):
+    """switch per-stage timing on/off; returns {stage: (total_ms, calls)} collected so far"""
+    buf = C.create_string_buffer(8192)
+    _check(lib().zb_dbg_profile(device, 1 if on else 0, buf, len(buf)))
+    out = {}
+    for ln in buf.value.decode().splitlines():
+        nm, ms, calls = ln.split()
+        out[nm] = (float(ms), int(calls))
+    return out
+
+
+def timer_start(device=0):
+    _check(lib().zb_dbg_timer(device, 0, None))
+
+
+def timer_stop(device=0):
+    ms = C.c_float(0)
+    _check(lib().zb_dbg_timer(device, 1, C.byref(ms)))
+    return ms.value
+
+
+def device_sync(device=0):
+    _check(lib().zb_device_sync(device))

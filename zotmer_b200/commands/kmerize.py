@@ -1,0 +1,87 @@
+"""
+Usage:
+    zot kmerize [options] <k> <output> <input>...
+
+Kmerize FASTA or FASTQ inputs to produce a standard container object.
+
+Arguments:
+    <k>         the length of the k-mers. Recommended values: 10-30
+    <output>    the name of the output file.
+                recommended naming convention
+                    - mykmers.k25 for a k-mer set of 25-mers
+                    - mykmers.kf25 for a k-mer frequency set of 25-mers
+                    - mykmers.e25 for an expanded k-mer set of 25-mers
+
+Options:
+    -m MEM      in-memory buffer size (in MB)
+    -C BAITS    capture mode - use kmers from the given FASTA file.
+    -D FRAC     subsample k-mers, using FRAC proportion of k-mers
+    -S SEED     if -D is given, give a seed for determining the
+                subspace (defaults to 0).
+    -v          produce verbose progress messages
+"""
+# Drop-in for zotmer/commands/kmerize.py:450-562.  The per-record Python loop (reads() ->
+# kmersList -> acgt tally -> KmerAccumulator2 -> radix_sort -> merge, :490-545) is replaced by
+# zb_kmerize_* : raw file bytes go to the GPU, which parses, extracts both strands, sorts and counts.
+# The spill machinery (-m, :527-553) is not reproduced: its output is byte-identical to the
+# in-memory path (golden `spill_equals_inmemory`); -m is accepted and ignored.
+import sys
+
+from zotmer_b200 import docopt_mini as docopt
+from zotmer_b200 import _native
+from zotmer_b200.library.file import readBytes
+from zotmer_b200.library.files import writeKmerSet
+from zotmer_b200.library.reads import isFasta, pieces
+import zotmer_b200.library.kmers as zotk
+
+
+def kmerizeFiles(K, inputs, device=0, verbose=False):
+    """-> (KmerSet with both strands, number of records).  kmerize.py:463-539."""
+    km = _native.Kmerizer(K, device)
+    try:
+        for fn in inputs:
+            data = readBytes(fn)
+            fa = isFasta(fn)
+            if verbose:
+                print('reading %s (%d bytes, %s)' % (fn, len(data), 'FASTA' if fa else 'FASTQ'), file=sys.stderr)
+            for piece in pieces(data, fa):
+                km.feed(piece, fa)
+        return km.finish()
+    finally:
+        km.close()
+
+
+def main(argv):
+    opts = docopt.docopt(__doc__, argv)
+
+    verbose = opts['-v']
+    K = int(opts['<k>'])
+    out = opts['<output>']
+
+    if opts['-D'] is not None or opts['-C'] is not None:
+        # kmerize.py:494-520 (murmur subsampling / bait capture): SURVEY.md 8f row 2, not built yet
+        print('zot kmerize: -D/-C are not available in zotmer_b200', file=sys.stderr)
+        sys.exit(1)
+
+    (kset, nr) = kmerizeFiles(K, opts['<input>'], verbose=verbose)
+
+    with zotk.kmers(out, 'w') as z:
+        st = kset.stats()
+        h = {}
+        for (c, f) in st['hist']:       # first-occurrence order == the reference's dict order (:544-545)
+            h[c] = f
+        writeKmerSet(z, kset)
+        acgt = st['acgt_weighted']
+        n = float(sum(acgt))
+        acgt = [c / n for c in acgt]    # ZeroDivisionError on input without k-mers, as :554-555
+        z.meta['K'] = K
+        z.meta['kmers'] = 'kmers'
+        z.meta['counts'] = 'counts'
+        z.meta['hist'] = h
+        z.meta['acgt'] = acgt
+        z.meta['reads'] = nr
+    kset.free()
+
+
+if __name__ == '__main__':
+    main(sys.argv[1:])

@@ -6,6 +6,7 @@
 #include <map>
 #include <mutex>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "kernels.h"
@@ -114,11 +115,19 @@ static void flush_pending(zb_kmerizer* h) {
     ZB_CUDA(cudaMemsetAsync(h->d_count.get(), 0, 8, c->stream));
     if (n == 0) return;
     DBuf<uint64_t> tmp(c, n);
-    const int which = radix_sort(c, h->pending.get(), tmp.get(), nullptr, nullptr, n, 2 * h->k);
+    int which;
+    {
+        Stage st(c, "sort");
+        which = radix_sort(c, h->pending.get(), tmp.get(), nullptr, nullptr, n, 2 * h->k);
+    }
     const uint64_t* sorted = which ? tmp.get() : h->pending.get();
     uint64_t* other = which ? h->pending.get() : tmp.get();
     DBuf<uint32_t> dc(c, n);
-    const size_t nd = reduce_by_key(c, sorted, nullptr, n, other, dc.get());  // distinct keys -> `other`
+    size_t nd;
+    {
+        Stage st(c, "count");
+        nd = reduce_by_key(c, sorted, nullptr, n, other, dc.get());  // distinct keys -> `other`
+    }
     if (h->acc_n == 0) {
         h->acc_k.alloc(c, nd);
         h->acc_c.alloc(c, nd);
@@ -151,6 +160,7 @@ static void extract_codes(zb_kmerizer* h, const uint8_t* codes, size_t n_codes) 
         // a slice may overshoot into the next tile: bound by whole tiles
         const size_t upper = div_up(len, EXTRACT_TILE) * EXTRACT_TILE;
         ensure_pending(h, h->pending_upper + upper);
+        Stage st(c, "extract");
         extract_canonical(c, h->k, codes + off, len, h->pending.get(), h->d_count.get());
         h->pending_upper += upper;
         off += len;
@@ -168,8 +178,11 @@ static void feed_dev_impl(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is
     ZB_CUDA(cudaMemsetAsync(codes.get(), 4, 32, c->stream));
     size_t n_codes = 0;
     uint64_t n_rec = 0;
-    if (is_fasta) parse_fasta(c, d_raw, n, cd, &n_codes, &n_rec);
-    else parse_fastq(c, d_raw, n, cd, &n_codes, &n_rec);
+    {
+        Stage st(c, "parse");
+        if (is_fasta) parse_fasta(c, d_raw, n, cd, &n_codes, &n_rec);
+        else parse_fastq(c, d_raw, n, cd, &n_codes, &n_rec);
+    }
     h->n_records += n_rec;
     if (n_codes == 0) return;
     const size_t padded = div_up(n_codes, EXTRACT_TILE) * EXTRACT_TILE + 32;
@@ -247,7 +260,10 @@ int zb_kmerize_feed(zb_kmerizer* h, const uint8_t* raw, size_t n, int is_fasta) 
     Ctx* c = h->c;
     ZB_CUDA(cudaSetDevice(c->device));
     DBuf<uint8_t> d(c, n + 16);
-    ZB_CUDA(cudaMemcpyAsync(d.get(), raw, n, cudaMemcpyHostToDevice, c->stream));
+    {
+        Stage st(c, "h2d");
+        ZB_CUDA(cudaMemcpyAsync(d.get(), raw, n, cudaMemcpyHostToDevice, c->stream));
+    }
     feed_dev_impl(h, d.get(), n, is_fasta);
     ZB_CATCH
 }
@@ -280,9 +296,18 @@ int zb_kmerize_finish(zb_kmerizer* h, zb_set** result, uint64_t* n_records) {
     // both strands: mirror the canonical run, sort the mirrored half, merge
     DBuf<uint64_t> rk(c, n), rk2(c, n);
     DBuf<uint32_t> rc(c, n), rc2(c, n);
-    const size_t nm = mirror_keys(c, h->k, h->acc_k.get(), h->acc_c.get(), n, rk.get(), rc.get());
-    const int which = radix_sort(c, rk.get(), rk2.get(), rc.get(), rc2.get(), nm, 2 * h->k);
+    size_t nm;
+    int which;
+    {
+        Stage st(c, "mirror");
+        nm = mirror_keys(c, h->k, h->acc_k.get(), h->acc_c.get(), n, rk.get(), rc.get());
+    }
+    {
+        Stage st(c, "mirror_sort");
+        which = radix_sort(c, rk.get(), rk2.get(), rc.get(), rc2.get(), nm, 2 * h->k);
+    }
     zb_set* s = new_set(c, n + nm);
+    Stage st_merge(c, "mirror_merge");
     merge_pairs(c, h->acc_k.get(), h->acc_c.get(), n, which ? rk2.get() : rk.get(), which ? rc2.get() : rc.get(), nm,
                 s->k.get(), s->cnt.get());
     ZB_CUDA(cudaStreamSynchronize(c->stream));
@@ -482,6 +507,7 @@ int zb_trim(const zb_set* s, uint64_t cmin, uint64_t cmax, zb_set** out) {
     Ctx* c = s->c;
     ZB_CUDA(cudaSetDevice(c->device));
     zb_set* r = new_set(c, s->n);
+    Stage st(c, "trim");
     r->n = trim_pairs(c, s->k.get(), s->cnt.get(), s->n, cmin, cmax, r->k.get(), r->cnt.get());
     *out = r;
     ZB_CATCH
@@ -616,6 +642,53 @@ int zb_dbg_extract(int device, int k, const uint8_t* codes, size_t n, uint64_t* 
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     *n_keys = (size_t)c->h_scalars[0];
     if (keys && *n_keys) ZB_CUDA(cudaMemcpy(keys, out.get(), *n_keys * 8, cudaMemcpyDeviceToHost));
+    ZB_CATCH
+}
+
+// per-stage CUDA-event timing of everything this context runs between on=1 and the report
+int zb_dbg_profile(int device, int on, char* report, size_t cap) {
+    ZB_TRY
+    Ctx* c = ctx_for(device);
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    if (report && cap) {
+        std::map<std::string, std::pair<double, int>> agg;
+        std::vector<std::string> order;
+        for (auto& r : c->stages) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) ms = -1;
+            if (!agg.count(r.name)) order.push_back(r.name);
+            agg[r.name].first += ms;
+            agg[r.name].second += 1;
+        }
+        std::string out;
+        char line[160];
+        for (auto& nm : order) {
+            snprintf(line, sizeof line, "%s %.4f %d\n", nm.c_str(), agg[nm].first, agg[nm].second);
+            out += line;
+        }
+        snprintf(report, cap, "%s", out.c_str());
+    }
+    for (auto& r : c->stages) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    c->stages.clear();
+    c->profile = (on != 0);
+    ZB_CATCH
+}
+
+// device timer on the library stream: op 0 = start (record), op 1 = stop (record, sync, elapsed ms)
+int zb_dbg_timer(int device, int op, float* ms) {
+    ZB_TRY
+    Ctx* c = ctx_for(device);
+    static thread_local cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (!e0) { ZB_CUDA(cudaEventCreate(&e0)); ZB_CUDA(cudaEventCreate(&e1)); }
+    if (op == 0) {
+        ZB_CUDA(cudaEventRecord(e0, c->stream));
+    } else {
+        ZB_CUDA(cudaEventRecord(e1, c->stream));
+        ZB_CUDA(cudaEventSynchronize(e1));
+        float t = 0;
+        ZB_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        if (ms) *ms = t;
+    }
     ZB_CATCH
 }
 

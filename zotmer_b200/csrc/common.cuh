@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <vector>
 
 #include "../../include/zotmer_b200.h"
 
@@ -42,6 +43,29 @@ struct Ctx {
     cudaMemPool_t pool = nullptr;
     uint64_t* h_scalars = nullptr;  // pinned, 64 x u64
     uint64_t launches = 0;          // kernels launched through this context (bench "gpu_launches")
+    // optional per-stage CUDA-event timing (zb_dbg_profile): name, start, stop
+    bool profile = false;
+    struct StageRec { const char* name; cudaEvent_t e0, e1; };
+    std::vector<StageRec> stages;
+};
+
+// RAII stage marker: records events on the context stream when profiling is on (no sync).
+struct Stage {
+    Ctx* c;
+    int idx = -1;
+    Stage(Ctx* c_, const char* name) : c(c_) {
+        if (!c->profile) return;
+        Ctx::StageRec r;
+        r.name = name;
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, c->stream);
+        idx = (int)c->stages.size();
+        c->stages.push_back(r);
+    }
+    ~Stage() {
+        if (idx >= 0) cudaEventRecord(c->stages[idx].e1, c->stream);
+    }
 };
 
 Ctx* ctx_for(int device);

@@ -254,6 +254,7 @@ static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uin
     ZB_CUDA(cudaMemsetAsync(ticket.get(), 0, MAX_PASSES * 4, c->stream));
 
     {
+        Stage st_h(c, "sort_hist");
         int blocks = (int)std::min<size_t>((size_t)c->sm_count * 4, div_up(n, 512 * 2 * 4));
         if (blocks < 1) blocks = 1;
         size_t sm = (size_t)plan.passes * BINS * 4;
@@ -274,6 +275,7 @@ static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uin
     int cur = 0;
     for (int p = 0; p < plan.passes; p++) {
         ZB_CUDA(cudaMemsetAsync(status.get(), 0, (size_t)tiles * BINS * 4, c->stream));
+        Stage st_p(c, vals ? "sort_pass_pairs" : "sort_pass_keys");
         if (vals)
             onesweep_kernel<BINS, true><<<tiles, SORT_THREADS, sm, c->stream>>>(
                 kb[cur], kb[cur ^ 1], vb[cur], vb[cur ^ 1], (uint32_t)n, plan.shift[p], plan.bits[p],

@@ -1,0 +1,75 @@
+"""
+Stream files inside a casket: 'kmers' = delta + codec64, 'counts' = codec64 (mirrors
+zotmer/library/files.py:54-227).  The reference codes value by value in Python (54 % of its
+kmerize time); here whole streams go through libzot_b200 (zb_encode/zb_decode, zb_set_encode,
+zb_set_from_streams) and k-mer sets stay on the device between decode and use.
+"""
+import numpy as np
+
+from zotmer_b200 import _native
+
+
+def readWords(f):
+    """files.py:54-63: the blob as little-endian u64 words (AssertionError on a ragged blob)."""
+    s = f.read()
+    assert (len(s) & 7) == 0
+    return np.frombuffer(s, dtype='<u8')
+
+
+def writeWords(f, ws):
+    """files.py:65-83"""
+    f.write(np.ascontiguousarray(ws, dtype='<u8').tobytes())
+    return len(ws)
+
+
+def _names(nm):
+    return ('kmers', 'counts') if nm is None else (nm + '-kmers', nm + '-counts')
+
+
+def readKmers(z, nm='kmers', device=0):
+    """files.py:152-153 -> uint64 array"""
+    return _native.decode_stream(readWords(z.open(nm)), delta=True, device=device)
+
+
+def readCounts(z, nm='counts', device=0):
+    """files.py:158-159 -> uint64 array"""
+    return _native.decode_stream(readWords(z.open(nm)), delta=False, device=device)
+
+
+def readKmersAndCounts(z, nm=None, device=0):
+    """files.py:219-227 -> (kmers, counts) arrays; AssertionError when the lengths differ (files.py:182)"""
+    xNm, cNm = _names(nm)
+    xs = readKmers(z, xNm, device)
+    cs = readCounts(z, cNm, device)
+    assert len(xs) == len(cs)
+    return xs, cs
+
+
+def readKmerSet(z, nm=None, counts=True, device=0):
+    """Device-resident form of readKmersAndCounts / readKmers: -> _native.KmerSet"""
+    xNm, cNm = _names(nm)
+    kw = readWords(z.open(xNm))
+    cw = readWords(z.open(cNm)) if counts else None
+    return _native.KmerSet.from_streams(kw, cw, device=device)
+
+
+def writeKmerSet(z, kset, nm=None):
+    """files.py:195-217 (writeKmersAndCounts / writeKmersAndCounts2) from a device-resident set."""
+    xNm, cNm = _names(nm)
+    kw, cw = kset.encode()
+    with z.add_stream(xNm) as f:
+        writeWords(f, kw)
+    with z.add_stream(cNm) as f:
+        writeWords(f, cw)
+
+
+def writeKmersAndCounts2(z, xs, cs, nm=None, device=0):
+    """files.py:209-217 from host arrays."""
+    xNm, cNm = _names(nm)
+    with z.add_stream(xNm) as f:
+        writeWords(f, _native.encode_stream(xs, delta=True, device=device))
+    with z.add_stream(cNm) as f:
+        writeWords(f, _native.encode_stream(cs, delta=False, device=device))
+
+
+writeKmersAndCounts = writeKmersAndCounts2
