@@ -18,13 +18,14 @@ static constexpr int ST_TILE = ST_THREADS * ST_ITEMS;  // 4096 elements per CTA
 // every global access is a fully coalesced 2 KB row.  Chained scan carries (#heads, weight sum).
 // Reference: zotmer/commands/kmerize.py:41-132 (merge = RLE of the sorted buffer, counts summed).
 // ---------------------------------------------------------------------------------------------
+template <bool WEIGHTED>
 __global__ void __launch_bounds__(ST_THREADS)
 rbk_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ w, uint64_t n,
            uint64_t* __restrict__ out_k, uint64_t* __restrict__ out_start, uint64_t* __restrict__ st_heads,
            uint64_t* __restrict__ st_wsum, uint32_t* __restrict__ ticket, uint64_t* __restrict__ totals) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_rowhead[ST_ITEMS][ST_THREADS / 32];  // heads per (row, warp)
-    __shared__ uint64_t s_rowsum[ST_ITEMS][ST_THREADS / 32];   // weight per (row, warp)
+    __shared__ uint64_t s_rowsum[ST_ITEMS][ST_THREADS / 32];   // weight per (row, warp) (WEIGHTED only)
     __shared__ uint64_t s_pref[2];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
@@ -40,14 +41,17 @@ rbk_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ w, ui
         const uint64_t i = base + (uint64_t)j * ST_THREADS + tid;
         const bool in = i < n;
         key[j] = in ? __ldg(keys + i) : 0;
-        wt[j] = in ? (w ? __ldg(w + i) : 1u) : 0u;
+        if (WEIGHTED) wt[j] = in ? __ldg(w + i) : 0u;
         uint64_t prev = __shfl_up_sync(0xffffffffu, key[j], 1);
         if (lane == 0 && in && i > 0) prev = __ldg(keys + i - 1);
         const bool head = in && (i == 0 || prev != key[j]);
         headbits |= (head ? 1u : 0u) << j;
         const unsigned b = __ballot_sync(0xffffffffu, head);
-        const uint64_t ws = warp_sum<uint64_t>(wt[j]);
-        if (lane == 0) { s_rowhead[j][warp] = __popc(b); s_rowsum[j][warp] = ws; }
+        if (WEIGHTED) {
+            const uint64_t ws = warp_sum<uint64_t>(wt[j]);
+            if (lane == 0) s_rowsum[j][warp] = ws;
+        }
+        if (lane == 0) s_rowhead[j][warp] = __popc(b);
     }
     __syncthreads();
     // exclusive scan over the 16 x 8 (row, warp) cells in position order, by warp 0
@@ -61,30 +65,32 @@ rbk_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ w, ui
         for (int q = 0; q < CELLS / 32; q++) {
             const int cell = lane * (CELLS / 32) + q;
             h[q] = (&s_rowhead[0][0])[cell];
-            s[q] = (&s_rowsum[0][0])[cell];
             hs += h[q];
-            ss += s[q];
+            if (WEIGHTED) { s[q] = (&s_rowsum[0][0])[cell]; ss += s[q]; }
         }
         uint32_t hi = warp_incl_scan(hs);
-        uint64_t si = warp_incl_scan(ss);
         const uint32_t htot = __shfl_sync(0xffffffffu, hi, 31);
-        const uint64_t stot = __shfl_sync(0xffffffffu, si, 31);
         uint32_t he = hi - hs;
-        uint64_t se = si - ss;
+        uint64_t si = 0, stot = 0, se = 0;
+        if (WEIGHTED) {
+            si = warp_incl_scan(ss);
+            stot = __shfl_sync(0xffffffffu, si, 31);
+            se = si - ss;
+        }
 #pragma unroll
         for (int q = 0; q < CELLS / 32; q++) {
             const int cell = lane * (CELLS / 32) + q;
             (&s_rowhead[0][0])[cell] = he;
-            (&s_rowsum[0][0])[cell] = se;
             he += h[q];
-            se += s[q];
+            if (WEIGHTED) { (&s_rowsum[0][0])[cell] = se; se += s[q]; }
         }
         const uint64_t ph = lookback_u64(st_heads, tile, htot);
-        const uint64_t pw = lookback_u64(st_wsum, tile, stot);
+        uint64_t pw = 0;
+        if (WEIGHTED) pw = lookback_u64(st_wsum, tile, stot);
         if (lane == 0) {
             s_pref[0] = ph;
             s_pref[1] = pw;
-            if (base + ST_TILE >= n) { totals[0] = ph + htot; totals[1] = pw + stot; }
+            if (base + ST_TILE >= n) { totals[0] = ph + htot; totals[1] = WEIGHTED ? pw + stot : n; }
         }
     }
     __syncthreads();
@@ -93,11 +99,13 @@ rbk_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ w, ui
     for (int j = 0; j < ST_ITEMS; j++) {
         const bool head = (headbits >> j) & 1u;
         const unsigned b = __ballot_sync(0xffffffffu, head);
-        const uint64_t wi = warp_incl_scan<uint64_t>(wt[j]);
+        uint64_t wi = 0;
+        if (WEIGHTED) wi = warp_incl_scan<uint64_t>(wt[j]);
         if (head) {
             const uint64_t hidx = ph + s_rowhead[j][warp] + __popc(b & lanemask_lt());
             out_k[hidx] = key[j];
-            out_start[hidx] = pw + s_rowsum[j][warp] + (wi - wt[j]);
+            // start of the run in the (weighted) prefix space; unweighted: simply its position
+            out_start[hidx] = WEIGHTED ? (pw + s_rowsum[j][warp] + (wi - wt[j])) : (base + (uint64_t)j * ST_THREADS + tid);
         }
     }
 }
@@ -123,7 +131,10 @@ size_t reduce_by_key(Ctx* c, const uint64_t* keys, const uint32_t* w, size_t n, 
     uint64_t* totals = status.get() + 2 * (size_t)tiles;      // [0]=heads [1]=weight
     uint32_t* ticket = reinterpret_cast<uint32_t*>(totals + 2);  // zeroed
     unsigned int* err = reinterpret_cast<unsigned int*>(totals + 3);
-    rbk_kernel<<<tiles, ST_THREADS, 0, c->stream>>>(keys, w, n, out_k, start.get(), st_heads, st_wsum, ticket, totals);
+    if (w)
+        rbk_kernel<true><<<tiles, ST_THREADS, 0, c->stream>>>(keys, w, n, out_k, start.get(), st_heads, st_wsum, ticket, totals);
+    else
+        rbk_kernel<false><<<tiles, ST_THREADS, 0, c->stream>>>(keys, w, n, out_k, start.get(), st_heads, st_wsum, ticket, totals);
     ZB_LAUNCH_CHECK(c);
     ZB_CUDA(cudaMemcpyAsync(c->h_scalars, totals, 16, cudaMemcpyDeviceToHost, c->stream));
     ZB_CUDA(cudaStreamSynchronize(c->stream));

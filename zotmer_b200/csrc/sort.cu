@@ -121,22 +121,27 @@ onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, c
         key[j] = (idx < n_valid) ? __ldg(kin + tile_base + idx) : ~0ull;
     }
 
-    // ---- stable rank inside the warp: lanes holding the same digit form a group, the lowest lane
-    // bumps the warp's counter of that digit by the group size.
+    // ---- stable rank inside the warp: lanes holding the same digit form a group (found with one
+    // ballot per digit bit -- MATCH.ANY is microcoded on sm_100 and saturates the XU pipe, see
+    // profiles/); every lane reads the warp's counter of its digit, the lowest lane of the group
+    // bumps it by the group size.
     uint16_t rnk[SORT_ITEMS];
     uint32_t* myhist = whist + warp * BINS;
     const unsigned lt = lanemask_lt();
+    constexpr int LOG_BINS = (BINS == 256) ? 8 : (BINS == 512) ? 9 : (BINS == 1024) ? 10 : 11;
 #pragma unroll
     for (int j = 0; j < SORT_ITEMS; j++) {
         const uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
-        const unsigned m = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(m) - 1;
-        uint32_t old = 0;
-        if ((int)lane == leader) {
-            old = myhist[d];
-            myhist[d] = old + __popc(m);
+        unsigned m = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < LOG_BINS; b++) {   // bits above `bits` are 0 in every lane: no effect
+            const bool bit = (d >> b) & 1u;
+            const unsigned v = __ballot_sync(0xffffffffu, bit);
+            m &= bit ? v : ~v;
         }
-        old = __shfl_sync(0xffffffffu, old, leader);
+        const uint32_t old = myhist[d];
+        __syncwarp();
+        if ((m & lt) == 0) myhist[d] = old + __popc(m);
         rnk[j] = (uint16_t)(old + __popc(m & lt));
         __syncwarp();
     }
