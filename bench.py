@@ -283,11 +283,19 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     barrier()
+    nat.dbg_profile(True, dev)
     e0 = time.perf_counter()
+    e_times = []
     for _ in range(args.steps):
+        t_it = time.perf_counter()
         nk, st = step_e2e()
+        e_times.append((time.perf_counter() - t_it) * 1e3)
     barrier()
     e2e_ms = (time.perf_counter() - e0) * 1e3 / args.steps
+    e_prof = nat.dbg_profile(False, dev)
+    if rank == 0:
+        print("e2e per-step wall ms: %s; stage ms/step: %s" % (
+            [round(x, 1) for x in e_times], {k: round(v[0] / args.steps, 3) for k, v in e_prof.items()}), file=sys.stderr)
 
     # ---------------- reduce over ranks (max time), aggregate throughput
     per_step_ms = ms_dev / args.steps   # CUDA events on the library stream around the K steps

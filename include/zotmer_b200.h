@@ -47,6 +47,8 @@ int zb_device_count(int* n);
 /* number of kernels this library has launched on `device` from the calling thread (bench "gpu_launches") */
 int zb_launch_count(int device, uint64_t* n);
 int zb_device_sync(int device);
+/* give the device memory cached by the library (freed sets, scratch) back to the driver */
+int zb_release_cache(int device);
 
 /* ------------------------------------------------------------------------------------------
  * kmerize + count          replaces zotmer/commands/kmerize.py:463-545

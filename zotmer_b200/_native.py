@@ -28,6 +28,7 @@ SIGNATURES = {
     "zb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "zb_launch_count": (C.c_int, [C.c_int, u64p]),
     "zb_device_sync": (C.c_int, [C.c_int]),
+    "zb_release_cache": (C.c_int, [C.c_int]),
     "zb_kmerize_open": (C.c_int, [C.c_int, C.c_int, C.POINTER(vp)]),
     "zb_kmerize_feed": (C.c_int, [vp, vp, C.c_size_t, C.c_int]),
     "zb_kmerize_feed_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_int]),

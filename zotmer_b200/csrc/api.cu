@@ -43,12 +43,65 @@ Ctx* ctx_for(int device) {
     ZB_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     ZB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    ZB_CUDA(cudaDeviceGetDefaultMemPool(&c->pool, device));
-    uint64_t keep = ~0ull;  // never give pages back: batches reuse them
-    ZB_CUDA(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
     ZB_CUDA(cudaMallocHost((void**)&c->h_scalars, 64 * sizeof(uint64_t)));
     g_ctx[device] = c;
     return c;
+}
+
+static size_t round_block(size_t b) {
+    if (b < 512) return 512;
+    if (b < ((size_t)1 << 20)) return (b + 511) & ~(size_t)511;
+    // large blocks: multiples of 1/8 of the enclosing power of two (<= 12.5 % slack), at least 2 MiB steps
+    size_t p2 = (size_t)1 << (63 - __builtin_clzll(b));
+    size_t step = std::max<size_t>(p2 >> 3, (size_t)2 << 20);
+    return (b + step - 1) / step * step;
+}
+
+void* dalloc(Ctx* c, size_t bytes) {
+    const size_t want = round_block(bytes);
+    auto it = c->free_blocks.lower_bound(want);
+    if (it != c->free_blocks.end() && it->first <= want + want / 4) {
+        void* p = it->second;
+        const size_t sz = it->first;
+        c->free_blocks.erase(it);
+        c->cached_bytes -= sz;
+        c->live_blocks[p] = sz;
+        c->live_bytes += sz;
+        return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaStreamSynchronize(c->stream);
+        dtrim(c);
+        e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("out of device memory: %zu bytes requested, %zu live", want, c->live_bytes);
+        throw Fail{ZB_E_NOMEM};
+    }
+    c->live_blocks[p] = want;
+    c->live_bytes += want;
+    return p;
+}
+
+void dfree(Ctx* c, void* p) {
+    if (!p) return;
+    auto it = c->live_blocks.find(p);
+    if (it == c->live_blocks.end()) return;
+    const size_t sz = it->second;
+    c->live_blocks.erase(it);
+    c->live_bytes -= sz;
+    c->free_blocks.insert({sz, p});
+    c->cached_bytes += sz;
+}
+
+void dtrim(Ctx* c) {
+    for (auto& kv : c->free_blocks) cudaFree(kv.second);
+    c->free_blocks.clear();
+    c->cached_bytes = 0;
 }
 
 }  // namespace zb
@@ -215,6 +268,14 @@ int zb_device_count(int* n) {
 int zb_launch_count(int device, uint64_t* n) {
     ZB_TRY
     *n = ctx_for(device)->launches;
+    ZB_CATCH
+}
+
+int zb_release_cache(int device) {
+    ZB_TRY
+    Ctx* c = ctx_for(device);
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    dtrim(c);
     ZB_CATCH
 }
 

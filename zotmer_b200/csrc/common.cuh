@@ -4,7 +4,9 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/zotmer_b200.h"
@@ -44,6 +46,10 @@ struct Ctx {
     uint64_t* h_scalars = nullptr;  // pinned, 64 x u64
     uint64_t launches = 0;          // kernels launched through this context (bench "gpu_launches")
     // optional per-stage CUDA-event timing (zb_dbg_profile): name, start, stop
+    // caching allocator state
+    std::multimap<size_t, void*> free_blocks;
+    std::unordered_map<void*, size_t> live_blocks;
+    size_t cached_bytes = 0, live_bytes = 0;
     bool profile = false;
     struct StageRec { const char* name; cudaEvent_t e0, e1; };
     std::vector<StageRec> stages;
@@ -70,15 +76,14 @@ struct Stage {
 
 Ctx* ctx_for(int device);
 
-inline void* dalloc(Ctx* c, size_t bytes) {
-    void* p = nullptr;
-    if (bytes == 0) bytes = 16;
-    ZB_CUDA(cudaMallocAsync(&p, bytes, c->stream));
-    return p;
-}
-inline void dfree(Ctx* c, void* p) {
-    if (p) cudaFreeAsync(p, c->stream);
-}
+// Device memory comes from a per-context caching allocator (api.cu): blocks are cudaMalloc'ed once,
+// kept in a size-ordered free list and handed out again on the next request of a similar size.  All
+// work of a context is ordered on its one stream, so a block freed by the host can be reused by the
+// next kernel without synchronisation.  (cudaMallocAsync pools showed 100-600 ms stalls when a
+// 1 GB block had to be re-mapped between steps.)
+void* dalloc(Ctx* c, size_t bytes);
+void dfree(Ctx* c, void* p);
+void dtrim(Ctx* c);  // give every cached block back to the driver
 
 // RAII device buffer bound to a context's stream/pool
 template <typename T>

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(BINS > 1024 ? 1024 : BINS) sort_scan_kernel(ui
 #define ST32_VAL 0x3fffffffu
 
 template <int BINS, bool HAS_VALS>
-__global__ void __launch_bounds__(SORT_THREADS, (BINS <= 256 ? 3 : 2))
+__global__ void __launch_bounds__(SORT_THREADS, (BINS <= 256 ? 4 : 2))
 onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const uint32_t* __restrict__ vin,
                 uint32_t* __restrict__ vout, uint32_t n, int shift, int bits,
                 const uint32_t* __restrict__ bin_start /*[BINS] global exclusive*/,
@@ -98,15 +98,27 @@ onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, c
     uint32_t* whist = svals + (HAS_VALS ? SORT_TILE : 0);                          // [WARPS][BINS]
     uint32_t* s_binstart = whist + SORT_WARPS * BINS;                              // [BINS] start inside the tile
     uint32_t* s_goff = s_binstart + BINS;                                          // [BINS] global pos - tile pos
+    // match masks [2][WARPS][BINS] live in the key staging area, which is idle while keys are ranked
+    uint32_t* mmask = reinterpret_cast<uint32_t*>(smem_raw);
+    static_assert(2 * SORT_WARPS * BINS * 4 <= SORT_TILE * 8 || BINS > 256, "mask area");
     __shared__ uint32_t s_scan[SORT_THREADS / 32 + 1];
     __shared__ uint32_t s_tile;
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t dmask = (1u << bits) - 1u;
     const int nbins = 1 << bits;
+    constexpr bool ATOMIC_MATCH = (2 * SORT_WARPS * BINS * 4 <= SORT_TILE * 8);
 
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < SORT_WARPS * BINS; i += SORT_THREADS) whist[i] = 0;
+    {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        uint4* w4 = reinterpret_cast<uint4*>(whist);
+        for (int i = tid; i < SORT_WARPS * BINS / 4; i += SORT_THREADS) w4[i] = z;
+        if (ATOMIC_MATCH) {
+            uint4* m4 = reinterpret_cast<uint4*>(mmask);
+            for (int i = tid; i < 2 * SORT_WARPS * BINS / 4; i += SORT_THREADS) m4[i] = z;
+        }
+    }
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t tile_base = tile * SORT_TILE;
@@ -121,29 +133,48 @@ onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, c
         key[j] = (idx < n_valid) ? __ldg(kin + tile_base + idx) : ~0ull;
     }
 
-    // ---- stable rank inside the warp: lanes holding the same digit form a group (found with one
-    // ballot per digit bit -- MATCH.ANY is microcoded on sm_100 and saturates the XU pipe, see
-    // profiles/); every lane reads the warp's counter of its digit, the lowest lane of the group
-    // bumps it by the group size.
+    // ---- stable rank inside the warp.  Lanes holding the same digit form a group; the group mask is
+    // built by OR-ing lane bits into a per-(warp,digit) shared word (one ATOMS per key; MATCH.ANY is
+    // microcoded on sm_100 and a ballot per digit bit costs ~40 instructions per key, see profiles/).
+    // Every lane reads the warp's running count of its digit, the lowest lane of the group bumps it.
     uint16_t rnk[SORT_ITEMS];
     uint32_t* myhist = whist + warp * BINS;
     const unsigned lt = lanemask_lt();
-    constexpr int LOG_BINS = (BINS == 256) ? 8 : (BINS == 512) ? 9 : (BINS == 1024) ? 10 : 11;
+    const uint32_t lanebit = 1u << lane;
+    if (ATOMIC_MATCH) {
 #pragma unroll
-    for (int j = 0; j < SORT_ITEMS; j++) {
-        const uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
-        unsigned m = 0xffffffffu;
-#pragma unroll
-        for (int b = 0; b < LOG_BINS; b++) {   // bits above `bits` are 0 in every lane: no effect
-            const bool bit = (d >> b) & 1u;
-            const unsigned v = __ballot_sync(0xffffffffu, bit);
-            m &= bit ? v : ~v;
+        for (int j = 0; j < SORT_ITEMS; j++) {
+            const uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
+            uint32_t* mm = mmask + ((j & 1) * SORT_WARPS + warp) * BINS + d;   // double-buffered
+            atomicOr(mm, lanebit);
+            __syncwarp();
+            const uint32_t m = *mm;
+            const uint32_t old = myhist[d];
+            __syncwarp();
+            if ((m & lt) == 0) {
+                *mm = 0;
+                myhist[d] = old + __popc(m);
+            }
+            rnk[j] = (uint16_t)(old + __popc(m & lt));
         }
-        const uint32_t old = myhist[d];
-        __syncwarp();
-        if ((m & lt) == 0) myhist[d] = old + __popc(m);
-        rnk[j] = (uint16_t)(old + __popc(m & lt));
-        __syncwarp();
+    } else {
+        constexpr int LOG_BINS = (BINS == 256) ? 8 : (BINS == 512) ? 9 : (BINS == 1024) ? 10 : 11;
+#pragma unroll
+        for (int j = 0; j < SORT_ITEMS; j++) {
+            const uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
+            unsigned m = 0xffffffffu;
+#pragma unroll
+            for (int b = 0; b < LOG_BINS; b++) {
+                const bool bit = (d >> b) & 1u;
+                const unsigned v = __ballot_sync(0xffffffffu, bit);
+                m &= bit ? v : ~v;
+            }
+            const uint32_t old = myhist[d];
+            __syncwarp();
+            if ((m & lt) == 0) myhist[d] = old + __popc(m);
+            rnk[j] = (uint16_t)(old + __popc(m & lt));
+            __syncwarp();
+        }
     }
     __syncthreads();
 
