@@ -126,19 +126,21 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
     uint64_t v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// status words of the chained scans: GPU-scope relaxed accesses (served by L2; `ld.volatile` compiles
+// to .STRONG.SYS, system scope, which is slower to poll)
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     uint32_t v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // streaming (read-once) 128-bit load / store that do not pollute L1
@@ -169,7 +171,7 @@ __device__ __forceinline__ T warp_incl_scan(T v) {
 
 // Block-wide exclusive scan of one value per thread.  THREADS multiple of 32, <= 1024.
 // `smem` needs THREADS/32 + 1 elements.  Returns exclusive prefix; *total gets the block sum.
-template <int THREADS, typename T>
+template <int THREADS, typename T, bool TRAILING_SYNC = true>
 __device__ __forceinline__ T block_excl_scan(T v, T* smem, T* total) {
     const unsigned l = lane_id(), w = threadIdx.x >> 5;
     T inc = warp_incl_scan(v);
@@ -184,7 +186,7 @@ __device__ __forceinline__ T block_excl_scan(T v, T* smem, T* total) {
     __syncthreads();
     T r = smem[w] + inc - v;
     *total = smem[THREADS / 32];
-    __syncthreads();
+    if (TRAILING_SYNC) __syncthreads();   // only needed when `smem` is reused by a later call
     return r;
 }
 

@@ -17,11 +17,11 @@ namespace zb {
 
 int g_sort_max_bits = 8;
 
-static constexpr int SORT_THREADS = 256;
-static constexpr int SORT_WARPS = SORT_THREADS / 32;
 static constexpr int SORT_ITEMS = 16;
-static constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys = 32 KB
 static constexpr int MAX_PASSES = 8;
+// threads per CTA for a given digit width: the tile (threads x 16 keys) grows with the number of bins so
+// that the per-digit work (warp prefix, chained scan) per key stays constant
+template <int BINS> struct SortCfg { static constexpr int THREADS = (BINS <= 256) ? 256 : 512; };
 
 struct SortPlan {
     int passes;
@@ -86,18 +86,19 @@ __global__ void __launch_bounds__(BINS > 1024 ? 1024 : BINS) sort_scan_kernel(ui
 #define ST32_PFX 0x80000000u
 #define ST32_VAL 0x3fffffffu
 
-template <int BINS, bool HAS_VALS>
-__global__ void __launch_bounds__(SORT_THREADS, (BINS <= 256 ? 4 : 2))
+template <int BINS, int SORT_THREADS, bool HAS_VALS>
+__global__ void __launch_bounds__(SORT_THREADS, (SORT_THREADS * (BINS <= 512 ? 64 : 128) <= 16384 ? 4 : 2))
 onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const uint32_t* __restrict__ vin,
                 uint32_t* __restrict__ vout, uint32_t n, int shift, int bits,
                 const uint32_t* __restrict__ bin_start /*[BINS] global exclusive*/,
                 uint32_t* __restrict__ status /*[tiles][BINS], zeroed*/, uint32_t* __restrict__ ticket) {
+    constexpr int SORT_WARPS = SORT_THREADS / 32;
+    constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw);                       // [TILE]
     uint32_t* svals = reinterpret_cast<uint32_t*>(skeys + SORT_TILE);              // [TILE] (if HAS_VALS)
     uint32_t* whist = svals + (HAS_VALS ? SORT_TILE : 0);                          // [WARPS][BINS]
-    uint32_t* s_binstart = whist + SORT_WARPS * BINS;                              // [BINS] start inside the tile
-    uint32_t* s_goff = s_binstart + BINS;                                          // [BINS] global pos - tile pos
+    uint32_t* s_goff = whist + SORT_WARPS * BINS;                                  // [BINS] global pos - tile pos
     // match masks [2][WARPS][BINS] live in the key staging area, which is idle while keys are ranked
     uint32_t* mmask = reinterpret_cast<uint32_t*>(smem_raw);
     static_assert(2 * SORT_WARPS * BINS * 4 <= SORT_TILE * 8 || BINS > 256, "mask area");
@@ -133,12 +134,54 @@ onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, c
         key[j] = (idx < n_valid) ? __ldg(kin + tile_base + idx) : ~0ull;
     }
 
-    // ---- stable rank inside the warp.  Lanes holding the same digit form a group; the group mask is
-    // built by OR-ing lane bits into a per-(warp,digit) shared word (one ATOMS per key; MATCH.ANY is
-    // microcoded on sm_100 and a ballot per digit bit costs ~40 instructions per key, see profiles/).
-    // Every lane reads the warp's running count of its digit, the lowest lane of the group bumps it.
-    uint16_t rnk[SORT_ITEMS];
+    // ---- (1) early counts: per-warp digit histogram with one shared-memory atomic per key, so that
+    // the tile's aggregate can be published BEFORE the (long) ranking phase and the chained scan of
+    // the following tiles never has to wait for it.
     uint32_t* myhist = whist + warp * BINS;
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; j++) atomicAdd(&myhist[(uint32_t)(key[j] >> shift) & dmask], 1u);
+    __syncthreads();
+
+    // ---- (2) per digit: exclusive prefix over warps -> tile count, publish it, tile-local bin starts
+    constexpr int PER = (BINS + SORT_THREADS - 1) / SORT_THREADS;  // digits per thread (blocked)
+    uint32_t cnt[PER], binst[PER];
+    uint32_t csum = 0;
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+        const int d = tid * PER + q;
+        uint32_t s = 0;
+        if (d < nbins) {
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; w++) {
+                uint32_t c = whist[w * BINS + d];
+                whist[w * BINS + d] = s;
+                s += c;
+            }
+            st_volatile_u32(status + (size_t)tile * BINS + d, (tile == 0 ? ST32_PFX : ST32_AGG) | s);
+        }
+        cnt[q] = s;
+        csum += s;
+    }
+    uint32_t tot;
+    uint32_t ex = block_excl_scan<SORT_THREADS, uint32_t, false>(csum, s_scan, &tot);
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+        const int d = tid * PER + q;
+        binst[q] = ex;
+        if (d < nbins) {
+            // the per-(warp,digit) words become running cursors = position inside the sorted tile
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; w++) whist[w * BINS + d] += ex;
+        }
+        ex += cnt[q];
+    }
+    __syncthreads();
+
+    // ---- (3) stable rank inside the warp.  Lanes holding the same digit form a group; the group mask
+    // is built by OR-ing lane bits into a per-(warp,digit) shared word (one ATOMS per key; MATCH.ANY is
+    // microcoded on sm_100 and a ballot per digit bit costs ~40 instructions per key, see profiles/).
+    // Every lane reads the cursor of its (warp,digit), the lowest lane of the group advances it.
+    uint16_t pos[SORT_ITEMS];
     const unsigned lt = lanemask_lt();
     const uint32_t lanebit = 1u << lane;
     if (ATOMIC_MATCH) {
@@ -149,13 +192,13 @@ onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, c
             atomicOr(mm, lanebit);
             __syncwarp();
             const uint32_t m = *mm;
-            const uint32_t old = myhist[d];
+            const uint32_t cur = myhist[d];
             __syncwarp();
             if ((m & lt) == 0) {
                 *mm = 0;
-                myhist[d] = old + __popc(m);
+                myhist[d] = cur + __popc(m);
             }
-            rnk[j] = (uint16_t)(old + __popc(m & lt));
+            pos[j] = (uint16_t)(cur + __popc(m & lt));
         }
     } else {
         constexpr int LOG_BINS = (BINS == 256) ? 8 : (BINS == 512) ? 9 : (BINS == 1024) ? 10 : 11;
@@ -169,74 +212,52 @@ onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, c
                 const unsigned v = __ballot_sync(0xffffffffu, bit);
                 m &= bit ? v : ~v;
             }
-            const uint32_t old = myhist[d];
+            const uint32_t cur = myhist[d];
             __syncwarp();
-            if ((m & lt) == 0) myhist[d] = old + __popc(m);
-            rnk[j] = (uint16_t)(old + __popc(m & lt));
+            if ((m & lt) == 0) myhist[d] = cur + __popc(m);
+            pos[j] = (uint16_t)(cur + __popc(m & lt));
             __syncwarp();
         }
     }
-    __syncthreads();
 
-    // ---- per digit: exclusive prefix over warps, tile count
-    constexpr int PER = (BINS + SORT_THREADS - 1) / SORT_THREADS;  // digits per thread (blocked)
-    uint32_t cnt[PER];
-    uint32_t csum = 0;
-#pragma unroll
-    for (int q = 0; q < PER; q++) {
-        const int d = tid * PER + q;
-        uint32_t s = 0;
-        if (d < nbins) {
-#pragma unroll
-            for (int w = 0; w < SORT_WARPS; w++) {
-                uint32_t c = whist[w * BINS + d];
-                whist[w * BINS + d] = s;
-                s += c;
-            }
-        }
-        cnt[q] = s;
-        csum += s;
-    }
-    uint32_t tot;
-    uint32_t ex = block_excl_scan<SORT_THREADS, uint32_t>(csum, s_scan, &tot);
-
-    // ---- chained scan across tiles, one status word per (tile, digit)
+    // ---- (4) chained scan across tiles, one status word per (tile, digit); predecessors published
+    // their aggregates before their own ranking phase, so this rarely spins.
 #pragma unroll
     for (int q = 0; q < PER; q++) {
         const int d = tid * PER + q;
         if (d < nbins) {
-            s_binstart[d] = ex;
             uint32_t* st = status + (size_t)tile * BINS + d;
             uint32_t excl = 0;
-            if (tile == 0) {
-                st_volatile_u32(st, ST32_PFX | cnt[q]);
-            } else {
-                st_volatile_u32(st, ST32_AGG | cnt[q]);
-                const uint32_t* p = st - BINS;
-                while (true) {
-                    uint32_t v;
-                    do { v = ld_volatile_u32(p); } while ((v & (ST32_AGG | ST32_PFX)) == 0);
-                    excl += v & ST32_VAL;
-                    if (v & ST32_PFX) break;
-                    p -= BINS;
+            if (tile != 0) {
+                // walk back over the predecessors, LB_W status words in flight at a time
+                constexpr int LB_W = 4;
+                int64_t p = (int64_t)tile - 1;
+                bool done = false;
+                while (!done) {
+                    uint32_t v[LB_W];
+#pragma unroll
+                    for (int u = 0; u < LB_W; u++)
+                        v[u] = (p - u >= 0) ? ld_volatile_u32(st - (size_t)(tile - (p - u)) * BINS) : ST32_PFX;
+#pragma unroll
+                    for (int u = 0; u < LB_W; u++) {
+                        if (!done) {
+                            if ((v[u] & (ST32_AGG | ST32_PFX)) == 0) break;   // not published yet: poll again from here
+                            excl += v[u] & ST32_VAL;
+                            p--;
+                            if (v[u] & ST32_PFX) done = true;
+                        }
+                    }
                 }
                 st_volatile_u32(st, ST32_PFX | (excl + cnt[q]));
             }
-            s_goff[d] = bin_start[d] + excl - ex;
-            ex += cnt[q];
+            s_goff[d] = bin_start[d] + excl - binst[q];
         }
     }
-    __syncthreads();
+    __syncthreads();   // masks are dead from here on: the staging area now receives the keys
 
-    // ---- place into tile-sorted order in shared memory
-    uint16_t pos[SORT_ITEMS];
+    // ---- (5) place into tile-sorted order in shared memory
 #pragma unroll
-    for (int j = 0; j < SORT_ITEMS; j++) {
-        const uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
-        const uint32_t p = s_binstart[d] + myhist[d] + rnk[j];
-        pos[j] = (uint16_t)p;
-        skeys[p] = key[j];
-    }
+    for (int j = 0; j < SORT_ITEMS; j++) skeys[pos[j]] = key[j];
     if (HAS_VALS) {
 #pragma unroll
         for (int j = 0; j < SORT_ITEMS; j++) {
@@ -262,7 +283,10 @@ onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, c
 
 template <int BINS>
 static size_t onesweep_smem(bool vals) {
-    return (size_t)SORT_TILE * 8 + (vals ? (size_t)SORT_TILE * 4 : 0) + (size_t)SORT_WARPS * BINS * 4 + 2 * BINS * 4;
+    constexpr int SORT_THREADS = SortCfg<BINS>::THREADS;
+    constexpr int SORT_WARPS = SORT_THREADS / 32;
+    constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+    return (size_t)SORT_TILE * 8 + (vals ? (size_t)SORT_TILE * 4 : 0) + (size_t)SORT_WARPS * BINS * 4 + BINS * 4;
 }
 
 template <int BINS>
@@ -281,6 +305,8 @@ static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uin
             sh += plan.bits[p];
         }
     }
+    constexpr int SORT_THREADS = SortCfg<BINS>::THREADS;
+    constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     const bool vals = (v0 != nullptr);
     const uint32_t tiles = (uint32_t)div_up(n, SORT_TILE);
     DBuf<uint32_t> ghist(c, (size_t)plan.passes * BINS);
@@ -303,9 +329,9 @@ static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uin
     }
     size_t sm = onesweep_smem<BINS>(vals);
     if (vals)
-        ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     else
-        ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     uint64_t* kb[2] = {k0, k1};
     uint32_t* vb[2] = {v0, v1};
     int cur = 0;
@@ -313,11 +339,11 @@ static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uin
         ZB_CUDA(cudaMemsetAsync(status.get(), 0, (size_t)tiles * BINS * 4, c->stream));
         Stage st_p(c, vals ? "sort_pass_pairs" : "sort_pass_keys");
         if (vals)
-            onesweep_kernel<BINS, true><<<tiles, SORT_THREADS, sm, c->stream>>>(
+            onesweep_kernel<BINS, SORT_THREADS, true><<<tiles, SORT_THREADS, sm, c->stream>>>(
                 kb[cur], kb[cur ^ 1], vb[cur], vb[cur ^ 1], (uint32_t)n, plan.shift[p], plan.bits[p],
                 ghist.get() + (size_t)p * BINS, status.get(), ticket.get() + p);
         else
-            onesweep_kernel<BINS, false><<<tiles, SORT_THREADS, sm, c->stream>>>(
+            onesweep_kernel<BINS, SORT_THREADS, false><<<tiles, SORT_THREADS, sm, c->stream>>>(
                 kb[cur], kb[cur ^ 1], nullptr, nullptr, (uint32_t)n, plan.shift[p], plan.bits[p],
                 ghist.get() + (size_t)p * BINS, status.get(), ticket.get() + p);
         ZB_LAUNCH_CHECK(c);
