@@ -18,71 +18,79 @@ static constexpr int ST_TILE = ST_THREADS * ST_ITEMS;  // 4096 elements per CTA
 // every global access is a fully coalesced 2 KB row.  Chained scan carries (#heads, weight sum).
 // Reference: zotmer/commands/kmerize.py:41-132 (merge = RLE of the sorted buffer, counts summed).
 // ---------------------------------------------------------------------------------------------
+// A CTA owns ST_ROUNDS consecutive 4096-element sub-tiles (16384 elements) and pays for ONE chained-scan
+// step: phase 1 streams the keys once and keeps only head flags (bit masks) and per-(row,warp) cell
+// counts; after the look-back, phase 2 re-reads just the keys at run heads (L2 hits) and writes them.
+static constexpr int ST_ROUNDS = 4;
+static constexpr int ST_BIG = ST_ROUNDS * ST_TILE;
+static constexpr int ST_CELLS = ST_ROUNDS * ST_ITEMS * (ST_THREADS / 32);  // 512
+
 template <bool WEIGHTED>
-__global__ void __launch_bounds__(ST_THREADS)
+__global__ void __launch_bounds__(ST_THREADS, 4)
 rbk_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ w, uint64_t n,
            uint64_t* __restrict__ out_k, uint64_t* __restrict__ out_start, uint64_t* __restrict__ st_heads,
            uint64_t* __restrict__ st_wsum, uint32_t* __restrict__ ticket, uint64_t* __restrict__ totals) {
     __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_rowhead[ST_ITEMS][ST_THREADS / 32];  // heads per (row, warp)
-    __shared__ uint64_t s_rowsum[ST_ITEMS][ST_THREADS / 32];   // weight per (row, warp) (WEIGHTED only)
+    __shared__ uint32_t s_head[ST_CELLS];                      // heads per (round,row,warp), then exclusive
+    __shared__ uint64_t s_sum[WEIGHTED ? ST_CELLS : 1];        // weight per cell, then exclusive
     __shared__ uint64_t s_pref[2];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint64_t base = (uint64_t)tile * ST_TILE;
+    const uint64_t base = (uint64_t)tile * ST_BIG;
 
-    uint64_t key[ST_ITEMS];
-    uint32_t wt[ST_ITEMS];
-    unsigned headbits = 0;
+    uint64_t headbits = 0;   // bit r*16+j
+#pragma unroll 1
+    for (int r = 0; r < ST_ROUNDS; r++) {
+        unsigned hb = 0;
 #pragma unroll
-    for (int j = 0; j < ST_ITEMS; j++) {
-        const uint64_t i = base + (uint64_t)j * ST_THREADS + tid;
-        const bool in = i < n;
-        key[j] = in ? __ldg(keys + i) : 0;
-        if (WEIGHTED) wt[j] = in ? __ldg(w + i) : 0u;
-        uint64_t prev = __shfl_up_sync(0xffffffffu, key[j], 1);
-        if (lane == 0 && in && i > 0) prev = __ldg(keys + i - 1);
-        const bool head = in && (i == 0 || prev != key[j]);
-        headbits |= (head ? 1u : 0u) << j;
-        const unsigned b = __ballot_sync(0xffffffffu, head);
-        if (WEIGHTED) {
-            const uint64_t ws = warp_sum<uint64_t>(wt[j]);
-            if (lane == 0) s_rowsum[j][warp] = ws;
+        for (int j = 0; j < ST_ITEMS; j++) {
+            const uint64_t i = base + (uint64_t)(r * ST_ITEMS + j) * ST_THREADS + tid;
+            const bool in = i < n;
+            const uint64_t key = in ? __ldg(keys + i) : 0;
+            uint64_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+            if (lane == 0 && in && i > 0) prev = __ldg(keys + i - 1);
+            const bool head = in && (i == 0 || prev != key);
+            hb |= (head ? 1u : 0u) << j;
+            const unsigned b = __ballot_sync(0xffffffffu, head);
+            if (WEIGHTED) {
+                const uint64_t ws = warp_sum<uint64_t>(in ? __ldg(w + i) : 0u);
+                if (lane == 0) s_sum[(r * ST_ITEMS + j) * (ST_THREADS / 32) + warp] = ws;
+            }
+            if (lane == 0) s_head[(r * ST_ITEMS + j) * (ST_THREADS / 32) + warp] = __popc(b);
         }
-        if (lane == 0) s_rowhead[j][warp] = __popc(b);
+        headbits |= (uint64_t)hb << (r * ST_ITEMS);
     }
     __syncthreads();
-    // exclusive scan over the 16 x 8 (row, warp) cells in position order, by warp 0
     if (warp == 0) {
-        constexpr int CELLS = ST_ITEMS * (ST_THREADS / 32);  // 128
-        uint32_t h[CELLS / 32];
-        uint64_t s[CELLS / 32];
+        constexpr int PERL = ST_CELLS / 32;  // 16 consecutive cells per lane
         uint32_t hs = 0;
         uint64_t ss = 0;
 #pragma unroll
-        for (int q = 0; q < CELLS / 32; q++) {
-            const int cell = lane * (CELLS / 32) + q;
-            h[q] = (&s_rowhead[0][0])[cell];
-            hs += h[q];
-            if (WEIGHTED) { s[q] = (&s_rowsum[0][0])[cell]; ss += s[q]; }
+        for (int q = 0; q < PERL; q++) {
+            hs += s_head[lane * PERL + q];
+            if (WEIGHTED) ss += s_sum[lane * PERL + q];
         }
-        uint32_t hi = warp_incl_scan(hs);
+        const uint32_t hi = warp_incl_scan(hs);
         const uint32_t htot = __shfl_sync(0xffffffffu, hi, 31);
         uint32_t he = hi - hs;
-        uint64_t si = 0, stot = 0, se = 0;
+        uint64_t stot = 0, se = 0;
         if (WEIGHTED) {
-            si = warp_incl_scan(ss);
+            const uint64_t si = warp_incl_scan(ss);
             stot = __shfl_sync(0xffffffffu, si, 31);
             se = si - ss;
         }
 #pragma unroll
-        for (int q = 0; q < CELLS / 32; q++) {
-            const int cell = lane * (CELLS / 32) + q;
-            (&s_rowhead[0][0])[cell] = he;
-            he += h[q];
-            if (WEIGHTED) { (&s_rowsum[0][0])[cell] = se; se += s[q]; }
+        for (int q = 0; q < PERL; q++) {
+            const uint32_t h = s_head[lane * PERL + q];
+            s_head[lane * PERL + q] = he;
+            he += h;
+            if (WEIGHTED) {
+                const uint64_t x = s_sum[lane * PERL + q];
+                s_sum[lane * PERL + q] = se;
+                se += x;
+            }
         }
         const uint64_t ph = lookback_u64(st_heads, tile, htot);
         uint64_t pw = 0;
@@ -90,22 +98,33 @@ rbk_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ w, ui
         if (lane == 0) {
             s_pref[0] = ph;
             s_pref[1] = pw;
-            if (base + ST_TILE >= n) { totals[0] = ph + htot; totals[1] = WEIGHTED ? pw + stot : n; }
+            if (base + ST_BIG >= n) { totals[0] = ph + htot; totals[1] = WEIGHTED ? pw + stot : n; }
         }
     }
     __syncthreads();
     const uint64_t ph = s_pref[0], pw = s_pref[1];
+    const unsigned lt = lanemask_lt();
+#pragma unroll 1
+    for (int r = 0; r < ST_ROUNDS; r++) {
+        const unsigned hb = (unsigned)(headbits >> (r * ST_ITEMS)) & 0xffffu;
 #pragma unroll
-    for (int j = 0; j < ST_ITEMS; j++) {
-        const bool head = (headbits >> j) & 1u;
-        const unsigned b = __ballot_sync(0xffffffffu, head);
-        uint64_t wi = 0;
-        if (WEIGHTED) wi = warp_incl_scan<uint64_t>(wt[j]);
-        if (head) {
-            const uint64_t hidx = ph + s_rowhead[j][warp] + __popc(b & lanemask_lt());
-            out_k[hidx] = key[j];
-            // start of the run in the (weighted) prefix space; unweighted: simply its position
-            out_start[hidx] = WEIGHTED ? (pw + s_rowsum[j][warp] + (wi - wt[j])) : (base + (uint64_t)j * ST_THREADS + tid);
+        for (int j = 0; j < ST_ITEMS; j++) {
+            const uint64_t i = base + (uint64_t)(r * ST_ITEMS + j) * ST_THREADS + tid;
+            const bool head = (hb >> j) & 1u;
+            const unsigned b = __ballot_sync(0xffffffffu, head);
+            const int cell = (r * ST_ITEMS + j) * (ST_THREADS / 32) + warp;
+            uint64_t wi = 0;
+            uint32_t wt = 0;
+            if (WEIGHTED) {
+                wt = (i < n) ? __ldg(w + i) : 0u;
+                wi = warp_incl_scan<uint64_t>(wt);
+            }
+            if (head) {
+                const uint64_t hidx = ph + s_head[cell] + __popc(b & lt);
+                out_k[hidx] = __ldg(keys + i);
+                // start of the run in the (weighted) prefix space; unweighted: simply its position
+                out_start[hidx] = WEIGHTED ? (pw + s_sum[cell] + (wi - wt)) : i;
+            }
         }
     }
 }
@@ -122,7 +141,7 @@ __global__ void rbk_finish_kernel(const uint64_t* __restrict__ start, uint64_t n
 
 size_t reduce_by_key(Ctx* c, const uint64_t* keys, const uint32_t* w, size_t n, uint64_t* out_k, uint32_t* out_c) {
     if (n == 0) return 0;
-    const uint32_t tiles = (uint32_t)div_up(n, ST_TILE);
+    const uint32_t tiles = (uint32_t)div_up(n, ST_BIG);
     DBuf<uint64_t> status(c, (size_t)tiles * 2 + 4);
     DBuf<uint64_t> start(c, n);
     ZB_CUDA(cudaMemsetAsync(status.get(), 0, ((size_t)tiles * 2 + 4) * 8, c->stream));
@@ -240,9 +259,26 @@ __device__ __forceinline__ uint64_t rc64(uint64_t x, int k) {
     return y >> (64 - 2 * k);
 }
 
-__global__ void mirror_kernel(int k, const uint64_t* __restrict__ ck, uint32_t* __restrict__ cc, uint64_t n,
-                              uint64_t* __restrict__ rk, uint32_t* __restrict__ rcnt,
-                              unsigned long long* __restrict__ counter, unsigned int* __restrict__ err) {
+// Odd k: no k-mer equals its own reverse complement, so the mirrored half has exactly n entries and
+// is written in place order (no compaction, no atomics).
+__global__ void __launch_bounds__(256) mirror_odd_kernel(int k, const uint64_t* __restrict__ ck,
+                                                         const uint32_t* __restrict__ cc, uint64_t n,
+                                                         uint64_t* __restrict__ rk, uint32_t* __restrict__ rcnt) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rk[i] = rc64(ck[i], k);
+    rcnt[i] = cc[i];
+}
+
+// Even k: reverse-palindromes (rc(x) == x) stay single and get their count doubled (the reference
+// emits x twice per window, kmerize.py both=True); everything else is appended through one atomic
+// reservation per CTA (order is irrelevant, the mirrored half is sorted afterwards).
+__global__ void __launch_bounds__(256) mirror_kernel(int k, const uint64_t* __restrict__ ck, uint32_t* __restrict__ cc,
+                                                     uint64_t n, uint64_t* __restrict__ rk, uint32_t* __restrict__ rcnt,
+                                                     unsigned long long* __restrict__ counter,
+                                                     unsigned int* __restrict__ err) {
+    __shared__ uint32_t s_scan[256 / 32 + 1];
+    __shared__ unsigned long long s_base;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = i < n;
     uint64_t x = 0, r = 0;
@@ -252,29 +288,30 @@ __global__ void mirror_kernel(int k, const uint64_t* __restrict__ ck, uint32_t* 
         x = ck[i];
         cnt = cc[i];
         r = rc64(x, k);
-        if (r == x) {  // reverse-palindrome (even k only): the reference emits it twice per window
+        if (r == x) {
             if (cnt > 0x7fffffffu) atomicExch(err, 1u);
             cc[i] = cnt * 2u;
         } else {
             emit = true;
         }
     }
-    const unsigned b = __ballot_sync(0xffffffffu, emit);
-    if (b) {
-        unsigned long long basep = 0;
-        const int leader = __ffs(b) - 1;
-        if ((int)lane_id() == leader) basep = atomicAdd(counter, (unsigned long long)__popc(b));
-        basep = __shfl_sync(0xffffffffu, basep, leader);
-        if (emit) {
-            const unsigned long long p = basep + __popc(b & lanemask_lt());
-            rk[p] = r;
-            rcnt[p] = cnt;
-        }
+    uint32_t tot;
+    const uint32_t off = block_excl_scan<256, uint32_t>(emit ? 1u : 0u, s_scan, &tot);
+    if (threadIdx.x == 0) s_base = tot ? atomicAdd(counter, (unsigned long long)tot) : 0ull;
+    __syncthreads();
+    if (emit) {
+        rk[s_base + off] = r;
+        rcnt[s_base + off] = cnt;
     }
 }
 
 size_t mirror_keys(Ctx* c, int k, const uint64_t* ck, uint32_t* cc, size_t n, uint64_t* rk, uint32_t* rcnt) {
     if (n == 0) return 0;
+    if (k & 1) {
+        mirror_odd_kernel<<<(unsigned)div_up(n, 256), 256, 0, c->stream>>>(k, ck, cc, n, rk, rcnt);
+        ZB_LAUNCH_CHECK(c);
+        return n;
+    }
     DBuf<unsigned long long> ctr(c, 2);
     ZB_CUDA(cudaMemsetAsync(ctr.get(), 0, 16, c->stream));
     mirror_kernel<<<(unsigned)div_up(n, 256), 256, 0, c->stream>>>(k, ck, cc, n, rk, rcnt, ctr.get(),
@@ -292,72 +329,84 @@ size_t mirror_keys(Ctx* c, int k, const uint64_t* ck, uint32_t* cc, size_t n, ui
 struct TrimOp {
     const uint32_t* cnt;
     uint64_t cmin, cmax;
-    __device__ bool keep(const uint64_t*, uint64_t i, uint64_t) const {
-        const uint64_t f = cnt[i];
+    __device__ bool keep(const uint64_t*, uint64_t i) const {
+        const uint64_t f = __ldg(cnt + i);
         return f >= cmin && (cmax == 0 || f <= cmax);
     }
     __device__ uint64_t key(uint64_t x) const { return x; }
 };
 struct ProjectOp {
     int shift;
-    __device__ bool keep(const uint64_t* keys, uint64_t i, uint64_t x) const {
-        return i == 0 || (keys[i - 1] >> shift) != (x >> shift);
+    __device__ bool keep(const uint64_t* keys, uint64_t i) const {
+        return i == 0 || (__ldg(keys + i - 1) >> shift) != (__ldg(keys + i) >> shift);
     }
     __device__ uint64_t key(uint64_t x) const { return x >> shift; }
 };
 
 template <typename Op, bool HAS_CNT>
-__global__ void __launch_bounds__(ST_THREADS)
+__global__ void __launch_bounds__(ST_THREADS, 4)
 compact_kernel(Op op, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt, uint64_t n,
                uint64_t* __restrict__ ok, uint32_t* __restrict__ oc, uint64_t* __restrict__ status,
                uint32_t* __restrict__ ticket, uint64_t* __restrict__ total) {
     __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_cell[ST_ITEMS][ST_THREADS / 32];
+    __shared__ uint32_t s_cell[ST_CELLS];
     __shared__ uint64_t s_pref;
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint64_t base = (uint64_t)tile * ST_TILE;
-    uint64_t key[ST_ITEMS];
-    unsigned keepbits = 0;
+    const uint64_t base = (uint64_t)tile * ST_BIG;
+    uint64_t keepbits = 0;   // bit r*16+j
+#pragma unroll 1
+    for (int r = 0; r < ST_ROUNDS; r++) {
+        unsigned kb = 0;
 #pragma unroll
-    for (int j = 0; j < ST_ITEMS; j++) {
-        const uint64_t i = base + (uint64_t)j * ST_THREADS + tid;
-        const bool in = i < n;
-        key[j] = in ? __ldg(keys + i) : 0;
-        const bool kp = in && op.keep(keys, i, key[j]);
-        keepbits |= (kp ? 1u : 0u) << j;
-        const unsigned b = __ballot_sync(0xffffffffu, kp);
-        if (lane == 0) s_cell[j][warp] = __popc(b);
+        for (int j = 0; j < ST_ITEMS; j++) {
+            const uint64_t i = base + (uint64_t)(r * ST_ITEMS + j) * ST_THREADS + tid;
+            const bool kp = (i < n) && op.keep(keys, i);
+            kb |= (kp ? 1u : 0u) << j;
+            const unsigned b = __ballot_sync(0xffffffffu, kp);
+            if (lane == 0) s_cell[(r * ST_ITEMS + j) * (ST_THREADS / 32) + warp] = __popc(b);
+        }
+        keepbits |= (uint64_t)kb << (r * ST_ITEMS);
     }
     __syncthreads();
     if (warp == 0) {
-        constexpr int CELLS = ST_ITEMS * (ST_THREADS / 32);
-        uint32_t h[CELLS / 32], hs = 0;
+        constexpr int PERL = ST_CELLS / 32;
+        uint32_t hs = 0;
 #pragma unroll
-        for (int q = 0; q < CELLS / 32; q++) { h[q] = (&s_cell[0][0])[lane * (CELLS / 32) + q]; hs += h[q]; }
+        for (int q = 0; q < PERL; q++) hs += s_cell[lane * PERL + q];
         const uint32_t hi = warp_incl_scan(hs);
         const uint32_t htot = __shfl_sync(0xffffffffu, hi, 31);
         uint32_t he = hi - hs;
 #pragma unroll
-        for (int q = 0; q < CELLS / 32; q++) { (&s_cell[0][0])[lane * (CELLS / 32) + q] = he; he += h[q]; }
+        for (int q = 0; q < PERL; q++) {
+            const uint32_t h = s_cell[lane * PERL + q];
+            s_cell[lane * PERL + q] = he;
+            he += h;
+        }
         const uint64_t p = lookback_u64(status, tile, htot);
         if (lane == 0) {
             s_pref = p;
-            if (base + ST_TILE >= n) *total = p + htot;
+            if (base + ST_BIG >= n) *total = p + htot;
         }
     }
     __syncthreads();
     const uint64_t p0 = s_pref;
+    const unsigned lt = lanemask_lt();
+#pragma unroll 1
+    for (int r = 0; r < ST_ROUNDS; r++) {
+        const unsigned kb = (unsigned)(keepbits >> (r * ST_ITEMS)) & 0xffffu;
 #pragma unroll
-    for (int j = 0; j < ST_ITEMS; j++) {
-        const bool kp = (keepbits >> j) & 1u;
-        const unsigned b = __ballot_sync(0xffffffffu, kp);
-        if (kp) {
-            const uint64_t o = p0 + s_cell[j][warp] + __popc(b & lanemask_lt());
-            ok[o] = op.key(key[j]);
-            if (HAS_CNT) oc[o] = cnt[base + (uint64_t)j * ST_THREADS + tid];
+        for (int j = 0; j < ST_ITEMS; j++) {
+            const uint64_t i = base + (uint64_t)(r * ST_ITEMS + j) * ST_THREADS + tid;
+            const bool kp = (kb >> j) & 1u;
+            const unsigned b = __ballot_sync(0xffffffffu, kp);
+            if (kp) {
+                const uint64_t o = p0 + s_cell[(r * ST_ITEMS + j) * (ST_THREADS / 32) + warp] + __popc(b & lt);
+                ok[o] = op.key(__ldg(keys + i));
+                if (HAS_CNT) oc[o] = __ldg(cnt + i);
+            }
         }
     }
 }
@@ -365,7 +414,7 @@ compact_kernel(Op op, const uint64_t* __restrict__ keys, const uint32_t* __restr
 template <typename Op, bool HAS_CNT>
 static size_t run_compact(Ctx* c, Op op, const uint64_t* k, const uint32_t* cnt, size_t n, uint64_t* ok, uint32_t* oc) {
     if (n == 0) return 0;
-    const uint32_t tiles = (uint32_t)div_up(n, ST_TILE);
+    const uint32_t tiles = (uint32_t)div_up(n, ST_BIG);
     DBuf<uint64_t> status(c, (size_t)tiles + 2);
     ZB_CUDA(cudaMemsetAsync(status.get(), 0, ((size_t)tiles + 2) * 8, c->stream));
     uint64_t* total = status.get() + tiles;
