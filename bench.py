@@ -179,32 +179,9 @@ def step_device(nat, dev, d_ptr, nbytes, dist_ctx):
 
 
 def exchange(nat, km, ctx):
-    """route every pending canonical k-mer to its owner rank: sizes first, then one all-to-all of keys"""
-    import torch
-    import torch.distributed as dist
-    world, dev = ctx["world"], ctx["dev"]
-    n = km.pending()
-    send = ctx["send"]
-    if send.numel() < max(n, 1):
-        send = ctx["send"] = torch.empty(int(n * 1.1) + 16, dtype=torch.int64, device="cuda:%d" % dev)
-    counts = km.take_bucketed_dev(world, send.data_ptr())
-    cin = torch.tensor(counts, dtype=torch.int64, device="cuda:%d" % dev)
-    cout = torch.empty_like(cin)
-    dist.all_to_all_single(cout, cin)
-    recv_counts = [int(x) for x in cout.tolist()]
-    nrecv = sum(recv_counts)
-    recv = ctx["recv"]
-    if recv.numel() < max(nrecv, 1):
-        recv = ctx["recv"] = torch.empty(int(nrecv * 1.1) + 16, dtype=torch.int64, device="cuda:%d" % dev)
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    dist.all_to_all_single(recv[:nrecv], send[:n], recv_counts, counts)
-    t1.record()
-    torch.cuda.synchronize(dev)
-    ctx["a2a_ms"].append(t0.elapsed_time(t1))
-    ctx["a2a_bytes"].append(8 * (n - counts[ctx["rank"]]))
-    km.add_canonical_dev(recv.data_ptr(), nrecv)
+    """route every pending canonical k-mer to its owner rank (zotmer_b200/multigpu.py)"""
+    from zotmer_b200 import multigpu
+    multigpu.exchange_pending(nat, km, ctx)
 
 
 def run_ours(args, rank, world, local_rank):

@@ -368,3 +368,29 @@ def test_codec_streams(nat):
         assert np.array_equal(nat.decode_stream(w, True), s)
     with pytest.raises(IndexError):
         nat.encode_stream(np.array([2 ** 61], np.uint64))
+
+
+def test_device_bucketing_matches_host_owner_function(nat):
+    """zb_kmerize_take_bucketed_dev (csrc/extract.cu owner_of) vs zotmer_b200.multigpu.owner_of"""
+    import torch
+    from zotmer_b200 import multigpu
+    rng = np.random.default_rng(21)
+    fq = make_fastq(rng, rnd_dna(rng, 30000), 3000, 100)
+    for world in (1, 2, 3, 8):
+        km = nat.Kmerizer(25)
+        km.feed(fq, False)
+        n = km.pending()
+        buf = torch.empty(n + 16, dtype=torch.int64, device="cuda:0")
+        counts = km.take_bucketed_dev(world, buf.data_ptr())
+        torch.cuda.synchronize()
+        keys = buf[:n].cpu().numpy().view(np.uint64)
+        assert sum(counts) == n
+        exp_owner = np.repeat(np.arange(world), counts)
+        assert np.array_equal(multigpu.owner_of(keys, world), exp_owner)
+        # hand everything back (as if received from peers) and finish: result == single-GPU oracle
+        km.add_canonical_dev(buf.data_ptr(), n)
+        s, nr = km.finish()
+        km.close()
+        ks, cc = s.fetch()
+        ek, ec, _, _ = co.kmerize(25, [(fq, False)])
+        assert np.array_equal(ks, ek) and np.array_equal(cc, ec)
