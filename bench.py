@@ -185,6 +185,7 @@ def exchange(nat, km, ctx):
 
 
 def run_ours(args, rank, world, local_rank):
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
     import torch
     from zotmer_b200 import _native as nat
     if nat.device_count() < 1:
@@ -223,17 +224,21 @@ def run_ours(args, rank, world, local_rank):
     if dist_ctx is not None:
         dist_ctx["a2a_ms"].clear(); dist_ctx["a2a_bytes"].clear()
     sampler = ClockSampler(dev)
-    barrier()
     if rank == 0:
-        sampler.start()
+        sampler.start()          # NVML init happens here, outside the timed region
+    barrier()
     nat.dbg_profile(True, dev)
     launches0 = nat.launch_count(dev)
     nat.timer_start(dev)
     w0 = time.perf_counter()
+    d_times = []
     for _ in range(args.steps):
+        t_it = time.perf_counter()
         s, t = step_device(nat, dev, d_in.data_ptr(), nbytes, dist_ctx)
         s.free(); t.free()
+        d_times.append((time.perf_counter() - t_it) * 1e3)
     ms_dev = nat.timer_stop(dev)
+    print("rank %d device-resident per-step wall ms: %s" % (rank, [round(x, 1) for x in d_times]), file=sys.stderr)
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3
     launches = nat.launch_count(dev) - launches0
