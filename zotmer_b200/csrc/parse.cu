@@ -67,6 +67,33 @@ __global__ void __launch_bounds__(256) count_newlines_kernel(const uint8_t* __re
     if (lane_id() == 0 && c) atomicAdd(out, c);
 }
 
+// 16 bytes -> 16-bit mask of the bytes equal to the (replicated) pattern
+__device__ __forceinline__ uint32_t eq_mask4(uint32_t w, uint32_t pat) {
+    const uint32_t x = w ^ pat;
+    const uint32_t z = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;   // 0x80 where the byte is zero
+    return (((z >> 7) * 0x01020408u) >> 24) & 0xfu;
+}
+__device__ __forceinline__ uint32_t eq_mask16(const uint4& v, uint32_t pat) {
+    return eq_mask4(v.x, pat) | (eq_mask4(v.y, pat) << 4) | (eq_mask4(v.z, pat) << 8) | (eq_mask4(v.w, pat) << 12);
+}
+// 4 text bytes -> 4 base codes (0..3, 4 = not AaCcGgTtUu), branch-free:
+// (ch >> 1) & 3 maps A,C,T/U,G -> 0,1,2,3 (case-insensitive); x ^ (x >> 1) swaps 2 <-> 3; the code is
+// valid iff the case-folded byte equals "ACGT"[code] (byte permute as a 4-entry table) or is 'U'.
+__device__ __forceinline__ uint32_t codes4(uint32_t w) {
+    const uint32_t x = (w >> 1) & 0x03030303u;
+    const uint32_t c = x ^ ((x >> 1) & 0x01010101u);
+    uint32_t sel = (c | (c >> 4)) & 0x00ff00ffu;
+    sel = (sel | (sel >> 8)) & 0xffffu;
+    const uint32_t expect = __byte_perm(0x54474341u, 0u, sel);
+    const uint32_t u = w & 0xdfdfdfdfu;
+    uint32_t d = u ^ expect;
+    uint32_t ok = ~(((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u;
+    d = u ^ 0x55555555u;
+    ok |= ~(((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u;
+    const uint32_t keep = (ok >> 7) * 3u;                       // 0x03 per valid byte
+    return (c & keep) | ((~ok & 0x80808080u) >> 5);             // 0x04 per invalid byte
+}
+
 __global__ void __launch_bounds__(PA_THREADS)
 fastq_kernel(const uint8_t* __restrict__ raw, uint64_t n, const unsigned long long* __restrict__ n_newlines,
              uint8_t* __restrict__ codes, uint64_t* __restrict__ st_lines, uint64_t* __restrict__ st_out,
@@ -75,6 +102,7 @@ fastq_kernel(const uint8_t* __restrict__ raw, uint64_t n, const unsigned long lo
     __shared__ uint32_t s_nl[PA_ROWS * PA_WARPS];
     __shared__ uint32_t s_em[PA_ROWS * PA_WARPS];
     __shared__ uint64_t s_pref[2];
+    __shared__ __align__(16) uint8_t s_stage[PA_TILE + 32];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
@@ -85,12 +113,14 @@ fastq_kernel(const uint8_t* __restrict__ raw, uint64_t n, const unsigned long lo
     const uint64_t max_line = (lines >> 2) << 2;
 
     uint4 v[PA_ROWS];
-    uint32_t nlx[PA_ROWS];  // newlines before my 16 bytes inside the tile
+    uint32_t nlm[PA_ROWS];  // newline mask of my 16 bytes
+    uint32_t nlx[PA_ROWS];  // newlines before my 16 bytes inside the warp-row
 #pragma unroll
     for (int r = 0; r < PA_ROWS; r++) {
         const uint64_t off = base + (uint64_t)r * (PA_THREADS * 16) + tid * 16;
         v[r] = (off < n) ? load16(raw, off, n, 0) : make_uint4(0, 0, 0, 0);
-        const uint32_t c = count_eq(v[r], 0x0a0a0a0au);
+        nlm[r] = eq_mask16(v[r], 0x0a0a0a0au);
+        const uint32_t c = __popc(nlm[r]);
         const uint32_t inc = warp_incl_scan(c);
         nlx[r] = inc - c;
         if (lane == 31) s_nl[r * PA_WARPS + warp] = inc;
@@ -104,27 +134,25 @@ fastq_kernel(const uint8_t* __restrict__ raw, uint64_t n, const unsigned long lo
     __syncthreads();
     const uint64_t line0 = s_pref[0];
 
-    uint64_t acc[PA_ROWS];
-    uint32_t cnt[PA_ROWS], emx[PA_ROWS];
+    // emitted bytes: those on line 1 (mod 4) of a complete record, the terminating '\n' included
+    uint32_t em[PA_ROWS], emx[PA_ROWS];
 #pragma unroll
     for (int r = 0; r < PA_ROWS; r++) {
         const uint64_t off = base + (uint64_t)r * (PA_THREADS * 16) + tid * 16;
         uint64_t line = line0 + s_nl[r * PA_WARPS + warp] + nlx[r];
-        uint64_t a = 0;
-        uint32_t m = 0;
-#pragma unroll
-        for (int b = 0; b < 16; b++) {
-            const uint32_t ch = byte_of(v[r], b);
-            const bool in = off + b < n;
-            const bool seq = in && ((line & 3) == 1) && (line < max_line);
-            if (seq) {
-                a |= (uint64_t)code_of(ch) << (4 * m);
-                m++;
-            }
-            line += (ch == '\n') ? 1 : 0;
+        uint32_t rem = nlm[r], E = 0, start = 0;
+        while (true) {
+            const uint32_t nxt = rem ? (uint32_t)(__ffs(rem) - 1) : 15u;   // last byte of this line inside the chunk
+            if (((line & 3) == 1) && (line < max_line)) E |= ((2u << nxt) - 1u) & ~((1u << start) - 1u);
+            if (!rem) break;
+            rem &= rem - 1u;
+            start = nxt + 1u;
+            line++;
+            if (start > 15u) break;
         }
-        acc[r] = a;
-        cnt[r] = m;
+        if (off + 16 > n) E &= (off < n) ? ((1u << (n - off)) - 1u) : 0u;
+        em[r] = E;
+        const uint32_t m = __popc(E);
         const uint32_t inc = warp_incl_scan(m);
         emx[r] = inc - m;
         if (lane == 31) s_em[r * PA_WARPS + warp] = inc;
@@ -135,19 +163,44 @@ fastq_kernel(const uint8_t* __restrict__ raw, uint64_t n, const unsigned long lo
         const uint64_t p = lookback_u64(st_out, tile, tot);
         if (lane == 0) {
             s_pref[1] = p;
+            s_nl[0] = tot;   // (s_nl is dead) tile total for the copy-out
             if (base + PA_TILE >= n) *total_out = p + tot;
         }
     }
     __syncthreads();
     const uint64_t out0 = s_pref[1];
+    const uint32_t tot = s_nl[0];
+    const uint32_t mis = (uint32_t)((uintptr_t)(codes + out0) & 15u);   // stage congruent to the global address
 #pragma unroll
     for (int r = 0; r < PA_ROWS; r++) {
-        uint64_t o = out0 + s_em[r * PA_WARPS + warp] + emx[r];
-        uint64_t a = acc[r];
-        for (uint32_t q = 0; q < cnt[r]; q++) {
-            codes[o + q] = (uint8_t)(a & 0xf);
-            a >>= 4;
+        uint32_t E = em[r];
+        if (E) {
+            uint32_t cw[4] = {codes4(v[r].x), codes4(v[r].y), codes4(v[r].z), codes4(v[r].w)};
+            uint8_t* dst = s_stage + mis + s_em[r * PA_WARPS + warp] + emx[r];
+            if (E == 0xffffu) {
+#pragma unroll
+                for (int b = 0; b < 16; b++) dst[b] = (uint8_t)(cw[b >> 2] >> (8 * (b & 3)));
+            } else {
+                uint32_t q = 0;
+#pragma unroll
+                for (int b = 0; b < 16; b++) {
+                    if ((E >> b) & 1u) dst[q++] = (uint8_t)(cw[b >> 2] >> (8 * (b & 3)));
+                }
+            }
         }
+    }
+    __syncthreads();
+    // copy out: whole 16-byte vectors where possible, single bytes at the ragged ends
+    uint8_t* gdst = codes + out0 - mis;   // 16-byte aligned
+    const uint32_t lo = mis, hi = mis + tot;
+    const uint32_t v0 = (lo + 15u) & ~15u, v1 = hi & ~15u;
+    if (v0 <= v1) {
+        for (uint32_t i = v0 + tid * 16; i < v1; i += PA_THREADS * 16)
+            *reinterpret_cast<uint4*>(gdst + i) = *reinterpret_cast<const uint4*>(s_stage + i);
+        for (uint32_t i = lo + tid; i < v0 && i < hi; i += PA_THREADS) gdst[i] = s_stage[i];
+        for (uint32_t i = v1 + tid; i < hi; i += PA_THREADS) gdst[i] = s_stage[i];
+    } else {
+        for (uint32_t i = lo + tid; i < hi; i += PA_THREADS) gdst[i] = s_stage[i];
     }
 }
 
