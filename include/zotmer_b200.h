@@ -128,6 +128,10 @@ int zb_set_from_streams(int device, const uint64_t* kmer_words, size_t n_kmer_wo
 /* sort keys (and optional u32 payload) in place; max_bits 8..11 = digit width cap; times `iters` sorts */
 int zb_dbg_sort_u64(int device, uint64_t* keys, uint32_t* vals, size_t n, int key_bits, int max_bits, int iters,
                     float* ms_per_sort);
+/* sort + run-length count (weights NULL = 1 each): distinct keys ascending + summed counts; out arrays hold n
+ * entries; mode 0 = segmented path when profitable, 1 = full LSD sort + reduce-by-key; both give the same result */
+int zb_dbg_sort_count(int device, const uint64_t* keys, const uint32_t* weights, size_t n, int key_bits, int mode,
+                      int iters, uint64_t* out_k, uint32_t* out_c, size_t* n_out, float* ms_per_call);
 /* text -> dense base codes (codes must hold n + 64 bytes) */
 int zb_dbg_parse(int device, const uint8_t* raw, size_t n, int is_fasta, uint8_t* codes, size_t* n_codes,
                  uint64_t* n_records);

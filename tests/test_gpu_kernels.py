@@ -98,6 +98,97 @@ def test_sort_skewed(nat):
     assert np.array_equal(out, keys)
 
 
+# ----------------------------------------------------------------------------- sort + count (segsort.cu)
+def np_count(keys, weights=None):
+    if len(keys) == 0:
+        return np.zeros(0, np.uint64), np.zeros(0, np.uint64)
+    u, inv = np.unique(keys, return_inverse=True)
+    w = np.ones(len(keys), np.uint64) if weights is None else weights.astype(np.uint64)
+    c = np.zeros(len(u), np.uint64)
+    np.add.at(c, inv, w)
+    return u, c
+
+
+def check_sort_count(nat, keys, bits, weights=None):
+    ek, ec = np_count(keys, weights)
+    for mode in (0, 1):   # segmented path and the classic full sort + RLE must agree with numpy and each other
+        k, c, _ = nat.dbg_sort_count(keys, weights, bits, mode)
+        assert np.array_equal(k, ek), "mode %d: keys differ" % mode
+        assert np.array_equal(c.astype(np.uint64), ec), "mode %d: counts differ" % mode
+
+
+@pytest.mark.parametrize("n", [1, 2, 17, 3583, 3584, 3585, 4096, 4097, 7168, 100000, 1 << 20, 2500001])
+@pytest.mark.parametrize("bits,dup", [(50, 1), (50, 6), (62, 3), (64, 1), (32, 2), (24, 1)])
+def test_sort_count_random(nat, n, bits, dup):
+    rng = np.random.default_rng(n * 7 + bits + dup)
+    m = max(1, n // dup)
+    base = rng.integers(0, 2 ** 63, m, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, m, dtype=np.uint64)
+    if bits < 64:
+        base &= np.uint64((1 << bits) - 1)
+    keys = base[rng.integers(0, m, n)]
+    check_sort_count(nat, keys, bits)
+
+
+@pytest.mark.parametrize("seglen", [1, 2, 15, 16, 17, 100, 511, 512, 513, 1000, 3584, 5000])
+def test_sort_count_segment_lengths(nat, seglen):
+    """keys sharing their top bits in groups of exactly `seglen`: around the 512-key limit of the in-shared-memory
+    path and across CTA boundaries (3584 owned positions), distinct and duplicated low parts"""
+    bits = 50
+    nseg = max(3, 60000 // seglen)
+    rng = np.random.default_rng(seglen)
+    n = nseg * seglen
+    lg = int(np.ceil(np.log2(n)))
+    T = 8 * max(1, (lg - 4 + 7) // 8)
+    low = bits - T
+    assert low >= 8
+    tops = rng.choice(1 << min(T, 20), nseg, replace=False).astype(np.uint64)
+    for distinct_low in (True, False):
+        if distinct_low:
+            lows = rng.integers(0, 1 << low, n, dtype=np.uint64)
+        else:
+            lows = rng.integers(0, 3, n, dtype=np.uint64) * np.uint64(12345)
+        keys = (np.repeat(tops, seglen) << np.uint64(low)) | lows
+        rng.shuffle(keys)
+        check_sort_count(nat, keys, bits)
+
+
+def test_sort_count_heavy_repeats(nat):
+    """a few keys repeated very often (big segments -> side path) mixed with unique keys"""
+    rng = np.random.default_rng(11)
+    n = 700000
+    keys = rng.integers(0, 2 ** 50, n, dtype=np.uint64)
+    keys[rng.integers(0, n, 200000)] = np.uint64(0)                       # poly-A like
+    keys[rng.integers(0, n, 50000)] = np.uint64((1 << 50) - 1)
+    hot = rng.integers(0, 2 ** 50, 40, dtype=np.uint64)
+    keys[rng.integers(0, n, 100000)] = hot[rng.integers(0, 40, 100000)]   # ~2500 copies each
+    check_sort_count(nat, keys, 50)
+    check_sort_count(nat, np.full(100000, 7, np.uint64), 50)              # one key only
+    check_sort_count(nat, np.full(513, (1 << 64) - 1, np.uint64), 64)
+
+
+@pytest.mark.parametrize("n", [5, 4097, 300000])
+def test_sort_count_weighted(nat, n):
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 2 ** 50, max(1, n // 2), dtype=np.uint64)[rng.integers(0, max(1, n // 2), n)]
+    w = rng.integers(1, 1000, n, dtype=np.uint32)
+    check_sort_count(nat, keys, 50, w)
+    # distinct keys with payload = the mirror sort of kmerize
+    keys = rng.permutation(n).astype(np.uint64) * np.uint64(1099511627791) & np.uint64((1 << 50) - 1)
+    keys = np.unique(keys)
+    rng.shuffle(keys)
+    w = rng.integers(1, 2 ** 32 - 1, len(keys), dtype=np.uint32)
+    check_sort_count(nat, keys, 50, w)
+
+
+def test_sort_count_weight_overflow(nat):
+    keys = np.full(3, 12345678901, np.uint64)
+    keys = np.concatenate([keys, np.arange(5000, dtype=np.uint64) << np.uint64(20)])
+    w = np.full(len(keys), 2 ** 31, np.uint32)
+    for mode in (0, 1):
+        with pytest.raises(IndexError):
+            nat.dbg_sort_count(keys, w, 50, mode)
+
+
 # ----------------------------------------------------------------------------- parse
 def expected_fasta_codes(data):
     out = bytearray()

@@ -1,0 +1,26 @@
+"""sort+count timing on config-2-like keys (canonical k=25 k-mers of 30x reads): segmented vs classic"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from zotmer_b200 import _native as nat
+from tools import synth
+nreads = int(os.environ.get("NREADS", 1000000))
+g = synth.genome(5000000)
+fq = synth.fastq_array(g, nreads).reshape(-1)
+codes, nr = nat.dbg_parse(fq.tobytes(), False)
+keys = nat.dbg_extract(25, codes)
+print("keys", len(keys), flush=True)
+for mode in (0, 1):
+    k, c, ms = nat.dbg_sort_count(keys, None, 50, mode, iters=4)
+    print("mode %d: %d distinct, %.3f ms per sort+count" % (mode, len(k), ms), flush=True)
+    if mode == 0:
+        k0, c0 = k, c
+assert np.array_equal(k0, k) and np.array_equal(c0, c)
+nat.dbg_profile(True)
+nat.dbg_sort_count(keys, None, 50, 0, iters=1)
+print({k: round(v[0], 3) for k, v in nat.dbg_profile(False).items()})
+w = c0
+k, c, ms = nat.dbg_sort_count(k0[::-1].copy(), w, 50, 0, iters=4)
+print("pairs (distinct, reversed): %d -> %.3f ms" % (len(k), ms))
+k, c, ms = nat.dbg_sort_count(k0[::-1].copy(), w, 50, 1, iters=4)
+print("pairs classic: %.3f ms" % ms)

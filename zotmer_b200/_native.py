@@ -54,6 +54,8 @@ SIGNATURES = {
     "zb_set_encode_sizes": (C.c_int, [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "zb_set_from_streams": (C.c_int, [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(vp)]),
     "zb_dbg_sort_u64": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "zb_dbg_sort_count": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp, vp,
+                                    C.POINTER(C.c_size_t), C.POINTER(C.c_float)]),
     "zb_dbg_parse": (C.c_int, [C.c_int, vp, C.c_size_t, C.c_int, vp, C.POINTER(C.c_size_t), u64p]),
     "zb_dbg_extract": (C.c_int, [C.c_int, C.c_int, vp, C.c_size_t, vp, C.POINTER(C.c_size_t)]),
     "zb_dbg_profile": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
@@ -302,6 +304,19 @@ def dbg_sort(keys, vals=None, key_bits=64, max_bits=8, iters=1, device=0):
     _check(lib().zb_dbg_sort_u64(device, _ptr(k), _ptr(v) if v is not None else None, len(k), key_bits, max_bits,
                                  iters, C.byref(ms)))
     return k, v, ms.value
+
+
+def dbg_sort_count(keys, weights=None, key_bits=64, mode=0, iters=1, device=0):
+    """sort + run-length count: (distinct keys ascending, summed counts, ms per call)"""
+    k = np.ascontiguousarray(keys, dtype=np.uint64)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.uint32)
+    ok = np.empty(max(len(k), 1), np.uint64)
+    oc = np.empty(max(len(k), 1), np.uint32)
+    n = C.c_size_t(0)
+    ms = C.c_float(0)
+    _check(lib().zb_dbg_sort_count(device, _ptr(k), _ptr(w) if w is not None else None, len(k), key_bits, mode, iters,
+                                   _ptr(ok), _ptr(oc), C.byref(n), C.byref(ms)))
+    return ok[:n.value].copy(), oc[:n.value].copy(), ms.value
 
 
 def dbg_parse(data, is_fasta, device=0):

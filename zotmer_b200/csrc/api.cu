@@ -167,20 +167,12 @@ static void flush_pending(zb_kmerizer* h) {
     h->pending_upper = 0;
     ZB_CUDA(cudaMemsetAsync(h->d_count.get(), 0, 8, c->stream));
     if (n == 0) return;
-    DBuf<uint64_t> tmp(c, n);
-    int which;
-    {
-        Stage st(c, "sort");
-        which = radix_sort(c, h->pending.get(), tmp.get(), nullptr, nullptr, n, 2 * h->k);
-    }
-    const uint64_t* sorted = which ? tmp.get() : h->pending.get();
-    uint64_t* other = which ? h->pending.get() : tmp.get();
+    // sort + count in one go (segsort.cu): distinct canonical keys -> `dk`, counts -> `dc`
+    DBuf<uint64_t> tmp(c, n), dk(c, n);
     DBuf<uint32_t> dc(c, n);
-    size_t nd;
-    {
-        Stage st(c, "count");
-        nd = reduce_by_key(c, sorted, nullptr, n, other, dc.get());  // distinct keys -> `other`
-    }
+    const size_t nd = sort_count(c, h->pending.get(), tmp.get(), nullptr, nullptr, n, 2 * h->k, dk.get(), dc.get());
+    tmp.release();
+    const uint64_t* other = dk.get();
     if (h->acc_n == 0) {
         h->acc_k.alloc(c, nd);
         h->acc_c.alloc(c, nd);
@@ -297,6 +289,7 @@ int zb_kmerize_open(int k, int device, zb_kmerizer** out) {
     h->k = k;
     h->d_count.alloc(c, 2);
     ZB_CUDA(cudaMemsetAsync(h->d_count.get(), 0, 16, c->stream));
+    if (const char* e = getenv("ZB_SORT_COUNT")) g_sort_count_mode = atoi(e);
     if (const char* e = getenv("ZB_MAX_PENDING")) {
         size_t v = strtoull(e, nullptr, 10);
         if (v >= (size_t)EXTRACT_TILE && v < ((size_t)1 << 30)) h->max_pending = v;
@@ -355,22 +348,23 @@ int zb_kmerize_finish(zb_kmerizer* h, zb_set** result, uint64_t* n_records) {
     h->pending_cap = 0;
     const size_t n = h->acc_n;
     // both strands: mirror the canonical run, sort the mirrored half, merge
-    DBuf<uint64_t> rk(c, n), rk2(c, n);
-    DBuf<uint32_t> rc(c, n), rc2(c, n);
+    DBuf<uint64_t> rk(c, n), rk2(c, n), mk(c, n);
+    DBuf<uint32_t> rc(c, n), rc2(c, n), mc(c, n);
     size_t nm;
-    int which;
     {
         Stage st(c, "mirror");
         nm = mirror_keys(c, h->k, h->acc_k.get(), h->acc_c.get(), n, rk.get(), rc.get());
     }
     {
+        // the mirrored keys are distinct, so "sort + count" is a sort of (key, count) pairs
         Stage st(c, "mirror_sort");
-        which = radix_sort(c, rk.get(), rk2.get(), rc.get(), rc2.get(), nm, 2 * h->k);
+        const size_t nm2 = sort_count(c, rk.get(), rk2.get(), rc.get(), rc2.get(), nm, 2 * h->k, mk.get(), mc.get());
+        if (nm2 != nm) ZB_FAIL(ZB_E_CUDA, "mirror: %zu distinct reverse complements of %zu keys", nm2, nm);
     }
+    rk.release(); rk2.release(); rc.release(); rc2.release();
     zb_set* s = new_set(c, n + nm);
     Stage st_merge(c, "mirror_merge");
-    merge_pairs(c, h->acc_k.get(), h->acc_c.get(), n, which ? rk2.get() : rk.get(), which ? rc2.get() : rc.get(), nm,
-                s->k.get(), s->cnt.get());
+    merge_pairs(c, h->acc_k.get(), h->acc_c.get(), n, mk.get(), mc.get(), nm, s->k.get(), s->cnt.get());
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     h->acc_k.release();
     h->acc_c.release();
@@ -670,6 +664,55 @@ int zb_dbg_sort_u64(int device, uint64_t* keys, uint32_t* vals, size_t n, int ke
     if (ms_per_sort) *ms_per_sort = total_ms / (float)(iters > 1 ? iters - 1 : 1);
     ZB_CUDA(cudaMemcpyAsync(keys, which ? b.get() : a.get(), n * 8, cudaMemcpyDeviceToHost, c->stream));
     if (vals) ZB_CUDA(cudaMemcpyAsync(vals, which ? vb.get() : va.get(), n * 4, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    ZB_CATCH
+}
+
+// sort + count (segsort.cu) of host keys (+ optional weights); mode 0 = auto, 1 = classic full sort + RLE
+int zb_dbg_sort_count(int device, const uint64_t* keys, const uint32_t* weights, size_t n, int key_bits, int mode,
+                      int iters, uint64_t* out_k, uint32_t* out_c, size_t* n_out, float* ms_per_call) {
+    ZB_TRY
+    Ctx* c = ctx_for(device);
+    if (!n_out) ZB_FAIL(ZB_E_ARG, "null argument");
+    const int saved = g_sort_count_mode;
+    g_sort_count_mode = mode;
+    DBuf<uint64_t> src(c, n), a(c, n), b(c, n), ok(c, n);
+    DBuf<uint32_t> vsrc, va, vb, oc(c, n);
+    if (weights) { vsrc.alloc(c, n); va.alloc(c, n); vb.alloc(c, n); }
+    ZB_CUDA(cudaMemcpyAsync(src.get(), keys, n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (weights) ZB_CUDA(cudaMemcpyAsync(vsrc.get(), weights, n * 4, cudaMemcpyHostToDevice, c->stream));
+    cudaEvent_t e0, e1;
+    ZB_CUDA(cudaEventCreate(&e0));
+    ZB_CUDA(cudaEventCreate(&e1));
+    float total_ms = 0;
+    size_t nd = 0;
+    if (iters < 1) iters = 1;
+    try {
+        for (int it = 0; it < iters; it++) {
+            ZB_CUDA(cudaMemcpyAsync(a.get(), src.get(), n * 8, cudaMemcpyDeviceToDevice, c->stream));
+            if (weights) ZB_CUDA(cudaMemcpyAsync(va.get(), vsrc.get(), n * 4, cudaMemcpyDeviceToDevice, c->stream));
+            ZB_CUDA(cudaEventRecord(e0, c->stream));
+            nd = sort_count(c, a.get(), b.get(), weights ? va.get() : nullptr, weights ? vb.get() : nullptr, n, key_bits,
+                            ok.get(), oc.get());
+            ZB_CUDA(cudaEventRecord(e1, c->stream));
+            ZB_CUDA(cudaStreamSynchronize(c->stream));
+            float ms = 0;
+            ZB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (it > 0 || iters == 1) total_ms += ms;
+        }
+    } catch (...) {
+        g_sort_count_mode = saved;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        throw;
+    }
+    g_sort_count_mode = saved;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_per_call) *ms_per_call = total_ms / (float)(iters > 1 ? iters - 1 : 1);
+    *n_out = nd;
+    if (nd && out_k) ZB_CUDA(cudaMemcpyAsync(out_k, ok.get(), nd * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (nd && out_c) ZB_CUDA(cudaMemcpyAsync(out_c, oc.get(), nd * 4, cudaMemcpyDeviceToHost, c->stream));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     ZB_CATCH
 }

@@ -14,7 +14,20 @@ namespace zb {
 // ping-ponged; returns 0 or 1 = which of (k0,v0)/(k1,v1) holds the sorted result.  v0/v1 may be
 // null (keys only).  Replaces zotmer/library/misc.py:400-424 (radix_sort).
 int radix_sort(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits);
+// Same, but only the bits [lo_bit, lo_bit + nbits) take part (stable): the first stage of sort_count.
+int radix_sort_range(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int lo_bit, int nbits);
 extern int g_sort_max_bits;  // digit width cap (8..11), tunable from bench via ZB_SORT_BITS
+
+// ---- segsort.cu ------------------------------------------------------------------------------
+// Sort + run-length count in one go (the hot path of kmerize: KmerAccumulator2.flush,
+// kmerize.py:412-424 = radix_sort + merge/RLE).  LSD passes run over the TOP bits of the key only, until
+// keys that still share those bits form short segments; one kernel then orders every segment in shared
+// memory, sums duplicates (weights v0, or 1 each when v0 == null) and writes distinct keys + counts.
+// k0/k1 (v0/v1) are ping-pong scratch and are destroyed; out_k/out_c (n entries) must not alias them.
+// Returns the number of distinct keys (synchronises).  Result is identical to radix_sort + reduce_by_key.
+size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
+                  uint64_t* out_k, uint32_t* out_c);
+extern int g_sort_count_mode;  // 0 = auto, 1 = always the classic full LSD sort + reduce_by_key (ZB_SORT_COUNT)
 
 // ---- setops.cu -------------------------------------------------------------------------------
 // Run-length count of a sorted key array (optionally weighted by `w`): distinct keys + counts.

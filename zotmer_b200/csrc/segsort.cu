@@ -1,0 +1,391 @@
+// segsort.cu -- sort + run-length count of u64 k-mer keys: the kernel behind KmerAccumulator2.flush
+// (zotmer/commands/kmerize.py:412-424: radix_sort of the pending list, misc.py:400-424, then merge()/RLE,
+// kmerize.py:41-132).  Same result as a full LSD sort followed by reduce_by_key, with far fewer passes over
+// the whole array:
+//
+//   1. stable LSD passes (sort.cu onesweep) over the TOP T = 8 * P bits of the key only.  P is chosen from n
+//      so that the keys sharing those T bits ("a segment", contiguous after step 1) number ~1..16 on average
+//      for well-spread keys, more where a key is repeated many times.
+//   2. segsort_count_kernel: a CTA stages 4096 consecutive keys in shared memory and owns the segments that
+//      START in its first 3584 positions (the last 512 are the halo a segment may run into).  Inside a
+//      tile every key is inserted into a shared-memory hash table (one CAS; the first key of a value becomes
+//      its "head"), heads are compacted in position order, every key adds its weight to its head, every head
+//      ranks itself among the (few) heads of its own segment.  A chained scan over CTAs turns the tile-local
+//      head index into the global output position.  Work per key is O(distinct values per segment), so highly
+//      repeated keys are cheap.
+//   3. segments longer than 512 keys ("big": one value repeated > 512 times in the batch, or a badly skewed
+//      key space) are skipped by step 2 and only listed; they are gathered into a side array, sorted and
+//      counted by the classic path (radix_sort + reduce_by_key) and merged back (merge-path).  Usually a few
+//      percent of the keys or nothing at all.
+//
+// Algorithmic bytes: P * 16 B/key (top passes) + 8 B/key (histogram) + 8 B/key (this kernel) + 12 B/distinct.
+#include <algorithm>
+#include <vector>
+
+#include "kernels.h"
+
+namespace zb {
+
+int g_sort_count_mode = 0;
+
+static constexpr int SS_THREADS = 512;
+static constexpr int SS_PER = 8;
+static constexpr int SS_LOADED = SS_THREADS * SS_PER;      // positions staged by a CTA (4096)
+static constexpr int SS_HALO = 512;                        // longest segment ordered in shared memory
+static constexpr int SS_TILE = SS_LOADED - SS_HALO;        // positions whose segments a CTA owns
+static constexpr int SS_PADDED = SS_LOADED + SS_LOADED / SS_PER;
+static constexpr int SS_HASH = 2 * SS_LOADED;              // slots of the tile-local hash table (load <= 0.5)
+#define SS_EMPTY 0xffffffffu
+
+// one pad slot per 8 keys: thread t reads positions 8t .. 8t+7, so the lane stride is 9 keys (no bank conflicts)
+__device__ __forceinline__ int ss_idx(int q) { return q + (q >> 3); }
+
+// highest set bit <= b in a 4096-bit mask (-1 if none)
+__device__ __forceinline__ int mask_prev(const uint32_t* m, int b) {
+    int w = b >> 5;
+    uint32_t v = m[w] & (0xffffffffu >> (31 - (b & 31)));
+    while (!v && w > 0) v = m[--w];
+    return v ? (w << 5) + 31 - __clz(v) : -1;
+}
+// lowest set bit >= b (SS_LOADED if none); b may equal SS_LOADED
+__device__ __forceinline__ int mask_next(const uint32_t* m, int b) {
+    if (b >= SS_LOADED) return SS_LOADED;
+    int w = b >> 5;
+    uint32_t v = m[w] & (0xffffffffu << (b & 31));
+    while (!v && w < SS_LOADED / 32 - 1) v = m[++w];
+    return v ? (w << 5) + __ffs(v) - 1 : SS_LOADED;
+}
+
+// CTA `tile` writes its distinct keys, ordered, to tmp_k/tmp_c[tile * SS_LOADED ...] and their number to
+// tile_heads[tile]; segcompact_kernel moves them to their final place once the per-tile counts are scanned
+// (no CTA ever waits for another one).
+// Shared memory: keys 36 KB + hash table 32 KB + 3 KB of bit masks / prefixes = 71 KB -> 3 CTAs (48 warps) per
+// SM; the weighted form adds the staged weights (18 KB) and a 32-bit sum per position (16 KB) -> 2 CTAs per SM.
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(SS_THREADS, WEIGHTED ? 2 : 3)
+segsort_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ w, uint64_t n, int lowbits,
+                     uint64_t* __restrict__ tmp_k, uint32_t* __restrict__ tmp_c, uint32_t* __restrict__ tile_heads,
+                     unsigned long long* __restrict__ big_n, uint64_t* __restrict__ big_start, uint64_t big_cap,
+                     unsigned int* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char ss_raw[];
+    uint64_t* sk = reinterpret_cast<uint64_t*>(ss_raw);                  // [SS_PADDED] staged keys
+    // slot = position of the value's head (low 16 bits) | number of keys with that value (high 16 bits,
+    // unweighted form only: a segment has at most SS_HALO keys)
+    uint32_t* table = reinterpret_cast<uint32_t*>(sk + SS_PADDED);       // [SS_HASH]
+    uint32_t* sflag = table + SS_HASH;                                   // [128] segment-start bits
+    uint32_t* shead = sflag + SS_LOADED / 32;                            // [128] head bits
+    uint32_t* shbase = shead + SS_LOADED / 32;                           // [SS_THREADS] heads before thread t's chunk
+    uint32_t* sw = shbase + SS_THREADS;                                  // [SS_PADDED] weights      (WEIGHTED)
+    uint32_t* wsum = sw + SS_PADDED;                                     // [SS_LOADED] sum per head position (WEIGHTED)
+    __shared__ uint32_t s_scan[SS_THREADS / 32 + 1];
+    __shared__ uint64_t s_halo;
+
+    const unsigned tid = threadIdx.x;
+    const uint32_t tile = blockIdx.x;
+    const uint64_t s = (uint64_t)tile * SS_TILE;
+    const int nvalid = (int)min((uint64_t)SS_LOADED + 1, n - s);   // positions q < nvalid hold data
+    {
+        const uint4 e4 = make_uint4(SS_EMPTY, SS_EMPTY, SS_EMPTY, SS_EMPTY);
+#pragma unroll
+        for (int j = 0; j < SS_HASH / 4 / SS_THREADS; j++) reinterpret_cast<uint4*>(table)[j * SS_THREADS + tid] = e4;
+        if (WEIGHTED) {
+#pragma unroll
+            for (int j = 0; j < SS_PER; j++) wsum[j * SS_THREADS + tid] = 0;
+        }
+    }
+    // ---- stage the keys (coalesced)
+#pragma unroll
+    for (int j = 0; j < SS_PER; j++) {
+        const int q = j * SS_THREADS + tid;
+        sk[ss_idx(q)] = (q < nvalid) ? __ldg(keys + s + q) : 0ull;
+        if (WEIGHTED) sw[ss_idx(q)] = (q < nvalid) ? __ldg(w + s + q) : 0u;
+    }
+    if (tid == 0) s_halo = (s > 0) ? __ldg(keys + s - 1) : 0ull;
+    __syncthreads();
+
+    // ---- my 8 consecutive positions; segment-start flags (a virtual start closes the data at q == nvalid)
+    const int q0 = tid * SS_PER;
+    uint32_t headbits = 0;
+    {
+        uint64_t kx[SS_PER];
+#pragma unroll
+        for (int j = 0; j < SS_PER; j++) kx[j] = sk[ss_idx(q0 + j)];
+        uint32_t fb = 0;
+        {
+            uint64_t prev = tid ? sk[ss_idx(q0 - 1)] : s_halo;
+#pragma unroll
+            for (int j = 0; j < SS_PER; j++) {
+                const int q = q0 + j;
+                const bool f = (q < nvalid) ? ((s == 0 && q == 0) || (((kx[j] ^ prev) >> lowbits) != 0)) : (q == nvalid);
+                fb |= (f ? 1u : 0u) << j;
+                prev = kx[j];
+            }
+            reinterpret_cast<uint8_t*>(sflag)[tid] = (uint8_t)fb;
+        }
+        __syncthreads();
+
+        // ---- which positions are mine (their segment starts in my first SS_TILE positions and is short
+        // enough); phase A: one hash insert per key -- the first key to claim a value's slot becomes its head,
+        // every other key of that value adds itself to the slot's count.
+        int st = mask_prev(sflag, q0);
+        const int after = mask_next(sflag, q0 + SS_PER);
+        int en = after;
+        {
+            const uint32_t up = fb >> 1;
+            if (up) en = q0 + __ffs(up);
+        }
+#pragma unroll
+        for (int j = 0; j < SS_PER; j++) {
+            const int q = q0 + j;
+            if ((fb >> j) & 1u) {
+                st = q;
+                const uint32_t up = (j < SS_PER - 1) ? (fb >> (j + 1)) : 0u;
+                en = up ? q + __ffs(up) : after;
+                if (st < SS_TILE && q < nvalid && en - st > SS_HALO) {   // a big segment that I own: list it
+                    const unsigned long long slot = atomicAdd(big_n, 1ull);
+                    if (slot < big_cap) big_start[slot] = s + q;
+                }
+            }
+            const bool ok = st >= 0 && st < SS_TILE && (en - st) <= SS_HALO && q < nvalid;
+            if (ok) {
+                const uint64_t x = kx[j];
+                uint32_t h = (uint32_t)((x * 0x9E3779B97F4A7C15ull) >> 51);   // 13 bits
+                const uint32_t mine = WEIGHTED ? (uint32_t)q : ((uint32_t)q | 0x10000u);
+                uint32_t hq;
+                while (true) {
+                    const uint32_t old = atomicCAS(&table[h], SS_EMPTY, mine);
+                    if (old == SS_EMPTY) { headbits |= 1u << j; hq = (uint32_t)q; break; }
+                    if (sk[ss_idx((int)(old & 0xffffu))] == x) {
+                        hq = old & 0xffffu;
+                        if (!WEIGHTED) atomicAdd(&table[h], 0x10000u);
+                        break;
+                    }
+                    h = (h + 1) & (SS_HASH - 1);
+                }
+                if (WEIGHTED) {
+                    const uint32_t wt = sw[ss_idx(q)];
+                    const uint32_t old = atomicAdd(&wsum[hq], wt);
+                    if (old + wt < old) atomicExch(err, 1u);
+                }
+            }
+        }
+    }
+    reinterpret_cast<uint8_t*>(shead)[tid] = (uint8_t)headbits;
+    uint32_t H;
+    const uint32_t hbase = block_excl_scan<SS_THREADS, uint32_t, false>(__popc(headbits), s_scan, &H);
+    shbase[tid] = hbase;
+    if (tid == 0) tile_heads[tile] = H;
+    __syncthreads();
+
+    // ---- phase B: every head ranks itself among the heads of its segment and writes (key, count)
+    const uint64_t base = (uint64_t)tile * SS_LOADED;
+    uint32_t hb = headbits;
+    while (hb) {
+        const int j = __ffs(hb) - 1;
+        hb &= hb - 1;
+        const int q = q0 + j;
+        const uint64_t x = sk[ss_idx(q)];
+        const int st = mask_prev(sflag, q);
+        const int en = mask_next(sflag, q + 1);
+        const uint32_t hb0 = shbase[st >> 3] + __popc((shead[st >> 5] >> (st & 24)) & ((1u << (st & 7)) - 1u));
+        uint32_t r = 0;
+        for (int wd = st >> 5; wd <= (en - 1) >> 5; wd++) {
+            uint32_t bits = shead[wd];
+            if (wd == (st >> 5)) bits &= 0xffffffffu << (st & 31);
+            if (wd == (en >> 5)) bits &= (1u << (en & 31)) - 1u;   // en a multiple of 32: wd never reaches it
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                r += (sk[ss_idx((wd << 5) + b)] < x) ? 1u : 0u;
+            }
+        }
+        uint32_t cnt;
+        if (WEIGHTED) {
+            cnt = wsum[q];
+        } else {
+            uint32_t h = (uint32_t)((x * 0x9E3779B97F4A7C15ull) >> 51);
+            uint32_t e = table[h];
+            while ((e & 0xffffu) != (uint32_t)q) { h = (h + 1) & (SS_HASH - 1); e = table[h]; }
+            cnt = e >> 16;
+        }
+        tmp_k[base + hb0 + r] = x;
+        tmp_c[base + hb0 + r] = cnt;
+    }
+}
+
+// exclusive scan of the per-tile head counts (one CTA; a few ten thousand tiles)
+__global__ void __launch_bounds__(1024) segscan_kernel(const uint32_t* __restrict__ tile_heads, uint32_t tiles,
+                                                        uint64_t* __restrict__ tile_off, uint64_t* __restrict__ totals) {
+    __shared__ uint64_t sm[1024 / 32 + 1];
+    uint64_t carry = 0;
+    for (uint32_t b0 = 0; b0 < tiles; b0 += 1024) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint64_t v = (i < tiles) ? tile_heads[i] : 0;
+        uint64_t tot;
+        const uint64_t ex = block_excl_scan<1024, uint64_t>(v, sm, &tot);
+        if (i < tiles) tile_off[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) totals[0] = carry;
+}
+
+__global__ void __launch_bounds__(256)
+segcompact_kernel(const uint64_t* __restrict__ tmp_k, const uint32_t* __restrict__ tmp_c,
+                  const uint32_t* __restrict__ tile_heads, const uint64_t* __restrict__ tile_off,
+                  uint64_t* __restrict__ out_k, uint32_t* __restrict__ out_c) {
+    const uint32_t tile = blockIdx.x;
+    const uint32_t H = tile_heads[tile];
+    const uint64_t src = (uint64_t)tile * SS_LOADED, dst = tile_off[tile];
+    for (uint32_t i = threadIdx.x; i < H; i += 256) {
+        out_k[dst + i] = tmp_k[src + i];
+        out_c[dst + i] = tmp_c[src + i];
+    }
+}
+
+// first index in [lo, n) whose top bits differ from those of keys[start]
+__global__ void big_len_kernel(const uint64_t* __restrict__ keys, uint64_t n, int lowbits,
+                               const uint64_t* __restrict__ big_start, uint64_t nbig, uint64_t* __restrict__ big_len) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbig) return;
+    const uint64_t st = big_start[i];
+    const uint64_t v = keys[st] >> lowbits;
+    uint64_t lo = st + 1, hi = n;   // keys are ordered by their top bits
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if ((keys[mid] >> lowbits) > v) hi = mid; else lo = mid + 1;
+    }
+    big_len[i] = lo - st;
+}
+
+__global__ void __launch_bounds__(256)
+big_gather_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ w, const uint64_t* __restrict__ big_start,
+                  const uint64_t* __restrict__ big_off /*[nbig+1] exclusive*/, uint64_t nbig, uint64_t total,
+                  uint64_t* __restrict__ bk, uint32_t* __restrict__ bw) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t lo = 0, hi = nbig;   // last segment with off <= i
+        while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (big_off[mid] <= i) lo = mid; else hi = mid;
+        }
+        const uint64_t src = big_start[lo] + (i - big_off[lo]);
+        bk[i] = keys[src];
+        if (w) bw[i] = w[src];
+    }
+}
+
+static size_t sort_count_classic(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
+                                 uint64_t* out_k, uint32_t* out_c) {
+    int which;
+    {
+        Stage st(c, "sort");
+        which = radix_sort(c, k0, k1, v0, v1, n, key_bits);
+    }
+    Stage st(c, "count");
+    return reduce_by_key(c, which ? k1 : k0, v0 ? (which ? v1 : v0) : nullptr, n, out_k, out_c);
+}
+
+size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
+                  uint64_t* out_k, uint32_t* out_c) {
+    if (n == 0) return 0;
+    if (key_bits < 1) key_bits = 1;
+    if (key_bits > 64) key_bits = 64;
+    // top passes: T = 8 P bits with P = ceil((log2 n - 4) / 8)  ->  n / 2^T keys per segment in [1/16, 16)
+    int lg = 0;
+    while (lg < 63 && ((size_t)1 << lg) < n) lg++;
+    int P = (lg - 4 + 7) / 8;
+    if (P < 1) P = 1;
+    const int T = 8 * P;
+    if (g_sort_count_mode == 1 || key_bits < T + 8) return sort_count_classic(c, k0, k1, v0, v1, n, key_bits, out_k, out_c);
+    const int lowbits = key_bits - T;
+    const bool weighted = (v0 != nullptr);
+
+    int which;
+    {
+        Stage st(c, "sort");
+        which = radix_sort_range(c, k0, k1, v0, v1, n, lowbits, T);
+    }
+    const uint64_t* sk = which ? k1 : k0;
+    const uint32_t* sv = weighted ? (which ? v1 : v0) : nullptr;
+
+    const uint32_t tiles = (uint32_t)div_up(n, SS_TILE);
+    const size_t big_cap = n / (SS_HALO + 1) + 2;
+    DBuf<uint64_t> big_start(c, big_cap);
+    DBuf<uint64_t> tmp_k(c, (size_t)tiles * SS_LOADED);
+    DBuf<uint32_t> tmp_c(c, (size_t)tiles * SS_LOADED);
+    DBuf<uint32_t> tile_heads(c, tiles);
+    DBuf<uint64_t> tile_off(c, (size_t)tiles + 4);
+    uint64_t* totals = tile_off.get() + tiles;                                       // [0] distinct, [1] big count
+    unsigned int* err = reinterpret_cast<unsigned int*>(totals + 2);
+    ZB_CUDA(cudaMemsetAsync(totals, 0, 32, c->stream));
+    size_t smem = (size_t)SS_PADDED * 8 + (size_t)SS_HASH * 4 + 2 * (SS_LOADED / 32) * 4 + SS_THREADS * 4 +
+                  (weighted ? (size_t)SS_PADDED * 4 + (size_t)SS_LOADED * 4 : 0);
+    {
+        Stage st(c, "segcount");
+        if (weighted) {
+            ZB_CUDA(cudaFuncSetAttribute(segsort_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            segsort_count_kernel<true><<<tiles, SS_THREADS, smem, c->stream>>>(
+                sk, sv, n, lowbits, tmp_k.get(), tmp_c.get(), tile_heads.get(),
+                reinterpret_cast<unsigned long long*>(totals + 1), big_start.get(), big_cap, err);
+        } else {
+            ZB_CUDA(cudaFuncSetAttribute(segsort_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            segsort_count_kernel<false><<<tiles, SS_THREADS, smem, c->stream>>>(
+                sk, nullptr, n, lowbits, tmp_k.get(), tmp_c.get(), tile_heads.get(),
+                reinterpret_cast<unsigned long long*>(totals + 1), big_start.get(), big_cap, err);
+        }
+        ZB_LAUNCH_CHECK(c);
+        segscan_kernel<<<1, 1024, 0, c->stream>>>(tile_heads.get(), tiles, tile_off.get(), totals);
+        ZB_LAUNCH_CHECK(c);
+        segcompact_kernel<<<tiles, 256, 0, c->stream>>>(tmp_k.get(), tmp_c.get(), tile_heads.get(), tile_off.get(), out_k, out_c);
+        ZB_LAUNCH_CHECK(c);
+    }
+    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, totals, 32, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    size_t n_out = (size_t)c->h_scalars[0];
+    const size_t nbig = (size_t)c->h_scalars[1];
+    if (reinterpret_cast<uint32_t*>(c->h_scalars + 2)[0] != 0)
+        ZB_FAIL(ZB_E_RANGE, "k-mer count exceeds 2^32-1 (reference: array('I') OverflowError, kmerize.py:374)");
+    if (nbig == 0) return n_out;
+    if (nbig > big_cap) ZB_FAIL(ZB_E_CUDA, "sort_count: big-segment list overflow (%zu > %zu)", nbig, big_cap);
+
+    // ---- big segments: gather, classic sort + count, merge back
+    Stage st_big(c, "segcount_big");
+    struct ProfileOff {   // the nested classic sort must not add its (tiny) passes to the per-stage report
+        Ctx* c; bool saved;
+        explicit ProfileOff(Ctx* c_) : c(c_), saved(c_->profile) { c->profile = false; }
+        ~ProfileOff() { c->profile = saved; }
+    } profile_off(c);
+    DBuf<uint64_t> big_len(c, nbig);
+    big_len_kernel<<<(unsigned)div_up(nbig, 128), 128, 0, c->stream>>>(sk, n, lowbits, big_start.get(), nbig, big_len.get());
+    ZB_LAUNCH_CHECK(c);
+    std::vector<uint64_t> off(nbig + 1);
+    ZB_CUDA(cudaMemcpyAsync(off.data() + 1, big_len.get(), nbig * 8, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    off[0] = 0;
+    for (size_t i = 1; i <= nbig; i++) off[i] += off[i - 1];
+    const size_t nb = (size_t)off[nbig];
+    DBuf<uint64_t> d_off(c, nbig + 1);
+    ZB_CUDA(cudaMemcpyAsync(d_off.get(), off.data(), (nbig + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    DBuf<uint64_t> b0(c, nb), b1(c, nb), bk(c, nb);
+    DBuf<uint32_t> w0, w1, bc(c, nb);
+    if (weighted) { w0.alloc(c, nb); w1.alloc(c, nb); }
+    {
+        const int blocks = (int)std::min<size_t>((size_t)c->sm_count * 8, div_up(nb, 256));
+        big_gather_kernel<<<blocks, 256, 0, c->stream>>>(sk, sv, big_start.get(), d_off.get(), nbig, nb, b0.get(),
+                                                         weighted ? w0.get() : nullptr);
+        ZB_LAUNCH_CHECK(c);
+    }
+    ZB_CUDA(cudaStreamSynchronize(c->stream));   // `off` (pageable host memory) must stay alive until the copy is done
+    const int bw = radix_sort(c, b0.get(), b1.get(), weighted ? w0.get() : nullptr, weighted ? w1.get() : nullptr, nb, key_bits);
+    const size_t nbd = reduce_by_key(c, bw ? b1.get() : b0.get(), weighted ? (bw ? w1.get() : w0.get()) : nullptr, nb,
+                                     bk.get(), bc.get());
+    DBuf<uint64_t> mk(c, n_out + nbd);
+    DBuf<uint32_t> mc(c, n_out + nbd);
+    merge_pairs(c, out_k, out_c, n_out, bk.get(), bc.get(), nbd, mk.get(), mc.get());
+    n_out += nbd;
+    ZB_CUDA(cudaMemcpyAsync(out_k, mk.get(), n_out * 8, cudaMemcpyDeviceToDevice, c->stream));
+    ZB_CUDA(cudaMemcpyAsync(out_c, mc.get(), n_out * 4, cudaMemcpyDeviceToDevice, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    return n_out;
+}
+
+}  // namespace zb

@@ -290,14 +290,14 @@ static size_t onesweep_smem(bool vals) {
 }
 
 template <int BINS>
-static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
-                           int maxbits) {
+static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int lo_bit,
+                           int key_bits, int maxbits) {
     SortPlan plan;
     plan.passes = (key_bits + maxbits - 1) / maxbits;
     if (plan.passes < 1) plan.passes = 1;
     if (plan.passes > MAX_PASSES) ZB_FAIL(ZB_E_ARG, "radix_sort: %d passes needed (max %d)", plan.passes, MAX_PASSES);
     {
-        int base = key_bits / plan.passes, rem = key_bits % plan.passes, sh = 0;
+        int base = key_bits / plan.passes, rem = key_bits % plan.passes, sh = lo_bit;
         for (int p = 0; p < plan.passes; p++) {
             plan.bits[p] = base + (p < rem ? 1 : 0);
             if (plan.bits[p] < 1) plan.bits[p] = 1;
@@ -352,16 +352,22 @@ static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uin
     return cur;
 }
 
-int radix_sort(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits) {
+int radix_sort_range(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int lo_bit, int nbits) {
     if (n == 0) return 0;
     if (n >= (1ull << 30)) ZB_FAIL(ZB_E_ARG, "radix_sort: n=%zu exceeds 2^30 keys per batch", n);
-    if (key_bits < 1) key_bits = 1;
-    if (key_bits > 64) key_bits = 64;
+    if (lo_bit < 0) lo_bit = 0;
+    if (lo_bit > 63) lo_bit = 63;
+    if (nbits < 1) nbits = 1;
+    if (lo_bit + nbits > 64) nbits = 64 - lo_bit;
     int mb = g_sort_max_bits;
-    if (mb <= 8) return radix_sort_impl<256>(c, k0, k1, v0, v1, n, key_bits, 8);
-    if (mb == 9) return radix_sort_impl<512>(c, k0, k1, v0, v1, n, key_bits, 9);
-    if (mb == 10) return radix_sort_impl<1024>(c, k0, k1, v0, v1, n, key_bits, 10);
-    return radix_sort_impl<2048>(c, k0, k1, v0, v1, n, key_bits, 11);
+    if (mb <= 8) return radix_sort_impl<256>(c, k0, k1, v0, v1, n, lo_bit, nbits, 8);
+    if (mb == 9) return radix_sort_impl<512>(c, k0, k1, v0, v1, n, lo_bit, nbits, 9);
+    if (mb == 10) return radix_sort_impl<1024>(c, k0, k1, v0, v1, n, lo_bit, nbits, 10);
+    return radix_sort_impl<2048>(c, k0, k1, v0, v1, n, lo_bit, nbits, 11);
+}
+
+int radix_sort(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits) {
+    return radix_sort_range(c, k0, k1, v0, v1, n, 0, key_bits);
 }
 
 }  // namespace zb
