@@ -129,7 +129,8 @@ int zb_set_from_streams(int device, const uint64_t* kmer_words, size_t n_kmer_wo
 int zb_dbg_sort_u64(int device, uint64_t* keys, uint32_t* vals, size_t n, int key_bits, int max_bits, int iters,
                     float* ms_per_sort);
 /* sort + run-length count (weights NULL = 1 each): distinct keys ascending + summed counts; out arrays hold n
- * entries; mode 0 = segmented path when profitable, 1 = full LSD sort + reduce-by-key; both give the same result */
+ * entries; mode 0 = segmented path when profitable, 1 = full LSD sort + reduce-by-key, 2 = segmented path with the
+ * promise that the keys are distinct (weights = payload; ZB_E_ARG when the promise is broken) */
 int zb_dbg_sort_count(int device, const uint64_t* keys, const uint32_t* weights, size_t n, int key_bits, int mode,
                       int iters, uint64_t* out_k, uint32_t* out_c, size_t* n_out, float* ms_per_call);
 /* text -> dense base codes (codes must hold n + 64 bytes) */

@@ -117,7 +117,7 @@ def check_sort_count(nat, keys, bits, weights=None):
         assert np.array_equal(c.astype(np.uint64), ec), "mode %d: counts differ" % mode
 
 
-@pytest.mark.parametrize("n", [1, 2, 17, 3583, 3584, 3585, 4096, 4097, 7168, 100000, 1 << 20, 2500001])
+@pytest.mark.parametrize("n", [1, 2, 17, 3071, 3072, 3073, 4096, 4097, 6144, 100000, 1 << 20, 2500001])
 @pytest.mark.parametrize("bits,dup", [(50, 1), (50, 6), (62, 3), (64, 1), (32, 2), (24, 1)])
 def test_sort_count_random(nat, n, bits, dup):
     rng = np.random.default_rng(n * 7 + bits + dup)
@@ -129,10 +129,10 @@ def test_sort_count_random(nat, n, bits, dup):
     check_sort_count(nat, keys, bits)
 
 
-@pytest.mark.parametrize("seglen", [1, 2, 15, 16, 17, 100, 511, 512, 513, 1000, 3584, 5000])
+@pytest.mark.parametrize("seglen", [1, 2, 15, 16, 17, 100, 511, 513, 1023, 1024, 1025, 3072, 5000])
 def test_sort_count_segment_lengths(nat, seglen):
-    """keys sharing their top bits in groups of exactly `seglen`: around the 512-key limit of the in-shared-memory
-    path and across CTA boundaries (3584 owned positions), distinct and duplicated low parts"""
+    """keys sharing their top bits in groups of exactly `seglen`: around the 1024-key limit of the in-shared-memory
+    path and across CTA boundaries (3072 owned positions), distinct and duplicated low parts"""
     bits = 50
     nseg = max(3, 60000 // seglen)
     rng = np.random.default_rng(seglen)
@@ -163,7 +163,7 @@ def test_sort_count_heavy_repeats(nat):
     keys[rng.integers(0, n, 100000)] = hot[rng.integers(0, 40, 100000)]   # ~2500 copies each
     check_sort_count(nat, keys, 50)
     check_sort_count(nat, np.full(100000, 7, np.uint64), 50)              # one key only
-    check_sort_count(nat, np.full(513, (1 << 64) - 1, np.uint64), 64)
+    check_sort_count(nat, np.full(1025, (1 << 64) - 1, np.uint64), 64)
 
 
 @pytest.mark.parametrize("n", [5, 4097, 300000])
@@ -178,6 +178,23 @@ def test_sort_count_weighted(nat, n):
     rng.shuffle(keys)
     w = rng.integers(1, 2 ** 32 - 1, len(keys), dtype=np.uint32)
     check_sort_count(nat, keys, 50, w)
+
+
+@pytest.mark.parametrize("n", [3, 5000, 400000])
+def test_sort_count_distinct_payload(nat, n):
+    """mode 2: keys promised distinct, weights are a payload (the mirror sort of kmerize)"""
+    rng = np.random.default_rng(n + 1)
+    keys = np.unique(rng.integers(0, 2 ** 50, n, dtype=np.uint64))
+    rng.shuffle(keys)
+    w = rng.integers(0, 2 ** 32 - 1, len(keys), dtype=np.uint32)
+    k, c, _ = nat.dbg_sort_count(keys, w, 50, 2)
+    order = np.argsort(keys)
+    assert np.array_equal(k, keys[order]) and np.array_equal(c, w[order])
+    if n >= 5000:   # a broken promise is reported, not silently mis-sorted
+        bad = keys.copy()
+        bad[len(bad) // 2] = bad[len(bad) // 2 + 1]
+        with pytest.raises(Exception):
+            nat.dbg_sort_count(bad, w, 50, 2)
 
 
 def test_sort_count_weight_overflow(nat):

@@ -20,7 +20,15 @@ nat.dbg_profile(True)
 nat.dbg_sort_count(keys, None, 50, 0, iters=1)
 print({k: round(v[0], 3) for k, v in nat.dbg_profile(False).items()})
 w = c0
-k, c, ms = nat.dbg_sort_count(k0[::-1].copy(), w, 50, 0, iters=4)
-print("pairs (distinct, reversed): %d -> %.3f ms" % (len(k), ms))
-k, c, ms = nat.dbg_sort_count(k0[::-1].copy(), w, 50, 1, iters=4)
-print("pairs classic: %.3f ms" % ms)
+rk = (k0 * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(14)   # a bijection of distinct keys, like rc()
+for mode, nm in ((0, "weighted"), (2, "distinct+payload"), (1, "classic")):
+    k, c, ms = nat.dbg_sort_count(rk, w, 50, mode, iters=4)
+    print("pairs %s: %d -> %.3f ms" % (nm, len(k), ms), flush=True)
+os.environ["ZB_SORT_CFG"] = "2"   # all passes stable (A/B against the unstable first pass)
+for mode in (0, 1):
+    k, c, ms = nat.dbg_sort_count(keys, None, 50, mode, iters=4)
+    print("cfg all-stable mode %d: %d distinct, %.3f ms per sort+count" % (mode, len(k), ms), flush=True)
+    assert np.array_equal(k0, k) and np.array_equal(c0, c)
+nat.dbg_profile(True)
+nat.dbg_sort_count(keys, None, 50, 0, iters=1)
+print({k: round(v[0], 3) for k, v in nat.dbg_profile(False).items()})

@@ -290,6 +290,7 @@ int zb_kmerize_open(int k, int device, zb_kmerizer** out) {
     h->d_count.alloc(c, 2);
     ZB_CUDA(cudaMemsetAsync(h->d_count.get(), 0, 16, c->stream));
     if (const char* e = getenv("ZB_SORT_COUNT")) g_sort_count_mode = atoi(e);
+    if (const char* e = getenv("ZB_SORT_CFG")) g_sort_cfg = atoi(e);
     if (const char* e = getenv("ZB_MAX_PENDING")) {
         size_t v = strtoull(e, nullptr, 10);
         if (v >= (size_t)EXTRACT_TILE && v < ((size_t)1 << 30)) h->max_pending = v;
@@ -358,7 +359,7 @@ int zb_kmerize_finish(zb_kmerizer* h, zb_set** result, uint64_t* n_records) {
     {
         // the mirrored keys are distinct, so "sort + count" is a sort of (key, count) pairs
         Stage st(c, "mirror_sort");
-        const size_t nm2 = sort_count(c, rk.get(), rk2.get(), rc.get(), rc2.get(), nm, 2 * h->k, mk.get(), mc.get());
+        const size_t nm2 = sort_count(c, rk.get(), rk2.get(), rc.get(), rc2.get(), nm, 2 * h->k, mk.get(), mc.get(), true);
         if (nm2 != nm) ZB_FAIL(ZB_E_CUDA, "mirror: %zu distinct reverse complements of %zu keys", nm2, nm);
     }
     rk.release(); rk2.release(); rc.release(); rc2.release();
@@ -675,7 +676,8 @@ int zb_dbg_sort_count(int device, const uint64_t* keys, const uint32_t* weights,
     Ctx* c = ctx_for(device);
     if (!n_out) ZB_FAIL(ZB_E_ARG, "null argument");
     const int saved = g_sort_count_mode;
-    g_sort_count_mode = mode;
+    g_sort_count_mode = (mode == 1) ? 1 : 0;
+    if (const char* e = getenv("ZB_SORT_CFG")) g_sort_cfg = atoi(e);
     DBuf<uint64_t> src(c, n), a(c, n), b(c, n), ok(c, n);
     DBuf<uint32_t> vsrc, va, vb, oc(c, n);
     if (weights) { vsrc.alloc(c, n); va.alloc(c, n); vb.alloc(c, n); }
@@ -693,7 +695,7 @@ int zb_dbg_sort_count(int device, const uint64_t* keys, const uint32_t* weights,
             if (weights) ZB_CUDA(cudaMemcpyAsync(va.get(), vsrc.get(), n * 4, cudaMemcpyDeviceToDevice, c->stream));
             ZB_CUDA(cudaEventRecord(e0, c->stream));
             nd = sort_count(c, a.get(), b.get(), weights ? va.get() : nullptr, weights ? vb.get() : nullptr, n, key_bits,
-                            ok.get(), oc.get());
+                            ok.get(), oc.get(), mode == 2);
             ZB_CUDA(cudaEventRecord(e1, c->stream));
             ZB_CUDA(cudaStreamSynchronize(c->stream));
             float ms = 0;

@@ -15,8 +15,12 @@ namespace zb {
 // null (keys only).  Replaces zotmer/library/misc.py:400-424 (radix_sort).
 int radix_sort(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits);
 // Same, but only the bits [lo_bit, lo_bit + nbits) take part (stable): the first stage of sort_count.
-int radix_sort_range(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int lo_bit, int nbits);
-extern int g_sort_max_bits;  // digit width cap (8..11), tunable from bench via ZB_SORT_BITS
+// stable_first = false: equal keys may come out in any order even when a payload is attached (keys-only sorts
+// always take that liberty: it is unobservable) -- the first pass then ranks with one atomic per key.
+int radix_sort_range(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int lo_bit, int nbits,
+                     bool stable_first = true);
+extern int g_sort_max_bits;
+extern int g_sort_cfg;   // onesweep CTA shape, see sort.cu  // digit width cap (8..11), tunable from bench via ZB_SORT_BITS
 
 // ---- segsort.cu ------------------------------------------------------------------------------
 // Sort + run-length count in one go (the hot path of kmerize: KmerAccumulator2.flush,
@@ -25,8 +29,10 @@ extern int g_sort_max_bits;  // digit width cap (8..11), tunable from bench via 
 // memory, sums duplicates (weights v0, or 1 each when v0 == null) and writes distinct keys + counts.
 // k0/k1 (v0/v1) are ping-pong scratch and are destroyed; out_k/out_c (n entries) must not alias them.
 // Returns the number of distinct keys (synchronises).  Result is identical to radix_sort + reduce_by_key.
+// distinct = true: the caller guarantees that no key occurs twice (v0 is then a payload that is carried along);
+// a violation is detected and reported as ZB_E_ARG.
 size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
-                  uint64_t* out_k, uint32_t* out_c);
+                  uint64_t* out_k, uint32_t* out_c, bool distinct = false);
 extern int g_sort_count_mode;  // 0 = auto, 1 = always the classic full LSD sort + reduce_by_key (ZB_SORT_COUNT)
 
 // ---- setops.cu -------------------------------------------------------------------------------

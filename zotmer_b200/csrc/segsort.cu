@@ -7,13 +7,13 @@
 //      so that the keys sharing those T bits ("a segment", contiguous after step 1) number ~1..16 on average
 //      for well-spread keys, more where a key is repeated many times.
 //   2. segsort_count_kernel: a CTA stages 4096 consecutive keys in shared memory and owns the segments that
-//      START in its first 3584 positions (the last 512 are the halo a segment may run into).  Inside a
+//      START in its first 3072 positions (the last 1024 are the halo a segment may run into).  Inside a
 //      tile every key is inserted into a shared-memory hash table (one CAS; the first key of a value becomes
 //      its "head"), heads are compacted in position order, every key adds its weight to its head, every head
 //      ranks itself among the (few) heads of its own segment.  A chained scan over CTAs turns the tile-local
 //      head index into the global output position.  Work per key is O(distinct values per segment), so highly
 //      repeated keys are cheap.
-//   3. segments longer than 512 keys ("big": one value repeated > 512 times in the batch, or a badly skewed
+//   3. segments longer than 1024 keys ("big": one value repeated > 1024 times in the batch, or a badly skewed
 //      key space) are skipped by step 2 and only listed; they are gathered into a side array, sorted and
 //      counted by the classic path (radix_sort + reduce_by_key) and merged back (merge-path).  Usually a few
 //      percent of the keys or nothing at all.
@@ -31,7 +31,7 @@ int g_sort_count_mode = 0;
 static constexpr int SS_THREADS = 512;
 static constexpr int SS_PER = 8;
 static constexpr int SS_LOADED = SS_THREADS * SS_PER;      // positions staged by a CTA (4096)
-static constexpr int SS_HALO = 512;                        // longest segment ordered in shared memory
+static constexpr int SS_HALO = 1024;                        // longest segment ordered in shared memory
 static constexpr int SS_TILE = SS_LOADED - SS_HALO;        // positions whose segments a CTA owns
 static constexpr int SS_PADDED = SS_LOADED + SS_LOADED / SS_PER;
 static constexpr int SS_HASH = 2 * SS_LOADED;              // slots of the tile-local hash table (load <= 0.5)
@@ -61,8 +61,10 @@ __device__ __forceinline__ int mask_next(const uint32_t* m, int b) {
 // (no CTA ever waits for another one).
 // Shared memory: keys 36 KB + hash table 32 KB + 3 KB of bit masks / prefixes = 71 KB -> 3 CTAs (48 warps) per
 // SM; the weighted form adds the staged weights (18 KB) and a 32-bit sum per position (16 KB) -> 2 CTAs per SM.
-template <bool WEIGHTED>
-__global__ void __launch_bounds__(SS_THREADS, WEIGHTED ? 2 : 3)
+// MODE 0: count keys (weight 1 each); MODE 1: sum the u32 weights of equal keys; MODE 2: the keys are known to
+// be distinct and carry a u32 payload (the mirror sort of kmerize) -- no hash table, every key is a head.
+template <int MODE>
+__global__ void __launch_bounds__(SS_THREADS, MODE == 1 ? 2 : 3)
 segsort_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ w, uint64_t n, int lowbits,
                      uint64_t* __restrict__ tmp_k, uint32_t* __restrict__ tmp_c, uint32_t* __restrict__ tile_heads,
                      unsigned long long* __restrict__ big_n, uint64_t* __restrict__ big_start, uint64_t big_cap,
@@ -72,19 +74,21 @@ segsort_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restri
     // slot = position of the value's head (low 16 bits) | number of keys with that value (high 16 bits,
     // unweighted form only: a segment has at most SS_HALO keys)
     uint32_t* table = reinterpret_cast<uint32_t*>(sk + SS_PADDED);       // [SS_HASH]
-    uint32_t* sflag = table + SS_HASH;                                   // [128] segment-start bits
+    uint32_t* sflag = table + (MODE == 2 ? 0 : SS_HASH);                 // [128] segment-start bits
     uint32_t* shead = sflag + SS_LOADED / 32;                            // [128] head bits
     uint32_t* shbase = shead + SS_LOADED / 32;                           // [SS_THREADS] heads before thread t's chunk
     uint32_t* sw = shbase + SS_THREADS;                                  // [SS_PADDED] weights      (WEIGHTED)
     uint32_t* wsum = sw + SS_PADDED;                                     // [SS_LOADED] sum per head position (WEIGHTED)
     __shared__ uint32_t s_scan[SS_THREADS / 32 + 1];
     __shared__ uint64_t s_halo;
+    constexpr bool WEIGHTED = (MODE == 1);
+    constexpr bool DISTINCT = (MODE == 2);
 
     const unsigned tid = threadIdx.x;
     const uint32_t tile = blockIdx.x;
     const uint64_t s = (uint64_t)tile * SS_TILE;
     const int nvalid = (int)min((uint64_t)SS_LOADED + 1, n - s);   // positions q < nvalid hold data
-    {
+    if (!DISTINCT) {
         const uint4 e4 = make_uint4(SS_EMPTY, SS_EMPTY, SS_EMPTY, SS_EMPTY);
 #pragma unroll
         for (int j = 0; j < SS_HASH / 4 / SS_THREADS; j++) reinterpret_cast<uint4*>(table)[j * SS_THREADS + tid] = e4;
@@ -100,7 +104,7 @@ segsort_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restri
         sk[ss_idx(q)] = (q < nvalid) ? __ldg(keys + s + q) : 0ull;
         if (WEIGHTED) sw[ss_idx(q)] = (q < nvalid) ? __ldg(w + s + q) : 0u;
     }
-    if (tid == 0) s_halo = (s > 0) ? __ldg(keys + s - 1) : 0ull;
+    if (tid == 0) s_halo = (s > 0) ? __ldg(keys + s - 1) : ~__ldg(keys);   // the very first key always starts a segment
     __syncthreads();
 
     // ---- my 8 consecutive positions; segment-start flags (a virtual start closes the data at q == nvalid)
@@ -116,7 +120,7 @@ segsort_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restri
 #pragma unroll
             for (int j = 0; j < SS_PER; j++) {
                 const int q = q0 + j;
-                const bool f = (q < nvalid) ? ((s == 0 && q == 0) || (((kx[j] ^ prev) >> lowbits) != 0)) : (q == nvalid);
+                const bool f = (q < nvalid) ? (((kx[j] ^ prev) >> lowbits) != 0) : (q == nvalid);
                 fb |= (f ? 1u : 0u) << j;
                 prev = kx[j];
             }
@@ -147,7 +151,8 @@ segsort_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restri
                 }
             }
             const bool ok = st >= 0 && st < SS_TILE && (en - st) <= SS_HALO && q < nvalid;
-            if (ok) {
+            if (ok && DISTINCT) headbits |= 1u << j;
+            if (ok && !DISTINCT) {
                 const uint64_t x = kx[j];
                 uint32_t h = (uint32_t)((x * 0x9E3779B97F4A7C15ull) >> 51);   // 13 bits
                 const uint32_t mine = WEIGHTED ? (uint32_t)q : ((uint32_t)q | 0x10000u);
@@ -177,13 +182,27 @@ segsort_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restri
     if (tid == 0) tile_heads[tile] = H;
     __syncthreads();
 
-    // ---- phase B: every head ranks itself among the heads of its segment and writes (key, count)
+    // ---- phase B: every head ranks itself among the heads of its segment and writes (key, count).
+    // Heads are sparse (one key in six for 30x reads), so the heads of a warp's 256 positions are dealt out
+    // evenly to its 32 lanes: head number g of the warp goes to lane g % 32.
     const uint64_t base = (uint64_t)tile * SS_LOADED;
-    uint32_t hb = headbits;
-    while (hb) {
-        const int j = __ffs(hb) - 1;
-        hb &= hb - 1;
-        const int q = q0 + j;
+    const unsigned lane = tid & 31;
+    const uint32_t hinc = warp_incl_scan<uint32_t>(__popc(headbits));
+    const uint32_t Hw = __shfl_sync(0xffffffffu, hinc, 31);
+    const int wq0 = (int)(tid & ~31u) * SS_PER;
+    for (uint32_t g0 = 0; g0 < Hw; g0 += 32) {
+        const uint32_t g = g0 + lane;
+        int o = 0;   // owner lane: the first one whose inclusive head count exceeds g
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const uint32_t v = __shfl_sync(0xffffffffu, hinc, o + step - 1);
+            if (v <= g) o += step;
+        }
+        uint32_t obits = __shfl_sync(0xffffffffu, headbits, o);
+        const uint32_t oinc = __shfl_sync(0xffffffffu, hinc, o);
+        if (g >= Hw) continue;
+        for (uint32_t i = g - (oinc - __popc(obits)); i > 0; i--) obits &= obits - 1;   // my head's bit in the owner's mask
+        const int q = wq0 + o * SS_PER + __ffs(obits) - 1;
         const uint64_t x = sk[ss_idx(q)];
         const int st = mask_prev(sflag, q);
         const int en = mask_next(sflag, q + 1);
@@ -196,12 +215,16 @@ segsort_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restri
             while (bits) {
                 const int b = __ffs(bits) - 1;
                 bits &= bits - 1;
-                r += (sk[ss_idx((wd << 5) + b)] < x) ? 1u : 0u;
+                const uint64_t y = sk[ss_idx((wd << 5) + b)];
+                r += (y < x) ? 1u : 0u;
+                if (DISTINCT && y == x && (wd << 5) + b != q) atomicExch(err, 2u);   // the caller's promise is broken
             }
         }
         uint32_t cnt;
         if (WEIGHTED) {
             cnt = wsum[q];
+        } else if (DISTINCT) {
+            cnt = __ldg(w + s + q);
         } else {
             uint32_t h = (uint32_t)((x * 0x9E3779B97F4A7C15ull) >> 51);
             uint32_t e = table[h];
@@ -285,8 +308,9 @@ static size_t sort_count_classic(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v
 }
 
 size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
-                  uint64_t* out_k, uint32_t* out_c) {
+                  uint64_t* out_k, uint32_t* out_c, bool distinct) {
     if (n == 0) return 0;
+    if (distinct && !v0) ZB_FAIL(ZB_E_ARG, "sort_count: distinct mode needs a payload");
     if (key_bits < 1) key_bits = 1;
     if (key_bits > 64) key_bits = 64;
     // top passes: T = 8 P bits with P = ceil((log2 n - 4) / 8)  ->  n / 2^T keys per segment in [1/16, 16)
@@ -302,7 +326,7 @@ size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1
     int which;
     {
         Stage st(c, "sort");
-        which = radix_sort_range(c, k0, k1, v0, v1, n, lowbits, T);
+        which = radix_sort_range(c, k0, k1, v0, v1, n, lowbits, T, false);
     }
     const uint64_t* sk = which ? k1 : k0;
     const uint32_t* sv = weighted ? (which ? v1 : v0) : nullptr;
@@ -317,20 +341,24 @@ size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1
     uint64_t* totals = tile_off.get() + tiles;                                       // [0] distinct, [1] big count
     unsigned int* err = reinterpret_cast<unsigned int*>(totals + 2);
     ZB_CUDA(cudaMemsetAsync(totals, 0, 32, c->stream));
-    size_t smem = (size_t)SS_PADDED * 8 + (size_t)SS_HASH * 4 + 2 * (SS_LOADED / 32) * 4 + SS_THREADS * 4 +
-                  (weighted ? (size_t)SS_PADDED * 4 + (size_t)SS_LOADED * 4 : 0);
+    const int mode = !weighted ? 0 : (distinct ? 2 : 1);
+    const size_t smem = (size_t)SS_PADDED * 8 + (mode == 2 ? 0 : (size_t)SS_HASH * 4) + 2 * (SS_LOADED / 32) * 4 +
+                        SS_THREADS * 4 + (mode == 1 ? (size_t)SS_PADDED * 4 + (size_t)SS_LOADED * 4 : 0);
     {
         Stage st(c, "segcount");
-        if (weighted) {
-            ZB_CUDA(cudaFuncSetAttribute(segsort_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            segsort_count_kernel<true><<<tiles, SS_THREADS, smem, c->stream>>>(
-                sk, sv, n, lowbits, tmp_k.get(), tmp_c.get(), tile_heads.get(),
-                reinterpret_cast<unsigned long long*>(totals + 1), big_start.get(), big_cap, err);
+        unsigned long long* bign = reinterpret_cast<unsigned long long*>(totals + 1);
+        if (mode == 1) {
+            ZB_CUDA(cudaFuncSetAttribute(segsort_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            segsort_count_kernel<1><<<tiles, SS_THREADS, smem, c->stream>>>(
+                sk, sv, n, lowbits, tmp_k.get(), tmp_c.get(), tile_heads.get(), bign, big_start.get(), big_cap, err);
+        } else if (mode == 2) {
+            ZB_CUDA(cudaFuncSetAttribute(segsort_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            segsort_count_kernel<2><<<tiles, SS_THREADS, smem, c->stream>>>(
+                sk, sv, n, lowbits, tmp_k.get(), tmp_c.get(), tile_heads.get(), bign, big_start.get(), big_cap, err);
         } else {
-            ZB_CUDA(cudaFuncSetAttribute(segsort_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            segsort_count_kernel<false><<<tiles, SS_THREADS, smem, c->stream>>>(
-                sk, nullptr, n, lowbits, tmp_k.get(), tmp_c.get(), tile_heads.get(),
-                reinterpret_cast<unsigned long long*>(totals + 1), big_start.get(), big_cap, err);
+            ZB_CUDA(cudaFuncSetAttribute(segsort_count_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            segsort_count_kernel<0><<<tiles, SS_THREADS, smem, c->stream>>>(
+                sk, nullptr, n, lowbits, tmp_k.get(), tmp_c.get(), tile_heads.get(), bign, big_start.get(), big_cap, err);
         }
         ZB_LAUNCH_CHECK(c);
         segscan_kernel<<<1, 1024, 0, c->stream>>>(tile_heads.get(), tiles, tile_off.get(), totals);
@@ -342,6 +370,8 @@ size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     size_t n_out = (size_t)c->h_scalars[0];
     const size_t nbig = (size_t)c->h_scalars[1];
+    if (reinterpret_cast<uint32_t*>(c->h_scalars + 2)[0] == 2)
+        ZB_FAIL(ZB_E_ARG, "sort_count: keys promised to be distinct are not");
     if (reinterpret_cast<uint32_t*>(c->h_scalars + 2)[0] != 0)
         ZB_FAIL(ZB_E_RANGE, "k-mer count exceeds 2^32-1 (reference: array('I') OverflowError, kmerize.py:374)");
     if (nbig == 0) return n_out;

@@ -17,8 +17,8 @@ namespace zb {
 
 int g_sort_max_bits = 8;
 
-static constexpr int SORT_ITEMS = 16;
 static constexpr int MAX_PASSES = 8;
+int g_sort_cfg = 0;   // 0: 256 threads x 16 keys per CTA, 1: 512 threads x 8 keys (ZB_SORT_CFG; 256-bin digits only)
 // threads per CTA for a given digit width: the tile (threads x 16 keys) grows with the number of bins so
 // that the per-digit work (warp prefix, chained scan) per key stays constant
 template <int BINS> struct SortCfg { static constexpr int THREADS = (BINS <= 256) ? 256 : 512; };
@@ -86,8 +86,11 @@ __global__ void __launch_bounds__(BINS > 1024 ? 1024 : BINS) sort_scan_kernel(ui
 #define ST32_PFX 0x80000000u
 #define ST32_VAL 0x3fffffffu
 
-template <int BINS, int SORT_THREADS, bool HAS_VALS>
-__global__ void __launch_bounds__(SORT_THREADS, (SORT_THREADS * (BINS <= 512 ? 64 : 128) <= 16384 ? 4 : 2))
+// STABLE = false: keys of one digit value may leave the tile in any order (allowed for the FIRST pass of an
+// LSD sort, where no earlier order has to be kept): the rank inside the tile is simply the return value of one
+// shared-memory atomicAdd per key, no warp matching and no per-warp histograms.
+template <int BINS, int SORT_THREADS, int SORT_ITEMS, bool HAS_VALS, bool STABLE>
+__global__ void __launch_bounds__(SORT_THREADS, (SORT_ITEMS == 8 ? 3 : (SORT_THREADS * (BINS <= 512 ? 64 : 128) <= 16384 ? 4 : 2)))
 onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const uint32_t* __restrict__ vin,
                 uint32_t* __restrict__ vout, uint32_t n, int shift, int bits,
                 const uint32_t* __restrict__ bin_start /*[BINS] global exclusive*/,
@@ -134,6 +137,46 @@ onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, c
         key[j] = (idx < n_valid) ? __ldg(kin + tile_base + idx) : ~0ull;
     }
 
+    uint16_t pos[SORT_ITEMS];
+    constexpr int PER = (BINS + SORT_THREADS - 1) / SORT_THREADS;  // digits per thread (blocked)
+    uint32_t cnt[PER], binst[PER];
+    if (!STABLE) {
+        // ---- unstable ranking: rank inside (tile, digit) = return value of the atomic
+        uint32_t* thist = whist;            // [BINS] counts, then tile-local bin starts
+#pragma unroll
+        for (int j = 0; j < SORT_ITEMS; j++) {   // padding keys of the last tile take no part
+            const bool valid = wbase + j * 32 + lane < n_valid;
+            pos[j] = valid ? (uint16_t)atomicAdd(&thist[(uint32_t)(key[j] >> shift) & dmask], 1u) : (uint16_t)0;
+        }
+        __syncthreads();
+        uint32_t csum = 0;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int d = tid * PER + q;
+            uint32_t s = 0;
+            if (d < nbins) {
+                s = thist[d];
+                st_volatile_u32(status + (size_t)tile * BINS + d, (tile == 0 ? ST32_PFX : ST32_AGG) | s);
+            }
+            cnt[q] = s;
+            csum += s;
+        }
+        uint32_t tot;
+        uint32_t ex = block_excl_scan<SORT_THREADS, uint32_t, false>(csum, s_scan, &tot);
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int d = tid * PER + q;
+            binst[q] = ex;
+            if (d < nbins) thist[d] = ex;
+            ex += cnt[q];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < SORT_ITEMS; j++) {
+            const uint32_t idx = wbase + j * 32 + lane;
+            pos[j] = (idx < n_valid) ? (uint16_t)(pos[j] + thist[(uint32_t)(key[j] >> shift) & dmask]) : (uint16_t)idx;
+        }
+    } else {
     // ---- (1) early counts: per-warp digit histogram with one shared-memory atomic per key, so that
     // the tile's aggregate can be published BEFORE the (long) ranking phase and the chained scan of
     // the following tiles never has to wait for it.
@@ -143,8 +186,6 @@ onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, c
     __syncthreads();
 
     // ---- (2) per digit: exclusive prefix over warps -> tile count, publish it, tile-local bin starts
-    constexpr int PER = (BINS + SORT_THREADS - 1) / SORT_THREADS;  // digits per thread (blocked)
-    uint32_t cnt[PER], binst[PER];
     uint32_t csum = 0;
 #pragma unroll
     for (int q = 0; q < PER; q++) {
@@ -181,7 +222,6 @@ onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, c
     // is built by OR-ing lane bits into a per-(warp,digit) shared word (one ATOMS per key; MATCH.ANY is
     // microcoded on sm_100 and a ballot per digit bit costs ~40 instructions per key, see profiles/).
     // Every lane reads the cursor of its (warp,digit), the lowest lane of the group advances it.
-    uint16_t pos[SORT_ITEMS];
     const unsigned lt = lanemask_lt();
     const uint32_t lanebit = 1u << lane;
     if (ATOMIC_MATCH) {
@@ -218,6 +258,8 @@ onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, c
             pos[j] = (uint16_t)(cur + __popc(m & lt));
             __syncwarp();
         }
+    }
+
     }
 
     // ---- (4) chained scan across tiles, one status word per (tile, digit); predecessors published
@@ -281,17 +323,16 @@ onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, c
     }
 }
 
-template <int BINS>
+template <int BINS, int SORT_THREADS, int SORT_ITEMS>
 static size_t onesweep_smem(bool vals) {
-    constexpr int SORT_THREADS = SortCfg<BINS>::THREADS;
     constexpr int SORT_WARPS = SORT_THREADS / 32;
     constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     return (size_t)SORT_TILE * 8 + (vals ? (size_t)SORT_TILE * 4 : 0) + (size_t)SORT_WARPS * BINS * 4 + BINS * 4;
 }
 
-template <int BINS>
+template <int BINS, int SORT_THREADS, int SORT_ITEMS>
 static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int lo_bit,
-                           int key_bits, int maxbits) {
+                           int key_bits, int maxbits, bool stable_first) {
     SortPlan plan;
     plan.passes = (key_bits + maxbits - 1) / maxbits;
     if (plan.passes < 1) plan.passes = 1;
@@ -305,7 +346,6 @@ static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uin
             sh += plan.bits[p];
         }
     }
-    constexpr int SORT_THREADS = SortCfg<BINS>::THREADS;
     constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     const bool vals = (v0 != nullptr);
     const uint32_t tiles = (uint32_t)div_up(n, SORT_TILE);
@@ -327,32 +367,34 @@ static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uin
         sort_scan_kernel<BINS><<<plan.passes, (BINS > 1024 ? 1024 : BINS), 0, c->stream>>>(ghist.get());
         ZB_LAUNCH_CHECK(c);
     }
-    size_t sm = onesweep_smem<BINS>(vals);
-    if (vals)
-        ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    else
-        ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    size_t sm = onesweep_smem<BINS, SORT_THREADS, SORT_ITEMS>(vals);
+    ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, SORT_ITEMS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, SORT_ITEMS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, SORT_ITEMS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, SORT_ITEMS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     uint64_t* kb[2] = {k0, k1};
     uint32_t* vb[2] = {v0, v1};
     int cur = 0;
     for (int p = 0; p < plan.passes; p++) {
         ZB_CUDA(cudaMemsetAsync(status.get(), 0, (size_t)tiles * BINS * 4, c->stream));
         Stage st_p(c, vals ? "sort_pass_pairs" : "sort_pass_keys");
-        if (vals)
-            onesweep_kernel<BINS, SORT_THREADS, true><<<tiles, SORT_THREADS, sm, c->stream>>>(
-                kb[cur], kb[cur ^ 1], vb[cur], vb[cur ^ 1], (uint32_t)n, plan.shift[p], plan.bits[p],
-                ghist.get() + (size_t)p * BINS, status.get(), ticket.get() + p);
-        else
-            onesweep_kernel<BINS, SORT_THREADS, false><<<tiles, SORT_THREADS, sm, c->stream>>>(
-                kb[cur], kb[cur ^ 1], nullptr, nullptr, (uint32_t)n, plan.shift[p], plan.bits[p],
-                ghist.get() + (size_t)p * BINS, status.get(), ticket.get() + p);
+        // the first pass has no earlier order to keep: unstable ranking (keys only, or when the caller allows it)
+        const bool stable = !(p == 0 && (!vals || !stable_first)) || g_sort_cfg == 2;
+#define ZB_ONESWEEP(V, S)                                                                                          \
+        onesweep_kernel<BINS, SORT_THREADS, SORT_ITEMS, V, S><<<tiles, SORT_THREADS, sm, c->stream>>>(              \
+            kb[cur], kb[cur ^ 1], vals ? vb[cur] : nullptr, vals ? vb[cur ^ 1] : nullptr, (uint32_t)n, plan.shift[p], \
+            plan.bits[p], ghist.get() + (size_t)p * BINS, status.get(), ticket.get() + p)
+        if (vals) { if (stable) ZB_ONESWEEP(true, true); else ZB_ONESWEEP(true, false); }
+        else { if (stable) ZB_ONESWEEP(false, true); else ZB_ONESWEEP(false, false); }
+#undef ZB_ONESWEEP
         ZB_LAUNCH_CHECK(c);
         cur ^= 1;
     }
     return cur;
 }
 
-int radix_sort_range(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int lo_bit, int nbits) {
+int radix_sort_range(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int lo_bit, int nbits,
+                     bool stable_first) {
     if (n == 0) return 0;
     if (n >= (1ull << 30)) ZB_FAIL(ZB_E_ARG, "radix_sort: n=%zu exceeds 2^30 keys per batch", n);
     if (lo_bit < 0) lo_bit = 0;
@@ -360,14 +402,15 @@ int radix_sort_range(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t*
     if (nbits < 1) nbits = 1;
     if (lo_bit + nbits > 64) nbits = 64 - lo_bit;
     int mb = g_sort_max_bits;
-    if (mb <= 8) return radix_sort_impl<256>(c, k0, k1, v0, v1, n, lo_bit, nbits, 8);
-    if (mb == 9) return radix_sort_impl<512>(c, k0, k1, v0, v1, n, lo_bit, nbits, 9);
-    if (mb == 10) return radix_sort_impl<1024>(c, k0, k1, v0, v1, n, lo_bit, nbits, 10);
-    return radix_sort_impl<2048>(c, k0, k1, v0, v1, n, lo_bit, nbits, 11);
+    if (mb <= 8 && g_sort_cfg == 1) return radix_sort_impl<256, 512, 8>(c, k0, k1, v0, v1, n, lo_bit, nbits, 8, stable_first);
+    if (mb <= 8) return radix_sort_impl<256, 256, 16>(c, k0, k1, v0, v1, n, lo_bit, nbits, 8, stable_first);
+    if (mb == 9) return radix_sort_impl<512, 512, 16>(c, k0, k1, v0, v1, n, lo_bit, nbits, 9, stable_first);
+    if (mb == 10) return radix_sort_impl<1024, 512, 16>(c, k0, k1, v0, v1, n, lo_bit, nbits, 10, stable_first);
+    return radix_sort_impl<2048, 512, 16>(c, k0, k1, v0, v1, n, lo_bit, nbits, 11, stable_first);
 }
 
 int radix_sort(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits) {
-    return radix_sort_range(c, k0, k1, v0, v1, n, 0, key_bits);
+    return radix_sort_range(c, k0, k1, v0, v1, n, 0, key_bits, true);
 }
 
 }  // namespace zb
