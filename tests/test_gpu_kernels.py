@@ -478,6 +478,61 @@ def test_codec_streams(nat):
         nat.encode_stream(np.array([2 ** 61], np.uint64))
 
 
+@pytest.mark.parametrize("n", [2047, 2048, 2049, 4096 + 3, 6 * 2048, 700001])
+@pytest.mark.parametrize("kind", ["small", "mixed", "runs", "wide"])
+def test_codec_device_vs_oracle(nat, n, kind):
+    """the device codec against the C restatement of codec64.py: word-for-word, around the 2048-value encode tiles
+    and the 512-word decode tiles, with group patterns that straddle tile edges"""
+    rng = np.random.default_rng(n + len(kind))
+    if kind == "small":
+        v = rng.integers(0, 1024, n, dtype=np.uint64)                      # 6 per word
+    elif kind == "mixed":
+        v = rng.integers(0, 2 ** 60, n, dtype=np.uint64) >> rng.integers(0, 60, n).astype(np.uint64)
+    elif kind == "runs":                                                   # long runs of one width, then a switch
+        width = np.repeat(rng.choice([3, 10, 12, 15, 20, 30, 60], n // 97 + 1), 97)[:n].astype(np.uint64)
+        v = rng.integers(0, 2 ** 60, n, dtype=np.uint64) >> (np.uint64(60) - width)
+    else:
+        v = rng.integers(2 ** 59, 2 ** 60, n, dtype=np.uint64)             # 1 per word
+    w = nat.encode_stream(v, False)
+    assert np.array_equal(w, co.encode(v, False))
+    assert np.array_equal(nat.decode_stream(w, False), v)
+    s = np.cumsum(v >> np.uint64(24), dtype=np.uint64)                     # ascending "k-mers", gaps of mixed widths
+    w = nat.encode_stream(s, True)
+    assert np.array_equal(w, co.encode(s, True))
+    assert np.array_equal(nat.decode_stream(w, True), s)
+
+
+def test_codec_set_streams_and_errors(nat):
+    rng = np.random.default_rng(77)
+    n = 300000
+    k = np.unique(rng.integers(0, 2 ** 50, n, dtype=np.uint64))
+    c = rng.integers(1, 5000, len(k), dtype=np.uint32)
+    c[::1000] = 2 ** 32 - 1
+    s = nat.KmerSet.from_arrays(k, c)
+    kw, cw = s.encode()
+    assert np.array_equal(kw, co.encode(k, True)) and np.array_equal(cw, co.encode(c.astype(np.uint64), False))
+    t = nat.KmerSet.from_streams(kw, cw)
+    tk, tc = t.fetch()
+    assert np.array_equal(tk, k) and np.array_equal(tc, c)
+    u = nat.KmerSet.from_streams(kw, None)                                 # counts default to 1 (files.py:152-156)
+    uk, uc = u.fetch()
+    assert np.array_equal(uk, k) and (uc == 1).all()
+    e = nat.KmerSet.from_streams(np.zeros(0, np.uint64), np.zeros(0, np.uint64))
+    assert len(e) == 0 and e.encode()[0].size == 0
+    with pytest.raises(AssertionError):                                    # streams of different length (files.py:182)
+        nat.KmerSet.from_streams(kw, cw[:-1])
+    bad = kw.copy()
+    bad[len(bad) // 2] = (bad[len(bad) // 2] & ~np.uint64(15)) | np.uint64(9)
+    with pytest.raises(AssertionError):                                    # unknown tag (codec64.py:128)
+        nat.decode_stream(bad, True)
+    big = co.encode(np.array([5, 2 ** 32, 7], np.uint64), False)           # a count beyond u32
+    with pytest.raises(IndexError):
+        nat.KmerSet.from_streams(co.encode(np.array([1, 2, 3], np.uint64), True), big)
+    wide = np.array([1, 2 ** 62], np.uint64)                               # gap > 60 bits
+    with pytest.raises(IndexError):
+        nat.encode_stream(wide, True)
+
+
 def test_device_bucketing_matches_host_owner_function(nat):
     """zb_kmerize_take_bucketed_dev (csrc/extract.cu owner_of) vs zotmer_b200.multigpu.owner_of"""
     import torch

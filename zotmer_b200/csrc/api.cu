@@ -108,13 +108,6 @@ void dtrim(Ctx* c) {
 
 using namespace zb;
 
-struct zb_set {
-    Ctx* c;
-    DBuf<uint64_t> k;
-    DBuf<uint32_t> cnt;
-    size_t n;
-};
-
 struct zb_kmerizer {
     Ctx* c;
     int k;
@@ -128,16 +121,6 @@ struct zb_kmerizer {
     uint64_t n_records = 0;
     size_t max_pending = (size_t)1 << 29;
 };
-
-#define ZB_TRY try {
-#define ZB_CATCH                                   \
-    }                                              \
-    catch (const zb::Fail& f) { return f.code; }   \
-    catch (const std::bad_alloc&) {                \
-        zb::set_error("out of host memory");       \
-        return ZB_E_NOMEM;                         \
-    }                                              \
-    return ZB_OK;
 
 static size_t read_pending_count(zb_kmerizer* h) {
     Ctx* c = h->c;
@@ -448,10 +431,7 @@ int zb_set_from_host(int device, const uint64_t* kmers, const uint32_t* counts, 
         if (counts) {
             ZB_CUDA(cudaMemcpyAsync(s->cnt.get(), counts, n * 4, cudaMemcpyHostToDevice, c->stream));
         } else {
-            std::vector<uint32_t> ones(std::min<size_t>(n, 1 << 20), 1u);
-            for (size_t o = 0; o < n; o += ones.size())
-                ZB_CUDA(cudaMemcpyAsync(s->cnt.get() + o, ones.data(), std::min(ones.size(), n - o) * 4,
-                                        cudaMemcpyHostToDevice, c->stream));
+            fill_u32(c, s->cnt.get(), n, 1u);
         }
         ZB_CUDA(cudaStreamSynchronize(c->stream));
     }

@@ -1,10 +1,30 @@
 // kernels.h -- internal host-side entry points of the CUDA translation units (not part of the C ABI).
 #pragma once
+#include <new>
 #include <string>
 #include <utility>
 #include <vector>
 
 #include "common.cuh"
+
+// the handle behind `zb_set*` (include/zotmer_b200.h): a device-resident counted k-mer set
+struct zb_set {
+    zb::Ctx* c;
+    zb::DBuf<uint64_t> k;
+    zb::DBuf<uint32_t> cnt;
+    size_t n;
+};
+
+// body of every extern "C" entry point: no exception crosses the C boundary
+#define ZB_TRY try {
+#define ZB_CATCH                                   \
+    }                                              \
+    catch (const zb::Fail& f) { return f.code; }   \
+    catch (const std::bad_alloc&) {                \
+        zb::set_error("out of host memory");       \
+        return ZB_E_NOMEM;                         \
+    }                                              \
+    return ZB_OK;
 
 namespace zb {
 
@@ -56,6 +76,7 @@ size_t project_keys(Ctx* c, const uint64_t* k, size_t n, int shift, uint64_t* ok
 // Histogram of counts in first-occurrence order + acgt tallies.  kmerize.py:544-545, merge.py:158-159.
 void set_stats(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, uint64_t acgt_w[4], uint64_t acgt_p[4],
                uint64_t* total, std::vector<std::pair<uint64_t, uint64_t>>* hist_first_order);
+void fill_u32(Ctx* c, uint32_t* p, size_t n, uint32_t v);
 // Intersection / difference cardinalities for a batch of pairs.  library/dist.py:241-265.
 struct SetRef {
     const uint64_t* k;

@@ -167,6 +167,15 @@ size_t reduce_by_key(Ctx* c, const uint64_t* keys, const uint32_t* w, size_t n, 
     return (size_t)n_out;
 }
 
+__global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint64_t n, uint32_t v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+void fill_u32(Ctx* c, uint32_t* p, size_t n, uint32_t v) {
+    if (n == 0) return;
+    fill_u32_kernel<<<(unsigned)std::min<size_t>(div_up(n, 256), (size_t)c->sm_count * 16), 256, 0, c->stream>>>(p, n, v);
+    ZB_LAUNCH_CHECK(c);
+}
+
 // ---------------------------------------------------------------------------------------------
 // merge-path merge of two sorted (key,count) lists; ties: A first, so equal keys end up adjacent.
 // Reference: zotmer/commands/merge.py:26-86 (two-pointer merge); the count sum is done by
