@@ -463,6 +463,81 @@ def test_pairs_abc(nat):
         assert tuple(int(v) for v in abc[p]) == co.split(sets[I[p]], sets[J[p]]), (I[p], J[p])
 
 
+def _rand_sets(rng, sizes, bits, share=0.5):
+    pool = np.unique(rng.integers(0, 2 ** bits, int(max(sizes) * 2) + 8, dtype=np.uint64))
+    out = []
+    for n in sizes:
+        m = min(n, len(pool))
+        own = np.unique(rng.integers(0, 2 ** bits, int(n * (1 - share)) + 1, dtype=np.uint64))
+        a = np.unique(np.concatenate([rng.choice(pool, int(m * share), replace=False), own]))
+        out.append(a if n else np.zeros(0, np.uint64))
+    return out
+
+
+@pytest.mark.parametrize("sizes,bits", [
+    ([3000, 1, 0, 2500, 7], 50),                       # fewer sets than one block, an empty set
+    ([20000] * 8 + [500], 50),                         # a block boundary (9 sets)
+    ([60000, 100, 40000, 0, 0, 3, 70000, 65000, 12, 9999, 30000, 30001, 64, 63, 65, 50000, 1000], 62),
+    ([5000] * 19, 20),                                 # dense small key space (20 bits: many shared keys)
+    ([150000] * 5, 64),
+])
+def test_allpairs_abc(nat, sizes, bits):
+    """tiled all-pairs cardinalities against the two-pointer oracle (library/dist.py:241-265) and the
+    pair-at-a-time kernel, whole matrix and tile shards"""
+    rng = np.random.default_rng(len(sizes) * 1000 + bits)
+    arrs = _rand_sets(rng, sizes, bits)
+    sets = [nat.KmerSet.from_arrays(a) for a in arrs]
+    n = len(sets)
+    I, J = np.triu_indices(n, 1)
+    abc = nat.allpairs_abc(sets)
+    ref = nat.pairs_abc(sets, I, J)
+    assert np.array_equal(abc, ref)
+    for p in range(0, len(I), max(1, len(I) // 40)):
+        assert tuple(int(v) for v in abc[p]) == co.split(arrs[I[p]], arrs[J[p]]), (I[p], J[p])
+    # shards over tile ranges add up to the whole matrix and do not overlap
+    nt = nat.allpairs_tiles(n)
+    tot = np.zeros_like(abc)
+    cuts = sorted(set([0, nt // 3, (2 * nt) // 3, nt]))
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        part = nat.allpairs_abc(sets, a, b)
+        assert not ((part != 0) & (tot != 0)).any()
+        tot += part
+    assert np.array_equal(tot, abc)
+
+
+def test_allpairs_all_ones_key(nat):
+    """k = 32: the k-mer TTT...T is 2^64-1, the value the kernel's hash tables use as their empty marker"""
+    rng = np.random.default_rng(9)
+    top = np.uint64(2 ** 64 - 1)
+    arrs = []
+    for i in range(11):
+        a = np.unique(rng.integers(0, 2 ** 63, 3000, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, 3000, dtype=np.uint64))
+        a = a[a != top]
+        if i % 3 != 1:
+            a = np.concatenate([a, np.array([top], np.uint64)])
+        arrs.append(a)
+    arrs[4] = np.concatenate([arrs[0][::2], arrs[4]])
+    arrs[4] = np.unique(arrs[4])
+    sets = [nat.KmerSet.from_arrays(a) for a in arrs]
+    I, J = np.triu_indices(len(sets), 1)
+    abc = nat.allpairs_abc(sets)
+    for p in range(len(I)):
+        assert tuple(int(v) for v in abc[p]) == co.split(arrs[I[p]], arrs[J[p]]), (I[p], J[p])
+
+
+def test_allpairs_skewed_keys_fall_back(nat):
+    """all keys share their top bits (one bucket holds everything): the tiled kernel cannot stage that and
+    the pair-at-a-time path must take over with the same result"""
+    rng = np.random.default_rng(5)
+    arrs = [np.unique(rng.integers(0, 40000, 20000, dtype=np.uint64)) | np.uint64(1 << 49) for _ in range(10)]
+    arrs[3] = np.concatenate([np.arange(10, dtype=np.uint64), arrs[3]])
+    sets = [nat.KmerSet.from_arrays(a) for a in arrs]
+    I, J = np.triu_indices(len(sets), 1)
+    abc = nat.allpairs_abc(sets)
+    for p in range(len(I)):
+        assert tuple(int(v) for v in abc[p]) == co.split(arrs[I[p]], arrs[J[p]])
+
+
 def test_codec_streams(nat):
     rng = np.random.default_rng(12)
     for n in (0, 1, 6, 7, 1000, 100000):

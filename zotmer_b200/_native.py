@@ -48,6 +48,8 @@ SIGNATURES = {
     "zb_trim": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
     "zb_project": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
     "zb_pairs_abc": (C.c_int, [C.c_int, C.POINTER(vp), vp, vp, C.c_size_t, vp]),
+    "zb_allpairs_tiles": (C.c_int, [C.c_int, u64p]),
+    "zb_allpairs_abc": (C.c_int, [C.c_int, C.POINTER(vp), C.c_uint64, C.c_uint64, vp]),
     "zb_encode_u64_stream": (C.c_int, [C.c_int, vp, C.c_size_t, C.c_int, vp, C.POINTER(C.c_size_t)]),
     "zb_decode_u64_stream": (C.c_int, [C.c_int, vp, C.c_size_t, C.c_int, vp, C.POINTER(C.c_size_t)]),
     "zb_set_encode": (C.c_int, [vp, vp, C.POINTER(C.c_size_t), vp, C.POINTER(C.c_size_t)]),
@@ -223,6 +225,24 @@ def pairs_abc(sets, I, J):
     arr = (vp * len(sets))(*[s.h for s in sets])
     out = np.zeros((len(I), 3), np.uint64)
     _check(lib().zb_pairs_abc(len(sets), arr, _ptr(I), _ptr(J), len(I), _ptr(out.reshape(-1)) if len(I) else None))
+    return out
+
+
+def allpairs_tiles(nsets):
+    n = C.c_uint64(0)
+    _check(lib().zb_allpairs_tiles(nsets, C.byref(n)))
+    return n.value
+
+
+def allpairs_abc(sets, tile_begin=0, tile_end=0):
+    """(|X n Y|, |X \\ Y|, |Y \\ X|) for all pairs i < j in row-major order -> uint64 array [n (n - 1) / 2, 3];
+    with a tile range only the pairs of those tiles are filled, the others are 0 (multi-GPU shards add up)"""
+    n = len(sets)
+    out = np.zeros((n * (n - 1) // 2, 3), np.uint64)
+    if n < 2:
+        return out
+    arr = (vp * n)(*[s.h for s in sets])
+    _check(lib().zb_allpairs_abc(n, arr, tile_begin, tile_end, _ptr(out.reshape(-1))))
     return out
 
 

@@ -79,7 +79,7 @@ def allPairsABC(sets):
     """(a,b,c) for every i<j in row-major order -> uint64 [npairs, 3]"""
     N = len(sets)
     (I, J) = np.triu_indices(N, 1)
-    return (I, J, _native.pairs_abc(sets, I, J))
+    return (I, J, _native.allpairs_abc(sets))
 
 
 def main(argv):

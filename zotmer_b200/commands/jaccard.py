@@ -82,7 +82,12 @@ def _line(xnm, ynm, xz, yz, isec, union, p):
 def _report(names, sets, pairs, p):
     I = np.array([i for (i, j) in pairs], dtype=np.uint32)
     J = np.array([j for (i, j) in pairs], dtype=np.uint32)
-    abc = _native.pairs_abc(sets, I, J)
+    n = len(sets)
+    if n > 2 and len(pairs) == n * (n - 1) // 2:
+        # -a over every input: the tiled all-pairs kernel (same row-major pair order)
+        abc = _native.allpairs_abc(sets)
+    else:
+        abc = _native.pairs_abc(sets, I, J)
     sizes = [len(s) for s in sets]
     for q in range(len(pairs)):
         (i, j) = pairs[q]

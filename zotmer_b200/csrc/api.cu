@@ -573,6 +573,37 @@ int zb_pairs_abc(int nsets, zb_set* const* sets, const uint32_t* I, const uint32
         refs[i].k = sets[i]->k.get();
         refs[i].n = sets[i]->n;
     }
+    pairs_abc_host(c, refs, I, J, npairs, abc);
+    ZB_CATCH
+}
+
+int zb_allpairs_tiles(int nsets, uint64_t* n_tiles) {
+    if (nsets < 0 || !n_tiles) { zb::set_error("bad argument"); return ZB_E_ARG; }
+    *n_tiles = allpairs_tiles(nsets);
+    return ZB_OK;
+}
+
+int zb_allpairs_abc(int nsets, zb_set* const* sets, uint64_t tile_begin, uint64_t tile_end, uint64_t* abc) {
+    ZB_TRY
+    if (nsets < 1 || !sets || (nsets > 1 && !abc)) ZB_FAIL(ZB_E_ARG, "bad argument");
+    Ctx* c = sets[0]->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    std::vector<SetRef> refs(nsets);
+    for (int i = 0; i < nsets; i++) {
+        if (!sets[i] || sets[i]->c != c) ZB_FAIL(ZB_E_ARG, "sets must live on one device");
+        refs[i].k = sets[i]->k.get();
+        refs[i].n = sets[i]->n;
+    }
+    allpairs_abc(c, refs, tile_begin, tile_end, abc);
+    ZB_CATCH
+}
+
+}  // extern "C"
+
+namespace zb {
+// (|X n Y|, |X \ Y|, |Y \ X|) for a list of pairs, one merge-path pass per pair (setops.cu pairs_abc_kernel)
+void pairs_abc_host(Ctx* c, const std::vector<SetRef>& refs, const uint32_t* I, const uint32_t* J, size_t npairs, uint64_t* abc) {
+    const int nsets = (int)refs.size();
     DBuf<SetRef> d_refs(c, nsets);
     ZB_CUDA(cudaMemcpyAsync(d_refs.get(), refs.data(), nsets * sizeof(SetRef), cudaMemcpyHostToDevice, c->stream));
     const size_t TILE = 4096;
@@ -606,8 +637,10 @@ int zb_pairs_abc(int nsets, zb_set* const* sets, const uint32_t* I, const uint32
         }
         p0 = p1;
     }
-    ZB_CATCH
 }
+}  // namespace zb
+
+extern "C" {
 
 // ------------------------------------------------------------------------------- diagnostics
 // Stage-level entry points used by tests/ and bench.py (kernel isolation); not part of the drop-in surface.

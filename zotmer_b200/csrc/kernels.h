@@ -85,6 +85,16 @@ struct SetRef {
 void pairs_abc(Ctx* c, const SetRef* d_sets, const uint32_t* d_I, const uint32_t* d_J, size_t npairs, uint64_t* d_abc,
                uint64_t total_work);
 
+void pairs_abc_host(Ctx* c, const std::vector<SetRef>& refs, const uint32_t* I, const uint32_t* J, size_t npairs, uint64_t* abc);
+
+// ---- allpairs.cu -----------------------------------------------------------------------------
+// All pairs i < j of `refs`: abc[3p .. 3p+2] with p = i (2n - i - 1) / 2 + (j - i - 1), bucketed by key range and
+// tiled by blocks of 8 sets in shared memory.  Only the block pairs ("tiles", row-major over the upper triangle
+// incl. the diagonal) in [tile_begin, tile_end) are computed (tile_end 0 = all); the rest of abc is zero, so
+// the shards of several GPUs add up to the full matrix.  library/dist.py:241-265, jaccard.py:31-54.
+uint64_t allpairs_tiles(int nsets);
+void allpairs_abc(Ctx* c, const std::vector<SetRef>& refs, uint64_t tile_begin, uint64_t tile_end, uint64_t* abc_host);
+
 // ---- parse.cu --------------------------------------------------------------------------------
 // Raw FASTA/FASTQ bytes (device) -> dense base codes (0..3, 4 = break).  `codes` must have room for
 // n + 64 bytes.  Returns number of codes written and the number of records (synchronises).
