@@ -498,10 +498,18 @@ def test_allpairs_abc(nat, sizes, bits):
     nt = nat.allpairs_tiles(n)
     tot = np.zeros_like(abc)
     cuts = sorted(set([0, nt // 3, (2 * nt) // 3, nt]))
+    from zotmer_b200 import multigpu
+    assert nt == multigpu.n_tiles(n)
     for a, b in zip(cuts[:-1], cuts[1:]):
         part = nat.allpairs_abc(sets, a, b)
         assert not ((part != 0) & (tot != 0)).any()
         tot += part
+        # the device's tile -> pairs map is the host's (zotmer_b200/multigpu.py tile_pairs)
+        mine = np.zeros(len(abc), bool)
+        for t in range(a, b):
+            for (i, j) in multigpu.tile_pairs(n, t):
+                mine[multigpu.pair_index(n, i, j)] = True
+        assert np.array_equal(part[mine], abc[mine]) and not part[~mine].any()
     assert np.array_equal(tot, abc)
 
 

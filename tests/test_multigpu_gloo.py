@@ -83,3 +83,65 @@ def test_exchange_gloo(world):
         p.join(timeout=120)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert dict(ret) == {r: "ok" for r in range(world)}
+
+
+# ------------------------------------------------------------------------------------------------
+# all-pairs distance matrix: tiling and sharding
+@pytest.mark.parametrize("nsets", [1, 2, 7, 8, 9, 16, 17, 41])
+def test_tiles_cover_every_pair_once(nsets):
+    seen = {}
+    for t in range(multigpu.n_tiles(nsets)):
+        bi, bj = multigpu.tile_blocks(nsets, t)
+        assert bi <= bj
+        for (i, j) in multigpu.tile_pairs(nsets, t):
+            assert i < j < nsets and (i, j) not in seen
+            seen[(i, j)] = t
+    assert len(seen) == nsets * (nsets - 1) // 2
+    idx = sorted(multigpu.pair_index(nsets, i, j) for (i, j) in seen)
+    assert idx == list(range(len(seen)))
+    for world in (1, 2, 3, 8):
+        rs = multigpu.tile_ranges(nsets, world)
+        assert rs[0][0] == 0 and rs[-1][1] == multigpu.n_tiles(nsets)
+        assert all(rs[r][1] == rs[r + 1][0] for r in range(world - 1))
+
+
+def _host_tiles(arrs, b, e):
+    """numpy stand-in for zotmer_b200._native.allpairs_abc(sets, b, e)"""
+    n = len(arrs)
+    out = np.zeros((n * (n - 1) // 2, 3), np.uint64)
+    for t in range(b, e):
+        for (i, j) in multigpu.tile_pairs(n, t):
+            a = len(np.intersect1d(arrs[i], arrs[j], assume_unique=True))
+            out[multigpu.pair_index(n, i, j)] = (a, len(arrs[i]) - a, len(arrs[j]) - a)
+    return out
+
+
+def _pairs_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(3)
+        pool = rng.integers(0, 2 ** 40, 4000, dtype=np.uint64)
+        arrs = [np.unique(pool[rng.integers(0, len(pool), int(rng.integers(0, 1500)))]) for _ in range(19)]
+        full = multigpu.allpairs_sharded(lambda b, e: _host_tiles(arrs, b, e), len(arrs), dist, rank, world)
+        assert np.array_equal(full, _host_tiles(arrs, 0, multigpu.n_tiles(len(arrs))))
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_allpairs_sharded_gloo(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_pairs_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert dict(ret) == {r: "ok" for r in range(world)}

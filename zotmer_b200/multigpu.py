@@ -8,6 +8,11 @@ so ownership is uniform even on low-complexity sequence -- with ONE all-to-all o
 and every rank sorts and counts its disjoint share locally.  x and rc(x) land on different owners, which
 is fine: the canonical key is what is routed, mirroring happens after counting on the owner.
 
+All-pairs distances (`zot dist`, `zot jaccard -a`) shard without any exchange: the upper triangle of the
+set x set matrix is cut into tiles (pairs of blocks of 8 sets, csrc/allpairs.cu), every rank computes a
+contiguous, pair-count-balanced range of tiles over its own copy of the sets, and the partial matrices (zero
+outside a rank's tiles) are added up -- the "final gather" of the north star.
+
 `owner_of` is the host (numpy) statement of the device function in csrc/extract.cu; tests check one
 against the other.  `exchange_tensors` is backend-agnostic (NCCL on GPUs, gloo in the CPU tests).
 """
@@ -88,3 +93,68 @@ def exchange_pending(nat, km, ctx):
     ctx["a2a_ms"].append(t0.elapsed_time(t1))
     ctx["a2a_bytes"].append(8 * (n - counts[ctx["rank"]]))
     km.add_canonical_dev(recv.data_ptr(), sum(recv_counts))
+
+
+# ------------------------------------------------------------------------------------------------
+# all-pairs distance matrix: tiles of 8 x 8 sets, sharded over ranks
+AP_S = 8   # sets per block, csrc/allpairs.cu
+
+
+def tile_blocks(nsets, t):
+    """tile number -> (bi, bj), bi <= bj: row-major over the upper triangle of blocks, diagonal included
+    (host statement of csrc/allpairs.cu tile_to_blocks)"""
+    nblk = -(-nsets // AP_S)
+    r, start = 0, 0
+    while start + (nblk - r) <= t:
+        start += nblk - r
+        r += 1
+    return r, r + (t - start)
+
+
+def tile_pairs(nsets, t):
+    """the set pairs (i < j) a tile covers"""
+    bi, bj = tile_blocks(nsets, t)
+    out = []
+    for i in range(bi * AP_S, min((bi + 1) * AP_S, nsets)):
+        for j in range(max(bj * AP_S, i + 1), min((bj + 1) * AP_S, nsets)):
+            out.append((i, j))
+    return out
+
+
+def n_tiles(nsets):
+    nblk = -(-nsets // AP_S)
+    return nblk * (nblk + 1) // 2
+
+
+def tile_ranges(nsets, world):
+    """contiguous tile ranges [(begin, end)] per rank with about the same number of set pairs each"""
+    nt = n_tiles(nsets)
+    w = np.array([len(tile_pairs(nsets, t)) for t in range(nt)], dtype=np.int64) if nt < 200000 else np.full(nt, 64)
+    cum = np.concatenate([[0], np.cumsum(w)])
+    total = int(cum[-1])
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(cum, total * r / world, side="left")))
+    cuts.append(nt)
+    cuts = [min(max(c, 0), nt) for c in cuts]
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def pair_index(nsets, i, j):
+    """row-major index of pair (i < j) in the upper triangle"""
+    return i * (2 * nsets - i - 1) // 2 + (j - i - 1)
+
+
+def allpairs_sharded(compute_tiles, nsets, dist, rank, world, device="cpu"):
+    """every rank computes its tile range with compute_tiles(begin, end) -> uint64 [npairs, 3] (zeros outside its
+    tiles; zotmer_b200._native.allpairs_abc on a GPU), then one all-reduce adds the shards up.
+    Returns the full matrix on every rank."""
+    import torch
+    b, e = tile_ranges(nsets, world)[rank]
+    part = compute_tiles(b, e)
+    t = torch.from_numpy(np.ascontiguousarray(part).view(np.int64).copy()).to(device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy().view(np.uint64)
