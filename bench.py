@@ -290,6 +290,9 @@ def run_ours(args, rank, world, local_rank):
         tl = torch.tensor([float(launches)], dtype=torch.float64, device="cuda:%d" % dev)
         dist.all_reduce(tl, op=dist.ReduceOp.SUM)
         launches = int(tl[0])
+    pairs = None
+    if not args.no_pairs:
+        pairs = bench_pairs(nat, dev, rank, world, max(2, min(args.steps, 3)))
     if rank != 0:
         return
     total_bases = bases * world
@@ -334,9 +337,89 @@ def run_ours(args, rank, world, local_rank):
         a_b = float(np.mean(dist_ctx["a2a_bytes"]))
         line["nvlink"] = {"all_to_all_ms": a_ms, "bytes_sent_per_gpu": a_b, "GBps_per_gpu_out": a_b / a_ms / 1e6,
                           "peak_GBps_per_direction": 900.0, "measured_peer_copy_GBps": 770.0}
+    if pairs is not None:
+        if world == 1 and not args.no_cpu_baseline:
+            pairs["cpu_baseline"] = cpu_baseline_pairs(pairs)
+        line["pairs"] = pairs
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line))
+
+
+PAIR_SETS = int(os.environ.get("ZB_BENCH_PAIR_SETS", 32))
+
+
+def bench_pairs(nat, dev, rank, world, steps):
+    """BASELINE.json's second metric, pairwise Jaccard set-pairs/s, on a bounded instance of config[3]:
+    PAIR_SETS synthetic bacterial k-mer sets (k=25, both strands, ~9.9 M k-mers each; 4 clades of related
+    genomes), all pairs.  Device-resident: the sets live in HBM (zb_allpairs_abc, CUDA-event kernel time);
+    e2e: the same call including the D2H of the (a, b, c) matrix and the Jaccard values on the host.
+    N > 1: every rank holds all sets and computes its share of the 8 x 8 tiles; one all-reduce adds them up."""
+    import torch
+    from tools import synth
+    from zotmer_b200 import multigpu
+    nclades = max(1, PAIR_SETS // 8)
+    base = [synth.genome(GENOME, seed=1000 + c) for c in range(nclades)]
+    sets = []
+    for i in range(PAIR_SETS):
+        g = synth.mutate(base[i % nclades], 0.001 + 0.009 * (i // nclades) / max(1, PAIR_SETS // nclades), 2000 + i)
+        km = nat.Kmerizer(K, dev)
+        km.feed(synth.fasta_bytes(g), True)
+        s, _ = km.finish()
+        km.close()
+        sets.append(s.project(0))     # Measure.prep: k-mers only (commands/dist.py:29-49)
+        s.free()
+    npairs = PAIR_SETS * (PAIR_SETS - 1) // 2
+    b, e = multigpu.tile_ranges(PAIR_SETS, world)[rank]
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+    def step():
+        part = nat.allpairs_abc(sets, b, e)
+        if world > 1:
+            t = torch.from_numpy(part.view(np.int64)).to("cuda:%d" % dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            part = t.cpu().numpy().view(np.uint64)
+        jac = part[:, 0].astype(np.float64) / np.maximum(part.sum(axis=1), 1).astype(np.float64)
+        return part, jac
+
+    step()
+    torch.cuda.synchronize(dev)
+    nat.device_sync(dev)
+    if world > 1:
+        dist.barrier()
+    nat.dbg_profile(True, dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        abc, jac = step()
+    nat.device_sync(dev)
+    if world > 1:
+        dist.barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / steps
+    prof = nat.dbg_profile(False, dev)
+    kern_ms = prof.get("allpairs", (0.0, 1))[0] / steps
+    vals = [kern_ms, wall_ms]
+    if world > 1:
+        tt = torch.tensor(vals, dtype=torch.float64, device="cuda:%d" % dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        kern_ms, wall_ms = float(tt[0]), float(tt[1])
+    sizes = [len(s) for s in sets]
+    pair_bytes = 8.0 * float(sum(sizes)) * (PAIR_SETS - 1)      # sum over pairs of 8 (|X| + |Y|)
+    for s in sets:
+        s.free()
+    peak, _ = load_peaks()
+    return {"metric": "pairwise Jaccard set-pairs/s", "value": npairs / (kern_ms * 1e-3), "unit": "set-pairs/s",
+            "e2e": {"value": npairs / (wall_ms * 1e-3), "unit": "set-pairs/s", "d2h_bytes_per_step": int(npairs * 24)},
+            "config": {"workload": "config[3] bounded: all pairs of %d synthetic bacterial k-mer sets (k=25, ~%d k-mers each, "
+                                   "%d clades)" % (PAIR_SETS, int(np.mean(sizes)), nclades),
+                       "pairs": npairs, "parallelism": "1 GPU" if world == 1 else "%d GPUs: tiles of 8x8 sets sharded, one all-reduce" % world},
+            "ms_per_step": kern_ms,
+            "roofline": {"bound": "hbm (pair-at-a-time model)", "achieved": pair_bytes / (kern_ms * 1e-3) / 1e9, "peak": peak * world,
+                         "unit": "GB/s", "frac": pair_bytes / (kern_ms * 1e-3) / 1e9 / (peak * world),
+                         "note": "numerator = 8 (|X| + |Y|) B per pair (SURVEY.md 8d); the tiled kernel reads every set about once "
+                                 "from HBM and re-uses it from L2 / shared memory, so this can exceed 1"},
+            "check": {"jaccard_first_pair": float(jac[0]), "max_jaccard": float(jac.max())}}
 
 
 def stage_keys(nat, dev, d_in, nbytes):
@@ -368,6 +451,24 @@ def cpu_baseline():
                           os.cpu_count())}
 
 
+def cpu_baseline_pairs(pairs):
+    """the reference's two-pointer split() (library/dist.py:241-265, oracle port, pure Python, 1 thread) on a bounded
+    sample: two sorted arrays of 300,000 k-mers with half of them shared; cost is linear in |X| + |Y|"""
+    from oracle import zot_oracle as zo
+    rng = np.random.default_rng(4)
+    m = 300000
+    pool = np.unique(rng.integers(0, 2 ** 50, 2 * m, dtype=np.uint64))
+    xs = [int(v) for v in np.sort(rng.choice(pool, m, replace=False))]
+    ys = [int(v) for v in np.sort(rng.choice(pool, m, replace=False))]
+    t0 = time.perf_counter()
+    zo.split(xs, ys)
+    dt = time.perf_counter() - t0
+    per_pair_elems = 2.0 * float(pairs["config"]["workload"].split("~")[1].split(" ")[0])
+    return {"value": 1.0 / (dt * per_pair_elems / (2.0 * m)), "unit": "set-pairs/s", "cores": 1, "kind": "port",
+            "sample": "split() on 2 x %d k-mers took %.2f s; scaled linearly to the %.0f k-mers of one pair of this "
+                      "workload (one measure; the reference repeats split() per measure)" % (m, dt, per_pair_elems)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -375,6 +476,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pairs", action="store_true", help="skip the set-pairs/s measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
