@@ -75,8 +75,23 @@ int zb_kmerize_close(zb_kmerizer* h);
  * receives the sizes; d_keys (device, capacity >= zb_kmerize_pending) the keys grouped by owner. */
 int zb_kmerize_pending(zb_kmerizer* h, uint64_t* n_keys);
 int zb_kmerize_take_bucketed_dev(zb_kmerizer* h, int nranks, uint64_t* d_keys, uint64_t* bucket_counts);
+/* The same exchange fused into one kernel over NVLink peer memory: zb_kmerize_bucket_counts tells how many of the
+ * pending keys each owner gets (so that the ranks can agree on write offsets), zb_kmerize_route_p2p then writes
+ * every pending key to d_dst[owner][...] -- d_dst[r] points into rank r's receive buffer (this rank's own memory
+ * for r == self, a buffer opened with zb_ipc_open otherwise), already advanced to this rank's slot in it.
+ * Returns after all stores have completed; the pending list is empty afterwards. */
+int zb_kmerize_bucket_counts(zb_kmerizer* h, int nranks, uint64_t* bucket_counts);
+int zb_kmerize_route_p2p(zb_kmerizer* h, int nranks, uint64_t* const* d_dst);
+/* device buffers that other processes on the node can map (cudaIpc*): alloc/free on the owner, open/close on peers */
+int zb_ipc_alloc(int device, size_t bytes, void** d_ptr, uint8_t handle[64]);
+int zb_ipc_open(int device, const uint8_t handle[64], void** d_ptr);
+int zb_ipc_close(int device, void* d_ptr);
+int zb_ipc_free(int device, void* d_ptr);
 /* count canonical keys received from peers (device array, any order) into the kmerizer */
 int zb_kmerize_add_canonical_dev(zb_kmerizer* h, const uint64_t* d_keys, size_t n);
+/* the same without the copy: the caller's array itself is sorted in place (its contents are destroyed) when the
+ * kmerizer next counts -- at the latest in zb_kmerize_finish; it must stay valid and untouched until then */
+int zb_kmerize_adopt_canonical_dev(zb_kmerizer* h, uint64_t* d_keys, size_t n);
 
 /* ------------------------------------------------------------------------------------------
  * counted sets

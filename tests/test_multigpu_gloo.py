@@ -85,6 +85,20 @@ def test_exchange_gloo(world):
     assert dict(ret) == {r: "ok" for r in range(world)}
 
 
+def test_p2p_offsets_tile_every_receive_buffer():
+    """slots of the fused exchange: per owner, the runs of all sources are disjoint, in source order and gap-free"""
+    rng = np.random.default_rng(2)
+    for world in (1, 2, 3, 8):
+        M = rng.integers(0, 1000, (world, world))
+        offs = [multigpu.p2p_offsets(M, r) for r in range(world)]
+        for dst in range(world):
+            pos = 0
+            for src in range(world):
+                assert offs[src][0][dst] == pos
+                pos += int(M[src][dst])
+            assert offs[dst][1] == pos
+
+
 # ------------------------------------------------------------------------------------------------
 # all-pairs distance matrix: tiling and sharding
 @pytest.mark.parametrize("nsets", [1, 2, 7, 8, 9, 16, 17, 41])

@@ -37,6 +37,13 @@ SIGNATURES = {
     "zb_kmerize_close": (C.c_int, [vp]),
     "zb_kmerize_pending": (C.c_int, [vp, u64p]),
     "zb_kmerize_take_bucketed_dev": (C.c_int, [vp, C.c_int, vp, u64p]),
+    "zb_kmerize_bucket_counts": (C.c_int, [vp, C.c_int, u64p]),
+    "zb_kmerize_route_p2p": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "zb_ipc_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]),
+    "zb_ipc_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(vp)]),
+    "zb_ipc_close": (C.c_int, [C.c_int, vp]),
+    "zb_ipc_free": (C.c_int, [C.c_int, vp]),
+    "zb_kmerize_adopt_canonical_dev": (C.c_int, [vp, vp, C.c_size_t]),
     "zb_kmerize_add_canonical_dev": (C.c_int, [vp, vp, C.c_size_t]),
     "zb_set_from_host": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.POINTER(vp)]),
     "zb_set_size": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
@@ -228,6 +235,28 @@ def pairs_abc(sets, I, J):
     return out
 
 
+def ipc_alloc(nbytes, device=0):
+    """-> (device pointer, 64-byte handle that another process on the node can open)"""
+    p = vp()
+    h = C.create_string_buffer(64)
+    _check(lib().zb_ipc_alloc(device, nbytes, C.byref(p), h))
+    return p.value, h.raw
+
+
+def ipc_open(handle, device=0):
+    p = vp()
+    _check(lib().zb_ipc_open(device, handle, C.byref(p)))
+    return p.value
+
+
+def ipc_close(ptr, device=0):
+    _check(lib().zb_ipc_close(device, vp(ptr)))
+
+
+def ipc_free(ptr, device=0):
+    _check(lib().zb_ipc_free(device, vp(ptr)))
+
+
 def allpairs_tiles(nsets):
     n = C.c_uint64(0)
     _check(lib().zb_allpairs_tiles(nsets, C.byref(n)))
@@ -276,6 +305,19 @@ class Kmerizer(object):
         cnt = (C.c_uint64 * nranks)()
         _check(lib().zb_kmerize_take_bucketed_dev(self.h, nranks, vp(dptr), cnt))
         return [int(x) for x in cnt]
+
+    def bucket_counts(self, nranks):
+        counts = (C.c_uint64 * nranks)()
+        _check(lib().zb_kmerize_bucket_counts(self.h, nranks, counts))
+        return [int(x) for x in counts]
+
+    def route_p2p(self, dst_ptrs):
+        """write every pending key to dst_ptrs[owner] (device addresses, own or peer memory)"""
+        arr = (vp * len(dst_ptrs))(*[vp(int(p)) for p in dst_ptrs])
+        _check(lib().zb_kmerize_route_p2p(self.h, len(dst_ptrs), arr))
+
+    def adopt_canonical_dev(self, dptr, n):
+        _check(lib().zb_kmerize_adopt_canonical_dev(self.h, vp(dptr), n))
 
     def add_canonical_dev(self, dptr, n):
         _check(lib().zb_kmerize_add_canonical_dev(self.h, vp(dptr), n))

@@ -120,6 +120,8 @@ struct zb_kmerizer {
     size_t acc_n = 0;
     uint64_t n_records = 0;
     size_t max_pending = (size_t)1 << 29;
+    uint64_t* adopted = nullptr;         // caller-owned key array that stands in for `pending` (multi-GPU receive buffer)
+    size_t adopted_n = 0;
 };
 
 static size_t read_pending_count(zb_kmerizer* h) {
@@ -143,17 +145,32 @@ static void ensure_pending(zb_kmerizer* h, size_t need_total) {
 }
 
 // count the pending canonical keys and fold them into the accumulated run
+static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n);
+
 static void flush_pending(zb_kmerizer* h) {
     Ctx* c = h->c;
+    if (h->adopted) {
+        uint64_t* keys = h->adopted;
+        const size_t n = h->adopted_n;
+        h->adopted = nullptr;
+        h->adopted_n = 0;
+        count_keys(h, keys, n);
+    }
     if (h->pending_upper == 0) return;
     const size_t n = read_pending_count(h);
     h->pending_upper = 0;
     ZB_CUDA(cudaMemsetAsync(h->d_count.get(), 0, 8, c->stream));
+    count_keys(h, h->pending.get(), n);
+}
+
+// sort + count `keys` (destroyed) and fold the result into the accumulated run
+static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n) {
+    Ctx* c = h->c;
     if (n == 0) return;
     // sort + count in one go (segsort.cu): distinct canonical keys -> `dk`, counts -> `dc`
     DBuf<uint64_t> tmp(c, n), dk(c, n);
     DBuf<uint32_t> dc(c, n);
-    const size_t nd = sort_count(c, h->pending.get(), tmp.get(), nullptr, nullptr, n, 2 * h->k, dk.get(), dc.get());
+    const size_t nd = sort_count(c, keys, tmp.get(), nullptr, nullptr, n, 2 * h->k, dk.get(), dc.get());
     tmp.release();
     const uint64_t* other = dk.get();
     if (h->acc_n == 0) {
@@ -395,6 +412,95 @@ int zb_kmerize_take_bucketed_dev(zb_kmerizer* h, int nranks, uint64_t* d_keys, u
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     h->pending_upper = 0;
     ZB_CUDA(cudaMemsetAsync(h->d_count.get(), 0, 8, c->stream));
+    ZB_CATCH
+}
+
+int zb_kmerize_bucket_counts(zb_kmerizer* h, int nranks, uint64_t* bucket_counts) {
+    ZB_TRY
+    if (!h || !bucket_counts || nranks < 1 || nranks > 64) ZB_FAIL(ZB_E_ARG, "bad argument");
+    Ctx* c = h->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    const size_t n = h->pending_upper ? read_pending_count(h) : 0;
+    DBuf<unsigned long long> cnt(c, 64);
+    ZB_CUDA(cudaMemsetAsync(cnt.get(), 0, 64 * 8, c->stream));
+    bucket_count(c, h->pending.get(), n, nranks, cnt.get());
+    std::vector<unsigned long long> hc(64, 0);
+    ZB_CUDA(cudaMemcpyAsync(hc.data(), cnt.get(), 64 * 8, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < nranks; r++) bucket_counts[r] = hc[r];
+    ZB_CATCH
+}
+
+int zb_kmerize_route_p2p(zb_kmerizer* h, int nranks, uint64_t* const* d_dst) {
+    ZB_TRY
+    if (!h || !d_dst || nranks < 1 || nranks > 64) ZB_FAIL(ZB_E_ARG, "bad argument");
+    Ctx* c = h->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    const size_t n = h->pending_upper ? read_pending_count(h) : 0;
+    PeerPtrs pp;
+    for (int r = 0; r < 64; r++) pp.p[r] = (r < nranks) ? d_dst[r] : nullptr;
+    DBuf<unsigned long long> cur(c, 64);
+    ZB_CUDA(cudaMemsetAsync(cur.get(), 0, 64 * 8, c->stream));
+    {
+        Stage st(c, "route_p2p");
+        route_p2p(c, h->pending.get(), n, nranks, pp, cur.get());
+    }
+    ZB_CUDA(cudaStreamSynchronize(c->stream));   // every store, local or over NVLink, has been issued and completed
+    h->pending_upper = 0;
+    ZB_CUDA(cudaMemsetAsync(h->d_count.get(), 0, 8, c->stream));
+    ZB_CATCH
+}
+
+int zb_ipc_alloc(int device, size_t bytes, void** d_ptr, uint8_t handle[64]) {
+    ZB_TRY
+    if (!d_ptr || !handle) ZB_FAIL(ZB_E_ARG, "null argument");
+    ctx_for(device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    ZB_CUDA(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t hd;
+    cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        ZB_CUDA(e);
+    }
+    memcpy(handle, &hd, 64);
+    *d_ptr = p;
+    ZB_CATCH
+}
+
+int zb_ipc_open(int device, const uint8_t handle[64], void** d_ptr) {
+    ZB_TRY
+    if (!d_ptr || !handle) ZB_FAIL(ZB_E_ARG, "null argument");
+    ctx_for(device);
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, 64);
+    ZB_CUDA(cudaIpcOpenMemHandle(d_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    ZB_CATCH
+}
+
+int zb_ipc_close(int device, void* d_ptr) {
+    ZB_TRY
+    ctx_for(device);
+    if (d_ptr) ZB_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    ZB_CATCH
+}
+
+int zb_ipc_free(int device, void* d_ptr) {
+    ZB_TRY
+    ctx_for(device);
+    if (d_ptr) ZB_CUDA(cudaFree(d_ptr));
+    ZB_CATCH
+}
+
+int zb_kmerize_adopt_canonical_dev(zb_kmerizer* h, uint64_t* d_keys, size_t n) {
+    ZB_TRY
+    if (!h || (n && !d_keys)) ZB_FAIL(ZB_E_ARG, "null argument");
+    ZB_CUDA(cudaSetDevice(h->c->device));
+    if (n >= ((size_t)1 << 30)) return zb_kmerize_add_canonical_dev(h, d_keys, n);   // too large for one sort: copy in pieces
+    flush_pending(h);          // an earlier adopted array must be consumed before its owner re-uses it
+    h->adopted = d_keys;
+    h->adopted_n = n;
     ZB_CATCH
 }
 

@@ -182,6 +182,73 @@ bucket_scatter_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks,
         if (ow[j] >= 0) out[sb[ow[j]] + rk[j]] = kx[j];
 }
 
+// Fused routing + transfer: every key goes straight to dst.p[owner] -- the owner's receive buffer, mapped into
+// this process through CUDA IPC, so for a remote owner the stores travel over NVLink as they are issued.  A CTA
+// groups its 2048 keys by owner in shared memory first, so every (CTA, owner) run leaves as consecutive,
+// fully used 128-byte lines.  `cursor[r]` counts what this rank has written to owner r so far.
+static constexpr int RT_THREADS = 256;
+static constexpr int RT_PER = 8;
+static constexpr int RT_TILE = RT_THREADS * RT_PER;
+
+__global__ void __launch_bounds__(RT_THREADS)
+route_p2p_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, PeerPtrs dst,
+                 unsigned long long* __restrict__ cursor) {
+    __shared__ uint32_t sc[64];                 // keys per owner in this tile, then exclusive start
+    __shared__ unsigned long long sb[64];       // my run's position in the owner's buffer
+    __shared__ uint64_t sk[RT_TILE];
+    __shared__ uint8_t so[RT_TILE];
+    const unsigned tid = threadIdx.x;
+    const uint64_t base = (uint64_t)blockIdx.x * RT_TILE;
+    if (tid < 64) sc[tid] = 0;
+    __syncthreads();
+    uint64_t kx[RT_PER];
+    int ow[RT_PER];
+    uint32_t rk[RT_PER];
+#pragma unroll
+    for (int j = 0; j < RT_PER; j++) {
+        const uint64_t i = base + (uint64_t)j * RT_THREADS + tid;
+        ow[j] = -1;
+        if (i < n) {
+            kx[j] = keys[i];
+            ow[j] = owner_of(kx[j], nranks);
+            rk[j] = atomicAdd(&sc[ow[j]], 1u);
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {   // exclusive scan of the (<= 64) per-owner counts, one reservation per owner
+        const uint32_t c0 = sc[tid], c1 = sc[tid + 32];
+        const uint32_t i0 = warp_incl_scan(c0);
+        const uint32_t t0 = __shfl_sync(0xffffffffu, i0, 31);
+        const uint32_t i1 = warp_incl_scan(c1);
+        if ((int)tid < nranks && c0) sb[tid] = atomicAdd(&cursor[tid], (unsigned long long)c0);
+        if ((int)tid + 32 < nranks && c1) sb[tid + 32] = atomicAdd(&cursor[tid + 32], (unsigned long long)c1);
+        sc[tid] = i0 - c0;
+        sc[tid + 32] = t0 + i1 - c1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RT_PER; j++) {
+        if (ow[j] >= 0) {
+            const uint32_t p = sc[ow[j]] + rk[j];
+            sk[p] = kx[j];
+            so[p] = (uint8_t)ow[j];
+        }
+    }
+    __syncthreads();
+    const uint32_t cnt = (uint32_t)min((uint64_t)RT_TILE, n - base);
+    for (uint32_t p = tid; p < cnt; p += RT_THREADS) {
+        const int o = so[p];
+        dst.p[o][sb[o] + (p - sc[o])] = sk[p];
+    }
+}
+
+void route_p2p(Ctx* c, const uint64_t* keys, size_t n, int nranks, const PeerPtrs& dst, unsigned long long* d_cursor) {
+    if (n == 0) return;
+    if (nranks > 64) ZB_FAIL(ZB_E_ARG, "route_p2p: nranks > 64");
+    route_p2p_kernel<<<(unsigned)div_up(n, RT_TILE), RT_THREADS, 0, c->stream>>>(keys, n, nranks, dst, d_cursor);
+    ZB_LAUNCH_CHECK(c);
+}
+
 void bucket_count(Ctx* c, const uint64_t* keys, size_t n, int nranks, unsigned long long* d_counts) {
     if (n == 0) return;
     if (nranks > 64) ZB_FAIL(ZB_E_ARG, "bucket_count: nranks > 64");

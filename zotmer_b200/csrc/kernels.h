@@ -113,5 +113,10 @@ void extract_canonical(Ctx* c, int k, const uint8_t* codes, size_t n, uint64_t* 
 void bucket_count(Ctx* c, const uint64_t* keys, size_t n, int nranks, unsigned long long* d_bucket_counts);
 void bucket_scatter(Ctx* c, const uint64_t* keys, size_t n, int nranks, unsigned long long* d_bucket_cursor,
                     uint64_t* out);
+// multi-GPU, fused: route every key into the owner's receive buffer (own memory or a peer's, CUDA IPC)
+struct PeerPtrs {
+    uint64_t* p[64];
+};
+void route_p2p(Ctx* c, const uint64_t* keys, size_t n, int nranks, const PeerPtrs& dst, unsigned long long* d_cursor);
 
 }  // namespace zb

@@ -96,6 +96,69 @@ def exchange_pending(nat, km, ctx):
 
 
 # ------------------------------------------------------------------------------------------------
+# fused exchange over NVLink peer memory
+def p2p_offsets(count_matrix, rank):
+    """count_matrix[src][dst] = keys rank src sends to owner dst.  -> (where in every owner's receive buffer this
+    rank's run starts [per dst], how many keys this rank receives in total).  Runs are laid out in source order."""
+    M = np.asarray(count_matrix, dtype=np.int64)
+    return [int(M[:rank, p].sum()) for p in range(M.shape[1])], int(M[:, rank].sum())
+
+
+class P2PExchange(object):
+    """Routing and transfer in ONE kernel (csrc/extract.cu route_p2p_kernel): every rank maps every other rank's
+    receive buffer (CUDA IPC) and the bucketing kernel stores each key straight into its owner's buffer over
+    NVLink.  NCCL is used only for the tiny count matrix (so that ranks agree on their slots) and the barrier that
+    says "all stores have landed".  Two receive buffers alternate, so a fast rank may already fill the next one
+    while a slow rank still reads the current one; the per-step barrier is the only synchronisation."""
+
+    def __init__(self, nat, dist, rank, world, dev, capacity_keys):
+        import torch
+        self.nat, self.dist, self.rank, self.world, self.dev = nat, dist, rank, world, dev
+        self.capacity = int(capacity_keys)
+        self.step = 0
+        self.bufs = []
+        self.route_ms = []
+        self.remote_bytes = []
+        self.cnt = torch.empty(world, dtype=torch.int64, device="cuda:%d" % dev)
+        self.allc = torch.empty(world * world, dtype=torch.int64, device="cuda:%d" % dev)
+        for _ in range(2):
+            ptr, handle = nat.ipc_alloc(self.capacity * 8, dev)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)
+            ptrs = [ptr if r == rank else nat.ipc_open(handles[r], dev) for r in range(world)]
+            self.bufs.append((ptr, ptrs))
+        dist.barrier()
+
+    def exchange(self, km):
+        import torch
+        counts = km.bucket_counts(self.world)
+        self.cnt.copy_(torch.tensor(counts, dtype=torch.int64))
+        self.dist.all_gather_into_tensor(self.allc, self.cnt)
+        M = self.allc.view(self.world, self.world).cpu().numpy()
+        offs, nrecv = p2p_offsets(M, self.rank)
+        if int(M.sum(axis=0).max()) > self.capacity:
+            raise RuntimeError("P2PExchange: a rank would receive %d keys, capacity is %d" % (int(M.sum(axis=0).max()), self.capacity))
+        own, ptrs = self.bufs[self.step & 1]
+        t0 = __import__("time").perf_counter()
+        km.route_p2p([ptrs[p] + 8 * offs[p] for p in range(self.world)])
+        self.route_ms.append((__import__("time").perf_counter() - t0) * 1e3)
+        self.remote_bytes.append(8 * (sum(counts) - counts[self.rank]))
+        self.dist.barrier()          # every rank's stores have completed
+        km.adopt_canonical_dev(own, nrecv)    # sorted in place by km.finish(); the other buffer takes the next step
+        self.step += 1
+
+    def close(self):
+        for (own, ptrs) in self.bufs:
+            for r, p in enumerate(ptrs):
+                if r != self.rank:
+                    self.nat.ipc_close(p, self.dev)
+        self.dist.barrier()
+        for (own, _) in self.bufs:
+            self.nat.ipc_free(own, self.dev)
+        self.bufs = []
+
+
+# ------------------------------------------------------------------------------------------------
 # all-pairs distance matrix: tiles of 8 x 8 sets, sharded over ranks
 AP_S = 8   # sets per block, csrc/allpairs.cu
 
