@@ -18,7 +18,7 @@ def readWords(f):
 
 def writeWords(f, ws):
     """files.py:65-83"""
-    f.write(np.ascontiguousarray(ws, dtype='<u8').tobytes())
+    f.write(memoryview(np.ascontiguousarray(ws, dtype='<u8')).cast('B'))   # no intermediate bytes copy
     return len(ws)
 
 
