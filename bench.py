@@ -113,9 +113,12 @@ class ClockSampler(object):
                 "samples": len(self.sm), "how": "NVML in-process, 100 ms period, during the timed steps"}
 
 
-def make_reads(rank, nreads):
+def make_reads(rank, nreads, world=1):
+    """rank's shard of the read set.  Weak scaling keeps the COVERAGE fixed as well as the reads per GPU: N ranks
+    sample a genome of N x 5 Mbp (config[4]'s shape -- the genome grows with the machine), so every owner rank
+    sees the same k-mer statistics (30x, ~10 M distinct genomic k-mers) as the single-GPU run."""
     from tools import synth
-    g = synth.genome(GENOME, seed=17)
+    g = synth.genome(GENOME * world, seed=17)
     return synth.fastq_array(g, nreads, L=READ_LEN, seed=18 + 1000 * rank).reshape(-1)
 
 
@@ -161,7 +164,9 @@ def workload_config(n):
     return {"workload": "config[1]: synthetic 30x 150bp FASTQ of a 5 Mbp genome, %d reads per GPU, kmerize+count k=25 "
                         "then trim min-count 2" % READS_PER_RANK,
             "k": K, "reads_per_gpu": READS_PER_RANK, "read_len": READ_LEN, "bases_per_gpu": READS_PER_RANK * READ_LEN,
-            "parallelism": "1 GPU" if n == 1 else "%d GPUs: reads sharded, hash-range all-to-all of canonical k-mers" % n,
+            "genome_bp": GENOME * n,
+            "parallelism": "1 GPU" if n == 1 else "%d GPUs: %d reads per GPU from a %d Mbp genome (30x), canonical k-mers "
+                                                  "routed to their hash-range owner over NVLink" % (n, READS_PER_RANK, GENOME * n // 1000000),
             "l2": "inputs (315 MB of text, 1 GB of keys per GPU) are larger than the 126 MB L2; no explicit flush"}
 
 
@@ -227,7 +232,7 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    fq = make_reads(rank, READS_PER_RANK)
+    fq = make_reads(rank, READS_PER_RANK, world)
     nbytes = fq.nbytes
     bases = READS_PER_RANK * READ_LEN
     d_in = torch.from_numpy(fq).to("cuda:%d" % dev)
