@@ -31,6 +31,17 @@ for it in range(3):   # several steps: the double-buffered receive side is re-us
     s, nr = km.finish()
     km.close()
     ks, cs = s.fetch()
+    if it == 0:
+        # one sorted set on rank 0 -> the file streams must be the single-process oracle's, byte for byte
+        whole = multigpu.gather_counted_set(nat, s, dist, rank, world, dev)
+        if rank == 0:
+            ek, ec, _, _ = co.kmerize(K, [(sh, False) for sh in shards])
+            wk, wc = whole.fetch()
+            assert np.array_equal(wk, ek) and np.array_equal(wc, ec), "gathered set differs from the oracle"
+            kw, cw = whole.encode()
+            assert np.array_equal(kw, co.encode(ek, True)) and np.array_equal(cw, co.encode(ec.astype(np.uint64), False))
+            if whole is not s:
+                whole.free()
     s.free()
     parts = [None] * world
     dist.all_gather_object(parts, (ks, cs))

@@ -46,6 +46,7 @@ SIGNATURES = {
     "zb_kmerize_adopt_canonical_dev": (C.c_int, [vp, vp, C.c_size_t]),
     "zb_kmerize_add_canonical_dev": (C.c_int, [vp, vp, C.c_size_t]),
     "zb_set_from_host": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.POINTER(vp)]),
+    "zb_set_from_device": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.POINTER(vp)]),
     "zb_set_size": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
     "zb_set_fetch": (C.c_int, [vp, vp, vp]),
     "zb_set_dev_ptrs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
@@ -138,6 +139,13 @@ class KmerSet(object):
             raise AssertionError("k-mer and count arrays differ in length")  # files.py:182
         h = vp()
         _check(lib().zb_set_from_host(device, _ptr(k), _ptr(c) if c is not None else None, len(k), C.byref(h)))
+        return KmerSet(h, device)
+
+    @staticmethod
+    def from_device(d_kmers, d_counts, n, device=0):
+        """copy of device arrays (sorted, duplicate-free k-mers + counts) into a new set"""
+        h = vp()
+        _check(lib().zb_set_from_device(device, vp(d_kmers), vp(d_counts) if d_counts else None, n, C.byref(h)))
         return KmerSet(h, device)
 
     @staticmethod

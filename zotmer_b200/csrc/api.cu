@@ -545,6 +545,21 @@ int zb_set_from_host(int device, const uint64_t* kmers, const uint32_t* counts, 
     ZB_CATCH
 }
 
+int zb_set_from_device(int device, const uint64_t* d_kmers, const uint32_t* d_counts, size_t n, zb_set** out) {
+    ZB_TRY
+    if (!out || (n && !d_kmers)) ZB_FAIL(ZB_E_ARG, "null argument");
+    Ctx* c = ctx_for(device);
+    zb_set* s = new_set(c, n);
+    if (n) {
+        ZB_CUDA(cudaMemcpyAsync(s->k.get(), d_kmers, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+        if (d_counts) ZB_CUDA(cudaMemcpyAsync(s->cnt.get(), d_counts, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+        else fill_u32(c, s->cnt.get(), n, 1u);
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    *out = s;
+    ZB_CATCH
+}
+
 int zb_set_size(const zb_set* s, size_t* n) {
     if (!s || !n) { zb::set_error("null argument"); return ZB_E_ARG; }
     *n = s->n;

@@ -158,6 +158,66 @@ class P2PExchange(object):
         self.bufs = []
 
 
+def gather_counted_set(nat, kset, dist, rank, world, dev, root=0):
+    """One sorted file from hash-owned shares: every rank sends its counted both-strand share (sorted, disjoint
+    from all others) to `root`, which merges them with zb_merge (merge-path tree) into THE sorted set -- the input
+    of the file writer, so the output is byte-identical to a single-GPU `zot kmerize` (codec64's greedy word
+    boundaries depend on the whole sequence, so the encode has to see one array).  Returns the merged KmerSet on
+    root, None elsewhere.  Volume: 12 B per distinct k-mer, far less than the key exchange at 30x coverage.
+    (Sets beyond one GPU's memory need the range-partitioned variant, SURVEY.md 8e(ii): not built.)"""
+    import torch
+    n = len(kset)
+    sizes = [None] * world
+    dist.all_gather_object(sizes, n)
+    kp, cp = kset.dev_ptrs()
+    dv = "cuda:%d" % dev
+    # wrap the set's device arrays as tensors without copying (torch only does the plumbing)
+    k_local = _as_tensor(kp, n, torch.int64, dev)
+    c_local = _as_tensor(cp, n, torch.int32, dev)
+    if rank == root:
+        shares = [kset]
+        reqs = []
+        bufs = []
+        for r in range(world):
+            if r == root:
+                continue
+            kb = torch.empty(max(sizes[r], 1), dtype=torch.int64, device=dv)
+            cb = torch.empty(max(sizes[r], 1), dtype=torch.int32, device=dv)
+            if sizes[r]:
+                reqs.append(dist.irecv(kb[:sizes[r]], src=r))
+                reqs.append(dist.irecv(cb[:sizes[r]], src=r))
+            bufs.append((r, kb, cb))
+        for q in reqs:
+            q.wait()
+        torch.cuda.synchronize(dev)
+        for (r, kb, cb) in bufs:
+            shares.append(nat.KmerSet.from_device(kb.data_ptr(), cb.data_ptr(), sizes[r], dev))
+        merged = nat.merge(shares) if len(shares) > 1 else kset
+        for sh in shares[1:]:
+            sh.free()
+        return merged
+    if n:
+        dist.send(k_local, dst=root)
+        dist.send(c_local, dst=root)
+    torch.cuda.synchronize(dev)
+    return None
+
+
+def _as_tensor(ptr, n, dtype, dev):
+    """a torch view of n elements of library-owned device memory (no copy)"""
+    import torch
+
+    class _Arr(object):
+        pass
+    if n == 0:
+        return torch.empty(0, dtype=dtype, device="cuda:%d" % dev)
+    a = _Arr()
+    itemsize = torch.empty(0, dtype=dtype).element_size()
+    typestr = {8: "<i8", 4: "<i4"}[itemsize]
+    a.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(a, device="cuda:%d" % dev)
+
+
 # ------------------------------------------------------------------------------------------------
 # all-pairs distance matrix: tiles of 8 x 8 sets, sharded over ranks
 AP_S = 8   # sets per block, csrc/allpairs.cu
