@@ -289,8 +289,12 @@ int zb_kmerize_open(int k, int device, zb_kmerizer** out) {
     h->k = k;
     h->d_count.alloc(c, 2);
     ZB_CUDA(cudaMemsetAsync(h->d_count.get(), 0, 16, c->stream));
-    if (const char* e = getenv("ZB_SORT_COUNT")) g_sort_count_mode = atoi(e);
-    if (const char* e = getenv("ZB_SORT_CFG")) g_sort_cfg = atoi(e);
+    {   // tuning / cross-check switches, re-read at every open (unset = default)
+        const char* e = getenv("ZB_SORT_COUNT");
+        g_sort_count_mode = e ? atoi(e) : 0;
+        e = getenv("ZB_SORT_CFG");
+        g_sort_cfg = e ? atoi(e) : 0;
+    }
     if (const char* e = getenv("ZB_MAX_PENDING")) {
         size_t v = strtoull(e, nullptr, 10);
         if (v >= (size_t)EXTRACT_TILE && v < ((size_t)1 << 30)) h->max_pending = v;
