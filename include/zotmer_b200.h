@@ -116,6 +116,13 @@ int zb_set_stats(const zb_set* s, uint64_t acgt_weighted[4], uint64_t acgt_plain
 int zb_merge(int nsets, zb_set* const* sets, zb_set** out);
 /* keep cmin <= count (and count <= cmax when cmax > 0) -- trim.py:54-62 */
 int zb_trim(const zb_set* s, uint64_t cmin, uint64_t cmax, zb_set** out);
+/* deterministic sub-sampling by k-mer hash, order kept.  mode 0: keep x iff
+ * float(murmer(x, seed) & 0xFFFFFFFFFF) / float(0xFFFFFFFFFF) < p  -- commands/sample.py:27-34 (sampleD; the only path
+ * `zot sample` ever takes under docopt);  mode 1: float(murmer(x, seed)) / float(0x1FFFFFFFFFFFFFFF) < p --
+ * library/basics.py:251-259 sub(), the filter of `zot kmerize -D` (kmerize.py:494-506).  Same IEEE double expression. */
+int zb_sample(const zb_set* s, int mode, uint64_t seed, double p, zb_set** out);
+/* keep the entries of s whose k-mer occurs in ref -- commands/project.py:18-40 (project1 / project2) */
+int zb_restrict(const zb_set* s, const zb_set* ref, zb_set** out);
 /* y = x >> shift_bits, adjacent duplicates dropped, counts discarded -- commands/dist.py:36-49 (Measure.prep) */
 int zb_project(const zb_set* s, int shift_bits, zb_set** out);
 /* (|X n Y|, |X \ Y|, |Y \ X|) for each listed pair -- library/dist.py:241-265 (split), jaccard.py:31-54.

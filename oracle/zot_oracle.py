@@ -526,6 +526,89 @@ def cmd_trim(out, inp, c, C0=0):
     w.close()
 
 
+def sub(s, p, x):
+    """library/basics.py:251-259."""
+    return float(murmer(x, s)) / float(0x1FFFFFFFFFFFFFFF) < p
+
+
+def cmd_kmerize_D(k, out, input_paths, d, S=0):
+    """kmerize.py:450-562 with -D d [-S S]: acgt over every k-mer (:492-493), only k-mers with sub(S, d, x) are
+    accumulated (:494-506; the two caches only memoise sub())."""
+    inputs = []
+    for p in input_paths:
+        with open(p, "rb") as f:
+            inputs.append((p, f.read()))
+    xs, cs, h, acgt, nr = kmerize_core(k, inputs)
+    keep = [i for i, x in enumerate(xs) if sub(S, d, x)]
+    xs = [xs[i] for i in keep]
+    cs = [cs[i] for i in keep]
+    h = {}
+    for c in cs:
+        h[c] = 1 + h.get(c, 0)
+    z = CasketWriter(out)
+    write_kmers_and_counts(z, xs, cs)
+    n = float(sum(acgt))
+    z.meta["K"] = k
+    z.meta["kmers"] = "kmers"
+    z.meta["counts"] = "counts"
+    z.meta["hist"] = h
+    z.meta["acgt"] = [c / n for c in acgt]
+    z.meta["reads"] = nr
+    z.close()
+
+
+def sample_core(xs, cs, p, S):
+    """commands/sample.py:27-34 sampleD (the path docopt always selects, :53)."""
+    M = 0xFFFFFFFFFF
+    ox, oc = [], []
+    for x, c in zip(xs, cs):
+        if float(murmer(x, S) & M) / float(M) < p:
+            ox.append(x)
+            oc.append(c)
+    return ox, oc
+
+
+def cmd_sample(out, inp, p=0.01, S=0):
+    """commands/sample.py:36-67."""
+    z0 = CasketReader(inp)
+    K = z0.meta["K"]
+    xs, cs = read_kmers_and_counts(z0)
+    z = CasketWriter(out)
+    z.meta = dict(z0.meta)
+    del z.meta["kmers"]
+    del z.meta["counts"]
+    ox, oc = sample_core(xs, cs, p, S)
+    h = {}
+    for c in oc:
+        h[c] = 1 + h.get(c, 0)
+    write_kmers_and_counts(z, ox, oc)
+    z.meta["K"] = K
+    z.meta["kmers"] = "kmers"
+    z.meta["counts"] = "counts"
+    z.meta["hist"] = h
+    z.close()
+
+
+def cmd_project(ref, out, inp):
+    """commands/project.py:42-70 (inputs with counts: project2 :30-40)."""
+    zr = CasketReader(ref)
+    K = zr.meta["K"]
+    rs = set(read_kmers(zr))
+    z0 = CasketReader(inp)
+    if z0.meta["K"] != K:
+        raise SystemExit(1)
+    xs, cs = read_kmers_and_counts(z0)
+    z = CasketWriter(out)
+    z.meta["K"] = K
+    ox = [x for x in xs if x in rs]
+    oc = [c for x, c in zip(xs, cs) if x in rs]
+    write_kmers_and_counts(z, ox, oc)
+    z.meta["kmers"] = "kmers"
+    z.meta["counts"] = "counts"
+    z.meta["hist"] = z0.meta["hist"]
+    z.close()
+
+
 def cmd_hist(input_paths):
     """hist.py:14-24."""
     out = []

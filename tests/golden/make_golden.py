@@ -299,6 +299,38 @@ def main():
     run_cmd("dump", {"<input>": "r1_c2.k25"}, out_txt="dump_r1_c2.txt")
     run_cmd("info", {"<input>": ["kat6.k5", "m3.k25"]}, out_txt="info.txt")
 
+    # ---- zot sample, zot project, zot kmerize -D (docopt gives flags as False/True)
+
+    def sample(out, inp, P=None, S=None, D=False, **kw):
+        return run_cmd("sample", {"<output>": os.path.join(DATA, out), "<input>": inp, "-P": P, "-S": S, "-D": D}, **kw)
+
+    sample("r1_P03_S7.k25", "r1.k25", "0.3", "7")
+    sample("g1_Pdef.k25", "g1.k25")                       # default p = 0.01, seed 0
+    sample("m5_P05_D.k25", "m5.k25", "0.5", None, True)    # -D given: same path
+    sample("r1_P1.k25", "r1.k25", "1.0", "123456789")      # p = 1: u < 1 fails only for h & M == M
+
+    def project(ref, out, inp, **kw):
+        return run_cmd("project", {"<ref>": ref, "<output>": os.path.join(DATA, out), "<input>": inp}, **kw)
+
+    project("r1_c2.k25", "proj_r1c2_r1.k25", "r1.k25")
+    project("s0.k25", "proj_s0_s1.k25", "s1.k25")
+    project("s1.k25", "proj_s1_m5.k25", "m5.k25")
+    _, se, exc = project("s0.k25", "proj_bad.k25", "s1.k16", expect_exc="SystemExit(1)")
+    kat["project_mismatched_K"] = {"exc": exc, "stderr": se}
+    if os.path.exists(os.path.join(DATA, "proj_bad.k25")):
+        os.remove(os.path.join(DATA, "proj_bad.k25"))
+
+    def kmerizeD(k, out, inputs, D, S=None):
+        return run_cmd("kmerize", {"<k>": str(k), "<output>": os.path.join(DATA, out),
+                                   "<input>": [os.path.join(DATA, i) for i in inputs],
+                                   "-m": None, "-C": None, "-D": D, "-S": S, "-v": False})
+
+    kmerizeD(25, "r1_D03_S5.k25", ["r1.fq"], "0.3", "5")
+    kmerizeD(25, "g1_D05.k25", ["g1.fa"], "0.5")
+    kmerizeD(16, "g1_D2.k16", ["g1.fa"], "2.0", "9")       # u can exceed 1 (murmer is not masked to 61 bits): d = 2 keeps fewer than all
+    kat["sub"] = [[s_, p_, x_, bool(basics.sub(s_, p_, x_))] for (s_, p_, x_) in
+                  [(0, 0.5, 0), (0, 0.5, 1), (5, 0.3, 0x1234567), (17, 0.01, 2 ** 50 - 1), (9, 2.0, 0xFFFFFFFF), (9, 2.0, 12345)]]
+
     with open(os.path.join(DATA, "kat.json"), "w") as f:
         json.dump(kat, f, indent=0, sort_keys=True)
     tot = sum(os.path.getsize(os.path.join(DATA, x)) for x in os.listdir(DATA))

@@ -42,6 +42,8 @@ _MODULES = {
     "zotmer.commands.hist": "zotmer/commands/hist.py",
     "zotmer.commands.info": "zotmer/commands/info.py",
     "zotmer.commands.dump": "zotmer/commands/dump.py",
+    "zotmer.commands.sample": "zotmer/commands/sample.py",
+    "zotmer.commands.project": "zotmer/commands/project.py",
 }
 
 _PKGS = ["zotmer", "zotmer.library", "zotmer.library.container", "zotmer.commands"]

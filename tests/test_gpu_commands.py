@@ -161,3 +161,37 @@ def test_jaccard_mismatched_K(zot, capsys):
         jaccard.main(["jaccard", "s0.k25", "s1.k16"])
     assert ei.value.code == 1
     assert capsys.readouterr().err == "mismatched K: s1.k16\n"
+
+
+# ----------------------------------------------------------------------------- SURVEY.md 8f row 2
+@pytest.mark.parametrize("out,inp,args", [("r1_P03_S7.k25", "r1.k25", ["-P", "0.3", "-S", "7"]), ("g1_Pdef.k25", "g1.k25", []),
+                                          ("m5_P05_D.k25", "m5.k25", ["-D", "-P", "0.5"]),
+                                          ("r1_P1.k25", "r1.k25", ["-P", "1.0", "-S", "123456789"])])
+def test_sample_file_bytes(zot, tmp_path, out, inp, args):
+    o = tmp_path / out
+    zot("sample", *(args + [o, inp]))
+    assert o.read_bytes() == rd(out)
+
+
+@pytest.mark.parametrize("ref,out,inp", [("r1_c2.k25", "proj_r1c2_r1.k25", "r1.k25"), ("s0.k25", "proj_s0_s1.k25", "s1.k25"),
+                                         ("s1.k25", "proj_s1_m5.k25", "m5.k25")])
+def test_project_file_bytes(zot, tmp_path, ref, out, inp):
+    o = tmp_path / out
+    zot("project", ref, o, inp)
+    assert o.read_bytes() == rd(out)
+
+
+def test_project_mismatched_K(zot, tmp_path, capsys):
+    from zotmer_b200.commands import project
+    with pytest.raises(SystemExit):
+        project.main(["project", "s0.k25", str(tmp_path / "x.k25"), "s1.k16"])
+    assert capsys.readouterr().err == "mismatched K (16)\n"
+
+
+@pytest.mark.parametrize("k,out,ins,args", [(25, "r1_D03_S5.k25", ["r1.fq"], ["-D", "0.3", "-S", "5"]),
+                                            (25, "g1_D05.k25", ["g1.fa"], ["-D", "0.5"]),
+                                            (16, "g1_D2.k16", ["g1.fa"], ["-D", "2.0", "-S", "9"])])
+def test_kmerize_D_file_bytes(zot, tmp_path, k, out, ins, args):
+    o = tmp_path / out
+    zot("kmerize", *(args + [k, o] + ins))
+    assert o.read_bytes() == rd(out)

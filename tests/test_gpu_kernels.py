@@ -463,6 +463,31 @@ def test_pairs_abc(nat):
         assert tuple(int(v) for v in abc[p]) == co.split(sets[I[p]], sets[J[p]]), (I[p], J[p])
 
 
+def test_sample_and_restrict_vs_oracle(nat):
+    """zb_sample (both float expressions of the reference, evaluated in IEEE double on the device) and zb_restrict"""
+    rng = np.random.default_rng(31)
+    k = np.unique(rng.integers(0, 2 ** 62, 120000, dtype=np.uint64))
+    c = rng.integers(1, 100, len(k), dtype=np.uint32)
+    s = nat.KmerSet.from_arrays(k, c)
+    M = 0xFFFFFFFFFF
+    for (p, seed) in ((0.3, 7), (0.01, 0), (1.0, 2 ** 63 + 5), (0.999999, 1)):
+        keep0 = np.array([float(zo.murmer(int(x), seed) & M) / float(M) < p for x in k])
+        keep1 = np.array([zo.sub(seed, p, int(x)) for x in k])
+        for mode, keep in ((0, keep0), (1, keep1)):
+            t = s.sample(p, seed, mode)
+            tk, tc = t.fetch()
+            assert np.array_equal(tk, k[keep]) and np.array_equal(tc, c[keep]), (p, seed, mode)
+            t.free()
+    ref = np.unique(np.concatenate([k[::3], rng.integers(0, 2 ** 62, 50000, dtype=np.uint64)]))
+    r = nat.KmerSet.from_arrays(ref)
+    t = s.restrict(r)
+    tk, tc = t.fetch()
+    keep = np.isin(k, ref)
+    assert np.array_equal(tk, k[keep]) and np.array_equal(tc, c[keep])
+    e = nat.KmerSet.from_arrays(np.zeros(0, np.uint64))
+    assert len(s.restrict(e)) == 0 and len(e.restrict(s)) == 0 and len(e.sample(0.5)) == 0
+
+
 def _rand_sets(rng, sizes, bits, share=0.5):
     pool = np.unique(rng.integers(0, 2 ** bits, int(max(sizes) * 2) + 8, dtype=np.uint64))
     out = []

@@ -197,3 +197,33 @@ def test_cmd_jaccard(in_golden_dir):
     sets = ["s%d.k25" % i for i in range(5)]
     assert zo.cmd_jaccard(sets, False) == rd("jaccard_first.txt").decode()
     assert zo.cmd_jaccard(sets, True) == rd("jaccard_all.txt").decode()
+
+
+# ----------------------------------------------------------------------------- SURVEY.md 8f row 2
+def test_sub_kat(kat):
+    for s_, p_, x_, want in kat["sub"]:
+        assert zo.sub(s_, p_, x_) == want
+
+
+@pytest.mark.parametrize("out,inp,p,S", [("r1_P03_S7.k25", "r1.k25", 0.3, 7), ("g1_Pdef.k25", "g1.k25", 0.01, 0),
+                                         ("m5_P05_D.k25", "m5.k25", 0.5, 0), ("r1_P1.k25", "r1.k25", 1.0, 123456789)])
+def test_cmd_sample(tmp_path, out, inp, p, S):
+    o = str(tmp_path / out)
+    zo.cmd_sample(o, g(inp), p, S)
+    assert open(o, "rb").read() == rd(out)
+
+
+@pytest.mark.parametrize("ref,out,inp", [("r1_c2.k25", "proj_r1c2_r1.k25", "r1.k25"), ("s0.k25", "proj_s0_s1.k25", "s1.k25"),
+                                         ("s1.k25", "proj_s1_m5.k25", "m5.k25")])
+def test_cmd_project(tmp_path, ref, out, inp):
+    o = str(tmp_path / out)
+    zo.cmd_project(g(ref), o, g(inp))
+    assert open(o, "rb").read() == rd(out)
+
+
+@pytest.mark.parametrize("k,out,ins,d,S", [(25, "r1_D03_S5.k25", ["r1.fq"], 0.3, 5), (25, "g1_D05.k25", ["g1.fa"], 0.5, 0),
+                                           (16, "g1_D2.k16", ["g1.fa"], 2.0, 9)])
+def test_cmd_kmerize_D(tmp_path, k, out, ins, d, S):
+    o = str(tmp_path / out)
+    zo.cmd_kmerize_D(k, o, [g(i) for i in ins], d, S)
+    assert open(o, "rb").read() == rd(out)

@@ -54,6 +54,8 @@ SIGNATURES = {
     "zb_set_stats": (C.c_int, [vp, u64p, u64p, u64p, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "zb_merge": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp)]),
     "zb_trim": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
+    "zb_sample": (C.c_int, [vp, C.c_int, C.c_uint64, C.c_double, C.POINTER(vp)]),
+    "zb_restrict": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "zb_project": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
     "zb_pairs_abc": (C.c_int, [C.c_int, C.POINTER(vp), vp, vp, C.c_size_t, vp]),
     "zb_allpairs_tiles": (C.c_int, [C.c_int, u64p]),
@@ -197,6 +199,18 @@ class KmerSet(object):
     def trim(self, cmin, cmax=0):
         h = vp()
         _check(lib().zb_trim(self.h, int(cmin), int(cmax), C.byref(h)))
+        return KmerSet(h, self.device)
+
+    def sample(self, p, seed=0, mode=0):
+        """hash sub-sampling: mode 0 = `zot sample`, mode 1 = `zot kmerize -D` (basics.sub)"""
+        h = vp()
+        _check(lib().zb_sample(self.h, int(mode), int(seed) & 0xFFFFFFFFFFFFFFFF, float(p), C.byref(h)))
+        return KmerSet(h, self.device)
+
+    def restrict(self, ref):
+        """the entries whose k-mer occurs in `ref` (`zot project`)"""
+        h = vp()
+        _check(lib().zb_restrict(self.h, ref.h, C.byref(h)))
         return KmerSet(h, self.device)
 
     def project(self, shift_bits):

@@ -58,15 +58,28 @@ def main(argv):
     K = int(opts['<k>'])
     out = opts['<output>']
 
-    if opts['-D'] is not None or opts['-C'] is not None:
-        # kmerize.py:494-520 (murmur subsampling / bait capture): SURVEY.md 8f row 2, not built yet
-        print('zot kmerize: -D/-C are not available in zotmer_b200', file=sys.stderr)
+    if opts['-C'] is not None:
+        # kmerize.py:507-517 (bait capture: whole reads are kept when one of their k-mers is a bait): a per-read
+        # decision, not built yet
+        print('zot kmerize: -C is not available in zotmer_b200', file=sys.stderr)
         sys.exit(1)
 
     (kset, nr) = kmerizeFiles(K, opts['<input>'], verbose=verbose)
 
     with zotk.kmers(out, 'w') as z:
-        st = kset.stats()
+        st = kset.stats()      # acgt counts EVERY k-mer, before any sub-sampling (kmerize.py:492-493)
+        if opts['-D'] is not None:
+            # kmerize.py:494-506: a k-mer is kept iff sub(S, d, x) (basics.py:251-259) -- a function of the k-mer
+            # alone (each strand is tested on its own), so filtering the counted set is the same as filtering
+            # the k-mers before counting them
+            d = float(opts['-D'])
+            S = 0
+            if opts['-S'] is not None:
+                S = int(opts['-S'])
+            kept = kset.sample(d, S, 1)
+            kset.free()
+            kset = kept
+            st['hist'] = kset.stats()['hist']
         h = {}
         for (c, f) in st['hist']:       # first-occurrence order == the reference's dict order (:544-545)
             h[c] = f

@@ -674,6 +674,31 @@ int zb_trim(const zb_set* s, uint64_t cmin, uint64_t cmax, zb_set** out) {
     ZB_CATCH
 }
 
+int zb_sample(const zb_set* s, int mode, uint64_t seed, double p, zb_set** out) {
+    ZB_TRY
+    if (!s || !out || mode < 0 || mode > 1) ZB_FAIL(ZB_E_ARG, "bad argument");
+    Ctx* c = s->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    zb_set* r = new_set(c, s->n);
+    Stage st(c, "sample");
+    r->n = sample_pairs(c, s->k.get(), s->cnt.get(), s->n, mode, seed, p, r->k.get(), r->cnt.get());
+    *out = r;
+    ZB_CATCH
+}
+
+int zb_restrict(const zb_set* s, const zb_set* ref, zb_set** out) {
+    ZB_TRY
+    if (!s || !ref || !out) ZB_FAIL(ZB_E_ARG, "null argument");
+    if (s->c != ref->c) ZB_FAIL(ZB_E_ARG, "sets must live on one device");
+    Ctx* c = s->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    zb_set* r = new_set(c, s->n);
+    Stage st(c, "restrict");
+    r->n = restrict_pairs(c, s->k.get(), s->cnt.get(), s->n, ref->k.get(), ref->n, r->k.get(), r->cnt.get());
+    *out = r;
+    ZB_CATCH
+}
+
 int zb_project(const zb_set* s, int shift_bits, zb_set** out) {
     ZB_TRY
     if (!s || !out || shift_bits < 0 || shift_bits > 63) ZB_FAIL(ZB_E_ARG, "bad argument");

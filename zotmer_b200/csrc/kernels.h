@@ -71,6 +71,12 @@ size_t mirror_keys(Ctx* c, int k, const uint64_t* ck, uint32_t* cc, size_t n, ui
 // Compaction cmin <= count (<= cmax when cmax > 0); returns kept count.  trim.py:54-62.
 size_t trim_pairs(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, uint64_t cmin, uint64_t cmax,
                   uint64_t* ok, uint32_t* oc);
+// Hash sub-sampling (mode 0: `zot sample`, commands/sample.py:27-34; mode 1: `zot kmerize -D`, basics.py:251-259)
+// and restriction to the k-mers of a reference set (`zot project`, commands/project.py:18-40); both keep order.
+size_t sample_pairs(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, int mode, uint64_t seed, double p,
+                    uint64_t* ok, uint32_t* oc);
+size_t restrict_pairs(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, const uint64_t* ref, size_t nref,
+                      uint64_t* ok, uint32_t* oc);
 // y = x >> shift with adjacent duplicates dropped.  commands/dist.py:36-49.
 size_t project_keys(Ctx* c, const uint64_t* k, size_t n, int shift, uint64_t* ok);
 // Histogram of counts in first-occurrence order + acgt tallies.  kmerize.py:544-545, merge.py:158-159.

@@ -352,6 +352,51 @@ struct ProjectOp {
     __device__ uint64_t key(uint64_t x) const { return x >> shift; }
 };
 
+// zotmer/library/basics.py:191-229 murmer(x, s): one 64-bit MurmurHash3 block + fmix64
+__device__ __forceinline__ uint64_t murmer64(uint64_t x, uint64_t s) {
+    uint64_t k = x * 0x87c37b91114253d5ull;
+    k = (k << 31) | (k >> 33);
+    k *= 0x4cf5ad432745937full;
+    uint64_t h = s ^ k;
+    h = (h << 27) | (h >> 37);
+    h = h * 5ull + 0x52dce729ull;
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull;
+    h ^= h >> 33;
+    return h;
+}
+// Deterministic sub-sampling by k-mer hash.  The keep test is the reference's float expression, evaluated in
+// IEEE double (int -> double round-to-nearest-even, correctly rounded division), so the decision is bit-exact:
+//   mode 0  commands/sample.py:27-34  sampleD:  float(murmer(y, s) & 0xFFFFFFFFFF) / float(0xFFFFFFFFFF) < p
+//   mode 1  library/basics.py:251-259 sub():    float(murmer(x, s)) / float(0x1FFFFFFFFFFFFFFF) < p   (kmerize -D)
+struct SampleOp {
+    int mode;
+    uint64_t seed;
+    double p;
+    __device__ bool keep(const uint64_t* keys, uint64_t i) const {
+        const uint64_t h = murmer64(__ldg(keys + i), seed);
+        const double u = (mode == 0) ? __ull2double_rn(h & 0xFFFFFFFFFFull) / 1099511627775.0
+                                     : __ull2double_rn(h) / 2305843009213693952.0;   // float(2^61 - 1) == 2^61
+        return u < p;
+    }
+    __device__ uint64_t key(uint64_t x) const { return x; }
+};
+// keep the entries whose k-mer occurs in the sorted reference array (commands/project.py:18-40 project1/2)
+struct RestrictOp {
+    const uint64_t* ref;
+    uint64_t nref;
+    __device__ bool keep(const uint64_t* keys, uint64_t i) const {
+        const uint64_t y = __ldg(keys + i);
+        uint64_t lo = 0, hi = nref;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (__ldg(ref + mid) < y) lo = mid + 1; else hi = mid;
+        }
+        return lo < nref && __ldg(ref + lo) == y;
+    }
+    __device__ uint64_t key(uint64_t x) const { return x; }
+};
+
 template <typename Op, bool HAS_CNT>
 __global__ void __launch_bounds__(ST_THREADS, 4)
 compact_kernel(Op op, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt, uint64_t n,
@@ -439,6 +484,18 @@ size_t trim_pairs(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, uint
                   uint64_t* ok, uint32_t* oc) {
     TrimOp op{cnt, cmin, cmax};
     return run_compact<TrimOp, true>(c, op, k, cnt, n, ok, oc);
+}
+
+size_t sample_pairs(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, int mode, uint64_t seed, double p,
+                    uint64_t* ok, uint32_t* oc) {
+    SampleOp op{mode, seed, p};
+    return run_compact<SampleOp, true>(c, op, k, cnt, n, ok, oc);
+}
+
+size_t restrict_pairs(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, const uint64_t* ref, size_t nref,
+                      uint64_t* ok, uint32_t* oc) {
+    RestrictOp op{ref, nref};
+    return run_compact<RestrictOp, true>(c, op, k, cnt, n, ok, oc);
 }
 
 size_t project_keys(Ctx* c, const uint64_t* k, size_t n, int shift, uint64_t* ok) {
