@@ -56,7 +56,7 @@ def load_peaks():
 
 class ClockSampler(object):
     """SM clock and throttle reasons sampled in-process through NVML (the library nvidia-smi uses) every
-    100 ms while the timed region runs.  Spawning nvidia-smi itself every 200 ms stalls CUDA API calls
+    20 ms while the timed region runs.  Spawning nvidia-smi itself every 200 ms stalls CUDA API calls
     for milliseconds at a time (measured: 104 ms/step with it, 20 ms/step without)."""
 
     def __init__(self, gpu_index=0):
@@ -101,7 +101,7 @@ class ClockSampler(object):
             except Exception as e:
                 self.err = repr(e)
                 break
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.02)
 
     def stop(self):
         self.stop_flag.set()
@@ -110,7 +110,7 @@ class ClockSampler(object):
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no samples: %s" % self.err]}
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
-                "samples": len(self.sm), "how": "NVML in-process, 100 ms period, during the timed steps"}
+                "samples": len(self.sm), "how": "NVML in-process, 20 ms period, during the timed steps"}
 
 
 def make_reads(rank, nreads, world=1):
@@ -161,8 +161,8 @@ def run_reference(args, rank):
 
 
 def workload_config(n):
-    return {"workload": "config[1]: synthetic 30x 150bp FASTQ of a 5 Mbp genome, %d reads per GPU, kmerize+count k=25 "
-                        "then trim min-count 2" % READS_PER_RANK,
+    return {"workload": "config[1]: synthetic 30x 150bp FASTQ of a %d Mbp genome, %d reads per GPU, kmerize+count k=25 "
+                        "then trim min-count 2" % (GENOME * n // 1000000, READS_PER_RANK),
             "k": K, "reads_per_gpu": READS_PER_RANK, "read_len": READ_LEN, "bases_per_gpu": READS_PER_RANK * READ_LEN,
             "genome_bp": GENOME * n,
             "parallelism": "1 GPU" if n == 1 else "%d GPUs: %d reads per GPU from a %d Mbp genome (30x), canonical k-mers "
