@@ -417,6 +417,36 @@ def test_merge(nat, sizes):
     assert st["acgt_plain"] == [int(((ek & np.uint64(3)) == np.uint64(b)).sum()) for b in range(4)]
 
 
+def test_merge_nway_equals_pairwise_tree(nat, monkeypatch):
+    """>= 4 inputs go through one weighted sort + count of the concatenation; it must equal the reference-shaped
+    pairwise tree (ZB_MERGE=tree) and the oracle, including counts that add up past 2^16 and empty inputs"""
+    rng = np.random.default_rng(44)
+    pool = np.unique(rng.integers(0, 2 ** 50, 150000, dtype=np.uint64))
+    sets = []
+    for i in range(9):
+        n = [40000, 0, 70000, 1, 65000, 30000, 150000, 5, 90000][i]
+        k = np.sort(rng.choice(pool, min(n, len(pool)), replace=False))
+        c = rng.integers(1, 200000, len(k), dtype=np.uint32)
+        sets.append((k, c))
+    hs = [nat.KmerSet.from_arrays(k, c) for k, c in sets]
+    a = nat.merge(hs)
+    monkeypatch.setenv("ZB_MERGE", "tree")
+    b = nat.merge(hs)
+    monkeypatch.delenv("ZB_MERGE")
+    ak, ac = a.fetch()
+    bk, bc = b.fetch()
+    assert np.array_equal(ak, bk) and np.array_equal(ac, bc)
+    ek, ec = co.merge([(k, c.astype(np.uint64)) for k, c in sets])
+    assert np.array_equal(ak, ek) and np.array_equal(ac.astype(np.uint64), ec)
+    # a sum beyond 2^32-1 is an error on both paths (the reference's array('I') would overflow)
+    big = [nat.KmerSet.from_arrays(np.array([7, 9], np.uint64), np.array([2 ** 31, 1], np.uint32)) for _ in range(4)]
+    for mode in (None, "tree"):
+        if mode:
+            monkeypatch.setenv("ZB_MERGE", mode)
+        with pytest.raises(IndexError):
+            nat.merge(big)
+
+
 def test_stats_large_counts(nat):
     rng = np.random.default_rng(5)
     k, _ = random_set(rng, 50000)

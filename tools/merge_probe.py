@@ -14,7 +14,10 @@ for i in range(nsets):
     sets.append(s)
 tot = sum(len(s) for s in sets)
 print("%d sets, %d (k-mer, count) entries in total, built in %.1f s" % (nsets, tot, time.time() - t0), flush=True)
-for it in range(3):
+for mode in ("tree", "auto"):
+  os.environ["ZB_MERGE"] = mode
+  print("ZB_MERGE=%s" % mode)
+  for it in range(3):
     nat.device_sync()
     t0 = time.perf_counter()
     m = nat.merge(sets)
@@ -24,7 +27,12 @@ for it in range(3):
         dt * 1e3, len(m), 12 * (tot + len(m)) / 1e9, 12 * (tot + len(m)) / dt / 1e9), flush=True)
     if it < 2:
         m.free()
+  if mode == "tree":
+    ref_k, ref_c = m.fetch()
+    m.free()
+    nat.release_cache()
 mk, mc = m.fetch()
+assert np.array_equal(mk, ref_k) and np.array_equal(mc, ref_c), "n-way merge differs from the pairwise tree"
 assert np.all(mk[1:] > mk[:-1])
 assert int(mc.astype(np.uint64).sum()) == sum(int(s.fetch()[1].astype(np.uint64).sum()) for s in sets[:4]) + sum(
     int(s.stats()["acgt_weighted"][0] + s.stats()["acgt_weighted"][1] + s.stats()["acgt_weighted"][2] + s.stats()["acgt_weighted"][3]) for s in sets[4:])

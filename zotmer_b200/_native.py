@@ -122,6 +122,11 @@ def launch_count(device=0):
     return n.value
 
 
+def release_cache(device=0):
+    """give the device memory cached by the library's allocator back to the driver"""
+    _check(lib().zb_release_cache(device))
+
+
 def _ptr(a):
     return a.ctypes.data_as(vp) if a is not None and len(a) else None
 

@@ -628,6 +628,41 @@ int zb_merge(int nsets, zb_set* const* sets, zb_set** out) {
     ZB_CUDA(cudaSetDevice(c->device));
     for (int i = 0; i < nsets; i++)
         if (!sets[i] || sets[i]->c != c) ZB_FAIL(ZB_E_ARG, "sets must live on one device");
+    size_t total = 0;
+    for (int i = 0; i < nsets; i++) total += sets[i]->n;
+    const char* mm = getenv("ZB_MERGE");
+    const bool want_tree = mm && !strcmp(mm, "tree");
+    if (nsets >= 4 && total > 0 && total < ((size_t)1 << 30) && !want_tree) {
+        // Many inputs: ONE weighted sort + count of the concatenation (segsort.cu) instead of log2(nsets) levels of
+        // merge + reduce-by-key over everything -- the inputs being sorted does not pay for 6 trips through HBM.
+        // key range: the sets are sorted, so the largest key is the largest last element
+        std::vector<uint64_t> last(nsets, 0);
+        for (int i = 0; i < nsets; i++)
+            if (sets[i]->n) ZB_CUDA(cudaMemcpyAsync(&last[i], sets[i]->k.get() + sets[i]->n - 1, 8, cudaMemcpyDeviceToHost, c->stream));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+        uint64_t maxkey = 0;
+        for (int i = 0; i < nsets; i++) maxkey = std::max(maxkey, last[i]);
+        const int key_bits = maxkey ? 64 - __builtin_clzll(maxkey) : 1;
+        DBuf<uint64_t> k0(c, total), k1(c, total);
+        DBuf<uint32_t> v0(c, total), v1(c, total);
+        size_t off = 0;
+        for (int i = 0; i < nsets; i++) {
+            if (!sets[i]->n) continue;
+            ZB_CUDA(cudaMemcpyAsync(k0.get() + off, sets[i]->k.get(), sets[i]->n * 8, cudaMemcpyDeviceToDevice, c->stream));
+            ZB_CUDA(cudaMemcpyAsync(v0.get() + off, sets[i]->cnt.get(), sets[i]->n * 4, cudaMemcpyDeviceToDevice, c->stream));
+            off += sets[i]->n;
+        }
+        zb_set* s = new_set(c, total);
+        try {
+            Stage st(c, "merge_nway");
+            s->n = sort_count(c, k0.get(), k1.get(), v0.get(), v1.get(), total, key_bits, s->k.get(), s->cnt.get());
+        } catch (...) {
+            delete s;
+            throw;
+        }
+        *out = s;
+        return ZB_OK;
+    }
     // pairwise tree; every level is merge-path + reduce-by-key (counts summed)
     struct Run { const uint64_t* k; const uint32_t* c; size_t n; DBuf<uint64_t> ok; DBuf<uint32_t> oc; };
     std::vector<Run> cur(nsets);
