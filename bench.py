@@ -110,7 +110,7 @@ class ClockSampler(object):
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no samples: %s" % self.err]}
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
-                "samples": len(self.sm), "how": "NVML in-process, 20 ms period, during the timed steps"}
+                "samples": len(self.sm), "how": "NVML in-process, 20 ms period, during the timed steps (device-resident and e2e regions)"}
 
 
 def make_reads(rank, nreads, world=1):
@@ -269,7 +269,6 @@ def run_ours(args, rank, world, local_rank):
     wall_ms = (time.perf_counter() - w0) * 1e3
     launches = nat.launch_count(dev) - launches0
     prof = nat.dbg_profile(False, dev)
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- end to end through host buffers (pinned in, pinned out)
     out_k = torch.empty(max(n_trim, 1), dtype=torch.int64).pin_memory().numpy().view(np.uint64)
@@ -301,6 +300,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_ms = (time.perf_counter() - e0) * 1e3 / args.steps
     e_prof = nat.dbg_profile(False, dev)
+    clocks = sampler.stop() if rank == 0 else None     # sampled over both timed regions (device-resident and e2e)
     if rank == 0:
         print("e2e per-step wall ms: %s; stage ms/step: %s" % (
             [round(x, 1) for x in e_times], {k: round(v[0] / args.steps, 3) for k, v in e_prof.items()}), file=sys.stderr)
