@@ -100,6 +100,10 @@ int zb_kmerize_adopt_canonical_dev(zb_kmerizer* h, uint64_t* d_keys, size_t n);
 int zb_set_from_host(int device, const uint64_t* kmers, const uint32_t* counts, size_t n, zb_set** out);
 /* the same from DEVICE arrays on `device` (copied) -- e.g. a share received from another GPU */
 int zb_set_from_device(int device, const uint64_t* d_kmers, const uint32_t* d_counts, size_t n, zb_set** out);
+/* key-range sharding (multi-GPU merge): idx[i] = first position whose k-mer is >= probes[i];
+ * zb_set_slice copies the entries [begin, end) into a new set */
+int zb_set_lower_bound(const zb_set* s, const uint64_t* probes, size_t m, uint64_t* idx);
+int zb_set_slice(const zb_set* s, size_t begin, size_t end, zb_set** out);
 int zb_set_size(const zb_set* s, size_t* n);
 int zb_set_fetch(const zb_set* s, uint64_t* kmers, uint32_t* counts); /* either may be NULL */
 int zb_set_dev_ptrs(const zb_set* s, const uint64_t** d_kmers, const uint32_t** d_counts);

@@ -59,6 +59,14 @@ pool = rng.integers(0, 2 ** 50, 60000, dtype=np.uint64)
 arrs = [np.unique(pool[rng.integers(0, len(pool), 20000)]) for _ in range(21)]
 sets = [nat.KmerSet.from_arrays(a, device=dev) for a in arrs]
 full = multigpu.allpairs_sharded(lambda b, e: nat.allpairs_abc(sets, b, e), len(sets), dist, rank, world, "cuda:%d" % dev)
+# zot merge sharded by key range: identical to the single-GPU merge (and the oracle)
+cnts = [rng.integers(1, 1000, len(a), dtype=np.uint32) for a in arrs[:9]]
+msets = [nat.KmerSet.from_arrays(a, c, device=dev) for a, c in zip(arrs[:9], cnts)]
+merged = multigpu.merge_sharded(nat, msets, dist, rank, world, dev)
+if rank == 0:
+    mk, mc = merged.fetch()
+    ek, ec = co.merge([(a, c.astype(np.uint64)) for a, c in zip(arrs[:9], cnts)])
+    assert np.array_equal(mk, ek) and np.array_equal(mc.astype(np.uint64), ec), "sharded merge differs from the oracle"
 if rank == 0:
     I, J = np.triu_indices(len(sets), 1)
     for p in range(0, len(I), 7):

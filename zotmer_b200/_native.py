@@ -47,6 +47,8 @@ SIGNATURES = {
     "zb_kmerize_add_canonical_dev": (C.c_int, [vp, vp, C.c_size_t]),
     "zb_set_from_host": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.POINTER(vp)]),
     "zb_set_from_device": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.POINTER(vp)]),
+    "zb_set_lower_bound": (C.c_int, [vp, vp, C.c_size_t, vp]),
+    "zb_set_slice": (C.c_int, [vp, C.c_size_t, C.c_size_t, C.POINTER(vp)]),
     "zb_set_size": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
     "zb_set_fetch": (C.c_int, [vp, vp, vp]),
     "zb_set_dev_ptrs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
@@ -204,6 +206,19 @@ class KmerSet(object):
     def trim(self, cmin, cmax=0):
         h = vp()
         _check(lib().zb_trim(self.h, int(cmin), int(cmax), C.byref(h)))
+        return KmerSet(h, self.device)
+
+    def lower_bound(self, probes):
+        """first position whose k-mer is >= each probe -> uint64 array"""
+        p = np.ascontiguousarray(probes, dtype=np.uint64)
+        out = np.zeros(len(p), np.uint64)
+        _check(lib().zb_set_lower_bound(self.h, _ptr(p), len(p), _ptr(out)))
+        return out
+
+    def slice(self, begin, end):
+        """copy of the entries [begin, end)"""
+        h = vp()
+        _check(lib().zb_set_slice(self.h, int(begin), int(end), C.byref(h)))
         return KmerSet(h, self.device)
 
     def sample(self, p, seed=0, mode=0):

@@ -564,6 +564,29 @@ int zb_set_from_device(int device, const uint64_t* d_kmers, const uint32_t* d_co
     ZB_CATCH
 }
 
+int zb_set_lower_bound(const zb_set* s, const uint64_t* probes, size_t m, uint64_t* idx) {
+    ZB_TRY
+    if (!s || (m && (!probes || !idx))) ZB_FAIL(ZB_E_ARG, "null argument");
+    ZB_CUDA(cudaSetDevice(s->c->device));
+    lower_bound(s->c, s->k.get(), s->n, probes, m, idx);
+    ZB_CATCH
+}
+
+int zb_set_slice(const zb_set* s, size_t begin, size_t end, zb_set** out) {
+    ZB_TRY
+    if (!s || !out || begin > end || end > s->n) ZB_FAIL(ZB_E_ARG, "bad slice");
+    Ctx* c = s->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    zb_set* r = new_set(c, end - begin);
+    if (end > begin) {
+        ZB_CUDA(cudaMemcpyAsync(r->k.get(), s->k.get() + begin, (end - begin) * 8, cudaMemcpyDeviceToDevice, c->stream));
+        ZB_CUDA(cudaMemcpyAsync(r->cnt.get(), s->cnt.get() + begin, (end - begin) * 4, cudaMemcpyDeviceToDevice, c->stream));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    *out = r;
+    ZB_CATCH
+}
+
 int zb_set_size(const zb_set* s, size_t* n) {
     if (!s || !n) { zb::set_error("null argument"); return ZB_E_ARG; }
     *n = s->n;

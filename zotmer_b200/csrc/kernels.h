@@ -83,6 +83,7 @@ size_t project_keys(Ctx* c, const uint64_t* k, size_t n, int shift, uint64_t* ok
 void set_stats(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, uint64_t acgt_w[4], uint64_t acgt_p[4],
                uint64_t* total, std::vector<std::pair<uint64_t, uint64_t>>* hist_first_order);
 void fill_u32(Ctx* c, uint32_t* p, size_t n, uint32_t v);
+void lower_bound(Ctx* c, const uint64_t* keys, size_t n, const uint64_t* h_probe, size_t m, uint64_t* h_idx);
 // Intersection / difference cardinalities for a batch of pairs.  library/dist.py:241-265.
 struct SetRef {
     const uint64_t* k;

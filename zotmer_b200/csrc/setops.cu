@@ -167,6 +167,29 @@ size_t reduce_by_key(Ctx* c, const uint64_t* keys, const uint32_t* w, size_t n, 
     return (size_t)n_out;
 }
 
+// idx[i] = first position of `keys` (ascending) that is >= probe[i]
+__global__ void lower_bound_kernel(const uint64_t* __restrict__ keys, uint64_t n, const uint64_t* __restrict__ probe,
+                                   uint32_t m, uint64_t* __restrict__ idx) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint64_t y = probe[i];
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < y) lo = mid + 1; else hi = mid;
+    }
+    idx[i] = lo;
+}
+void lower_bound(Ctx* c, const uint64_t* keys, size_t n, const uint64_t* h_probe, size_t m, uint64_t* h_idx) {
+    if (m == 0) return;
+    DBuf<uint64_t> d(c, 2 * m);
+    ZB_CUDA(cudaMemcpyAsync(d.get(), h_probe, m * 8, cudaMemcpyHostToDevice, c->stream));
+    lower_bound_kernel<<<(unsigned)div_up(m, 128), 128, 0, c->stream>>>(keys, n, d.get(), (uint32_t)m, d.get() + m);
+    ZB_LAUNCH_CHECK(c);
+    ZB_CUDA(cudaMemcpyAsync(h_idx, d.get() + m, m * 8, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+}
+
 __global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint64_t n, uint32_t v) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
 }

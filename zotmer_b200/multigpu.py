@@ -203,6 +203,76 @@ def gather_counted_set(nat, kset, dist, rank, world, dev, root=0):
     return None
 
 
+def merge_sharded(nat, sets, dist, rank, world, dev, root=0):
+    """`zot merge` over several GPUs: the key space is cut into `world` ranges at splitters taken from
+    the quantiles of the inputs, rank r merges range r of EVERY input (no exchange during the merge: every rank
+    holds the inputs, e.g. decoded from the same files), and the ranges -- sorted and disjoint by construction --
+    are concatenated on `root`.  Returns the merged KmerSet on root, None elsewhere; identical to nat.merge(sets)."""
+    import torch
+    # splitters: equally spaced order statistics of the largest input (identical on every rank)
+    big = max(sets, key=len)
+    nb = len(big)
+    if world > 1 and nb >= world:
+        pos = np.array([(nb * r) // world for r in range(1, world)], dtype=np.int64)
+        kp, _ = big.dev_ptrs()
+        keys = _as_tensor(kp, nb, torch.int64, dev)
+        split = keys[torch.from_numpy(pos).to(keys.device)].cpu().numpy().view(np.uint64)
+    else:
+        split = np.zeros(0, np.uint64)
+    lo = None if rank == 0 or len(split) == 0 else split[rank - 1]
+    hi = None if rank == world - 1 or len(split) == 0 else split[rank]
+    if len(split) == 0 and rank != 0:
+        lo = hi = None
+    parts = []
+    for s in sets:
+        n = len(s)
+        if len(split) == 0:
+            b, e = (0, n) if rank == 0 else (0, 0)
+        else:
+            probes = [x for x in (lo, hi) if x is not None]
+            idx = s.lower_bound(np.array(probes, np.uint64)) if probes else []
+            b = 0 if lo is None else int(idx[0])
+            e = n if hi is None else int(idx[-1])
+        parts.append(s.slice(b, e))
+    mine = nat.merge(parts) if len(parts) > 1 else parts[0]
+    for p in parts:
+        if p is not mine:
+            p.free()
+    # concatenate the ranges on root, in rank order
+    n = len(mine)
+    sizes = [None] * world
+    dist.all_gather_object(sizes, n)
+    dv = "cuda:%d" % dev
+    kp, cp = mine.dev_ptrs()
+    k_local = _as_tensor(kp, n, torch.int64, dev)
+    c_local = _as_tensor(cp, n, torch.int32, dev)
+    out = None
+    if rank == root:
+        total = sum(sizes)
+        kb = torch.empty(max(total, 1), dtype=torch.int64, device=dv)
+        cb = torch.empty(max(total, 1), dtype=torch.int32, device=dv)
+        off = 0
+        reqs = []
+        for r in range(world):
+            if r == root:
+                kb[off:off + n].copy_(k_local)
+                cb[off:off + n].copy_(c_local)
+            elif sizes[r]:
+                reqs.append(dist.irecv(kb[off:off + sizes[r]], src=r))
+                reqs.append(dist.irecv(cb[off:off + sizes[r]], src=r))
+            off += sizes[r]
+        for q in reqs:
+            q.wait()
+        torch.cuda.synchronize(dev)
+        out = nat.KmerSet.from_device(kb.data_ptr(), cb.data_ptr(), total, dev)
+    elif n:
+        dist.send(k_local, dst=root)
+        dist.send(c_local, dst=root)
+    torch.cuda.synchronize(dev)
+    mine.free()
+    return out
+
+
 def _as_tensor(ptr, n, dtype, dev):
     """a torch view of n elements of library-owned device memory (no copy)"""
     import torch
