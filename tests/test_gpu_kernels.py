@@ -379,6 +379,33 @@ def test_kmerize_batched_flush(nat, monkeypatch):
     assert np.array_equal(ks, ek) and np.array_equal(cc, ec)
 
 
+@pytest.mark.parametrize("k", [25, 24, 31])
+def test_kmerize_low_complexity(nat, k):
+    """homopolymers, dinucleotide repeats and a tiny alphabet: a handful of k-mers with counts in the hundreds of thousands
+    (segments far beyond the shared-memory limit of the sort+count kernel), mixed with ordinary reads"""
+    rng = np.random.default_rng(k)
+    L = 100
+    reads = []
+    reads += [b"A" * L] * 3000 + [b"T" * L] * 2500 + [b"AT" * (L // 2)] * 2000 + [b"ACG" * (L // 3) + b"A"] * 1500
+    genome = rnd_dna(rng, 20000)
+    two = np.frombuffer(b"AC", np.uint8)[rng.integers(0, 2, 30000)].tobytes()
+    for i in range(6000):
+        p = int(rng.integers(0, len(genome) - L))
+        reads.append(genome[p:p + L])
+        p = int(rng.integers(0, len(two) - L))
+        reads.append(two[p:p + L])
+    order = rng.permutation(len(reads))
+    fq = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, reads[i], b"I" * L) for i in order)
+    s, nr = run_kmerize(nat, k, [(fq, False)])
+    ks, cc = s.fetch()
+    ek, ec, eacgt, enr = co.kmerize(k, [(fq, False)])
+    assert nr == enr
+    assert np.array_equal(ks, ek) and np.array_equal(cc, ec)
+    assert int(cc.max()) > 100000
+    st = s.stats()
+    assert st["acgt_weighted"] == eacgt and st["hist"] == co.hist(ec.astype(np.uint64))
+
+
 def test_kmerize_palindromes_even_k(nat):
     pal = b"ACGTTGCAAGCTTGCAACGT"
     fa = b">p\n" + pal * 50 + b"\n>q\n" + b"AT" * 100 + b"\n"
