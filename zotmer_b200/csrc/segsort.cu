@@ -186,6 +186,29 @@ segsort_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restri
     // Heads are sparse (one key in six for 30x reads), so the heads of a warp's 256 positions are dealt out
     // evenly to its 32 lanes: head number g of the warp goes to lane g % 32.
     const uint64_t base = (uint64_t)tile * SS_LOADED;
+    if (DISTINCT) {
+        // every key is a head: nothing to deal out, each thread finishes its own 8 positions; the segment's heads are
+        // simply its positions
+        uint32_t hb = headbits;
+        while (hb) {
+            const int j = __ffs(hb) - 1;
+            hb &= hb - 1;
+            const int q = q0 + j;
+            const uint64_t x = sk[ss_idx(q)];
+            const int st = mask_prev(sflag, q);
+            const int en = mask_next(sflag, q + 1);
+            const uint32_t hb0 = shbase[st >> 3] + __popc((shead[st >> 5] >> (st & 24)) & ((1u << (st & 7)) - 1u));
+            uint32_t r = 0;
+            for (int p2 = st; p2 < en; p2++) {
+                const uint64_t y = sk[ss_idx(p2)];
+                r += (y < x) ? 1u : 0u;
+                if (y == x && p2 != q) atomicExch(err, 2u);   // the caller's promise is broken
+            }
+            tmp_k[base + hb0 + r] = x;
+            tmp_c[base + hb0 + r] = __ldg(w + s + q);
+        }
+        return;
+    }
     const unsigned lane = tid & 31;
     const uint32_t hinc = warp_incl_scan<uint32_t>(__popc(headbits));
     const uint32_t Hw = __shfl_sync(0xffffffffu, hinc, 31);
