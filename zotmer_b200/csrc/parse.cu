@@ -14,8 +14,8 @@
 // whitespace run that contains a '\n' (or touches either end of the file) vanishes, while a
 // whitespace run inside a line is an ordinary invalid byte.  Whitespace = " \t\n\r\v\f" (py2 strip).
 //
-// Both kernels are single-pass: chained scans ("decoupled look-back") carry the line number / the
-// line state and the output offset from tile to tile.
+// FASTQ: three dependency-free kernels (per-tile counts, one-CTA scan, emit).  FASTA: single pass, a chained scan
+// ("decoupled look-back") carries the line state and the output offset from tile to tile.
 #include "kernels.h"
 #include "fasta_rules.cuh"
 
@@ -55,18 +55,6 @@ __device__ __forceinline__ uint32_t cells_excl_scan(uint32_t* cells /*[ROWS*WARP
 }
 
 // ------------------------------------------------------------------------------------- FASTQ
-__global__ void __launch_bounds__(256) count_newlines_kernel(const uint8_t* __restrict__ raw, uint64_t n,
-                                                            unsigned long long* __restrict__ out) {
-    unsigned long long c = 0;
-    const uint64_t chunks = (n + 15) / 16;
-    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < chunks; q += (uint64_t)gridDim.x * blockDim.x) {
-        const uint4 v = load16(raw, q * 16, n, 0);
-        c += count_eq(v, 0x0a0a0a0au);
-    }
-    c = warp_sum(c);
-    if (lane_id() == 0 && c) atomicAdd(out, c);
-}
-
 // 16 bytes -> 16-bit mask of the bytes equal to the (replicated) pattern
 __device__ __forceinline__ uint32_t eq_mask4(uint32_t w, uint32_t pat) {
     const uint32_t x = w ^ pat;
@@ -94,23 +82,116 @@ __device__ __forceinline__ uint32_t codes4(uint32_t w) {
     return (c & keep) | ((~ok & 0x80808080u) >> 5);             // 0x04 per invalid byte
 }
 
+// FASTQ in three dependency-free kernels (no CTA ever waits for another one):
+//   fq_count_kernel  per 16 KB tile: number of newlines, and the number of bytes that lie on lines whose index
+//                    INSIDE the tile is 0, 1, 2, 3 (mod 4) -- whichever of the four classes turns out to be "line 1
+//                    of a record" depends on the line number at the start of the tile, i.e. on a prefix sum
+//   fq_scan_kernel   one CTA: line number at the start of every tile -> emitted bytes of every tile -> output offset
+//   fastq_kernel     classifies, converts and compacts its tile straight to its final place
+// (the first version carried line number and output offset with two chained scans inside one kernel: 38 % of its
+// stall samples sat behind those look-backs, profiles/r01_kmerize_step.md)
+struct FqTile {
+    uint32_t nl;
+    uint32_t cls[4];
+};
+
 __global__ void __launch_bounds__(PA_THREADS)
-fastq_kernel(const uint8_t* __restrict__ raw, uint64_t n, const unsigned long long* __restrict__ n_newlines,
-             uint8_t* __restrict__ codes, uint64_t* __restrict__ st_lines, uint64_t* __restrict__ st_out,
-             uint32_t* __restrict__ ticket, uint64_t* __restrict__ total_out) {
-    __shared__ uint32_t s_tile;
+fq_count_kernel(const uint8_t* __restrict__ raw, uint64_t n, FqTile* __restrict__ tiles) {
+    __shared__ uint32_t s_nl[PA_ROWS * PA_WARPS];
+    __shared__ uint32_t s_cls[4];
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t base = (uint64_t)blockIdx.x * PA_TILE;
+    if (tid < 4) s_cls[tid] = 0;
+    uint32_t nlm[PA_ROWS], nlx[PA_ROWS], lim[PA_ROWS];
+#pragma unroll
+    for (int r = 0; r < PA_ROWS; r++) {
+        const uint64_t off = base + (uint64_t)r * (PA_THREADS * 16) + tid * 16;
+        const uint4 v = (off < n) ? load16(raw, off, n, 0) : make_uint4(0, 0, 0, 0);
+        lim[r] = (off >= n) ? 0u : (off + 16 > n ? (uint32_t)(n - off) : 16u);   // bytes of the chunk inside the text
+        nlm[r] = eq_mask16(v, 0x0a0a0a0au) & ((1u << lim[r]) - 1u);
+        const uint32_t c = __popc(nlm[r]);
+        const uint32_t inc = warp_incl_scan(c);
+        nlx[r] = inc - c;
+        if (lane == 31) s_nl[r * PA_WARPS + warp] = inc;
+    }
+    __syncthreads();
+    uint32_t tot = 0;
+    if (warp == 0) tot = cells_excl_scan(s_nl);
+    __syncthreads();
+    uint32_t cls[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < PA_ROWS; r++) {
+        uint32_t line = s_nl[r * PA_WARPS + warp] + nlx[r];   // line index inside the tile at the chunk's first byte
+        uint32_t rem = nlm[r], start = 0;
+        while (start < lim[r]) {
+            const uint32_t nxt = rem ? (uint32_t)(__ffs(rem) - 1) : lim[r] - 1u;   // last byte of this line inside the chunk
+            const uint32_t len = nxt + 1u - start;
+#pragma unroll
+            for (int q = 0; q < 4; q++) cls[q] += ((line & 3u) == (uint32_t)q) ? len : 0u;
+            if (!rem) break;
+            rem &= rem - 1u;
+            start = nxt + 1u;
+            line++;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t c = warp_sum(cls[q]);
+        if (lane == 0 && c) atomicAdd(&s_cls[q], c);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        FqTile t;
+        t.nl = tot;
+        for (int q = 0; q < 4; q++) t.cls[q] = s_cls[q];
+        tiles[blockIdx.x] = t;
+    }
+}
+
+// scalars[0] = number of newlines, scalars[1] = emitted bytes (written by fastq_kernel)
+__global__ void __launch_bounds__(1024)
+fq_scan_kernel(const FqTile* __restrict__ tiles, uint32_t ntiles, uint64_t* __restrict__ line0, uint64_t* __restrict__ out0,
+               unsigned long long* __restrict__ scalars) {
+    __shared__ uint64_t sm[1024 / 32 + 1];
+    uint64_t carry = 0;
+    for (uint32_t b0 = 0; b0 < ntiles; b0 += 1024) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint64_t v = (i < ntiles) ? tiles[i].nl : 0;
+        uint64_t tot;
+        const uint64_t ex = block_excl_scan<1024, uint64_t>(v, sm, &tot);
+        if (i < ntiles) line0[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) scalars[0] = carry;
+    __syncthreads();   // line0[] of this block's own earlier writes is visible to the whole block
+    carry = 0;
+    for (uint32_t b0 = 0; b0 < ntiles; b0 += 1024) {
+        const uint32_t i = b0 + threadIdx.x;
+        // sequence lines are those with global index = 1 (mod 4): local index = 1 - line0 (mod 4)
+        const uint64_t v = (i < ntiles) ? tiles[i].cls[(1u - (uint32_t)line0[i]) & 3u] : 0;
+        uint64_t tot;
+        const uint64_t ex = block_excl_scan<1024, uint64_t>(v, sm, &tot);
+        if (i < ntiles) out0[i] = carry + ex;
+        carry += tot;
+    }
+}
+
+__global__ void __launch_bounds__(PA_THREADS)
+fastq_kernel(const uint8_t* __restrict__ raw, uint64_t n, const unsigned long long* __restrict__ scalars,
+             uint8_t* __restrict__ codes, const uint64_t* __restrict__ tile_line0, const uint64_t* __restrict__ tile_out0,
+             unsigned long long* __restrict__ total_out) {
     __shared__ uint32_t s_nl[PA_ROWS * PA_WARPS];
     __shared__ uint32_t s_em[PA_ROWS * PA_WARPS];
-    __shared__ uint64_t s_pref[2];
+    __shared__ uint32_t s_tot;
     __shared__ __align__(16) uint8_t s_stage[PA_TILE + 32];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = blockIdx.x;
     const uint64_t base = (uint64_t)tile * PA_TILE;
     // complete records only: lines = newlines (+1 if the text does not end in '\n')
-    const uint64_t lines = *n_newlines + ((n > 0 && raw[n - 1] != '\n') ? 1 : 0);
+    const uint64_t lines = scalars[0] + ((n > 0 && raw[n - 1] != '\n') ? 1 : 0);
     const uint64_t max_line = (lines >> 2) << 2;
+    const uint64_t line0 = tile_line0[tile];
+    const uint64_t out0 = tile_out0[tile];
 
     uint4 v[PA_ROWS];
     uint32_t nlm[PA_ROWS];  // newline mask of my 16 bytes
@@ -120,19 +201,15 @@ fastq_kernel(const uint8_t* __restrict__ raw, uint64_t n, const unsigned long lo
         const uint64_t off = base + (uint64_t)r * (PA_THREADS * 16) + tid * 16;
         v[r] = (off < n) ? load16(raw, off, n, 0) : make_uint4(0, 0, 0, 0);
         nlm[r] = eq_mask16(v[r], 0x0a0a0a0au);
+        if (off + 16 > n) nlm[r] &= (off < n) ? ((1u << (n - off)) - 1u) : 0u;
         const uint32_t c = __popc(nlm[r]);
         const uint32_t inc = warp_incl_scan(c);
         nlx[r] = inc - c;
         if (lane == 31) s_nl[r * PA_WARPS + warp] = inc;
     }
     __syncthreads();
-    if (warp == 0) {
-        const uint32_t tot = cells_excl_scan(s_nl);
-        const uint64_t p = lookback_u64(st_lines, tile, tot);
-        if (lane == 0) s_pref[0] = p;
-    }
+    if (warp == 0) cells_excl_scan(s_nl);
     __syncthreads();
-    const uint64_t line0 = s_pref[0];
 
     // emitted bytes: those on line 1 (mod 4) of a complete record, the terminating '\n' included
     uint32_t em[PA_ROWS], emx[PA_ROWS];
@@ -160,16 +237,15 @@ fastq_kernel(const uint8_t* __restrict__ raw, uint64_t n, const unsigned long lo
     __syncthreads();
     if (warp == 0) {
         const uint32_t tot = cells_excl_scan(s_em);
-        const uint64_t p = lookback_u64(st_out, tile, tot);
         if (lane == 0) {
-            s_pref[1] = p;
-            s_nl[0] = tot;   // (s_nl is dead) tile total for the copy-out
-            if (base + PA_TILE >= n) *total_out = p + tot;
+            s_tot = tot;
+            // offsets come from counts that ignore the dropped partial record at the very end of the text; every byte
+            // that IS emitted sits before the dropped ones, so its offset is exact and the largest end is the total
+            if (tot) atomicMax(total_out, (unsigned long long)(out0 + tot));
         }
     }
     __syncthreads();
-    const uint64_t out0 = s_pref[1];
-    const uint32_t tot = s_nl[0];
+    const uint32_t tot = s_tot;
     const uint32_t mis = (uint32_t)((uintptr_t)(codes + out0) & 15u);   // stage congruent to the global address
 #pragma unroll
     for (int r = 0; r < PA_ROWS; r++) {
@@ -209,19 +285,19 @@ void parse_fastq(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n
     *n_records = 0;
     if (n == 0) return;
     const uint32_t tiles = (uint32_t)div_up(n, PA_TILE);
-    DBuf<uint64_t> st(c, (size_t)tiles * 2 + 4);
-    ZB_CUDA(cudaMemsetAsync(st.get(), 0, ((size_t)tiles * 2 + 4) * 8, c->stream));
-    uint64_t* st_lines = st.get();
-    uint64_t* st_out = st.get() + tiles;
-    unsigned long long* nnl = reinterpret_cast<unsigned long long*>(st.get() + 2 * (size_t)tiles);
-    uint64_t* total = st.get() + 2 * (size_t)tiles + 1;
-    uint32_t* ticket = reinterpret_cast<uint32_t*>(st.get() + 2 * (size_t)tiles + 2);
-    int blocks = (int)std::min<size_t>((size_t)c->sm_count * 8, div_up(n, 256 * 16));
-    count_newlines_kernel<<<blocks, 256, 0, c->stream>>>(raw, n, nnl);
+    DBuf<FqTile> info(c, tiles);
+    DBuf<uint64_t> st(c, (size_t)tiles * 2 + 2);
+    uint64_t* line0 = st.get();
+    uint64_t* out0 = st.get() + tiles;
+    unsigned long long* scalars = reinterpret_cast<unsigned long long*>(st.get() + 2 * (size_t)tiles);   // [0] newlines [1] codes
+    ZB_CUDA(cudaMemsetAsync(scalars, 0, 16, c->stream));
+    fq_count_kernel<<<tiles, PA_THREADS, 0, c->stream>>>(raw, n, info.get());
     ZB_LAUNCH_CHECK(c);
-    fastq_kernel<<<tiles, PA_THREADS, 0, c->stream>>>(raw, n, nnl, codes, st_lines, st_out, ticket, total);
+    fq_scan_kernel<<<1, 1024, 0, c->stream>>>(info.get(), tiles, line0, out0, scalars);
     ZB_LAUNCH_CHECK(c);
-    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, nnl, 16, cudaMemcpyDeviceToHost, c->stream));
+    fastq_kernel<<<tiles, PA_THREADS, 0, c->stream>>>(raw, n, scalars, codes, line0, out0, scalars + 1);
+    ZB_LAUNCH_CHECK(c);
+    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, scalars, 16, cudaMemcpyDeviceToHost, c->stream));
     uint8_t last = 0;
     ZB_CUDA(cudaMemcpyAsync(&last, raw + n - 1, 1, cudaMemcpyDeviceToHost, c->stream));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
