@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -22,8 +23,19 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// One context (stream, allocator, scratch scalars) per (device, host thread): two host threads that drive the same
+// GPU get two streams, so the H2D copy of one batch overlaps the kernels of another (bench.py's e2e does that).
 static std::mutex g_ctx_mu;
-static std::map<int, Ctx*> g_ctx;  // one context per device (calls on a device are serialised by the caller)
+static std::map<std::pair<int, std::thread::id>, Ctx*> g_ctx;
+static bool g_profile_on[64] = {false};
+
+static std::vector<Ctx*> contexts_of(int device) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    std::vector<Ctx*> v;
+    for (auto& kv : g_ctx)
+        if (kv.first.first == device) v.push_back(kv.second);
+    return v;
+}
 
 Ctx* ctx_for(int device) {
     std::lock_guard<std::mutex> lk(g_ctx_mu);
@@ -35,16 +47,18 @@ Ctx* ctx_for(int device) {
     }
     if (device < 0 || device >= ndev) ZB_FAIL(ZB_E_ARG, "device %d out of range (have %d)", device, ndev);
     ZB_CUDA(cudaSetDevice(device));
-    auto it = g_ctx.find(device);
+    const auto key = std::make_pair(device, std::this_thread::get_id());
+    auto it = g_ctx.find(key);
     if (it != g_ctx.end()) return it->second;
     Ctx* c = new Ctx();
+    c->profile = g_profile_on[device & 63];
     c->device = device;
     cudaDeviceProp prop;
     ZB_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     ZB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     ZB_CUDA(cudaMallocHost((void**)&c->h_scalars, 64 * sizeof(uint64_t)));
-    g_ctx[device] = c;
+    g_ctx[key] = c;
     return c;
 }
 
@@ -58,6 +72,7 @@ static size_t round_block(size_t b) {
 }
 
 void* dalloc(Ctx* c, size_t bytes) {
+    std::lock_guard<std::mutex> lk(c->alloc_mu);   // a set may be freed by another thread than the one that made it
     const size_t want = round_block(bytes);
     auto it = c->free_blocks.lower_bound(want);
     if (it != c->free_blocks.end() && it->first <= want + want / 4) {
@@ -74,7 +89,9 @@ void* dalloc(Ctx* c, size_t bytes) {
     if (e != cudaSuccess) {
         cudaGetLastError();
         cudaStreamSynchronize(c->stream);
-        dtrim(c);
+        for (auto& kv : c->free_blocks) cudaFree(kv.second);
+        c->free_blocks.clear();
+        c->cached_bytes = 0;
         e = cudaMalloc(&p, want);
     }
     if (e != cudaSuccess) {
@@ -89,6 +106,7 @@ void* dalloc(Ctx* c, size_t bytes) {
 
 void dfree(Ctx* c, void* p) {
     if (!p) return;
+    std::lock_guard<std::mutex> lk(c->alloc_mu);
     auto it = c->live_blocks.find(p);
     if (it == c->live_blocks.end()) return;
     const size_t sz = it->second;
@@ -99,6 +117,7 @@ void dfree(Ctx* c, void* p) {
 }
 
 void dtrim(Ctx* c) {
+    std::lock_guard<std::mutex> lk(c->alloc_mu);
     for (auto& kv : c->free_blocks) cudaFree(kv.second);
     c->free_blocks.clear();
     c->cached_bytes = 0;
@@ -259,22 +278,27 @@ int zb_device_count(int* n) {
 
 int zb_launch_count(int device, uint64_t* n) {
     ZB_TRY
-    *n = ctx_for(device)->launches;
+    ctx_for(device);
+    uint64_t tot = 0;
+    for (Ctx* c : contexts_of(device)) tot += c->launches;   // every host thread's context on this device
+    *n = tot;
     ZB_CATCH
 }
 
 int zb_release_cache(int device) {
     ZB_TRY
-    Ctx* c = ctx_for(device);
-    ZB_CUDA(cudaStreamSynchronize(c->stream));
-    dtrim(c);
+    ctx_for(device);
+    for (Ctx* c : contexts_of(device)) {
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+        dtrim(c);
+    }
     ZB_CATCH
 }
 
 int zb_device_sync(int device) {
     ZB_TRY
-    Ctx* c = ctx_for(device);
-    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    ctx_for(device);
+    for (Ctx* c : contexts_of(device)) ZB_CUDA(cudaStreamSynchronize(c->stream));
     ZB_CATCH
 }
 
@@ -975,17 +999,20 @@ int zb_dbg_extract(int device, int k, const uint8_t* codes, size_t n, uint64_t* 
 // per-stage CUDA-event timing of everything this context runs between on=1 and the report
 int zb_dbg_profile(int device, int on, char* report, size_t cap) {
     ZB_TRY
-    Ctx* c = ctx_for(device);
-    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    ctx_for(device);
+    const std::vector<Ctx*> all = contexts_of(device);   // stages of every host thread's context on this device
+    for (Ctx* c : all) ZB_CUDA(cudaStreamSynchronize(c->stream));
     if (report && cap) {
         std::map<std::string, std::pair<double, int>> agg;
         std::vector<std::string> order;
-        for (auto& r : c->stages) {
-            float ms = 0;
-            if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) ms = -1;
-            if (!agg.count(r.name)) order.push_back(r.name);
-            agg[r.name].first += ms;
-            agg[r.name].second += 1;
+        for (Ctx* c : all) {
+            for (auto& r : c->stages) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) ms = -1;
+                if (!agg.count(r.name)) order.push_back(r.name);
+                agg[r.name].first += ms;
+                agg[r.name].second += 1;
+            }
         }
         std::string out;
         char line[160];
@@ -995,9 +1022,12 @@ int zb_dbg_profile(int device, int on, char* report, size_t cap) {
         }
         snprintf(report, cap, "%s", out.c_str());
     }
-    for (auto& r : c->stages) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
-    c->stages.clear();
-    c->profile = (on != 0);
+    for (Ctx* c : all) {
+        for (auto& r : c->stages) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+        c->stages.clear();
+        c->profile = (on != 0);
+    }
+    g_profile_on[device & 63] = (on != 0);
     ZB_CATCH
 }
 

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <map>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -36,8 +37,8 @@ struct Fail {
     } while (0)
 
 // ----------------------------------------------------------------------------- device context
-// One context per (host thread, device): a stream, a stream-ordered memory pool that keeps its
-// pages (so repeated batches do not pay cudaMalloc), and a few scratch scalars in pinned memory.
+// One context per (host thread, device): a stream, a caching device allocator (so repeated batches do not pay
+// cudaMalloc), and a few scratch scalars in pinned memory.  A handle stays with the context that created it.
 struct Ctx {
     int device = -1;
     int sm_count = 0;
@@ -50,6 +51,7 @@ struct Ctx {
     std::multimap<size_t, void*> free_blocks;
     std::unordered_map<void*, size_t> live_blocks;
     size_t cached_bytes = 0, live_bytes = 0;
+    std::mutex alloc_mu;
     bool profile = false;
     struct StageRec { const char* name; cudaEvent_t e0, e1; };
     std::vector<StageRec> stages;
