@@ -445,8 +445,8 @@ def test_merge(nat, sizes):
 
 
 def test_merge_nway_equals_pairwise_tree(nat, monkeypatch):
-    """>= 4 inputs go through one weighted sort + count of the concatenation; it must equal the reference-shaped
-    pairwise tree (ZB_MERGE=tree) and the oracle, including counts that add up past 2^16 and empty inputs"""
+    """>= 3 inputs are merged bucket by bucket of the key space in shared memory (nwaymerge.cu); it must equal the
+    reference-shaped pairwise tree (ZB_MERGE=tree) and the oracle, including counts that add up past 2^16 and empty inputs"""
     rng = np.random.default_rng(44)
     pool = np.unique(rng.integers(0, 2 ** 50, 150000, dtype=np.uint64))
     sets = []
@@ -467,11 +467,79 @@ def test_merge_nway_equals_pairwise_tree(nat, monkeypatch):
     assert np.array_equal(ak, ek) and np.array_equal(ac.astype(np.uint64), ec)
     # a sum beyond 2^32-1 is an error on both paths (the reference's array('I') would overflow)
     big = [nat.KmerSet.from_arrays(np.array([7, 9], np.uint64), np.array([2 ** 31, 1], np.uint32)) for _ in range(4)]
-    for mode in (None, "tree"):
+    for mode in (None, "sort", "tree"):
         if mode:
             monkeypatch.setenv("ZB_MERGE", mode)
         with pytest.raises(IndexError):
             nat.merge(big)
+
+
+def _merge_all_modes(nat, monkeypatch, sets):
+    """zb_merge through its three routes (key-range buckets in shared memory = default, weighted sort of the
+    concatenation, pairwise tree) against the oracle"""
+    hs = [nat.KmerSet.from_arrays(k, c) for k, c in sets]
+    ek, ec = co.merge([(k, c.astype(np.uint64)) for k, c in sets])
+    for mode in (None, "sort", "tree"):
+        if mode:
+            monkeypatch.setenv("ZB_MERGE", mode)
+        else:
+            monkeypatch.delenv("ZB_MERGE", raising=False)
+        m = nat.merge(hs)
+        mk, mc = m.fetch()
+        assert np.array_equal(mk, ek) and np.array_equal(mc.astype(np.uint64), ec), mode
+        m.free()
+    monkeypatch.delenv("ZB_MERGE", raising=False)
+    for h in hs:
+        h.free()
+
+
+@pytest.mark.parametrize("nsets,n,bits", [(3, 50000, 50), (64, 20000, 50), (200, 3000, 50), (7, 100000, 64), (5, 2000, 10),
+                                          (16, 300, 3), (33, 1, 50), (1024, 500, 40)])
+def test_merge_buckets_shapes(nat, monkeypatch, nsets, n, bits):
+    rng = np.random.default_rng(nsets * 1000 + bits)
+    pool = np.unique(rng.integers(0, 2 ** bits if bits < 64 else 2 ** 64 - 1, 3 * n, dtype=np.uint64, endpoint=False))
+    sets = []
+    for i in range(nsets):
+        k = np.sort(rng.choice(pool, min(n, len(pool)) if i % 7 != 6 else 0, replace=False))
+        sets.append((k, rng.integers(1, 1000, len(k), dtype=np.uint32)))
+    _merge_all_modes(nat, monkeypatch, sets)
+
+
+def test_merge_buckets_skewed_keys(nat, monkeypatch):
+    """key spaces that the interpolated bucket search and the fixed-prefix buckets do not like: a dense cluster
+    (more bucket bits needed), everything in one tiny range (falls back to the sort), identical inputs"""
+    rng = np.random.default_rng(77)
+    # 90 % of the keys inside 2^-20 of the key space
+    dense = np.unique(np.concatenate([rng.integers(2 ** 45, 2 ** 45 + 2 ** 30, 180000, dtype=np.uint64),
+                                      rng.integers(0, 2 ** 50, 20000, dtype=np.uint64)]))
+    sets = []
+    for i in range(12):
+        k = np.sort(rng.choice(dense, 60000, replace=False))
+        sets.append((k, rng.integers(1, 9, len(k), dtype=np.uint32)))
+    _merge_all_modes(nat, monkeypatch, sets)
+    # consecutive integers plus one far outlier: almost every key shares all of its top bits
+    base = np.arange(1, 200001, dtype=np.uint64)
+    sets = [(np.concatenate([base[i::3], np.array([2 ** 63 + 5], np.uint64)]), np.full(len(base[i::3]) + 1, i + 1, np.uint32))
+            for i in range(6)]
+    _merge_all_modes(nat, monkeypatch, sets)
+    # the same set 40 times: every bucket holds each key 40 times
+    k, c = random_set(rng, 30000)
+    _merge_all_modes(nat, monkeypatch, [(k, c)] * 40)
+
+
+def test_merge_more_inputs_than_buckets_take(nat, monkeypatch):
+    """> 1024 inputs do not fit the bucket kernel's slice table: the sort route takes over, same result"""
+    rng = np.random.default_rng(78)
+    pool = np.unique(rng.integers(0, 2 ** 50, 5000, dtype=np.uint64))
+    sets = []
+    for i in range(1100):
+        k = np.sort(rng.choice(pool, 40, replace=False))
+        sets.append((k, rng.integers(1, 5, len(k), dtype=np.uint32)))
+    hs = [nat.KmerSet.from_arrays(k, c) for k, c in sets]
+    m = nat.merge(hs)
+    mk, mc = m.fetch()
+    ek, ec = co.merge([(k, c.astype(np.uint64)) for k, c in sets])
+    assert np.array_equal(mk, ek) and np.array_equal(mc.astype(np.uint64), ec)
 
 
 def test_stats_large_counts(nat):

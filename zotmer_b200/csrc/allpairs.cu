@@ -193,7 +193,7 @@ static bool allpairs_try(Ctx* c, const SetRef* d_sets, int nsets, uint32_t NB, i
                          uint32_t ntiles, uint64_t* d_abc) {
     DBuf<uint32_t> boff(c, (size_t)nsets * (NB + 1) + 1);
     unsigned int* d_ovf = reinterpret_cast<unsigned int*>(boff.get() + (size_t)nsets * (NB + 1));
-    ZB_CUDA(cudaMemsetAsync(d_ovf, 0, 4, c->stream));
+    ZB_CUDA(dev_memset(c, d_ovf, 0, 4));
     {
         const uint64_t tot = (uint64_t)nsets * (NB + 1);
         bucket_offsets_kernel<<<(unsigned)div_up(tot, 256), 256, 0, c->stream>>>(d_sets, nsets, shift, NB, boff.get());
@@ -210,7 +210,7 @@ static bool allpairs_try(Ctx* c, const SetRef* d_sets, int nsets, uint32_t NB, i
     allpairs_kernel<<<(unsigned)(groups * ntiles), AP_THREADS, smem, c->stream>>>(
         d_sets, nsets, boff.get(), NB, nblk, tile_begin, ntiles, reinterpret_cast<unsigned long long*>(d_abc), d_ovf);
     ZB_LAUNCH_CHECK(c);
-    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, d_ovf, 4, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(read_back(c, d_ovf, 4));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     return reinterpret_cast<uint32_t*>(c->h_scalars)[0] == 0;
 }
@@ -254,7 +254,7 @@ void allpairs_abc(Ctx* c, const std::vector<SetRef>& refs, uint64_t tile_begin, 
         if (lgNB > 24) break;
         const uint32_t NB = 1u << lgNB;
         if (div_up(NB, AP_BPC) * (uint64_t)ntiles > 0x7fffffffull) break;
-        ZB_CUDA(cudaMemsetAsync(d_abc.get(), 0, npairs * 3 * 8, c->stream));
+        ZB_CUDA(dev_memset(c, d_abc.get(), 0, npairs * 3 * 8));
         ok = allpairs_try(c, d_refs.get(), nsets, NB, key_bits - lgNB, nblk, (uint32_t)tile_begin, ntiles, d_abc.get());
         if (lgNB == key_bits) break;
     }

@@ -57,9 +57,58 @@ Ctx* ctx_for(int device) {
     ZB_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     ZB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    ZB_CUDA(cudaMallocHost((void**)&c->h_scalars, 64 * sizeof(uint64_t)));
+    ZB_CUDA(cudaHostAlloc((void**)&c->h_scalars, 64 * sizeof(uint64_t), cudaHostAllocMapped));
+    ZB_CUDA(cudaHostGetDevicePointer((void**)&c->d_h_scalars, c->h_scalars, 0));
     g_ctx[key] = c;
     return c;
+}
+
+__global__ void readback_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst_host, int nwords) {
+    if ((int)threadIdx.x < nwords) dst_host[threadIdx.x] = src[threadIdx.x];
+}
+
+cudaError_t read_back(Ctx* c, const void* d_src, size_t bytes) {
+    if (bytes > 128 || (bytes & 3)) return cudaErrorInvalidValue;
+    readback_kernel<<<1, 32, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(d_src), c->d_h_scalars, (int)(bytes / 4));
+    return cudaGetLastError();
+}
+
+// generic fill: bytes up to the first 16-byte boundary and after the last one singly, the body as uint4
+__global__ void __launch_bounds__(256) fill_kernel(uint8_t* __restrict__ p, uint8_t v, size_t n) {
+    const size_t head = min(n, (size_t)((16 - ((uintptr_t)p & 15)) & 15));
+    const size_t body = (n - head) / 16;
+    const size_t t0 = (size_t)blockIdx.x * 256 + threadIdx.x, stride = (size_t)gridDim.x * 256;
+    const uint32_t w = 0x01010101u * v;
+    uint4* __restrict__ q = reinterpret_cast<uint4*>(p + head);
+    for (size_t i = t0; i < body; i += stride) q[i] = make_uint4(w, w, w, w);
+    if (t0 < head) p[t0] = v;
+    const size_t tail0 = head + body * 16;
+    if (t0 < n - tail0) p[tail0 + t0] = v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) copy_kernel(T* __restrict__ dst, const T* __restrict__ src, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) dst[i] = src[i];
+}
+
+cudaError_t dev_memset(Ctx* c, void* p, int value, size_t bytes) {
+    if (bytes == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<size_t>((size_t)c->sm_count * 8, div_up(std::max<size_t>(bytes / 16, 32), 256));
+    fill_kernel<<<blocks, 256, 0, c->stream>>>(reinterpret_cast<uint8_t*>(p), (uint8_t)value, bytes);
+    return cudaGetLastError();
+}
+
+cudaError_t dev_copy(Ctx* c, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return cudaSuccess;
+    const uintptr_t al = (uintptr_t)dst | (uintptr_t)src | (uintptr_t)bytes;
+    const size_t unit = (al & 15) == 0 ? 16 : (al & 7) == 0 ? 8 : (al & 3) == 0 ? 4 : 1;
+    const size_t n = bytes / unit;
+    const unsigned blocks = (unsigned)std::min<size_t>((size_t)c->sm_count * 8, div_up(n, 256));
+    if (unit == 16) copy_kernel<uint4><<<blocks, 256, 0, c->stream>>>((uint4*)dst, (const uint4*)src, n);
+    else if (unit == 8) copy_kernel<uint64_t><<<blocks, 256, 0, c->stream>>>((uint64_t*)dst, (const uint64_t*)src, n);
+    else if (unit == 4) copy_kernel<uint32_t><<<blocks, 256, 0, c->stream>>>((uint32_t*)dst, (const uint32_t*)src, n);
+    else copy_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((uint8_t*)dst, (const uint8_t*)src, n);
+    return cudaGetLastError();
 }
 
 static size_t round_block(size_t b) {
@@ -145,7 +194,7 @@ struct zb_kmerizer {
 
 static size_t read_pending_count(zb_kmerizer* h) {
     Ctx* c = h->c;
-    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, h->d_count.get(), 8, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(read_back(c, h->d_count.get(), 8));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     return (size_t)c->h_scalars[0];
 }
@@ -157,7 +206,7 @@ static void ensure_pending(zb_kmerizer* h, size_t need_total) {
     DBuf<uint64_t> nb(c, ncap);
     if (h->pending_upper) {
         size_t have = read_pending_count(h);
-        ZB_CUDA(cudaMemcpyAsync(nb.get(), h->pending.get(), have * 8, cudaMemcpyDeviceToDevice, c->stream));
+        ZB_CUDA(dev_copy(c, nb.get(), h->pending.get(), have * 8));
     }
     h->pending = std::move(nb);
     h->pending_cap = ncap;
@@ -178,7 +227,7 @@ static void flush_pending(zb_kmerizer* h) {
     if (h->pending_upper == 0) return;
     const size_t n = read_pending_count(h);
     h->pending_upper = 0;
-    ZB_CUDA(cudaMemsetAsync(h->d_count.get(), 0, 8, c->stream));
+    ZB_CUDA(dev_memset(c, h->d_count.get(), 0, 8));
     count_keys(h, h->pending.get(), n);
 }
 
@@ -195,8 +244,8 @@ static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n) {
     if (h->acc_n == 0) {
         h->acc_k.alloc(c, nd);
         h->acc_c.alloc(c, nd);
-        ZB_CUDA(cudaMemcpyAsync(h->acc_k.get(), other, nd * 8, cudaMemcpyDeviceToDevice, c->stream));
-        ZB_CUDA(cudaMemcpyAsync(h->acc_c.get(), dc.get(), nd * 4, cudaMemcpyDeviceToDevice, c->stream));
+        ZB_CUDA(dev_copy(c, h->acc_k.get(), other, nd * 8));
+        ZB_CUDA(dev_copy(c, h->acc_c.get(), dc.get(), nd * 4));
         h->acc_n = nd;
     } else {
         const size_t tot = h->acc_n + nd;
@@ -239,7 +288,7 @@ static void feed_dev_impl(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is
     const size_t cap = 32 + n + 2 * EXTRACT_TILE + 64;
     DBuf<uint8_t> codes(c, cap);
     uint8_t* cd = codes.get() + 32;
-    ZB_CUDA(cudaMemsetAsync(codes.get(), 4, 32, c->stream));
+    ZB_CUDA(dev_memset(c, codes.get(), 4, 32));
     size_t n_codes = 0;
     uint64_t n_rec = 0;
     {
@@ -250,8 +299,28 @@ static void feed_dev_impl(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is
     h->n_records += n_rec;
     if (n_codes == 0) return;
     const size_t padded = div_up(n_codes, EXTRACT_TILE) * EXTRACT_TILE + 32;
-    ZB_CUDA(cudaMemsetAsync(cd + n_codes, 4, padded - n_codes, c->stream));
+    ZB_CUDA(dev_memset(c, cd + n_codes, 4, padded - n_codes));
     extract_codes(h, cd, n_codes);
+}
+
+// Large host <-> device copies go out in 16 MiB pieces with at most three of them queued: a copy engine serves the
+// streams of all host threads in the order the transfers were queued, so whatever another thread's step needs from
+// the engine waits for three pieces, not for a whole 315 MB input (measured: with one 315 MB copy queued the other
+// thread's sort + count took 13 ms instead of 6).
+static void copy_chunked(Ctx* c, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    const size_t piece = (size_t)16 << 20;
+    if (bytes <= 2 * piece) {
+        ZB_CUDA(cudaMemcpyAsync(dst, src, bytes, kind, c->stream));
+        return;
+    }
+    if (!c->copy_ev[0])
+        for (int i = 0; i < 3; i++) ZB_CUDA(cudaEventCreateWithFlags(&c->copy_ev[i], cudaEventDisableTiming));
+    size_t i = 0;
+    for (size_t o = 0; o < bytes; o += piece, i++) {
+        if (i >= 3) ZB_CUDA(cudaEventSynchronize(c->copy_ev[i % 3]));
+        ZB_CUDA(cudaMemcpyAsync((char*)dst + o, (const char*)src + o, std::min(piece, bytes - o), kind, c->stream));
+        ZB_CUDA(cudaEventRecord(c->copy_ev[i % 3], c->stream));
+    }
 }
 
 static zb_set* new_set(Ctx* c, size_t n) {
@@ -312,7 +381,7 @@ int zb_kmerize_open(int k, int device, zb_kmerizer** out) {
     h->c = c;
     h->k = k;
     h->d_count.alloc(c, 2);
-    ZB_CUDA(cudaMemsetAsync(h->d_count.get(), 0, 16, c->stream));
+    ZB_CUDA(dev_memset(c, h->d_count.get(), 0, 16));
     {   // tuning / cross-check switches, re-read at every open (unset = default)
         const char* e = getenv("ZB_SORT_COUNT");
         g_sort_count_mode = e ? atoi(e) : 0;
@@ -345,7 +414,7 @@ int zb_kmerize_feed(zb_kmerizer* h, const uint8_t* raw, size_t n, int is_fasta) 
     DBuf<uint8_t> d(c, n + 16);
     {
         Stage st(c, "h2d");
-        ZB_CUDA(cudaMemcpyAsync(d.get(), raw, n, cudaMemcpyHostToDevice, c->stream));
+        copy_chunked(c, d.get(), raw, n, cudaMemcpyHostToDevice);
     }
     feed_dev_impl(h, d.get(), n, is_fasta);
     ZB_CATCH
@@ -359,9 +428,9 @@ int zb_kmerize_feed_codes_dev(zb_kmerizer* h, const uint8_t* d_codes, size_t n, 
     if (n == 0) { h->n_records += n_records; return ZB_OK; }
     const size_t padded = div_up(n, EXTRACT_TILE) * EXTRACT_TILE + 32;
     DBuf<uint8_t> codes(c, 32 + padded);
-    ZB_CUDA(cudaMemsetAsync(codes.get(), 4, 32, c->stream));
-    ZB_CUDA(cudaMemcpyAsync(codes.get() + 32, d_codes, n, cudaMemcpyDeviceToDevice, c->stream));
-    ZB_CUDA(cudaMemsetAsync(codes.get() + 32 + n, 4, padded - n, c->stream));
+    ZB_CUDA(dev_memset(c, codes.get(), 4, 32));
+    ZB_CUDA(dev_copy(c, codes.get() + 32, d_codes, n));
+    ZB_CUDA(dev_memset(c, codes.get() + 32 + n, 4, padded - n));
     extract_codes(h, codes.get() + 32, n);
     h->n_records += n_records;
     ZB_CATCH
@@ -427,7 +496,7 @@ int zb_kmerize_take_bucketed_dev(zb_kmerizer* h, int nranks, uint64_t* d_keys, u
     ZB_CUDA(cudaSetDevice(c->device));
     const size_t n = h->pending_upper ? read_pending_count(h) : 0;
     DBuf<unsigned long long> cnt(c, 128);
-    ZB_CUDA(cudaMemsetAsync(cnt.get(), 0, 128 * 8, c->stream));
+    ZB_CUDA(dev_memset(c, cnt.get(), 0, 128 * 8));
     bucket_count(c, h->pending.get(), n, nranks, cnt.get());
     std::vector<unsigned long long> hc(64, 0), start(64, 0);
     ZB_CUDA(cudaMemcpyAsync(hc.data(), cnt.get(), 64 * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -439,7 +508,7 @@ int zb_kmerize_take_bucketed_dev(zb_kmerizer* h, int nranks, uint64_t* d_keys, u
     bucket_scatter(c, h->pending.get(), n, nranks, cnt.get() + 64, d_keys);
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     h->pending_upper = 0;
-    ZB_CUDA(cudaMemsetAsync(h->d_count.get(), 0, 8, c->stream));
+    ZB_CUDA(dev_memset(c, h->d_count.get(), 0, 8));
     ZB_CATCH
 }
 
@@ -450,7 +519,7 @@ int zb_kmerize_bucket_counts(zb_kmerizer* h, int nranks, uint64_t* bucket_counts
     ZB_CUDA(cudaSetDevice(c->device));
     const size_t n = h->pending_upper ? read_pending_count(h) : 0;
     DBuf<unsigned long long> cnt(c, 64);
-    ZB_CUDA(cudaMemsetAsync(cnt.get(), 0, 64 * 8, c->stream));
+    ZB_CUDA(dev_memset(c, cnt.get(), 0, 64 * 8));
     bucket_count(c, h->pending.get(), n, nranks, cnt.get());
     std::vector<unsigned long long> hc(64, 0);
     ZB_CUDA(cudaMemcpyAsync(hc.data(), cnt.get(), 64 * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -468,14 +537,14 @@ int zb_kmerize_route_p2p(zb_kmerizer* h, int nranks, uint64_t* const* d_dst) {
     PeerPtrs pp;
     for (int r = 0; r < 64; r++) pp.p[r] = (r < nranks) ? d_dst[r] : nullptr;
     DBuf<unsigned long long> cur(c, 64);
-    ZB_CUDA(cudaMemsetAsync(cur.get(), 0, 64 * 8, c->stream));
+    ZB_CUDA(dev_memset(c, cur.get(), 0, 64 * 8));
     {
         Stage st(c, "route_p2p");
         route_p2p(c, h->pending.get(), n, nranks, pp, cur.get());
     }
     ZB_CUDA(cudaStreamSynchronize(c->stream));   // every store, local or over NVLink, has been issued and completed
     h->pending_upper = 0;
-    ZB_CUDA(cudaMemsetAsync(h->d_count.get(), 0, 8, c->stream));
+    ZB_CUDA(dev_memset(c, h->d_count.get(), 0, 8));
     ZB_CATCH
 }
 
@@ -543,7 +612,7 @@ int zb_kmerize_add_canonical_dev(zb_kmerizer* h, const uint64_t* d_keys, size_t 
         if (have >= h->max_pending) { flush_pending(h); have = 0; }
         const size_t len = std::min(n - off, h->max_pending - have);
         ensure_pending(h, have + len);
-        ZB_CUDA(cudaMemcpyAsync(h->pending.get() + have, d_keys + off, len * 8, cudaMemcpyDeviceToDevice, c->stream));
+        ZB_CUDA(dev_copy(c, h->pending.get() + have, d_keys + off, len * 8));
         const unsigned long long nc = have + len;
         c->h_scalars[8] = nc;
         ZB_CUDA(cudaMemcpyAsync(h->d_count.get(), c->h_scalars + 8, 8, cudaMemcpyHostToDevice, c->stream));
@@ -579,8 +648,8 @@ int zb_set_from_device(int device, const uint64_t* d_kmers, const uint32_t* d_co
     Ctx* c = ctx_for(device);
     zb_set* s = new_set(c, n);
     if (n) {
-        ZB_CUDA(cudaMemcpyAsync(s->k.get(), d_kmers, n * 8, cudaMemcpyDeviceToDevice, c->stream));
-        if (d_counts) ZB_CUDA(cudaMemcpyAsync(s->cnt.get(), d_counts, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+        ZB_CUDA(dev_copy(c, s->k.get(), d_kmers, n * 8));
+        if (d_counts) ZB_CUDA(dev_copy(c, s->cnt.get(), d_counts, n * 4));
         else fill_u32(c, s->cnt.get(), n, 1u);
         ZB_CUDA(cudaStreamSynchronize(c->stream));
     }
@@ -603,8 +672,8 @@ int zb_set_slice(const zb_set* s, size_t begin, size_t end, zb_set** out) {
     ZB_CUDA(cudaSetDevice(c->device));
     zb_set* r = new_set(c, end - begin);
     if (end > begin) {
-        ZB_CUDA(cudaMemcpyAsync(r->k.get(), s->k.get() + begin, (end - begin) * 8, cudaMemcpyDeviceToDevice, c->stream));
-        ZB_CUDA(cudaMemcpyAsync(r->cnt.get(), s->cnt.get() + begin, (end - begin) * 4, cudaMemcpyDeviceToDevice, c->stream));
+        ZB_CUDA(dev_copy(c, r->k.get(), s->k.get() + begin, (end - begin) * 8));
+        ZB_CUDA(dev_copy(c, r->cnt.get(), s->cnt.get() + begin, (end - begin) * 4));
         ZB_CUDA(cudaStreamSynchronize(c->stream));
     }
     *out = r;
@@ -622,8 +691,8 @@ int zb_set_fetch(const zb_set* s, uint64_t* kmers, uint32_t* counts) {
     if (!s) ZB_FAIL(ZB_E_ARG, "null set");
     Ctx* c = s->c;
     ZB_CUDA(cudaSetDevice(c->device));
-    if (s->n && kmers) ZB_CUDA(cudaMemcpyAsync(kmers, s->k.get(), s->n * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (s->n && counts) ZB_CUDA(cudaMemcpyAsync(counts, s->cnt.get(), s->n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (s->n && kmers) copy_chunked(c, kmers, s->k.get(), s->n * 8, cudaMemcpyDeviceToHost);
+    if (s->n && counts) copy_chunked(c, counts, s->cnt.get(), s->n * 4, cudaMemcpyDeviceToHost);
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     ZB_CATCH
 }
@@ -679,9 +748,8 @@ int zb_merge(int nsets, zb_set* const* sets, zb_set** out) {
     for (int i = 0; i < nsets; i++) total += sets[i]->n;
     const char* mm = getenv("ZB_MERGE");
     const bool want_tree = mm && !strcmp(mm, "tree");
-    if (nsets >= 4 && total > 0 && total < ((size_t)1 << 30) && !want_tree) {
-        // Many inputs: ONE weighted sort + count of the concatenation (segsort.cu) instead of log2(nsets) levels of
-        // merge + reduce-by-key over everything -- the inputs being sorted does not pay for 6 trips through HBM.
+    const bool want_sort = mm && !strcmp(mm, "sort");
+    if (nsets >= 3 && total > 0 && !want_tree) {
         // key range: the sets are sorted, so the largest key is the largest last element
         std::vector<uint64_t> last(nsets, 0);
         for (int i = 0; i < nsets; i++)
@@ -690,18 +758,44 @@ int zb_merge(int nsets, zb_set* const* sets, zb_set** out) {
         uint64_t maxkey = 0;
         for (int i = 0; i < nsets; i++) maxkey = std::max(maxkey, last[i]);
         const int key_bits = maxkey ? 64 - __builtin_clzll(maxkey) : 1;
+        if (!want_sort) {
+            // Many inputs: ONE pass over them, bucket by bucket of the key space in shared memory (nwaymerge.cu)
+            std::vector<const uint64_t*> ks(nsets);
+            std::vector<const uint32_t*> cs(nsets);
+            std::vector<size_t> ns(nsets);
+            for (int i = 0; i < nsets; i++) { ks[i] = sets[i]->k.get(); cs[i] = sets[i]->cnt.get(); ns[i] = sets[i]->n; }
+            zb_set* s = new zb_set();
+            s->c = c;
+            s->n = 0;
+            bool done = false;
+            try {
+                Stage st(c, "merge_nway");
+                done = merge_nway(c, ks, cs, ns, key_bits, &s->k, &s->cnt, &s->n);
+            } catch (...) {
+                delete s;
+                throw;
+            }
+            if (done) {
+                ZB_CUDA(cudaStreamSynchronize(c->stream));
+                *out = s;
+                return ZB_OK;
+            }
+            delete s;
+        }
+        if (nsets < 4 || total >= ((size_t)1 << 30)) goto tree;
+        // Fallback (skewed key space, > 1024 inputs): ONE weighted sort + count of the concatenation (segsort.cu)
         DBuf<uint64_t> k0(c, total), k1(c, total);
         DBuf<uint32_t> v0(c, total), v1(c, total);
         size_t off = 0;
         for (int i = 0; i < nsets; i++) {
             if (!sets[i]->n) continue;
-            ZB_CUDA(cudaMemcpyAsync(k0.get() + off, sets[i]->k.get(), sets[i]->n * 8, cudaMemcpyDeviceToDevice, c->stream));
-            ZB_CUDA(cudaMemcpyAsync(v0.get() + off, sets[i]->cnt.get(), sets[i]->n * 4, cudaMemcpyDeviceToDevice, c->stream));
+            ZB_CUDA(dev_copy(c, k0.get() + off, sets[i]->k.get(), sets[i]->n * 8));
+            ZB_CUDA(dev_copy(c, v0.get() + off, sets[i]->cnt.get(), sets[i]->n * 4));
             off += sets[i]->n;
         }
         zb_set* s = new_set(c, total);
         try {
-            Stage st(c, "merge_nway");
+            Stage st(c, "merge_sort");
             s->n = sort_count(c, k0.get(), k1.get(), v0.get(), v1.get(), total, key_bits, s->k.get(), s->cnt.get());
         } catch (...) {
             delete s;
@@ -710,6 +804,7 @@ int zb_merge(int nsets, zb_set* const* sets, zb_set** out) {
         *out = s;
         return ZB_OK;
     }
+tree:
     // pairwise tree; every level is merge-path + reduce-by-key (counts summed)
     struct Run { const uint64_t* k; const uint32_t* c; size_t n; DBuf<uint64_t> ok; DBuf<uint32_t> oc; };
     std::vector<Run> cur(nsets);
@@ -736,8 +831,8 @@ int zb_merge(int nsets, zb_set* const* sets, zb_set** out) {
     }
     zb_set* s = new_set(c, cur[0].n);
     if (cur[0].n) {
-        ZB_CUDA(cudaMemcpyAsync(s->k.get(), cur[0].k, cur[0].n * 8, cudaMemcpyDeviceToDevice, c->stream));
-        ZB_CUDA(cudaMemcpyAsync(s->cnt.get(), cur[0].c, cur[0].n * 4, cudaMemcpyDeviceToDevice, c->stream));
+        ZB_CUDA(dev_copy(c, s->k.get(), cur[0].k, cur[0].n * 8));
+        ZB_CUDA(dev_copy(c, s->cnt.get(), cur[0].c, cur[0].n * 4));
     }
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     *out = s;
@@ -855,7 +950,7 @@ void pairs_abc_host(Ctx* c, const std::vector<SetRef>& refs, const uint32_t* I, 
         const size_t np = p1 - p0;
         DBuf<uint64_t> d_abc(c, 3 * np + np + 1);
         DBuf<uint32_t> d_ij(c, 2 * np);
-        ZB_CUDA(cudaMemsetAsync(d_abc.get(), 0, 3 * np * 8, c->stream));
+        ZB_CUDA(dev_memset(c, d_abc.get(), 0, 3 * np * 8));
         ZB_CUDA(cudaMemcpyAsync(d_abc.get() + 3 * np, tstart.data(), (np + 1) * 8, cudaMemcpyHostToDevice, c->stream));
         ZB_CUDA(cudaMemcpyAsync(d_ij.get(), I + p0, np * 4, cudaMemcpyHostToDevice, c->stream));
         ZB_CUDA(cudaMemcpyAsync(d_ij.get() + np, J + p0, np * 4, cudaMemcpyHostToDevice, c->stream));
@@ -894,8 +989,8 @@ int zb_dbg_sort_u64(int device, uint64_t* keys, uint32_t* vals, size_t n, int ke
     float total_ms = 0;
     if (iters < 1) iters = 1;
     for (int it = 0; it < iters; it++) {
-        ZB_CUDA(cudaMemcpyAsync(a.get(), src.get(), n * 8, cudaMemcpyDeviceToDevice, c->stream));
-        if (vals) ZB_CUDA(cudaMemcpyAsync(va.get(), vsrc.get(), n * 4, cudaMemcpyDeviceToDevice, c->stream));
+        ZB_CUDA(dev_copy(c, a.get(), src.get(), n * 8));
+        if (vals) ZB_CUDA(dev_copy(c, va.get(), vsrc.get(), n * 4));
         ZB_CUDA(cudaEventRecord(e0, c->stream));
         which = radix_sort(c, a.get(), b.get(), vals ? va.get() : nullptr, vals ? vb.get() : nullptr, n, key_bits);
         ZB_CUDA(cudaEventRecord(e1, c->stream));
@@ -936,8 +1031,8 @@ int zb_dbg_sort_count(int device, const uint64_t* keys, const uint32_t* weights,
     if (iters < 1) iters = 1;
     try {
         for (int it = 0; it < iters; it++) {
-            ZB_CUDA(cudaMemcpyAsync(a.get(), src.get(), n * 8, cudaMemcpyDeviceToDevice, c->stream));
-            if (weights) ZB_CUDA(cudaMemcpyAsync(va.get(), vsrc.get(), n * 4, cudaMemcpyDeviceToDevice, c->stream));
+            ZB_CUDA(dev_copy(c, a.get(), src.get(), n * 8));
+            if (weights) ZB_CUDA(dev_copy(c, va.get(), vsrc.get(), n * 4));
             ZB_CUDA(cudaEventRecord(e0, c->stream));
             nd = sort_count(c, a.get(), b.get(), weights ? va.get() : nullptr, weights ? vb.get() : nullptr, n, key_bits,
                             ok.get(), oc.get(), mode == 2);
@@ -985,11 +1080,11 @@ int zb_dbg_extract(int device, int k, const uint8_t* codes, size_t n, uint64_t* 
     DBuf<uint8_t> cd(c, 32 + padded);
     DBuf<uint64_t> out(c, padded);
     DBuf<unsigned long long> cnt(c, 1);
-    ZB_CUDA(cudaMemsetAsync(cd.get(), 4, 32 + padded, c->stream));
-    ZB_CUDA(cudaMemsetAsync(cnt.get(), 0, 8, c->stream));
+    ZB_CUDA(dev_memset(c, cd.get(), 4, 32 + padded));
+    ZB_CUDA(dev_memset(c, cnt.get(), 0, 8));
     if (n) ZB_CUDA(cudaMemcpyAsync(cd.get() + 32, codes, n, cudaMemcpyHostToDevice, c->stream));
     extract_canonical(c, k, cd.get() + 32, n, out.get(), cnt.get());
-    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, cnt.get(), 8, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(read_back(c, cnt.get(), 8));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     *n_keys = (size_t)c->h_scalars[0];
     if (keys && *n_keys) ZB_CUDA(cudaMemcpy(keys, out.get(), *n_keys * 8, cudaMemcpyDeviceToHost));

@@ -294,14 +294,14 @@ static size_t encode_dev(Ctx* c, const T* d_vals, size_t n, bool delta, uint64_t
     DBuf<uint64_t> woff(c, (size_t)tiles + 2);
     uint64_t* total = woff.get() + tiles;
     unsigned int* err = reinterpret_cast<unsigned int*>(woff.get() + tiles + 1);
-    ZB_CUDA(cudaMemsetAsync(total, 0, 16, c->stream));
+    ZB_CUDA(dev_memset(c, total, 0, 16));
     enc_tile_kernel<T><<<tiles, EN_THREADS, 0, c->stream>>>(d_vals, n, delta ? 1 : 0, info.get(), err);
     ZB_LAUNCH_CHECK(c);
     enc_scan_kernel<<<1, 1024, 0, c->stream>>>(info.get(), tiles, entry.get(), woff.get(), total);
     ZB_LAUNCH_CHECK(c);
     enc_emit_kernel<T><<<tiles, EN_THREADS, 0, c->stream>>>(d_vals, n, delta ? 1 : 0, entry.get(), woff.get(), d_words, err);
     ZB_LAUNCH_CHECK(c);
-    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, total, 16, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(read_back(c, total, 16));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     if (reinterpret_cast<uint32_t*>(c->h_scalars + 1)[0] != 0)
         ZB_FAIL(ZB_E_RANGE, "codec64: value or k-mer gap needs more than 60 bits (reference: IndexError, codec64.py:93-99)");
@@ -326,12 +326,12 @@ static void decode_plan(Ctx* c, const uint64_t* d_words, size_t nw, DecodePlan* 
     p->soff.alloc(c, p->tiles);
     uint64_t* total = p->coff.get() + p->tiles;
     unsigned int* err = reinterpret_cast<unsigned int*>(p->coff.get() + p->tiles + 1);
-    ZB_CUDA(cudaMemsetAsync(total, 0, 16, c->stream));
+    ZB_CUDA(dev_memset(c, total, 0, 16));
     dec_tile_kernel<<<p->tiles, DE_THREADS, 0, c->stream>>>(d_words, nw, p->tcnt.get(), p->tsum.get(), err);
     ZB_LAUNCH_CHECK(c);
     dec_scan_kernel<<<1, 1024, 0, c->stream>>>(p->tcnt.get(), p->tsum.get(), p->tiles, p->coff.get(), p->soff.get(), total);
     ZB_LAUNCH_CHECK(c);
-    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, total, 16, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(read_back(c, total, 16));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     if (reinterpret_cast<uint32_t*>(c->h_scalars + 1)[0] != 0)
         ZB_FAIL(ZB_E_FORMAT, "codec64: corrupt stream (tag outside 1..6; reference: KeyError, codec64.py:128)");
@@ -344,7 +344,7 @@ static void decode_emit(Ctx* c, const uint64_t* d_words, size_t nw, bool delta, 
     unsigned int* err = reinterpret_cast<unsigned int*>(p->coff.get() + p->tiles + 1);
     dec_emit_kernel<T><<<p->tiles, DE_THREADS, 0, c->stream>>>(d_words, nw, delta ? 1 : 0, p->coff.get(), p->soff.get(), d_out, err);
     ZB_LAUNCH_CHECK(c);
-    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, err, 4, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(read_back(c, err, 4));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     if (reinterpret_cast<uint32_t*>(c->h_scalars)[0] != 0)
         ZB_FAIL(ZB_E_RANGE, "count exceeds 2^32-1 (reference: array('I') OverflowError, kmerize.py:374)");

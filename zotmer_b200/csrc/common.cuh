@@ -45,6 +45,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaMemPool_t pool = nullptr;
     uint64_t* h_scalars = nullptr;  // pinned, 64 x u64
+    uint32_t* d_h_scalars = nullptr;  // the same buffer as the device sees it
     uint64_t launches = 0;          // kernels launched through this context (bench "gpu_launches")
     // optional per-stage CUDA-event timing (zb_dbg_profile): name, start, stop
     // caching allocator state
@@ -52,6 +53,7 @@ struct Ctx {
     std::unordered_map<void*, size_t> live_blocks;
     size_t cached_bytes = 0, live_bytes = 0;
     std::mutex alloc_mu;
+    cudaEvent_t copy_ev[3] = {nullptr, nullptr, nullptr};   // bulk host <-> device copies: at most three pieces queued
     bool profile = false;
     struct StageRec { const char* name; cudaEvent_t e0, e1; };
     std::vector<StageRec> stages;
@@ -77,6 +79,16 @@ struct Stage {
 };
 
 Ctx* ctx_for(int device);
+
+// Few-byte device -> host read-back into c->h_scalars, done by a one-warp kernel that stores into the (mapped) pinned
+// buffer instead of a copy-engine transfer: a small cudaMemcpyAsync queues behind whatever bulk copies OTHER host
+// threads have in flight on the engine (bench.py's pipelined e2e: the sort + count of one step waited up to 5.7 ms
+// for the 315 MB input copy of the next step).  Synchronise the stream before reading h_scalars.
+cudaError_t read_back(Ctx* c, const void* d_src, size_t bytes);
+// Fill / device-to-device copy done by kernels on the context's stream, for the same reason: cudaMemsetAsync and
+// cudaMemcpyAsync(DeviceToDevice) may be served by a copy engine and then queue behind other threads' bulk transfers.
+cudaError_t dev_memset(Ctx* c, void* p, int value, size_t bytes);
+cudaError_t dev_copy(Ctx* c, void* dst, const void* src, size_t bytes);
 
 // Device memory comes from a per-context caching allocator (api.cu): blocks are cudaMalloc'ed once,
 // kept in a size-ordered free list and handed out again on the next request of a similar size.  All

@@ -55,6 +55,13 @@ size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1
                   uint64_t* out_k, uint32_t* out_c, bool distinct = false);
 extern int g_sort_count_mode;  // 0 = auto, 1 = always the classic full LSD sort + reduce_by_key (ZB_SORT_COUNT)
 
+// ---- nwaymerge.cu ----------------------------------------------------------------------------
+// N-way union of sorted counted sets with the counts summed, one pass over the inputs (key-range buckets merged in
+// shared memory).  merge.py:26-86, :94-163.  Allocates out_k / out_c (n_out entries).  Returns false when the
+// inputs do not suit it (> 1024 of them, key space too skewed for the buckets): the caller falls back to sort_count.
+bool merge_nway(Ctx* c, const std::vector<const uint64_t*>& ks, const std::vector<const uint32_t*>& cs,
+                const std::vector<size_t>& ns, int key_bits, DBuf<uint64_t>* out_k, DBuf<uint32_t>* out_c, size_t* n_out);
+
 // ---- setops.cu -------------------------------------------------------------------------------
 // Run-length count of a sorted key array (optionally weighted by `w`): distinct keys + counts.
 // Replaces kmerize.py:41-132 (merge with an empty left run) / KmerAccumulator2.flush :412-424.

@@ -1,0 +1,397 @@
+// nwaymerge.cu -- N-way union of sorted counted k-mer sets with the counts summed, in ONE pass over the inputs:
+// the kernel behind `zot merge` (zotmer/commands/merge.py:26-86 merge() = pairwise merge of two (x, c) streams,
+// :94-163 _kmerRadixBlockStream + mergeNinto = N-way union over key-range blocks with a heap and a dict).
+//
+// The reference cuts the key space into 4096 radix blocks and merges the inputs block by block; so does this,
+// with blocks small enough for shared memory:
+//
+//   1. the key space is cut into NB = 2^cb buckets by the top cb bits of the key, cb chosen so that ALL inputs
+//      together hold <= 4096 entries per bucket (~2000 on average).  bm_offsets_kernel finds where every bucket
+//      starts in every input (one streaming pass over the keys); bm_starts_kernel adds them up to the
+//      bucket's position in the (virtual) concatenation and takes the largest bucket.
+//   2. bm_merge_kernel: one CTA per bucket gathers the bucket's slice of every input (contiguous runs) into
+//      shared memory, inserts every key into a shared-memory hash table (one CAS; the first entry of a key is its
+//      "head", every other entry adds its count to the head's sum), orders the heads by the next 11 key bits with a
+//      shared-memory counting sort and by the whole key inside those (tiny) groups, and writes the bucket's
+//      distinct (key, count) run.  No CTA waits for another one.
+//   3. a one-CTA scan of the per-bucket head counts and a compaction kernel place the runs (as segsort.cu does).
+//
+// Algorithmic bytes: 12 B per input entry read + 12 B per output entry staged, re-read and written; the offsets
+// table is 4 B per (bucket, input).  Fallback (skewed keys whose buckets do not fit, > 1024 inputs): the caller
+// uses the weighted sort_count of the concatenation.
+#include <algorithm>
+#include <vector>
+
+#include "kernels.h"
+
+namespace zb {
+
+static constexpr int BM_THREADS = 512;
+static constexpr int BM_PER = 8;
+static constexpr int BM_CAP = BM_THREADS * BM_PER;      // entries of one bucket (all inputs together)
+static constexpr int BM_HASH = 2 * BM_CAP;              // hash slots (load <= 0.5)
+static constexpr int BM_HASH_BITS = 13;
+static constexpr int BM_MAXSETS = 1024;
+static constexpr int BM_SETS_PER = BM_MAXSETS / BM_THREADS;
+static constexpr int BM_FINE = 2048;                    // groups of the in-bucket counting sort (about one distinct key each)
+static constexpr int BM_FINE_BITS = 11;
+#define BM_EMPTY 0xffffffffu
+
+struct KCRef {
+    const uint64_t* k;
+    const uint32_t* c;
+    uint64_t n;
+};
+
+// off[b * nsets + i] = first index of input i whose key has top bits >= b   (b = 0 .. nb; row nb = sizes).
+// One streaming pass over the keys (blockIdx.y = input): element j closes every bucket between its predecessor's and
+// its own.  (A binary search per (bucket, input) -- 17 M searches over 5 GB of keys for 64 bacterial sets -- took
+// 7.9 ms: nearly every probe misses the TLB.  This reads 8 B per entry, coalesced.)  `off` is zeroed by the caller
+// (rows of empty inputs stay zero).
+__global__ void __launch_bounds__(256)
+bm_offsets_kernel(const KCRef* __restrict__ sets, int nsets, int shift, uint32_t nb, uint32_t* __restrict__ off) {
+    const int i = blockIdx.y;
+    const uint64_t n = sets[i].n;
+    const uint64_t* __restrict__ k = sets[i].k;
+    for (uint64_t j = (uint64_t)blockIdx.x * 256 + threadIdx.x; j < n; j += (uint64_t)gridDim.x * 256) {
+        const uint64_t cur = (shift < 64) ? (__ldg(k + j) >> shift) : 0ull;
+        const uint64_t prev = (shift < 64 && j > 0) ? (__ldg(k + j - 1) >> shift) : 0ull;
+        for (uint64_t b = (j > 0) ? prev + 1 : 1; b <= cur; b++) off[b * nsets + i] = (uint32_t)j;   // off[0][i] = 0 already
+        if (j == n - 1)
+            for (uint64_t b = cur + 1; b <= nb; b++) off[b * nsets + i] = (uint32_t)n;
+    }
+}
+
+// start[b] = sum over inputs of off[b][i] (position of bucket b in the virtual concatenation); one warp per bucket
+__global__ void __launch_bounds__(256)
+bm_starts_kernel(const uint32_t* __restrict__ off, int nsets, uint32_t nb, uint64_t* __restrict__ start) {
+    const uint32_t b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b > nb) return;
+    uint64_t s = 0;
+    for (int i = lane_id(); i < nsets; i += 32) s += off[(size_t)b * nsets + i];
+    s = warp_sum(s);
+    if (lane_id() == 0) start[b] = s;
+}
+
+__global__ void __launch_bounds__(256)
+bm_maxsize_kernel(const uint64_t* __restrict__ start, uint32_t nb, unsigned long long* __restrict__ maxsize) {
+    const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+    unsigned long long v = (b < nb) ? (unsigned long long)(start[b + 1] - start[b]) : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane_id() == 0 && v) atomicMax(maxsize, v);
+}
+
+// One CTA per bucket.  Shared memory: keys 32 KB + hash table 32 KB + count sums 16 KB + slice prefixes 8 KB + group
+// sizes 8 KB = 96 KB -> 2 CTAs per SM.
+// BY_SLICE: a warp copies whole slices (few inputs: a thread finds the slice of its entry by bisection instead).
+template <bool BY_SLICE>
+__global__ void __launch_bounds__(BM_THREADS, 2)
+bm_merge_kernel(const KCRef* __restrict__ sets, int nsets, const uint32_t* __restrict__ off, const uint64_t* __restrict__ start,
+                int fine_shift, uint32_t fine_mask, uint64_t* __restrict__ tmp_k, uint32_t* __restrict__ tmp_c,
+                uint32_t* __restrict__ tile_heads, unsigned int* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char bm_raw[];
+    uint64_t* sk = reinterpret_cast<uint64_t*>(bm_raw);                  // [BM_CAP] gathered keys
+    uint32_t* table = reinterpret_cast<uint32_t*>(sk + BM_CAP);          // [BM_HASH] position of a key's head
+    uint32_t* wsum = table + BM_HASH;                                    // [BM_CAP] count of an entry; sum of counts at a head
+    uint32_t* spre = wsum + BM_CAP;                                      // [BM_MAXSETS + 1] slice starts inside the bucket
+    uint32_t* soff = spre + BM_MAXSETS + 1;                              // [BM_MAXSETS] slice starts inside the inputs
+    uint32_t* hist = soff + BM_MAXSETS;                                  // [BM_FINE + 1]
+    uint64_t* hs = reinterpret_cast<uint64_t*>(table);                   // [BM_CAP] heads grouped by fine digit (after the dedupe)
+    uint32_t* hc = reinterpret_cast<uint32_t*>(sk);                      // [BM_CAP] their counts            (after the dedupe)
+    __shared__ uint32_t s_scan[BM_THREADS / 32 + 1];
+
+    const unsigned tid = threadIdx.x;
+    const uint32_t b = blockIdx.x;
+    const uint64_t s0 = start[b];
+    const int m = (int)(start[b + 1] - s0);
+    if (m == 0) {
+        if (tid == 0) tile_heads[b] = 0;
+        return;
+    }
+    {
+        const uint4 e4 = make_uint4(BM_EMPTY, BM_EMPTY, BM_EMPTY, BM_EMPTY);
+#pragma unroll
+        for (int j = 0; j < BM_HASH / 4 / BM_THREADS; j++) reinterpret_cast<uint4*>(table)[j * BM_THREADS + tid] = e4;
+#pragma unroll
+        for (int j = 0; j < BM_FINE / BM_THREADS; j++) hist[j * BM_THREADS + tid] = 0;
+    }
+    // ---- where every input's slice of this bucket starts (in the input, and inside the bucket)
+    {
+        uint32_t len[BM_SETS_PER];
+        uint32_t tot = 0;
+#pragma unroll
+        for (int u = 0; u < BM_SETS_PER; u++) {
+            const int i = (int)tid * BM_SETS_PER + u;
+            uint32_t o0 = 0, o1 = 0;
+            if (i < nsets) {
+                o0 = __ldg(off + (size_t)b * nsets + i);
+                o1 = __ldg(off + (size_t)(b + 1) * nsets + i);
+                soff[i] = o0;
+            }
+            len[u] = o1 - o0;
+            tot += len[u];
+        }
+        uint32_t all;
+        uint32_t ex = block_excl_scan<BM_THREADS, uint32_t, false>(tot, s_scan, &all);
+#pragma unroll
+        for (int u = 0; u < BM_SETS_PER; u++) {
+            const int i = (int)tid * BM_SETS_PER + u;
+            if (i < nsets) spre[i] = ex;
+            ex += len[u];
+        }
+        if (tid == 0) spre[nsets] = (uint32_t)m;
+    }
+    __syncthreads();
+
+    // ---- gather the slices: entry q of the bucket = element q - spre[i] of input i's slice
+    if (BY_SLICE) {
+        const int lane = (int)(tid & 31), warp = (int)(tid >> 5);
+        constexpr int NW = BM_THREADS / 32;
+        for (int i0 = warp; i0 < nsets; i0 += 2 * NW) {   // two slices at a time: four loads in flight per lane
+            const int i1 = i0 + NW;
+            const uint32_t a0 = spre[i0], alen = spre[i0 + 1] - a0;
+            const uint64_t* __restrict__ ak = sets[i0].k + soff[i0];
+            const uint32_t* __restrict__ ac = sets[i0].c + soff[i0];
+            uint32_t b0 = 0, blen = 0;
+            const uint64_t* __restrict__ bk = ak;
+            const uint32_t* __restrict__ bc = ac;
+            if (i1 < nsets) {
+                b0 = spre[i1];
+                blen = spre[i1 + 1] - b0;
+                bk = sets[i1].k + soff[i1];
+                bc = sets[i1].c + soff[i1];
+            }
+            const uint32_t mx = max(alen, blen);
+            for (uint32_t e = lane; e < mx; e += 32) {
+                uint64_t ka = 0, kb = 0;
+                uint32_t ca = 0, cb2 = 0;
+                if (e < alen) { ka = __ldg(ak + e); ca = __ldg(ac + e); }
+                if (e < blen) { kb = __ldg(bk + e); cb2 = __ldg(bc + e); }
+                if (e < alen) { sk[a0 + e] = ka; wsum[a0 + e] = ca; }
+                if (e < blen) { sk[b0 + e] = kb; wsum[b0 + e] = cb2; }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < BM_PER; j++) {
+            const int q = j * BM_THREADS + (int)tid;
+            if (q < m) {
+                int lo = 0, hi = nsets - 1;   // first input whose slice ends beyond q
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (spre[mid + 1] <= (uint32_t)q) lo = mid + 1; else hi = mid;
+                }
+                const uint64_t src = (uint64_t)soff[lo] + ((uint32_t)q - spre[lo]);
+                sk[q] = __ldg(sets[lo].k + src);
+                wsum[q] = __ldg(sets[lo].c + src);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- dedupe: the first entry to claim a key's slot is its head; every other entry adds its count to the head's
+    uint64_t kx[BM_PER];
+    uint32_t headbits = 0;
+#pragma unroll
+    for (int j = 0; j < BM_PER; j++) {
+        const int q = j * BM_THREADS + (int)tid;
+        kx[j] = 0;
+        if (q < m) {
+            const uint64_t x = sk[q];
+            kx[j] = x;
+            uint32_t h = (uint32_t)((x * 0x9E3779B97F4A7C15ull) >> (64 - BM_HASH_BITS));
+            while (true) {
+                const uint32_t old = atomicCAS(&table[h], BM_EMPTY, (uint32_t)q);
+                if (old == BM_EMPTY) { headbits |= 1u << j; break; }
+                if (sk[old] == x) {
+                    const uint32_t wt = wsum[q];   // nobody else touches the slot of an entry that is not a head
+                    const uint32_t before = atomicAdd(&wsum[old], wt);
+                    if (before + wt < before) atomicExch(err, 1u);
+                    break;
+                }
+                h = (h + 1) & (BM_HASH - 1);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- heads: counting sort by the next key bits (rank inside a group = arrival order, fixed up below)
+    uint32_t rd[BM_PER], wx[BM_PER];
+#pragma unroll
+    for (int j = 0; j < BM_PER; j++) {
+        if ((headbits >> j) & 1u) {
+            const uint32_t d = (uint32_t)(kx[j] >> fine_shift) & fine_mask;
+            rd[j] = atomicAdd(&hist[d], 1u) | (d << 16);
+            wx[j] = wsum[j * BM_THREADS + tid];
+        }
+    }
+    __syncthreads();
+    {   // exclusive scan of the group sizes
+        constexpr int GP = BM_FINE / BM_THREADS;
+        uint32_t v[GP];
+        uint32_t t = 0;
+#pragma unroll
+        for (int u = 0; u < GP; u++) { v[u] = hist[tid * GP + u]; t += v[u]; }
+        uint32_t all;
+        uint32_t ex = block_excl_scan<BM_THREADS, uint32_t, false>(t, s_scan, &all);
+#pragma unroll
+        for (int u = 0; u < GP; u++) { hist[tid * GP + u] = ex; ex += v[u]; }
+        if (tid == 0) { hist[BM_FINE] = all; tile_heads[b] = all; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < BM_PER; j++) {
+        if ((headbits >> j) & 1u) {
+            const uint32_t p = hist[rd[j] >> 16] + (rd[j] & 0xffffu);
+            hs[p] = kx[j];
+            hc[p] = wx[j];
+        }
+    }
+    __syncthreads();
+
+    // ---- every head ranks itself inside its group (one or two keys) and writes (key, count)
+    const int H = (int)hist[BM_FINE];
+    for (int p = (int)tid; p < H; p += BM_THREADS) {
+        const uint64_t x = hs[p];
+        const uint32_t d = (uint32_t)(x >> fine_shift) & fine_mask;
+        const int g0 = (int)hist[d], g1 = (int)hist[d + 1];
+        int r = 0;
+        if (g1 - g0 > 1)
+            for (int p2 = g0; p2 < g1; p2++) r += (hs[p2] < x) ? 1 : 0;
+        tmp_k[s0 + g0 + r] = x;
+        tmp_c[s0 + g0 + r] = hc[p];
+    }
+}
+
+__global__ void __launch_bounds__(1024) bm_scan_kernel(const uint32_t* __restrict__ tile_heads, uint32_t tiles,
+                                                       uint64_t* __restrict__ tile_off, uint64_t* __restrict__ totals) {
+    __shared__ uint64_t sm[1024 / 32 + 1];
+    uint64_t carry = 0;
+    for (uint32_t b0 = 0; b0 < tiles; b0 += 1024) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint64_t v = (i < tiles) ? tile_heads[i] : 0;
+        uint64_t tot;
+        const uint64_t ex = block_excl_scan<1024, uint64_t>(v, sm, &tot);
+        if (i < tiles) tile_off[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) totals[0] = carry;
+}
+
+// 8 buckets per CTA, one warp each (a bucket's run is ~1000 entries)
+__global__ void __launch_bounds__(256)
+bm_compact_kernel(const uint64_t* __restrict__ tmp_k, const uint32_t* __restrict__ tmp_c, const uint32_t* __restrict__ tile_heads,
+                  const uint64_t* __restrict__ start, const uint64_t* __restrict__ tile_off, uint32_t nb,
+                  uint64_t* __restrict__ out_k, uint32_t* __restrict__ out_c) {
+    const uint32_t b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= nb) return;
+    const uint32_t H = tile_heads[b];
+    const uint64_t src = start[b], dst = tile_off[b];
+    for (uint32_t i = lane_id(); i < H; i += 32) {
+        out_k[dst + i] = tmp_k[src + i];
+        out_c[dst + i] = tmp_c[src + i];
+    }
+}
+
+bool merge_nway(Ctx* c, const std::vector<const uint64_t*>& ks, const std::vector<const uint32_t*>& cs,
+                const std::vector<size_t>& ns, int key_bits, DBuf<uint64_t>* out_k, DBuf<uint32_t>* out_c, size_t* n_out) {
+    const int nsets = (int)ks.size();
+    if (nsets < 1 || nsets > BM_MAXSETS) return false;
+    size_t total = 0;
+    for (int i = 0; i < nsets; i++) {
+        if (ns[i] >= ((size_t)1 << 32)) return false;
+        total += ns[i];
+    }
+    if (total == 0) { *n_out = 0; return true; }
+    if (key_bits < 1) key_bits = 1;
+    if (key_bits > 64) key_bits = 64;
+
+    std::vector<KCRef> refs(nsets);
+    for (int i = 0; i < nsets; i++) refs[i] = KCRef{ks[i], cs[i], (uint64_t)ns[i]};
+    DBuf<KCRef> d_refs(c, nsets);
+    ZB_CUDA(cudaMemcpyAsync(d_refs.get(), refs.data(), nsets * sizeof(KCRef), cudaMemcpyHostToDevice, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));   // `refs` is pageable host memory
+
+    // buckets: at most 2/3 of the capacity on average; more bits when the largest one does not fit
+    int cb = 0;
+    while (cb < key_bits && (total >> cb) > (size_t)BM_CAP * 2 / 3) cb++;
+    DBuf<uint32_t> off;
+    DBuf<uint64_t> start;
+    uint32_t nb = 0;
+    for (int attempt = 0;; attempt++) {
+        if (cb > 30 || ((size_t)1 << cb) * (size_t)nsets > ((size_t)1 << 28)) return false;
+        nb = 1u << cb;
+        const size_t noff = (size_t)(nb + 1) * nsets;
+        off.alloc(c, noff);
+        start.alloc(c, (size_t)nb + 4);
+        unsigned long long* d_max = reinterpret_cast<unsigned long long*>(start.get() + nb + 2);
+        ZB_CUDA(dev_memset(c, d_max, 0, 8));
+        {
+            Stage st(c, "merge_offsets");
+            ZB_CUDA(dev_memset(c, off.get(), 0, noff * 4));
+            size_t nmax = 0;
+            for (int i = 0; i < nsets; i++) nmax = std::max(nmax, ns[i]);
+            const dim3 grid((unsigned)std::min<size_t>(div_up(nmax, 256 * 8), 65535), (unsigned)nsets);
+            bm_offsets_kernel<<<grid, 256, 0, c->stream>>>(d_refs.get(), nsets, key_bits - cb, nb, off.get());
+            ZB_LAUNCH_CHECK(c);
+            bm_starts_kernel<<<(unsigned)div_up((size_t)nb + 1, 8), 256, 0, c->stream>>>(off.get(), nsets, nb, start.get());
+            ZB_LAUNCH_CHECK(c);
+            bm_maxsize_kernel<<<(unsigned)div_up(nb, 256), 256, 0, c->stream>>>(start.get(), nb, d_max);
+            ZB_LAUNCH_CHECK(c);
+        }
+        ZB_CUDA(read_back(c, d_max, 8));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+        const size_t mx = (size_t)c->h_scalars[0];
+        if (mx <= (size_t)BM_CAP) break;
+        if (attempt >= 3 || cb >= key_bits) return false;   // badly skewed key space: the caller sorts instead
+        int more = 1;
+        while (((mx >> more) > (size_t)BM_CAP / 2) && more < 8) more++;
+        cb = std::min(key_bits, cb + more);
+    }
+    const int fb = std::min(BM_FINE_BITS, key_bits - cb);
+    const int fine_shift = key_bits - cb - fb;
+    const uint32_t fine_mask = (1u << fb) - 1u;
+
+    DBuf<uint64_t> tmp_k(c, total);
+    DBuf<uint32_t> tmp_c(c, total);
+    DBuf<uint32_t> tile_heads(c, nb);
+    DBuf<uint64_t> tile_off(c, (size_t)nb + 4);
+    uint64_t* totals = tile_off.get() + nb;
+    unsigned int* err = reinterpret_cast<unsigned int*>(totals + 1);
+    ZB_CUDA(dev_memset(c, totals, 0, 16));
+    const size_t smem = (size_t)BM_CAP * 8 + (size_t)BM_HASH * 4 + (size_t)BM_CAP * 4 + (size_t)(2 * BM_MAXSETS + 1) * 4 +
+                        (size_t)(BM_FINE + 1) * 4;
+    {
+        Stage st(c, "merge_buckets");
+        if (nsets >= 16) {
+            ZB_CUDA(cudaFuncSetAttribute(bm_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            bm_merge_kernel<true><<<nb, BM_THREADS, smem, c->stream>>>(d_refs.get(), nsets, off.get(), start.get(), fine_shift,
+                                                                       fine_mask, tmp_k.get(), tmp_c.get(), tile_heads.get(), err);
+        } else {
+            ZB_CUDA(cudaFuncSetAttribute(bm_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            bm_merge_kernel<false><<<nb, BM_THREADS, smem, c->stream>>>(d_refs.get(), nsets, off.get(), start.get(), fine_shift,
+                                                                        fine_mask, tmp_k.get(), tmp_c.get(), tile_heads.get(), err);
+        }
+        ZB_LAUNCH_CHECK(c);
+        bm_scan_kernel<<<1, 1024, 0, c->stream>>>(tile_heads.get(), nb, tile_off.get(), totals);
+        ZB_LAUNCH_CHECK(c);
+    }
+    ZB_CUDA(read_back(c, totals, 16));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    const size_t nd = (size_t)c->h_scalars[0];
+    if (reinterpret_cast<uint32_t*>(c->h_scalars + 1)[0] != 0)
+        ZB_FAIL(ZB_E_RANGE, "k-mer count exceeds 2^32-1 (reference: array('I') OverflowError, kmerize.py:374)");
+    out_k->alloc(c, nd);
+    out_c->alloc(c, nd);
+    {
+        Stage st(c, "merge_compact");
+        bm_compact_kernel<<<(unsigned)div_up(nb, 8), 256, 0, c->stream>>>(tmp_k.get(), tmp_c.get(), tile_heads.get(), start.get(),
+                                                                         tile_off.get(), nb, out_k->get(), out_c->get());
+        ZB_LAUNCH_CHECK(c);
+    }
+    *n_out = nd;
+    return true;
+}
+
+}  // namespace zb

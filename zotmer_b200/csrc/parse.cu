@@ -290,14 +290,14 @@ void parse_fastq(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n
     uint64_t* line0 = st.get();
     uint64_t* out0 = st.get() + tiles;
     unsigned long long* scalars = reinterpret_cast<unsigned long long*>(st.get() + 2 * (size_t)tiles);   // [0] newlines [1] codes
-    ZB_CUDA(cudaMemsetAsync(scalars, 0, 16, c->stream));
+    ZB_CUDA(dev_memset(c, scalars, 0, 16));
     fq_count_kernel<<<tiles, PA_THREADS, 0, c->stream>>>(raw, n, info.get());
     ZB_LAUNCH_CHECK(c);
     fq_scan_kernel<<<1, 1024, 0, c->stream>>>(info.get(), tiles, line0, out0, scalars);
     ZB_LAUNCH_CHECK(c);
     fastq_kernel<<<tiles, PA_THREADS, 0, c->stream>>>(raw, n, scalars, codes, line0, out0, scalars + 1);
     ZB_LAUNCH_CHECK(c);
-    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, scalars, 16, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(read_back(c, scalars, 16));
     uint8_t last = 0;
     ZB_CUDA(cudaMemcpyAsync(&last, raw + n - 1, 1, cudaMemcpyDeviceToHost, c->stream));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
@@ -498,7 +498,7 @@ void parse_fasta(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n
     if (n == 0) return;
     const uint32_t tiles = (uint32_t)div_up(n, PA_TILE);
     DBuf<uint64_t> st(c, (size_t)tiles * 2 + 4);
-    ZB_CUDA(cudaMemsetAsync(st.get(), 0, ((size_t)tiles * 2 + 4) * 8, c->stream));
+    ZB_CUDA(dev_memset(c, st.get(), 0, ((size_t)tiles * 2 + 4) * 8));
     uint64_t* st_out = st.get();
     uint32_t* st_state = reinterpret_cast<uint32_t*>(st.get() + tiles);
     uint64_t* total = st.get() + 2 * (size_t)tiles;
@@ -506,7 +506,7 @@ void parse_fasta(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n
     uint32_t* ticket = reinterpret_cast<uint32_t*>(st.get() + 2 * (size_t)tiles + 2);
     fasta_kernel<<<tiles, PA_THREADS, 0, c->stream>>>(raw, n, codes, st_state, st_out, ticket, total, nrec);
     ZB_LAUNCH_CHECK(c);
-    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, total, 16, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(read_back(c, total, 16));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     *n_codes = (size_t)c->h_scalars[0];
     *n_records = c->h_scalars[1];

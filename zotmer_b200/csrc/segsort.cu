@@ -363,7 +363,7 @@ size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1
     DBuf<uint64_t> tile_off(c, (size_t)tiles + 4);
     uint64_t* totals = tile_off.get() + tiles;                                       // [0] distinct, [1] big count
     unsigned int* err = reinterpret_cast<unsigned int*>(totals + 2);
-    ZB_CUDA(cudaMemsetAsync(totals, 0, 32, c->stream));
+    ZB_CUDA(dev_memset(c, totals, 0, 32));
     const int mode = !weighted ? 0 : (distinct ? 2 : 1);
     const size_t smem = (size_t)SS_PADDED * 8 + (mode == 2 ? 0 : (size_t)SS_HASH * 4) + 2 * (SS_LOADED / 32) * 4 +
                         SS_THREADS * 4 + (mode == 1 ? (size_t)SS_PADDED * 4 + (size_t)SS_LOADED * 4 : 0);
@@ -389,7 +389,7 @@ size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1
         segcompact_kernel<<<tiles, 256, 0, c->stream>>>(tmp_k.get(), tmp_c.get(), tile_heads.get(), tile_off.get(), out_k, out_c);
         ZB_LAUNCH_CHECK(c);
     }
-    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, totals, 32, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(read_back(c, totals, 32));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     size_t n_out = (size_t)c->h_scalars[0];
     const size_t nbig = (size_t)c->h_scalars[1];
@@ -435,8 +435,8 @@ size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1
     DBuf<uint32_t> mc(c, n_out + nbd);
     merge_pairs(c, out_k, out_c, n_out, bk.get(), bc.get(), nbd, mk.get(), mc.get());
     n_out += nbd;
-    ZB_CUDA(cudaMemcpyAsync(out_k, mk.get(), n_out * 8, cudaMemcpyDeviceToDevice, c->stream));
-    ZB_CUDA(cudaMemcpyAsync(out_c, mc.get(), n_out * 4, cudaMemcpyDeviceToDevice, c->stream));
+    ZB_CUDA(dev_copy(c, out_k, mk.get(), n_out * 8));
+    ZB_CUDA(dev_copy(c, out_c, mc.get(), n_out * 4));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     return n_out;
 }

@@ -144,7 +144,7 @@ size_t reduce_by_key(Ctx* c, const uint64_t* keys, const uint32_t* w, size_t n, 
     const uint32_t tiles = (uint32_t)div_up(n, ST_BIG);
     DBuf<uint64_t> status(c, (size_t)tiles * 2 + 4);
     DBuf<uint64_t> start(c, n);
-    ZB_CUDA(cudaMemsetAsync(status.get(), 0, ((size_t)tiles * 2 + 4) * 8, c->stream));
+    ZB_CUDA(dev_memset(c, status.get(), 0, ((size_t)tiles * 2 + 4) * 8));
     uint64_t* st_heads = status.get();
     uint64_t* st_wsum = status.get() + tiles;
     uint64_t* totals = status.get() + 2 * (size_t)tiles;      // [0]=heads [1]=weight
@@ -155,12 +155,12 @@ size_t reduce_by_key(Ctx* c, const uint64_t* keys, const uint32_t* w, size_t n, 
     else
         rbk_kernel<false><<<tiles, ST_THREADS, 0, c->stream>>>(keys, w, n, out_k, start.get(), st_heads, st_wsum, ticket, totals);
     ZB_LAUNCH_CHECK(c);
-    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, totals, 16, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(read_back(c, totals, 16));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     const uint64_t n_out = c->h_scalars[0], total = c->h_scalars[1];
     rbk_finish_kernel<<<(unsigned)div_up(n_out, 256), 256, 0, c->stream>>>(start.get(), n_out, total, out_c, err);
     ZB_LAUNCH_CHECK(c);
-    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, err, 4, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(read_back(c, err, 4));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     if (*reinterpret_cast<uint32_t*>(c->h_scalars) != 0)
         ZB_FAIL(ZB_E_RANGE, "k-mer count exceeds 2^32-1 (reference: array('I') OverflowError, kmerize.py:374)");
@@ -345,11 +345,11 @@ size_t mirror_keys(Ctx* c, int k, const uint64_t* ck, uint32_t* cc, size_t n, ui
         return n;
     }
     DBuf<unsigned long long> ctr(c, 2);
-    ZB_CUDA(cudaMemsetAsync(ctr.get(), 0, 16, c->stream));
+    ZB_CUDA(dev_memset(c, ctr.get(), 0, 16));
     mirror_kernel<<<(unsigned)div_up(n, 256), 256, 0, c->stream>>>(k, ck, cc, n, rk, rcnt, ctr.get(),
                                                                  reinterpret_cast<unsigned int*>(ctr.get() + 1));
     ZB_LAUNCH_CHECK(c);
-    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, ctr.get(), 16, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(read_back(c, ctr.get(), 16));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     if (c->h_scalars[1] != 0) ZB_FAIL(ZB_E_RANGE, "palindromic k-mer count exceeds 2^32-1");
     return (size_t)c->h_scalars[0];
@@ -493,12 +493,12 @@ static size_t run_compact(Ctx* c, Op op, const uint64_t* k, const uint32_t* cnt,
     if (n == 0) return 0;
     const uint32_t tiles = (uint32_t)div_up(n, ST_BIG);
     DBuf<uint64_t> status(c, (size_t)tiles + 2);
-    ZB_CUDA(cudaMemsetAsync(status.get(), 0, ((size_t)tiles + 2) * 8, c->stream));
+    ZB_CUDA(dev_memset(c, status.get(), 0, ((size_t)tiles + 2) * 8));
     uint64_t* total = status.get() + tiles;
     uint32_t* ticket = reinterpret_cast<uint32_t*>(status.get() + tiles + 1);
     compact_kernel<Op, HAS_CNT><<<tiles, ST_THREADS, 0, c->stream>>>(op, k, cnt, n, ok, oc, status.get(), ticket, total);
     ZB_LAUNCH_CHECK(c);
-    ZB_CUDA(cudaMemcpyAsync(c->h_scalars, total, 8, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(read_back(c, total, 8));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     return (size_t)c->h_scalars[0];
 }
@@ -591,9 +591,9 @@ void set_stats(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, uint64_
         DBuf<unsigned long long> d(c, 8 + 2 * HBINS + 1);
         DBuf<uint64_t> oidx(c, ovf_cap);
         DBuf<uint32_t> ocnt(c, ovf_cap);
-        ZB_CUDA(cudaMemsetAsync(d.get(), 0, (8 + HBINS) * 8, c->stream));
-        ZB_CUDA(cudaMemsetAsync(d.get() + 8 + HBINS, 0xff, HBINS * 8, c->stream));
-        ZB_CUDA(cudaMemsetAsync(d.get() + 8 + 2 * HBINS, 0, 8, c->stream));
+        ZB_CUDA(dev_memset(c, d.get(), 0, (8 + HBINS) * 8));
+        ZB_CUDA(dev_memset(c, d.get() + 8 + HBINS, 0xff, HBINS * 8));
+        ZB_CUDA(dev_memset(c, d.get() + 8 + 2 * HBINS, 0, 8));
         int blocks = (int)std::min<size_t>((size_t)c->sm_count * 8, div_up(n, 256 * 16));
         stats_kernel<<<blocks, 256, 0, c->stream>>>(k, cnt, n, d.get(), d.get() + 8, d.get() + 8 + HBINS,
                                                     d.get() + 8 + 2 * HBINS, oidx.get(), ocnt.get(), ovf_cap);

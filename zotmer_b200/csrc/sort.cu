@@ -352,8 +352,8 @@ static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uin
     DBuf<uint32_t> ghist(c, (size_t)plan.passes * BINS);
     DBuf<uint32_t> status(c, (size_t)tiles * BINS);
     DBuf<uint32_t> ticket(c, MAX_PASSES);
-    ZB_CUDA(cudaMemsetAsync(ghist.get(), 0, (size_t)plan.passes * BINS * 4, c->stream));
-    ZB_CUDA(cudaMemsetAsync(ticket.get(), 0, MAX_PASSES * 4, c->stream));
+    ZB_CUDA(dev_memset(c, ghist.get(), 0, (size_t)plan.passes * BINS * 4));
+    ZB_CUDA(dev_memset(c, ticket.get(), 0, MAX_PASSES * 4));
 
     {
         Stage st_h(c, "sort_hist");
@@ -376,7 +376,7 @@ static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uin
     uint32_t* vb[2] = {v0, v1};
     int cur = 0;
     for (int p = 0; p < plan.passes; p++) {
-        ZB_CUDA(cudaMemsetAsync(status.get(), 0, (size_t)tiles * BINS * 4, c->stream));
+        ZB_CUDA(dev_memset(c, status.get(), 0, (size_t)tiles * BINS * 4));
         Stage st_p(c, vals ? "sort_pass_pairs" : "sort_pass_keys");
         // the first pass has no earlier order to keep: unstable ranking (keys only, or when the caller allows it)
         const bool stable = !(p == 0 && (!vals || !stable_first)) || g_sort_cfg == 2;
