@@ -73,18 +73,19 @@ def test_config1_properties(nat, config1):
     assert [int(v) for v in bc] == [int(v) for v in st["acgt_weighted"]]
 
 
-def test_config1_both_sort_count_paths_agree(nat, config1, monkeypatch):
+def test_config1_all_sort_count_paths_agree(nat, config1, monkeypatch):
     ks, cs = config1["set"].fetch()
-    monkeypatch.setenv("ZB_SORT_COUNT", "1")       # classic: full LSD sort + reduce-by-key
-    km = nat.Kmerizer(K)
-    km.feed(config1["fq"], False)
-    s2, _ = km.finish()
-    km.close()
+    for route in ("1", "2"):   # classic: full LSD sort + reduce-by-key; segment route (default = bucket route)
+        monkeypatch.setenv("ZB_SORT_COUNT", route)
+        km = nat.Kmerizer(K)
+        km.feed(config1["fq"], False)
+        s2, _ = km.finish()
+        km.close()
+        k2, c2 = s2.fetch()
+        s2.free()
+        assert np.array_equal(ks, k2) and np.array_equal(cs, c2), route
     monkeypatch.delenv("ZB_SORT_COUNT")
     nat.Kmerizer(K).close()                        # re-reads the environment: back to the default path
-    k2, c2 = s2.fetch()
-    s2.free()
-    assert np.array_equal(ks, k2) and np.array_equal(cs, c2)
 
 
 def test_config1_vs_c_oracle_trim_codec_merge(nat, config1):

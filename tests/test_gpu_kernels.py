@@ -111,7 +111,7 @@ def np_count(keys, weights=None):
 
 def check_sort_count(nat, keys, bits, weights=None):
     ek, ec = np_count(keys, weights)
-    for mode in (0, 1):   # segmented path and the classic full sort + RLE must agree with numpy and each other
+    for mode in (0, 3, 1):   # bucket route, segment route and the classic full sort + RLE must agree with numpy and each other
         k, c, _ = nat.dbg_sort_count(keys, weights, bits, mode)
         assert np.array_equal(k, ek), "mode %d: keys differ" % mode
         assert np.array_equal(c.astype(np.uint64), ec), "mode %d: counts differ" % mode
@@ -166,6 +166,34 @@ def test_sort_count_heavy_repeats(nat):
     check_sort_count(nat, np.full(1025, (1 << 64) - 1, np.uint64), 64)
 
 
+@pytest.mark.parametrize("dups", [1, 5])
+def test_sort_count_skewed_buckets(nat, dups):
+    """bucket route: key-range buckets of 2x, 5x, 25x and 75x the average size (done in 2..16 rounds inside the kernel,
+    the last one handed to the segment route), keys only and distinct keys with payload"""
+    rng = np.random.default_rng(90 + dups)
+    n = 300000
+    bits = 50
+    parts = [rng.integers(0, 2 ** bits, n * 50 // 100, dtype=np.uint64)]
+    for top, share in ((0x03, 0.30), (0x57, 0.10), (0xa1, 0.02), (0xfe, 0.008)):
+        m = int(n * share)
+        parts.append((np.uint64(top) << np.uint64(bits - 8)) | rng.integers(0, 2 ** (bits - 8), m, dtype=np.uint64))
+    base = np.unique(np.concatenate(parts))
+    keys = base[rng.integers(0, len(base), len(base) * dups)] if dups > 1 else base.copy()
+    rng.shuffle(keys)
+    check_sort_count(nat, keys, bits)
+    # distinct + payload
+    w = rng.integers(0, 2 ** 32 - 1, len(base), dtype=np.uint32)
+    perm = rng.permutation(len(base))
+    for mode in (2, 4):
+        k, c, _ = nat.dbg_sort_count(base[perm], w[perm], bits, mode)
+        assert np.array_equal(k, base) and np.array_equal(c, w)
+    # canonical-like skew at a size where the fullest buckets pass the capacity: 7/16 of the keys below 2^48
+    n2 = 2200000
+    top2 = rng.choice(4, n2, p=[7 / 16, 5 / 16, 3 / 16, 1 / 16]).astype(np.uint64)
+    keys2 = (top2 << np.uint64(48)) | rng.integers(0, 2 ** 48, n2, dtype=np.uint64)
+    check_sort_count(nat, keys2, bits)
+
+
 @pytest.mark.parametrize("n", [5, 4097, 300000])
 def test_sort_count_weighted(nat, n):
     rng = np.random.default_rng(n)
@@ -187,21 +215,22 @@ def test_sort_count_distinct_payload(nat, n):
     keys = np.unique(rng.integers(0, 2 ** 50, n, dtype=np.uint64))
     rng.shuffle(keys)
     w = rng.integers(0, 2 ** 32 - 1, len(keys), dtype=np.uint32)
-    k, c, _ = nat.dbg_sort_count(keys, w, 50, 2)
     order = np.argsort(keys)
-    assert np.array_equal(k, keys[order]) and np.array_equal(c, w[order])
-    if n >= 5000:   # a broken promise is reported, not silently mis-sorted
-        bad = keys.copy()
-        bad[len(bad) // 2] = bad[len(bad) // 2 + 1]
-        with pytest.raises(Exception):
-            nat.dbg_sort_count(bad, w, 50, 2)
+    for mode in (2, 4):   # bucket route, segment route
+        k, c, _ = nat.dbg_sort_count(keys, w, 50, mode)
+        assert np.array_equal(k, keys[order]) and np.array_equal(c, w[order])
+        if n >= 5000:   # a broken promise is reported, not silently mis-sorted
+            bad = keys.copy()
+            bad[len(bad) // 2] = bad[len(bad) // 2 + 1]
+            with pytest.raises(Exception):
+                nat.dbg_sort_count(bad, w, 50, mode)
 
 
 def test_sort_count_weight_overflow(nat):
     keys = np.full(3, 12345678901, np.uint64)
     keys = np.concatenate([keys, np.arange(5000, dtype=np.uint64) << np.uint64(20)])
     w = np.full(len(keys), 2 ** 31, np.uint32)
-    for mode in (0, 1):
+    for mode in (0, 3, 1):
         with pytest.raises(IndexError):
             nat.dbg_sort_count(keys, w, 50, mode)
 

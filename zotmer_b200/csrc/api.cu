@@ -1016,7 +1016,8 @@ int zb_dbg_sort_count(int device, const uint64_t* keys, const uint32_t* weights,
     Ctx* c = ctx_for(device);
     if (!n_out) ZB_FAIL(ZB_E_ARG, "null argument");
     const int saved = g_sort_count_mode;
-    g_sort_count_mode = (mode == 1) ? 1 : 0;
+    // mode: 0 = count (bucket route), 1 = classic, 2 = distinct + payload (bucket route), 3 / 4 = 0 / 2 on the segment route
+    g_sort_count_mode = (mode == 1) ? 1 : (mode >= 3 ? 2 : 0);
     if (const char* e = getenv("ZB_SORT_CFG")) g_sort_cfg = atoi(e);
     DBuf<uint64_t> src(c, n), a(c, n), b(c, n), ok(c, n);
     DBuf<uint32_t> vsrc, va, vb, oc(c, n);
@@ -1035,7 +1036,7 @@ int zb_dbg_sort_count(int device, const uint64_t* keys, const uint32_t* weights,
             if (weights) ZB_CUDA(dev_copy(c, va.get(), vsrc.get(), n * 4));
             ZB_CUDA(cudaEventRecord(e0, c->stream));
             nd = sort_count(c, a.get(), b.get(), weights ? va.get() : nullptr, weights ? vb.get() : nullptr, n, key_bits,
-                            ok.get(), oc.get(), mode == 2);
+                            ok.get(), oc.get(), mode == 2 || mode == 4);
             ZB_CUDA(cudaEventRecord(e1, c->stream));
             ZB_CUDA(cudaStreamSynchronize(c->stream));
             float ms = 0;

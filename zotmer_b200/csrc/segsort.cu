@@ -330,8 +330,8 @@ static size_t sort_count_classic(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v
     return reduce_by_key(c, which ? k1 : k0, v0 ? (which ? v1 : v0) : nullptr, n, out_k, out_c);
 }
 
-size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
-                  uint64_t* out_k, uint32_t* out_c, bool distinct) {
+static size_t sort_count_segsort(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
+                                 uint64_t* out_k, uint32_t* out_c, bool distinct) {
     if (n == 0) return 0;
     if (distinct && !v0) ZB_FAIL(ZB_E_ARG, "sort_count: distinct mode needs a payload");
     if (key_bits < 1) key_bits = 1;
@@ -342,7 +342,7 @@ size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1
     int P = (lg - 4 + 7) / 8;
     if (P < 1) P = 1;
     const int T = 8 * P;
-    if (g_sort_count_mode == 1 || key_bits < T + 8) return sort_count_classic(c, k0, k1, v0, v1, n, key_bits, out_k, out_c);
+    if (key_bits < T + 8) return sort_count_classic(c, k0, k1, v0, v1, n, key_bits, out_k, out_c);
     const int lowbits = key_bits - T;
     const bool weighted = (v0 != nullptr);
 
@@ -439,6 +439,416 @@ size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1
     ZB_CUDA(dev_copy(c, out_c, mc.get(), n_out * 4));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     return n_out;
+}
+
+// =============================================================================== bucket route
+// The same result with one LSD pass fewer.  LSD passes run over the top cb bits only, cb chosen so that a "bucket"
+// (the keys sharing those bits, contiguous afterwards) holds ~1000-2000 keys: 16 bits = TWO 8-bit passes for the
+// 125 M keys of one bench step, where the segment route needs 24 bits = three.  bc_bounds_kernel finds the bucket
+// boundaries by bisection; bucket_count_kernel gives every bucket to one CTA, which dedupes the bucket through a
+// shared-memory hash table (the first key of a value is its head and collects the count), orders the heads by the
+// next 11 key bits with a shared-memory counting sort and by the whole key inside those (mostly one-key) groups, and
+// writes the bucket's distinct run; scan + compaction place the runs.  A bucket that does not fit (skewed key
+// space, one value repeated thousands of times) is only listed: those keys are gathered and go through the segment
+// route above, and the two results are merged.
+static constexpr int BC_THREADS = 512;
+static constexpr int BC_PER = 8;
+static constexpr int BC_CAP = BC_THREADS * BC_PER;      // keys of one bucket
+static constexpr int BC_HASH = 2 * BC_CAP;
+static constexpr int BC_HASH_BITS = 13;
+static constexpr int BC_FINE = 2048;
+static constexpr int BC_FINE_BITS = 11;
+
+// start[b] = first index whose top bits are >= b (b = 0 .. nb); the keys are ordered by those bits
+__global__ void __launch_bounds__(256)
+bc_bounds_kernel(const uint64_t* __restrict__ keys, uint64_t n, int shift, uint32_t nb, uint64_t* __restrict__ start) {
+    const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+    if (b > nb) return;
+    uint64_t lo = 0, hi = n;
+    if (b == nb) {
+        lo = n;
+    } else if (b > 0) {
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if ((keys[mid] >> shift) < b) lo = mid + 1; else hi = mid;
+        }
+    }
+    start[b] = lo;
+}
+
+// MODE 0: count keys; MODE 2: keys are distinct and carry a u32 payload (the mirror sort of kmerize).
+// Shared memory: keys 2 x 32 KB + hash table 32 KB + group sizes 8 KB = 104 KB -> 2 CTAs per SM.
+// A bucket of up to 16 x BC_CAP keys is done in 2, 4, 8 or 16 rounds, one per value of the key bits right below the
+// bucket prefix (canonical k-mers are not spread evenly: prefixes starting with A hold 7/16 of them, with T 1/16, so
+// the fullest buckets are 1.75 x the average; real genomes are far more skewed).  A round compacts its share of the
+// bucket into shared memory and proceeds like a small bucket; only a bucket whose share of one round still does not
+// fit is left to the caller (listed in big_list).
+// Persistent: a CTA takes buckets blockIdx.x, + gridDim.x, ... and, while it works on one, the TMA engine copies
+// the keys of its next one into the other half of a double buffer (one cp.async.bulk per bucket, completion on an
+// mbarrier) -- the first version loaded a bucket with plain loads and then spent 34 % of its time waiting for them.
+template <int MODE>
+__global__ void __launch_bounds__(BC_THREADS, 2)
+bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ w, const uint64_t* __restrict__ start,
+                    uint32_t nb, int shift, int fine_shift, uint32_t fine_mask, uint64_t* __restrict__ tmp_k,
+                    uint32_t* __restrict__ tmp_c, uint32_t* __restrict__ tile_heads, unsigned long long* __restrict__ big_n,
+                    uint32_t* __restrict__ big_list, unsigned int* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char bc_raw[];
+    uint64_t* buf0 = reinterpret_cast<uint64_t*>(bc_raw);                // 2 x [BC_CAP + 2] keys of this / the next bucket
+    // slot = position of the value's head (low 16 bits) | number of keys with that value (high 16 bits)
+    uint32_t* table = reinterpret_cast<uint32_t*>(buf0 + 2 * (BC_CAP + 2));   // [BC_HASH]
+    uint32_t* hist = table + BC_HASH;                                    // [BC_FINE + 1]
+    uint64_t* hs = reinterpret_cast<uint64_t*>(table);                   // [BC_CAP] heads grouped by fine digit (after the dedupe)
+    __shared__ uint32_t s_scan[BC_THREADS / 32 + 1];
+    __shared__ uint32_t s_sub[16];
+    __shared__ uint32_t s_cnt;
+    __shared__ __align__(8) uint64_t s_bar[2];
+    constexpr bool DISTINCT = (MODE == 2);
+
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    uint32_t phases = 0;   // bit i = parity the next wait on s_bar[i] expects
+    uint32_t b = blockIdx.x;
+    uint64_t s0 = 0, mm = 0;
+    if (b < nb) { s0 = __ldg(start + b); mm = __ldg(start + b + 1) - s0; }
+    __syncthreads();
+    // keys of a bucket as the bulk copy takes them: from the 16-byte boundary at or below the first key, an even number
+    // of keys (an odd last key is fetched by a plain load)
+#define BC_SKEW(s0_) ((uint32_t)(((uintptr_t)(keys + (s0_))) >> 3) & 1u)
+#define BC_NCOPY(s0_, mm_) (((mm_) == 0 || (mm_) > (uint64_t)BC_CAP) ? 0u : ((BC_SKEW(s0_) + (uint32_t)(mm_)) & ~1u))
+    if (tid == 0 && BC_NCOPY(s0, mm)) {
+        mbar_expect_tx(&s_bar[0], BC_NCOPY(s0, mm) * 8);
+        bulk_g2s(buf0, keys + s0 - BC_SKEW(s0), BC_NCOPY(s0, mm) * 8, &s_bar[0]);
+    }
+    for (uint32_t it = 0; b < nb; b += gridDim.x, it++) {
+        const int cur = (int)(it & 1);
+        uint64_t* bufc = buf0 + cur * (BC_CAP + 2);
+        const uint32_t bn = b + gridDim.x;
+        uint64_t s0n = 0, mmn = 0;
+        if (bn < nb) { s0n = __ldg(start + bn); mmn = __ldg(start + bn + 1) - s0n; }
+        __syncthreads();   // everybody is done with the previous bucket (its keys / counts lived in the other buffer)
+        if (tid == 0 && BC_NCOPY(s0n, mmn)) {
+            uint64_t* bufn = buf0 + (cur ^ 1) * (BC_CAP + 2);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer was last written by ordinary stores
+            mbar_expect_tx(&s_bar[cur ^ 1], BC_NCOPY(s0n, mmn) * 8);
+            bulk_g2s(bufn, keys + s0n - BC_SKEW(s0n), BC_NCOPY(s0n, mmn) * 8, &s_bar[cur ^ 1]);
+        }
+        const uint32_t ncopy = BC_NCOPY(s0, mm);
+        const uint64_t* sk = bufc + BC_SKEW(s0);                             // the bucket's keys (when it fits)
+        uint32_t* hc = reinterpret_cast<uint32_t*>(bufc);                    // [BC_CAP] counts of the grouped heads (after the dedupe)
+
+        int rbits = 0;
+        bool give_up = mm > (uint64_t)BC_CAP * 16 || (mm > (uint64_t)BC_CAP && shift < 4);
+        if (mm > (uint64_t)BC_CAP && !give_up) {
+            // share of every value of the next 4 key bits; the fewest rounds whose shares all fit
+            if (tid < 16) s_sub[tid] = 0;
+            __syncthreads();
+            for (uint64_t i = tid; i < mm; i += BC_THREADS)
+                atomicAdd(&s_sub[(uint32_t)(__ldg(keys + s0 + i) >> (shift - 4)) & 15u], 1u);
+            __syncthreads();
+            for (rbits = 1; rbits <= 4; rbits++) {
+                const int per = 16 >> rbits;
+                bool fits = true;
+                for (int r = 0; r < (1 << rbits); r++) {
+                    uint32_t t = 0;
+                    for (int u = 0; u < per; u++) t += s_sub[r * per + u];
+                    fits &= t <= (uint32_t)BC_CAP;
+                }
+                if (fits) break;
+            }
+            give_up = rbits > 4;
+        }
+        if (mm == 0 || give_up) {
+            if (tid == 0) {
+                tile_heads[b] = 0;
+                if (mm) big_list[atomicAdd(big_n, 1ull)] = b;
+            }
+            s0 = s0n;
+            mm = mmn;
+            continue;
+        }
+        uint32_t out_base = 0;
+        for (int round = 0; round < (1 << rbits); round++) {
+            if (round) __syncthreads();   // the previous round is done with the shared arrays
+            if (!DISTINCT) {
+                const uint4 e4 = make_uint4(SS_EMPTY, SS_EMPTY, SS_EMPTY, SS_EMPTY);
+#pragma unroll
+                for (int j = 0; j < BC_HASH / 4 / BC_THREADS; j++) reinterpret_cast<uint4*>(table)[j * BC_THREADS + tid] = e4;
+            }
+#pragma unroll
+            for (int j = 0; j < BC_FINE / BC_THREADS; j++) hist[j * BC_THREADS + tid] = 0;
+            uint64_t kx[BC_PER];
+            uint32_t wx[BC_PER];
+            int m;
+            if (rbits == 0) {
+                m = (int)mm;
+                if (DISTINCT) {   // the payload comes by plain loads, issued before the wait for the keys
+#pragma unroll
+                    for (int j = 0; j < BC_PER; j++) {
+                        const int q = j * BC_THREADS + (int)tid;
+                        wx[j] = (q < m) ? __ldg(w + s0 + q) : 0u;
+                    }
+                }
+                if (tid == 0 && ((BC_SKEW(s0) + (uint32_t)m) & 1u)) bufc[BC_SKEW(s0) + m - 1] = __ldg(keys + s0 + m - 1);
+                if (ncopy) {
+                    mbar_wait(&s_bar[cur], (phases >> cur) & 1u);
+                    phases ^= 1u << cur;
+                }
+                __syncthreads();   // table / hist initialised, the odd last key stored
+#pragma unroll
+                for (int j = 0; j < BC_PER; j++) {
+                    const int q = j * BC_THREADS + (int)tid;
+                    kx[j] = (q < m) ? sk[q] : 0ull;
+                }
+            } else {
+                // compact this round's keys (any order) into the buffer; DISTINCT: their positions into `table` for the payload
+                sk = bufc;
+                if (tid == 0) s_cnt = 0;
+                __syncthreads();
+                const uint32_t rmask = (1u << rbits) - 1u;
+                for (uint64_t i0 = 0; i0 < mm; i0 += BC_THREADS) {
+                    const uint64_t i = i0 + tid;
+                    const uint64_t x = (i < mm) ? __ldg(keys + s0 + i) : 0ull;
+                    const bool sel = (i < mm) && (((uint32_t)(x >> (shift - rbits)) & rmask) == (uint32_t)round);
+                    const unsigned bal = __ballot_sync(0xffffffffu, sel);
+                    uint32_t base = 0;
+                    if (lane_id() == 0 && bal) base = atomicAdd(&s_cnt, (uint32_t)__popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (sel) {
+                        const uint32_t slot = base + __popc(bal & lanemask_lt());
+                        bufc[slot] = x;
+                        if (DISTINCT) table[slot] = (uint32_t)i;
+                    }
+                }
+                __syncthreads();
+                m = (int)s_cnt;
+#pragma unroll
+                for (int j = 0; j < BC_PER; j++) {
+                    const int q = j * BC_THREADS + (int)tid;
+                    kx[j] = (q < m) ? sk[q] : 0ull;
+                    if (DISTINCT) wx[j] = (q < m) ? __ldg(w + s0 + table[q]) : 0u;
+                }
+                if (DISTINCT) __syncthreads();   // `table` is about to be reused for the grouped heads
+            }
+
+            uint32_t headbits = 0;
+            if (DISTINCT) {
+#pragma unroll
+                for (int j = 0; j < BC_PER; j++)
+                    if (j * BC_THREADS + (int)tid < m) headbits |= 1u << j;
+            } else {
+                // ---- dedupe: one hash insert per key; the first key to claim a value's slot is its head
+#pragma unroll
+                for (int j = 0; j < BC_PER; j++) {
+                    const int q = j * BC_THREADS + (int)tid;
+                    if (q < m) {
+                        const uint64_t x = kx[j];
+                        uint32_t h = (uint32_t)((x * 0x9E3779B97F4A7C15ull) >> (64 - BC_HASH_BITS));
+                        while (true) {
+                            const uint32_t old = atomicCAS(&table[h], SS_EMPTY, (uint32_t)q | 0x10000u);
+                            if (old == SS_EMPTY) { headbits |= 1u << j; wx[j] = h; break; }
+                            if (sk[old & 0xffffu] == x) { atomicAdd(&table[h], 0x10000u); break; }
+                            h = (h + 1) & (BC_HASH - 1);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+
+            // ---- heads: counting sort by the next key bits (rank inside a group = arrival order, fixed up below)
+            uint32_t rd[BC_PER];
+#pragma unroll
+            for (int j = 0; j < BC_PER; j++) {
+                if ((headbits >> j) & 1u) {
+                    const uint32_t d = (uint32_t)(kx[j] >> fine_shift) & fine_mask;
+                    rd[j] = atomicAdd(&hist[d], 1u) | (d << 16);
+                    if (!DISTINCT) wx[j] = table[wx[j]] >> 16;
+                }
+            }
+            __syncthreads();
+            {   // exclusive scan of the group sizes
+                constexpr int GP = BC_FINE / BC_THREADS;
+                uint32_t v[GP];
+                uint32_t t = 0;
+#pragma unroll
+                for (int u = 0; u < GP; u++) { v[u] = hist[tid * GP + u]; t += v[u]; }
+                uint32_t all;
+                uint32_t ex = block_excl_scan<BC_THREADS, uint32_t, false>(t, s_scan, &all);
+#pragma unroll
+                for (int u = 0; u < GP; u++) { hist[tid * GP + u] = ex; ex += v[u]; }
+                if (tid == 0) hist[BC_FINE] = all;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < BC_PER; j++) {
+                if ((headbits >> j) & 1u) {
+                    const uint32_t p = hist[rd[j] >> 16] + (rd[j] & 0xffffu);
+                    hs[p] = kx[j];
+                    hc[p] = wx[j];
+                }
+            }
+            __syncthreads();
+
+            // ---- every head ranks itself inside its group and writes (key, count)
+            const int H = (int)hist[BC_FINE];
+            for (int p = (int)tid; p < H; p += BC_THREADS) {
+                const uint64_t x = hs[p];
+                const uint32_t d = (uint32_t)(x >> fine_shift) & fine_mask;
+                const int g0 = (int)hist[d], g1 = (int)hist[d + 1];
+                int r = 0;
+                if (g1 - g0 > 1) {
+                    for (int p2 = g0; p2 < g1; p2++) {
+                        const uint64_t y = hs[p2];
+                        r += (y < x) ? 1 : 0;
+                        if (DISTINCT && y == x && p2 != p) atomicExch(err, 2u);   // the caller's promise is broken
+                    }
+                }
+                tmp_k[s0 + out_base + g0 + r] = x;
+                tmp_c[s0 + out_base + g0 + r] = hc[p];
+            }
+            out_base += (uint32_t)H;
+        }
+        if (tid == 0) tile_heads[b] = out_base;
+        s0 = s0n;
+        mm = mmn;
+    }
+#undef BC_SKEW
+#undef BC_NCOPY
+}
+
+// one warp per bucket: its run of H distinct keys moves from the bucket's own offset to its final place
+__global__ void __launch_bounds__(256)
+bucket_compact_kernel(const uint64_t* __restrict__ tmp_k, const uint32_t* __restrict__ tmp_c, const uint32_t* __restrict__ tile_heads,
+                      const uint64_t* __restrict__ start, const uint64_t* __restrict__ tile_off, uint32_t nb,
+                      uint64_t* __restrict__ out_k, uint32_t* __restrict__ out_c) {
+    const uint32_t b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= nb) return;
+    const uint32_t H = tile_heads[b];
+    const uint64_t src = start[b], dst = tile_off[b];
+    for (uint32_t i = lane_id(); i < H; i += 32) {
+        out_k[dst + i] = tmp_k[src + i];
+        out_c[dst + i] = tmp_c[src + i];
+    }
+}
+
+__global__ void big_bucket_ranges_kernel(const uint32_t* __restrict__ big_list, uint64_t nbig, const uint64_t* __restrict__ start,
+                                         uint64_t* __restrict__ big_start, uint64_t* __restrict__ big_len) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbig) return;
+    const uint32_t b = big_list[i];
+    big_start[i] = start[b];
+    big_len[i] = start[b + 1] - start[b];
+}
+
+static size_t sort_count_buckets(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
+                                 uint64_t* out_k, uint32_t* out_c, bool distinct) {
+    const bool weighted = (v0 != nullptr);
+    int cb = 0;
+    while (cb < key_bits && (n >> cb) > (size_t)BC_CAP / 2) cb++;
+    const uint32_t nb = 1u << cb;
+    const int shift = key_bits - cb;
+    int which = 0;
+    if (cb > 0) {
+        Stage st(c, "sort");
+        which = radix_sort_range(c, k0, k1, v0, v1, n, shift, cb, false);
+    }
+    const uint64_t* sk = which ? k1 : k0;
+    const uint32_t* sv = weighted ? (which ? v1 : v0) : nullptr;
+    const int fb = std::min(BC_FINE_BITS, shift);
+    const int fine_shift = shift - fb;
+    const uint32_t fine_mask = (1u << fb) - 1u;
+
+    DBuf<uint64_t> start(c, (size_t)nb + 2);
+    DBuf<uint64_t> tmp_k(c, n);
+    DBuf<uint32_t> tmp_c(c, n);
+    DBuf<uint32_t> tile_heads(c, nb);
+    DBuf<uint32_t> big_list(c, nb);
+    DBuf<uint64_t> tile_off(c, (size_t)nb + 4);
+    uint64_t* totals = tile_off.get() + nb;                                          // [0] distinct, [1] big buckets
+    unsigned int* err = reinterpret_cast<unsigned int*>(totals + 2);
+    ZB_CUDA(dev_memset(c, totals, 0, 32));
+    const size_t smem = (size_t)2 * (BC_CAP + 2) * 8 + (size_t)BC_HASH * 4 + (size_t)(BC_FINE + 1) * 4;
+    const unsigned grid = (unsigned)std::min<size_t>(nb, (size_t)c->sm_count * 2);   // persistent: 2 CTAs per SM
+    {
+        Stage st(c, "segcount");
+        bc_bounds_kernel<<<(unsigned)div_up((size_t)nb + 1, 256), 256, 0, c->stream>>>(sk, n, shift, nb, start.get());
+        ZB_LAUNCH_CHECK(c);
+        unsigned long long* bign = reinterpret_cast<unsigned long long*>(totals + 1);
+        if (distinct) {
+            ZB_CUDA(cudaFuncSetAttribute(bucket_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            bucket_count_kernel<2><<<grid, BC_THREADS, smem, c->stream>>>(sk, sv, start.get(), nb, shift, fine_shift, fine_mask, tmp_k.get(),
+                                                                        tmp_c.get(), tile_heads.get(), bign, big_list.get(), err);
+        } else {
+            ZB_CUDA(cudaFuncSetAttribute(bucket_count_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            bucket_count_kernel<0><<<grid, BC_THREADS, smem, c->stream>>>(sk, nullptr, start.get(), nb, shift, fine_shift, fine_mask, tmp_k.get(),
+                                                                        tmp_c.get(), tile_heads.get(), bign, big_list.get(), err);
+        }
+        ZB_LAUNCH_CHECK(c);
+        segscan_kernel<<<1, 1024, 0, c->stream>>>(tile_heads.get(), nb, tile_off.get(), totals);
+        ZB_LAUNCH_CHECK(c);
+        bucket_compact_kernel<<<(unsigned)div_up(nb, 8), 256, 0, c->stream>>>(tmp_k.get(), tmp_c.get(), tile_heads.get(), start.get(),
+                                                                             tile_off.get(), nb, out_k, out_c);
+        ZB_LAUNCH_CHECK(c);
+    }
+    ZB_CUDA(read_back(c, totals, 32));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    size_t n_out = (size_t)c->h_scalars[0];
+    const size_t nbig = (size_t)c->h_scalars[1];
+    if (reinterpret_cast<uint32_t*>(c->h_scalars + 2)[0] == 2)
+        ZB_FAIL(ZB_E_ARG, "sort_count: keys promised to be distinct are not");
+    if (nbig == 0) return n_out;
+
+    // ---- buckets that did not fit: gather their keys, segment route, merge back
+    Stage st_big(c, "segcount_big");
+    DBuf<uint64_t> big_start(c, nbig), big_len(c, nbig);
+    big_bucket_ranges_kernel<<<(unsigned)div_up(nbig, 128), 128, 0, c->stream>>>(big_list.get(), nbig, start.get(), big_start.get(),
+                                                                               big_len.get());
+    ZB_LAUNCH_CHECK(c);
+    std::vector<uint64_t> off(nbig + 1);
+    ZB_CUDA(cudaMemcpyAsync(off.data() + 1, big_len.get(), nbig * 8, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    off[0] = 0;
+    for (size_t i = 1; i <= nbig; i++) off[i] += off[i - 1];
+    const size_t nbk = (size_t)off[nbig];
+    DBuf<uint64_t> d_off(c, nbig + 1);
+    ZB_CUDA(cudaMemcpyAsync(d_off.get(), off.data(), (nbig + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    DBuf<uint64_t> b0(c, nbk), b1(c, nbk), bk(c, nbk);
+    DBuf<uint32_t> w0, w1, bc(c, nbk);
+    if (weighted) { w0.alloc(c, nbk); w1.alloc(c, nbk); }
+    {
+        const int blocks = (int)std::min<size_t>((size_t)c->sm_count * 8, div_up(nbk, 256));
+        big_gather_kernel<<<blocks, 256, 0, c->stream>>>(sk, sv, big_start.get(), d_off.get(), nbig, nbk, b0.get(),
+                                                         weighted ? w0.get() : nullptr);
+        ZB_LAUNCH_CHECK(c);
+    }
+    ZB_CUDA(cudaStreamSynchronize(c->stream));   // `off` (pageable host memory) must stay alive until the copy is done
+    const size_t nbd = sort_count_segsort(c, b0.get(), b1.get(), weighted ? w0.get() : nullptr, weighted ? w1.get() : nullptr, nbk,
+                                          key_bits, bk.get(), bc.get(), distinct);
+    DBuf<uint64_t> mk(c, n_out + nbd);
+    DBuf<uint32_t> mc(c, n_out + nbd);
+    merge_pairs(c, out_k, out_c, n_out, bk.get(), bc.get(), nbd, mk.get(), mc.get());
+    n_out += nbd;
+    ZB_CUDA(dev_copy(c, out_k, mk.get(), n_out * 8));
+    ZB_CUDA(dev_copy(c, out_c, mc.get(), n_out * 4));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    return n_out;
+}
+
+// g_sort_count_mode (ZB_SORT_COUNT): 0 = bucket route (weighted sums: segment route), 1 = classic full sort +
+// reduce-by-key, 2 = segment route
+size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
+                  uint64_t* out_k, uint32_t* out_c, bool distinct) {
+    if (n == 0) return 0;
+    if (distinct && !v0) ZB_FAIL(ZB_E_ARG, "sort_count: distinct mode needs a payload");
+    if (key_bits < 1) key_bits = 1;
+    if (key_bits > 64) key_bits = 64;
+    if (g_sort_count_mode == 1) return sort_count_classic(c, k0, k1, v0, v1, n, key_bits, out_k, out_c);
+    const bool weighted_sum = (v0 != nullptr) && !distinct;
+    if (g_sort_count_mode == 2 || weighted_sum) return sort_count_segsort(c, k0, k1, v0, v1, n, key_bits, out_k, out_c, distinct);
+    return sort_count_buckets(c, k0, k1, v0, v1, n, key_bits, out_k, out_c, distinct);
 }
 
 }  // namespace zb
