@@ -134,9 +134,10 @@ int zb_project(const zb_set* s, int shift_bits, zb_set** out);
 int zb_pairs_abc(int nsets, zb_set* const* sets, const uint32_t* I, const uint32_t* J, size_t npairs, uint64_t* abc);
 /* The same for ALL pairs i < j -- the loop nests of commands/dist.py:145-168 and jaccard.py:148-166 (-a).
  * abc holds 3 * nsets (nsets - 1) / 2 u64, pair (i, j) at p = i (2 nsets - i - 1) / 2 + (j - i - 1).
- * The work is cut into zb_allpairs_tiles(nsets) independent tiles (pairs of blocks of 8 sets); only tiles
- * [tile_begin, tile_end) are computed (tile_end 0 = all) and every other entry of abc is 0, so that the
- * shards computed on several GPUs simply add up (the "final gather" of the distance matrix). */
+ * The work is cut into zb_allpairs_tiles(nsets) independent units (a pair of blocks of 32 sets x one of 8
+ * key-range shards of the k-mer space); only units [tile_begin, tile_end) are computed (tile_end 0 = all): abc then
+ * holds the cardinalities restricted to the k-mers of those shards and 0 for pairs outside those units, so that the
+ * parts computed on several GPUs simply add up (the "final gather" of the distance matrix). */
 int zb_allpairs_tiles(int nsets, uint64_t* n_tiles);
 int zb_allpairs_abc(int nsets, zb_set* const* sets, uint64_t tile_begin, uint64_t tile_end, uint64_t* abc);
 

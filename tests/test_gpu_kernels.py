@@ -659,6 +659,8 @@ def _rand_sets(rng, sizes, bits, share=0.5):
     ([60000, 100, 40000, 0, 0, 3, 70000, 65000, 12, 9999, 30000, 30001, 64, 63, 65, 50000, 1000], 62),
     ([5000] * 19, 20),                                 # dense small key space (20 bits: many shared keys)
     ([150000] * 5, 64),
+    ([3000] * 31 + [0, 50, 4000], 40),                 # 34 sets: two blocks of 32 (a diagonal and a cross tile)
+    ([800] * 70, 24),                                  # three blocks, dense key space
 ])
 def test_allpairs_abc(nat, sizes, bits):
     """tiled all-pairs cardinalities against the two-pointer oracle (library/dist.py:241-265) and the
@@ -673,22 +675,29 @@ def test_allpairs_abc(nat, sizes, bits):
     assert np.array_equal(abc, ref)
     for p in range(0, len(I), max(1, len(I) // 40)):
         assert tuple(int(v) for v in abc[p]) == co.split(arrs[I[p]], arrs[J[p]]), (I[p], J[p])
-    # shards over tile ranges add up to the whole matrix and do not overlap
+    # parts over ranges of work units (tile x key-range shard) add up to the whole matrix; a part is zero outside
+    # the pairs of its units' tiles, and what it holds is the pair restricted to the units' key shards
     nt = nat.allpairs_tiles(n)
-    tot = np.zeros_like(abc)
-    cuts = sorted(set([0, nt // 3, (2 * nt) // 3, nt]))
     from zotmer_b200 import multigpu
     assert nt == multigpu.n_tiles(n)
+    tot = np.zeros_like(abc)
+    cuts = sorted(set([0, 1, nt // 3, (2 * nt) // 3, nt - 1, nt]))
+    key_bits = max([int(a.max()).bit_length() for a in arrs if len(a)] + [1])
     for a, b in zip(cuts[:-1], cuts[1:]):
         part = nat.allpairs_abc(sets, a, b)
-        assert not ((part != 0) & (tot != 0)).any()
         tot += part
-        # the device's tile -> pairs map is the host's (zotmer_b200/multigpu.py tile_pairs)
         mine = np.zeros(len(abc), bool)
-        for t in range(a, b):
-            for (i, j) in multigpu.tile_pairs(n, t):
+        for u in range(a, b):
+            for (i, j) in multigpu.tile_pairs(n, u):
                 mine[multigpu.pair_index(n, i, j)] = True
-        assert np.array_equal(part[mine], abc[mine]) and not part[~mine].any()
+        assert not part[~mine].any()
+        if b - a == 1:   # one unit: check the key-shard restriction against numpy
+            sh = a % multigpu.AP_KS
+            assert key_bits >= 3 and multigpu.AP_KS == 8
+            sub = [x[(x >> np.uint64(key_bits - 3)) == np.uint64(sh)] if len(x) else x for x in arrs]
+            for (i, j) in multigpu.tile_pairs(n, a)[:50]:
+                isec = len(np.intersect1d(sub[i], sub[j], assume_unique=True))
+                assert tuple(int(v) for v in part[multigpu.pair_index(n, i, j)]) == (isec, len(sub[i]) - isec, len(sub[j]) - isec)
     assert np.array_equal(tot, abc)
 
 

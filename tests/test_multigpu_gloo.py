@@ -101,32 +101,42 @@ def test_p2p_offsets_tile_every_receive_buffer():
 
 # ------------------------------------------------------------------------------------------------
 # all-pairs distance matrix: tiling and sharding
-@pytest.mark.parametrize("nsets", [1, 2, 7, 8, 9, 16, 17, 41])
+@pytest.mark.parametrize("nsets", [1, 2, 7, 31, 32, 33, 64, 65, 130])
 def test_tiles_cover_every_pair_once(nsets):
+    """every pair belongs to exactly one tile, and to each of that tile's AP_KS key-range shards (work units)"""
     seen = {}
-    for t in range(multigpu.n_tiles(nsets)):
-        bi, bj = multigpu.tile_blocks(nsets, t)
+    assert multigpu.n_tiles(nsets) % multigpu.AP_KS == 0
+    for u in range(multigpu.n_tiles(nsets)):
+        bi, bj = multigpu.tile_blocks(nsets, u)
         assert bi <= bj
-        for (i, j) in multigpu.tile_pairs(nsets, t):
-            assert i < j < nsets and (i, j) not in seen
-            seen[(i, j)] = t
+        for (i, j) in multigpu.tile_pairs(nsets, u):
+            assert i < j < nsets
+            seen.setdefault((i, j), []).append(u)
     assert len(seen) == nsets * (nsets - 1) // 2
+    for us in seen.values():
+        assert len(us) == multigpu.AP_KS and us == list(range(us[0], us[0] + multigpu.AP_KS)) and us[0] % multigpu.AP_KS == 0
     idx = sorted(multigpu.pair_index(nsets, i, j) for (i, j) in seen)
     assert idx == list(range(len(seen)))
     for world in (1, 2, 3, 8):
         rs = multigpu.tile_ranges(nsets, world)
         assert rs[0][0] == 0 and rs[-1][1] == multigpu.n_tiles(nsets)
         assert all(rs[r][1] == rs[r + 1][0] for r in range(world - 1))
+        if nsets >= 2 and world == 8:   # even one tile spreads over 8 ranks (one key-range shard each)
+            assert all(e > b for b, e in rs)
 
 
 def _host_tiles(arrs, b, e):
-    """numpy stand-in for zotmer_b200._native.allpairs_abc(sets, b, e)"""
+    """numpy stand-in for zotmer_b200._native.allpairs_abc(sets, b, e): the cardinalities of every pair of the
+    units' tiles, restricted to the k-mers of the units' key-range shards"""
     n = len(arrs)
+    key_bits = max([int(a.max()).bit_length() for a in arrs if len(a)] + [1])
     out = np.zeros((n * (n - 1) // 2, 3), np.uint64)
-    for t in range(b, e):
-        for (i, j) in multigpu.tile_pairs(n, t):
-            a = len(np.intersect1d(arrs[i], arrs[j], assume_unique=True))
-            out[multigpu.pair_index(n, i, j)] = (a, len(arrs[i]) - a, len(arrs[j]) - a)
+    for u in range(b, e):
+        sh = u % multigpu.AP_KS
+        part = [a[np.array([multigpu.key_shard(x, key_bits) == sh for x in a], bool)] if len(a) else a for a in arrs]
+        for (i, j) in multigpu.tile_pairs(n, u):
+            a = len(np.intersect1d(part[i], part[j], assume_unique=True))
+            out[multigpu.pair_index(n, i, j)] += np.array((a, len(part[i]) - a, len(part[j]) - a), np.uint64)
     return out
 
 
@@ -138,7 +148,7 @@ def _pairs_worker(rank, world, port, ret):
     try:
         rng = np.random.default_rng(3)
         pool = rng.integers(0, 2 ** 40, 4000, dtype=np.uint64)
-        arrs = [np.unique(pool[rng.integers(0, len(pool), int(rng.integers(0, 1500)))]) for _ in range(19)]
+        arrs = [np.unique(pool[rng.integers(0, len(pool), int(rng.integers(0, 300)))]) for _ in range(37)]
         full = multigpu.allpairs_sharded(lambda b, e: _host_tiles(arrs, b, e), len(arrs), dist, rank, world)
         assert np.array_equal(full, _host_tiles(arrs, 0, multigpu.n_tiles(len(arrs))))
         ret[rank] = "ok"

@@ -20,6 +20,7 @@ for it in range(3):
     nat.dbg_profile(True)
     t0 = time.time(); abc = nat.allpairs_abc(sets); dt = time.time() - t0
     prof = nat.dbg_profile(False)
+    print("   stages (ms):", {k: round(v[0], 3) for k, v in prof.items()})
     print("allpairs: %d pairs in %.1f ms wall, kernel %.2f ms -> %.0f set-pairs/s (kernel), eq. %.1f TB/s of 8(|X|+|Y|) B/pair" % (
         npairs, dt * 1e3, prof["allpairs"][0], npairs / prof["allpairs"][0] * 1e3,
         sum(8 * (abc[:, 0] * 2 + abc[:, 1] + abc[:, 2])) / prof["allpairs"][0] / 1e9), flush=True)

@@ -3,18 +3,26 @@
 // (commands/jaccard.py:148-166 -> :31-54), where the reference walks two sorted arrays once per pair (and once
 // more per measure).
 //
-// A pair-at-a-time merge reads 8 (|X| + |Y|) bytes of HBM per pair.  Here the key space is cut into NB buckets
-// by the top bits of the key (bucket b of every set holds the same key range, so intersections never cross
-// buckets) and the sets into blocks of 8; a CTA takes one pair of blocks (64 set pairs, 28 on the diagonal) and
-// a run of 16 buckets.  Per bucket the 8 slices (~0.3 K keys each) of one block are hashed into shared memory
-// and the 8 slices of the other block are streamed past them.  A slice is fetched once per 8 partner sets, and
-// CTAs are ordered bucket-major, so at any time the resident CTAs touch the same few buckets of all sets (a few
-// MB: L2 hits).  HBM sees every set about once; the kernel is bound by shared-memory probe throughput, not by
-// HBM -- which is why its set-pairs/s can exceed the naive 8 (|X| + |Y|) B/pair HBM roofline (SURVEY.md 8d
-// allows that and asks to say so).
+// A pair-at-a-time merge reads 8 (|X| + |Y|) bytes per pair: O(N^2) trips over the sets.  Here every set is read
+// once per BLOCK of 32 partner sets:
 //
-// Skewed key spaces: if a slice does not fit its table the kernel raises a flag; the host retries with 16x more
-// buckets and finally falls back to the pair-at-a-time kernel (setops.cu pairs_abc).
+//   * the sets are cut into blocks of 32; a tile is a pair of blocks (bi <= bj): 32 sets on the diagonal (the 496
+//     pairs inside the block), 64 sets off it (the 1024 pairs across the two blocks);
+//   * the key space is cut into 2^cb buckets by the top bits of the key (bucket b of every set holds the same key
+//     range, so intersections never cross buckets), cb such that a tile's sets together hold <= 4096 keys per
+//     bucket; ap_offsets_kernel finds every bucket in every set with one streaming pass;
+//   * ap_bucket_kernel: a CTA gathers the bucket's slice of each of the tile's sets into shared memory and
+//     inserts every key into a shared-memory hash table -- the first entry of a key is its head and collects a
+//     32-bit mask per block of "which sets hold this key".  A warp then takes 32 heads, transposes the 32 x 32 bit
+//     matrix (5 shuffle steps), so that lane l holds "which of these 32 keys are in set l", and a pair's shared keys
+//     are popc(column_i & column_j): 16 (diagonal) or 32 (cross) popcounts per lane for 32 keys, accumulated per
+//     CTA in shared memory and flushed once per tile.
+//   * work units: a tile's buckets are cut into AB_KS = 8 key-range shards; units [begin, end) are what one GPU
+//     computes, and (a, b, c) of the shards of a pair simply add up -- 32 sets (one tile) still spread over 8 GPUs.
+//
+// HBM sees every set once per tile it belongs to (N / 32 times), the rest is shared-memory work.
+// Skewed key spaces (a bucket that does not fit after three attempts): pair-at-a-time merge path (setops.cu
+// pairs_abc), whole pairs attributed to the first shard of their tile.
 #include <algorithm>
 #include <vector>
 
@@ -22,273 +30,409 @@
 
 namespace zb {
 
-static constexpr int AP_S = 8;              // sets per block
-static constexpr int AP_THREADS = 256;
-static constexpr int AP_WARPS = AP_THREADS / 32;
-static constexpr int AP_SLOTS = 1024;       // hash slots per staged slice (8 tables = 64 KB -> 3 CTAs per SM)
-static constexpr int AP_CAP = 704;          // longest slice a table takes (load <= 0.69)
-static constexpr int AP_FILT = 4096;        // filter bits per slice
-static constexpr int AP_BPC = 16;           // buckets per CTA (one atomic per pair per CTA)
-static_assert(AP_WARPS == AP_S, "one warp per set of a block");
-#define AP_EMPTY 0xffffffffffffffffull
+static constexpr int AB_S = 32;               // sets per block
+static constexpr int AB_KS = 8;               // key-range shards per tile
+static constexpr int AB_THREADS = 512;
+static constexpr int AB_WARPS = AB_THREADS / 32;
+static constexpr int AB_PER = 8;
+static constexpr int AB_CAP = AB_THREADS * AB_PER;   // keys of one bucket, all sets of the tile together
+static constexpr int AB_HASH = 2 * AB_CAP;
+static constexpr int AB_HASH_BITS = 13;
+#define AB_EMPTY 0xffffffffu
 
-// boff[s][b] = first index of set s whose key >> shift is >= b   (b = 0 .. NB)
-__global__ void bucket_offsets_kernel(const SetRef* __restrict__ sets, int nsets, int shift, uint32_t NB,
-                                      uint32_t* __restrict__ boff) {
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (uint64_t)nsets * (NB + 1)) return;
-    const int s = (int)(idx / (NB + 1));
-    const uint32_t b = (uint32_t)(idx % (NB + 1));
-    const SetRef X = sets[s];
-    uint64_t lo = 0, hi = X.n;
-    if (b < NB) {
-        while (lo < hi) {
-            const uint64_t mid = (lo + hi) >> 1;
-            if ((X.k[mid] >> shift) < (uint64_t)b) lo = mid + 1; else hi = mid;
-        }
-    } else {
-        lo = X.n;
+// off[b * nsets + i] = first index of set i whose key >> shift is >= b   (b = 0 .. nb); `off` zeroed by the caller.
+// One streaming pass over the keys (blockIdx.y = set): element j closes every bucket between its predecessor's and
+// its own (a binary search per (bucket, set) misses the TLB on nearly every probe: 3.8 x slower, nwaymerge.cu).
+__global__ void __launch_bounds__(256)
+ap_offsets_kernel(const SetRef* __restrict__ sets, int nsets, int shift, uint32_t nb, uint32_t* __restrict__ off) {
+    const int i = blockIdx.y;
+    const uint64_t n = sets[i].n;
+    const uint64_t* __restrict__ k = sets[i].k;
+    for (uint64_t j = (uint64_t)blockIdx.x * 256 + threadIdx.x; j < n; j += (uint64_t)gridDim.x * 256) {
+        const uint64_t cur = (shift < 64) ? (__ldg(k + j) >> shift) : 0ull;
+        const uint64_t prev = (shift < 64 && j > 0) ? (__ldg(k + j - 1) >> shift) : 0ull;
+        for (uint64_t b = (j > 0) ? prev + 1 : 1; b <= cur; b++) off[b * nsets + i] = (uint32_t)j;
+        if (j == n - 1)
+            for (uint64_t b = cur + 1; b <= nb; b++) off[b * nsets + i] = (uint32_t)n;
     }
-    boff[idx] = (uint32_t)lo;
+}
+
+// largest number of keys one block of 32 sets holds in one bucket; one warp per (bucket, block)
+__global__ void __launch_bounds__(256)
+ap_blockmax_kernel(const uint32_t* __restrict__ off, int nsets, uint32_t nb, uint32_t nblk, unsigned int* __restrict__ mx) {
+    const uint64_t wid = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (wid >= (uint64_t)nb * nblk) return;
+    const uint32_t b = (uint32_t)(wid / nblk), blk = (uint32_t)(wid % nblk);
+    const int i = (int)(blk * AB_S + lane_id());
+    uint32_t v = 0;
+    if (i < nsets) v = off[(size_t)(b + 1) * nsets + i] - off[(size_t)b * nsets + i];
+    v = warp_sum(v);
+    if (lane_id() == 0 && v) atomicMax(mx, v);
 }
 
 // upper-triangular (diagonal included) block pair number t -> (bi, bj), bi <= bj < nblk
-__device__ __forceinline__ void tile_to_blocks(uint32_t t, uint32_t nblk, uint32_t& bi, uint32_t& bj) {
-    // row bi starts at bi * nblk - bi (bi - 1) / 2
-    double x = (2.0 * nblk + 1.0 - sqrt((2.0 * nblk + 1.0) * (2.0 * nblk + 1.0) - 8.0 * (double)t)) * 0.5;
-    uint32_t r = (uint32_t)x;
-    if (r >= nblk) r = nblk - 1;
-    while (r > 0 && (uint64_t)r * nblk - (uint64_t)r * (r - 1) / 2 > t) r--;
-    while ((uint64_t)(r + 1) * nblk - (uint64_t)(r + 1) * r / 2 <= t) r++;
-    bi = r;
-    bj = r + (t - (uint32_t)((uint64_t)r * nblk - (uint64_t)r * (r - 1) / 2));
+__host__ __device__ inline void tile_to_blocks(uint64_t t, uint64_t nblk, uint32_t& bi, uint32_t& bj) {
+    uint64_t r = 0, start = 0;
+    while (start + (nblk - r) <= t) { start += nblk - r; r++; }
+    bi = (uint32_t)r;
+    bj = (uint32_t)(r + (t - start));
 }
 
-// One CTA = one pair of blocks (bi, bj) x AP_BPC consecutive buckets.  Per bucket: warp a hashes slice a of block
-// bi into shared-memory table a; then warp w streams slice w of block bj from L2 and probes every table:
-// hits[a] counts |set (bi, a) n set (bj, w)| within the bucket.  Probes are independent of each other, so the
-// shared-memory latency is hidden by instruction-level parallelism (a merge is one long dependent chain).
-__global__ void __launch_bounds__(AP_THREADS, 3)
-allpairs_kernel(const SetRef* __restrict__ sets, int nsets, const uint32_t* __restrict__ boff, uint32_t NB, uint32_t nblk,
-                uint32_t tile_begin, uint32_t ntiles, unsigned long long* __restrict__ abc, unsigned int* __restrict__ overflow) {
-    extern __shared__ __align__(16) uint64_t tab[];   // [AP_S][AP_SLOTS]
-    __shared__ uint32_t s_lo[2 * AP_S][AP_BPC + 1];
-    // membership filter in front of the tables: bit (f, a) is set iff slice a holds a key whose filter hash is f.
-    // One 32-byte row = the same 32 filter positions of all 8 slices, so a key tests all 8 slices with two 16-byte
-    // loads; only slices whose bit is set (real members + ~7 % false positives) are probed in their table.
-    __shared__ __align__(16) uint32_t s_filt[AP_FILT / 32][AP_S];
-    __shared__ unsigned int s_ones;                    // bit a: slice a holds the key 2^64-1 (= the empty marker)
-    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile = tile_begin + blockIdx.x % ntiles;
-    const uint32_t b0 = (blockIdx.x / ntiles) * AP_BPC;
+// a run of buckets of one tile, and where it starts in the flattened list of all (tile, bucket) work items
+struct ApSeg {
     uint32_t bi, bj;
-    tile_to_blocks(tile, nblk, bi, bj);
-    const bool diag = (bi == bj);
-    const int steps = (int)min((uint32_t)AP_BPC, NB - b0);
+    uint32_t b0, b1;
+    uint64_t wstart;
+};
 
-    for (int idx = tid; idx < 2 * AP_S * (AP_BPC + 1); idx += AP_THREADS) {
-        const int sl = idx / (AP_BPC + 1), q = idx % (AP_BPC + 1);
-        const int si = (sl < AP_S) ? (int)bi * AP_S + sl : (int)bj * AP_S + sl - AP_S;
-        s_lo[sl][q] = (si < nsets) ? boff[(size_t)si * (NB + 1) + min(b0 + q, NB)] : 0u;
+// 32 x 32 bit-matrix transpose across a warp: lane l gives row l, gets column l (bit r = bit l of lane r's row)
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x) {
+    const unsigned l = lane_id();
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int j = 16 >> s;
+        const uint32_t m = (s == 0) ? 0x0000ffffu : (s == 1) ? 0x00ff00ffu : (s == 2) ? 0x0f0f0f0fu : (s == 3) ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (l & j) ? (((y >> j) & m) | (x & ~m)) : ((x & m) | ((y & m) << j));
     }
-    const int ja = (int)bi * AP_S + (int)warp;   // the set whose slices I insert
-    const int jb = (int)bj * AP_S + (int)warp;   // the set whose slices I stream
-    const uint64_t* Ak = (ja < nsets) ? sets[ja].k : nullptr;
-    const uint64_t* Bk = (jb < nsets) ? sets[jb].k : nullptr;
-    // tables I have to probe: sets of block bi that exist and (on the diagonal) come before mine
-    const int na = min((int)AP_S, max(0, nsets - (int)bi * AP_S));
-    const int nprobe = (jb < nsets) ? (diag ? min(na, (int)warp) : na) : 0;
-    uint32_t hits[AP_S];
-#pragma unroll
-    for (int a = 0; a < AP_S; a++) hits[a] = 0;
-    uint64_t* mytab = tab + warp * AP_SLOTS;
-
-    for (int q = 0; q < steps; q++) {
-        __syncthreads();   // offsets loaded (first step) / every probe of the previous step is done
-        {
-            const uint4 e4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-#pragma unroll
-            for (int r = 0; r < AP_S * AP_SLOTS / 2 / AP_THREADS; r++) reinterpret_cast<uint4*>(tab)[r * AP_THREADS + tid] = e4;
-            if (tid == 0) s_ones = 0;
-            for (int r = tid; r < AP_FILT / 32 * AP_S / 4; r += AP_THREADS) reinterpret_cast<uint4*>(&s_filt[0][0])[r] = make_uint4(0, 0, 0, 0);
-        }
-        __syncthreads();
-        {
-            const uint32_t lo = s_lo[warp][q], len = s_lo[warp][q + 1] - lo;
-            if (len > AP_CAP) {
-                if (lane == 0) atomicExch(overflow, 1u);
-            } else {
-                for (uint32_t i = lane; i < len; i += 32) {
-                    const uint64_t key = __ldg(Ak + lo + i);
-                    if (key == AP_EMPTY) { atomicOr(&s_ones, 1u << warp); continue; }
-                    const uint64_t hh = key * 0x9E3779B97F4A7C15ull;
-                    uint32_t h = (uint32_t)(hh >> 54);
-                    const uint32_t f = (uint32_t)(hh >> 20) & (AP_FILT - 1);   // filter hash: other bits than the slot
-                    atomicOr(&s_filt[f >> 5][warp], 1u << (f & 31));
-                    while (atomicCAS(reinterpret_cast<unsigned long long*>(&mytab[h]), AP_EMPTY, key) != AP_EMPTY)
-                        h = (h + 1) & (AP_SLOTS - 1);
-                }
-            }
-        }
-        __syncthreads();
-        if (nprobe) {
-            const uint32_t lo = s_lo[(diag ? 0 : AP_S) + warp][q], len = s_lo[(diag ? 0 : AP_S) + warp][q + 1] - lo;
-            const unsigned ones = s_ones;
-            // two keys per round, both loads in flight before the first probe
-            for (uint32_t i = lane; i < len; i += 64) {
-                const bool two = i + 32 < len;
-                uint64_t kk[2];
-                kk[0] = __ldg(Bk + lo + i);
-                kk[1] = two ? __ldg(Bk + lo + i + 32) : AP_EMPTY;
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const uint64_t key = kk[u];
-                    if (key == AP_EMPTY) {   // the empty marker itself (k = 32, all T) or the missing second key
-                        if (u == 0 || two) {
-#pragma unroll
-                            for (int a = 0; a < AP_S; a++) hits[a] += (a < nprobe) ? ((ones >> a) & 1u) : 0u;
-                        }
-                        continue;
-                    }
-                    const uint64_t hh = key * 0x9E3779B97F4A7C15ull;
-                    const uint32_t h0 = (uint32_t)(hh >> 54);
-                    const uint32_t f = (uint32_t)(hh >> 20) & (AP_FILT - 1);
-                    const uint4 f0 = *reinterpret_cast<const uint4*>(&s_filt[f >> 5][0]);
-                    const uint4 f1 = *reinterpret_cast<const uint4*>(&s_filt[f >> 5][4]);
-                    const uint32_t fw[AP_S] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-                    uint32_t cand = 0;   // slices whose filter bit is set
-#pragma unroll
-                    for (int a = 0; a < AP_S; a++) cand |= ((fw[a] >> (f & 31)) & 1u) << a;
-                    cand &= (1u << nprobe) - 1u;
-#pragma unroll
-                    for (int a = 0; a < AP_S; a++) {
-                        if ((cand >> a) & 1u) {
-                            const uint64_t* t = tab + a * AP_SLOTS;
-                            uint32_t h = h0;
-                            while (true) {
-                                const uint64_t v = t[h];
-                                if (v == key) { hits[a]++; break; }
-                                if (v == AP_EMPTY) break;
-                                h = (h + 1) & (AP_SLOTS - 1);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int a = 0; a < AP_S; a++) {
-        const uint32_t h = warp_sum(hits[a]);
-        if (lane == 0 && h && a < nprobe) {
-            const uint64_t ia = (uint64_t)bi * AP_S + a;
-            const uint64_t p = ia * (2ull * nsets - ia - 1) / 2 + ((uint64_t)jb - ia - 1);
-            atomicAdd(&abc[3 * p], (unsigned long long)h);
-        }
-    }
+    return x;
 }
 
-// returns false when a bucket overflowed the staging budget (result unusable)
-static bool allpairs_try(Ctx* c, const SetRef* d_sets, int nsets, uint32_t NB, int shift, uint32_t nblk, uint32_t tile_begin,
-                         uint32_t ntiles, uint64_t* d_abc) {
-    DBuf<uint32_t> boff(c, (size_t)nsets * (NB + 1) + 1);
-    unsigned int* d_ovf = reinterpret_cast<unsigned int*>(boff.get() + (size_t)nsets * (NB + 1));
-    ZB_CUDA(dev_memset(c, d_ovf, 0, 4));
+// Persistent: CTA c takes the work items [c W / G, (c + 1) W / G) -- consecutive buckets of (mostly) one tile, so its
+// reads of every set are sequential and its pair counters are flushed once.
+// Shared memory: keys 32 KB + hash table 32 KB + 2 x masks 16 KB + set index 4 KB + counters 4 KB + slice tables.
+__global__ void __launch_bounds__(AB_THREADS, 2)
+ap_bucket_kernel(const SetRef* __restrict__ sets, int nsets, const uint32_t* __restrict__ off, const ApSeg* __restrict__ segs,
+                 uint32_t nsegs, uint64_t W, unsigned long long* __restrict__ isect) {
+    extern __shared__ __align__(16) unsigned char ab_raw[];
+    uint64_t* sk = reinterpret_cast<uint64_t*>(ab_raw);                  // [AB_CAP] gathered keys
+    uint32_t* table = reinterpret_cast<uint32_t*>(sk + AB_CAP);          // [AB_HASH] position of a key's head
+    uint32_t* mA = table + AB_HASH;                                      // [AB_CAP] at a head: sets of block bi holding the key
+    uint32_t* mB = mA + AB_CAP;                                          // [AB_CAP]            sets of block bj (off the diagonal)
+    uint32_t* acc = mB + AB_CAP;                                         // [32 * 32] shared keys per pair of the tile
+    uint8_t* sb = reinterpret_cast<uint8_t*>(acc + AB_S * AB_S);         // [AB_CAP] which of the tile's sets an entry came from
+    __shared__ uint32_t spre[2 * AB_S + 1];                              // slice starts inside the bucket
+    __shared__ uint32_t soff[2 * AB_S];                                  // slice starts inside the sets
+
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t w0 = W * blockIdx.x / gridDim.x, w1 = W * (blockIdx.x + 1) / gridDim.x;
+    if (w0 >= w1) return;
+    uint32_t s = 0;   // segment of w0
     {
-        const uint64_t tot = (uint64_t)nsets * (NB + 1);
-        bucket_offsets_kernel<<<(unsigned)div_up(tot, 256), 256, 0, c->stream>>>(d_sets, nsets, shift, NB, boff.get());
-        ZB_LAUNCH_CHECK(c);
+        uint32_t lo = 0, hi = nsegs - 1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (segs[mid].wstart <= w0) lo = mid; else hi = mid - 1;
+        }
+        s = lo;
     }
-    const size_t smem = (size_t)AP_S * AP_SLOTS * 8;
-    ZB_CUDA(cudaFuncSetAttribute(allpairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint64_t groups = div_up(NB, AP_BPC);
-    // keep one launch below 2^31 CTAs: split the bucket groups
-    const uint64_t max_groups = std::max<uint64_t>(1, 0x7fffffffull / ntiles);
-    if (groups > max_groups) ZB_FAIL(ZB_E_ARG, "allpairs: %u block pairs x %llu bucket groups exceed one launch; shard the tiles",
-                                     ntiles, (unsigned long long)groups);
-    Stage st(c, "allpairs");
-    allpairs_kernel<<<(unsigned)(groups * ntiles), AP_THREADS, smem, c->stream>>>(
-        d_sets, nsets, boff.get(), NB, nblk, tile_begin, ntiles, reinterpret_cast<unsigned long long*>(d_abc), d_ovf);
-    ZB_LAUNCH_CHECK(c);
-    ZB_CUDA(read_back(c, d_ovf, 4));
-    ZB_CUDA(cudaStreamSynchronize(c->stream));
-    return reinterpret_cast<uint32_t*>(c->h_scalars)[0] == 0;
+    for (int idx = tid; idx < AB_S * AB_S; idx += AB_THREADS) acc[idx] = 0;
+    ApSeg seg = segs[s];
+    uint64_t seg_end = seg.wstart + (seg.b1 - seg.b0);
+
+    for (uint64_t wi = w0; wi <= w1; wi++) {
+        // ---- tile change (or the end of my range): flush the pair counters
+        if (wi == w1 || wi >= seg_end) {
+            __syncthreads();
+            const bool diag = (seg.bi == seg.bj);
+            for (int idx = tid; idx < AB_S * AB_S; idx += AB_THREADS) {
+                const uint32_t v = acc[idx];
+                acc[idx] = 0;
+                const uint64_t gi = (uint64_t)seg.bi * AB_S + (idx >> 5), gj = (uint64_t)seg.bj * AB_S + (idx & 31);
+                if (v && gi < gj && gj < (uint64_t)nsets && (!diag || (idx >> 5) < (idx & 31)))
+                    atomicAdd(&isect[gi * (2ull * nsets - gi - 1) / 2 + (gj - gi - 1)], (unsigned long long)v);
+            }
+            if (wi == w1) break;
+            while (wi >= seg_end) {
+                s++;
+                seg = segs[s];
+                seg_end = seg.wstart + (seg.b1 - seg.b0);
+            }
+        }
+        const uint32_t b = seg.b0 + (uint32_t)(wi - seg.wstart);
+        const bool diag = (seg.bi == seg.bj);
+        const int nA = min(AB_S, nsets - (int)seg.bi * AB_S);
+        const int nT = nA + (diag ? 0 : min(AB_S, nsets - (int)seg.bj * AB_S));   // sets of the tile
+        __syncthreads();   // the previous bucket (and the flush) are done with the shared arrays
+
+        // ---- where every set's slice of this bucket starts
+        if (warp == 0) {
+            uint32_t len[2], tot = 0;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int t = (int)lane * 2 + u;
+                len[u] = 0;
+                if (t < nT) {
+                    const int g = (t < nA) ? (int)seg.bi * AB_S + t : (int)seg.bj * AB_S + (t - nA);
+                    const uint32_t o0 = __ldg(off + (size_t)b * nsets + g);
+                    len[u] = __ldg(off + (size_t)(b + 1) * nsets + g) - o0;
+                    soff[t] = o0;
+                }
+                tot += len[u];
+            }
+            uint32_t ex = warp_incl_scan(tot) - tot;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int t = (int)lane * 2 + u;
+                if (t < nT) spre[t] = ex;
+                ex += len[u];
+            }
+            if (lane == 31) spre[nT] = ex;
+        }
+        {
+            const uint4 e4 = make_uint4(AB_EMPTY, AB_EMPTY, AB_EMPTY, AB_EMPTY);
+#pragma unroll
+            for (int j = 0; j < AB_HASH / 4 / AB_THREADS; j++) reinterpret_cast<uint4*>(table)[j * AB_THREADS + tid] = e4;
+        }
+        __syncthreads();
+        const int m = (int)spre[nT];
+        if (m == 0) continue;
+        for (int q = (int)tid; q < m; q += AB_THREADS) { mA[q] = 0; mB[q] = 0; }
+
+        // ---- gather: a warp copies whole slices, four at a time (eight loads in flight per lane)
+        {
+            constexpr int U = 4;
+            for (int t0 = (int)warp; t0 < nT; t0 += U * AB_WARPS) {
+                uint32_t q0[U], len[U];
+                const uint64_t* pk[U];
+                uint32_t mx = 0;
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int t = t0 + u * AB_WARPS;
+                    q0[u] = 0; len[u] = 0; pk[u] = nullptr;
+                    if (t < nT) {
+                        const int g = (t < nA) ? (int)seg.bi * AB_S + t : (int)seg.bj * AB_S + (t - nA);
+                        q0[u] = spre[t];
+                        len[u] = spre[t + 1] - q0[u];
+                        pk[u] = sets[g].k + soff[t];
+                    }
+                    mx = max(mx, len[u]);
+                }
+                for (uint32_t e = lane; e < mx; e += 32) {
+                    uint64_t kv[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        if (e < len[u]) kv[u] = __ldg(pk[u] + e);
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        if (e < len[u]) { sk[q0[u] + e] = kv[u]; sb[q0[u] + e] = (uint8_t)(t0 + u * AB_WARPS); }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- dedupe: the first entry to claim a key's slot is its head; every entry sets its set's bit there
+#pragma unroll
+        for (int j = 0; j < AB_PER; j++) {
+            const int q = j * AB_THREADS + (int)tid;
+            if (q < m) {
+                const uint64_t x = sk[q];
+                uint32_t h = (uint32_t)((x * 0x9E3779B97F4A7C15ull) >> (64 - AB_HASH_BITS));
+                uint32_t hq;
+                while (true) {
+                    const uint32_t old = atomicCAS(&table[h], AB_EMPTY, (uint32_t)q);
+                    if (old == AB_EMPTY) { hq = (uint32_t)q; break; }
+                    if (sk[old] == x) { hq = old; break; }
+                    h = (h + 1) & (AB_HASH - 1);
+                }
+                const int t = (int)sb[q];
+                if (t < nA) atomicOr(&mA[hq], 1u << t); else atomicOr(&mB[hq], 1u << (t - nA));
+            }
+        }
+        __syncthreads();
+
+        // ---- count: 32 positions per warp step; lane l ends up with "which of these 32 keys are in set l"
+        for (int c0 = (int)warp * 32; c0 < m; c0 += AB_THREADS) {
+            const int q = c0 + (int)lane;
+            const uint32_t a = (q < m) ? mA[q] : 0u;
+            const uint32_t bb = (q < m && !diag) ? mB[q] : 0u;
+            const bool useful = diag ? (a & (a - 1)) != 0 : (a != 0 && bb != 0);
+            if (!__any_sync(0xffffffffu, useful)) continue;
+            const uint32_t colA = warp_transpose32(useful ? a : 0u);
+            if (diag) {
+                // pairs (l, l + d mod 32), d = 1 .. 16: every unordered pair once
+#pragma unroll
+                for (int d = 1; d <= 16; d++) {
+                    const uint32_t other = __shfl_sync(0xffffffffu, colA, (lane + d) & 31);
+                    const uint32_t cnt = __popc(colA & other);
+                    if (cnt && (d < 16 || lane < 16)) {
+                        const uint32_t o = (lane + d) & 31;
+                        atomicAdd(&acc[min(lane, o) * 32 + max(lane, o)], cnt);
+                    }
+                }
+            } else {
+                const uint32_t colB = warp_transpose32(useful ? bb : 0u);
+#pragma unroll
+                for (int d = 0; d < 32; d++) {
+                    const uint32_t o = (lane + d) & 31;
+                    const uint32_t other = __shfl_sync(0xffffffffu, colB, o);
+                    const uint32_t cnt = __popc(colA & other);
+                    if (cnt) atomicAdd(&acc[lane * 32 + o], cnt);
+                }
+            }
+        }
+    }
 }
 
 uint64_t allpairs_tiles(int nsets) {
-    const uint64_t nblk = div_up((size_t)nsets, AP_S);
-    return nblk * (nblk + 1) / 2;
+    const uint64_t nblk = div_up((size_t)nsets, AB_S);
+    return nblk * (nblk + 1) / 2 * AB_KS;
 }
 
-void allpairs_abc(Ctx* c, const std::vector<SetRef>& refs, uint64_t tile_begin, uint64_t tile_end, uint64_t* abc_host) {
+// first bucket of key-range shard s (s = 0 .. AB_KS) when the key space is cut into nb buckets
+static inline uint64_t shard_bucket(uint64_t s, uint64_t nb) { return (s * nb + AB_KS - 1) / AB_KS; }
+
+// a per pair on the device, b and c on the host from the shard sizes.  Returns false when the key space is too skewed.
+static bool allpairs_buckets(Ctx* c, const SetRef* d_sets, const std::vector<SetRef>& refs, int key_bits, uint64_t ub,
+                             uint64_t ue, uint64_t* abc_host) {
+    const int nsets = (int)refs.size();
+    const uint64_t npairs = (uint64_t)nsets * (nsets - 1) / 2;
+    const uint32_t nblk = (uint32_t)div_up((size_t)nsets, AB_S);
+    // the fullest tile: the two largest blocks (one block when there is only one)
+    uint64_t top1 = 0, top2 = 0;
+    size_t nmax = 0;
+    for (uint32_t blk = 0; blk < nblk; blk++) {
+        uint64_t t = 0;
+        for (int i = blk * AB_S; i < std::min<int>((blk + 1) * AB_S, nsets); i++) {
+            if (refs[i].n >= ((uint64_t)1 << 32)) return false;
+            t += refs[i].n;
+            nmax = std::max<size_t>(nmax, refs[i].n);
+        }
+        if (t > top1) { top2 = top1; top1 = t; } else if (t > top2) top2 = t;
+    }
+    const uint64_t tile_total = top1 + top2;
+    if (tile_total == 0) return true;
+    int cb = 0;
+    while (cb < key_bits && (tile_total >> cb) > (uint64_t)AB_CAP * 2 / 3) cb++;
+    cb = std::max(cb, std::min(3, key_bits));
+    DBuf<uint32_t> off;
+    uint32_t nb = 0;
+    for (int attempt = 0;; attempt++) {
+        if (cb > 30 || (((size_t)1 << cb) + 1) * (size_t)nsets > ((size_t)1 << 29)) return false;
+        nb = 1u << cb;
+        const size_t noff = (size_t)(nb + 1) * nsets;
+        off.alloc(c, noff + 2);
+        unsigned int* d_mx = off.get() + noff;
+        ZB_CUDA(dev_memset(c, off.get(), 0, (noff + 2) * 4));
+        {
+            Stage st(c, "allpairs_offsets");
+            const dim3 grid((unsigned)std::min<size_t>(std::max<size_t>(div_up(nmax, 256 * 8), 1), 65535), (unsigned)nsets);
+            ap_offsets_kernel<<<grid, 256, 0, c->stream>>>(d_sets, nsets, key_bits - cb, nb, off.get());
+            ZB_LAUNCH_CHECK(c);
+            ap_blockmax_kernel<<<(unsigned)div_up((size_t)nb * nblk, 8), 256, 0, c->stream>>>(off.get(), nsets, nb, nblk, d_mx);
+            ZB_LAUNCH_CHECK(c);
+        }
+        ZB_CUDA(read_back(c, d_mx, 4));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+        const uint64_t mx = reinterpret_cast<uint32_t*>(c->h_scalars)[0];
+        const uint64_t worst = (nblk > 1) ? 2 * mx : mx;   // any two blocks together
+        if (worst <= (uint64_t)AB_CAP) break;
+        if (attempt >= 3 || cb >= key_bits) return false;
+        int more = 1;
+        while (((worst >> more) > (uint64_t)AB_CAP * 2 / 3) && more < 8) more++;
+        cb = std::min(key_bits, cb + more);
+    }
+
+    // work list: for every tile touched by the units [ub, ue), the buckets of its shards in that range
+    std::vector<ApSeg> segs;
+    uint64_t W = 0;
+    for (uint64_t t = ub / AB_KS; t <= (ue - 1) / AB_KS; t++) {
+        const uint64_t s0 = std::max(ub, t * AB_KS) - t * AB_KS, s1 = std::min(ue, (t + 1) * AB_KS) - t * AB_KS;
+        ApSeg sg;
+        tile_to_blocks(t, nblk, sg.bi, sg.bj);
+        sg.b0 = (uint32_t)std::min<uint64_t>(shard_bucket(s0, nb), nb);
+        sg.b1 = (uint32_t)std::min<uint64_t>(shard_bucket(s1, nb), nb);
+        sg.wstart = W;
+        if (sg.b1 > sg.b0) {
+            W += sg.b1 - sg.b0;
+            segs.push_back(sg);
+        }
+    }
+    std::vector<uint64_t> isect(npairs, 0);
+    if (W) {
+        DBuf<ApSeg> d_segs(c, segs.size());
+        DBuf<uint64_t> d_isect(c, npairs);
+        ZB_CUDA(cudaMemcpyAsync(d_segs.get(), segs.data(), segs.size() * sizeof(ApSeg), cudaMemcpyHostToDevice, c->stream));
+        ZB_CUDA(dev_memset(c, d_isect.get(), 0, npairs * 8));
+        const size_t smem = (size_t)AB_CAP * 8 + (size_t)AB_HASH * 4 + (size_t)2 * AB_CAP * 4 + (size_t)AB_S * AB_S * 4 + AB_CAP;
+        ZB_CUDA(cudaFuncSetAttribute(ap_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)std::min<uint64_t>(W, (uint64_t)c->sm_count * 2);
+        {
+            Stage st(c, "allpairs");
+            ap_bucket_kernel<<<grid, AB_THREADS, smem, c->stream>>>(d_sets, nsets, off.get(), d_segs.get(), (uint32_t)segs.size(), W,
+                                                                     reinterpret_cast<unsigned long long*>(d_isect.get()));
+            ZB_LAUNCH_CHECK(c);
+        }
+        ZB_CUDA(cudaMemcpyAsync(isect.data(), d_isect.get(), npairs * 8, cudaMemcpyDeviceToHost, c->stream));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    // sizes of the shards: rows of `off` at the shard boundaries
+    std::vector<uint32_t> rows((size_t)(AB_KS + 1) * nsets);
+    for (int s = 0; s <= AB_KS; s++)
+        ZB_CUDA(cudaMemcpyAsync(rows.data() + (size_t)s * nsets, off.get() + (size_t)std::min<uint64_t>(shard_bucket(s, nb), nb) * nsets,
+                                (size_t)nsets * 4, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    for (uint64_t t = ub / AB_KS; t <= (ue - 1) / AB_KS; t++) {
+        const uint64_t s0 = std::max(ub, t * AB_KS) - t * AB_KS, s1 = std::min(ue, (t + 1) * AB_KS) - t * AB_KS;
+        uint32_t bi, bj;
+        tile_to_blocks(t, nblk, bi, bj);
+        for (uint64_t i = (uint64_t)bi * AB_S; i < std::min<uint64_t>((uint64_t)(bi + 1) * AB_S, nsets); i++)
+            for (uint64_t j = std::max<uint64_t>((uint64_t)bj * AB_S, i + 1); j < std::min<uint64_t>((uint64_t)(bj + 1) * AB_S, nsets); j++) {
+                const uint64_t p = i * (2ull * nsets - i - 1) / 2 + (j - i - 1);
+                const uint64_t a = isect[p];
+                const uint64_t ni = rows[s1 * nsets + i] - rows[s0 * nsets + i], nj = rows[s1 * nsets + j] - rows[s0 * nsets + j];
+                abc_host[3 * p] = a;
+                abc_host[3 * p + 1] = ni - a;
+                abc_host[3 * p + 2] = nj - a;
+            }
+    }
+    return true;
+}
+
+void allpairs_abc(Ctx* c, const std::vector<SetRef>& refs, uint64_t unit_begin, uint64_t unit_end, uint64_t* abc_host) {
     const int nsets = (int)refs.size();
     const uint64_t npairs = (uint64_t)nsets * (nsets - 1) / 2;
     if (npairs == 0) return;
-    const uint32_t nblk = (uint32_t)div_up((size_t)nsets, AP_S);
-    const uint64_t all_tiles = allpairs_tiles(nsets);
-    if (tile_end == 0 || tile_end > all_tiles) tile_end = all_tiles;
+    const uint32_t nblk = (uint32_t)div_up((size_t)nsets, AB_S);
+    const uint64_t all_units = allpairs_tiles(nsets);
+    if (unit_end == 0 || unit_end > all_units) unit_end = all_units;
     memset(abc_host, 0, npairs * 3 * 8);
-    if (tile_begin >= tile_end) return;
-    const uint32_t ntiles = (uint32_t)(tile_end - tile_begin);
+    if (unit_begin >= unit_end) return;
 
     DBuf<SetRef> d_refs(c, nsets);
     ZB_CUDA(cudaMemcpyAsync(d_refs.get(), refs.data(), nsets * sizeof(SetRef), cudaMemcpyHostToDevice, c->stream));
     // key range: the sets are sorted, so the largest key is the largest last element
-    uint64_t maxkey = 0, max_n = 0;
+    uint64_t maxkey = 0;
     {
         std::vector<uint64_t> last(nsets, 0);
-        for (int i = 0; i < nsets; i++) {
-            max_n = std::max<uint64_t>(max_n, refs[i].n);
+        for (int i = 0; i < nsets; i++)
             if (refs[i].n) ZB_CUDA(cudaMemcpyAsync(&last[i], refs[i].k + refs[i].n - 1, 8, cudaMemcpyDeviceToHost, c->stream));
-        }
         ZB_CUDA(cudaStreamSynchronize(c->stream));
         for (int i = 0; i < nsets; i++) maxkey = std::max(maxkey, last[i]);
     }
     const int key_bits = maxkey ? 64 - __builtin_clzll(maxkey) : 1;
-    DBuf<uint64_t> d_abc(c, npairs * 3);
-    bool ok = false;
-    int lgNB = 4;
-    while ((max_n >> lgNB) > 384 && lgNB < 22) lgNB++;   // <= 384 keys of the largest set per bucket on average
-    for (int attempt = 0; attempt < 2 && !ok; attempt++, lgNB += 4) {
-        if (lgNB > key_bits) lgNB = key_bits;
-        if (lgNB > 24) break;
-        const uint32_t NB = 1u << lgNB;
-        if (div_up(NB, AP_BPC) * (uint64_t)ntiles > 0x7fffffffull) break;
-        ZB_CUDA(dev_memset(c, d_abc.get(), 0, npairs * 3 * 8));
-        ok = allpairs_try(c, d_refs.get(), nsets, NB, key_bits - lgNB, nblk, (uint32_t)tile_begin, ntiles, d_abc.get());
-        if (lgNB == key_bits) break;
-    }
-    if (ok) {
-        ZB_CUDA(cudaMemcpyAsync(abc_host, d_abc.get(), npairs * 3 * 8, cudaMemcpyDeviceToHost, c->stream));
-        ZB_CUDA(cudaStreamSynchronize(c->stream));
-    }
-    // pairs of the requested tiles: fill |X \ Y|, |Y \ X| (and, after an overflow, everything pair by pair)
+    if (!getenv("ZB_ALLPAIRS_PAIRWISE") && allpairs_buckets(c, d_refs.get(), refs, key_bits, unit_begin, unit_end, abc_host)) return;
+
+    // skewed key space: pair-at-a-time merge path (setops.cu); a pair goes, whole, to the first shard of its tile
+    memset(abc_host, 0, npairs * 3 * 8);
     std::vector<uint32_t> I, J;
-    for (uint64_t t = tile_begin; t < tile_end; t++) {
-        // same enumeration as tile_to_blocks
-        uint64_t r = 0, start = 0;
-        while (start + (nblk - r) <= t) { start += nblk - r; r++; }
-        const uint64_t bi = r, bj = r + (t - start);
-        for (uint64_t i = bi * AP_S; i < std::min<uint64_t>((bi + 1) * AP_S, nsets); i++)
-            for (uint64_t j = std::max(bj * AP_S, i + 1); j < std::min<uint64_t>((bj + 1) * AP_S, nsets); j++) {
+    for (uint64_t t = div_up(unit_begin, AB_KS); t * AB_KS < unit_end; t++) {
+        uint32_t bi, bj;
+        tile_to_blocks(t, nblk, bi, bj);
+        for (uint64_t i = (uint64_t)bi * AB_S; i < std::min<uint64_t>((uint64_t)(bi + 1) * AB_S, nsets); i++)
+            for (uint64_t j = std::max<uint64_t>((uint64_t)bj * AB_S, i + 1); j < std::min<uint64_t>((uint64_t)(bj + 1) * AB_S, nsets); j++) {
                 I.push_back((uint32_t)i);
                 J.push_back((uint32_t)j);
             }
     }
-    if (!ok) {
-        // skewed key space: pair-at-a-time merge path (setops.cu)
-        std::vector<uint64_t> tmp(I.size() * 3);
-        pairs_abc_host(c, refs, I.data(), J.data(), I.size(), tmp.data());
-        for (size_t q = 0; q < I.size(); q++) {
-            const uint64_t i = I[q], j = J[q];
-            const uint64_t p = i * (2ull * nsets - i - 1) / 2 + (j - i - 1);
-            abc_host[3 * p] = tmp[3 * q];
-        }
-    }
+    if (I.empty()) return;
+    std::vector<uint64_t> tmp(I.size() * 3);
+    pairs_abc_host(c, refs, I.data(), J.data(), I.size(), tmp.data());
     for (size_t q = 0; q < I.size(); q++) {
         const uint64_t i = I[q], j = J[q];
         const uint64_t p = i * (2ull * nsets - i - 1) / 2 + (j - i - 1);
-        const uint64_t a = abc_host[3 * p];
+        const uint64_t a = tmp[3 * q];
+        abc_host[3 * p] = a;
         abc_host[3 * p + 1] = refs[i].n - a;
         abc_host[3 * p + 2] = refs[j].n - a;
     }

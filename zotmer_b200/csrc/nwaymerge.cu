@@ -148,28 +148,33 @@ bm_merge_kernel(const KCRef* __restrict__ sets, int nsets, const uint32_t* __res
     if (BY_SLICE) {
         const int lane = (int)(tid & 31), warp = (int)(tid >> 5);
         constexpr int NW = BM_THREADS / 32;
-        for (int i0 = warp; i0 < nsets; i0 += 2 * NW) {   // two slices at a time: four loads in flight per lane
-            const int i1 = i0 + NW;
-            const uint32_t a0 = spre[i0], alen = spre[i0 + 1] - a0;
-            const uint64_t* __restrict__ ak = sets[i0].k + soff[i0];
-            const uint32_t* __restrict__ ac = sets[i0].c + soff[i0];
-            uint32_t b0 = 0, blen = 0;
-            const uint64_t* __restrict__ bk = ak;
-            const uint32_t* __restrict__ bc = ac;
-            if (i1 < nsets) {
-                b0 = spre[i1];
-                blen = spre[i1 + 1] - b0;
-                bk = sets[i1].k + soff[i1];
-                bc = sets[i1].c + soff[i1];
+        constexpr int U = 4;   // slices a warp copies at a time: 2 U loads in flight per lane
+        for (int i0 = warp; i0 < nsets; i0 += U * NW) {
+            uint32_t q0[U], len[U];
+            const uint64_t* pk[U];
+            const uint32_t* pc[U];
+            uint32_t mx = 0;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + u * NW;
+                q0[u] = 0; len[u] = 0; pk[u] = nullptr; pc[u] = nullptr;
+                if (i < nsets) {
+                    q0[u] = spre[i];
+                    len[u] = spre[i + 1] - q0[u];
+                    pk[u] = sets[i].k + soff[i];
+                    pc[u] = sets[i].c + soff[i];
+                }
+                mx = max(mx, len[u]);
             }
-            const uint32_t mx = max(alen, blen);
             for (uint32_t e = lane; e < mx; e += 32) {
-                uint64_t ka = 0, kb = 0;
-                uint32_t ca = 0, cb2 = 0;
-                if (e < alen) { ka = __ldg(ak + e); ca = __ldg(ac + e); }
-                if (e < blen) { kb = __ldg(bk + e); cb2 = __ldg(bc + e); }
-                if (e < alen) { sk[a0 + e] = ka; wsum[a0 + e] = ca; }
-                if (e < blen) { sk[b0 + e] = kb; wsum[b0 + e] = cb2; }
+                uint64_t kv[U];
+                uint32_t cv[U];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (e < len[u]) { kv[u] = __ldg(pk[u] + e); cv[u] = __ldg(pc[u] + e); }
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (e < len[u]) { sk[q0[u] + e] = kv[u]; wsum[q0[u] + e] = cv[u]; }
             }
         }
     } else {
@@ -257,8 +262,13 @@ bm_merge_kernel(const KCRef* __restrict__ sets, int nsets, const uint32_t* __res
         const uint32_t d = (uint32_t)(x >> fine_shift) & fine_mask;
         const int g0 = (int)hist[d], g1 = (int)hist[d + 1];
         int r = 0;
-        if (g1 - g0 > 1)
+        const int g = g1 - g0;
+        if (g > 1 && g <= 4) {   // the usual case, without a data-dependent loop
+#pragma unroll
+            for (int u = 0; u < 4; u++) r += (u < g && hs[min(g0 + u, g1 - 1)] < x) ? 1 : 0;
+        } else if (g > 4) {
             for (int p2 = g0; p2 < g1; p2++) r += (hs[p2] < x) ? 1 : 0;
+        }
         tmp_k[s0 + g0 + r] = x;
         tmp_c[s0 + g0 + r] = hc[p];
     }

@@ -847,7 +847,10 @@ size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1
     if (key_bits > 64) key_bits = 64;
     if (g_sort_count_mode == 1) return sort_count_classic(c, k0, k1, v0, v1, n, key_bits, out_k, out_c);
     const bool weighted_sum = (v0 != nullptr) && !distinct;
-    if (g_sort_count_mode == 2 || weighted_sum) return sort_count_segsort(c, k0, k1, v0, v1, n, key_bits, out_k, out_c, distinct);
+    // the bucket kernel's bulk copies start at 16-byte boundaries inside the key arrays
+    const bool aligned = (((uintptr_t)k0 | (uintptr_t)k1) & 15) == 0;
+    if (g_sort_count_mode == 2 || weighted_sum || !aligned)
+        return sort_count_segsort(c, k0, k1, v0, v1, n, key_bits, out_k, out_c, distinct);
     return sort_count_buckets(c, k0, k1, v0, v1, n, key_bits, out_k, out_c, distinct);
 }
 

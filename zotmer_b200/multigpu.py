@@ -9,7 +9,7 @@ and every rank sorts and counts its disjoint share locally.  x and rc(x) land on
 is fine: the canonical key is what is routed, mirroring happens after counting on the owner.
 
 All-pairs distances (`zot dist`, `zot jaccard -a`) shard without any exchange: the upper triangle of the
-set x set matrix is cut into tiles (pairs of blocks of 8 sets, csrc/allpairs.cu), every rank computes a
+set x set matrix is cut into work units (pairs of blocks of 32 sets x 8 key-range shards, csrc/allpairs.cu), every rank computes a
 contiguous, pair-count-balanced range of tiles over its own copy of the sets, and the partial matrices (zero
 outside a rank's tiles) are added up -- the "final gather" of the north star.
 
@@ -289,13 +289,15 @@ def _as_tensor(ptr, n, dtype, dev):
 
 
 # ------------------------------------------------------------------------------------------------
-# all-pairs distance matrix: tiles of 8 x 8 sets, sharded over ranks
-AP_S = 8   # sets per block, csrc/allpairs.cu
+# all-pairs distance matrix: work units = (pair of blocks of 32 sets) x (one of 8 key-range shards), sharded over ranks
+AP_S = 32   # sets per block, csrc/allpairs.cu AB_S
+AP_KS = 8   # key-range shards per tile, csrc/allpairs.cu AB_KS
 
 
-def tile_blocks(nsets, t):
-    """tile number -> (bi, bj), bi <= bj: row-major over the upper triangle of blocks, diagonal included
-    (host statement of csrc/allpairs.cu tile_to_blocks)"""
+def tile_blocks(nsets, u):
+    """work unit -> (bi, bj), bi <= bj: its tile u // AP_KS, row-major over the upper triangle of blocks, diagonal
+    included (host statement of csrc/allpairs.cu tile_to_blocks)"""
+    t = u // AP_KS
     nblk = -(-nsets // AP_S)
     r, start = 0, 0
     while start + (nblk - r) <= t:
@@ -304,9 +306,9 @@ def tile_blocks(nsets, t):
     return r, r + (t - start)
 
 
-def tile_pairs(nsets, t):
-    """the set pairs (i < j) a tile covers"""
-    bi, bj = tile_blocks(nsets, t)
+def tile_pairs(nsets, u):
+    """the set pairs (i < j) a work unit contributes to (it holds their counts over ITS key-range shard u % AP_KS)"""
+    bi, bj = tile_blocks(nsets, u)
     out = []
     for i in range(bi * AP_S, min((bi + 1) * AP_S, nsets)):
         for j in range(max(bj * AP_S, i + 1), min((bj + 1) * AP_S, nsets)):
@@ -314,15 +316,20 @@ def tile_pairs(nsets, t):
     return out
 
 
+def key_shard(x, key_bits):
+    """key-range shard of k-mer x when the largest k-mer of the collection has key_bits bits: floor(x AP_KS / 2^key_bits)"""
+    return (int(x) * AP_KS) >> key_bits
+
+
 def n_tiles(nsets):
     nblk = -(-nsets // AP_S)
-    return nblk * (nblk + 1) // 2
+    return nblk * (nblk + 1) // 2 * AP_KS
 
 
 def tile_ranges(nsets, world):
     """contiguous tile ranges [(begin, end)] per rank with about the same number of set pairs each"""
     nt = n_tiles(nsets)
-    w = np.array([len(tile_pairs(nsets, t)) for t in range(nt)], dtype=np.int64) if nt < 200000 else np.full(nt, 64)
+    w = np.array([len(tile_pairs(nsets, t)) for t in range(nt)], dtype=np.int64) if nt < 20000 else np.full(nt, 1024)
     cum = np.concatenate([[0], np.cumsum(w)])
     total = int(cum[-1])
     cuts = [0]
