@@ -66,6 +66,11 @@ int zb_release_cache(int device);
 int zb_kmerize_open(int k, int device, zb_kmerizer** out);
 int zb_kmerize_feed(zb_kmerizer* h, const uint8_t* raw, size_t n, int is_fasta);
 int zb_kmerize_feed_dev(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is_fasta);
+/* capture mode -- `zot kmerize -C BAITS`, kmerize.py:478-483 (the bait k-mers) and :507-517 (`if found:
+ * buf.addList(xs)`): from now on a fed record contributes ALL its k-mers iff one of them is in `baits` (a both-strand
+ * k-mer set of the bait sequences, e.g. the result of kmerizing the bait FASTA); other records only count as records.
+ * `baits` must stay alive while the kmerizer is fed; NULL switches the mode off. */
+int zb_kmerize_set_baits(zb_kmerizer* h, const zb_set* baits);
 /* pre-parsed input: one code per base (0..3 = ACGT, 4 = break) -- used by the synthetic read generator */
 int zb_kmerize_feed_codes_dev(zb_kmerizer* h, const uint8_t* d_codes, size_t n, uint64_t n_records);
 int zb_kmerize_finish(zb_kmerizer* h, zb_set** result, uint64_t* n_records);

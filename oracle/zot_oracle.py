@@ -557,6 +557,45 @@ def cmd_kmerize_D(k, out, input_paths, d, S=0):
     z.close()
 
 
+def cmd_kmerize_C(k, out, input_paths, bait_path):
+    """kmerize.py:450-562 with -C BAITS: B = the k-mers (both strands) of every record of the bait FASTA (:478-483);
+    acgt over every k-mer of every record (:492-493); a record's k-mers are accumulated, all of them, iff one of them
+    is in B (:507-517)."""
+    with open(bait_path, "rb") as f:
+        bait_data = f.read()
+    B = set()
+    for seq in sequences("baits.fa", bait_data):       # readFasta whatever the suffix (:481)
+        B |= set(kmers_list(k, seq, True))
+    buf = []
+    acgt = [0, 0, 0, 0]
+    nr = 0
+    for p in input_paths:
+        with open(p, "rb") as f:
+            data = f.read()
+        for seq in sequences(p, data):
+            xs = kmers_list(k, seq, True)
+            for x in xs:
+                acgt[x & 3] += 1
+            if any(x in B for x in xs):
+                buf.extend(xs)
+            nr += 1
+    buf.sort()
+    xs, cs = count_sorted(buf)
+    h = {}
+    for c in cs:
+        h[c] = 1 + h.get(c, 0)
+    z = CasketWriter(out)
+    write_kmers_and_counts(z, xs, cs)
+    n = float(sum(acgt))
+    z.meta["K"] = k
+    z.meta["kmers"] = "kmers"
+    z.meta["counts"] = "counts"
+    z.meta["hist"] = h
+    z.meta["acgt"] = [c / n for c in acgt]
+    z.meta["reads"] = nr
+    z.close()
+
+
 def sample_core(xs, cs, p, S):
     """commands/sample.py:27-34 sampleD (the path docopt always selects, :53)."""
     M = 0xFFFFFFFFFF

@@ -93,6 +93,11 @@ def make_inputs():
     fq.append("@partial\nACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT\n+\n")  # dropped: only 3 lines (file.py:45-52)
     write(os.path.join(DATA, "r1.fq"), "".join(fq))
 
+    # ---- baits.fa : bait sequences for `zot kmerize -C` (pieces of the genome r1.fq was read from, one of them
+    # reverse-complemented, and a piece of g1.fa's chr1); no random numbers drawn here
+    write(os.path.join(DATA, "baits.fa"), ">b1\n%s\n>b2 rc\n%s\n>b3 chr1\n%s\n" % (
+        genome[300:380], revcomp(genome[1200:1260]), wrap(chrom[700:790], 40)))
+
     # ---- r2.fq : enough records (2500 x 60 bp) to force >= 2 spills with -m 1 (kmerize.py:527-539)
     fq = []
     for i in range(2500):
@@ -328,6 +333,16 @@ def main():
     kmerizeD(25, "r1_D03_S5.k25", ["r1.fq"], "0.3", "5")
     kmerizeD(25, "g1_D05.k25", ["g1.fa"], "0.5")
     kmerizeD(16, "g1_D2.k16", ["g1.fa"], "2.0", "9")       # u can exceed 1 (murmer is not masked to 61 bits): d = 2 keeps fewer than all
+    def kmerizeC(k, out, inputs, baits):
+        return run_cmd("kmerize", {"<k>": str(k), "<output>": os.path.join(DATA, out),
+                                   "<input>": [os.path.join(DATA, i) for i in inputs],
+                                   "-m": None, "-C": os.path.join(DATA, baits), "-D": None, "-S": None, "-v": False})
+
+    kmerizeC(25, "r1_C.k25", ["r1.fq"], "baits.fa")               # reads that hold a bait 25-mer, whole
+    kmerizeC(25, "g1_C.k25", ["g1.fa"], "baits.fa")               # FASTA records: chr1 is captured, the others are not
+    kmerizeC(16, "mix_C.k16", ["r1.fq", "g1.fa"], "baits.fa")
+    kmerizeC(25, "r1_Cself.k25", ["r1.fq"], "g1.fa")              # baits that share nothing with the reads: empty set
+
     kat["sub"] = [[s_, p_, x_, bool(basics.sub(s_, p_, x_))] for (s_, p_, x_) in
                   [(0, 0.5, 0), (0, 0.5, 1), (5, 0.3, 0x1234567), (17, 0.01, 2 ** 50 - 1), (9, 2.0, 0xFFFFFFFF), (9, 2.0, 12345)]]
 

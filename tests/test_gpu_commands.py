@@ -188,6 +188,16 @@ def test_project_mismatched_K(zot, tmp_path, capsys):
     assert capsys.readouterr().err == "mismatched K (16)\n"
 
 
+@pytest.mark.parametrize("k,out,ins,baits", [(25, "r1_C.k25", ["r1.fq"], "baits.fa"), (25, "g1_C.k25", ["g1.fa"], "baits.fa"),
+                                             (16, "mix_C.k16", ["r1.fq", "g1.fa"], "baits.fa"),
+                                             (25, "r1_Cself.k25", ["r1.fq"], "g1.fa")])
+def test_kmerize_C_file_bytes(zot, tmp_path, k, out, ins, baits):
+    """capture mode: records holding a bait k-mer are kept whole (device: capture_records), acgt / reads cover all"""
+    o = tmp_path / out
+    zot("kmerize", "-C", baits, k, o, *ins)
+    assert o.read_bytes() == rd(out)
+
+
 @pytest.mark.parametrize("k,out,ins,args", [(25, "r1_D03_S5.k25", ["r1.fq"], ["-D", "0.3", "-S", "5"]),
                                             (25, "g1_D05.k25", ["g1.fa"], ["-D", "0.5"]),
                                             (16, "g1_D2.k16", ["g1.fa"], ["-D", "2.0", "-S", "9"])])

@@ -445,6 +445,50 @@ def test_kmerize_palindromes_even_k(nat):
         assert np.array_equal(ks, ek) and np.array_equal(cc, ec), k
 
 
+@pytest.mark.parametrize("k", [9, 25, 32])
+def test_kmerize_capture_vs_oracle(nat, k):
+    """capture mode on a few thousand reads / a multi-record FASTA spanning many tiles: every record is judged on its
+    own (kmerize.py:507-517), records are told apart by the parser's record marks"""
+    rng = np.random.default_rng(k)
+    genome = "".join("ACGT"[i] for i in rng.integers(0, 4, 60000))
+    baits = ">b\n" + genome[1000:1200] + "\n>c\n" + genome[30000:30100] + "\n"
+    recs = []
+    for i in range(4000):
+        L = int(rng.choice([150, 150, 80, 40, k, k - 1, 0]))
+        p = int(rng.integers(0, len(genome) - 150))
+        r = genome[p:p + L]
+        if L > 20 and rng.random() < 0.2:
+            q = int(rng.integers(0, L))
+            r = r[:q] + "N" + r[q + 1:]
+        recs.append(r)
+    fq = "".join("@r%d\n%s\n+\n%s\n" % (i, r, "I" * len(r)) for i, r in enumerate(recs)).encode()
+    fa = "".join(">s%d\n%s\n" % (i, "\n".join(r[j:j + 60] for j in range(0, len(r), 60))) for i, r in enumerate(recs[:1500]))
+    fa = (fa + ">long\n" + genome[900:21000] + "\n>other\n" + genome[40000:52000] + "\n").encode()
+    B = set()
+    for seq in zo.sequences("b.fa", baits.encode()):
+        B |= set(zo.kmers_list(k, seq, True))
+    bs, _ = run_kmerize(nat, k, [(baits.encode(), True)])
+    assert sorted(B) == [int(x) for x in bs.fetch()[0]]
+    for name, data, is_fa in (("x.fq", fq, False), ("x.fa", fa, True)):
+        buf = []
+        nrec = 0
+        for seq in zo.sequences(name, data):
+            xs = zo.kmers_list(k, seq, True)
+            if any(x in B for x in xs):
+                buf.extend(xs)
+            nrec += 1
+        buf.sort()
+        ek, ec = zo.count_sorted(buf)
+        km = nat.Kmerizer(k)
+        km.set_baits(bs)
+        km.feed(data, is_fa)
+        s, nr = km.finish()
+        km.close()
+        ks, cc = s.fetch()
+        assert nr == nrec
+        assert len(ek) > 0 and [int(x) for x in ks] == ek and [int(c) for c in cc] == ec, name
+
+
 def test_kmerize_empty(nat):
     s, nr = run_kmerize(nat, 25, [(b">nothing\nACGT\n", True)])
     assert len(s) == 0 and nr == 1

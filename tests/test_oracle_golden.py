@@ -227,3 +227,13 @@ def test_cmd_kmerize_D(tmp_path, k, out, ins, d, S):
     o = str(tmp_path / out)
     zo.cmd_kmerize_D(k, o, [g(i) for i in ins], d, S)
     assert open(o, "rb").read() == rd(out)
+
+
+@pytest.mark.parametrize("k,out,ins,baits", [(25, "r1_C.k25", ["r1.fq"], "baits.fa"), (25, "g1_C.k25", ["g1.fa"], "baits.fa"),
+                                             (16, "mix_C.k16", ["r1.fq", "g1.fa"], "baits.fa"),
+                                             (25, "r1_Cself.k25", ["r1.fq"], "g1.fa")])
+def test_cmd_kmerize_C(tmp_path, k, out, ins, baits):
+    """capture mode (kmerize.py:478-483, :507-517) against the files the reference wrote"""
+    o = str(tmp_path / out)
+    zo.cmd_kmerize_C(k, o, [g(i) for i in ins], g(baits))
+    assert open(o, "rb").read() == rd(out)

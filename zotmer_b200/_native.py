@@ -32,6 +32,7 @@ SIGNATURES = {
     "zb_kmerize_open": (C.c_int, [C.c_int, C.c_int, C.POINTER(vp)]),
     "zb_kmerize_feed": (C.c_int, [vp, vp, C.c_size_t, C.c_int]),
     "zb_kmerize_feed_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_int]),
+    "zb_kmerize_set_baits": (C.c_int, [vp, vp]),
     "zb_kmerize_feed_codes_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_uint64]),
     "zb_kmerize_finish": (C.c_int, [vp, C.POINTER(vp), u64p]),
     "zb_kmerize_close": (C.c_int, [vp]),
@@ -334,6 +335,12 @@ class Kmerizer(object):
 
     def feed_dev(self, dptr, n, is_fasta):
         _check(lib().zb_kmerize_feed_dev(self.h, vp(dptr), n, 1 if is_fasta else 0))
+
+    def set_baits(self, baits):
+        """capture mode (`zot kmerize -C`): records fed from now on count only if they hold a k-mer of the KmerSet
+        `baits` (which must stay alive while this kmerizer is fed); None switches it off"""
+        self._baits = baits
+        _check(lib().zb_kmerize_set_baits(self.h, baits.h if baits is not None else None))
 
     def feed_codes_dev(self, dptr, n, n_records):
         _check(lib().zb_kmerize_feed_codes_dev(self.h, vp(dptr), n, n_records))

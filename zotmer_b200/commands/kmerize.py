@@ -35,10 +35,13 @@ from zotmer_b200.library.reads import isFasta, pieces
 import zotmer_b200.library.kmers as zotk
 
 
-def kmerizeFiles(K, inputs, device=0, verbose=False):
-    """-> (KmerSet with both strands, number of records).  kmerize.py:463-539."""
+def kmerizeFiles(K, inputs, device=0, verbose=False, baits=None):
+    """-> (KmerSet with both strands, number of records).  kmerize.py:463-539.
+    baits: KmerSet of the bait k-mers (-C): only records holding one of them contribute (kmerize.py:507-517)."""
     km = _native.Kmerizer(K, device)
     try:
+        if baits is not None:
+            km.set_baits(baits)
         for fn in inputs:
             data = readBytes(fn)
             fa = isFasta(fn)
@@ -51,6 +54,20 @@ def kmerizeFiles(K, inputs, device=0, verbose=False):
         km.close()
 
 
+def baitSet(K, fn, device=0):
+    """kmerize.py:478-483: B = set of the k-mers (both strands) of every record of the FASTA file `fn` (readFasta
+    whatever its suffix)."""
+    km = _native.Kmerizer(K, device)
+    try:
+        data = readBytes(fn)
+        for piece in pieces(data, True):
+            km.feed(piece, True)
+        (b, _) = km.finish()
+        return b
+    finally:
+        km.close()
+
+
 def main(argv):
     opts = docopt.docopt(__doc__, argv)
 
@@ -58,16 +75,19 @@ def main(argv):
     K = int(opts['<k>'])
     out = opts['<output>']
 
-    if opts['-C'] is not None:
-        # kmerize.py:507-517 (bait capture: whole reads are kept when one of their k-mers is a bait): a per-read
-        # decision, not built yet
-        print('zot kmerize: -C is not available in zotmer_b200', file=sys.stderr)
-        sys.exit(1)
-
     (kset, nr) = kmerizeFiles(K, opts['<input>'], verbose=verbose)
+    st = kset.stats()      # acgt counts EVERY k-mer, before any sub-sampling / capture (kmerize.py:492-493)
+
+    if opts['-C'] is not None and opts['-D'] is None:
+        # kmerize.py:507-517 (the -D branch comes first in the reference's if / elif chain): whole records are kept
+        # when one of their k-mers is a bait.  acgt still covers every record (above), hence the second pass.
+        baits = baitSet(K, opts['-C'])
+        kset.free()
+        (kset, nr) = kmerizeFiles(K, opts['<input>'], verbose=verbose, baits=baits)
+        baits.free()
+        st['hist'] = kset.stats()['hist']
 
     with zotk.kmers(out, 'w') as z:
-        st = kset.stats()      # acgt counts EVERY k-mer, before any sub-sampling (kmerize.py:492-493)
         if opts['-D'] is not None:
             # kmerize.py:494-506: a k-mer is kept iff sub(S, d, x) (basics.py:251-259) -- a function of the k-mer
             # alone (each strand is tested on its own), so filtering the counted set is the same as filtering

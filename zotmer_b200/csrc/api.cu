@@ -188,6 +188,7 @@ struct zb_kmerizer {
     size_t acc_n = 0;
     uint64_t n_records = 0;
     size_t max_pending = (size_t)1 << 29;
+    const zb_set* baits = nullptr;       // capture mode (`zot kmerize -C`): only records that hold one of these k-mers count
     uint64_t* adopted = nullptr;         // caller-owned key array that stands in for `pending` (multi-GPU receive buffer)
     size_t adopted_n = 0;
 };
@@ -293,13 +294,14 @@ static void feed_dev_impl(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is
     uint64_t n_rec = 0;
     {
         Stage st(c, "parse");
-        if (is_fasta) parse_fasta(c, d_raw, n, cd, &n_codes, &n_rec);
-        else parse_fastq(c, d_raw, n, cd, &n_codes, &n_rec);
+        if (is_fasta) parse_fasta(c, d_raw, n, cd, &n_codes, &n_rec, h->baits != nullptr);
+        else parse_fastq(c, d_raw, n, cd, &n_codes, &n_rec, h->baits != nullptr);
     }
     h->n_records += n_rec;
     if (n_codes == 0) return;
     const size_t padded = div_up(n_codes, EXTRACT_TILE) * EXTRACT_TILE + 32;
     ZB_CUDA(dev_memset(c, cd + n_codes, 4, padded - n_codes));
+    if (h->baits) capture_records(c, h->k, cd, n_codes, h->baits->k.get(), h->baits->n);
     extract_codes(h, cd, n_codes);
 }
 
@@ -393,6 +395,14 @@ int zb_kmerize_open(int k, int device, zb_kmerizer** out) {
         if (v >= (size_t)EXTRACT_TILE && v < ((size_t)1 << 30)) h->max_pending = v;
     }
     *out = h;
+    ZB_CATCH
+}
+
+int zb_kmerize_set_baits(zb_kmerizer* h, const zb_set* baits) {
+    ZB_TRY
+    if (!h) ZB_FAIL(ZB_E_ARG, "null handle");
+    if (baits && baits->c != h->c) ZB_FAIL(ZB_E_ARG, "the bait set must live in the kmerizer's context");
+    h->baits = baits;
     ZB_CATCH
 }
 

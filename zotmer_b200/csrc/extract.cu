@@ -127,6 +127,120 @@ void extract_canonical(Ctx* c, int k, const uint8_t* codes, size_t n, uint64_t* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// capture mode (`zot kmerize -C BAITS`, kmerize.py:478-483 and :507-517): `if found: buf.addList(xs)` -- a record
+// contributes ALL its k-mers iff one of them is a bait k-mer.  The bait set holds both strands of every bait k-mer, so
+// "x in B or rc(x) in B" is "canonical(x) in B".  Records are the stretches between codes 5 (parse_* with
+// mark_records); a record that is not captured is overwritten with 4s, and the ordinary extractor then runs on
+// what is left.  A rarely used mode: plain kernels, one thread per base.
+// ---------------------------------------------------------------------------------------------
+static constexpr int CP_THREADS = 256;
+static constexpr int CP_PER = 16;
+static constexpr int CP_TILE = CP_THREADS * CP_PER;
+
+__global__ void __launch_bounds__(CP_THREADS)
+capture_hit_kernel(int k, const uint8_t* __restrict__ codes, uint64_t n, const uint64_t* __restrict__ baits, uint64_t nbaits,
+                   uint8_t* __restrict__ hit) {
+    const uint64_t p = (uint64_t)blockIdx.x * CP_THREADS + threadIdx.x;
+    if (p >= n) return;
+    bool ok = true;
+    uint64_t fwd = 0, rc = 0;
+    for (int i = 0; i < k; i++) {   // the stream is padded with 4s behind n, so p + i never leaves it
+        const uint32_t cd = codes[p + i];
+        ok &= cd < 4u;
+        fwd = (fwd << 2) | (cd & 3u);
+        rc |= (uint64_t)(3u - (cd & 3u)) << (2 * i);
+    }
+    uint8_t h = 0;
+    if (ok) {
+        const uint64_t x = min(fwd, rc);
+        uint64_t lo = 0, hi = nbaits;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (baits[mid] < x) lo = mid + 1; else hi = mid;
+        }
+        h = (lo < nbaits && baits[lo] == x) ? 1 : 0;
+    }
+    hit[p] = h;
+}
+
+__global__ void __launch_bounds__(CP_THREADS)
+capture_count_kernel(const uint8_t* __restrict__ codes, uint64_t n, uint32_t* __restrict__ tile_seps) {
+    __shared__ uint32_t sm[CP_THREADS / 32 + 1];
+    const uint64_t p0 = (uint64_t)blockIdx.x * CP_TILE + (uint64_t)threadIdx.x * CP_PER;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < CP_PER; j++) cnt += (p0 + j < n && codes[p0 + j] == 5) ? 1u : 0u;
+    uint32_t tot;
+    block_excl_scan<CP_THREADS, uint32_t>(cnt, sm, &tot);
+    if (threadIdx.x == 0) tile_seps[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024)
+capture_scan_kernel(const uint32_t* __restrict__ tile_seps, uint32_t tiles, uint64_t* __restrict__ tile_base) {
+    __shared__ uint64_t sm[1024 / 32 + 1];
+    uint64_t carry = 0;
+    for (uint32_t b0 = 0; b0 < tiles; b0 += 1024) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint64_t v = (i < tiles) ? tile_seps[i] : 0;
+        uint64_t tot;
+        const uint64_t ex = block_excl_scan<1024, uint64_t>(v, sm, &tot);
+        if (i < tiles) tile_base[i] = carry + ex;
+        carry += tot;
+    }
+}
+
+// BLANK = false: found[record] = 1 for every record with a hit; BLANK = true: records without one become 4s.
+// record of position p = number of separators before p.
+template <bool BLANK>
+__global__ void __launch_bounds__(CP_THREADS)
+capture_apply_kernel(uint8_t* __restrict__ codes, uint64_t n, const uint64_t* __restrict__ tile_base,
+                     const uint8_t* __restrict__ hit, uint8_t* __restrict__ found) {
+    __shared__ uint32_t sm[CP_THREADS / 32 + 1];
+    const uint64_t p0 = (uint64_t)blockIdx.x * CP_TILE + (uint64_t)threadIdx.x * CP_PER;
+    uint8_t cd[CP_PER];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < CP_PER; j++) {
+        cd[j] = (p0 + j < n) ? codes[p0 + j] : (uint8_t)4;
+        cnt += (cd[j] == 5) ? 1u : 0u;
+    }
+    uint32_t tot;
+    uint64_t rec = tile_base[blockIdx.x] + block_excl_scan<CP_THREADS, uint32_t>(cnt, sm, &tot);
+#pragma unroll
+    for (int j = 0; j < CP_PER; j++) {
+        if (p0 + j < n) {
+            if (BLANK) {
+                if (cd[j] != 5 && !found[rec]) codes[p0 + j] = 4;
+            } else if (hit[p0 + j]) {
+                found[rec] = 1;
+            }
+        }
+        rec += (cd[j] == 5) ? 1u : 0u;
+    }
+}
+
+void capture_records(Ctx* c, int k, uint8_t* codes, size_t n, const uint64_t* baits, size_t nbaits) {
+    if (n == 0) return;
+    const uint32_t tiles = (uint32_t)div_up(n, CP_TILE);
+    DBuf<uint8_t> hit(c, n);
+    DBuf<uint32_t> tile_seps(c, tiles);
+    DBuf<uint64_t> tile_base(c, tiles);
+    DBuf<uint8_t> found(c, n + 2);   // at most one record per code
+    ZB_CUDA(dev_memset(c, found.get(), 0, n + 2));
+    Stage st(c, "capture");
+    capture_hit_kernel<<<(unsigned)div_up(n, CP_THREADS), CP_THREADS, 0, c->stream>>>(k, codes, n, baits, nbaits, hit.get());
+    ZB_LAUNCH_CHECK(c);
+    capture_count_kernel<<<tiles, CP_THREADS, 0, c->stream>>>(codes, n, tile_seps.get());
+    ZB_LAUNCH_CHECK(c);
+    capture_scan_kernel<<<1, 1024, 0, c->stream>>>(tile_seps.get(), tiles, tile_base.get());
+    ZB_LAUNCH_CHECK(c);
+    capture_apply_kernel<false><<<tiles, CP_THREADS, 0, c->stream>>>(codes, n, tile_base.get(), hit.get(), found.get());
+    ZB_LAUNCH_CHECK(c);
+    capture_apply_kernel<true><<<tiles, CP_THREADS, 0, c->stream>>>(codes, n, tile_base.get(), hit.get(), found.get());
+    ZB_LAUNCH_CHECK(c);
+}
+
+// ---------------------------------------------------------------------------------------------
 // multi-GPU routing: owner(key) = floor(mix64(key) * nranks / 2^64) -- the high bits of an
 // invertible 64-bit mix, so ownership is uniform even for low-complexity sequence.
 // ---------------------------------------------------------------------------------------------

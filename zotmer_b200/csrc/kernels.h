@@ -113,8 +113,12 @@ void allpairs_abc(Ctx* c, const std::vector<SetRef>& refs, uint64_t tile_begin, 
 // Raw FASTA/FASTQ bytes (device) -> dense base codes (0..3, 4 = break).  `codes` must have room for
 // n + 64 bytes.  Returns number of codes written and the number of records (synchronises).
 // Replaces file.py:19-52 (readFasta/readFastq) as used by reads.py:86-125.
-void parse_fastq(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n_codes, uint64_t* n_records);
-void parse_fasta(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n_codes, uint64_t* n_records);
+// mark_records: the code between two records is 5 instead of 4 (both are "no base" to the extractor), so that
+// capture_records can tell where a record ends.
+void parse_fastq(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n_codes, uint64_t* n_records,
+                 bool mark_records = false);
+void parse_fasta(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n_codes, uint64_t* n_records,
+                 bool mark_records = false);
 
 // ---- extract.cu ------------------------------------------------------------------------------
 // codes: device pointer to a buffer laid out as [32 bytes of 4][n codes][padding of 4 up to a
@@ -123,6 +127,10 @@ void parse_fasta(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n
 // basics.py:303-347.
 static const int EXTRACT_TILE = 4096;
 void extract_canonical(Ctx* c, int k, const uint8_t* codes, size_t n, uint64_t* out, unsigned long long* d_count);
+// `zot kmerize -C` (kmerize.py:478-483, :507-517): a record is kept, whole, iff one of its k-mers (either strand) is in
+// the bait set; every other record of the code stream (records delimited by code 5, see parse_*) is blanked out.
+// baits: sorted k-mers closed under reverse complement (a both-strand kmerize of the bait FASTA).
+void capture_records(Ctx* c, int k, uint8_t* codes, size_t n, const uint64_t* baits, size_t nbaits);
 // multi-GPU: same, but also tallies owner-bucket sizes (owner = mix64(key) range partition).
 void bucket_count(Ctx* c, const uint64_t* keys, size_t n, int nranks, unsigned long long* d_bucket_counts);
 void bucket_scatter(Ctx* c, const uint64_t* keys, size_t n, int nranks, unsigned long long* d_bucket_cursor,

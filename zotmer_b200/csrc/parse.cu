@@ -179,7 +179,7 @@ fq_scan_kernel(const FqTile* __restrict__ tiles, uint32_t ntiles, uint64_t* __re
 __global__ void __launch_bounds__(PA_THREADS)
 fastq_kernel(const uint8_t* __restrict__ raw, uint64_t n, const unsigned long long* __restrict__ scalars,
              uint8_t* __restrict__ codes, const uint64_t* __restrict__ tile_line0, const uint64_t* __restrict__ tile_out0,
-             unsigned long long* __restrict__ total_out) {
+             unsigned long long* __restrict__ total_out, bool mark) {
     __shared__ uint32_t s_nl[PA_ROWS * PA_WARPS];
     __shared__ uint32_t s_em[PA_ROWS * PA_WARPS];
     __shared__ uint32_t s_tot;
@@ -252,6 +252,13 @@ fastq_kernel(const uint8_t* __restrict__ raw, uint64_t n, const unsigned long lo
         uint32_t E = em[r];
         if (E) {
             uint32_t cw[4] = {codes4(v[r].x), codes4(v[r].y), codes4(v[r].z), codes4(v[r].w)};
+            if (mark) {   // the '\n' that ends a sequence line becomes 5 = "a record ends here" (capture mode)
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t mm = (nlm[r] >> (4 * i)) & 0xfu;
+                    cw[i] |= (mm & 1u) | ((mm & 2u) << 7) | ((mm & 4u) << 14) | ((mm & 8u) << 21);
+                }
+            }
             uint8_t* dst = s_stage + mis + s_em[r * PA_WARPS + warp] + emx[r];
             if (E == 0xffffu) {
 #pragma unroll
@@ -280,7 +287,7 @@ fastq_kernel(const uint8_t* __restrict__ raw, uint64_t n, const unsigned long lo
     }
 }
 
-void parse_fastq(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n_codes, uint64_t* n_records) {
+void parse_fastq(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n_codes, uint64_t* n_records, bool mark_records) {
     *n_codes = 0;
     *n_records = 0;
     if (n == 0) return;
@@ -295,7 +302,7 @@ void parse_fastq(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n
     ZB_LAUNCH_CHECK(c);
     fq_scan_kernel<<<1, 1024, 0, c->stream>>>(info.get(), tiles, line0, out0, scalars);
     ZB_LAUNCH_CHECK(c);
-    fastq_kernel<<<tiles, PA_THREADS, 0, c->stream>>>(raw, n, scalars, codes, line0, out0, scalars + 1);
+    fastq_kernel<<<tiles, PA_THREADS, 0, c->stream>>>(raw, n, scalars, codes, line0, out0, scalars + 1, mark_records);
     ZB_LAUNCH_CHECK(c);
     ZB_CUDA(read_back(c, scalars, 16));
     uint8_t last = 0;
@@ -314,7 +321,7 @@ void parse_fastq(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n
 __global__ void __launch_bounds__(PA_THREADS)
 fasta_kernel(const uint8_t* __restrict__ raw, uint64_t n, uint8_t* __restrict__ codes, uint32_t* __restrict__ st_state,
              uint64_t* __restrict__ st_out, uint32_t* __restrict__ ticket, uint64_t* __restrict__ total_out,
-             unsigned long long* __restrict__ n_records) {
+             unsigned long long* __restrict__ n_records, uint32_t brk) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_cell[PA_ROWS * PA_WARPS];   // inclusive transfer map per (row, warp), then exclusive
     __shared__ uint32_t s_bcell[PA_ROWS * PA_WARPS];  // backward (gb, pb) per cell
@@ -453,7 +460,7 @@ fasta_kernel(const uint8_t* __restrict__ raw, uint64_t n, uint8_t* __restrict__ 
         for (int b = 0; b < 16; b++) {
             const bool in = off + b < n;
             if (in && ((emit >> b) & 1u)) {
-                const uint32_t cd = ((p.HS >> b) & 1u) ? 4u : code_of(byte_of(v[r], b));
+                const uint32_t cd = ((p.HS >> b) & 1u) ? brk : code_of(byte_of(v[r], b));
                 a |= (uint64_t)cd << (4 * m);
                 m++;
             }
@@ -492,7 +499,7 @@ fasta_kernel(const uint8_t* __restrict__ raw, uint64_t n, uint8_t* __restrict__ 
     }
 }
 
-void parse_fasta(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n_codes, uint64_t* n_records) {
+void parse_fasta(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n_codes, uint64_t* n_records, bool mark_records) {
     *n_codes = 0;
     *n_records = 0;
     if (n == 0) return;
@@ -504,7 +511,7 @@ void parse_fasta(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n
     uint64_t* total = st.get() + 2 * (size_t)tiles;
     unsigned long long* nrec = reinterpret_cast<unsigned long long*>(st.get() + 2 * (size_t)tiles + 1);
     uint32_t* ticket = reinterpret_cast<uint32_t*>(st.get() + 2 * (size_t)tiles + 2);
-    fasta_kernel<<<tiles, PA_THREADS, 0, c->stream>>>(raw, n, codes, st_state, st_out, ticket, total, nrec);
+    fasta_kernel<<<tiles, PA_THREADS, 0, c->stream>>>(raw, n, codes, st_state, st_out, ticket, total, nrec, mark_records ? 5u : 4u);
     ZB_LAUNCH_CHECK(c);
     ZB_CUDA(read_back(c, total, 16));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
