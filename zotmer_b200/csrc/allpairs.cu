@@ -9,7 +9,7 @@
 //   * the sets are cut into blocks of 32; a tile is a pair of blocks (bi <= bj): 32 sets on the diagonal (the 496
 //     pairs inside the block), 64 sets off it (the 1024 pairs across the two blocks);
 //   * the key space is cut into 2^cb buckets by the top bits of the key (bucket b of every set holds the same key
-//     range, so intersections never cross buckets), cb such that a tile's sets together hold <= 4096 keys per
+//     range, so intersections never cross buckets), cb such that a tile's sets together hold <= 2048 keys per
 //     bucket; ap_offsets_kernel finds every bucket in every set with one streaming pass;
 //   * ap_bucket_kernel: a CTA gathers the bucket's slice of each of the tile's sets into shared memory and
 //     inserts every key into a shared-memory hash table -- the first entry of a key is its head and collects a
@@ -32,12 +32,12 @@ namespace zb {
 
 static constexpr int AB_S = 32;               // sets per block
 static constexpr int AB_KS = 8;               // key-range shards per tile
-static constexpr int AB_THREADS = 512;
+static constexpr int AB_THREADS = 256;
 static constexpr int AB_WARPS = AB_THREADS / 32;
 static constexpr int AB_PER = 8;
 static constexpr int AB_CAP = AB_THREADS * AB_PER;   // keys of one bucket, all sets of the tile together
 static constexpr int AB_HASH = 2 * AB_CAP;
-static constexpr int AB_HASH_BITS = 13;
+static constexpr int AB_HASH_BITS = 12;
 #define AB_EMPTY 0xffffffffu
 
 // off[b * nsets + i] = first index of set i whose key >> shift is >= b   (b = 0 .. nb); `off` zeroed by the caller.
@@ -100,8 +100,10 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x) {
 
 // Persistent: CTA c takes the work items [c W / G, (c + 1) W / G) -- consecutive buckets of (mostly) one tile, so its
 // reads of every set are sequential and its pair counters are flushed once.
-// Shared memory: keys 32 KB + hash table 32 KB + 2 x masks 16 KB + set index 4 KB + counters 4 KB + slice tables.
-__global__ void __launch_bounds__(AB_THREADS, 2)
+// Shared memory: keys 16 KB + hash table 16 KB + 2 x masks 8 KB + set index 2 KB + counters 4 KB + slice tables = 55 KB
+// -> 4 CTAs of 256 threads per SM (2 CTAs of 512 threads with 4096-key buckets: 4.1 instead of 3.2 ms for 32 sets --
+// barrier and load-latency stalls, 29 % + 28 %, overlap better across four independent CTAs).
+__global__ void __launch_bounds__(AB_THREADS, 4)
 ap_bucket_kernel(const SetRef* __restrict__ sets, int nsets, const uint32_t* __restrict__ off, const ApSeg* __restrict__ segs,
                  uint32_t nsegs, uint64_t W, unsigned long long* __restrict__ isect) {
     extern __shared__ __align__(16) unsigned char ab_raw[];
@@ -356,7 +358,7 @@ static bool allpairs_buckets(Ctx* c, const SetRef* d_sets, const std::vector<Set
         ZB_CUDA(dev_memset(c, d_isect.get(), 0, npairs * 8));
         const size_t smem = (size_t)AB_CAP * 8 + (size_t)AB_HASH * 4 + (size_t)2 * AB_CAP * 4 + (size_t)AB_S * AB_S * 4 + AB_CAP;
         ZB_CUDA(cudaFuncSetAttribute(ap_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const unsigned grid = (unsigned)std::min<uint64_t>(W, (uint64_t)c->sm_count * 2);
+        const unsigned grid = (unsigned)std::min<uint64_t>(W, (uint64_t)c->sm_count * 4);
         {
             Stage st(c, "allpairs");
             ap_bucket_kernel<<<grid, AB_THREADS, smem, c->stream>>>(d_sets, nsets, off.get(), d_segs.get(), (uint32_t)segs.size(), W,
