@@ -255,7 +255,7 @@ __device__ __forceinline__ int owner_of(uint64_t key, int nranks) {
 }
 
 __global__ void __launch_bounds__(256)
-bucket_count_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, unsigned long long* __restrict__ counts) {
+owner_count_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, unsigned long long* __restrict__ counts) {
     __shared__ unsigned int sc[64];
     if (threadIdx.x < 64) sc[threadIdx.x] = 0;
     __syncthreads();
@@ -266,7 +266,7 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, u
 }
 
 __global__ void __launch_bounds__(256)
-bucket_scatter_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, unsigned long long* __restrict__ cursor,
+owner_scatter_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, unsigned long long* __restrict__ cursor,
                       uint64_t* __restrict__ out) {
     // per-CTA: count per owner, reserve ranges with one atomic per owner, then place.
     __shared__ unsigned int sc[64];
@@ -367,13 +367,13 @@ void bucket_count(Ctx* c, const uint64_t* keys, size_t n, int nranks, unsigned l
     if (n == 0) return;
     if (nranks > 64) ZB_FAIL(ZB_E_ARG, "bucket_count: nranks > 64");
     int blocks = (int)std::min<size_t>((size_t)c->sm_count * 8, div_up(n, 256));
-    bucket_count_kernel<<<blocks, 256, 0, c->stream>>>(keys, n, nranks, d_counts);
+    owner_count_kernel<<<blocks, 256, 0, c->stream>>>(keys, n, nranks, d_counts);
     ZB_LAUNCH_CHECK(c);
 }
 
 void bucket_scatter(Ctx* c, const uint64_t* keys, size_t n, int nranks, unsigned long long* d_cursor, uint64_t* out) {
     if (n == 0) return;
-    bucket_scatter_kernel<<<(unsigned)div_up(n, 256 * 8), 256, 0, c->stream>>>(keys, n, nranks, d_cursor, out);
+    owner_scatter_kernel<<<(unsigned)div_up(n, 256 * 8), 256, 0, c->stream>>>(keys, n, nranks, d_cursor, out);
     ZB_LAUNCH_CHECK(c);
 }
 
