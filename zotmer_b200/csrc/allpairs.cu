@@ -45,16 +45,7 @@ static constexpr int AB_HASH_BITS = 12;
 // its own (a binary search per (bucket, set) misses the TLB on nearly every probe: 3.8 x slower, nwaymerge.cu).
 __global__ void __launch_bounds__(256)
 ap_offsets_kernel(const SetRef* __restrict__ sets, int nsets, int shift, uint32_t nb, uint32_t* __restrict__ off) {
-    const int i = blockIdx.y;
-    const uint64_t n = sets[i].n;
-    const uint64_t* __restrict__ k = sets[i].k;
-    for (uint64_t j = (uint64_t)blockIdx.x * 256 + threadIdx.x; j < n; j += (uint64_t)gridDim.x * 256) {
-        const uint64_t cur = (shift < 64) ? (__ldg(k + j) >> shift) : 0ull;
-        const uint64_t prev = (shift < 64 && j > 0) ? (__ldg(k + j - 1) >> shift) : 0ull;
-        for (uint64_t b = (j > 0) ? prev + 1 : 1; b <= cur; b++) off[b * nsets + i] = (uint32_t)j;
-        if (j == n - 1)
-            for (uint64_t b = cur + 1; b <= nb; b++) off[b * nsets + i] = (uint32_t)n;
-    }
+    bucket_offsets_body(sets, nsets, shift, nb, off);
 }
 
 // largest number of keys one block of 32 sets holds in one bucket; one warp per (bucket, block)
@@ -70,12 +61,26 @@ ap_blockmax_kernel(const uint32_t* __restrict__ off, int nsets, uint32_t nb, uin
     if (lane_id() == 0 && v) atomicMax(mx, v);
 }
 
-// upper-triangular (diagonal included) block pair number t -> (bi, bj), bi <= bj < nblk
-__host__ __device__ inline void tile_to_blocks(uint64_t t, uint64_t nblk, uint32_t& bi, uint32_t& bj) {
+// Tiles.  More than two blocks: upper-triangular (diagonal included) block pair number t -> (bi, bj), bi <= bj < nblk;
+// a diagonal tile counts the pairs inside its block (AP_WITHIN_A), the others the pairs across (AP_CROSS).  Up to two
+// blocks (<= 64 sets): ONE tile does everything in one pass over the sets -- inside the first block, inside the second
+// and across (as three tiles the sets would be read twice).
+#define AP_WITHIN_A 1u
+#define AP_WITHIN_B 2u
+#define AP_CROSS 4u
+__host__ __device__ inline uint64_t tile_count(uint64_t nblk) { return nblk <= 2 ? 1 : nblk * (nblk + 1) / 2; }
+__host__ __device__ inline void tile_to_blocks(uint64_t t, uint64_t nblk, uint32_t& bi, uint32_t& bj, uint32_t& flags) {
+    if (nblk <= 2) {
+        bi = 0;
+        bj = (uint32_t)(nblk - 1);
+        flags = (nblk == 2) ? (AP_WITHIN_A | AP_WITHIN_B | AP_CROSS) : AP_WITHIN_A;
+        return;
+    }
     uint64_t r = 0, start = 0;
     while (start + (nblk - r) <= t) { start += nblk - r; r++; }
     bi = (uint32_t)r;
     bj = (uint32_t)(r + (t - start));
+    flags = (bi == bj) ? AP_WITHIN_A : AP_CROSS;
 }
 
 // a run of buckets of one tile, and where it starts in the flattened list of all (tile, bucket) work items
@@ -83,6 +88,7 @@ struct ApSeg {
     uint32_t bi, bj;
     uint32_t b0, b1;
     uint64_t wstart;
+    uint32_t flags, pad;
 };
 
 // 32 x 32 bit-matrix transpose across a warp: lane l gives row l, gets column l (bit r = bit l of lane r's row)
@@ -103,16 +109,22 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x) {
 // Shared memory: keys 16 KB + hash table 16 KB + 2 x masks 8 KB + set index 2 KB + counters 4 KB + slice tables = 55 KB
 // -> 4 CTAs of 256 threads per SM (2 CTAs of 512 threads with 4096-key buckets: 4.1 instead of 3.2 ms for 32 sets --
 // barrier and load-latency stalls, 29 % + 28 %, overlap better across four independent CTAs).
-__global__ void __launch_bounds__(AB_THREADS, 4)
+template <bool FOLD>   // FOLD: the one tile of <= 64 sets (inside both blocks + across); else diagonal and cross tiles
+__global__ void __launch_bounds__(AB_THREADS, FOLD ? 3 : 4)
 ap_bucket_kernel(const SetRef* __restrict__ sets, int nsets, const uint32_t* __restrict__ off, const ApSeg* __restrict__ segs,
                  uint32_t nsegs, uint64_t W, unsigned long long* __restrict__ isect) {
+    constexpr int two_acc = FOLD ? 1 : 0;
     extern __shared__ __align__(16) unsigned char ab_raw[];
     uint64_t* sk = reinterpret_cast<uint64_t*>(ab_raw);                  // [AB_CAP] gathered keys
     uint32_t* table = reinterpret_cast<uint32_t*>(sk + AB_CAP);          // [AB_HASH] position of a key's head
     uint32_t* mA = table + AB_HASH;                                      // [AB_CAP] at a head: sets of block bi holding the key
     uint32_t* mB = mA + AB_CAP;                                          // [AB_CAP]            sets of block bj (off the diagonal)
-    uint32_t* acc = mB + AB_CAP;                                         // [32 * 32] shared keys per pair of the tile
-    uint8_t* sb = reinterpret_cast<uint8_t*>(acc + AB_S * AB_S);         // [AB_CAP] which of the tile's sets an entry came from
+    // shared keys per pair of the tile.  acc_w[i * 32 + j]: i < j = pair (i, j) inside block bi, i > j = pair (j, i)
+    // inside block bj; acc_x[i * 32 + j] = set i of block bi with set j of block bj (the same array when a tile only
+    // counts across)
+    uint32_t* acc_w = mB + AB_CAP;                                       // [32 * 32]
+    uint32_t* acc_x = two_acc ? acc_w + AB_S * AB_S : acc_w;             // [32 * 32]
+    uint8_t* sb = reinterpret_cast<uint8_t*>(acc_w + (two_acc ? 2 : 1) * AB_S * AB_S);   // [AB_CAP] which of the tile's sets an entry came from
     __shared__ uint32_t spre[2 * AB_S + 1];                              // slice starts inside the bucket
     __shared__ uint32_t soff[2 * AB_S];                                  // slice starts inside the sets
 
@@ -128,7 +140,7 @@ ap_bucket_kernel(const SetRef* __restrict__ sets, int nsets, const uint32_t* __r
         }
         s = lo;
     }
-    for (int idx = tid; idx < AB_S * AB_S; idx += AB_THREADS) acc[idx] = 0;
+    for (int idx = tid; idx < (two_acc ? 2 : 1) * AB_S * AB_S; idx += AB_THREADS) acc_w[idx] = 0;
     ApSeg seg = segs[s];
     uint64_t seg_end = seg.wstart + (seg.b1 - seg.b0);
 
@@ -136,13 +148,25 @@ ap_bucket_kernel(const SetRef* __restrict__ sets, int nsets, const uint32_t* __r
         // ---- tile change (or the end of my range): flush the pair counters
         if (wi == w1 || wi >= seg_end) {
             __syncthreads();
-            const bool diag = (seg.bi == seg.bj);
             for (int idx = tid; idx < AB_S * AB_S; idx += AB_THREADS) {
-                const uint32_t v = acc[idx];
-                acc[idx] = 0;
-                const uint64_t gi = (uint64_t)seg.bi * AB_S + (idx >> 5), gj = (uint64_t)seg.bj * AB_S + (idx & 31);
-                if (v && gi < gj && gj < (uint64_t)nsets && (!diag || (idx >> 5) < (idx & 31)))
-                    atomicAdd(&isect[gi * (2ull * nsets - gi - 1) / 2 + (gj - gi - 1)], (unsigned long long)v);
+                const uint32_t i = idx >> 5, j = idx & 31;
+                const uint32_t fl = FOLD ? (AP_WITHIN_A | AP_WITHIN_B | AP_CROSS) : (seg.bi == seg.bj ? AP_WITHIN_A : AP_CROSS);
+                if (fl & (AP_WITHIN_A | AP_WITHIN_B)) {
+                    const uint32_t v = acc_w[idx];
+                    acc_w[idx] = 0;
+                    // upper triangle: inside block bi; lower triangle: inside block bj
+                    const uint64_t gi = (i < j) ? (uint64_t)seg.bi * AB_S + i : (uint64_t)seg.bj * AB_S + j;
+                    const uint64_t gj = (i < j) ? (uint64_t)seg.bi * AB_S + j : (uint64_t)seg.bj * AB_S + i;
+                    if (v && i != j && gj < (uint64_t)nsets)
+                        atomicAdd(&isect[gi * (2ull * nsets - gi - 1) / 2 + (gj - gi - 1)], (unsigned long long)v);
+                }
+                if (fl & AP_CROSS) {
+                    const uint32_t v = acc_x[idx];
+                    acc_x[idx] = 0;
+                    const uint64_t gi = (uint64_t)seg.bi * AB_S + i, gj = (uint64_t)seg.bj * AB_S + j;
+                    if (v && gj < (uint64_t)nsets)
+                        atomicAdd(&isect[gi * (2ull * nsets - gi - 1) / 2 + (gj - gi - 1)], (unsigned long long)v);
+                }
             }
             if (wi == w1) break;
             while (wi >= seg_end) {
@@ -152,9 +176,10 @@ ap_bucket_kernel(const SetRef* __restrict__ sets, int nsets, const uint32_t* __r
             }
         }
         const uint32_t b = seg.b0 + (uint32_t)(wi - seg.wstart);
-        const bool diag = (seg.bi == seg.bj);
+        const uint32_t flags = FOLD ? (AP_WITHIN_A | AP_WITHIN_B | AP_CROSS) : (seg.bi == seg.bj ? AP_WITHIN_A : AP_CROSS);
+        const bool two = (flags & (AP_WITHIN_B | AP_CROSS)) != 0;                 // the tile has a second block
         const int nA = min(AB_S, nsets - (int)seg.bi * AB_S);
-        const int nT = nA + (diag ? 0 : min(AB_S, nsets - (int)seg.bj * AB_S));   // sets of the tile
+        const int nT = nA + (two ? min(AB_S, nsets - (int)seg.bj * AB_S) : 0);    // sets of the tile
         __syncthreads();   // the previous bucket (and the flush) are done with the shared arrays
 
         // ---- where every set's slice of this bucket starts
@@ -247,29 +272,34 @@ ap_bucket_kernel(const SetRef* __restrict__ sets, int nsets, const uint32_t* __r
         for (int c0 = (int)warp * 32; c0 < m; c0 += AB_THREADS) {
             const int q = c0 + (int)lane;
             const uint32_t a = (q < m) ? mA[q] : 0u;
-            const uint32_t bb = (q < m && !diag) ? mB[q] : 0u;
-            const bool useful = diag ? (a & (a - 1)) != 0 : (a != 0 && bb != 0);
+            const uint32_t bb = (q < m && two) ? mB[q] : 0u;
+            const bool useful = ((flags & AP_WITHIN_A) && (a & (a - 1)) != 0) || ((flags & AP_WITHIN_B) && (bb & (bb - 1)) != 0) ||
+                                ((flags & AP_CROSS) && a != 0 && bb != 0);
             if (!__any_sync(0xffffffffu, useful)) continue;
-            const uint32_t colA = warp_transpose32(useful ? a : 0u);
-            if (diag) {
+            const uint32_t colA = warp_transpose32(a);
+            const uint32_t colB = two ? warp_transpose32(bb) : 0u;
+            if (flags & (AP_WITHIN_A | AP_WITHIN_B)) {
                 // pairs (l, l + d mod 32), d = 1 .. 16: every unordered pair once
 #pragma unroll
                 for (int d = 1; d <= 16; d++) {
-                    const uint32_t other = __shfl_sync(0xffffffffu, colA, (lane + d) & 31);
-                    const uint32_t cnt = __popc(colA & other);
-                    if (cnt && (d < 16 || lane < 16)) {
-                        const uint32_t o = (lane + d) & 31;
-                        atomicAdd(&acc[min(lane, o) * 32 + max(lane, o)], cnt);
+                    const uint32_t o = (lane + d) & 31;
+                    const uint32_t oa = __shfl_sync(0xffffffffu, colA, o);
+                    const uint32_t ob = __shfl_sync(0xffffffffu, colB, o);
+                    if (d < 16 || lane < 16) {
+                        const uint32_t lo = min(lane, o), hi = max(lane, o);
+                        const uint32_t ca = __popc(colA & oa), cbb = __popc(colB & ob);
+                        if (ca && (flags & AP_WITHIN_A)) atomicAdd(&acc_w[lo * 32 + hi], ca);
+                        if (cbb && (flags & AP_WITHIN_B)) atomicAdd(&acc_w[hi * 32 + lo], cbb);
                     }
                 }
-            } else {
-                const uint32_t colB = warp_transpose32(useful ? bb : 0u);
+            }
+            if (flags & AP_CROSS) {
 #pragma unroll
                 for (int d = 0; d < 32; d++) {
                     const uint32_t o = (lane + d) & 31;
                     const uint32_t other = __shfl_sync(0xffffffffu, colB, o);
                     const uint32_t cnt = __popc(colA & other);
-                    if (cnt) atomicAdd(&acc[lane * 32 + o], cnt);
+                    if (cnt) atomicAdd(&acc_x[lane * 32 + o], cnt);
                 }
             }
         }
@@ -277,8 +307,24 @@ ap_bucket_kernel(const SetRef* __restrict__ sets, int nsets, const uint32_t* __r
 }
 
 uint64_t allpairs_tiles(int nsets) {
-    const uint64_t nblk = div_up((size_t)nsets, AB_S);
-    return nblk * (nblk + 1) / 2 * AB_KS;
+    return tile_count(div_up((size_t)nsets, AB_S)) * AB_KS;
+}
+
+// the set pairs (i < j) a tile covers
+static void tile_pairs(uint64_t t, uint32_t nblk, int nsets, std::vector<uint32_t>& I, std::vector<uint32_t>& J) {
+    uint32_t bi, bj, flags;
+    tile_to_blocks(t, nblk, bi, bj, flags);
+    const uint32_t a0 = bi * AB_S, a1 = std::min<uint32_t>((bi + 1) * AB_S, nsets);
+    const uint32_t b0 = bj * AB_S, b1 = std::min<uint32_t>((bj + 1) * AB_S, nsets);
+    if (flags & AP_WITHIN_A)
+        for (uint32_t i = a0; i < a1; i++)
+            for (uint32_t j = i + 1; j < a1; j++) { I.push_back(i); J.push_back(j); }
+    if (flags & AP_CROSS)
+        for (uint32_t i = a0; i < a1; i++)
+            for (uint32_t j = b0; j < b1; j++) { I.push_back(i); J.push_back(j); }
+    if (flags & AP_WITHIN_B)
+        for (uint32_t i = b0; i < b1; i++)
+            for (uint32_t j = i + 1; j < b1; j++) { I.push_back(i); J.push_back(j); }
 }
 
 // first bucket of key-range shard s (s = 0 .. AB_KS) when the key space is cut into nb buckets
@@ -318,7 +364,7 @@ static bool allpairs_buckets(Ctx* c, const SetRef* d_sets, const std::vector<Set
         ZB_CUDA(dev_memset(c, off.get(), 0, (noff + 2) * 4));
         {
             Stage st(c, "allpairs_offsets");
-            const dim3 grid((unsigned)std::min<size_t>(std::max<size_t>(div_up(nmax, 256 * 8), 1), 65535), (unsigned)nsets);
+            const dim3 grid((unsigned)std::min<size_t>(std::max<size_t>(div_up(nmax, 256 * 2 * 8), 1), 65535), (unsigned)nsets);
             ap_offsets_kernel<<<grid, 256, 0, c->stream>>>(d_sets, nsets, key_bits - cb, nb, off.get());
             ZB_LAUNCH_CHECK(c);
             ap_blockmax_kernel<<<(unsigned)div_up((size_t)nb * nblk, 8), 256, 0, c->stream>>>(off.get(), nsets, nb, nblk, d_mx);
@@ -341,7 +387,8 @@ static bool allpairs_buckets(Ctx* c, const SetRef* d_sets, const std::vector<Set
     for (uint64_t t = ub / AB_KS; t <= (ue - 1) / AB_KS; t++) {
         const uint64_t s0 = std::max(ub, t * AB_KS) - t * AB_KS, s1 = std::min(ue, (t + 1) * AB_KS) - t * AB_KS;
         ApSeg sg;
-        tile_to_blocks(t, nblk, sg.bi, sg.bj);
+        sg.pad = 0;
+        tile_to_blocks(t, nblk, sg.bi, sg.bj, sg.flags);
         sg.b0 = (uint32_t)std::min<uint64_t>(shard_bucket(s0, nb), nb);
         sg.b1 = (uint32_t)std::min<uint64_t>(shard_bucket(s1, nb), nb);
         sg.wstart = W;
@@ -356,13 +403,19 @@ static bool allpairs_buckets(Ctx* c, const SetRef* d_sets, const std::vector<Set
         DBuf<uint64_t> d_isect(c, npairs);
         ZB_CUDA(cudaMemcpyAsync(d_segs.get(), segs.data(), segs.size() * sizeof(ApSeg), cudaMemcpyHostToDevice, c->stream));
         ZB_CUDA(dev_memset(c, d_isect.get(), 0, npairs * 8));
-        const size_t smem = (size_t)AB_CAP * 8 + (size_t)AB_HASH * 4 + (size_t)2 * AB_CAP * 4 + (size_t)AB_S * AB_S * 4 + AB_CAP;
-        ZB_CUDA(cudaFuncSetAttribute(ap_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const unsigned grid = (unsigned)std::min<uint64_t>(W, (uint64_t)c->sm_count * 4);
+        const int two_acc = (nblk == 2) ? 1 : 0;   // the one tile of <= 64 sets counts inside both blocks and across
+        const size_t smem = (size_t)AB_CAP * 8 + (size_t)AB_HASH * 4 + (size_t)2 * AB_CAP * 4 + (size_t)(1 + two_acc) * AB_S * AB_S * 4 + AB_CAP;
+        const unsigned grid = (unsigned)std::min<uint64_t>(W, (uint64_t)c->sm_count * (two_acc ? 3 : 4));
         {
             Stage st(c, "allpairs");
-            ap_bucket_kernel<<<grid, AB_THREADS, smem, c->stream>>>(d_sets, nsets, off.get(), d_segs.get(), (uint32_t)segs.size(), W,
-                                                                     reinterpret_cast<unsigned long long*>(d_isect.get()));
+            unsigned long long* d_is = reinterpret_cast<unsigned long long*>(d_isect.get());
+            if (two_acc) {
+                ZB_CUDA(cudaFuncSetAttribute(ap_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ap_bucket_kernel<true><<<grid, AB_THREADS, smem, c->stream>>>(d_sets, nsets, off.get(), d_segs.get(), (uint32_t)segs.size(), W, d_is);
+            } else {
+                ZB_CUDA(cudaFuncSetAttribute(ap_bucket_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ap_bucket_kernel<false><<<grid, AB_THREADS, smem, c->stream>>>(d_sets, nsets, off.get(), d_segs.get(), (uint32_t)segs.size(), W, d_is);
+            }
             ZB_LAUNCH_CHECK(c);
         }
         ZB_CUDA(cudaMemcpyAsync(isect.data(), d_isect.get(), npairs * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -376,17 +429,17 @@ static bool allpairs_buckets(Ctx* c, const SetRef* d_sets, const std::vector<Set
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     for (uint64_t t = ub / AB_KS; t <= (ue - 1) / AB_KS; t++) {
         const uint64_t s0 = std::max(ub, t * AB_KS) - t * AB_KS, s1 = std::min(ue, (t + 1) * AB_KS) - t * AB_KS;
-        uint32_t bi, bj;
-        tile_to_blocks(t, nblk, bi, bj);
-        for (uint64_t i = (uint64_t)bi * AB_S; i < std::min<uint64_t>((uint64_t)(bi + 1) * AB_S, nsets); i++)
-            for (uint64_t j = std::max<uint64_t>((uint64_t)bj * AB_S, i + 1); j < std::min<uint64_t>((uint64_t)(bj + 1) * AB_S, nsets); j++) {
-                const uint64_t p = i * (2ull * nsets - i - 1) / 2 + (j - i - 1);
-                const uint64_t a = isect[p];
-                const uint64_t ni = rows[s1 * nsets + i] - rows[s0 * nsets + i], nj = rows[s1 * nsets + j] - rows[s0 * nsets + j];
-                abc_host[3 * p] = a;
-                abc_host[3 * p + 1] = ni - a;
-                abc_host[3 * p + 2] = nj - a;
-            }
+        std::vector<uint32_t> I, J;
+        tile_pairs(t, nblk, nsets, I, J);
+        for (size_t q = 0; q < I.size(); q++) {
+            const uint64_t i = I[q], j = J[q];
+            const uint64_t p = i * (2ull * nsets - i - 1) / 2 + (j - i - 1);
+            const uint64_t a = isect[p];
+            const uint64_t ni = rows[s1 * nsets + i] - rows[s0 * nsets + i], nj = rows[s1 * nsets + j] - rows[s0 * nsets + j];
+            abc_host[3 * p] = a;
+            abc_host[3 * p + 1] = ni - a;
+            abc_host[3 * p + 2] = nj - a;
+        }
     }
     return true;
 }
@@ -418,15 +471,7 @@ void allpairs_abc(Ctx* c, const std::vector<SetRef>& refs, uint64_t unit_begin, 
     // skewed key space: pair-at-a-time merge path (setops.cu); a pair goes, whole, to the first shard of its tile
     memset(abc_host, 0, npairs * 3 * 8);
     std::vector<uint32_t> I, J;
-    for (uint64_t t = div_up(unit_begin, AB_KS); t * AB_KS < unit_end; t++) {
-        uint32_t bi, bj;
-        tile_to_blocks(t, nblk, bi, bj);
-        for (uint64_t i = (uint64_t)bi * AB_S; i < std::min<uint64_t>((uint64_t)(bi + 1) * AB_S, nsets); i++)
-            for (uint64_t j = std::max<uint64_t>((uint64_t)bj * AB_S, i + 1); j < std::min<uint64_t>((uint64_t)(bj + 1) * AB_S, nsets); j++) {
-                I.push_back((uint32_t)i);
-                J.push_back((uint32_t)j);
-            }
-    }
+    for (uint64_t t = div_up(unit_begin, AB_KS); t * AB_KS < unit_end; t++) tile_pairs(t, nblk, nsets, I, J);
     if (I.empty()) return;
     std::vector<uint64_t> tmp(I.size() * 3);
     pairs_abc_host(c, refs, I.data(), J.data(), I.size(), tmp.data());

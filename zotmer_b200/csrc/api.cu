@@ -70,6 +70,7 @@ __global__ void readback_kernel(const uint32_t* __restrict__ src, uint32_t* __re
 cudaError_t read_back(Ctx* c, const void* d_src, size_t bytes) {
     if (bytes > 128 || (bytes & 3)) return cudaErrorInvalidValue;
     readback_kernel<<<1, 32, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(d_src), c->d_h_scalars, (int)(bytes / 4));
+    c->launches++;
     return cudaGetLastError();
 }
 
@@ -95,6 +96,7 @@ cudaError_t dev_memset(Ctx* c, void* p, int value, size_t bytes) {
     if (bytes == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)std::min<size_t>((size_t)c->sm_count * 8, div_up(std::max<size_t>(bytes / 16, 32), 256));
     fill_kernel<<<blocks, 256, 0, c->stream>>>(reinterpret_cast<uint8_t*>(p), (uint8_t)value, bytes);
+    c->launches++;
     return cudaGetLastError();
 }
 
@@ -108,6 +110,7 @@ cudaError_t dev_copy(Ctx* c, void* dst, const void* src, size_t bytes) {
     else if (unit == 8) copy_kernel<uint64_t><<<blocks, 256, 0, c->stream>>>((uint64_t*)dst, (const uint64_t*)src, n);
     else if (unit == 4) copy_kernel<uint32_t><<<blocks, 256, 0, c->stream>>>((uint32_t*)dst, (const uint32_t*)src, n);
     else copy_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((uint8_t*)dst, (const uint8_t*)src, n);
+    c->launches++;
     return cudaGetLastError();
 }
 

@@ -204,6 +204,52 @@ __device__ __forceinline__ T block_excl_scan(T v, T* smem, T* total) {
     return r;
 }
 
+// ---- bucket offsets of sorted key arrays: off[b * nsets + i] = first index of set i whose key >> shift is >= b
+// (b = 0 .. nb; `off` zeroed by the caller; blockIdx.y = set).  One streaming pass over the keys: element j closes
+// every bucket between its predecessor's and its own.  Two keys per thread (one 16-byte load), the predecessor of
+// the first one comes from the neighbouring lane.  Ref = any struct with members `k` (sorted u64 keys) and `n`.
+template <typename Ref>
+__device__ __forceinline__ void bucket_offsets_body(const Ref* __restrict__ sets, int nsets, int shift, uint32_t nb,
+                                                    uint32_t* __restrict__ off) {
+    const int i = blockIdx.y;
+    const uint64_t n = sets[i].n;
+    const uint64_t* __restrict__ k = sets[i].k;
+    const bool vec = (((uintptr_t)k) & 15) == 0;
+    const uint64_t npair = (n + 1) >> 1;
+    const unsigned lane = threadIdx.x & 31;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < npair; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t t = base + lane;
+        uint64_t k0 = 0, k1 = 0;
+        const bool has0 = 2 * t < n, has1 = 2 * t + 1 < n;
+        if (has1 && vec) {
+            const uint4 v = ld_stream_v4(k + 2 * t);
+            k0 = ((uint64_t)v.y << 32) | v.x;
+            k1 = ((uint64_t)v.w << 32) | v.z;
+        } else {
+            if (has0) k0 = __ldg(k + 2 * t);
+            if (has1) k1 = __ldg(k + 2 * t + 1);
+        }
+        uint64_t prev = __shfl_up_sync(0xffffffffu, k1, 1);
+        if (lane == 0 && has0 && t > 0) prev = __ldg(k + 2 * t - 1);
+        if (has0) {
+            const uint64_t j = 2 * t;
+            const uint64_t cur = (shift < 64) ? (k0 >> shift) : 0ull;
+            const uint64_t pb = (shift < 64 && j > 0) ? (prev >> shift) : 0ull;
+            for (uint64_t b = (j > 0) ? pb + 1 : 1; b <= cur; b++) off[b * nsets + i] = (uint32_t)j;   // off[0][i] = 0 already
+            if (j == n - 1)
+                for (uint64_t b = cur + 1; b <= nb; b++) off[b * nsets + i] = (uint32_t)n;
+        }
+        if (has1) {
+            const uint64_t j = 2 * t + 1;
+            const uint64_t cur = (shift < 64) ? (k1 >> shift) : 0ull;
+            const uint64_t pb = (shift < 64) ? (k0 >> shift) : 0ull;
+            for (uint64_t b = pb + 1; b <= cur; b++) off[b * nsets + i] = (uint32_t)j;
+            if (j == n - 1)
+                for (uint64_t b = cur + 1; b <= nb; b++) off[b * nsets + i] = (uint32_t)n;
+        }
+    }
+}
+
 // ---- chained scan ("decoupled look-back") over tiles, one 64-bit status word per tile.
 // status: bits 63..62 = 0 invalid / 1 tile aggregate / 2 inclusive prefix; bits 61..0 value.
 // The status array must be zeroed before the launch and tile ids must be handed out in launch

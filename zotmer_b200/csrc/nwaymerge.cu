@@ -50,16 +50,7 @@ struct KCRef {
 // (rows of empty inputs stay zero).
 __global__ void __launch_bounds__(256)
 bm_offsets_kernel(const KCRef* __restrict__ sets, int nsets, int shift, uint32_t nb, uint32_t* __restrict__ off) {
-    const int i = blockIdx.y;
-    const uint64_t n = sets[i].n;
-    const uint64_t* __restrict__ k = sets[i].k;
-    for (uint64_t j = (uint64_t)blockIdx.x * 256 + threadIdx.x; j < n; j += (uint64_t)gridDim.x * 256) {
-        const uint64_t cur = (shift < 64) ? (__ldg(k + j) >> shift) : 0ull;
-        const uint64_t prev = (shift < 64 && j > 0) ? (__ldg(k + j - 1) >> shift) : 0ull;
-        for (uint64_t b = (j > 0) ? prev + 1 : 1; b <= cur; b++) off[b * nsets + i] = (uint32_t)j;   // off[0][i] = 0 already
-        if (j == n - 1)
-            for (uint64_t b = cur + 1; b <= nb; b++) off[b * nsets + i] = (uint32_t)n;
-    }
+    bucket_offsets_body(sets, nsets, shift, nb, off);
 }
 
 // start[b] = sum over inputs of off[b][i] (position of bucket b in the virtual concatenation); one warp per bucket
@@ -342,7 +333,7 @@ bool merge_nway(Ctx* c, const std::vector<const uint64_t*>& ks, const std::vecto
             ZB_CUDA(dev_memset(c, off.get(), 0, noff * 4));
             size_t nmax = 0;
             for (int i = 0; i < nsets; i++) nmax = std::max(nmax, ns[i]);
-            const dim3 grid((unsigned)std::min<size_t>(div_up(nmax, 256 * 8), 65535), (unsigned)nsets);
+            const dim3 grid((unsigned)std::min<size_t>(div_up(nmax, 256 * 2 * 8), 65535), (unsigned)nsets);
             bm_offsets_kernel<<<grid, 256, 0, c->stream>>>(d_refs.get(), nsets, key_bits - cb, nb, off.get());
             ZB_LAUNCH_CHECK(c);
             bm_starts_kernel<<<(unsigned)div_up((size_t)nb + 1, 8), 256, 0, c->stream>>>(off.get(), nsets, nb, start.get());

@@ -295,10 +295,13 @@ AP_KS = 8   # key-range shards per tile, csrc/allpairs.cu AB_KS
 
 
 def tile_blocks(nsets, u):
-    """work unit -> (bi, bj), bi <= bj: its tile u // AP_KS, row-major over the upper triangle of blocks, diagonal
-    included (host statement of csrc/allpairs.cu tile_to_blocks)"""
+    """work unit -> (bi, bj), bi <= bj: its tile u // AP_KS.  More than two blocks: row-major over the upper triangle
+    of blocks, diagonal included; up to two blocks (<= 64 sets): ONE tile (0, nblk - 1) that covers every pair
+    (host statement of csrc/allpairs.cu tile_to_blocks)"""
     t = u // AP_KS
     nblk = -(-nsets // AP_S)
+    if nblk <= 2:
+        return 0, nblk - 1
     r, start = 0, 0
     while start + (nblk - r) <= t:
         start += nblk - r
@@ -308,6 +311,9 @@ def tile_blocks(nsets, u):
 
 def tile_pairs(nsets, u):
     """the set pairs (i < j) a work unit contributes to (it holds their counts over ITS key-range shard u % AP_KS)"""
+    nblk = -(-nsets // AP_S)
+    if nblk <= 2:
+        return [(i, j) for i in range(nsets) for j in range(i + 1, nsets)]
     bi, bj = tile_blocks(nsets, u)
     out = []
     for i in range(bi * AP_S, min((bi + 1) * AP_S, nsets)):
@@ -323,7 +329,7 @@ def key_shard(x, key_bits):
 
 def n_tiles(nsets):
     nblk = -(-nsets // AP_S)
-    return nblk * (nblk + 1) // 2 * AP_KS
+    return (1 if nblk <= 2 else nblk * (nblk + 1) // 2) * AP_KS
 
 
 def tile_ranges(nsets, world):
