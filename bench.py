@@ -271,44 +271,37 @@ def run_ours(args, rank, world, local_rank):
     prof = nat.dbg_profile(False, dev)
 
     # ---------------- end to end through host buffers (pinned in, pinned out)
-    # N = 1: three steps are kept in flight by three host threads (the library gives every host thread its own stream and
-    # allocator), so the H2D copy of one step overlaps the kernels / D2H of the other -- what a user with more than one
-    # input file does.  Every step still copies its own 315 MB in and its own result out inside the timed region.
+    # N = 1: four steps are kept in flight by four host threads (the library gives every host thread its own stream and
+    # allocator and hands the copy-in / copy-out engines from thread to thread), so the H2D copy of one step overlaps the
+    # kernels / D2H of the others -- what a user with more than one input file does.  Every step still copies its own
+    # 315 MB in and its own result out inside the timed region.
     # N > 1: one step in flight (the exchange is a collective; all ranks must issue it in the same order).
-    inflight = 1 if world > 1 else int(os.environ.get("ZB_E2E_INFLIGHT", 3))
+    inflight = 1 if world > 1 else int(os.environ.get("ZB_E2E_INFLIGHT", 4))
 
     def make_out():
         return (torch.empty(max(n_trim, 1), dtype=torch.int64).pin_memory().numpy().view(np.uint64),
                 torch.empty(max(n_trim, 1), dtype=torch.int32).pin_memory().numpy().view(np.uint32))
 
-    # With several steps in flight each of the three resources is handed from step to step (one lock each), so the
-    # steps form a pipeline instead of marching in lock-step: copy-in engine (H2D + parse + extract), SMs (sort, count,
-    # mirror, trim, stats), copy-out engine (D2H of the result).
+    # With several steps in flight the LIBRARY hands the device's copy engines from step to step (one lock per engine
+    # inside libzot_b200: copy-in for the H2D of the input, copy-out for the D2H of the result; kernels of different
+    # steps overlap freely), so the steps of the host threads form a pipeline; the user code below is just the plain
+    # sequence of API calls.
     import threading
-    lock_in, lock_sm, lock_out = threading.Lock(), threading.Lock(), threading.Lock()
-
     trace = [] if os.environ.get("ZB_E2E_TRACE") else None
 
     def step_e2e(out_k, out_c):
         tr = [threading.get_ident() % 1000, time.perf_counter()] if trace is not None else None
         km = nat.Kmerizer(K, dev)
-        with lock_in:
-            if tr: tr.append(time.perf_counter())
-            km.feed(h_in, False)
-            if tr: tr.append(time.perf_counter())
-        with lock_sm:
-            if tr: tr.append(time.perf_counter())
-            if dist_ctx is not None:
-                exchange(nat, km, dist_ctx)
-            s, nr = km.finish()
-            km.close()
-            t = s.trim(2)
-            st = s.stats()
-            if tr: tr.append(time.perf_counter())
-        with lock_out:
-            if tr: tr.append(time.perf_counter())
-            k_, c_ = t.fetch(out_k=out_k, out_c=out_c)
-            if tr: tr.append(time.perf_counter())
+        km.feed(h_in, False)
+        if tr: tr.append(time.perf_counter())
+        if dist_ctx is not None:
+            exchange(nat, km, dist_ctx)
+        s, nr = km.finish()
+        km.close()
+        t = s.trim(2)
+        st = s.stats()
+        if tr: tr.append(time.perf_counter())
+        k_, c_ = t.fetch(out_k=out_k, out_c=out_c)
         s.free(); t.free()
         if tr:
             tr.append(time.perf_counter())
@@ -383,7 +376,7 @@ def run_ours(args, rank, world, local_rank):
         if trace:
             t00 = min(r[1] for r in trace)
             for r in sorted(trace, key=lambda r: r[1]):
-                print("trace thread %3d: start %.2f | in %.2f-%.2f | sm %.2f-%.2f | out %.2f-%.2f | end %.2f" % (
+                print("trace thread %3d: start %.2f | fed %.2f | counted + trimmed %.2f | fetched %.2f" % (
                     (r[0],) + tuple((x - t00) * 1e3 for x in r[1:])), file=sys.stderr)
 
     # ---------------- reduce over ranks (max time), aggregate throughput

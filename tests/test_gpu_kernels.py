@@ -489,6 +489,48 @@ def test_kmerize_capture_vs_oracle(nat, k):
         assert len(ek) > 0 and [int(x) for x in ks] == ek and [int(c) for c in cc] == ec, name
 
 
+def test_concurrent_host_threads(nat):
+    """four host threads drive the same GPU at once (every thread has its own library context): kmerize + trim + stats
+    + merge + fetch, ten rounds each, every result identical to the single-threaded one"""
+    import threading
+    from tools import synth
+    g = synth.genome(300000, seed=21)
+    inputs = [synth.fastq_array(g, 20000, seed=30 + i).reshape(-1).tobytes() for i in range(4)]
+
+    def work(data):
+        km = nat.Kmerizer(25)
+        km.feed(data, False)
+        s, nr = km.finish()
+        km.close()
+        t = s.trim(2)
+        m = nat.merge([s, t, s])
+        out = (s.fetch(), t.fetch(), m.fetch(), s.stats()["hist"], nr)
+        s.free(); t.free(); m.free()
+        return out
+
+    def same(a, b):
+        return all(np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) for x, y in zip(a[:3], b[:3])) and a[3:] == b[3:]
+
+    expect = [work(d) for d in inputs]
+    errors = []
+
+    def runner(i):
+        try:
+            for _ in range(10):
+                if not same(work(inputs[i]), expect[i]):
+                    errors.append("thread %d: result differs" % i)
+                    return
+        except Exception as e:   # pragma: no cover
+            errors.append("thread %d: %r" % (i, e))
+
+    ths = [threading.Thread(target=runner, args=(i,)) for i in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errors, errors
+
+
 def test_kmerize_empty(nat):
     s, nr = run_kmerize(nat, 25, [(b">nothing\nACGT\n", True)])
     assert len(s) == 0 and nr == 1

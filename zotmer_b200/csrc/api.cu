@@ -308,12 +308,12 @@ static void feed_dev_impl(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is
     extract_codes(h, cd, n_codes);
 }
 
-// Large host <-> device copies go out in 16 MiB pieces with at most three of them queued: a copy engine serves the
+// Large host <-> device copies go out in 32 MiB pieces with at most three of them queued: a copy engine serves the
 // streams of all host threads in the order the transfers were queued, so whatever another thread's step needs from
 // the engine waits for three pieces, not for a whole 315 MB input (measured: with one 315 MB copy queued the other
 // thread's sort + count took 13 ms instead of 6).
 static void copy_chunked(Ctx* c, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
-    const size_t piece = (size_t)16 << 20;
+    const size_t piece = (size_t)32 << 20;
     if (bytes <= 2 * piece) {
         ZB_CUDA(cudaMemcpyAsync(dst, src, bytes, kind, c->stream));
         return;
@@ -327,6 +327,26 @@ static void copy_chunked(Ctx* c, void* dst, const void* src, size_t bytes, cudaM
         ZB_CUDA(cudaEventRecord(c->copy_ev[i % 3], c->stream));
     }
 }
+
+// The copy engines of a device are handed from host thread to host thread: the bulk copies of a kmerize step (H2D
+// of the input, D2H of the result) each hold their engine's lock, so several host threads that drive the same GPU
+// copy one after the other at full PCIe rate while their kernels overlap freely (measured on bench.py's e2e with 3 - 4
+// steps in flight: 7.1 - 7.3 ms/step; without the copy locks 12.0 -- the engine interleaves the pieces of all copies
+// and every step waits for all of them; with a lock around the SM phases as well 8.7 - 9.0 -- the host round trips
+// inside a phase, a dozen few-byte read-backs, then leave the GPU idle).  Locks are never nested; a single-threaded
+// caller never waits.  ZB_ENGINE_LOCKS overrides the policy (bit 0 copy-in, bit 1 SMs, bit 2 copy-out; default 5).
+enum { ENG_H2D = 0, ENG_SM = 1, ENG_D2H = 2 };
+static std::mutex g_engine_mu[64][3];
+static int engine_lock_mask() {
+    static const int m = [] { const char* e = getenv("ZB_ENGINE_LOCKS"); return e ? atoi(e) : 5; }();
+    return m;
+}
+struct EngineLock {
+    std::unique_lock<std::mutex> lk;
+    EngineLock(const Ctx* c, int kind) : lk(g_engine_mu[c->device & 63][kind], std::defer_lock) {
+        if ((engine_lock_mask() >> kind) & 1) lk.lock();
+    }
+};
 
 static zb_set* new_set(Ctx* c, size_t n) {
     zb_set* s = new zb_set();
@@ -413,6 +433,7 @@ int zb_kmerize_feed_dev(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is_f
     ZB_TRY
     if (!h) ZB_FAIL(ZB_E_ARG, "null handle");
     ZB_CUDA(cudaSetDevice(h->c->device));
+    EngineLock el(h->c, ENG_SM);
     feed_dev_impl(h, d_raw, n, is_fasta);
     ZB_CATCH
 }
@@ -426,10 +447,14 @@ int zb_kmerize_feed(zb_kmerizer* h, const uint8_t* raw, size_t n, int is_fasta) 
     ZB_CUDA(cudaSetDevice(c->device));
     DBuf<uint8_t> d(c, n + 16);
     {
+        EngineLock el(c, ENG_H2D);
         Stage st(c, "h2d");
         copy_chunked(c, d.get(), raw, n, cudaMemcpyHostToDevice);
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
     }
+    EngineLock el(c, ENG_SM);
     feed_dev_impl(h, d.get(), n, is_fasta);
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
     ZB_CATCH
 }
 
@@ -454,6 +479,7 @@ int zb_kmerize_finish(zb_kmerizer* h, zb_set** result, uint64_t* n_records) {
     if (!h || !result) ZB_FAIL(ZB_E_ARG, "null argument");
     Ctx* c = h->c;
     ZB_CUDA(cudaSetDevice(c->device));
+    EngineLock el(c, ENG_SM);
     flush_pending(h);
     h->pending.release();
     h->pending_cap = 0;
@@ -704,6 +730,7 @@ int zb_set_fetch(const zb_set* s, uint64_t* kmers, uint32_t* counts) {
     if (!s) ZB_FAIL(ZB_E_ARG, "null set");
     Ctx* c = s->c;
     ZB_CUDA(cudaSetDevice(c->device));
+    EngineLock el(c, ENG_D2H);
     if (s->n && kmers) copy_chunked(c, kmers, s->k.get(), s->n * 8, cudaMemcpyDeviceToHost);
     if (s->n && counts) copy_chunked(c, counts, s->cnt.get(), s->n * 4, cudaMemcpyDeviceToHost);
     ZB_CUDA(cudaStreamSynchronize(c->stream));
@@ -734,7 +761,10 @@ int zb_set_stats(const zb_set* s, uint64_t acgt_weighted[4], uint64_t acgt_plain
     ZB_CUDA(cudaSetDevice(c->device));
     uint64_t aw[4], ap[4], tot;
     std::vector<std::pair<uint64_t, uint64_t>> hist;
-    set_stats(c, s->k.get(), s->cnt.get(), s->n, aw, ap, &tot, &hist);
+    {
+        EngineLock el(c, ENG_SM);
+        set_stats(c, s->k.get(), s->cnt.get(), s->n, aw, ap, &tot, &hist);
+    }
     for (int q = 0; q < 4; q++) {
         if (acgt_weighted) acgt_weighted[q] = aw[q];
         if (acgt_plain) acgt_plain[q] = ap[q];
@@ -858,6 +888,7 @@ int zb_trim(const zb_set* s, uint64_t cmin, uint64_t cmax, zb_set** out) {
     Ctx* c = s->c;
     ZB_CUDA(cudaSetDevice(c->device));
     zb_set* r = new_set(c, s->n);
+    EngineLock el(c, ENG_SM);
     Stage st(c, "trim");
     r->n = trim_pairs(c, s->k.get(), s->cnt.get(), s->n, cmin, cmax, r->k.get(), r->cnt.get());
     *out = r;

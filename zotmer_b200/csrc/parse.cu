@@ -148,10 +148,10 @@ fq_count_kernel(const uint8_t* __restrict__ raw, uint64_t n, FqTile* __restrict_
     }
 }
 
-// scalars[0] = number of newlines, scalars[1] = emitted bytes (written by fastq_kernel)
+// scalars[0] = number of newlines, scalars[1] = emitted bytes (written by fastq_kernel), scalars[2] = last byte of the text
 __global__ void __launch_bounds__(1024)
 fq_scan_kernel(const FqTile* __restrict__ tiles, uint32_t ntiles, uint64_t* __restrict__ line0, uint64_t* __restrict__ out0,
-               unsigned long long* __restrict__ scalars) {
+               unsigned long long* __restrict__ scalars, const uint8_t* __restrict__ raw, uint64_t n) {
     __shared__ uint64_t sm[1024 / 32 + 1];
     uint64_t carry = 0;
     for (uint32_t b0 = 0; b0 < ntiles; b0 += 1024) {
@@ -162,7 +162,10 @@ fq_scan_kernel(const FqTile* __restrict__ tiles, uint32_t ntiles, uint64_t* __re
         if (i < ntiles) line0[i] = carry + ex;
         carry += tot;
     }
-    if (threadIdx.x == 0) scalars[0] = carry;
+    if (threadIdx.x == 0) {
+        scalars[0] = carry;
+        scalars[2] = raw[n - 1];   // the host wants to know whether the text ends in a newline
+    }
     __syncthreads();   // line0[] of this block's own earlier writes is visible to the whole block
     carry = 0;
     for (uint32_t b0 = 0; b0 < ntiles; b0 += 1024) {
@@ -293,21 +296,20 @@ void parse_fastq(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n
     if (n == 0) return;
     const uint32_t tiles = (uint32_t)div_up(n, PA_TILE);
     DBuf<FqTile> info(c, tiles);
-    DBuf<uint64_t> st(c, (size_t)tiles * 2 + 2);
+    DBuf<uint64_t> st(c, (size_t)tiles * 2 + 3);
     uint64_t* line0 = st.get();
     uint64_t* out0 = st.get() + tiles;
-    unsigned long long* scalars = reinterpret_cast<unsigned long long*>(st.get() + 2 * (size_t)tiles);   // [0] newlines [1] codes
-    ZB_CUDA(dev_memset(c, scalars, 0, 16));
+    unsigned long long* scalars = reinterpret_cast<unsigned long long*>(st.get() + 2 * (size_t)tiles);   // [0] newlines [1] codes [2] last byte
+    ZB_CUDA(dev_memset(c, scalars, 0, 24));
     fq_count_kernel<<<tiles, PA_THREADS, 0, c->stream>>>(raw, n, info.get());
     ZB_LAUNCH_CHECK(c);
-    fq_scan_kernel<<<1, 1024, 0, c->stream>>>(info.get(), tiles, line0, out0, scalars);
+    fq_scan_kernel<<<1, 1024, 0, c->stream>>>(info.get(), tiles, line0, out0, scalars, raw, n);
     ZB_LAUNCH_CHECK(c);
     fastq_kernel<<<tiles, PA_THREADS, 0, c->stream>>>(raw, n, scalars, codes, line0, out0, scalars + 1, mark_records);
     ZB_LAUNCH_CHECK(c);
-    ZB_CUDA(read_back(c, scalars, 16));
-    uint8_t last = 0;
-    ZB_CUDA(cudaMemcpyAsync(&last, raw + n - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(read_back(c, scalars, 24));   // (a 1-byte cudaMemcpy of the last byte would queue behind other threads' bulk copies)
     ZB_CUDA(cudaStreamSynchronize(c->stream));
+    const uint8_t last = (uint8_t)c->h_scalars[2];
     const uint64_t lines = c->h_scalars[0] + (last != '\n' ? 1 : 0);
     *n_records = lines / 4;
     *n_codes = (size_t)c->h_scalars[1];

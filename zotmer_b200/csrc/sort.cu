@@ -360,18 +360,27 @@ static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uin
         int blocks = (int)std::min<size_t>((size_t)c->sm_count * 4, div_up(n, 512 * 2 * 4));
         if (blocks < 1) blocks = 1;
         size_t sm = (size_t)plan.passes * BINS * 4;
-        if (sm > 48 * 1024)
-            ZB_CUDA(cudaFuncSetAttribute(sort_hist_kernel<BINS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        if ((size_t)MAX_PASSES * BINS * 4 > 48 * 1024)   // a fixed limit per instantiation (see below)
+            ZB_CUDA(cudaFuncSetAttribute(sort_hist_kernel<BINS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_PASSES * BINS * 4));
         sort_hist_kernel<BINS><<<blocks, 512, sm, c->stream>>>(k0, n, plan, ghist.get());
         ZB_LAUNCH_CHECK(c);
         sort_scan_kernel<BINS><<<plan.passes, (BINS > 1024 ? 1024 : BINS), 0, c->stream>>>(ghist.get());
         ZB_LAUNCH_CHECK(c);
     }
     size_t sm = onesweep_smem<BINS, SORT_THREADS, SORT_ITEMS>(vals);
-    ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, SORT_ITEMS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, SORT_ITEMS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, SORT_ITEMS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, SORT_ITEMS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    {   // every instantiation gets ITS OWN fixed limit: the attribute is global to the function, and host threads
+        // sorting keys and pairs at the same time must not lower each other's limit between attribute and launch
+        const int sm_keys = (int)onesweep_smem<BINS, SORT_THREADS, SORT_ITEMS>(false);
+        const int sm_pairs = (int)onesweep_smem<BINS, SORT_THREADS, SORT_ITEMS>(true);
+        const int sm_limit = 227 * 1024;   // per CTA on sm_100; the 11-bit shape with a payload does not fit (keys only does)
+        if (vals && sm_pairs > sm_limit) ZB_FAIL(ZB_E_ARG, "radix_sort: %d-bin passes cannot carry a payload", BINS);
+        if (sm_pairs <= sm_limit) {
+            ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, SORT_ITEMS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_pairs));
+            ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, SORT_ITEMS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_pairs));
+        }
+        ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, SORT_ITEMS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_keys));
+        ZB_CUDA(cudaFuncSetAttribute(onesweep_kernel<BINS, SORT_THREADS, SORT_ITEMS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_keys));
+    }
     uint64_t* kb[2] = {k0, k1};
     uint32_t* vb[2] = {v0, v1};
     int cur = 0;
