@@ -195,6 +195,11 @@ def exchange(nat, km, ctx):
 
 def run_ours(args, rank, world, local_rank):
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
+    # ... and since NCCL still prints its version banner to file descriptor 1 from C, everything written to stdout
+    # while the bench runs goes to stderr; the JSON line alone is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     from zotmer_b200 import _native as nat
     if nat.device_count() < 1:
@@ -452,7 +457,8 @@ def run_ours(args, rank, world, local_rank):
         line["pairs"] = pairs
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 PAIR_SETS = int(os.environ.get("ZB_BENCH_PAIR_SETS", 32))
