@@ -503,6 +503,8 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
     __shared__ uint32_t s_cnt;
     __shared__ __align__(8) uint64_t s_bar[2];
     constexpr bool DISTINCT = (MODE == 2);
+    // groups of the heads' counting sort: ~300 heads per bucket when keys repeat 6.5 x (MODE 0), every key a head in MODE 2
+    constexpr int FINE = DISTINCT ? BC_FINE : BC_FINE / 4;
 
     const unsigned tid = threadIdx.x;
     if (tid == 0) {
@@ -579,7 +581,7 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
                 for (int j = 0; j < BC_HASH / 4 / BC_THREADS; j++) reinterpret_cast<uint4*>(table)[j * BC_THREADS + tid] = e4;
             }
 #pragma unroll
-            for (int j = 0; j < BC_FINE / BC_THREADS; j++) hist[j * BC_THREADS + tid] = 0;
+            for (int j = 0; j < FINE / BC_THREADS; j++) hist[j * BC_THREADS + tid] = 0;
             uint64_t kx[BC_PER];
             uint32_t wx[BC_PER];
             int m;
@@ -602,6 +604,7 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
                 for (int j = 0; j < BC_PER; j++) {
                     const int q = j * BC_THREADS + (int)tid;
                     kx[j] = (q < m) ? sk[q] : 0ull;
+                    if ((j + 1) * BC_THREADS >= m) break;
                 }
             } else {
                 // compact this round's keys (any order) into the buffer; DISTINCT: their positions into `table` for the payload
@@ -634,6 +637,8 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
                 if (DISTINCT) __syncthreads();   // `table` is about to be reused for the grouped heads
             }
 
+            // item loops below stop at the last slice of 512 positions that holds keys (a bucket is half full on average)
+            const int jn = (m + BC_THREADS - 1) / BC_THREADS;
             uint32_t headbits = 0;
             if (DISTINCT) {
 #pragma unroll
@@ -643,6 +648,7 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
                 // ---- dedupe: one hash insert per key; the first key to claim a value's slot is its head
 #pragma unroll
                 for (int j = 0; j < BC_PER; j++) {
+                    if (j >= jn) break;
                     const int q = j * BC_THREADS + (int)tid;
                     if (q < m) {
                         const uint64_t x = kx[j];
@@ -662,6 +668,7 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
             uint32_t rd[BC_PER];
 #pragma unroll
             for (int j = 0; j < BC_PER; j++) {
+                if (j >= jn) break;
                 if ((headbits >> j) & 1u) {
                     const uint32_t d = (uint32_t)(kx[j] >> fine_shift) & fine_mask;
                     rd[j] = atomicAdd(&hist[d], 1u) | (d << 16);
@@ -670,7 +677,7 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
             }
             __syncthreads();
             {   // exclusive scan of the group sizes
-                constexpr int GP = BC_FINE / BC_THREADS;
+                constexpr int GP = FINE / BC_THREADS;
                 uint32_t v[GP];
                 uint32_t t = 0;
 #pragma unroll
@@ -679,11 +686,12 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
                 uint32_t ex = block_excl_scan<BC_THREADS, uint32_t, false>(t, s_scan, &all);
 #pragma unroll
                 for (int u = 0; u < GP; u++) { hist[tid * GP + u] = ex; ex += v[u]; }
-                if (tid == 0) hist[BC_FINE] = all;
+                if (tid == 0) hist[FINE] = all;
             }
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < BC_PER; j++) {
+                if (j >= jn) break;
                 if ((headbits >> j) & 1u) {
                     const uint32_t p = hist[rd[j] >> 16] + (rd[j] & 0xffffu);
                     hs[p] = kx[j];
@@ -693,7 +701,7 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
             __syncthreads();
 
             // ---- every head ranks itself inside its group and writes (key, count)
-            const int H = (int)hist[BC_FINE];
+            const int H = (int)hist[FINE];
             for (int p = (int)tid; p < H; p += BC_THREADS) {
                 const uint64_t x = hs[p];
                 const uint32_t d = (uint32_t)(x >> fine_shift) & fine_mask;
@@ -757,7 +765,7 @@ static size_t sort_count_buckets(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v
     }
     const uint64_t* sk = which ? k1 : k0;
     const uint32_t* sv = weighted ? (which ? v1 : v0) : nullptr;
-    const int fb = std::min(BC_FINE_BITS, shift);
+    const int fb = std::min(distinct ? BC_FINE_BITS : BC_FINE_BITS - 2, shift);   // 2048 / 512 groups, see the kernel
     const int fine_shift = shift - fb;
     const uint32_t fine_mask = (1u << fb) - 1u;
 
