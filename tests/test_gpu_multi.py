@@ -13,12 +13,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("mode", ["p2p", "nccl"])
-def test_two_rank_kmerize_and_allpairs(mode):
+@pytest.mark.parametrize("mode,k", [("p2p", 25), ("nccl", 25), ("p2p", 31)])
+def test_two_rank_kmerize_and_allpairs(mode, k):
+    """k = 31 is BASELINE.json config[4]'s k (a 1/1000-scale instance of it: same code path, 62-bit keys)"""
     from zotmer_b200 import _native
     if _native.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    env = dict(os.environ, ZB_EXCHANGE=mode)
+    env = dict(os.environ, ZB_EXCHANGE=mode, ZB_CHECK_K=str(k))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "mgpu_check.py")],
                        env=env, capture_output=True, text=True, timeout=600)

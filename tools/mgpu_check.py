@@ -13,7 +13,7 @@ from oracle import c_oracle as co
 rank, world, dev = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % dev))
-K = 25
+K = int(os.environ.get("ZB_CHECK_K", 25))   # 31 = config[4]'s k (62-bit keys)
 g = synth.genome(300000, seed=5)
 shards = [synth.fastq_array(g, 20000, seed=50 + r).reshape(-1).tobytes() for r in range(world)]
 mode = os.environ.get("ZB_EXCHANGE", "p2p")
