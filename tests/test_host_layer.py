@@ -197,3 +197,45 @@ def test_fasta_line_rules_host_build(tmp_path):
         assert r.returncode == 0, r.stderr
         exp, nrec = expected(data)
         assert open(co, "rb").read() == exp and int(r.stdout) == nrec
+
+
+def test_compressed_inputs_inflate_like_gunzip(tmp_path):
+    """.gz (one member, several members, BGZF in parallel) and .bz2 (one and several streams) give the bytes
+    `gunzip -c` / `bunzip2 -c` give (file.py:93-102)"""
+    import bz2, gzip, struct, subprocess, zlib
+    import numpy as np
+    from zotmer_b200.library import file as zfile
+    rng = np.random.default_rng(3)
+    text = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, bytes(rng.choice(list(b"ACGT"), 100).astype(np.uint8)), b"I" * 100) for i in range(40000))
+    # plain gzip, two concatenated members
+    p1 = tmp_path / "a.fq.gz"
+    p1.write_bytes(gzip.compress(text[:1000000], 1) + gzip.compress(text[1000000:], 1))
+    assert zfile.readBytes(str(p1)) == text
+    # BGZF: 64 KB members with the BC extra field, as bgzip writes them, plus its empty EOF member
+    def member(chunk):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = co.compress(chunk) + co.flush()
+        bsize = 18 + len(body) + 8
+        return (b"\x1f\x8b\x08\x04" + b"\0" * 4 + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1) + body +
+                struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+    bg = b"".join(member(text[i:i + 65280]) for i in range(0, len(text), 65280)) + member(b"")
+    p2 = tmp_path / "b.fq.gz"
+    p2.write_bytes(bg)
+    assert len(bg) >= (1 << 20) and zfile._bgzf_blocks(bg) is not None
+    assert zfile.readBytes(str(p2)) == text
+    assert gzip.decompress(bg) == text                      # it really is a valid multi-member gzip file
+    try:
+        ref = subprocess.run(["gunzip", "-c", str(p2)], stdout=subprocess.PIPE, check=False).stdout
+        assert ref == text
+    except FileNotFoundError:
+        pass
+    # truncated file: the complete members and whatever the broken one still yields, as `gunzip -c` prints before it
+    # complains (the reference never looks at its exit status)
+    p3 = tmp_path / "c.fq.gz"
+    p3.write_bytes(gzip.compress(text[:5000]) + gzip.compress(text[5000:9000])[:-20])
+    got = zfile.readBytes(str(p3))
+    assert got.startswith(text[:5000]) and text[:9000].startswith(got)
+    # bz2, two streams
+    p4 = tmp_path / "d.fa.bz2"
+    p4.write_bytes(bz2.compress(text[:300000]) + bz2.compress(text[300000:700000]))
+    assert zfile.readBytes(str(p4)) == text[:700000]
