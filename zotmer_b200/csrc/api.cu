@@ -131,10 +131,35 @@ void* dalloc(Ctx* c, size_t bytes) {
         void* p = it->second;
         const size_t sz = it->first;
         c->free_blocks.erase(it);
+        c->freed_at.erase(p);
         c->cached_bytes -= sz;
         c->live_blocks[p] = sz;
         c->live_bytes += sz;
         return p;
+    }
+    // A miss.  A caller whose buffers grow from batch to batch (the running counted set of a long kmerize) leaves a
+    // trail of cached blocks that will never fit again: above the limit, the least recently released ones go back
+    // to the driver (human-scale run: 150 GB were cached, and the first allocation that failed spent 0.8 s freeing them).
+    if (c->cache_limit == 0) {
+        size_t fr = 0, tot = 0;
+        c->cache_limit = (cudaMemGetInfo(&fr, &tot) == cudaSuccess && tot) ? tot / 4 : ((size_t)32 << 30);
+    }
+    if (c->cached_bytes > c->cache_limit) {
+        std::vector<std::pair<uint64_t, void*>> byage;
+        for (auto& kv : c->freed_at) byage.push_back({kv.second, kv.first});
+        std::sort(byage.begin(), byage.end());
+        for (auto& ap : byage) {
+            if (c->cached_bytes <= c->cache_limit / 2) break;
+            for (auto fit = c->free_blocks.begin(); fit != c->free_blocks.end(); ++fit) {
+                if (fit->second == ap.second) {
+                    c->cached_bytes -= fit->first;
+                    cudaFree(fit->second);
+                    c->free_blocks.erase(fit);
+                    break;
+                }
+            }
+            c->freed_at.erase(ap.second);
+        }
     }
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, want);
@@ -143,6 +168,7 @@ void* dalloc(Ctx* c, size_t bytes) {
         cudaStreamSynchronize(c->stream);
         for (auto& kv : c->free_blocks) cudaFree(kv.second);
         c->free_blocks.clear();
+        c->freed_at.clear();
         c->cached_bytes = 0;
         e = cudaMalloc(&p, want);
     }
@@ -165,6 +191,7 @@ void dfree(Ctx* c, void* p) {
     c->live_blocks.erase(it);
     c->live_bytes -= sz;
     c->free_blocks.insert({sz, p});
+    c->freed_at[p] = ++c->tick;
     c->cached_bytes += sz;
 }
 
@@ -172,6 +199,7 @@ void dtrim(Ctx* c) {
     std::lock_guard<std::mutex> lk(c->alloc_mu);
     for (auto& kv : c->free_blocks) cudaFree(kv.second);
     c->free_blocks.clear();
+    c->freed_at.clear();
     c->cached_bytes = 0;
 }
 
@@ -189,6 +217,11 @@ struct zb_kmerizer {
     DBuf<uint64_t> acc_k;                // counted canonical run accumulated so far
     DBuf<uint32_t> acc_c;
     size_t acc_n = 0;
+    // scratch of the fold (merge into mrg, reduce into alt, swap alt <-> acc): kept across batches and grown
+    // geometrically, so that a long kmerize whose running set grows with every batch does not leave a trail of
+    // ever larger blocks in the allocator's cache (human-scale run: 150 GB of them)
+    DBuf<uint64_t> alt_k, mrg_k;
+    DBuf<uint32_t> alt_c, mrg_c;
     uint64_t n_records = 0;
     size_t max_pending = (size_t)1 << 29;
     const zb_set* baits = nullptr;       // capture mode (`zot kmerize -C`): only records that hold one of these k-mers count
@@ -253,14 +286,20 @@ static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n) {
         h->acc_n = nd;
     } else {
         const size_t tot = h->acc_n + nd;
-        DBuf<uint64_t> mk(c, tot);
-        DBuf<uint32_t> mc(c, tot);
-        merge_pairs(c, h->acc_k.get(), h->acc_c.get(), h->acc_n, other, dc.get(), nd, mk.get(), mc.get());
-        DBuf<uint64_t> rk(c, tot);
-        DBuf<uint32_t> rc(c, tot);
-        const size_t nn = reduce_by_key(c, mk.get(), mc.get(), tot, rk.get(), rc.get());
-        h->acc_k = std::move(rk);
-        h->acc_c = std::move(rc);
+        if (h->mrg_k.n < tot) {
+            const size_t cap = std::max(tot, 2 * h->mrg_k.n);
+            h->mrg_k.alloc(c, cap);
+            h->mrg_c.alloc(c, cap);
+        }
+        if (h->alt_k.n < tot) {
+            const size_t cap = std::max(tot, 2 * h->alt_k.n);
+            h->alt_k.alloc(c, cap);
+            h->alt_c.alloc(c, cap);
+        }
+        merge_pairs(c, h->acc_k.get(), h->acc_c.get(), h->acc_n, other, dc.get(), nd, h->mrg_k.get(), h->mrg_c.get());
+        const size_t nn = reduce_by_key(c, h->mrg_k.get(), h->mrg_c.get(), tot, h->alt_k.get(), h->alt_c.get());
+        std::swap(h->acc_k, h->alt_k);
+        std::swap(h->acc_c, h->alt_c);
         h->acc_n = nn;
     }
 }
@@ -505,6 +544,7 @@ int zb_kmerize_finish(zb_kmerizer* h, zb_set** result, uint64_t* n_records) {
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     h->acc_k.release();
     h->acc_c.release();
+    h->alt_k.release(); h->alt_c.release(); h->mrg_k.release(); h->mrg_c.release();
     h->acc_n = 0;
     if (n_records) *n_records = h->n_records;
     *result = s;

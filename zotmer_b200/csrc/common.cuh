@@ -52,6 +52,9 @@ struct Ctx {
     std::multimap<size_t, void*> free_blocks;
     std::unordered_map<void*, size_t> live_blocks;
     size_t cached_bytes = 0, live_bytes = 0;
+    std::unordered_map<void*, uint64_t> freed_at;   // cached block -> tick of its release (least recently used go first)
+    uint64_t tick = 0;
+    size_t cache_limit = 0;                        // cached bytes above which a miss evicts old blocks (a quarter of the device)
     std::mutex alloc_mu;
     cudaEvent_t copy_ev[3] = {nullptr, nullptr, nullptr};   // bulk host <-> device copies: at most three pieces queued
     bool profile = false;
