@@ -556,7 +556,7 @@ def stage_keys(nat, dev, d_in, nbytes):
 def cpu_baseline():
     """oracle port of the reference (pure Python, 1 thread) on a bounded sample of the same reads"""
     from oracle import zot_oracle as zo
-    sample_reads = int(os.environ.get("ZB_CPU_SAMPLE_READS", 12000))
+    sample_reads = int(os.environ.get("ZB_CPU_SAMPLE_READS", 30000))   # ~11 s of CPython on the GPU box
     fq = make_reads(0, READS_PER_RANK)[:sample_reads * 315].tobytes()
     t0 = time.perf_counter()
     xs, cs, h, acgt, nr = zo.kmerize_core(K, [("reads.fq", fq)])
