@@ -347,13 +347,14 @@ static void feed_dev_impl(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is
     extract_codes(h, cd, n_codes);
 }
 
-// Large host <-> device copies go out in 32 MiB pieces with at most three of them queued: a copy engine serves the
+// Large host <-> device copies go out in 64 MiB pieces with at most three of them queued: a copy engine serves the
 // streams of all host threads in the order the transfers were queued, so whatever another thread's step needs from
 // the engine waits for three pieces, not for a whole 315 MB input (measured: with one 315 MB copy queued the other
 // thread's sort + count took 13 ms instead of 6).
 static void copy_chunked(Ctx* c, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
-    const size_t piece = (size_t)32 << 20;
-    if (bytes <= 2 * piece) {
+    static const size_t piece_mb = [] { const char* e = getenv("ZB_COPY_PIECE_MB"); return e ? (size_t)atoi(e) : (size_t)64; }();
+    const size_t piece = piece_mb << 20;   // ZB_COPY_PIECE_MB=0: one unthrottled copy
+    if (piece == 0 || bytes <= 2 * piece) {
         ZB_CUDA(cudaMemcpyAsync(dst, src, bytes, kind, c->stream));
         return;
     }
