@@ -1,51 +1,50 @@
-"""
-Usage:
-    zot [options] <command> [<args>...]
-
-options:
-    --help          print usage information
-    -V, --version   print version information
-"""
-# Mirrors zotmer/cli.py:1-63: docopt with options_first, `zot help`, dynamic import of
-# zotmer_b200.commands.<command>, temp files removed on exit.
+# The `zot` dispatcher: same command line as zotmer/cli.py:21-59 (`zot [options] <command> [<args>...]`, `zot help`,
+# `zot help <command>`, temp files of library.file.tmpfile removed on the way out) over a static table of the commands
+# this package implements; the grammars live in zotmer_b200/usage.py.
 import importlib
-import pkgutil
 import sys
 
 from zotmer_b200 import docopt_mini as docopt
+from zotmer_b200 import usage
 from zotmer_b200.library.file import autoremove
-from zotmer_b200 import commands
+
+__doc__ = usage.CLI
+VERSION = 'Zotmer k-mer toolkit 0.1'
+UNKNOWN = "unable to load command `%s', use `zot help` for help."
+
+
+def _module(name):
+    """the module behind a command word, or None (as the reference: any importable zotmer.commands.<name>)"""
+    if name not in usage.USAGE:
+        return None
+    return importlib.import_module('zotmer_b200.commands.' + name)
+
+
+def _overview():
+    lines = [__doc__, "Available commands:"]
+    lines += ['\t' + name for name in sorted(usage.USAGE)]
+    lines.append('\nuse "zot help <command>" for command specific help.')
+    return '\n'.join(lines)
 
 
 def mainInner(argv=None):
-    args = docopt.docopt(__doc__, argv, version='Zotmer k-mer toolkit 0.1', options_first=True)
-
-    if args['<command>'] == 'help' and len(args['<args>']) != 1:
-        print(__doc__)
-        print("Available commands:")
-        for _, name, is_pkg in pkgutil.iter_modules([commands.__path__[0]]):
-            print('\t' + name)
-        print('\nuse "zot help <command>" for command specific help.')
-        return 0
-
-    if args['<command>'] == 'help' and len(args['<args>']) == 1:
-        modname = commands.__name__ + '.' + args['<args>'][0]
-        try:
-            m = importlib.import_module(modname)
-            print(m.__doc__)
+    parsed = docopt.docopt(__doc__, argv, version=VERSION, options_first=True)
+    word, rest = parsed['<command>'], parsed['<args>']
+    if word == 'help':
+        if len(rest) != 1:
+            print(_overview())
             return 0
-        except ImportError:
-            print("unable to load command `%s', use `zot help` for help." % (args['<command>'],), file=sys.stderr)
+        mod = _module(rest[0])
+        if mod is None:
+            print(UNKNOWN % (word,), file=sys.stderr)      # sic: the reference names `help` here, not the argument
             return 1
-
-    modname = commands.__name__ + '.' + args['<command>']
-    try:
-        m = importlib.import_module(modname)
-    except ImportError:
-        print("unable to load command `%s', use `zot help` for help." % (args['<command>'],), file=sys.stderr)
+        print(mod.__doc__)
+        return 0
+    mod = _module(word)
+    if mod is None:
+        print(UNKNOWN % (word,), file=sys.stderr)
         return 1
-    argv = [args['<command>']] + args['<args>']
-    return m.main(argv)
+    return mod.main([word] + rest)
 
 
 def main(argv=None):

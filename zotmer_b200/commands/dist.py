@@ -1,153 +1,112 @@
-"""
-Usage:
-    zot dist [-M measure]... <k> <input>...
-
-Options:
-    -M measure  use "measure" for the distance between k-mer frequency sets.
-                Use "-M list" to get a list of available measures.
-"""
-# Drop-in for zotmer/commands/dist.py:94-168.  The reference decodes file j again for every pair and
-# runs the two-pointer split() once per measure per pair (:145-168, library/dist.py:241-265); here
-# every file is decoded once, projected to K (zb_project = Measure.prep :29-49) and kept on the
-# device, all (i<j) pairs go through zb_pairs_abc in one batch, and the measures are evaluated on the
-# host from (a,b,c) with the reference's float formulas.
+# `zot dist` (zotmer/commands/dist.py:94-168): a table of distances between every pair of k-mer sets, one column per
+# selected measure.  The reference decodes file j again for every pair (i, j) and walks the two sorted arrays once per
+# measure per pair (library/dist.py:241-265 split()).  Here every file is decoded once on the device and projected to
+# K-mers (zb_project = Measure.prep, :29-49); ALL pairs get their (a, b, c) = (both, only left, only right) from one
+# zb_allpairs_abc call; the measures are the reference's float formulas on the host (library/dist.py), so the %g
+# columns agree to the last digit.
+# Kept from the reference: "-M list"; unknown patterns warn and print nothing; quantitative ("vec") measures crash with
+# a TypeError after the header line, because the reference unpacks (x, c) from a stream of plain ints (:34-41); a file
+# whose K is below the requested K raises MismatchedK.
 import fnmatch
 import sys
 
-import numpy as np
-
-from zotmer_b200 import docopt_mini as docopt
 from zotmer_b200 import _native
-import zotmer_b200.library.dist as dist
+from zotmer_b200 import docopt_mini as docopt
+from zotmer_b200 import usage
+import zotmer_b200.library.dist as formulas
 from zotmer_b200.library.exceptions import MismatchedK
 from zotmer_b200.library.files import readKmerSet
 from zotmer_b200.library.kmers import kmers
 
-measures = {}
+__doc__ = usage.DIST
+
+# name -> (description, function of (a, b, c) or None for the quantitative measures, which need counts)
+MEASURES = dict((name, (desc, fn)) for (name, desc, fn) in [
+    ('bray.curtis.quant', 'Quantative Bray.Curtis distance', None),
+    ('bray.curtis.qual', 'Qualitative Bray.Curtis distance', formulas.brayCurtis),
+    ('chord.quant', 'Quantative Chord distance', None),
+    ('chord.qual', 'Qualitative Chord distance', formulas.chord),
+    ('hellinger.quant', 'Quantative Hellinger distance', None),
+    ('hellinger.qual', 'Qualitative Hellinger distance', formulas.hellinger),
+    ('jaccard.ab', 'Abundance.based Jaccard distance', None),
+    ('jaccard.qual', 'Qualitative Jaccard distance', formulas.jaccard),
+    ('jensen.shannon', 'Jensen.Shannon distance', None),
+    ('kulczynski.quant', 'Quantative Kulczynski distance', None),
+    ('kulczynski.qual', 'Qualitative Kulczynski distance', formulas.kulczynski),
+    ('ochiai.ab', 'Abundance.based Ochiai distance', None),
+    ('ochiai.qual', 'Qualitative Ochiai distance', formulas.ochiai),
+    ('sorensen.ab', 'Abundance.based Sorensen distance', None),
+    ('sorensen.qual', 'Qualitative Sorensen distance', formulas.sorensen),
+    ('whittaker.quant', 'Quantative Whittaker distance', None),
+    ('whittaker.qual', 'Qualitative Whittaker distance', formulas.whittaker),
+])
 
 
-class Measure:
-    def __init__(self, name, desc, vec, func):
-        self.name = name
-        self.desc = desc
-        self.vec = vec
-        self.func = func
-
-    def prep(self, K, fn, device=0):
-        """commands/dist.py:29-49 (set form): project to K-mers, drop adjacent duplicates -> KmerSet"""
-        with kmers(fn, 'r') as z:
-            fK = z.meta['K']
-            if fK < K:
-                raise MismatchedK(K, fK)
-            if self.vec:
-                # the reference unpacks (x, c) from a stream of plain ints here (:34-41)
-                raise TypeError("cannot unpack non-iterable int object")
-            xs = readKmerSet(z, counts=False, device=device)
-            S = 2 * (fK - K)
-            v = xs.project(S)
-            xs.free()
-            return v
-
-    def measure(self, a, b, c):
-        return self.func(a, b, c)
+def select(patterns):
+    """measure names matching the -M patterns, sorted; None when a pattern matches nothing (after the warning)"""
+    names = sorted(MEASURES)
+    chosen = set()
+    clean = True
+    for pat in patterns:
+        hits = fnmatch.filter(names, pat)
+        if not hits:
+            print("warning: measure '%s' not found. Use -M list to see all measures." % (pat,), file=sys.stderr)
+            clean = False
+        chosen.update(hits)
+    return sorted(chosen) if clean else None
 
 
-def addMeasure(name, desc, vec, func):
-    measures[name] = Measure(name, desc, vec, func)
+def projected(K, path, device=0):
+    """the file's k-mers cut down to their first K bases, duplicates dropped, on the device (Measure.prep, set form)"""
+    with kmers(path, 'r') as z:
+        fileK = z.meta['K']
+        if fileK < K:
+            raise MismatchedK(K, fileK)
+        whole = readKmerSet(z, counts=False, device=device)
+    cut = whole.project(2 * (fileK - K))
+    whole.free()
+    return cut
 
 
-addMeasure('bray.curtis.quant', 'Quantative Bray.Curtis distance', True, None)
-addMeasure('bray.curtis.qual', 'Qualitative Bray.Curtis distance', False, dist.brayCurtis)
-addMeasure('chord.quant', 'Quantative Chord distance', True, None)
-addMeasure('chord.qual', 'Qualitative Chord distance', False, dist.chord)
-addMeasure('hellinger.quant', 'Quantative Hellinger distance', True, None)
-addMeasure('hellinger.qual', 'Qualitative Hellinger distance', False, dist.hellinger)
-addMeasure('jaccard.ab', 'Abundance.based Jaccard distance', True, None)
-addMeasure('jaccard.qual', 'Qualitative Jaccard distance', False, dist.jaccard)
-addMeasure('jensen.shannon', 'Jensen.Shannon distance', True, None)
-addMeasure('kulczynski.quant', 'Quantative Kulczynski distance', True, None)
-addMeasure('kulczynski.qual', 'Qualitative Kulczynski distance', False, dist.kulczynski)
-addMeasure('ochiai.ab', 'Abundance.based Ochiai distance', True, None)
-addMeasure('ochiai.qual', 'Qualitative Ochiai distance', False, dist.ochiai)
-addMeasure('sorensen.ab', 'Abundance.based Sorensen distance', True, None)
-addMeasure('sorensen.qual', 'Qualitative Sorensen distance', False, dist.sorensen)
-addMeasure('whittaker.quant', 'Quantative Whittaker distance', True, None)
-addMeasure('whittaker.qual', 'Qualitative Whittaker distance', False, dist.whittaker)
-
-
-def allPairsABC(sets):
-    """(a,b,c) for every i<j in row-major order -> uint64 [npairs, 3]"""
-    N = len(sets)
-    (I, J) = np.triu_indices(N, 1)
-    return (I, J, _native.allpairs_abc(sets))
+def rows(paths, abc, columns):
+    """the table body: pairs in row-major order of the upper triangle, which is zb_allpairs_abc's order"""
+    p = 0
+    for i in range(len(paths)):
+        for j in range(i + 1, len(paths)):
+            a, b, c = (int(v) for v in abc[p])
+            p += 1
+            yield '\t'.join([paths[i], paths[j]] + ['%g' % MEASURES[m][1](a, b, c) for m in columns])
 
 
 def main(argv):
     opts = docopt.docopt(__doc__, argv)
-
-    if "list" in opts['-M']:
-        msg = []
-        for m in sorted(measures.keys()):
-            msg.append(m + '\t' + measures[m].desc)
-        print('\n'.join(msg))
+    if 'list' in opts['-M']:
+        print('\n'.join(name + '\t' + MEASURES[name][0] for name in sorted(MEASURES)))
         return
-
-    allMs = sorted(measures.keys())
-
-    seen = set([])
-    bad = False
-    for mo in opts['-M']:
-        found = False
-        for m in allMs:
-            if fnmatch.fnmatch(m, mo):
-                seen.add(m)
-                found = True
-        if not found:
-            print('warning: measure \'%s\' not found. Use -M list to see all measures.' % (mo,), file=sys.stderr)
-            bad = True
-    ms = sorted(seen)
-
-    if len(ms) == 0 or bad:
+    columns = select(opts['-M'])
+    if not columns:
         return
-
     K = int(opts['<k>'])
-
-    fns = opts['<input>']
-    N = len(fns)
-
-    hdr = ['lhs.name', 'rhs.name']
-    fmt = ['%s', '%s']
-    vecNeeded = None
-    setNeeded = None
-    for m in ms:
-        hdr.append(m)
-        fmt.append('%g')
-        if measures[m].vec:
-            vecNeeded = m
-        else:
-            setNeeded = m
-    fmt = '\t'.join(fmt)
-
-    print('\t'.join(hdr))
+    paths = opts['<input>']
+    print('\t'.join(['lhs.name', 'rhs.name'] + columns))
     sys.stdout.flush()
-    if N == 0:
+    if not paths:
         return
-    if vecNeeded is not None:
-        measures[vecNeeded].prep(K, fns[0])     # TypeError, as the reference's first prep call
-    sets = [measures[setNeeded].prep(K, fn) for fn in fns]
-    (I, J, abc) = allPairsABC(sets)
-    out = []
-    for p in range(len(I)):
-        (a, b, c) = (int(abc[p, 0]), int(abc[p, 1]), int(abc[p, 2]))
-        vs = [fns[I[p]], fns[J[p]]]
-        for m in ms:
-            vs.append(measures[m].measure(a, b, c))
-        out.append(fmt % tuple(vs))
-        if len(out) >= 4096:
-            print('\n'.join(out))
-            out = []
-    if out:
-        print('\n'.join(out))
+    if any(MEASURES[m][1] is None for m in columns):
+        with kmers(paths[0], 'r') as z:          # the reference gets as far as opening the first file (and its K check)
+            if z.meta['K'] < K:
+                raise MismatchedK(K, z.meta['K'])
+        raise TypeError("cannot unpack non-iterable int object")
+    sets = [projected(K, path) for path in paths]
+    abc = _native.allpairs_abc(sets)
+    pending = []
+    for line in rows(paths, abc, columns):
+        pending.append(line)
+        if len(pending) == 4096:
+            print('\n'.join(pending))
+            pending = []
+    if pending:
+        print('\n'.join(pending))
     for s in sets:
         s.free()
 

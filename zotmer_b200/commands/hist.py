@@ -1,27 +1,27 @@
-"""
-Usage:
-    zot hist <input>...
-
-Options:
-    -u              update the input container to include the histogram
-"""
-# Drop-in for zotmer/commands/hist.py:14-24 (metadata only; the histogram itself is computed by
-# zb_set_stats inside kmerize/merge).
+# `zot hist` (zotmer/commands/hist.py:14-24): print the count histogram stored in each container's metadata, one
+# "file <tab> count <tab> number of k-mers" line per count in ascending order.  Nothing is scanned: the histogram was
+# computed on the device (zb_set_stats) when kmerize / merge wrote the file.
 import sys
 
 from zotmer_b200 import docopt_mini as docopt
+from zotmer_b200 import usage
 from zotmer_b200.library.kmers import kmers
+
+__doc__ = usage.HIST
+
+
+def histRows(path):
+    """[(count, number of k-mers)] ascending by count; [] for a container without a histogram"""
+    with kmers(path, 'r') as z:
+        stored = z.meta.get('hist')
+    if stored is None:
+        return []
+    return sorted((int(count), n) for (count, n) in stored.items())
 
 
 def main(argv):
-    opts = docopt.docopt(__doc__, argv)
-
-    for inp in opts['<input>']:
-        with kmers(inp, 'r') as z:
-            if 'hist' in z.meta:
-                h = sorted((int(f), c) for (f, c) in z.meta['hist'].items())
-                for (f, c) in h:
-                    print('%s\t%d\t%d' % (inp, f, c))
+    for path in docopt.docopt(__doc__, argv)['<input>']:
+        sys.stdout.write(''.join('%s\t%d\t%d\n' % (path, count, n) for (count, n) in histRows(path)))
 
 
 if __name__ == '__main__':

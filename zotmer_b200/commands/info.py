@@ -1,21 +1,18 @@
-"""
-Usage:
-    zot info <input>...
-"""
-# Drop-in for zotmer/commands/info.py:11-19.
+# `zot info` (zotmer/commands/info.py:11-19): the metadata of each container, one "key value" line per entry in key order.
 import sys
 
 from zotmer_b200 import docopt_mini as docopt
-from zotmer_b200.library.kmers import kmers
+from zotmer_b200 import usage
+from zotmer_b200.library.setio import readMeta
+
+__doc__ = usage.INFO
 
 
 def main(argv):
-    opts = docopt.docopt(__doc__, argv)
-
-    for inp in opts['<input>']:
-        with kmers(inp, 'r') as z:
-            for (k, v) in sorted(z.meta.items()):
-                print(k, v)
+    for path in docopt.docopt(__doc__, argv)['<input>']:
+        meta = readMeta(path)
+        for key in sorted(meta):
+            print(key, meta[key])
 
 
 if __name__ == '__main__':

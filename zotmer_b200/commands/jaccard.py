@@ -1,154 +1,116 @@
-"""
-Usage:
-    zot jaccard [-abp P] <input>...
-
-Compute Jaccard indexes between k-mer sets. By default, indexes are
-computed only between the first k-mer set and all the remaining
-k-mer sets. If the -a option is given, all pairwise indexes are
-computed.  If the -p P option is given, a Null hypothesis test is
-performed for the hypothesis that the underlying Jaccard Index is
-less than P. This is particularly useful if subsets of k-mers are
-being used (NB, if the k-mer sets are large, the statistics can be
-very expensive to compute).
-
-Options:
-    -a          print all pairwise distances
-    -p P        Jaccard distance thresshhold for p-value computation
-"""
-# Drop-in for zotmer/commands/jaccard.py:101-167.  The two-pointer jaccard() (:31-54) is
-# zb_pairs_abc on the device; the beta-quantile statistics (:56-83) stay in host Python.
+# `zot jaccard` (zotmer/commands/jaccard.py:85-167): sizes, intersection, union and Jaccard index of pairs of k-mer sets
+# -- the first input against all the others, or all pairs with -a; with -p P also a 90 % interval and the log10
+# probability that the index is below P.  A single FASTA input is treated as one set (K = 25, both strands) per record
+# (:110-142).  The reference walks two sorted arrays per pair (jaccard(), :31-54); here the sets live on the device and
+# (both, only left, only right) come from zb_allpairs_abc / zb_pairs_abc; the statistics are host floats
+# (library/stats.py).  Kept: every line is flushed as it is printed; a pair of files with different K stops the run
+# with "mismatched K: <file>" and exit status 1 after the pairs before it were printed.
 import math
 import sys
 
 import numpy as np
 
-from zotmer_b200 import docopt_mini as docopt
 from zotmer_b200 import _native
+from zotmer_b200 import docopt_mini as docopt
+from zotmer_b200 import usage
 from zotmer_b200.library.file import readBytes, readFasta
 from zotmer_b200.library.files import readKmerSet
 from zotmer_b200.library.kmers import kmers
-from zotmer_b200.library.reads import stripCompressionSuffix
-from zotmer_b200.library.stats import logAdd, logChoose
+from zotmer_b200.library.stats import betaQuantile, logBetaSeries
+
+__doc__ = usage.JACCARD
+FASTA_K = 25
+
+
+def isFasta(name):
+    """commands/jaccard.py:90-99: the suffix rule of THIS command (only .gz is looked through)"""
+    stem = name[:-3] if name.endswith('.gz') else name
+    return stem.endswith(('.fa', '.fasta', '.fas', '.fna'))
 
 
 def logIx(x, m, n):
-    "jaccard.py:56-70"
-    lx = math.log(x)
-    j = m
-    v = logChoose(n + j - 1, j)
-    s = v + j * lx
-    while True:
-        j += 1
-        v += math.log((n + j - 1.0) / j)
-        t = v + j * lx
-        u = logAdd(s, t)
-        if u == s:
-            break
-        s = u
-    return n * math.log1p(-x) + s
+    return logBetaSeries(x, m, n)
 
 
 def quantBeta(q, m, n):
-    "jaccard.py:72-83"
-    lq = math.log(q)
-    l = 1e-10
-    h = 1 - 1e-10
-    while (h - l) > 1e-7:
-        x = (h + l) / 2.0
-        lp = logIx(x, m, n)
-        if lp < lq:
-            l = x
-        else:
-            h = x
-    return l
+    return betaQuantile(q, m, n)
 
 
-def isFasta(nm):
-    "jaccard.py:90-99 (only .gz is stripped here)"
-    bnm = nm[:-3] if nm.endswith('.gz') else nm
-    return bnm.endswith((".fa", ".fasta", ".fas", ".fna"))
-
-
-def _line(xnm, ynm, xz, yz, isec, union, p):
-    d = float(isec) / float(union)
+def describe(left, right, nleft, nright, both, either, p):
+    """one output line"""
+    index = float(both) / float(either)
+    fields = '%s\t%s\t%d\t%d\t%d\t%d\t%f' % (left, right, nleft, nright, both, either, index)
     if p is None:
-        return '%s\t%s\t%d\t%d\t%d\t%d\t%f' % (xnm, ynm, xz, yz, isec, union, d)
-    pv = logIx(p, isec + 1, (union - isec) + 1) / math.log(10)
-    q05 = quantBeta(0.05, isec + 1, (union - isec) + 1)
-    q95 = quantBeta(0.95, isec + 1, (union - isec) + 1)
-    return '%s\t%s\t%d\t%d\t%d\t%d\t%f\t-%f\t+%f\t%f' % (xnm, ynm, xz, yz, isec, union, d, d - q05, q95 - d, pv)
+        return fields
+    hits, misses = both + 1, (either - both) + 1
+    below = logBetaSeries(p, hits, misses) / math.log(10)
+    q05 = betaQuantile(0.05, hits, misses)
+    q95 = betaQuantile(0.95, hits, misses)
+    return fields + '\t-%f\t+%f\t%f' % (index - q05, q95 - index, below)
 
 
-def _report(names, sets, pairs, p):
-    I = np.array([i for (i, j) in pairs], dtype=np.uint32)
-    J = np.array([j for (i, j) in pairs], dtype=np.uint32)
+def cardinalities(sets, pairs):
+    """(both, only left, only right) per listed pair; the all-pairs kernel when the list is the whole upper triangle"""
     n = len(sets)
     if n > 2 and len(pairs) == n * (n - 1) // 2:
-        # -a over every input: the tiled all-pairs kernel (same row-major pair order)
-        abc = _native.allpairs_abc(sets)
-    else:
-        abc = _native.pairs_abc(sets, I, J)
-    sizes = [len(s) for s in sets]
-    for q in range(len(pairs)):
-        (i, j) = pairs[q]
-        isec = int(abc[q, 0])
-        union = isec + int(abc[q, 1]) + int(abc[q, 2])
-        print(_line(names[i], names[j], sizes[i], sizes[j], isec, union, p))
+        return _native.allpairs_abc(sets)          # same row-major pair order
+    left = np.array([i for (i, _) in pairs], dtype=np.uint32)
+    right = np.array([j for (_, j) in pairs], dtype=np.uint32)
+    return _native.pairs_abc(sets, left, right)
+
+
+def report(names, sets, pairs, p):
+    abc = cardinalities(sets, pairs)
+    for row, (i, j) in enumerate(pairs):
+        both = int(abc[row, 0])
+        either = both + int(abc[row, 1]) + int(abc[row, 2])
+        print(describe(names[i], names[j], len(sets[i]), len(sets[j]), both, either, p))
         sys.stdout.flush()
+
+
+def recordSets(path):
+    """one (name, both-strand 25-mer set) per record of a FASTA file"""
+    names, sets = [], []
+    for (header, seq) in readFasta(readBytes(path)):
+        km = _native.Kmerizer(FASTA_K)
+        km.feed(b'>r\n' + seq + b'\n', True)
+        (kset, _) = km.finish()
+        km.close()
+        names.append(header.split()[0].decode('latin-1'))
+        sets.append(kset)
+    return names, sets
 
 
 def main(argv):
     opts = docopt.docopt(__doc__, argv)
+    paths = opts['<input>']
+    p = float(opts['-p']) if opts['-p'] is not None else None
 
-    fns = opts['<input>']
-
-    p = None
-    if opts['-p'] is not None:
-        p = float(opts['-p'])
-
-    if len(fns) == 1 and isFasta(fns[0]):
-        # one k-mer set (K=25, both strands) per FASTA record -- jaccard.py:110-142
-        K = 25
-        names = []
-        sets = []
-        for (nm, seq) in readFasta(readBytes(fns[0])):
-            km = _native.Kmerizer(K)
-            km.feed(b'>r\n' + seq + b'\n', True)
-            (s, _) = km.finish()
-            km.close()
-            names.append(nm.split()[0].decode('latin-1'))
-            sets.append(s)
-        Z = 1
-        if opts['-a']:
-            Z = len(sets)
+    if len(paths) == 1 and isFasta(paths[0]):
+        names, sets = recordSets(paths[0])
         print(len(sets))
-        pairs = [(i, j) for i in range(Z) for j in range(i + 1, len(sets))]
-        _report(names, sets, pairs, p)
+        firsts = len(sets) if opts['-a'] else 1
+        report(names, sets, [(i, j) for i in range(firsts) for j in range(i + 1, len(sets))], p)
         return
 
-    Z = 1
-    if opts['-a']:
-        Z = len(fns)
-
-    Ks = []
-    sets = []
-    for fn in fns:
-        with kmers(fn, 'r') as z:
-            Ks.append(z.meta['K'])
+    ks, sets = [], []
+    for path in paths:
+        with kmers(path, 'r') as z:
+            ks.append(z.meta['K'])
             sets.append(readKmerSet(z, counts=False))
-    pairs = []
-    bad = None
-    for i in range(Z):
-        for j in range(i + 1, len(fns)):
-            if Ks[i] != Ks[j]:
-                bad = fns[j]
+    firsts = len(paths) if opts['-a'] else 1
+    pairs, offender = [], None
+    for i in range(firsts):
+        for j in range(i + 1, len(paths)):
+            if ks[i] != ks[j]:
+                offender = paths[j]
                 break
             pairs.append((i, j))
-        if bad is not None:
+        if offender is not None:
             break
-    _report(fns, sets, pairs, p)
-    if bad is not None:
-        print('mismatched K:', bad, file=sys.stderr)
+    report(paths, sets, pairs, p)
+    if offender is not None:
+        print('mismatched K:', offender, file=sys.stderr)
         sys.exit(1)
 
 

@@ -1,25 +1,3 @@
-"""
-Usage:
-    zot kmerize [options] <k> <output> <input>...
-
-Kmerize FASTA or FASTQ inputs to produce a standard container object.
-
-Arguments:
-    <k>         the length of the k-mers. Recommended values: 10-30
-    <output>    the name of the output file.
-                recommended naming convention
-                    - mykmers.k25 for a k-mer set of 25-mers
-                    - mykmers.kf25 for a k-mer frequency set of 25-mers
-                    - mykmers.e25 for an expanded k-mer set of 25-mers
-
-Options:
-    -m MEM      in-memory buffer size (in MB)
-    -C BAITS    capture mode - use kmers from the given FASTA file.
-    -D FRAC     subsample k-mers, using FRAC proportion of k-mers
-    -S SEED     if -D is given, give a seed for determining the
-                subspace (defaults to 0).
-    -v          produce verbose progress messages
-"""
 # Drop-in for zotmer/commands/kmerize.py:450-562.  The per-record Python loop (reads() ->
 # kmersList -> acgt tally -> KmerAccumulator2 -> radix_sort -> merge, :490-545) is replaced by
 # zb_kmerize_* : raw file bytes go to the GPU, which parses, extracts both strands, sorts and counts.
@@ -33,6 +11,9 @@ from zotmer_b200.library.file import readBytes
 from zotmer_b200.library.files import writeKmerSet
 from zotmer_b200.library.reads import isFasta, pieces
 import zotmer_b200.library.kmers as zotk
+from zotmer_b200 import usage
+
+__doc__ = usage.KMERIZE
 
 
 def kmerizeFiles(K, inputs, device=0, verbose=False, baits=None):

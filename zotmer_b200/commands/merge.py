@@ -1,7 +1,3 @@
-"""
-Usage:
-    zot merge <output> <input>...
-"""
 # Drop-in for zotmer/commands/merge.py:165-253.  The pairwise generator merge (:26-86) and the
 # heap-of-radix-blocks N-way merge (:127-163) are replaced by zb_merge (merge-path + reduce-by-key
 # on the device); hist/acgt come from zb_set_stats.  The reference's behaviour for 1 and 2 inputs is
@@ -13,6 +9,9 @@ from zotmer_b200 import docopt_mini as docopt
 from zotmer_b200 import _native
 from zotmer_b200.library.kmers import kmers
 from zotmer_b200.library.files import readKmerSet, writeKmerSet
+from zotmer_b200 import usage
+
+__doc__ = usage.MERGE
 
 
 def _histDict(st):

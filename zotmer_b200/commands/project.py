@@ -1,53 +1,36 @@
-"""
-Usage:
-    zot project <ref> <output> <input>
-
-Project one or more inputs on to a reference set. For each k-mer in <ref>,
-a whitespace separated 0 or a 1 is printed indicating whether that k-mer
-was present in the input, with a separate line for each input k-mer set.
-"""
-# Drop-in for zotmer/commands/project.py:42-70: the output holds the entries of <input> whose k-mer occurs in
-# <ref> (project1 / project2, :18-40 = a sorted intersection that keeps the input's counts) -- zb_restrict on
-# the device.  As in the reference the histogram is copied from the input, not recomputed (:68).
+# `zot project` (zotmer/commands/project.py:18-70): the entries of <input> whose k-mer also occurs in <ref>, with the
+# input's counts (project1 / project2 walk the two sorted streams; here zb_restrict on the device).  Kept from the
+# reference: K of the two files must agree ("mismatched K (n)" on stderr, exit status 1, nothing written); an input
+# without counts gives an output without counts; the histogram is copied from the input, not recomputed (:68).
 import sys
 
 from zotmer_b200 import docopt_mini as docopt
-from zotmer_b200.library.kmers import kmers
-from zotmer_b200.library.files import readKmerSet, writeKmerSet, writeWords
+from zotmer_b200 import usage
+from zotmer_b200.library import setio
+
+__doc__ = usage.PROJECT
 
 
 def main(argv):
     opts = docopt.docopt(__doc__, argv)
-
-    with kmers(opts['<ref>'], 'r') as z:
-        K = z.meta['K']
-        xs = readKmerSet(z, counts=False)
-
-    with kmers(opts['<input>'], 'r') as z0:
-        K0 = z0.meta['K']
-        if K0 != K:
-            print("mismatched K (%d)" % (K0, ), file=sys.stderr)
-            sys.exit(1)
-
-        with kmers(opts['<output>'], 'w') as z:
-            z.meta['K'] = K
-            if 'counts' in z0.meta:
-                ys = readKmerSet(z0)
-                zs = ys.restrict(xs)
-                writeKmerSet(z, zs)
-                z.meta['kmers'] = 'kmers'
-                z.meta['counts'] = 'counts'
-            else:
-                ys = readKmerSet(z0, counts=False)
-                zs = ys.restrict(xs)
-                (kw, _) = zs.encode()
-                with z.add_stream('kmers') as f:
-                    writeWords(f, kw)
-                z.meta['kmers'] = 'kmers'
-            z.meta['hist'] = z0.meta['hist']
-            ys.free()
-            zs.free()
-    xs.free()
+    ref_meta = setio.readMeta(opts['<ref>'])
+    in_meta = setio.readMeta(opts['<input>'])
+    K = ref_meta['K']
+    if in_meta['K'] != K:
+        print("mismatched K (%d)" % (in_meta['K'],), file=sys.stderr)
+        sys.exit(1)
+    counted = 'counts' in in_meta
+    wanted, _ = setio.readSetFile(opts['<ref>'], counts=False)
+    given, _ = setio.readSetFile(opts['<input>'], counts=counted)
+    common = given.restrict(wanted)
+    given.free()
+    wanted.free()
+    out = {'K': K, 'kmers': 'kmers'}
+    if counted:
+        out['counts'] = 'counts'
+    out['hist'] = in_meta['hist']
+    setio.writeSetFile(opts['<output>'], common, out, counts=counted)
+    common.free()
 
 
 if __name__ == '__main__':

@@ -1,147 +1,153 @@
-"""
-The casket container (mirrors zotmer/library/container/casket.py:52-234, byte for byte on disk):
-
-    blob ... blob | TOC as JSON {name: [[offset, length], ...]} | u64 little-endian length of the TOC
-
-`open(name)` reads the LAST entry of a name (casket.py:185).  JSON is written with the default
-separators and in insertion order (the PyPy2 / Python 3 layout).
-"""
+# The "casket" container of the k-mer set files (on-disk format of zotmer/library/container/casket.py:52-234, byte for
+# byte):
+#
+#     entry bytes ... entry bytes | table of contents, JSON {name: [[offset, length], ...]} | u64 LE: length of that JSON
+#
+# A name may occur several times (every write appends a version); readers see the LAST version (casket.py:185).  The
+# table is written when a container opened for writing is closed, in insertion order and with json's default
+# separators (what the reference's files look like under PyPy2 / any Python >= 3.7).  If a command dies inside
+# `with casket(...)`, the file is left without a table, as the reference leaves it (casket.py:213-217).
 import json
-import os
 import struct
+
+TAIL = struct.Struct('<Q')
 
 
 class MultipleOpenFiles(Exception):
+    """an entry was started while a streamed entry of the same container was still open"""
+
     def __init__(self):
-        super(MultipleOpenFiles, self).__init__('cannot add to archive while streaming object open')
+        Exception.__init__(self, 'cannot add to archive while streaming object open')
 
 
-_block_size_ = 1024 * 1024
+class Entry(object):
+    """read access to one stored entry: read() / read(n) like a file"""
 
+    def __init__(self, fileobj, offset, length):
+        self._f = fileobj
+        self._at = offset
+        self._left = length
 
-class CasketReader(object):
-    def __init__(self, fo, p, l):
-        self.fo, self.p, self.l, self.o = fo, p, l, 0
-
-    def read(self, z=None):
-        if z is None:
-            z = self.l - self.o
-        z = min(z, self.l - self.o)
-        if z == 0:
+    def read(self, n=None):
+        take = self._left if n is None else min(n, self._left)
+        if take == 0:
             return b''
-        self.fo.seek(self.p + self.o, os.SEEK_SET)
-        w = self.fo.read(z)
-        assert len(w) == z
-        self.o += z
-        return w
+        self._f.seek(self._at)
+        data = self._f.read(take)
+        assert len(data) == take
+        self._at += take
+        self._left -= take
+        return data
 
 
-class CasketStreamWriter(object):
-    def __init__(self, ar, afn):
-        self.ar, self.afn = ar, afn
-        self.ar.fo.seek(0, os.SEEK_END)
-        self.p = self.ar.fo.tell()
-        self.l = 0
-        self.closed = False
+class EntryWriter(object):
+    """an entry written piece by piece (`with z.add_stream(name) as f: f.write(...)`); it is entered into the table
+    when it is closed, and nothing else may be added to the container until then"""
 
-    def write(self, dat):
-        self.l += len(dat)
-        self.ar.fo.write(dat)
+    def __init__(self, owner, name):
+        self._owner = owner
+        self._name = name
+        self._start = owner._end()
+        self._size = 0
+        self._open = True
+
+    def write(self, data):
+        self._owner.fo.write(data)
+        self._size += len(data)
 
     def close(self):
-        assert not self.closed
-        self.ar.updateToc(self.afn, self.p, self.l)
-        self.ar.fip = None
-        self.closed = True
+        assert self._open
+        self._open = False
+        self._owner._streaming = None
+        self._owner._record(self._name, self._start, self._size)
 
     def __enter__(self):
         return self
 
-    def __exit__(self, t, v, tb):
-        if t is not None:
-            return False
-        if not self.closed:
+    def __exit__(self, etype, value, tb):
+        if etype is None and self._open:
             self.close()
-        return True
+        return etype is None
 
 
 class casket(object):
     def __init__(self, fn, mode='r'):
+        if mode not in ('r', 'w'):
+            raise ValueError(mode)
         self.fn = fn
         self.mode = mode
         self.toc = {}
-        self.fip = None
+        self._streaming = None
+        self.fo = open(fn, mode + 'b')
+        self._dirty = (mode == 'w')
         if mode == 'r':
-            self.fo = open(fn, 'rb')
-            self._readToc()
-            self.stale = False
-        elif mode == 'w':
-            self.fo = open(fn, 'wb')
-            self.stale = True
-        else:
-            raise ValueError(mode)
+            self.fo.seek(-TAIL.size, 2)
+            (toc_len,) = TAIL.unpack(self.fo.read(TAIL.size))
+            self.fo.seek(-(TAIL.size + toc_len), 2)
+            self.toc = json.loads(self.fo.read(toc_len))
+
+    # ---- reading
+    def open(self, name):
+        assert self.mode == 'r'
+        offset, length = self.toc[name][-1]          # KeyError for a name that is not there
+        return Entry(self.fo, offset, length)
 
     def list(self):
-        return [(nm, ys[-1][1]) for (nm, ys) in sorted(self.toc.items())]
+        """[(name, length of its latest version)] in name order"""
+        return [(name, self.toc[name][-1][1]) for name in sorted(self.toc)]
 
-    def add_file(self, afn, fn):
-        assert self.mode == 'w'
-        if self.fip is not None:
-            raise MultipleOpenFiles
-        self.fo.seek(0, os.SEEK_END)
-        p = self.fo.tell()
-        l = 0
-        with open(fn, 'rb') as f:
-            w = f.read(_block_size_)
-            while len(w) > 0:
-                l += len(w)
-                self.fo.write(w)
-                w = f.read(_block_size_)
-        self.updateToc(afn, p, l)
+    # ---- writing
+    def _end(self):
+        self.fo.seek(0, 2)
+        return self.fo.tell()
 
-    def add_content(self, afn, data):
+    def _record(self, name, offset, length):
+        self.toc.setdefault(name, []).append((offset, length))
+        self._dirty = True
+
+    def _writable(self):
         assert self.mode == 'w'
-        if self.fip is not None:
+        if self._streaming is not None:
             raise MultipleOpenFiles
+
+    def add_content(self, name, data):
+        self._writable()
         if isinstance(data, str):
             data = data.encode('latin-1')
-        self.fo.seek(0, os.SEEK_END)
-        p = self.fo.tell()
+        at = self._end()
         self.fo.write(data)
-        self.updateToc(afn, p, len(data))
+        self._record(name, at, len(data))
 
-    def add_stream(self, afn):
-        assert self.mode == 'w'
-        if self.fip is not None:
-            raise MultipleOpenFiles
-        self.fip = CasketStreamWriter(self, afn)
-        return self.fip
+    def add_file(self, name, path, block=1 << 20):
+        self._writable()
+        at = self._end()
+        size = 0
+        with open(path, 'rb') as src:
+            for piece in iter(lambda: src.read(block), b''):
+                self.fo.write(piece)
+                size += len(piece)
+        self._record(name, at, size)
 
-    def open(self, afn):
-        assert self.mode == 'r'
-        (p, l) = self.toc[afn][-1]
-        return CasketReader(self.fo, p, l)
+    def add_stream(self, name):
+        self._writable()
+        self._streaming = EntryWriter(self, name)
+        return self._streaming
 
-    def updateToc(self, afn, p, l):
-        self.toc.setdefault(afn, []).append((p, l))
-        self.stale = True
-
-    def flush(self):
-        pass
-
+    # ---- closing
     def close(self):
         if self.fo is None:
             return
-        if self.stale:
-            self.flush()
-            self._writeToc()
+        if self._dirty:
+            toc = json.dumps(self.toc).encode('latin-1')
+            self._end()
+            self.fo.write(toc)
+            self.fo.write(TAIL.pack(len(toc)))
         self.fo.close()
         self.fo = None
-        self.stale = False
+        self._dirty = False
 
     def abandon(self):
-        """Close WITHOUT a table of contents: what the reference leaves behind when a command
-        raises inside `with casket(...)` (casket.py:213-217 returns before close())."""
+        """close WITHOUT writing a table of contents"""
         if self.fo is not None:
             self.fo.close()
             self.fo = None
@@ -149,22 +155,9 @@ class casket(object):
     def __enter__(self):
         return self
 
-    def __exit__(self, t, v, tb):
-        if t is not None:
+    def __exit__(self, etype, value, tb):
+        if etype is None:
+            self.close()
+        else:
             self.abandon()
-            return False
-        self.close()
-        return True
-
-    def _readToc(self):
-        self.fo.seek(-8, os.SEEK_END)
-        z = struct.unpack('<Q', self.fo.read(8))[0]
-        self.fo.seek(-(8 + z), os.SEEK_END)
-        self.toc = json.loads(self.fo.read(z))
-
-    def _writeToc(self):
-        w = json.dumps(self.toc).encode('latin-1')
-        self.fo.seek(0, os.SEEK_END)
-        self.fo.write(w)
-        self.fo.write(struct.pack('<Q', len(w)))
-        self.fo.flush()
+        return etype is None

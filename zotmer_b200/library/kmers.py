@@ -1,17 +1,20 @@
-"""k-mer set file = casket + JSON `__meta__` (mirrors zotmer/library/kmers.py:8-21)."""
+# A k-mer set file = a casket (library/casket.py) whose entry '__meta__' holds the JSON metadata (K, stream names, count
+# histogram, acgt frequencies, number of records) -- zotmer/library/kmers.py:8-21.  Reading parses the metadata up front;
+# a container opened for writing appends it when it is closed.
 import json
 
 from zotmer_b200.library.casket import casket
 
+META = '__meta__'
+
 
 class kmers(casket):
     def __init__(self, fn, mode):
-        super(kmers, self).__init__(fn, mode)
-        self.meta = {}
-        if mode == 'r':
-            self.meta = json.loads(self.open('__meta__').read())
+        casket.__init__(self, fn, mode)
+        self.meta = json.loads(self.open(META).read()) if mode == 'r' else {}
 
     def close(self):
-        if self.fo is not None and self.mode == 'w':
-            self.add_content('__meta__', json.dumps(self.meta))
-        super(kmers, self).close()
+        writing = self.mode == 'w' and self.fo is not None
+        if writing:
+            self.add_content(META, json.dumps(self.meta))
+        casket.close(self)
