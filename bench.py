@@ -566,7 +566,10 @@ def cpu_baseline():
     zo.words_to_bytes(zo.encode(zo.delta(tx)))
     zo.words_to_bytes(zo.encode(tc))
     dt = time.perf_counter() - t0
+    import shutil
+    pypy = shutil.which("pypy") or shutil.which("pypy3")
     return {"value": sample_reads * READ_LEN / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+            "pypy": pypy or "not installed on this box and not installable offline (north star: PyPy only if it installs offline)",
             "sample": "first %d of the %d reads (%.1f Mbases, %.1f s): kmerize+count, codec64 encode, trim; CPython %s "
                       "single thread (the reference has no parallelism); host has %d cores" % (
                           sample_reads, READS_PER_RANK, sample_reads * READ_LEN / 1e6, dt, sys.version.split()[0],
