@@ -435,6 +435,32 @@ def test_kmerize_low_complexity(nat, k):
     assert st["acgt_weighted"] == eacgt and st["hist"] == co.hist(ec.astype(np.uint64))
 
 
+@pytest.mark.parametrize("skew", [False, True])
+def test_kmerize_mirror_routes(nat, monkeypatch, skew):
+    """the both-strand union at the end of kmerize: the fused route (mirrored half ordered by its top bits only, united with
+    the canonical half inside key-range buckets in shared memory) against the classic route (ZB_SORT_COUNT=1: full sort of
+    the mirrored half + merge path) and the oracle.  skew: a two-letter genome puts most canonical k-mers into 16 of 256
+    buckets, which overflow, so the fused route must hand over to sort + merge after its top-bit passes."""
+    rng = np.random.default_rng(77 + skew)
+    genome = rnd_dna(rng, 150000)
+    reads = make_fastq(rng, genome, 12000, 150)
+    if skew:
+        two = np.frombuffer(b"AC", np.uint8)[rng.integers(0, 2, 300000)].tobytes()
+        reads += make_fastq(rng, two, 24000, 150)
+    ek, ec, _, enr = co.kmerize(25, [(reads, False)])
+    for mode in (None, "1"):
+        if mode is None:
+            monkeypatch.delenv("ZB_SORT_COUNT", raising=False)
+        else:
+            monkeypatch.setenv("ZB_SORT_COUNT", mode)
+        s, nr = run_kmerize(nat, 25, [(reads, False)])
+        ks, cc = s.fetch()
+        assert nr == enr
+        assert np.array_equal(ks, ek) and np.array_equal(cc, ec), mode
+    monkeypatch.delenv("ZB_SORT_COUNT", raising=False)
+    nat.Kmerizer(25, 0).close()     # re-read the switches: back to the default route
+
+
 def test_kmerize_palindromes_even_k(nat):
     pal = b"ACGTTGCAAGCTTGCAACGT"
     fa = b">p\n" + pal * 50 + b"\n>q\n" + b"AT" * 100 + b"\n"

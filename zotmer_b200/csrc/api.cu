@@ -524,25 +524,41 @@ int zb_kmerize_finish(zb_kmerizer* h, zb_set** result, uint64_t* n_records) {
     h->pending.release();
     h->pending_cap = 0;
     const size_t n = h->acc_n;
-    // both strands: mirror the canonical run, sort the mirrored half, merge
-    DBuf<uint64_t> rk(c, n), rk2(c, n), mk(c, n);
-    DBuf<uint32_t> rc(c, n), rc2(c, n), mc(c, n);
+    // both strands: mirror the canonical run and unite the two halves
+    DBuf<uint64_t> rk(c, n), rk2(c, n);
+    DBuf<uint32_t> rc(c, n), rc2(c, n);
     size_t nm;
     {
         Stage st(c, "mirror");
         nm = mirror_keys(c, h->k, h->acc_k.get(), h->acc_c.get(), n, rk.get(), rc.get());
     }
-    {
-        // the mirrored keys are distinct, so "sort + count" is a sort of (key, count) pairs
-        Stage st(c, "mirror_sort");
-        const size_t nm2 = sort_count(c, rk.get(), rk2.get(), rc.get(), rc2.get(), nm, 2 * h->k, mk.get(), mc.get(), true);
-        if (nm2 != nm) ZB_FAIL(ZB_E_CUDA, "mirror: %zu distinct reverse complements of %zu keys", nm2, nm);
+    zb_set* s = new_set(c, n + nm);
+    bool fused = false;
+    int which = 0;
+    if (g_sort_count_mode == 0 && n + nm > 0) {
+        Stage st(c, "mirror_merge");
+        fused = merge_mirrored(c, h->acc_k.get(), h->acc_c.get(), n, rk.get(), rk2.get(), rc.get(), rc2.get(), nm, 2 * h->k,
+                               s->k.get(), s->cnt.get(), &which);
+    }
+    if (!fused) {
+        // skewed key space (or a cross-check route): sort the mirrored half completely, then merge path
+        uint64_t* m0 = which ? rk2.get() : rk.get();
+        uint64_t* m1 = which ? rk.get() : rk2.get();
+        uint32_t* v0 = which ? rc2.get() : rc.get();
+        uint32_t* v1 = which ? rc.get() : rc2.get();
+        DBuf<uint64_t> mk(c, n);
+        DBuf<uint32_t> mc(c, n);
+        {
+            // the mirrored keys are distinct, so "sort + count" is a sort of (key, count) pairs
+            Stage st(c, "mirror_sort");
+            const size_t nm2 = sort_count(c, m0, m1, v0, v1, nm, 2 * h->k, mk.get(), mc.get(), true);
+            if (nm2 != nm) { delete s; ZB_FAIL(ZB_E_CUDA, "mirror: %zu distinct reverse complements of %zu keys", nm2, nm); }
+        }
+        Stage st_merge(c, "mirror_merge");
+        merge_pairs(c, h->acc_k.get(), h->acc_c.get(), n, mk.get(), mc.get(), nm, s->k.get(), s->cnt.get());
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
     }
     rk.release(); rk2.release(); rc.release(); rc2.release();
-    zb_set* s = new_set(c, n + nm);
-    Stage st_merge(c, "mirror_merge");
-    merge_pairs(c, h->acc_k.get(), h->acc_c.get(), n, mk.get(), mc.get(), nm, s->k.get(), s->cnt.get());
-    ZB_CUDA(cudaStreamSynchronize(c->stream));
     h->acc_k.release();
     h->acc_c.release();
     h->alt_k.release(); h->alt_c.release(); h->mrg_k.release(); h->mrg_c.release();

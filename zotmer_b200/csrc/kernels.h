@@ -53,6 +53,12 @@ extern int g_sort_cfg;   // onesweep CTA shape, see sort.cu  // digit width cap 
 // a violation is detected and reported as ZB_E_ARG.
 size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
                   uint64_t* out_k, uint32_t* out_c, bool distinct = false);
+// The both-strand set of kmerize: the sorted canonical counted set (ck, cc, n) united with its nm mirrored pairs
+// (mk, mc: distinct, disjoint from ck, unordered; destroyed, mk2 / mc2 are scratch) into out_k / out_c (n + nm entries).
+// Returns false when the key space is too skewed for its buckets; M is then still complete in mk/mc (which_out = 0) or
+// mk2/mc2 (1) and the caller sorts + merges instead.
+bool merge_mirrored(Ctx* c, const uint64_t* ck, const uint32_t* cc, size_t n, uint64_t* mk, uint64_t* mk2, uint32_t* mc,
+                    uint32_t* mc2, size_t nm, int key_bits, uint64_t* out_k, uint32_t* out_c, int* which_out);
 extern int g_sort_count_mode;  // 0 = auto, 1 = always the classic full LSD sort + reduce_by_key (ZB_SORT_COUNT)
 
 // ---- nwaymerge.cu ----------------------------------------------------------------------------

@@ -845,6 +845,162 @@ static size_t sort_count_buckets(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v
     return n_out;
 }
 
+// =============================================================================== mirrored half, fused
+// The last step of kmerize: the both-strand set is the canonical counted set C (sorted) united with its reverse
+// complements M (mirror_keys: distinct, disjoint from C, in no order).  Instead of sorting M completely, compacting it
+// and merge-pathing it with C (three trips through HBM), M is ordered by its top cb bits only (LSD passes), and one CTA
+// per key-range bucket then has everything in shared memory: the bucket's slice of C (already sorted) and the bucket of
+// M, which it counting-sorts by the next key bits.  An element of M lands at (its rank in M's bucket) + (keys of the C
+// slice below it, by bisection); an element of C at (its index in the slice) + (keys of M's bucket below it: the
+// groups before its own, plus a look at its own group).  The output position of the bucket is known beforehand --
+// nothing is deduplicated -- so the result is written in place, without staging or compaction.
+static constexpr int MM_THREADS = 512;
+static constexpr int MM_PER = 8;
+static constexpr int MM_CAP = MM_THREADS * MM_PER;     // entries of one bucket: C slice + M bucket
+static constexpr int MM_FINE = 2048;
+static constexpr int MM_FINE_BITS = 11;
+
+__global__ void __launch_bounds__(MM_THREADS, 2)
+mirror_merge_kernel(const uint64_t* __restrict__ ck, const uint32_t* __restrict__ cc, const uint64_t* __restrict__ startC,
+                    const uint64_t* __restrict__ mk, const uint32_t* __restrict__ mc, const uint64_t* __restrict__ startM,
+                    int fine_shift, uint32_t fine_mask, uint64_t* __restrict__ out_k, uint32_t* __restrict__ out_c,
+                    unsigned int* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char mm_raw[];
+    uint64_t* sCk = reinterpret_cast<uint64_t*>(mm_raw);                 // [MM_CAP] the C slice (sorted)
+    uint64_t* hs = sCk + MM_CAP;                                         // [MM_CAP] M's bucket grouped by fine digit
+    uint32_t* sCc = reinterpret_cast<uint32_t*>(hs + MM_CAP);            // [MM_CAP]
+    uint32_t* hc = sCc + MM_CAP;                                         // [MM_CAP]
+    uint32_t* hist = hc + MM_CAP;                                        // [MM_FINE + 1]
+    __shared__ uint32_t s_scan[MM_THREADS / 32 + 1];
+
+    const unsigned tid = threadIdx.x;
+    const uint32_t b = blockIdx.x;
+    const uint64_t c0 = startC[b], m0 = startM[b];
+    const uint64_t nC64 = startC[b + 1] - c0, nM64 = startM[b + 1] - m0;
+    if (nC64 + nM64 > (uint64_t)MM_CAP) {
+        if (tid == 0) atomicExch(err, 1u);      // the caller falls back to sort + merge
+        return;
+    }
+    const int nC = (int)nC64, nM = (int)nM64;
+    if (nC + nM == 0) return;
+    const uint64_t o0 = c0 + m0;
+#pragma unroll
+    for (int j = 0; j < MM_FINE / MM_THREADS; j++) hist[j * MM_THREADS + tid] = 0;
+    for (int i = (int)tid; i < nC; i += MM_THREADS) {
+        sCk[i] = __ldg(ck + c0 + i);
+        sCc[i] = __ldg(cc + c0 + i);
+    }
+    uint64_t kx[MM_PER];
+    uint32_t wx[MM_PER], rd[MM_PER];
+    const int jn = (nM + MM_THREADS - 1) / MM_THREADS;
+#pragma unroll
+    for (int j = 0; j < MM_PER; j++) {
+        if (j >= jn) break;
+        const int q = j * MM_THREADS + (int)tid;
+        kx[j] = (q < nM) ? __ldg(mk + m0 + q) : 0ull;
+        wx[j] = (q < nM) ? __ldg(mc + m0 + q) : 0u;
+    }
+    __syncthreads();
+    // ---- M: counting sort by the next key bits
+#pragma unroll
+    for (int j = 0; j < MM_PER; j++) {
+        if (j >= jn) break;
+        if (j * MM_THREADS + (int)tid < nM) {
+            const uint32_t d = (uint32_t)(kx[j] >> fine_shift) & fine_mask;
+            rd[j] = atomicAdd(&hist[d], 1u) | (d << 16);
+        }
+    }
+    __syncthreads();
+    {
+        constexpr int GP = MM_FINE / MM_THREADS;
+        uint32_t v[GP];
+        uint32_t t = 0;
+#pragma unroll
+        for (int u = 0; u < GP; u++) { v[u] = hist[tid * GP + u]; t += v[u]; }
+        uint32_t all;
+        uint32_t ex = block_excl_scan<MM_THREADS, uint32_t, false>(t, s_scan, &all);
+#pragma unroll
+        for (int u = 0; u < GP; u++) { hist[tid * GP + u] = ex; ex += v[u]; }
+        if (tid == 0) hist[MM_FINE] = all;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < MM_PER; j++) {
+        if (j >= jn) break;
+        if (j * MM_THREADS + (int)tid < nM) {
+            const uint32_t p = hist[rd[j] >> 16] + (rd[j] & 0xffffu);
+            hs[p] = kx[j];
+            hc[p] = wx[j];
+        }
+    }
+    __syncthreads();
+    // ---- M elements: rank inside the group + keys of the C slice below
+    for (int p = (int)tid; p < nM; p += MM_THREADS) {
+        const uint64_t x = hs[p];
+        const uint32_t d = (uint32_t)(x >> fine_shift) & fine_mask;
+        const int g0 = (int)hist[d], g1 = (int)hist[d + 1];
+        int r = g0;
+        for (int p2 = g0; p2 < g1; p2++) r += (hs[p2] < x) ? 1 : 0;
+        int lo = 0, hi = nC;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (sCk[mid] < x) lo = mid + 1; else hi = mid;
+        }
+        out_k[o0 + r + lo] = x;
+        out_c[o0 + r + lo] = hc[p];
+    }
+    // ---- C elements: index in the slice + keys of M's bucket below (whole groups before mine, then my own group)
+    for (int i = (int)tid; i < nC; i += MM_THREADS) {
+        const uint64_t x = sCk[i];
+        const uint32_t d = (uint32_t)(x >> fine_shift) & fine_mask;
+        const int g0 = (int)hist[d], g1 = (int)hist[d + 1];
+        int r = g0;
+        for (int p2 = g0; p2 < g1; p2++) r += (hs[p2] < x) ? 1 : 0;
+        out_k[o0 + i + r] = x;
+        out_c[o0 + i + r] = sCc[i];
+    }
+}
+
+// out = C united with M (nm mirrored pairs in mk/mc, destroyed; mk2/mc2 are ping-pong scratch).  Returns false when a
+// bucket does not fit (skewed key space): the caller sorts M and merges instead; M is then still complete in (*mk_out).
+bool merge_mirrored(Ctx* c, const uint64_t* ck, const uint32_t* cc, size_t n, uint64_t* mk, uint64_t* mk2, uint32_t* mc,
+                    uint32_t* mc2, size_t nm, int key_bits, uint64_t* out_k, uint32_t* out_c, int* which_out) {
+    *which_out = 0;
+    if (key_bits < 1) key_bits = 1;
+    if (key_bits > 64) key_bits = 64;
+    int cb = 0;
+    while (cb < key_bits && ((n + nm) >> cb) > (size_t)MM_CAP * 2 / 3) cb++;   // C is A-heavy where M is T-heavy: their sum is even
+    if (cb > 24) return false;
+    const uint32_t nb = 1u << cb;
+    const int shift = key_bits - cb;
+    int which = 0;
+    if (cb > 0 && nm > 0) {
+        Stage st(c, "sort");
+        which = radix_sort_range(c, mk, mk2, mc, mc2, nm, shift, cb, false);
+    }
+    *which_out = which;
+    const uint64_t* sk = which ? mk2 : mk;
+    const uint32_t* sv = which ? mc2 : mc;
+    const int fb = std::min(MM_FINE_BITS, shift);
+    DBuf<uint64_t> starts(c, 2 * ((size_t)nb + 1) + 2);
+    uint64_t* startC = starts.get();
+    uint64_t* startM = starts.get() + nb + 1;
+    unsigned int* err = reinterpret_cast<unsigned int*>(starts.get() + 2 * ((size_t)nb + 1));
+    ZB_CUDA(dev_memset(c, err, 0, 8));
+    Stage st(c, "mirror_buckets");
+    bc_bounds_kernel<<<(unsigned)div_up((size_t)nb + 1, 256), 256, 0, c->stream>>>(ck, n, shift, nb, startC);
+    ZB_LAUNCH_CHECK(c);
+    bc_bounds_kernel<<<(unsigned)div_up((size_t)nb + 1, 256), 256, 0, c->stream>>>(sk, nm, shift, nb, startM);
+    ZB_LAUNCH_CHECK(c);
+    const size_t smem = (size_t)MM_CAP * (8 + 8 + 4 + 4) + (size_t)(MM_FINE + 1) * 4;
+    ZB_CUDA(cudaFuncSetAttribute(mirror_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mirror_merge_kernel<<<nb, MM_THREADS, smem, c->stream>>>(ck, cc, startC, sk, sv, startM, shift - fb, (1u << fb) - 1u, out_k, out_c, err);
+    ZB_LAUNCH_CHECK(c);
+    ZB_CUDA(read_back(c, err, 4));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    return reinterpret_cast<uint32_t*>(c->h_scalars)[0] == 0;
+}
+
 // g_sort_count_mode (ZB_SORT_COUNT): 0 = bucket route (weighted sums: segment route), 1 = classic full sort +
 // reduce-by-key, 2 = segment route
 size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
