@@ -239,3 +239,30 @@ def test_compressed_inputs_inflate_like_gunzip(tmp_path):
     p4 = tmp_path / "d.fa.bz2"
     p4.write_bytes(bz2.compress(text[:300000]) + bz2.compress(text[300000:700000]))
     assert zfile.readBytes(str(p4)) == text[:700000]
+
+
+def test_map_bytes_and_pieces(tmp_path):
+    """mapBytes: plain files come back as a read-only mapping that `pieces` can cut (len / rfind / buffer protocol) and
+    numpy can view without a copy; empty, compressed and stdin-like inputs as bytes"""
+    import gzip
+    import numpy as np
+    from zotmer_b200.library import file as zfile
+    from zotmer_b200.library.reads import pieces
+    fq = b"".join(b"@r%d\nACGTACGTAC\n+\nIIIIIIIIII\n" % i for i in range(3000))
+    fa = b"".join(b">s%d\nACGTTGCA\nAACC\n" % i for i in range(3000))
+    for name, text, is_fa in (("a.fq", fq, False), ("b.fa", fa, True)):
+        p = tmp_path / name
+        p.write_bytes(text)
+        m = zfile.mapBytes(str(p))
+        assert not isinstance(m, bytes) and len(m) == len(text)
+        assert np.frombuffer(m, dtype=np.uint8).tobytes() == text
+        parts = [bytes(x) for x in pieces(m, is_fa, max_piece=4096)]
+        assert len(parts) > 5 and b"".join(parts) == text
+        assert parts == [bytes(x) for x in pieces(text, is_fa, max_piece=4096)]
+        assert all(x.startswith(b">" if is_fa else b"@r") for x in parts)
+    e = tmp_path / "e.fq"
+    e.write_bytes(b"")
+    assert zfile.mapBytes(str(e)) == b""
+    z = tmp_path / "z.fq.gz"
+    z.write_bytes(gzip.compress(fq))
+    assert zfile.mapBytes(str(z)) == fq

@@ -7,7 +7,7 @@ import sys
 
 from zotmer_b200 import docopt_mini as docopt
 from zotmer_b200 import _native
-from zotmer_b200.library.file import readBytes
+from zotmer_b200.library.file import mapBytes
 from zotmer_b200.library.files import writeKmerSet
 from zotmer_b200.library.reads import isFasta, pieces
 import zotmer_b200.library.kmers as zotk
@@ -24,7 +24,7 @@ def kmerizeFiles(K, inputs, device=0, verbose=False, baits=None):
         if baits is not None:
             km.set_baits(baits)
         for fn in inputs:
-            data = readBytes(fn)
+            data = mapBytes(fn)
             fa = isFasta(fn)
             if verbose:
                 print('reading %s (%d bytes, %s)' % (fn, len(data), 'FASTA' if fa else 'FASTQ'), file=sys.stderr)
@@ -40,7 +40,7 @@ def baitSet(K, fn, device=0):
     whatever its suffix)."""
     km = _native.Kmerizer(K, device)
     try:
-        data = readBytes(fn)
+        data = mapBytes(fn)
         for piece in pieces(data, True):
             km.feed(piece, True)
         (b, _) = km.finish()

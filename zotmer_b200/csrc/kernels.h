@@ -59,6 +59,7 @@ size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1
 // mk2/mc2 (1) and the caller sorts + merges instead.
 bool merge_mirrored(Ctx* c, const uint64_t* ck, const uint32_t* cc, size_t n, uint64_t* mk, uint64_t* mk2, uint32_t* mc,
                     uint32_t* mc2, size_t nm, int key_bits, uint64_t* out_k, uint32_t* out_c, int* which_out);
+extern int g_mm_cfg;           // mirror_merge_kernel shape (ZB_MM_CFG): 0 = 256 threads / 2048 entries, 1 = 512 / 4096
 extern int g_sort_count_mode;  // 0 = auto, 1 = always the classic full LSD sort + reduce_by_key (ZB_SORT_COUNT)
 
 // ---- nwaymerge.cu ----------------------------------------------------------------------------

@@ -854,111 +854,131 @@ static size_t sort_count_buckets(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v
 // slice below it, by bisection); an element of C at (its index in the slice) + (keys of M's bucket below it: the
 // groups before its own, plus a look at its own group).  The output position of the bucket is known beforehand --
 // nothing is deduplicated -- so the result is written in place, without staging or compaction.
-static constexpr int MM_THREADS = 512;
-static constexpr int MM_PER = 8;
-static constexpr int MM_CAP = MM_THREADS * MM_PER;     // entries of one bucket: C slice + M bucket
-static constexpr int MM_FINE = 2048;
-static constexpr int MM_FINE_BITS = 11;
+// Two shapes (g_mm_cfg / ZB_MM_CFG): 0 = 256 threads, buckets of <= 2048 entries, 1024 groups (48 KB: 4 CTAs per SM);
+// 1 = 512 threads, <= 4096 entries, 2048 groups (98 KB: 2 CTAs per SM).
+int g_mm_cfg = 0;
 
-__global__ void __launch_bounds__(MM_THREADS, 2)
+template <int THREADS, int PER, int FINE_BITS>
+__global__ void __launch_bounds__(THREADS, (THREADS == 256) ? 4 : 2)
 mirror_merge_kernel(const uint64_t* __restrict__ ck, const uint32_t* __restrict__ cc, const uint64_t* __restrict__ startC,
                     const uint64_t* __restrict__ mk, const uint32_t* __restrict__ mc, const uint64_t* __restrict__ startM,
                     int fine_shift, uint32_t fine_mask, uint64_t* __restrict__ out_k, uint32_t* __restrict__ out_c,
                     unsigned int* __restrict__ err) {
+    constexpr int CAP = THREADS * PER;
+    constexpr int FINE = 1 << FINE_BITS;
+    constexpr int GP = FINE / THREADS;
     extern __shared__ __align__(16) unsigned char mm_raw[];
-    uint64_t* sCk = reinterpret_cast<uint64_t*>(mm_raw);                 // [MM_CAP] the C slice (sorted)
-    uint64_t* hs = sCk + MM_CAP;                                         // [MM_CAP] M's bucket grouped by fine digit
-    uint32_t* sCc = reinterpret_cast<uint32_t*>(hs + MM_CAP);            // [MM_CAP]
-    uint32_t* hc = sCc + MM_CAP;                                         // [MM_CAP]
-    uint32_t* hist = hc + MM_CAP;                                        // [MM_FINE + 1]
-    __shared__ uint32_t s_scan[MM_THREADS / 32 + 1];
+    uint64_t* sCk = reinterpret_cast<uint64_t*>(mm_raw);                 // [CAP] the C slice (sorted)
+    uint64_t* hs = sCk + CAP;                                            // [CAP] M's bucket grouped by fine digit
+    uint32_t* hc = reinterpret_cast<uint32_t*>(hs + CAP);                // [CAP] its counts
+    uint32_t* hist = hc + CAP;                                           // [FINE + 1] group starts of M's bucket
+    uint32_t* cstart = hist + FINE + 1;                                  // [FINE + 1] group starts of the C slice
+    __shared__ uint32_t s_scan[THREADS / 32 + 1];
 
     const unsigned tid = threadIdx.x;
     const uint32_t b = blockIdx.x;
     const uint64_t c0 = startC[b], m0 = startM[b];
     const uint64_t nC64 = startC[b + 1] - c0, nM64 = startM[b + 1] - m0;
-    if (nC64 + nM64 > (uint64_t)MM_CAP) {
+    if (nC64 + nM64 > (uint64_t)CAP) {
         if (tid == 0) atomicExch(err, 1u);      // the caller falls back to sort + merge
         return;
     }
     const int nC = (int)nC64, nM = (int)nM64;
     if (nC + nM == 0) return;
     const uint64_t o0 = c0 + m0;
+    uint64_t kx[PER];
+    uint32_t wx[PER], rd[PER];
+    const int jn = (nM + THREADS - 1) / THREADS;
 #pragma unroll
-    for (int j = 0; j < MM_FINE / MM_THREADS; j++) hist[j * MM_THREADS + tid] = 0;
-    for (int i = (int)tid; i < nC; i += MM_THREADS) {
-        sCk[i] = __ldg(ck + c0 + i);
-        sCc[i] = __ldg(cc + c0 + i);
-    }
-    uint64_t kx[MM_PER];
-    uint32_t wx[MM_PER], rd[MM_PER];
-    const int jn = (nM + MM_THREADS - 1) / MM_THREADS;
-#pragma unroll
-    for (int j = 0; j < MM_PER; j++) {
+    for (int j = 0; j < PER; j++) {
         if (j >= jn) break;
-        const int q = j * MM_THREADS + (int)tid;
+        const int q = j * THREADS + (int)tid;
         kx[j] = (q < nM) ? __ldg(mk + m0 + q) : 0ull;
         wx[j] = (q < nM) ? __ldg(mc + m0 + q) : 0u;
     }
-    __syncthreads();
-    // ---- M: counting sort by the next key bits
+    for (int i = (int)tid; i < nC; i += THREADS) sCk[i] = __ldg(ck + c0 + i);
 #pragma unroll
-    for (int j = 0; j < MM_PER; j++) {
+    for (int j = 0; j < GP; j++) hist[j * THREADS + tid] = 0;
+    __syncthreads();
+    // ---- C: group starts by the next key bits (the slice is sorted: element i opens every group between its
+    //      predecessor's and its own; the groups after the last element start at nC)
+    for (int i = (int)tid; i < nC; i += THREADS) {
+        const int d = (int)((uint32_t)(sCk[i] >> fine_shift) & fine_mask);
+        const int dp = (i > 0) ? (int)((uint32_t)(sCk[i - 1] >> fine_shift) & fine_mask) : -1;
+        for (int g = dp + 1; g <= d; g++) cstart[g] = (uint32_t)i;
+    }
+    {
+        const int dl = (nC > 0) ? (int)((uint32_t)(sCk[nC - 1] >> fine_shift) & fine_mask) : -1;
+        for (int g = dl + 1 + (int)tid; g <= FINE; g += THREADS) cstart[g] = (uint32_t)nC;
+    }
+    // ---- M: counting sort by the same bits
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
         if (j >= jn) break;
-        if (j * MM_THREADS + (int)tid < nM) {
+        if (j * THREADS + (int)tid < nM) {
             const uint32_t d = (uint32_t)(kx[j] >> fine_shift) & fine_mask;
             rd[j] = atomicAdd(&hist[d], 1u) | (d << 16);
         }
     }
     __syncthreads();
     {
-        constexpr int GP = MM_FINE / MM_THREADS;
         uint32_t v[GP];
         uint32_t t = 0;
 #pragma unroll
         for (int u = 0; u < GP; u++) { v[u] = hist[tid * GP + u]; t += v[u]; }
         uint32_t all;
-        uint32_t ex = block_excl_scan<MM_THREADS, uint32_t, false>(t, s_scan, &all);
+        uint32_t ex = block_excl_scan<THREADS, uint32_t, false>(t, s_scan, &all);
 #pragma unroll
         for (int u = 0; u < GP; u++) { hist[tid * GP + u] = ex; ex += v[u]; }
-        if (tid == 0) hist[MM_FINE] = all;
+        if (tid == 0) hist[FINE] = all;
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < MM_PER; j++) {
+    for (int j = 0; j < PER; j++) {
         if (j >= jn) break;
-        if (j * MM_THREADS + (int)tid < nM) {
+        if (j * THREADS + (int)tid < nM) {
             const uint32_t p = hist[rd[j] >> 16] + (rd[j] & 0xffffu);
             hs[p] = kx[j];
             hc[p] = wx[j];
         }
     }
     __syncthreads();
-    // ---- M elements: rank inside the group + keys of the C slice below
-    for (int p = (int)tid; p < nM; p += MM_THREADS) {
-        const uint64_t x = hs[p];
-        const uint32_t d = (uint32_t)(x >> fine_shift) & fine_mask;
-        const int g0 = (int)hist[d], g1 = (int)hist[d + 1];
-        int r = g0;
-        for (int p2 = g0; p2 < g1; p2++) r += (hs[p2] < x) ? 1 : 0;
-        int lo = 0, hi = nC;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (sCk[mid] < x) lo = mid + 1; else hi = mid;
-        }
-        out_k[o0 + r + lo] = x;
-        out_c[o0 + r + lo] = hc[p];
-    }
     // ---- C elements: index in the slice + keys of M's bucket below (whole groups before mine, then my own group)
-    for (int i = (int)tid; i < nC; i += MM_THREADS) {
+    for (int i = (int)tid; i < nC; i += THREADS) {
+        const uint32_t w = __ldg(cc + c0 + i);
         const uint64_t x = sCk[i];
         const uint32_t d = (uint32_t)(x >> fine_shift) & fine_mask;
         const int g0 = (int)hist[d], g1 = (int)hist[d + 1];
         int r = g0;
         for (int p2 = g0; p2 < g1; p2++) r += (hs[p2] < x) ? 1 : 0;
         out_k[o0 + i + r] = x;
-        out_c[o0 + i + r] = sCc[i];
+        out_c[o0 + i + r] = w;
     }
+    // ---- M elements (in group order): rank inside the group + keys of the C slice below, the same way
+    for (int p = (int)tid; p < nM; p += THREADS) {
+        const uint64_t x = hs[p];
+        const uint32_t d = (uint32_t)(x >> fine_shift) & fine_mask;
+        const int g0 = (int)hist[d], g1 = (int)hist[d + 1];
+        int r = g0;
+        for (int p2 = g0; p2 < g1; p2++) r += (hs[p2] < x) ? 1 : 0;
+        const int q0 = (int)cstart[d], q1 = (int)cstart[d + 1];
+        int lo = q0;
+        for (int q = q0; q < q1; q++) lo += (sCk[q] < x) ? 1 : 0;
+        out_k[o0 + r + lo] = x;
+        out_c[o0 + r + lo] = hc[p];
+    }
+}
+
+template <int THREADS, int PER, int FINE_BITS>
+static void launch_mirror_merge(Ctx* c, uint32_t nb, const uint64_t* ck, const uint32_t* cc, const uint64_t* startC,
+                                const uint64_t* sk, const uint32_t* sv, const uint64_t* startM, int shift, uint64_t* out_k,
+                                uint32_t* out_c, unsigned int* err) {
+    constexpr int CAP = THREADS * PER;
+    const int fb = std::min(FINE_BITS, shift);
+    const size_t smem = (size_t)CAP * (8 + 8 + 4) + 2 * (size_t)((1 << FINE_BITS) + 1) * 4;
+    auto kern = mirror_merge_kernel<THREADS, PER, FINE_BITS>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<nb, THREADS, smem, c->stream>>>(ck, cc, startC, sk, sv, startM, shift - fb, (1u << fb) - 1u, out_k, out_c, err);
 }
 
 // out = C united with M (nm mirrored pairs in mk/mc, destroyed; mk2/mc2 are ping-pong scratch).  Returns false when a
@@ -968,8 +988,9 @@ bool merge_mirrored(Ctx* c, const uint64_t* ck, const uint32_t* cc, size_t n, ui
     *which_out = 0;
     if (key_bits < 1) key_bits = 1;
     if (key_bits > 64) key_bits = 64;
+    const size_t cap = g_mm_cfg == 1 ? 4096 : 2048;
     int cb = 0;
-    while (cb < key_bits && ((n + nm) >> cb) > (size_t)MM_CAP * 2 / 3) cb++;   // C is A-heavy where M is T-heavy: their sum is even
+    while (cb < key_bits && ((n + nm) >> cb) > cap * 2 / 3) cb++;   // C is A-heavy where M is T-heavy: their sum is even
     if (cb > 24) return false;
     const uint32_t nb = 1u << cb;
     const int shift = key_bits - cb;
@@ -981,7 +1002,6 @@ bool merge_mirrored(Ctx* c, const uint64_t* ck, const uint32_t* cc, size_t n, ui
     *which_out = which;
     const uint64_t* sk = which ? mk2 : mk;
     const uint32_t* sv = which ? mc2 : mc;
-    const int fb = std::min(MM_FINE_BITS, shift);
     DBuf<uint64_t> starts(c, 2 * ((size_t)nb + 1) + 2);
     uint64_t* startC = starts.get();
     uint64_t* startM = starts.get() + nb + 1;
@@ -992,9 +1012,8 @@ bool merge_mirrored(Ctx* c, const uint64_t* ck, const uint32_t* cc, size_t n, ui
     ZB_LAUNCH_CHECK(c);
     bc_bounds_kernel<<<(unsigned)div_up((size_t)nb + 1, 256), 256, 0, c->stream>>>(sk, nm, shift, nb, startM);
     ZB_LAUNCH_CHECK(c);
-    const size_t smem = (size_t)MM_CAP * (8 + 8 + 4 + 4) + (size_t)(MM_FINE + 1) * 4;
-    ZB_CUDA(cudaFuncSetAttribute(mirror_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mirror_merge_kernel<<<nb, MM_THREADS, smem, c->stream>>>(ck, cc, startC, sk, sv, startM, shift - fb, (1u << fb) - 1u, out_k, out_c, err);
+    if (g_mm_cfg == 1) launch_mirror_merge<512, 8, 11>(c, nb, ck, cc, startC, sk, sv, startM, shift, out_k, out_c, err);
+    else launch_mirror_merge<256, 8, 10>(c, nb, ck, cc, startC, sk, sv, startM, shift, out_k, out_c, err);
     ZB_LAUNCH_CHECK(c);
     ZB_CUDA(read_back(c, err, 4));
     ZB_CUDA(cudaStreamSynchronize(c->stream));

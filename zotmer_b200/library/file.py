@@ -101,6 +101,23 @@ def readBytes(fn):
     return data
 
 
+def mapBytes(fn):
+    """readBytes for the device parser: a plain regular file is mapped read-only instead of being read into a fresh
+    bytes object (no copy and no page faults of a second 315 MB buffer: the H2D copy reads the page cache itself --
+    SURVEY.md 8f row 3).  The result supports len(), rfind() and the buffer protocol, which is all `pieces` and
+    `Kmerizer.feed` need; anything else (stdin, compressed, empty, not mappable) comes back as bytes."""
+    if fn == "-" or fn.endswith(".gz") or fn.endswith(".bz2"):
+        return readBytes(fn)
+    import mmap
+    with open(fn, "rb") as f:
+        try:
+            if os.fstat(f.fileno()).st_size == 0:
+                return b""
+            return mmap.mmap(f.fileno(), 0, flags=mmap.MAP_SHARED | getattr(mmap, "MAP_POPULATE", 0), prot=mmap.PROT_READ)
+        except (OSError, ValueError):
+            return f.read()
+
+
 def readFasta(data):
     """(name, sequence) pairs of FASTA text -- file.py:19-36 semantics on bytes."""
     nm = None
