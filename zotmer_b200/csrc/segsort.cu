@@ -977,7 +977,7 @@ static void launch_mirror_merge(Ctx* c, uint32_t nb, const uint64_t* ck, const u
     const int fb = std::min(FINE_BITS, shift);
     const size_t smem = (size_t)CAP * (8 + 8 + 4) + 2 * (size_t)((1 << FINE_BITS) + 1) * 4;
     auto kern = mirror_merge_kernel<THREADS, PER, FINE_BITS>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // same value on every call
     kern<<<nb, THREADS, smem, c->stream>>>(ck, cc, startC, sk, sv, startM, shift - fb, (1u << fb) - 1u, out_k, out_c, err);
 }
 

@@ -39,6 +39,23 @@ class Entry(object):
         self._left -= take
         return data
 
+    def view(self):
+        """the unread rest of the entry as a read-only buffer over a mapping of the file -- no copy into a bytes object
+        (the word streams of a k-mer set go straight from the page cache to the device); None when the file cannot be
+        mapped, the caller then read()s"""
+        import mmap
+        if self._left == 0:
+            return b''
+        try:
+            m = mmap.mmap(self._f.fileno(), 0, flags=mmap.MAP_SHARED | getattr(mmap, 'MAP_POPULATE', 0), prot=mmap.PROT_READ)
+        except (OSError, ValueError, AttributeError):
+            return None
+        out = memoryview(m)[self._at:self._at + self._left]
+        assert len(out) == self._left
+        self._at += self._left
+        self._left = 0
+        return out
+
 
 class EntryWriter(object):
     """an entry written piece by piece (`with z.add_stream(name) as f: f.write(...)`); it is entered into the table

@@ -11,7 +11,9 @@ from zotmer_b200 import _native
 
 def readWords(f):
     """files.py:54-63: the blob as little-endian u64 words (AssertionError on a ragged blob)."""
-    s = f.read()
+    s = f.view() if hasattr(f, 'view') else None     # casket entries: a view of the mapped file instead of a copy
+    if s is None:
+        s = f.read()
     assert (len(s) & 7) == 0
     return np.frombuffer(s, dtype='<u8')
 
