@@ -486,13 +486,13 @@ def bench_pairs(nat, dev, rank, world, steps):
         sets.append(s.project(0))     # Measure.prep: k-mers only (commands/dist.py:29-49)
         s.free()
     npairs = PAIR_SETS * (PAIR_SETS - 1) // 2
-    b, e = multigpu.tile_ranges(PAIR_SETS, world)[rank]
+    b, e, st = multigpu.unit_share(PAIR_SETS, rank, world)
     dist = None
     if world > 1:
         import torch.distributed as dist
 
     def step():
-        part = nat.allpairs_abc(sets, b, e)
+        part = nat.allpairs_abc(sets, b, e, st)
         if world > 1:
             t = torch.from_numpy(part.view(np.int64)).to("cuda:%d" % dev)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)

@@ -145,6 +145,11 @@ int zb_pairs_abc(int nsets, zb_set* const* sets, const uint32_t* I, const uint32
  * parts computed on several GPUs simply add up (the "final gather" of the distance matrix). */
 int zb_allpairs_tiles(int nsets, uint64_t* n_tiles);
 int zb_allpairs_abc(int nsets, zb_set* const* sets, uint64_t tile_begin, uint64_t tile_end, uint64_t* abc);
+/* The same over the units unit_begin, unit_begin + unit_stride, ... < unit_end (unit_end 0 = all).  Rank r of W GPUs
+ * takes (r, 0, W): it then holds some key-range shards of every tile, so the ranks stay balanced however unevenly the
+ * tiles cost (sets of different sizes or divergence). */
+int zb_allpairs_abc_strided(int nsets, zb_set* const* sets, uint64_t unit_begin, uint64_t unit_end, uint64_t unit_stride,
+                            uint64_t* abc);
 
 /* ------------------------------------------------------------------------------------------
  * stream codec             replaces zotmer/library/codec64.py:82-150 + files.py:85-110 (delta)

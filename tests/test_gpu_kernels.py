@@ -811,6 +811,29 @@ def test_allpairs_abc(nat, sizes, bits):
                 isec = len(np.intersect1d(sub[i], sub[j], assume_unique=True))
                 assert tuple(int(v) for v in part[multigpu.pair_index(n, i, j)]) == (isec, len(sub[i]) - isec, len(sub[j]) - isec)
     assert np.array_equal(tot, abc)
+    # strided shares (rank r of W takes units r, r + W, ...: some key-range shards of every tile) add up as well
+    for world in (2, 3, 8):
+        tot = np.zeros_like(abc)
+        for r in range(world):
+            b, e, st = multigpu.unit_share(n, r, world)
+            tot += nat.allpairs_abc(sets, b, e, st)
+        assert np.array_equal(tot, abc), world
+
+
+def test_allpairs_strided_fall_back(nat, monkeypatch):
+    """strided shares on the pair-at-a-time route (forced): every pair is computed by exactly one share"""
+    rng = np.random.default_rng(15)
+    arrs = _rand_sets(rng, [3000] * 70, 40)
+    sets = [nat.KmerSet.from_arrays(a) for a in arrs]
+    from zotmer_b200 import multigpu
+    abc = nat.allpairs_abc(sets)
+    monkeypatch.setenv("ZB_ALLPAIRS_PAIRWISE", "1")
+    for world in (1, 3, 8):
+        tot = np.zeros_like(abc)
+        for r in range(world):
+            b, e, st = multigpu.unit_share(len(sets), r, world)
+            tot += nat.allpairs_abc(sets, b, e, st)
+        assert np.array_equal(tot, abc), world
 
 
 def test_allpairs_all_ones_key(nat):

@@ -123,15 +123,19 @@ def test_tiles_cover_every_pair_once(nsets):
         assert all(rs[r][1] == rs[r + 1][0] for r in range(world - 1))
         if nsets >= 2 and world == 8:   # even one tile spreads over 8 ranks (one key-range shard each)
             assert all(e > b for b, e in rs)
+        # strided shares: a partition of the units, level to within one unit
+        shares = [multigpu.share_units(nsets, r, world) for r in range(world)]
+        assert sorted(u for sh in shares for u in sh) == list(range(multigpu.n_tiles(nsets)))
+        assert max(len(sh) for sh in shares) - min(len(sh) for sh in shares) <= 1
 
 
-def _host_tiles(arrs, b, e):
+def _host_tiles(arrs, b, e, stride=1):
     """numpy stand-in for zotmer_b200._native.allpairs_abc(sets, b, e): the cardinalities of every pair of the
     units' tiles, restricted to the k-mers of the units' key-range shards"""
     n = len(arrs)
     key_bits = max([int(a.max()).bit_length() for a in arrs if len(a)] + [1])
     out = np.zeros((n * (n - 1) // 2, 3), np.uint64)
-    for u in range(b, e):
+    for u in range(b, e, stride):
         sh = u % multigpu.AP_KS
         part = [a[np.array([multigpu.key_shard(x, key_bits) == sh for x in a], bool)] if len(a) else a for a in arrs]
         for (i, j) in multigpu.tile_pairs(n, u):
@@ -149,7 +153,7 @@ def _pairs_worker(rank, world, port, ret):
         rng = np.random.default_rng(3)
         pool = rng.integers(0, 2 ** 40, 4000, dtype=np.uint64)
         arrs = [np.unique(pool[rng.integers(0, len(pool), int(rng.integers(0, 300)))]) for _ in range(37)]
-        full = multigpu.allpairs_sharded(lambda b, e: _host_tiles(arrs, b, e), len(arrs), dist, rank, world)
+        full = multigpu.allpairs_sharded(lambda b, e, st: _host_tiles(arrs, b, e, st), len(arrs), dist, rank, world)
         assert np.array_equal(full, _host_tiles(arrs, 0, multigpu.n_tiles(len(arrs))))
         ret[rank] = "ok"
     finally:

@@ -66,13 +66,15 @@ if rank == 0:
 torch.cuda.empty_cache()
 
 npairs = NSETS * (NSETS - 1) // 2
-ub, ue = multigpu.tile_ranges(NSETS, world)[rank]
+ub, ue, ust = multigpu.unit_share(NSETS, rank, world)
+if os.environ.get("ZB_CONTIGUOUS"):      # the earlier sharding: one contiguous range of units per rank
+    (ub, ue), ust = multigpu.tile_ranges(NSETS, world)[rank], 1
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 nat.dbg_profile(True, di)
 t0 = time.time()
-abc = nat.allpairs_abc(sets, ub, ue)
+abc = nat.allpairs_abc(sets, ub, ue, ust)
 t_own = time.time() - t0
 if world > 1:      # the "final gather": (a, b, c) restricted to a key-range shard add up over the shards
     t = torch.from_numpy(abc.view(np.int64)).to(dev)
@@ -89,8 +91,8 @@ if world > 1:
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     kern, wall = float(tt[0]), float(tt[1])
     if rank == 0:
-        print("%d ranks, work units [%d, %d) on rank 0; own share: slowest rank %.2f s, fastest %.2f s (kernel %.2f / %.2f s)" % (
-            world, ub, ue, float(tt[2]), float(lo[2]), float(tt[0]) / 1e3, float(lo[0]) / 1e3), flush=True)
+        print("%d ranks, work units range(%d, %d, %d) on rank 0; own share: slowest rank %.2f s, fastest %.2f s (kernel %.2f / %.2f s)" % (
+            world, ub, ue, ust, float(tt[2]), float(lo[2]), float(tt[0]) / 1e3, float(lo[0]) / 1e3), flush=True)
 if rank != 0:
     for x in sets:
         x.free()

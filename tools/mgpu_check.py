@@ -58,7 +58,7 @@ rng = np.random.default_rng(1)
 pool = rng.integers(0, 2 ** 50, 60000, dtype=np.uint64)
 arrs = [np.unique(pool[rng.integers(0, len(pool), 20000)]) for _ in range(21)]
 sets = [nat.KmerSet.from_arrays(a, device=dev) for a in arrs]
-full = multigpu.allpairs_sharded(lambda b, e: nat.allpairs_abc(sets, b, e), len(sets), dist, rank, world, "cuda:%d" % dev)
+full = multigpu.allpairs_sharded(lambda b, e, st: nat.allpairs_abc(sets, b, e, st), len(sets), dist, rank, world, "cuda:%d" % dev)
 # zot merge sharded by key range: identical to the single-GPU merge (and the oracle)
 cnts = [rng.integers(1, 1000, len(a), dtype=np.uint32) for a in arrs[:9]]
 msets = [nat.KmerSet.from_arrays(a, c, device=dev) for a, c in zip(arrs[:9], cnts)]

@@ -63,6 +63,7 @@ SIGNATURES = {
     "zb_pairs_abc": (C.c_int, [C.c_int, C.POINTER(vp), vp, vp, C.c_size_t, vp]),
     "zb_allpairs_tiles": (C.c_int, [C.c_int, u64p]),
     "zb_allpairs_abc": (C.c_int, [C.c_int, C.POINTER(vp), C.c_uint64, C.c_uint64, vp]),
+    "zb_allpairs_abc_strided": (C.c_int, [C.c_int, C.POINTER(vp), C.c_uint64, C.c_uint64, C.c_uint64, vp]),
     "zb_encode_u64_stream": (C.c_int, [C.c_int, vp, C.c_size_t, C.c_int, vp, C.POINTER(C.c_size_t)]),
     "zb_decode_u64_stream": (C.c_int, [C.c_int, vp, C.c_size_t, C.c_int, vp, C.POINTER(C.c_size_t)]),
     "zb_set_encode": (C.c_int, [vp, vp, C.POINTER(C.c_size_t), vp, C.POINTER(C.c_size_t)]),
@@ -306,15 +307,16 @@ def allpairs_tiles(nsets):
     return n.value
 
 
-def allpairs_abc(sets, tile_begin=0, tile_end=0):
+def allpairs_abc(sets, tile_begin=0, tile_end=0, stride=1):
     """(|X n Y|, |X \\ Y|, |Y \\ X|) for all pairs i < j in row-major order -> uint64 array [n (n - 1) / 2, 3];
-    with a tile range only the pairs of those tiles are filled, the others are 0 (multi-GPU shards add up)"""
+    with a unit range only the pairs of those units are filled (restricted to the units' key-range shards), the others
+    are 0 (multi-GPU shards add up); stride > 1 takes every stride-th unit of the range (rank r of W: (r, 0, W))"""
     n = len(sets)
     out = np.zeros((n * (n - 1) // 2, 3), np.uint64)
     if n < 2:
         return out
     arr = (vp * n)(*[s.h for s in sets])
-    _check(lib().zb_allpairs_abc(n, arr, tile_begin, tile_end, _ptr(out.reshape(-1))))
+    _check(lib().zb_allpairs_abc_strided(n, arr, tile_begin, tile_end, stride, _ptr(out.reshape(-1))))
     return out
 
 

@@ -331,8 +331,23 @@ static void tile_pairs(uint64_t t, uint32_t nblk, int nsets, std::vector<uint32_
 static inline uint64_t shard_bucket(uint64_t s, uint64_t nb) { return (s * nb + AB_KS - 1) / AB_KS; }
 
 // a per pair on the device, b and c on the host from the shard sizes.  Returns false when the key space is too skewed.
-static bool allpairs_buckets(Ctx* c, const SetRef* d_sets, const std::vector<SetRef>& refs, int key_bits, uint64_t ub,
-                             uint64_t ue, uint64_t* abc_host) {
+// One piece of work: shards [s0, s1) of tile t.
+struct ApPiece { uint64_t t; uint32_t s0, s1; };
+
+// units ub, ub + stride, ... < ue as pieces; consecutive shards of one tile are one piece
+static std::vector<ApPiece> unit_pieces(uint64_t ub, uint64_t ue, uint64_t stride) {
+    std::vector<ApPiece> out;
+    for (uint64_t u = ub; u < ue; u += stride) {
+        const uint64_t t = u / AB_KS;
+        const uint32_t s = (uint32_t)(u % AB_KS);
+        if (!out.empty() && out.back().t == t && out.back().s1 == s) out.back().s1 = s + 1;
+        else out.push_back(ApPiece{t, s, s + 1});
+    }
+    return out;
+}
+
+static bool allpairs_buckets(Ctx* c, const SetRef* d_sets, const std::vector<SetRef>& refs, int key_bits,
+                             const std::vector<ApPiece>& pieces, uint64_t* abc_host) {
     const int nsets = (int)refs.size();
     const uint64_t npairs = (uint64_t)nsets * (nsets - 1) / 2;
     const uint32_t nblk = (uint32_t)div_up((size_t)nsets, AB_S);
@@ -384,8 +399,8 @@ static bool allpairs_buckets(Ctx* c, const SetRef* d_sets, const std::vector<Set
     // work list: for every tile touched by the units [ub, ue), the buckets of its shards in that range
     std::vector<ApSeg> segs;
     uint64_t W = 0;
-    for (uint64_t t = ub / AB_KS; t <= (ue - 1) / AB_KS; t++) {
-        const uint64_t s0 = std::max(ub, t * AB_KS) - t * AB_KS, s1 = std::min(ue, (t + 1) * AB_KS) - t * AB_KS;
+    for (const ApPiece& pc : pieces) {
+        const uint64_t t = pc.t, s0 = pc.s0, s1 = pc.s1;
         ApSeg sg;
         sg.pad = 0;
         tile_to_blocks(t, nblk, sg.bi, sg.bj, sg.flags);
@@ -427,24 +442,40 @@ static bool allpairs_buckets(Ctx* c, const SetRef* d_sets, const std::vector<Set
         ZB_CUDA(cudaMemcpyAsync(rows.data() + (size_t)s * nsets, off.get() + (size_t)std::min<uint64_t>(shard_bucket(s, nb), nb) * nsets,
                                 (size_t)nsets * 4, cudaMemcpyDeviceToHost, c->stream));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
-    for (uint64_t t = ub / AB_KS; t <= (ue - 1) / AB_KS; t++) {
-        const uint64_t s0 = std::max(ub, t * AB_KS) - t * AB_KS, s1 = std::min(ue, (t + 1) * AB_KS) - t * AB_KS;
+    // |X_i| and |X_j| restricted to the shards of a tile's pieces add up piece by piece; a (from the device) already
+    // holds the sum over all pieces of the tile
+    for (const ApPiece& pc : pieces) {
+        const uint64_t t = pc.t, s0 = pc.s0, s1 = pc.s1;
         std::vector<uint32_t> I, J;
         tile_pairs(t, nblk, nsets, I, J);
         for (size_t q = 0; q < I.size(); q++) {
             const uint64_t i = I[q], j = J[q];
             const uint64_t p = i * (2ull * nsets - i - 1) / 2 + (j - i - 1);
-            const uint64_t a = isect[p];
             const uint64_t ni = rows[s1 * nsets + i] - rows[s0 * nsets + i], nj = rows[s1 * nsets + j] - rows[s0 * nsets + j];
+            abc_host[3 * p + 1] += ni;
+            abc_host[3 * p + 2] += nj;
+        }
+    }
+    uint64_t last_t = ~0ull;
+    for (const ApPiece& pc : pieces) {
+        if (pc.t == last_t) continue;     // pieces of one tile are adjacent in the list
+        last_t = pc.t;
+        std::vector<uint32_t> I, J;
+        tile_pairs(pc.t, nblk, nsets, I, J);
+        for (size_t q = 0; q < I.size(); q++) {
+            const uint64_t i = I[q], j = J[q];
+            const uint64_t p = i * (2ull * nsets - i - 1) / 2 + (j - i - 1);
+            const uint64_t a = isect[p];
             abc_host[3 * p] = a;
-            abc_host[3 * p + 1] = ni - a;
-            abc_host[3 * p + 2] = nj - a;
+            abc_host[3 * p + 1] -= a;
+            abc_host[3 * p + 2] -= a;
         }
     }
     return true;
 }
 
-void allpairs_abc(Ctx* c, const std::vector<SetRef>& refs, uint64_t unit_begin, uint64_t unit_end, uint64_t* abc_host) {
+void allpairs_abc(Ctx* c, const std::vector<SetRef>& refs, uint64_t unit_begin, uint64_t unit_end, uint64_t unit_stride,
+                  uint64_t* abc_host) {
     const int nsets = (int)refs.size();
     const uint64_t npairs = (uint64_t)nsets * (nsets - 1) / 2;
     if (npairs == 0) return;
@@ -453,6 +484,8 @@ void allpairs_abc(Ctx* c, const std::vector<SetRef>& refs, uint64_t unit_begin, 
     if (unit_end == 0 || unit_end > all_units) unit_end = all_units;
     memset(abc_host, 0, npairs * 3 * 8);
     if (unit_begin >= unit_end) return;
+    if (unit_stride < 1) unit_stride = 1;
+    const std::vector<ApPiece> pieces = unit_pieces(unit_begin, unit_end, unit_stride);
 
     DBuf<SetRef> d_refs(c, nsets);
     ZB_CUDA(cudaMemcpyAsync(d_refs.get(), refs.data(), nsets * sizeof(SetRef), cudaMemcpyHostToDevice, c->stream));
@@ -466,12 +499,16 @@ void allpairs_abc(Ctx* c, const std::vector<SetRef>& refs, uint64_t unit_begin, 
         for (int i = 0; i < nsets; i++) maxkey = std::max(maxkey, last[i]);
     }
     const int key_bits = maxkey ? 64 - __builtin_clzll(maxkey) : 1;
-    if (!getenv("ZB_ALLPAIRS_PAIRWISE") && allpairs_buckets(c, d_refs.get(), refs, key_bits, unit_begin, unit_end, abc_host)) return;
+    if (!getenv("ZB_ALLPAIRS_PAIRWISE") && allpairs_buckets(c, d_refs.get(), refs, key_bits, pieces, abc_host)) return;
 
-    // skewed key space: pair-at-a-time merge path (setops.cu); a pair goes, whole, to the first shard of its tile
+    // skewed key space: pair-at-a-time merge path (setops.cu); a pair goes, whole, to ONE unit of its tile: shard
+    // t mod AB_KS, so that strided shares (every rank holds some shards of every tile) still split the tiles evenly
     memset(abc_host, 0, npairs * 3 * 8);
     std::vector<uint32_t> I, J;
-    for (uint64_t t = div_up(unit_begin, AB_KS); t * AB_KS < unit_end; t++) tile_pairs(t, nblk, nsets, I, J);
+    for (const ApPiece& pc : pieces) {
+        const uint32_t home = (uint32_t)(pc.t % AB_KS);
+        if (pc.s0 <= home && home < pc.s1) tile_pairs(pc.t, nblk, nsets, I, J);
+    }
     if (I.empty()) return;
     std::vector<uint64_t> tmp(I.size() * 3);
     pairs_abc_host(c, refs, I.data(), J.data(), I.size(), tmp.data());

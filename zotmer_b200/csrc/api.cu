@@ -1014,7 +1014,14 @@ int zb_allpairs_tiles(int nsets, uint64_t* n_tiles) {
 }
 
 int zb_allpairs_abc(int nsets, zb_set* const* sets, uint64_t tile_begin, uint64_t tile_end, uint64_t* abc) {
+    return zb_allpairs_abc_strided(nsets, sets, tile_begin, tile_end, 1, abc);
+}
+
+int zb_allpairs_abc_strided(int nsets, zb_set* const* sets, uint64_t unit_begin, uint64_t unit_end, uint64_t unit_stride,
+                            uint64_t* abc) {
     ZB_TRY
+    const uint64_t tile_begin = unit_begin, tile_end = unit_end;
+    if (unit_stride < 1) ZB_FAIL(ZB_E_ARG, "unit_stride must be >= 1");
     if (nsets < 1 || !sets || (nsets > 1 && !abc)) ZB_FAIL(ZB_E_ARG, "bad argument");
     Ctx* c = sets[0]->c;
     ZB_CUDA(cudaSetDevice(c->device));
@@ -1024,7 +1031,7 @@ int zb_allpairs_abc(int nsets, zb_set* const* sets, uint64_t tile_begin, uint64_
         refs[i].k = sets[i]->k.get();
         refs[i].n = sets[i]->n;
     }
-    allpairs_abc(c, refs, tile_begin, tile_end, abc);
+    allpairs_abc(c, refs, tile_begin, tile_end, unit_stride, abc);
     ZB_CATCH
 }
 

@@ -114,7 +114,10 @@ void pairs_abc_host(Ctx* c, const std::vector<SetRef>& refs, const uint32_t* I, 
 // incl. the diagonal) in [tile_begin, tile_end) are computed (tile_end 0 = all); the rest of abc is zero, so
 // the shards of several GPUs add up to the full matrix.  library/dist.py:241-265, jaccard.py:31-54.
 uint64_t allpairs_tiles(int nsets);
-void allpairs_abc(Ctx* c, const std::vector<SetRef>& refs, uint64_t tile_begin, uint64_t tile_end, uint64_t* abc_host);
+// With unit_stride > 1 only the units tile_begin, tile_begin + stride, ... are computed: rank r of W takes (r, 0, W) and
+// so holds some key-range shards of EVERY tile, which balances ranks whatever the tiles cost.
+void allpairs_abc(Ctx* c, const std::vector<SetRef>& refs, uint64_t tile_begin, uint64_t tile_end, uint64_t unit_stride,
+                  uint64_t* abc_host);
 
 // ---- parse.cu --------------------------------------------------------------------------------
 // Raw FASTA/FASTQ bytes (device) -> dense base codes (0..3, 4 = break).  `codes` must have room for

@@ -23,10 +23,11 @@ class MultipleOpenFiles(Exception):
 class Entry(object):
     """read access to one stored entry: read() / read(n) like a file"""
 
-    def __init__(self, fileobj, offset, length):
+    def __init__(self, fileobj, offset, length, owner=None):
         self._f = fileobj
         self._at = offset
         self._left = length
+        self._owner = owner      # the casket: keeps ONE mapping of the file for all its entries
 
     def read(self, n=None):
         take = self._left if n is None else min(n, self._left)
@@ -46,10 +47,14 @@ class Entry(object):
         import mmap
         if self._left == 0:
             return b''
-        try:
-            m = mmap.mmap(self._f.fileno(), 0, flags=mmap.MAP_SHARED | getattr(mmap, 'MAP_POPULATE', 0), prot=mmap.PROT_READ)
-        except (OSError, ValueError, AttributeError):
-            return None
+        m = getattr(self._owner, '_map', None)
+        if m is None:
+            try:
+                m = mmap.mmap(self._f.fileno(), 0, flags=mmap.MAP_SHARED | getattr(mmap, 'MAP_POPULATE', 0), prot=mmap.PROT_READ)
+            except (OSError, ValueError, AttributeError):
+                return None
+            if self._owner is not None:
+                self._owner._map = m
         out = memoryview(m)[self._at:self._at + self._left]
         assert len(out) == self._left
         self._at += self._left
@@ -95,6 +100,7 @@ class casket(object):
         self.mode = mode
         self.toc = {}
         self._streaming = None
+        self._map = None
         self.fo = open(fn, mode + 'b')
         self._dirty = (mode == 'w')
         if mode == 'r':
@@ -107,7 +113,7 @@ class casket(object):
     def open(self, name):
         assert self.mode == 'r'
         offset, length = self.toc[name][-1]          # KeyError for a name that is not there
-        return Entry(self.fo, offset, length)
+        return Entry(self.fo, offset, length, self)
 
     def list(self):
         """[(name, length of its latest version)] in name order"""

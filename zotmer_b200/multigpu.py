@@ -348,18 +348,32 @@ def tile_ranges(nsets, world):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def unit_share(nsets, rank, world):
+    """(begin, end, stride) of rank's work units: every world-th unit, starting at `rank`.  A rank so holds key-range
+    shards of EVERY tile (with 8 ranks: shard `rank` of each), and the ranks stay level however unevenly the tiles cost --
+    contiguous ranges (tile_ranges) left the ranks holding the more diverged sets of 1,000 35 % behind the others
+    (profiles/r01_allpairs.md).  More ranks than units: the surplus ranks get nothing."""
+    return rank, n_tiles(nsets), max(1, world)
+
+
+def share_units(nsets, rank, world):
+    """the units of unit_share, listed"""
+    b, e, st = unit_share(nsets, rank, world)
+    return list(range(b, e, st))
+
+
 def pair_index(nsets, i, j):
     """row-major index of pair (i < j) in the upper triangle"""
     return i * (2 * nsets - i - 1) // 2 + (j - i - 1)
 
 
 def allpairs_sharded(compute_tiles, nsets, dist, rank, world, device="cpu"):
-    """every rank computes its tile range with compute_tiles(begin, end) -> uint64 [npairs, 3] (zeros outside its
-    tiles; zotmer_b200._native.allpairs_abc on a GPU), then one all-reduce adds the shards up.
+    """every rank computes its share of the work units with compute_tiles(begin, end, stride) -> uint64 [npairs, 3]
+    (zeros outside its units; zotmer_b200._native.allpairs_abc on a GPU), then one all-reduce adds the shards up.
     Returns the full matrix on every rank."""
     import torch
-    b, e = tile_ranges(nsets, world)[rank]
-    part = compute_tiles(b, e)
+    b, e, st = unit_share(nsets, rank, world)
+    part = compute_tiles(b, e, st)
     t = torch.from_numpy(np.ascontiguousarray(part).view(np.int64).copy()).to(device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
