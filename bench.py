@@ -441,8 +441,9 @@ def run_ours(args, rank, world, local_rank):
     if dist_ctx is not None and dist_ctx.get("p2p") is not None and "route_p2p" in prof:
         r_ms = prof["route_p2p"][0] / max(1, prof["route_p2p"][1])
         r_b = float(np.mean(dist_ctx["p2p"].remote_bytes)) if dist_ctx["p2p"].remote_bytes else 0.0
-        line["nvlink"] = {"exchange": "fused: route_p2p_kernel stores every key into its owner's buffer over NVLink peer memory "
-                                      "(CUDA IPC); NCCL only for the count matrix and the barrier",
+        line["nvlink"] = {"exchange": "fused: route_p2p_kernel stores every key into its owner's buffer over NVLink peer memory (CUDA IPC); "
+                                      + ("a thread block reserves its run there with one system-scope atomic on the owner's cursor word; "
+                                         "NCCL only for the barrier" if dist_ctx["p2p"].reserve else "NCCL only for the count matrix and the barrier"),
                           "route_kernel_ms": r_ms, "remote_bytes_per_gpu": r_b, "GBps_per_gpu_out": r_b / r_ms / 1e6 if r_ms else None,
                           "note": "the kernel also moves this rank's own share locally, so the NVLink rate is a lower bound",
                           "peak_GBps_per_direction": 900.0, "measured_peer_copy_GBps": 770.0}

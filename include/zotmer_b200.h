@@ -87,6 +87,14 @@ int zb_kmerize_take_bucketed_dev(zb_kmerizer* h, int nranks, uint64_t* d_keys, u
  * Returns after all stores have completed; the pending list is empty afterwards. */
 int zb_kmerize_bucket_counts(zb_kmerizer* h, int nranks, uint64_t* bucket_counts);
 int zb_kmerize_route_p2p(zb_kmerizer* h, int nranks, uint64_t* const* d_dst);
+/* The same without zb_kmerize_bucket_counts and without any agreement between the ranks beforehand: d_dst[r] is the
+ * START of rank r's receive buffer (capacity_keys keys) and d_cursor[r] a u64 word in rank r's memory, zero before the
+ * step; every thread block reserves its run with one system-scope atomic add on the owner's word (over NVLink for a
+ * remote owner) and stores it there.  After all ranks have returned (a barrier), *d_cursor[self] is the number of keys
+ * received; their order depends on timing.  sent_counts[nranks] (host, may be NULL) receives what this rank sent to
+ * whom.  ZB_E_RANGE when a reservation passed capacity_keys (nothing was stored out of bounds). */
+int zb_kmerize_route_p2p_reserve(zb_kmerizer* h, int nranks, uint64_t* const* d_dst, uint64_t* const* d_cursor,
+                                 uint64_t capacity_keys, uint64_t* sent_counts);
 /* device buffers that other processes on the node can map (cudaIpc*): alloc/free on the owner, open/close on peers */
 int zb_ipc_alloc(int device, size_t bytes, void** d_ptr, uint8_t handle[64]);
 int zb_ipc_open(int device, const uint8_t handle[64], void** d_ptr);

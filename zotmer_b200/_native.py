@@ -40,6 +40,7 @@ SIGNATURES = {
     "zb_kmerize_take_bucketed_dev": (C.c_int, [vp, C.c_int, vp, u64p]),
     "zb_kmerize_bucket_counts": (C.c_int, [vp, C.c_int, u64p]),
     "zb_kmerize_route_p2p": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "zb_kmerize_route_p2p_reserve": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.c_uint64, C.POINTER(C.c_uint64)]),
     "zb_ipc_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]),
     "zb_ipc_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(vp)]),
     "zb_ipc_close": (C.c_int, [C.c_int, vp]),
@@ -366,6 +367,16 @@ class Kmerizer(object):
         """write every pending key to dst_ptrs[owner] (device addresses, own or peer memory)"""
         arr = (vp * len(dst_ptrs))(*[vp(int(p)) for p in dst_ptrs])
         _check(lib().zb_kmerize_route_p2p(self.h, len(dst_ptrs), arr))
+
+    def route_p2p_reserve(self, dst_ptrs, cursor_ptrs, capacity_keys):
+        """write every pending key to its owner's receive buffer (dst_ptrs[owner] = its START), reserving the place with
+        an atomic add on the owner's cursor word (cursor_ptrs[owner]) -> keys sent per owner"""
+        n = len(dst_ptrs)
+        arr = (vp * n)(*[vp(int(p)) for p in dst_ptrs])
+        cur = (vp * n)(*[vp(int(p)) for p in cursor_ptrs])
+        sent = (C.c_uint64 * n)()
+        _check(lib().zb_kmerize_route_p2p_reserve(self.h, n, arr, cur, int(capacity_keys), sent))
+        return [int(x) for x in sent]
 
     def adopt_canonical_dev(self, dptr, n):
         _check(lib().zb_kmerize_adopt_canonical_dev(self.h, vp(dptr), n))

@@ -646,6 +646,35 @@ int zb_kmerize_route_p2p(zb_kmerizer* h, int nranks, uint64_t* const* d_dst) {
     ZB_CATCH
 }
 
+int zb_kmerize_route_p2p_reserve(zb_kmerizer* h, int nranks, uint64_t* const* d_dst, uint64_t* const* d_cursor,
+                                 uint64_t capacity_keys, uint64_t* sent_counts) {
+    ZB_TRY
+    if (!h || !d_dst || !d_cursor || nranks < 1 || nranks > 64) ZB_FAIL(ZB_E_ARG, "bad argument");
+    Ctx* c = h->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    const size_t n = h->pending_upper ? read_pending_count(h) : 0;
+    PeerPtrs pp, pc;
+    for (int r = 0; r < 64; r++) {
+        pp.p[r] = (r < nranks) ? d_dst[r] : nullptr;
+        pc.p[r] = (r < nranks) ? d_cursor[r] : nullptr;
+    }
+    DBuf<unsigned long long> cur(c, 65);      // [0, 64): keys sent per owner; [64]: overflow flag
+    ZB_CUDA(dev_memset(c, cur.get(), 0, 65 * 8));
+    {
+        Stage st(c, "route_p2p");
+        route_p2p(c, h->pending.get(), n, nranks, pp, cur.get(), &pc, capacity_keys, reinterpret_cast<unsigned int*>(cur.get() + 64));
+    }
+    std::vector<unsigned long long> hc(65, 0);
+    ZB_CUDA(cudaMemcpyAsync(hc.data(), cur.get(), 65 * 8, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));   // every store and reservation, local or over NVLink, has completed
+    h->pending_upper = 0;
+    ZB_CUDA(dev_memset(c, h->d_count.get(), 0, 8));
+    if (sent_counts)
+        for (int r = 0; r < nranks; r++) sent_counts[r] = hc[r];
+    if (hc[64] & 0xffffffffull) ZB_FAIL(ZB_E_RANGE, "route_p2p: a receive buffer of %llu keys overflowed", (unsigned long long)capacity_keys);
+    ZB_CATCH
+}
+
 int zb_ipc_alloc(int device, size_t bytes, void** d_ptr, uint8_t handle[64]) {
     ZB_TRY
     if (!d_ptr || !handle) ZB_FAIL(ZB_E_ARG, "null argument");

@@ -304,9 +304,16 @@ static constexpr int RT_THREADS = 256;
 static constexpr int RT_PER = 8;
 static constexpr int RT_TILE = RT_THREADS * RT_PER;
 
+// RESERVE: nobody has told this rank where its runs go -- a CTA reserves its run in the owner's buffer with ONE
+// system-scope atomicAdd on the owner's cursor word (rcur.p[o], in the owner's memory: over NVLink for a remote owner),
+// so the ranks need neither the owner-count pass over the keys nor the all-gather of the count matrix before they can
+// route.  The order of the runs in a receive buffer then depends on timing; the owner sorts the buffer anyway.  A
+// reservation past `cap` keys raises *err and its keys are not stored.  `cursor` (local) tallies what went to whom.
+template <bool RESERVE>
 __global__ void __launch_bounds__(RT_THREADS)
 route_p2p_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, PeerPtrs dst,
-                 unsigned long long* __restrict__ cursor) {
+                 unsigned long long* __restrict__ cursor, PeerPtrs rcur, unsigned long long cap,
+                 unsigned int* __restrict__ err) {
     __shared__ uint32_t sc[64];                 // keys per owner in this tile, then exclusive start
     __shared__ unsigned long long sb[64];       // my run's position in the owner's buffer
     __shared__ uint64_t sk[RT_TILE];
@@ -334,8 +341,25 @@ route_p2p_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, Peer
         const uint32_t i0 = warp_incl_scan(c0);
         const uint32_t t0 = __shfl_sync(0xffffffffu, i0, 31);
         const uint32_t i1 = warp_incl_scan(c1);
-        if ((int)tid < nranks && c0) sb[tid] = atomicAdd(&cursor[tid], (unsigned long long)c0);
-        if ((int)tid + 32 < nranks && c1) sb[tid + 32] = atomicAdd(&cursor[tid + 32], (unsigned long long)c1);
+        if (RESERVE) {
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const int o = (int)tid + 32 * half;
+                const uint32_t cn = half ? c1 : c0;
+                if (o < nranks && cn) {
+                    unsigned long long at = atomicAdd_system(reinterpret_cast<unsigned long long*>(rcur.p[o]), (unsigned long long)cn);
+                    atomicAdd(&cursor[o], (unsigned long long)cn);
+                    if (at + cn > cap) {
+                        atomicExch(err, 1u);
+                        at = ~0ull;
+                    }
+                    sb[o] = at;
+                }
+            }
+        } else {
+            if ((int)tid < nranks && c0) sb[tid] = atomicAdd(&cursor[tid], (unsigned long long)c0);
+            if ((int)tid + 32 < nranks && c1) sb[tid + 32] = atomicAdd(&cursor[tid + 32], (unsigned long long)c1);
+        }
         sc[tid] = i0 - c0;
         sc[tid + 32] = t0 + i1 - c1;
     }
@@ -352,14 +376,17 @@ route_p2p_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, Peer
     const uint32_t cnt = (uint32_t)min((uint64_t)RT_TILE, n - base);
     for (uint32_t p = tid; p < cnt; p += RT_THREADS) {
         const int o = so[p];
+        if (RESERVE && sb[o] == ~0ull) continue;
         dst.p[o][sb[o] + (p - sc[o])] = sk[p];
     }
 }
 
-void route_p2p(Ctx* c, const uint64_t* keys, size_t n, int nranks, const PeerPtrs& dst, unsigned long long* d_cursor) {
+void route_p2p(Ctx* c, const uint64_t* keys, size_t n, int nranks, const PeerPtrs& dst, unsigned long long* d_cursor,
+               const PeerPtrs* rcur, unsigned long long cap, unsigned int* d_err) {
     if (n == 0) return;
     if (nranks > 64) ZB_FAIL(ZB_E_ARG, "route_p2p: nranks > 64");
-    route_p2p_kernel<<<(unsigned)div_up(n, RT_TILE), RT_THREADS, 0, c->stream>>>(keys, n, nranks, dst, d_cursor);
+    if (rcur) route_p2p_kernel<true><<<(unsigned)div_up(n, RT_TILE), RT_THREADS, 0, c->stream>>>(keys, n, nranks, dst, d_cursor, *rcur, cap, d_err);
+    else route_p2p_kernel<false><<<(unsigned)div_up(n, RT_TILE), RT_THREADS, 0, c->stream>>>(keys, n, nranks, dst, d_cursor, dst, 0ull, nullptr);
     ZB_LAUNCH_CHECK(c);
 }
 

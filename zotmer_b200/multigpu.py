@@ -109,12 +109,22 @@ class P2PExchange(object):
     receive buffer (CUDA IPC) and the bucketing kernel stores each key straight into its owner's buffer over
     NVLink.  NCCL is used only for the tiny count matrix (so that ranks agree on their slots) and the barrier that
     says "all stores have landed".  Two receive buffers alternate, so a fast rank may already fill the next one
-    while a slow rank still reads the current one; the per-step barrier is the only synchronisation."""
+    while a slow rank still reads the current one; the per-step barrier is the only synchronisation.
 
-    def __init__(self, nat, dist, rank, world, dev, capacity_keys):
+    reserve (ZB_P2P_RESERVE=1 or reserve=True; off by default): no count matrix at all -- every receive buffer ends in
+    a cursor word, and a thread block of the routing kernel reserves its run in the owner's buffer with one system-scope
+    atomic add on that word (over NVLink for a remote owner).  That drops the owner-count pass over the keys, the
+    all-gather and two host round trips from every step; after the barrier the owner reads its own cursor = keys
+    received.  The runs land in timing order, which the owner's sort makes irrelevant.  Measured at N = 2: step 6.46 ->
+    6.37 ms (the kernel waits ~3 us per thread block for its reservation: 0.88 -> 1.07 ms, which eats most of what the
+    dropped pass and round trips save); not measured at N = 8, hence not the default yet (profiles/r01_scaling.md)."""
+
+    def __init__(self, nat, dist, rank, world, dev, capacity_keys, reserve=None):
+        import os
         import torch
         self.nat, self.dist, self.rank, self.world, self.dev = nat, dist, rank, world, dev
         self.capacity = int(capacity_keys)
+        self.reserve = (os.environ.get("ZB_P2P_RESERVE", "0") == "1") if reserve is None else bool(reserve)
         self.step = 0
         self.bufs = []
         self.route_ms = []
@@ -122,15 +132,35 @@ class P2PExchange(object):
         self.cnt = torch.empty(world, dtype=torch.int64, device="cuda:%d" % dev)
         self.allc = torch.empty(world * world, dtype=torch.int64, device="cuda:%d" % dev)
         for _ in range(2):
-            ptr, handle = nat.ipc_alloc(self.capacity * 8, dev)
+            ptr, handle = nat.ipc_alloc(self.capacity * 8 + 256, dev)     # the cursor word sits behind the keys
+            _as_tensor(ptr + self.capacity * 8, 1, torch.int64, dev).zero_()
             handles = [None] * world
             dist.all_gather_object(handles, handle)
             ptrs = [ptr if r == rank else nat.ipc_open(handles[r], dev) for r in range(world)]
             self.bufs.append((ptr, ptrs))
+        torch.cuda.synchronize(dev)
         dist.barrier()
+
+    def _exchange_reserve(self, km):
+        import time
+        import torch
+        own, ptrs = self.bufs[self.step & 1]
+        t0 = time.perf_counter()
+        sent = km.route_p2p_reserve(ptrs, [p + self.capacity * 8 for p in ptrs], self.capacity)
+        self.route_ms.append((time.perf_counter() - t0) * 1e3)
+        self.remote_bytes.append(8 * (sum(sent) - sent[self.rank]))
+        self.dist.barrier()          # every rank's stores and reservations have completed
+        cur = _as_tensor(own + self.capacity * 8, 1, torch.int64, self.dev)
+        nrecv = int(cur.item())
+        cur.zero_()                  # for the step after the next one; peers touch it again only after the next barrier
+        torch.cuda.current_stream(self.dev).synchronize()
+        km.adopt_canonical_dev(own, nrecv)
+        self.step += 1
 
     def exchange(self, km):
         import torch
+        if self.reserve:
+            return self._exchange_reserve(km)
         counts = km.bucket_counts(self.world)
         self.cnt.copy_(torch.tensor(counts, dtype=torch.int64))
         self.dist.all_gather_into_tensor(self.allc, self.cnt)
