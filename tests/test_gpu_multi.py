@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("mode,k", [("p2p", 25), ("p2p_counts", 25), ("nccl", 25), ("p2p", 31)])
+@pytest.mark.parametrize("mode,k", [("p2p", 25), ("p2p_reserve", 25), ("nccl", 25), ("p2p", 31)])
 def test_two_rank_kmerize_and_allpairs(mode, k):
     """k = 31 is BASELINE.json config[4]'s k (a 1/1000-scale instance of it: same code path, 62-bit keys)"""
     from zotmer_b200 import _native

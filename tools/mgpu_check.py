@@ -17,8 +17,9 @@ K = int(os.environ.get("ZB_CHECK_K", 25))   # 31 = config[4]'s k (62-bit keys)
 g = synth.genome(300000, seed=5)
 shards = [synth.fastq_array(g, 20000, seed=50 + r).reshape(-1).tobytes() for r in range(world)]
 mode = os.environ.get("ZB_EXCHANGE", "p2p")
-# p2p: runs reserved in the owner's buffer by remote atomics; p2p_counts: slots agreed on beforehand through a count matrix
-p2p = multigpu.P2PExchange(nat, dist, rank, world, dev, 126 * 20000 * 2, reserve=(mode == "p2p")) if mode.startswith("p2p") else None
+# p2p: slots agreed on beforehand through a count matrix (the default); p2p_reserve: runs reserved in the owner's buffer by
+# remote atomics
+p2p = multigpu.P2PExchange(nat, dist, rank, world, dev, 126 * 20000 * 2, reserve=(mode == "p2p_reserve")) if mode.startswith("p2p") else None
 ctx = {"world": world, "rank": rank, "dev": dev, "a2a_ms": [], "a2a_bytes": [],
        "send": torch.empty(16, dtype=torch.int64, device="cuda:%d" % dev),
        "recv": torch.empty(16, dtype=torch.int64, device="cuda:%d" % dev)}
