@@ -266,3 +266,33 @@ def test_map_bytes_and_pieces(tmp_path):
     z = tmp_path / "z.fq.gz"
     z.write_bytes(gzip.compress(fq))
     assert zfile.mapBytes(str(z)) == fq
+
+
+def test_casket_entry_views_equal_reads(tmp_path):
+    """the word streams of a k-mer set file come back as views of ONE mapping per container (casket.Entry.view), with
+    the bytes read() returns; a partly read entry yields its rest; a ragged blob still trips readWords' assertion"""
+    import numpy as np
+    from zotmer_b200.library.kmers import kmers
+    from zotmer_b200.library.casket import casket
+    from zotmer_b200.library.files import readWords
+    for name in ("kat6.k5", "r1_c2.k25", "m5.k25"):
+        with kmers(g(name), "r") as z:
+            for nm in ("kmers", "counts"):
+                want = z.open(nm).read()
+                got = readWords(z.open(nm))
+                assert got.dtype == np.dtype("<u8") and got.tobytes() == want
+                e = z.open(nm)
+                head = e.read(8)
+                assert head + bytes(e.view()) == want and e.read() == b""
+            assert z._map is not None
+            m = z._map
+            readWords(z.open("kmers"))
+            assert z._map is m                      # mapped once
+    p = tmp_path / "ragged.k"
+    with casket(str(p), "w") as w:
+        w.add_content("kmers", b"\x01" * 13)
+        w.add_content("empty", b"")
+    with casket(str(p), "r") as z:
+        assert len(readWords(z.open("empty"))) == 0
+        with pytest.raises(AssertionError):
+            readWords(z.open("kmers"))
