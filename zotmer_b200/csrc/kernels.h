@@ -109,10 +109,11 @@ void pairs_abc(Ctx* c, const SetRef* d_sets, const uint32_t* d_I, const uint32_t
 void pairs_abc_host(Ctx* c, const std::vector<SetRef>& refs, const uint32_t* I, const uint32_t* J, size_t npairs, uint64_t* abc);
 
 // ---- allpairs.cu -----------------------------------------------------------------------------
-// All pairs i < j of `refs`: abc[3p .. 3p+2] with p = i (2n - i - 1) / 2 + (j - i - 1), bucketed by key range and
-// tiled by blocks of 8 sets in shared memory.  Only the block pairs ("tiles", row-major over the upper triangle
-// incl. the diagonal) in [tile_begin, tile_end) are computed (tile_end 0 = all); the rest of abc is zero, so
-// the shards of several GPUs add up to the full matrix.  library/dist.py:241-265, jaccard.py:31-54.
+// All pairs i < j of `refs`: abc[3p .. 3p+2] with p = i (2n - i - 1) / 2 + (j - i - 1).  Sets in blocks of 32; a tile is a
+// pair of blocks (row-major over the upper triangle of blocks incl. the diagonal; up to 64 sets: ONE tile), a work unit is
+// (tile, one of 8 key-range shards).  Only the units tile_begin, tile_begin + unit_stride, ... < tile_end are computed
+// (tile_end 0 = all); abc then holds the cardinalities restricted to those units' key shards and zero elsewhere, so the
+// parts of several GPUs add up to the full matrix.  library/dist.py:241-265, jaccard.py:31-54.
 uint64_t allpairs_tiles(int nsets);
 // With unit_stride > 1 only the units tile_begin, tile_begin + stride, ... are computed: rank r of W takes (r, 0, W) and
 // so holds some key-range shards of EVERY tile, which balances ranks whatever the tiles cost.
