@@ -50,7 +50,10 @@ class Entry(object):
         m = getattr(self._owner, '_map', None)
         if m is None:
             try:
-                m = mmap.mmap(self._f.fileno(), 0, flags=mmap.MAP_SHARED | getattr(mmap, 'MAP_POPULATE', 0), prot=mmap.PROT_READ)
+                import os
+                big = os.fstat(self._f.fileno()).st_size > (2 << 30)
+                m = mmap.mmap(self._f.fileno(), 0, flags=mmap.MAP_SHARED | (0 if big else getattr(mmap, 'MAP_POPULATE', 0)),
+                              prot=mmap.PROT_READ)
             except (OSError, ValueError, AttributeError):
                 return None
             if self._owner is not None:

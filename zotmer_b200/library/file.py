@@ -111,9 +111,12 @@ def mapBytes(fn):
     import mmap
     with open(fn, "rb") as f:
         try:
-            if os.fstat(f.fileno()).st_size == 0:
+            size = os.fstat(f.fileno()).st_size
+            if size == 0:
                 return b""
-            return mmap.mmap(f.fileno(), 0, flags=mmap.MAP_SHARED | getattr(mmap, "MAP_POPULATE", 0), prot=mmap.PROT_READ)
+            # up to 2 GiB the page tables are filled in one go; a larger file is faulted in piece by piece as it is fed
+            populate = getattr(mmap, "MAP_POPULATE", 0) if size <= (2 << 30) else 0
+            return mmap.mmap(f.fileno(), 0, flags=mmap.MAP_SHARED | populate, prot=mmap.PROT_READ)
         except (OSError, ValueError):
             return f.read()
 
