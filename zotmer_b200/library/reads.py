@@ -39,14 +39,19 @@ def pieces(data, is_fasta, max_piece=MAX_PIECE):
                 raise ValueError("FASTA record larger than %d bytes cannot be fed in pieces" % max_piece)
             cut += 1
         else:
+            # newline number q (1-based, counted from `start`) ends a record when q % 4 == 0: count the newlines of the
+            # window (64 MiB at a time -- no index array of a gigabyte of text), then step back over the q % 4 newlines
+            # of the incomplete last record
             import numpy as np
-            a = np.frombuffer(mv[start:end], dtype=np.uint8)
-            nl = np.flatnonzero(a == 10)
-            # newline number q (1-based, counted from `start`) ends a record when q % 4 == 0
-            usable = (len(nl) // 4) * 4
-            if usable == 0:
+            total = 0
+            for o in range(start, end, 1 << 26):
+                total += int(np.count_nonzero(np.frombuffer(mv[o:min(o + (1 << 26), end)], dtype=np.uint8) == 10))
+            if total < 4:
                 raise ValueError("FASTQ record larger than %d bytes cannot be fed in pieces" % max_piece)
-            cut = start + int(nl[usable - 1]) + 1
+            at = end
+            for _ in range(total % 4 + 1):
+                at = data.rfind(b"\n", start, at)
+            cut = at + 1
         yield mv[start:cut]
         start = cut
     if start < n:
