@@ -454,6 +454,8 @@ int zb_kmerize_open(int k, int device, zb_kmerizer** out) {
         g_sort_cfg = e ? atoi(e) : 0;
         e = getenv("ZB_MM_CFG");
         g_mm_cfg = e ? atoi(e) : 0;
+        e = getenv("ZB_ROUTE_PER");
+        g_route_per = (e && atoi(e) == 16) ? 16 : 8;
     }
     if (const char* e = getenv("ZB_MAX_PENDING")) {
         size_t v = strtoull(e, nullptr, 10);

@@ -301,19 +301,19 @@ owner_scatter_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, 
 // groups its 2048 keys by owner in shared memory first, so every (CTA, owner) run leaves as consecutive,
 // fully used 128-byte lines.  `cursor[r]` counts what this rank has written to owner r so far.
 static constexpr int RT_THREADS = 256;
-static constexpr int RT_PER = 8;
-static constexpr int RT_TILE = RT_THREADS * RT_PER;
+int g_route_per = 8;   // keys per thread of a routing tile in reserve mode (ZB_ROUTE_PER: 8 or 16 = half as many reservations)
 
 // RESERVE: nobody has told this rank where its runs go -- a CTA reserves its run in the owner's buffer with ONE
 // system-scope atomicAdd on the owner's cursor word (rcur.p[o], in the owner's memory: over NVLink for a remote owner),
 // so the ranks need neither the owner-count pass over the keys nor the all-gather of the count matrix before they can
 // route.  The order of the runs in a receive buffer then depends on timing; the owner sorts the buffer anyway.  A
 // reservation past `cap` keys raises *err and its keys are not stored.  `cursor` (local) tallies what went to whom.
-template <bool RESERVE>
+template <bool RESERVE, int RT_PER>
 __global__ void __launch_bounds__(RT_THREADS)
 route_p2p_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, PeerPtrs dst,
                  unsigned long long* __restrict__ cursor, PeerPtrs rcur, unsigned long long cap,
                  unsigned int* __restrict__ err) {
+    constexpr int RT_TILE = RT_THREADS * RT_PER;
     __shared__ uint32_t sc[64];                 // keys per owner in this tile, then exclusive start
     __shared__ unsigned long long sb[64];       // my run's position in the owner's buffer
     __shared__ uint64_t sk[RT_TILE];
@@ -385,8 +385,12 @@ void route_p2p(Ctx* c, const uint64_t* keys, size_t n, int nranks, const PeerPtr
                const PeerPtrs* rcur, unsigned long long cap, unsigned int* d_err) {
     if (n == 0) return;
     if (nranks > 64) ZB_FAIL(ZB_E_ARG, "route_p2p: nranks > 64");
-    if (rcur) route_p2p_kernel<true><<<(unsigned)div_up(n, RT_TILE), RT_THREADS, 0, c->stream>>>(keys, n, nranks, dst, d_cursor, *rcur, cap, d_err);
-    else route_p2p_kernel<false><<<(unsigned)div_up(n, RT_TILE), RT_THREADS, 0, c->stream>>>(keys, n, nranks, dst, d_cursor, dst, 0ull, nullptr);
+    if (rcur && g_route_per == 16)
+        route_p2p_kernel<true, 16><<<(unsigned)div_up(n, (size_t)RT_THREADS * 16), RT_THREADS, 0, c->stream>>>(keys, n, nranks, dst, d_cursor, *rcur, cap, d_err);
+    else if (rcur)
+        route_p2p_kernel<true, 8><<<(unsigned)div_up(n, (size_t)RT_THREADS * 8), RT_THREADS, 0, c->stream>>>(keys, n, nranks, dst, d_cursor, *rcur, cap, d_err);
+    else
+        route_p2p_kernel<false, 8><<<(unsigned)div_up(n, (size_t)RT_THREADS * 8), RT_THREADS, 0, c->stream>>>(keys, n, nranks, dst, d_cursor, dst, 0ull, nullptr);
     ZB_LAUNCH_CHECK(c);
 }
 

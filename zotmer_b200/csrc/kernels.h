@@ -147,6 +147,7 @@ void bucket_count(Ctx* c, const uint64_t* keys, size_t n, int nranks, unsigned l
 void bucket_scatter(Ctx* c, const uint64_t* keys, size_t n, int nranks, unsigned long long* d_bucket_cursor,
                     uint64_t* out);
 // multi-GPU, fused: route every key into the owner's receive buffer (own memory or a peer's, CUDA IPC)
+extern int g_route_per;   // ZB_ROUTE_PER, see extract.cu
 struct PeerPtrs {
     uint64_t* p[64];
 };

@@ -855,7 +855,8 @@ static size_t sort_count_buckets(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v
 // groups before its own, plus a look at its own group).  The output position of the bucket is known beforehand --
 // nothing is deduplicated -- so the result is written in place, without staging or compaction.
 // Two shapes (g_mm_cfg / ZB_MM_CFG): 0 = 256 threads, buckets of <= 2048 entries, 1024 groups (48 KB: 4 CTAs per SM);
-// 1 = 512 threads, <= 4096 entries, 2048 groups (98 KB: 2 CTAs per SM).
+// 1 = 512 threads, <= 4096 entries, 2048 groups (98 KB: 2 CTAs per SM); 2 = shape 0 with 2048 groups (half as many keys
+// per group to rank against, 57 KB: 3 CTAs per SM; not measured yet).
 int g_mm_cfg = 0;
 
 template <int THREADS, int PER, int FINE_BITS>
@@ -1013,6 +1014,7 @@ bool merge_mirrored(Ctx* c, const uint64_t* ck, const uint32_t* cc, size_t n, ui
     bc_bounds_kernel<<<(unsigned)div_up((size_t)nb + 1, 256), 256, 0, c->stream>>>(sk, nm, shift, nb, startM);
     ZB_LAUNCH_CHECK(c);
     if (g_mm_cfg == 1) launch_mirror_merge<512, 8, 11>(c, nb, ck, cc, startC, sk, sv, startM, shift, out_k, out_c, err);
+    else if (g_mm_cfg == 2) launch_mirror_merge<256, 8, 11>(c, nb, ck, cc, startC, sk, sv, startM, shift, out_k, out_c, err);
     else launch_mirror_merge<256, 8, 10>(c, nb, ck, cc, startC, sk, sv, startM, shift, out_k, out_c, err);
     ZB_LAUNCH_CHECK(c);
     ZB_CUDA(read_back(c, err, 4));
