@@ -296,3 +296,11 @@ def test_casket_entry_views_equal_reads(tmp_path):
         assert len(readWords(z.open("empty"))) == 0
         with pytest.raises(AssertionError):
             readWords(z.open("kmers"))
+
+
+def test_tools_and_bench_compile():
+    """the probes under tools/ and bench.py are run on GPU boxes only: at least they must parse here"""
+    import glob
+    import py_compile
+    for fn in sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))) + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]:
+        py_compile.compile(fn, doraise=True)
