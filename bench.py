@@ -1,22 +1,28 @@
 #!/usr/bin/env python
 """
-bench.py -- measures BASELINE.json's metric "kmerize+count Gbases/s" on the configuration it is
-quoted on: synthetic 30x 150 bp Illumina-like FASTQ of a 5 Mbp genome (1,000,000 reads, 150 Mbases),
-kmerize+count at k=25 followed by zot trim at min-count 2.
+bench.py -- measures BASELINE.json's metric "kmerize+count Gbases/s at 1/2/4/8 B200; pairwise Jaccard set-pairs/s".
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over one batch (the whole read set of a rank):
-  value : inputs resident in HBM (raw FASTQ text on the device) -> parse, extract, sort, count,
-          mirror, trim, all through the C ABI (zb_kmerize_feed_dev ... zb_trim); device-timed.
-  e2e   : the same through the host-buffer C ABI (zb_kmerize_feed from pinned host memory, results
-          fetched back to pinned host memory), H2D and D2H inside the timed region.
-N > 1 (weak scaling): every rank kmerizes its own 1M-read shard of the same genome, routes each
-canonical k-mer to its owner rank (high bits of a 64-bit mix) with one NCCL all-to-all over NVLink,
-and sorts/counts/trims its disjoint key range locally.
---impl reference: the reference's own algorithm (pure Python, single thread, as the reference is)
-timed on a bounded sample of the same workload on the host.
+Headline workload (`value`, `e2e`): BASELINE.json configs[1] -- synthetic 30x 150 bp Illumina-like FASTQ of a 5 Mbp genome
+(1,000,000 reads = 150 Mbases per GPU), kmerize+count at k=25, then zot trim at min-count 2.  One "step" = one pass of
+the hot path over the whole read set of a rank, doing what `zot kmerize` + `zot trim` do up to the file write (and what
+the reference arm does on the CPU): parse, extract both strands, sort, count, count histogram + acgt tallies, codec64
+(+ delta) encode of the counted set, trim, codec64 encode of the trimmed set -- all through the C ABI.
+  value : FASTQ text already resident in HBM (zb_kmerize_feed_dev), results left in HBM; CUDA events.
+  e2e   : FASTQ text in pinned HOST memory (zb_kmerize_feed), the four encoded word streams fetched into pinned host
+          memory (zb_words_fetch) -- the bytes the commands would write -- H2D and D2H inside the timed region;
+          several steps in flight (one host thread each), at N > 1 as well: exchanges are issued in step order.
+N > 1 (weak scaling): every rank kmerizes its own 1M-read shard, routes each canonical k-mer to its owner rank (high
+bits of a 64-bit mix) with one fused routing kernel that stores into the owner's buffer over NVLink peer memory, and
+sorts / counts / trims its disjoint share.  Before anything is timed the ranks run a small multi-GPU kmerize (k = 25 and
+k = 31) and compare the union of their shares with the oracle, bit for bit (`mgpu_parity`).
+Further objects of the JSON line (each skippable): `human` = configs[4]'s per-GPU shape (375 Mbp of genome, 75 M reads,
+k = 31; reads generated on the device); `pairs` = configs[3] (all pairs of 1,000 sets, 499,500 pairs); `cli` = the
+`zot kmerize` command itself, FASTQ file in -> k-mer set file out, wall clock.
+--impl reference: the reference's own algorithm (pure Python, single thread, as the reference is) timed on a bounded
+sample of the same workload on the host.
 """
 import argparse
 import json
@@ -42,6 +48,8 @@ UNIT = "Gbases/s"
 # (1 + 2*W*8*(3+2P) + 12*d with W=0.84, P=7, d~0.3) and per key per radix pass (8 read + 8 write)
 BYTES_PER_BASE = 233.0
 BYTES_PER_KEY_PASS = 16.0
+# configs[4] (k=31, 8 passes, W=0.8, d~0.13): SURVEY.md 8d
+HUMAN_BYTES_PER_BASE = 246.0
 
 
 def load_peaks():
@@ -71,14 +79,7 @@ class ClockSampler(object):
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            idx = self.gpu_index
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            if vis:
-                try:
-                    idx = int(vis.split(",")[self.gpu_index])
-                except Exception:
-                    idx = self.gpu_index
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(physical_index(self.gpu_index))
             self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
@@ -113,6 +114,67 @@ class ClockSampler(object):
                 "samples": len(self.sm), "how": "NVML in-process, 20 ms period, during the timed steps (device-resident and e2e regions)"}
 
 
+def physical_index(local_index):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_index])
+        except Exception:
+            pass
+    return local_index
+
+
+_GPU_CPUS = {}
+
+
+def gpu_cpus(gpu_index):
+    """the CPUs next to a GPU (NVML's affinity mask) that this process may run on, or None"""
+    if gpu_index not in _GPU_CPUS:
+        pick = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(physical_index(gpu_index))
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+            cpus = set(i * 64 + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1)
+            allowed = os.sched_getaffinity(0)
+            if cpus & allowed and (cpus & allowed) != allowed:
+                pick = cpus & allowed
+        except Exception:
+            pick = None
+        _GPU_CPUS[gpu_index] = pick
+    return _GPU_CPUS[gpu_index]
+
+
+class near_gpu(object):
+    """Context manager: while pinned host buffers are allocated and first touched, the calling thread runs on the CPUs
+    next to its GPU (NVML's affinity mask), so that the pages land in that socket's memory -- with 8 ranks on one host
+    the H2D rate per rank halved in round 1 (25 GB/s instead of 52).  The mask is restored afterwards; nothing else is
+    pinned down.  Does nothing when NVML or the mask is unavailable.  One instance per `with` (threads use their own)."""
+
+    def __init__(self, gpu_index):
+        self.pick = gpu_cpus(gpu_index)
+        self.saved = None
+
+    def __enter__(self):
+        if self.pick:
+            try:
+                self.saved = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, self.pick)
+            except Exception:
+                self.saved = None
+        return self
+
+    def __exit__(self, *a):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:
+                pass
+        return False
+
+
 def make_reads(rank, nreads, world=1):
     """rank's shard of the read set.  Weak scaling keeps the COVERAGE fixed as well as the reads per GPU: N ranks
     sample a genome of N x 5 Mbp (config[4]'s shape -- the genome grows with the machine), so every owner rank
@@ -123,6 +185,17 @@ def make_reads(rank, nreads, world=1):
 
 
 # ------------------------------------------------------------------------------------------------
+def reference_step(zo, fq):
+    """what the reference does for `zot kmerize` + `zot trim` up to the file write (oracle port)"""
+    xs, cs, h, acgt, nr = zo.kmerize_core(K, [("reads.fq", fq)])
+    zo.words_to_bytes(zo.encode(zo.delta(xs)))       # the reference writes the set (54 % of its time)
+    zo.words_to_bytes(zo.encode(cs))
+    tx, tc = zo.trim_core(xs, cs, 2, None)
+    zo.words_to_bytes(zo.encode(zo.delta(tx)))
+    zo.words_to_bytes(zo.encode(tc))
+    return len(xs)
+
+
 def run_reference(args, rank):
     """The reference's own CPU path (pure Python, single thread): oracle port timed on a bounded sample."""
     if rank != 0:
@@ -131,21 +204,11 @@ def run_reference(args, rank):
     sample_reads = int(os.environ.get("ZB_REF_SAMPLE_READS", 4000))
     fq = make_reads(0, READS_PER_RANK)[:sample_reads * 315].tobytes()
     bases = sample_reads * READ_LEN
-
-    def step():
-        xs, cs, h, acgt, nr = zo.kmerize_core(K, [("reads.fq", fq)])
-        zo.words_to_bytes(zo.encode(zo.delta(xs)))       # the reference writes the set (54 % of its time)
-        zo.words_to_bytes(zo.encode(cs))
-        tx, tc = zo.trim_core(xs, cs, 2, None)
-        zo.words_to_bytes(zo.encode(zo.delta(tx)))
-        zo.words_to_bytes(zo.encode(tc))
-        return len(xs)
-
     for _ in range(args.warmup):
-        step()
+        reference_step(zo, fq)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        reference_step(zo, fq)
     dt = (time.perf_counter() - t0) / args.steps
     val = bases / dt / 1e9
     sample = "first %d of the %d reads (%d bases) per step; CPython %s, 1 thread" % (
@@ -162,7 +225,8 @@ def run_reference(args, rank):
 
 def workload_config(n):
     return {"workload": "config[1]: synthetic 30x 150bp FASTQ of a %d Mbp genome, %d reads per GPU, kmerize+count k=25 "
-                        "then trim min-count 2" % (GENOME * n // 1000000, READS_PER_RANK),
+                        "(count histogram, acgt, codec64 encode of the set), then trim min-count 2 (+ encode)" % (
+                            GENOME * n // 1000000, READS_PER_RANK),
             "k": K, "reads_per_gpu": READS_PER_RANK, "read_len": READ_LEN, "bases_per_gpu": READS_PER_RANK * READ_LEN,
             "genome_bp": GENOME * n,
             "parallelism": "1 GPU" if n == 1 else "%d GPUs: %d reads per GPU from a %d Mbp genome (30x), canonical k-mers "
@@ -171,28 +235,79 @@ def workload_config(n):
 
 
 # ------------------------------------------------------------------------------------------------
-def step_device(nat, dev, d_ptr, nbytes, dist_ctx):
-    """one step with inputs resident in HBM -> (trimmed set, full set)"""
-    km = nat.Kmerizer(K, dev)
-    km.feed_dev(d_ptr, nbytes, False)
-    if dist_ctx is not None:
-        exchange(nat, km, dist_ctx)
+def finish_step(km, fetch=None):
+    """the rest of a step once the rank's keys are in the kmerizer: count, stats, encode, trim, encode
+    -> (n distinct, n after trim, stats, words of the full set, words of the trimmed set)"""
     s, nr = km.finish()
     km.close()
+    st = s.stats()            # count histogram (first-occurrence order) + acgt: part of every `zot kmerize`
+    w = s.encode_dev()        # the two streams `zot kmerize` writes
     t = s.trim(2)
-    return s, t
+    tw = t.encode_dev()       # the two streams `zot trim` writes
+    out = (len(s), len(t), st, w.sizes(), tw.sizes())
+    if fetch is not None:
+        w.fetch(fetch[0], fetch[1])
+        tw.fetch(fetch[2], fetch[3])
+    for x in (w, tw, s, t):
+        x.free()
+    return out
 
 
-def exchange(nat, km, ctx):
-    """route every pending canonical k-mer to its owner rank (zotmer_b200/multigpu.py): fused routing + transfer
-    over NVLink peer memory when the ranks could map each other's buffers, else bucket -> NCCL all-to-all"""
+def step_device(nat, dev, d_ptr, nbytes, p2p):
+    """one step with inputs resident in HBM"""
+    km = nat.Kmerizer(K, dev)
+    km.feed_dev(d_ptr, nbytes, False)
+    if p2p is not None:
+        p2p.exchange(km, consume=False)
+    return finish_step(km)
+
+
+# ------------------------------------------------------------------------------------------------
+def mgpu_parity(nat, rank, world, dev):
+    """tools/mgpu_check.py's comparison, before anything is timed: a small read set sharded over the ranks, default
+    exchange, k = 25 and k = 31 (configs[4]'s k: 62-bit keys); the union of the ranks' counted shares must be the
+    oracle's kmerize of all the reads, bit for bit.  The oracle is only the checker here."""
+    import torch
+    import torch.distributed as dist
     from zotmer_b200 import multigpu
-    if ctx.get("p2p") is not None:
-        ctx["p2p"].exchange(km)
-    else:
-        multigpu.exchange_pending(nat, km, ctx)
+    from tools import synth
+    from oracle import c_oracle as co
+    g = synth.genome(300000, seed=5)
+    nreads = 20000
+    shards = [synth.fastq_array(g, nreads, seed=50 + r).reshape(-1).tobytes() for r in range(world)]
+    out = {}
+    for k in (25, 31):
+        p2p = multigpu.P2PExchange(nat, dist, rank, world, dev, (READ_LEN - k + 1) * nreads * 2)
+        ok = True
+        for it in range(3):          # three steps: the receive buffers are reused
+            km = nat.Kmerizer(k, dev)
+            km.feed(shards[rank], False)
+            p2p.exchange(km)
+            s, nr = km.finish()
+            km.close()
+            ks, cs = s.fetch()
+            s.free()
+            parts = [None] * world
+            dist.all_gather_object(parts, (ks, cs))
+            if rank == 0 and it in (0, 2):
+                gk = np.concatenate([p[0] for p in parts])
+                gc = np.concatenate([p[1] for p in parts])
+                order = np.argsort(gk, kind="stable")
+                ek, ec, _, _ = co.kmerize(k, [(sh, False) for sh in shards])
+                ok = ok and len(np.unique(gk)) == len(gk) and np.array_equal(gk[order], ek) and np.array_equal(gc[order], ec)
+        p2p.close()
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device="cuda:%d" % dev)
+        dist.broadcast(flag, src=0)
+        out["k%d" % k] = "ok" if int(flag.item()) else "MISMATCH"
+    out["how"] = ("%d ranks x %d reads of a 300 kbp genome, exchange %s, 3 steps; union of the per-rank counted shares == oracle "
+                  "kmerize of all reads (k-mers and counts, bit for bit)" % (
+                      world, nreads, "p2p_reserve" if os.environ.get("ZB_P2P_RESERVE", "0") == "1" else "p2p"))
+    if any(v == "MISMATCH" for v in out.values()):
+        raise SystemExit("bench.py: multi-GPU parity FAILED: %r" % out)
+    return out
 
 
+# ------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
     # ... and since NCCL still prints its version banner to file descriptor 1 from C, everything written to stdout
@@ -206,34 +321,23 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device (zotmer_b200 has no CPU path)")
     dev = local_rank
     torch.cuda.set_device(dev)
-    dist_ctx = None
+    dist = None
+    p2p = None
+    parity = None
+    inflight = int(os.environ.get("ZB_E2E_INFLIGHT", 4 if world == 1 else 3))
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % dev))
-        dist_ctx = {"world": world, "rank": rank, "dev": dev, "a2a_ms": [], "a2a_bytes": [],
-                    "send": torch.empty(16, dtype=torch.int64, device="cuda:%d" % dev),
-                    "recv": torch.empty(16, dtype=torch.int64, device="cuda:%d" % dev)}
-
-    if dist_ctx is not None and os.environ.get("ZB_EXCHANGE", "p2p") == "p2p":
         from zotmer_b200 import multigpu
-        import torch.distributed as dist
-        ok = True
-        try:
-            # 126 keys per read; an owner receives about one rank's worth of keys (+ 30 % head room)
-            dist_ctx["p2p"] = multigpu.P2PExchange(nat, dist, rank, world, dev, int(READS_PER_RANK * 126 * 1.3) + (1 << 20))
-        except Exception as e:   # no peer mapping on this box: every rank must agree to fall back
-            print("rank %d: P2P exchange unavailable (%r), using NCCL all-to-all" % (rank, e), file=sys.stderr)
-            ok = False
-        flags = [None] * world
-        dist.all_gather_object(flags, ok)
-        if not all(flags):
-            dist_ctx["p2p"] = None
+        dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % dev))
+        parity = mgpu_parity(nat, rank, world, dev)
+        # 126 keys per read; an owner receives about one rank's worth of keys (+ 30 % head room); one buffer more than
+        # steps in flight (multigpu.P2PExchange)
+        p2p = multigpu.P2PExchange(nat, dist, rank, world, dev, int(READS_PER_RANK * 126 * 1.3) + (1 << 20), nbuf=inflight + 1)
 
     def barrier():
         torch.cuda.synchronize(dev)
         nat.device_sync(dev)
         if world > 1:
-            import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize(dev)
 
@@ -241,19 +345,18 @@ def run_ours(args, rank, world, local_rank):
     nbytes = fq.nbytes
     bases = READS_PER_RANK * READ_LEN
     d_in = torch.from_numpy(fq).to("cuda:%d" % dev)
-    pinned_in = torch.from_numpy(fq).pin_memory()
-    h_in = pinned_in.numpy()
+    with near_gpu(dev):
+        pinned_in = nat.PinnedArray(nbytes, np.uint8)
+        pinned_in.a[:] = fq
+    h_in = pinned_in.a
 
     # ---------------- device-resident: warm-up, then K timed steps
-    n_trim = n_full = 0
-    for _ in range(args.warmup):
-        s, t = step_device(nat, dev, d_in.data_ptr(), nbytes, dist_ctx)
-        n_full, n_trim = len(s), len(t)
-        s.free(); t.free()
-    if dist_ctx is not None:
-        dist_ctx["a2a_ms"].clear(); dist_ctx["a2a_bytes"].clear()
-        if dist_ctx.get("p2p") is not None:
-            dist_ctx["p2p"].route_ms.clear(); dist_ctx["p2p"].remote_bytes.clear()
+    res = None
+    for _ in range(max(1, args.warmup)):
+        res = step_device(nat, dev, d_in.data_ptr(), nbytes, p2p)
+    n_full, n_trim, st0, wsz, twsz = res
+    if p2p is not None:
+        p2p.route_ms.clear(); p2p.remote_bytes.clear()
     sampler = ClockSampler(dev)
     if rank == 0:
         sampler.start()          # NVML init happens here, outside the timed region
@@ -261,59 +364,52 @@ def run_ours(args, rank, world, local_rank):
     nat.dbg_profile(True, dev)
     launches0 = nat.launch_count(dev)
     nat.timer_start(dev)
-    w0 = time.perf_counter()
     d_times = []
     for _ in range(args.steps):
         t_it = time.perf_counter()
-        s, t = step_device(nat, dev, d_in.data_ptr(), nbytes, dist_ctx)
-        s.free(); t.free()
+        step_device(nat, dev, d_in.data_ptr(), nbytes, p2p)
         d_times.append((time.perf_counter() - t_it) * 1e3)
     ms_dev = nat.timer_stop(dev)
     print("rank %d device-resident per-step wall ms: %s" % (rank, [round(x, 1) for x in d_times]), file=sys.stderr)
     barrier()
-    wall_ms = (time.perf_counter() - w0) * 1e3
     launches = nat.launch_count(dev) - launches0
     prof = nat.dbg_profile(False, dev)
+    route_ms_dev = list(p2p.route_ms) if p2p is not None else []
+    remote_bytes_dev = list(p2p.remote_bytes) if p2p is not None else []
 
     # ---------------- end to end through host buffers (pinned in, pinned out)
-    # N = 1: four steps are kept in flight by four host threads (the library gives every host thread its own stream and
-    # allocator and hands the copy-in / copy-out engines from thread to thread), so the H2D copy of one step overlaps the
-    # kernels / D2H of the others -- what a user with more than one input file does.  Every step still copies its own
-    # 315 MB in and its own result out inside the timed region.
-    # N > 1: one step in flight (the exchange is a collective; all ranks must issue it in the same order).
-    inflight = 1 if world > 1 else int(os.environ.get("ZB_E2E_INFLIGHT", 4))
-
+    # `inflight` steps are kept in flight by as many host threads that simply call the API (the library gives every host
+    # thread its own stream and allocator and hands the copy-in / copy-out engines from thread to thread), so the H2D
+    # copy of one step overlaps the kernels / D2H of the others -- what a user with more than one input file does.  Every
+    # step still copies its own 315 MB in and its own encoded result out inside the timed region.  N > 1: the exchange of
+    # step s is a collective; P2PExchange issues them in step order whatever thread a step runs on.
     def make_out():
-        return (torch.empty(max(n_trim, 1), dtype=torch.int64).pin_memory().numpy().view(np.uint64),
-                torch.empty(max(n_trim, 1), dtype=torch.int32).pin_memory().numpy().view(np.uint32))
+        with near_gpu(dev):
+            bufs = [nat.PinnedArray(max(n, 1) + 64, np.uint64) for n in (wsz[0], wsz[1], twsz[0], twsz[1])]
+            for b in bufs:
+                b.a[:] = 0
+        return bufs
 
-    # With several steps in flight the LIBRARY hands the device's copy engines from step to step (one lock per engine
-    # inside libzot_b200: copy-in for the H2D of the input, copy-out for the D2H of the result; kernels of different
-    # steps overlap freely), so the steps of the host threads form a pipeline; the user code below is just the plain
-    # sequence of API calls.
-    import threading
     trace = [] if os.environ.get("ZB_E2E_TRACE") else None
 
-    def step_e2e(out_k, out_c):
+    def step_e2e(seq, out):
+        torch.cuda.set_device(dev)
         tr = [threading.get_ident() % 1000, time.perf_counter()] if trace is not None else None
         km = nat.Kmerizer(K, dev)
         km.feed(h_in, False)
         if tr: tr.append(time.perf_counter())
-        if dist_ctx is not None:
-            exchange(nat, km, dist_ctx)
-        s, nr = km.finish()
-        km.close()
-        t = s.trim(2)
-        st = s.stats()
+        if p2p is not None:
+            p2p.exchange(km, seq=seq, consume=False)
         if tr: tr.append(time.perf_counter())
-        k_, c_ = t.fetch(out_k=out_k, out_c=out_c)
-        s.free(); t.free()
+        r = finish_step(km, fetch=[b.a for b in out])
         if tr:
             tr.append(time.perf_counter())
             trace.append(tr)
-        return len(k_), st
+        return r
 
-    share = [args.steps // inflight + (1 if i < args.steps % inflight else 0) for i in range(inflight)]
+    warm = min(args.warmup, 2)
+    total_steps = inflight * warm + args.steps
+    base_seq = p2p.step if p2p is not None else 0
     gate = threading.Barrier(inflight + 1)     # everybody is warm
     go = threading.Barrier(inflight + 1)       # the per-stage profile has been reset: the timed region starts
     results = [None] * inflight
@@ -321,16 +417,18 @@ def run_ours(args, rank, world, local_rank):
 
     def worker(i):
         try:
-            bufs = make_out()
-            for _ in range(min(args.warmup, 2)):
-                step_e2e(*bufs)
+            out = make_out()
+            # step numbers: thread i runs i, i + inflight, ... -- the same assignment on every rank
+            seqs = list(range(i, total_steps, inflight))
+            for s_ in seqs[:warm]:
+                step_e2e(base_seq + s_, out)
             gate.wait()
             go.wait()
             r = None
-            for _ in range(share[i]):
-                r = step_e2e(*bufs)
-            results[i] = r
-        except Exception as e:   # pragma: no cover
+            for s_ in seqs[warm:]:
+                r = step_e2e(base_seq + s_, out)
+            results[i] = (r, out)
+        except BaseException as e:   # pragma: no cover
             errors.append(e)
             for b_ in (gate, go):
                 try:
@@ -339,65 +437,72 @@ def run_ours(args, rank, world, local_rank):
                     pass
 
     nat.dbg_profile(True, dev)
-    if inflight == 1:
-        bufs = make_out()
-        for _ in range(min(args.warmup, 2)):
-            step_e2e(*bufs)
-        barrier()
-        nat.dbg_profile(True, dev)
+    ths = [threading.Thread(target=worker, args=(i,)) for i in range(inflight)]
+    for t_ in ths:
+        t_.start()
+    e0 = time.perf_counter()
+    try:
+        gate.wait()
+        barrier()                    # all ranks are warm
+        nat.dbg_profile(True, dev)   # drop the warm-up stages (no worker touches the library between the two barriers)
+        go.wait()
         e0 = time.perf_counter()
-        e_times = []
-        for _ in range(args.steps):
-            t_it = time.perf_counter()
-            nk, st = step_e2e(*bufs)
-            e_times.append((time.perf_counter() - t_it) * 1e3)
-    else:
-        ths = [threading.Thread(target=worker, args=(i,)) for i in range(inflight)]
-        for t_ in ths:
-            t_.start()
-        e0 = time.perf_counter()
-        try:
-            gate.wait()
-            nat.dbg_profile(True, dev)   # drop the warm-up stages (no worker touches the library between the two barriers)
-            go.wait()
-            e0 = time.perf_counter()
-        except threading.BrokenBarrierError:
-            pass
-        for t_ in ths:
-            t_.join()
-        if errors:
-            raise errors[0]
-        nk, st = [r for r in results if r is not None][0]
-        e_times = []
+    except threading.BrokenBarrierError:
+        pass
+    for t_ in ths:
+        t_.join()
+    if errors:
+        raise errors[0]
     barrier()
     e2e_ms = (time.perf_counter() - e0) * 1e3 / args.steps
     e_prof = nat.dbg_profile(False, dev)
+    (e_res, e_out) = [r for r in results if r is not None][0]
     clocks = sampler.stop() if rank == 0 else None     # sampled over both timed regions (device-resident and e2e)
+    # the fetched words are the set's streams: check one against a fresh device-side encode of the same set
+    e2e_ok = (e_res[0], e_res[1], e_res[3], e_res[4]) == (n_full, n_trim, wsz, twsz) and e_res[2]["hist"] == st0["hist"]
     if rank == 0:
-        print("e2e (%d in flight) per-step wall ms: %s; stage ms/step: %s" % (
-            inflight, [round(x, 1) for x in e_times] if e_times else round(e2e_ms, 2),
-            {k: round(v[0] / args.steps, 3) for k, v in e_prof.items()}), file=sys.stderr)
-
+        print("e2e (%d in flight) %.2f ms/step; stage ms/step: %s" % (
+            inflight, e2e_ms, {k: round(v[0] / args.steps, 3) for k, v in e_prof.items()}), file=sys.stderr)
         if trace:
             t00 = min(r[1] for r in trace)
             for r in sorted(trace, key=lambda r: r[1]):
-                print("trace thread %3d: start %.2f | fed %.2f | counted + trimmed %.2f | fetched %.2f" % (
+                print("trace thread %3d: start %.2f | fed %.2f | exchanged %.2f | counted, encoded, fetched %.2f" % (
                     (r[0],) + tuple((x - t00) * 1e3 for x in r[1:])), file=sys.stderr)
 
     # ---------------- reduce over ranks (max time), aggregate throughput
     per_step_ms = ms_dev / args.steps   # CUDA events on the library stream around the K steps
-    vals = [per_step_ms, e2e_ms, float(launches)]
     if world > 1:
-        import torch.distributed as dist
-        tt = torch.tensor(vals[:2], dtype=torch.float64, device="cuda:%d" % dev)
+        tt = torch.tensor([per_step_ms, e2e_ms], dtype=torch.float64, device="cuda:%d" % dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         per_step_ms, e2e_ms = float(tt[0]), float(tt[1])
-        tl = torch.tensor([float(launches)], dtype=torch.float64, device="cuda:%d" % dev)
+        tl = torch.tensor([float(launches), 1.0 if e2e_ok else 0.0], dtype=torch.float64, device="cuda:%d" % dev)
         dist.all_reduce(tl, op=dist.ReduceOp.SUM)
         launches = int(tl[0])
+        e2e_ok = int(tl[1]) == world
+    keys_per_step = stage_keys(nat, dev, d_in, nbytes)
+    if p2p is not None:
+        p2p.close()
+        p2p = None
+    for b in e_out:
+        b.free()
+    del d_in
+    pinned_in.free()
+    nat.release_cache(dev)
+    torch.cuda.empty_cache()
+
+    human = None
+    if not args.no_human:
+        human = bench_human(nat, dev, rank, world)
+        nat.release_cache(dev)
+        torch.cuda.empty_cache()
     pairs = None
     if not args.no_pairs:
-        pairs = bench_pairs(nat, dev, rank, world, max(2, min(args.steps, 3)))
+        pairs = bench_pairs(nat, dev, rank, world, max(1, min(args.steps, 2)))
+        nat.release_cache(dev)
+        torch.cuda.empty_cache()
+    cli = None
+    if not args.no_cli and world == 1:
+        cli = bench_cli(nat, dev)
     if rank != 0:
         return
     total_bases = bases * world
@@ -410,7 +515,6 @@ def run_ours(args, rank, world, local_rank):
     pass_ms = sp[0] / sp[1] if sp[1] else None
     roofline = None
     stage_ms = {k: round(v[0] / args.steps, 4) for k, v in prof.items()}
-    keys_per_step = stage_keys(nat, dev, d_in, nbytes) if pass_ms else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "onesweep_traffic.json")
     if os.path.exists(tp):
@@ -427,75 +531,303 @@ def run_ours(args, rank, world, local_rank):
                     "pipeline_achieved": BYTES_PER_BASE * bases / (per_step_ms * 1e-3) / 1e9,
                     "pipeline_frac": BYTES_PER_BASE * bases / (per_step_ms * 1e-3) / 1e9 / peak,
                     "pipeline_bytes_per_base": BYTES_PER_BASE,
-                    "stage_ms_per_step": stage_ms}
+                    "pipeline_note": "SURVEY.md 8d's fixed numerator (7 full radix passes over both strands); this design sorts "
+                                     "canonical keys with 2 top-bit passes, so the bytes that really cross HBM are in `kernels`",
+                    "stage_ms_per_step": stage_ms,
+                    "kernels": kernel_table(prof, args.steps, per_step_ms, peak, nbytes, bases, keys_per_step, n_full, n_trim, wsz, twsz)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": workload_config(world),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nk * 12),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(8 * (sum(wsz) + sum(twsz))),
                 "ms_per_step": e2e_ms, "steps_in_flight": inflight,
-                "result": "trimmed (k-mer u64, count u32) arrays + count histogram of the full set"},
+                "result": "the four codec64 word streams (k-mers + counts of the full set and of the trimmed set) in pinned host "
+                          "memory + count histogram / acgt of the full set", "result_check": "ok" if e2e_ok else "MISMATCH",
+                "pinned_near_gpu_cpus": len(gpu_cpus(dev)) if gpu_cpus(dev) else None},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-        "result": {"distinct_kmers": int(n_full), "after_trim": int(n_trim)},
+        "result": {"distinct_kmers": int(n_full), "after_trim": int(n_trim), "kmer_words": int(wsz[0]), "count_words": int(wsz[1]),
+                   "trimmed_kmer_words": int(twsz[0]), "trimmed_count_words": int(twsz[1])},
     }
-    if dist_ctx is not None and dist_ctx.get("p2p") is not None and "route_p2p" in prof:
+    if parity is not None:
+        line["mgpu_parity"] = parity
+    if route_ms_dev and "route_p2p" in prof:
         r_ms = prof["route_p2p"][0] / max(1, prof["route_p2p"][1])
-        r_b = float(np.mean(dist_ctx["p2p"].remote_bytes)) if dist_ctx["p2p"].remote_bytes else 0.0
+        r_b = float(np.mean(remote_bytes_dev)) if remote_bytes_dev else 0.0
+        reserve = os.environ.get("ZB_P2P_RESERVE", "0") == "1"
         line["nvlink"] = {"exchange": "fused: route_p2p_kernel stores every key into its owner's buffer over NVLink peer memory (CUDA IPC); "
                                       + ("a thread block reserves its run there with one system-scope atomic on the owner's cursor word; "
-                                         "NCCL only for the barrier" if dist_ctx["p2p"].reserve else "NCCL only for the count matrix and the barrier"),
+                                         "NCCL only for the closing all-reduce" if reserve else "NCCL only for the count matrix and the closing all-reduce"),
                           "route_kernel_ms": r_ms, "remote_bytes_per_gpu": r_b, "GBps_per_gpu_out": r_b / r_ms / 1e6 if r_ms else None,
                           "note": "the kernel also moves this rank's own share locally, so the NVLink rate is a lower bound",
                           "peak_GBps_per_direction": 900.0, "measured_peer_copy_GBps": 770.0}
-    elif dist_ctx is not None and dist_ctx["a2a_ms"]:
-        a_ms = float(np.mean(dist_ctx["a2a_ms"]))
-        a_b = float(np.mean(dist_ctx["a2a_bytes"]))
-        line["nvlink"] = {"all_to_all_ms": a_ms, "bytes_sent_per_gpu": a_b, "GBps_per_gpu_out": a_b / a_ms / 1e6,
-                          "peak_GBps_per_direction": 900.0, "measured_peer_copy_GBps": 770.0}
+    if human is not None:
+        line["human"] = human
     if pairs is not None:
         if world == 1 and not args.no_cpu_baseline:
             pairs["cpu_baseline"] = cpu_baseline_pairs(pairs)
         line["pairs"] = pairs
+    if cli is not None:
+        line["cli"] = cli
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
-PAIR_SETS = int(os.environ.get("ZB_BENCH_PAIR_SETS", 32))
+def kernel_table(prof, steps, step_ms, peak, text_bytes, bases, nkeys, n_full, n_trim, wsz, twsz):
+    """every stage that takes >= 5 % of the device-resident step: ms per step, the bytes its algorithm has to move, GB/s and
+    the fraction of the measured HBM peak.  T = text bytes, C = base codes (one per base + one break per read), N = canonical
+    keys, D = distinct canonical k-mers, S = both-strand set, R = set after trim."""
+    T, C, N = float(text_bytes), float(bases + bases // READ_LEN), float(nkeys)
+    S, R = float(n_full), float(n_trim)
+    D = S / 2.0
+    npass = max(1, prof.get("sort_pass_keys", (0, 1))[1] // max(1, steps))
+    model = {
+        "parse": (2 * T + C, "fq_count + fq_scan + fastq_kernel: text read twice, codes written"),
+        "extract": (C + 8 * N, "extract_kernel: codes read, canonical keys written"),
+        "sort_hist": (8 * N, "sort_hist_kernel: keys read once for all digit histograms"),
+        "sort_pass_keys": (16 * N * npass, "onesweep_kernel x %d: 8 B read + 8 B written per key and pass" % npass),
+        "segcount": (8 * N + 2 * 12 * D + 12 * D, "bc_bounds + bucket_count + scan + compact: keys read, distinct run staged, re-read, written"),
+        "mirror": (12 * D + 12 * D, "mirror_kernel: canonical run read, reverse complements written"),
+        "sort_pass_pairs": (2 * 24 * D, "onesweep_kernel<pairs> x 2 over the mirrored half (top bits only)"),
+        "mirror_buckets": (2 * 12 * D + 12 * S, "bc_bounds x 2 + mirror_merge_kernel: both halves read, both-strand set written"),
+        "stats": (12 * S, "stats_kernel: set read once (histogram bins + first occurrence, acgt)"),
+        "encode": (12 * S * 2 + 8 * (wsz[0] + wsz[1]) * 2 + 12 * R * 2 + 8 * (twsz[0] + twsz[1]) * 2,
+                   "enc_tile + enc_emit x 4 streams: values read twice, words written (+ one copy into exact-size buffers)"),
+        "trim": (12 * S + 12 * R, "compact_kernel<TrimOp>: set read, kept entries written"),
+        "route_p2p": (16 * N, "route_p2p_kernel: keys read, stored into the owners' buffers (local HBM or NVLink)"),
+    }
+    nested = {"sort", "mirror_merge"}     # containers of other stages
+    rows = []
+    for name, (ms_tot, calls) in prof.items():
+        ms = ms_tot / steps
+        if name in nested or ms < 0.05 * step_ms:
+            continue
+        by, what = model.get(name, (None, ""))
+        row = {"stage": name, "ms_per_step": round(ms, 4), "share_of_step": round(ms / step_ms, 3), "launch_groups_per_step": calls // max(1, steps),
+               "what": what}
+        if by:
+            row["algorithmic_bytes"] = int(by)
+            row["GBps"] = round(by / (ms * 1e-3) / 1e9, 1)
+            row["frac_of_hbm_peak"] = round(by / (ms * 1e-3) / 1e9 / peak, 3)
+        rows.append(row)
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    return rows
 
 
-def bench_pairs(nat, dev, rank, world, steps):
-    """BASELINE.json's second metric, pairwise Jaccard set-pairs/s, on a bounded instance of config[3]:
-    PAIR_SETS synthetic bacterial k-mer sets (k=25, both strands, ~9.9 M k-mers each; 4 clades of related
-    genomes), all pairs.  Device-resident: the sets live in HBM (zb_allpairs_abc, CUDA-event kernel time);
-    e2e: the same call including the D2H of the (a, b, c) matrix and the Jaccard values on the host.
-    N > 1: every rank holds all sets and computes its share of the work units (tile x key-range shard); one all-reduce
-    adds the partial (a, b, c) up."""
+# ------------------------------------------------------------------------------------------------
+HUMAN_K = 31
+HUMAN_GENOME_PER_RANK = int(os.environ.get("ZB_HUMAN_GENOME", 375000000))
+HUMAN_READS_PER_RANK = int(os.environ.get("ZB_HUMAN_READS", 75000000))
+HUMAN_BATCH = int(os.environ.get("ZB_HUMAN_BATCH", 3000000))
+HUMAN_ERR = 0.001
+
+
+def bench_human(nat, dev, rank, world):
+    """BASELINE.json configs[4]: human-scale synthetic genome at 30x 150 bp reads, kmerize+count k=31 with the hash-range
+    exchange; weak scaling as the config defines it -- 375 Mbp of genome and 75 M reads per GPU, so N = 8 is the 3 Gbp /
+    600 M reads / 90 Gbases instance.  A 200 GB FASTQ cannot be staged on the box: the reads are generated
+    on the device batch by batch as base codes (torch: generation is plumbing and is NOT timed) and fed through
+    zb_kmerize_feed_codes_dev; timed per batch: extraction, route_p2p exchange, sort + count of what the previous exchange
+    delivered, fold into the rank's running counted set; then finish (last count, mirror, merge), stats and trim -c 2.
+    Checked through invariants (the oracle cannot run 11 Gbases): sum of counts = 2 x windows, every share strictly
+    ascending, sum(hist c x freq) = sum of counts, record count."""
     import torch
-    from tools import synth
     from zotmer_b200 import multigpu
-    nclades = max(1, PAIR_SETS // 8)
-    base = [synth.genome(GENOME, seed=1000 + c) for c in range(nclades)]
-    sets = []
-    for i in range(PAIR_SETS):
-        g = synth.mutate(base[i % nclades], 0.001 + 0.009 * (i // nclades) / max(1, PAIR_SETS // nclades), 2000 + i)
-        km = nat.Kmerizer(K, dev)
-        km.feed(synth.fasta_bytes(g), True)
-        s, _ = km.finish()
-        km.close()
-        sets.append(s.project(0))     # Measure.prep: k-mers only (commands/dist.py:29-49)
-        s.free()
-    npairs = PAIR_SETS * (PAIR_SETS - 1) // 2
-    b, e, st = multigpu.unit_share(PAIR_SETS, rank, world)
     dist = None
     if world > 1:
         import torch.distributed as dist
+    dv = "cuda:%d" % dev
+    L, Kh = READ_LEN, HUMAN_K
+    G = HUMAN_GENOME_PER_RANK * world
+    nreads = HUMAN_READS_PER_RANK
+    B = min(HUMAN_BATCH, nreads)
+    gen = torch.Generator(device=dv)
+    gen.manual_seed(5)
+    genome = torch.randint(0, 4, (G,), dtype=torch.uint8, device=dv, generator=gen)
+    rep_len = max(200, min(6000, G // 1000))
+    fam = torch.randint(0, 4, (20, rep_len), dtype=torch.uint8, device=dv, generator=gen)
+    ncopies = int(0.05 * G / rep_len)
+    where = torch.randperm(G // rep_len - 1, device=dv, generator=gen)[:ncopies] * rep_len   # disjoint: one writer per base
+    which = torch.randint(0, 20, (ncopies,), device=dv, generator=gen)
+    for c0 in range(0, ncopies, 4096):
+        w = where[c0:c0 + 4096]
+        idx = (w[:, None] + torch.arange(rep_len, device=dv)[None, :]).reshape(-1)
+        genome[idx] = fam[which[c0:c0 + 4096]].reshape(-1)
+    del where, which, fam
+    torch.cuda.synchronize(dev)
+    p2p = None
+    if world > 1:
+        p2p = multigpu.P2PExchange(nat, dist, rank, world, dev, int(B * (L - Kh + 1) * 1.15) + (1 << 20))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        nat.device_sync(dev)
+        if world > 1:
+            dist.barrier()
+
+    rgen = torch.Generator(device=dv)
+    ar = torch.arange(L, device=dv, dtype=torch.int64)
+
+    def make_batch(b, seed):
+        rgen.manual_seed(seed)
+        pos = torch.randint(0, G - L, (b,), device=dv, generator=rgen)
+        codes = torch.empty((b, L + 1), dtype=torch.uint8, device=dv)
+        rd = genome[(pos[:, None] + ar[None, :]).reshape(-1)].reshape(b, L)
+        rev = torch.rand(b, device=dv, generator=rgen) < 0.5
+        rd = torch.where(rev[:, None], 3 - rd.flip(1), rd)
+        e = torch.rand((b, L), device=dv, generator=rgen) < HUMAN_ERR
+        sub = torch.randint(1, 4, (b, L), dtype=torch.uint8, device=dv, generator=rgen)
+        rd = torch.where(e, (rd + sub) & 3, rd)
+        codes[:, :L] = rd
+        codes[:, L] = 4
+        return codes
+
+    # warm-up: two batches through a throw-away kmerizer (device allocator, peer mappings, kernel attributes)
+    kw = nat.Kmerizer(Kh, dev)
+    for it in range(2):
+        codes = make_batch(B, 7 + it)
+        kw.feed_codes_dev(codes.data_ptr(), codes.numel(), B)
+        if p2p is not None:
+            p2p.exchange(kw)
+        nat.device_sync(dev)
+        del codes
+    sw, _ = kw.finish()
+    kw.close()
+    sw.trim(2).free()
+    sw.free()
+    barrier()
+
+    nat.dbg_profile(True, dev)
+    km = nat.Kmerizer(Kh, dev)
+    timed, fed, windows, nb = 0.0, 0, 0, 0
+    while fed < nreads:
+        b = min(B, nreads - fed)
+        codes = make_batch(b, 1000003 * (rank + 1) + nb)          # NOT timed
+        barrier()
+        t0 = time.perf_counter()
+        km.feed_codes_dev(codes.data_ptr(), codes.numel(), b)
+        if p2p is not None:
+            p2p.exchange(km)
+        nat.device_sync(dev)
+        timed += time.perf_counter() - t0
+        del codes
+        fed += b
+        windows += b * (L - Kh + 1)
+        nb += 1
+    barrier()
+    del genome
+    torch.cuda.empty_cache()                   # the generator's scratch goes back to the driver before the big allocations
+    t_feed = timed
+    t0 = time.perf_counter()
+    s, nr = km.finish()
+    km.close()
+    st = s.stats()
+    t = s.trim(2)
+    nat.device_sync(dev)
+    timed += time.perf_counter() - t0
+    t_finish = timed - t_feed
+    prof = nat.dbg_profile(False, dev)
+    barrier()
+    # ---- invariants
+    kp, cp = s.dev_ptrs()
+    n = len(s)
+    ok_sorted = True
+    step = 1 << 27
+    kt = multigpu._as_tensor(kp, n, torch.int64, dev)
+    for a in range(0, n - 1, step):            # keys < 2^62: signed comparison is fine
+        bnd = min(n - 1, a + step)
+        ok_sorted = ok_sorted and bool((kt[a + 1:bnd + 1] > kt[a:bnd]).all())
+    hist_total = sum(int(c) * int(f) for c, f in st["hist"])
+    good = ok_sorted and hist_total == st["total"]
+    vals = torch.tensor([float(st["total"]), float(windows), float(n), float(len(t)), float(nr)], dtype=torch.float64, device=dv)
+    tmax = torch.tensor([timed, t_feed], dtype=torch.float64, device=dv)
+    flags = torch.tensor([1.0 if good else 0.0], dtype=torch.float64, device=dv)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    total, win, ndist, ntrim, nrec = [float(x) for x in vals.tolist()]
+    checks = {"sum_of_counts_is_2x_windows": total == 2.0 * win, "shares_strictly_ascending_and_hist_adds_up": flags.item() == 1.0,
+              "records": nrec == float(nreads) * world}
+    s.free()
+    t.free()
+    if p2p is not None:
+        p2p.close()
+    if not all(checks.values()):
+        raise SystemExit("bench.py: human-scale invariants FAILED: %r" % checks)
+    peak, _ = load_peaks()
+    secs = float(tmax[0])
+    bases = float(nreads) * L * world
+    val = bases / secs / 1e9
+    return {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "scaling": "weak",
+            "config": {"workload": "config[4]: %.3f Gbp synthetic genome (5 %% repeats), %d reads x %d bp (%.2f Gbases, 30x), error %.1f %%, "
+                                   "kmerize+count k=%d, stats, trim min-count 2; %d GPU(s), %d reads and %d Mbp per GPU" % (
+                                       G / 1e9, nreads * world, L, bases / 1e9, 100 * HUMAN_ERR, Kh, world, nreads, HUMAN_GENOME_PER_RANK // 1000000),
+                       "k": Kh, "batches_per_gpu": nb, "batch_reads": B,
+                       "data": "reads generated on the device as base codes (not timed); inputs resident in HBM"},
+            "seconds": secs, "seconds_batches": float(tmax[1]), "seconds_finish_stats_trim_rank0": t_finish,
+            "distinct_kmers_both_strands": int(ndist), "after_trim": int(ntrim), "sum_of_counts": int(total),
+            "roofline": {"bound": "hbm", "bytes_per_base": HUMAN_BYTES_PER_BASE, "achieved": HUMAN_BYTES_PER_BASE * bases / world / secs / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": HUMAN_BYTES_PER_BASE * bases / world / secs / 1e9 / peak,
+                         "note": "SURVEY.md 8d's fixed numerator for k=31 (8 full passes over both strands), per GPU"},
+            "stage_ms_rank0": {k: round(v[0], 1) for k, v in prof.items()},
+            "checks": checks}
+
+
+# ------------------------------------------------------------------------------------------------
+PAIR_SETS = int(os.environ.get("ZB_BENCH_PAIR_SETS", 1000))
+PAIR_CLADES = 10
+PAIR_KEYS = int(os.environ.get("ZB_BENCH_PAIR_KEYS", 9950000))
+
+
+def bench_pairs(nat, dev, rank, world, steps):
+    """BASELINE.json's second metric, pairwise Jaccard set-pairs/s, on configs[3] at FULL size: all 499,500 pairs of 1,000
+    synthetic bacterial k-mer sets (k=25: 50-bit keys, ~10 M k-mers each = 80 GB), through zb_allpairs_abc -- the call behind
+    `zot dist` / `zot jaccard -a`.  The sets are made on the device (1,000 x 80 MB cannot come through PCIe in a bounded
+    run; not timed): 10 clade bases of distinct random keys; a member keeps a base key with probability 1 - q (q = share
+    of k-mers hit by a substitution, 2.5 % .. 22 % for 0.1 % .. 1 % divergence at k=25) and draws fresh keys for the rest.
+    value: kernel time of the call (CUDA events); e2e: the call incl. the D2H of the (a, b, c) matrix, the all-reduce over
+    ranks and the Jaccard values on the host.  N > 1: every rank holds all sets and computes its share of the work units
+    (tile x key-range shard); one all-reduce adds the partial matrices up.
+    Checked: a + b = |X_i| and a + c = |X_j| for EVERY pair; 24 sampled pairs against the pair-at-a-time merge-path
+    kernel (zb_pairs_abc); inside a clade |X n Y| within 1 % of (1 - qi)(1 - qj)|base|."""
+    import torch
+    from zotmer_b200 import multigpu
+    dv = torch.device("cuda:%d" % dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+    g = torch.Generator(device=dv)
+    g.manual_seed(1000)
+    t0 = time.time()
+    clades = min(PAIR_CLADES, PAIR_SETS)
+    basesets = [torch.unique(torch.randint(0, 1 << 50, (PAIR_KEYS,), generator=g, device=dv, dtype=torch.int64)) for _ in range(clades)]
+    sets, q_of, clade_of = [], [], []
+    for i in range(PAIR_SETS):
+        c = i % clades
+        q = 0.025 + 0.195 * ((i // clades) / max(1, PAIR_SETS // clades - 1)) if PAIR_SETS > clades else 0.05
+        b = basesets[c]
+        drop = torch.rand(b.numel(), generator=g, device=dv) < q
+        fresh = torch.randint(0, 1 << 50, (int(drop.sum().item()),), generator=g, device=dv, dtype=torch.int64)
+        keys = torch.unique(torch.cat([b[~drop], fresh]))
+        sets.append(nat.KmerSet.from_device(keys.data_ptr(), None, keys.numel(), device=dev))
+        q_of.append(q)
+        clade_of.append(c)
+        del keys, fresh, drop
+    base_sizes = np.array([b.numel() for b in basesets], np.float64)
+    del basesets
+    torch.cuda.synchronize(dev)
+    torch.cuda.empty_cache()
+    build_s = time.time() - t0
+    sizes = np.array([len(s) for s in sets], np.uint64)
+    npairs = PAIR_SETS * (PAIR_SETS - 1) // 2
+    b, e, stp = multigpu.unit_share(PAIR_SETS, rank, world)
 
     def step():
-        part = nat.allpairs_abc(sets, b, e, st)
+        part = nat.allpairs_abc(sets, b, e, stp)
         if world > 1:
-            t = torch.from_numpy(part.view(np.int64)).to("cuda:%d" % dev)
+            t = torch.from_numpy(part.view(np.int64)).to(dv)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             part = t.cpu().numpy().view(np.uint64)
         jac = part[:, 0].astype(np.float64) / np.maximum(part.sum(axis=1), 1).astype(np.float64)
@@ -516,24 +848,45 @@ def bench_pairs(nat, dev, rank, world, steps):
     wall_ms = (time.perf_counter() - t0) * 1e3 / steps
     prof = nat.dbg_profile(False, dev)
     kern_ms = (prof.get("allpairs", (0.0, 1))[0] + prof.get("allpairs_offsets", (0.0, 1))[0]) / steps   # both kernels of the call
-    vals = [kern_ms, wall_ms]
     if world > 1:
-        tt = torch.tensor(vals, dtype=torch.float64, device="cuda:%d" % dev)
+        tt = torch.tensor([kern_ms, wall_ms], dtype=torch.float64, device=dv)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         kern_ms, wall_ms = float(tt[0]), float(tt[1])
-    sizes = [len(s) for s in sets]
-    pair_bytes = 8.0 * float(sum(sizes)) * (PAIR_SETS - 1)      # sum over pairs of 8 (|X| + |Y|)
-    nblk = -(-PAIR_SETS // multigpu.AP_S)
-    moved_bytes = 8.0 * float(sum(sizes)) * (1 + nblk)         # offsets pass + one gather per tile a set belongs to
+    # ---- checks (rank 0 holds the full matrix after the all-reduce; so does every rank)
+    I, J = np.triu_indices(PAIR_SETS, 1)
+    adds_up = bool(np.array_equal(abc[:, 0] + abc[:, 1], sizes[I]) and np.array_equal(abc[:, 0] + abc[:, 2], sizes[J]))
+    rng = np.random.default_rng(5)
+    pick = rng.choice(npairs, size=min(24, npairs), replace=False)
+    cl, qq = np.array(clade_of), np.array(q_of)
+    same = cl[I] == cl[J]
+    if same.any():
+        pick[: min(8, len(pick))] = np.flatnonzero(same)[rng.choice(int(same.sum()), size=min(8, len(pick)), replace=False)]
+    ref = nat.pairs_abc(sets, I[pick], J[pick])
+    sampled = bool(np.array_equal(ref, abc[pick]))
+    clade_ok, rel_max = True, 0.0
+    if same.any() and PAIR_KEYS >= 1000000:
+        expect = (1 - qq[I]) * (1 - qq[J]) * base_sizes[cl[I]]
+        rel = np.abs(abc[same, 0].astype(np.float64) - expect[same]) / expect[same]
+        rel_max = float(rel.max())
+        clade_ok = rel_max < 0.01
     for s in sets:
         s.free()
+    checks = {"every_pair_adds_up": adds_up, "sampled_pairs_equal_pair_at_a_time_kernel": sampled, "clade_structure": clade_ok}
+    if not all(checks.values()):
+        raise SystemExit("bench.py: all-pairs checks FAILED: %r" % checks)
     peak, _ = load_peaks()
+    nblk = -(-PAIR_SETS // multigpu.AP_S)
+    pair_bytes = 8.0 * float(sizes.sum()) * (PAIR_SETS - 1)      # sum over pairs of 8 (|X| + |Y|)
+    moved_bytes = 8.0 * float(sizes.sum()) * (1 + nblk)         # offsets pass + one gather per tile a set belongs to
     return {"metric": "pairwise Jaccard set-pairs/s", "value": npairs / (kern_ms * 1e-3), "unit": "set-pairs/s",
             "e2e": {"value": npairs / (wall_ms * 1e-3), "unit": "set-pairs/s", "d2h_bytes_per_step": int(npairs * 24)},
-            "config": {"workload": "config[3] bounded: all pairs of %d synthetic bacterial k-mer sets (k=25, ~%d k-mers each, "
-                                   "%d clades)" % (PAIR_SETS, int(np.mean(sizes)), nclades),
-                       "pairs": npairs, "parallelism": "1 GPU" if world == 1 else "%d GPUs: work units (pairs of 32-set blocks x 8 key-range shards) sharded, one all-reduce" % world},
-            "ms_per_step": kern_ms,
+            "config": {"workload": "config[3]: all pairs of %d synthetic bacterial k-mer sets (k=25, ~%d k-mers each, %d clades, %.1f GB of "
+                                   "keys resident in HBM; built on the device in %.1f s, not timed)" % (
+                                       PAIR_SETS, int(sizes.mean()), clades, sizes.sum() * 8 / 1e9, build_s),
+                       "pairs": npairs, "steps": steps,
+                       "parallelism": "1 GPU" if world == 1 else "%d GPUs: work units (pairs of 32-set blocks x 8 key-range shards) sharded, one all-reduce" % world},
+            "ms_per_step": kern_ms, "n_gpus": world,
+            "stage_ms_rank0": {k: round(v[0] / steps, 2) for k, v in prof.items()},
             "roofline": {"bound": "hbm", "achieved": moved_bytes / (kern_ms * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
                          "frac": moved_bytes / (kern_ms * 1e-3) / 1e9 / (peak * world),
                          "note": "numerator = the bytes this design has to move: every k-mer (8 B) once for the bucket offsets and "
@@ -542,7 +895,43 @@ def bench_pairs(nat, dev, rank, world, steps):
                          "pair_at_a_time_model_GBps": pair_bytes / (kern_ms * 1e-3) / 1e9,
                          "pair_at_a_time_note": "8 (|X| + |Y|) B per pair (SURVEY.md 8d) over the same time: what a merge per pair would "
                                                 "have to sustain to keep up"},
-            "check": {"jaccard_first_pair": float(jac[0]), "max_jaccard": float(jac.max())}}
+            "check": dict(checks, jaccard_first_pair=float(jac[0]), max_jaccard=float(jac.max()), clade_rel_err_max=rel_max)}
+
+
+# ------------------------------------------------------------------------------------------------
+def bench_cli(nat, dev):
+    """the drop-in command itself, as a user runs it: `zot kmerize 25 out.k25 reads.fq` on configs[1]'s FASTQ (315 MB file in
+    the page cache -> k-mer set file), wall clock of cli.main() in a warm process (library loaded, CUDA context up)."""
+    import io
+    import contextlib
+    import shutil
+    import tempfile
+    from zotmer_b200 import cli
+    tmp = tempfile.mkdtemp(prefix="zb_cli_", dir=os.environ.get("ZB_TMP"))
+    try:
+        fq = os.path.join(tmp, "reads_5M_30x.fq")
+        make_reads(0, READS_PER_RANK).tofile(fq)
+        out = os.path.join(tmp, "r.k25")
+        times = []
+        for it in range(5):
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                cli.main(["kmerize", str(K), out, fq])
+            nat.device_sync(dev)
+            times.append((time.perf_counter() - t0) * 1e3)
+        nat.dbg_profile(True, dev)
+        with contextlib.redirect_stdout(io.StringIO()):
+            cli.main(["kmerize", str(K), out, fq])
+        stages = {k: round(v[0], 2) for k, v in nat.dbg_profile(False, dev).items()}
+        ms = float(np.median(times[2:]))
+        return {"command": "zot kmerize %d r.k25 reads_5M_30x.fq" % K, "wall_ms": ms, "wall_ms_all": [round(x, 1) for x in times],
+                "value": READS_PER_RANK * READ_LEN / ms / 1e6, "unit": UNIT, "input_bytes": os.path.getsize(fq),
+                "output_bytes": os.path.getsize(out), "tmpdir": os.path.dirname(tmp),
+                "stage_ms": stages,
+                "note": "files in -> file out through zotmer_b200/cli.py (docopt grammar, staged H2D through the pinned ring, kernels, "
+                        "codec64 on the device, D2H + pwrite by the I/O threads, casket table); median of the last 3 of 5 runs"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def stage_keys(nat, dev, d_in, nbytes):
@@ -560,18 +949,13 @@ def cpu_baseline():
     sample_reads = int(os.environ.get("ZB_CPU_SAMPLE_READS", 30000))   # ~11 s of CPython on the GPU box
     fq = make_reads(0, READS_PER_RANK)[:sample_reads * 315].tobytes()
     t0 = time.perf_counter()
-    xs, cs, h, acgt, nr = zo.kmerize_core(K, [("reads.fq", fq)])
-    zo.words_to_bytes(zo.encode(zo.delta(xs)))
-    zo.words_to_bytes(zo.encode(cs))
-    tx, tc = zo.trim_core(xs, cs, 2, None)
-    zo.words_to_bytes(zo.encode(zo.delta(tx)))
-    zo.words_to_bytes(zo.encode(tc))
+    reference_step(zo, fq)
     dt = time.perf_counter() - t0
     import shutil
     pypy = shutil.which("pypy") or shutil.which("pypy3")
     return {"value": sample_reads * READ_LEN / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
             "pypy": pypy or "not installed on this box and not installable offline (north star: PyPy only if it installs offline)",
-            "sample": "first %d of the %d reads (%.1f Mbases, %.1f s): kmerize+count, codec64 encode, trim; CPython %s "
+            "sample": "first %d of the %d reads (%.1f Mbases, %.1f s): kmerize+count (hist, acgt), codec64 encode, trim, encode; CPython %s "
                       "single thread (the reference has no parallelism); host has %d cores" % (
                           sample_reads, READS_PER_RANK, sample_reads * READ_LEN / 1e6, dt, sys.version.split()[0],
                           os.cpu_count())}
@@ -602,7 +986,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-pairs", action="store_true", help="skip the set-pairs/s measurement")
+    ap.add_argument("--no-pairs", action="store_true", help="skip the set-pairs/s measurement (configs[3])")
+    ap.add_argument("--no-human", action="store_true", help="skip the human-scale k=31 measurement (configs[4])")
+    ap.add_argument("--no-cli", action="store_true", help="skip the command-level measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

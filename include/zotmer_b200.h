@@ -40,6 +40,9 @@ extern "C" {
 
 typedef struct zb_set zb_set;             /* device-resident counted k-mer set */
 typedef struct zb_kmerizer zb_kmerizer;   /* streaming kmerize+count state */
+typedef struct zb_words zb_words;         /* the two packed codec64 streams of a set ('kmers', 'counts'), device-resident */
+typedef struct zb_encplan zb_encplan;     /* first phase of a range-partitioned encode (several GPUs, one file) */
+typedef struct zb_staged zb_staged;       /* input text on its way to the device (asynchronous, pinned staging ring) */
 
 const char* zb_last_error(void);
 int zb_version(void);
@@ -105,6 +108,9 @@ int zb_kmerize_add_canonical_dev(zb_kmerizer* h, const uint64_t* d_keys, size_t 
 /* the same without the copy: the caller's array itself is sorted in place (its contents are destroyed) when the
  * kmerizer next counts -- at the latest in zb_kmerize_finish; it must stay valid and untouched until then */
 int zb_kmerize_adopt_canonical_dev(zb_kmerizer* h, uint64_t* d_keys, size_t n);
+/* count NOW whatever is pending (extracted but uncounted keys, an adopted array) and fold it into the running counted
+ * set -- KmerAccumulator2.flush, kmerize.py:412-424; afterwards an adopted array may be reused by its owner */
+int zb_kmerize_flush(zb_kmerizer* h);
 
 /* ------------------------------------------------------------------------------------------
  * counted sets
@@ -174,6 +180,51 @@ int zb_set_encode(const zb_set* s, uint64_t* kmer_words, size_t* n_kmer_words, u
 int zb_set_encode_sizes(const zb_set* s, size_t* n_kmer_words, size_t* n_count_words);
 int zb_set_from_streams(int device, const uint64_t* kmer_words, size_t n_kmer_words,
                         const uint64_t* count_words, size_t n_count_words, zb_set** out);
+/* The same encode with the words LEFT IN HBM (codec64 kernels only): the result is fetched into host memory
+ * (zb_words_fetch; pinned destinations copy at full PCIe rate) or written to a file by the library's I/O threads
+ * (zb_words_write_fd: device -> pinned ring -> pwrite at the given file offsets, the two streams in parallel) --
+ * the body of writeKmersAndCounts2 (files.py:209-217) + writeWords (files.py:65-83). */
+int zb_set_encode_dev(const zb_set* s, zb_words** out);
+int zb_words_sizes(const zb_words* w, size_t* n_kmer_words, size_t* n_count_words);
+int zb_words_dev_ptrs(const zb_words* w, const uint64_t** d_kmer_words, const uint64_t** d_count_words);
+int zb_words_fetch(const zb_words* w, uint64_t* kmer_words, uint64_t* count_words); /* either may be NULL */
+int zb_words_write_fd(const zb_words* w, int fd, uint64_t kmers_offset, uint64_t counts_offset);
+int zb_words_free(zb_words* w);
+/* Range-partitioned encode: `s` is ONE RANGE of a longer sorted set whose ranges live on several GPUs and go to one
+ * file.  codec64's greedy word boundaries (codec64.py:82-120) depend on everything before them, but only through
+ * "how many values of this range the last word of the previous range has already taken" (0..5).  plan: prev_kmer =
+ * last k-mer of the previous range (0 for the first; the delta base, files.py:85-98), next_* = the first n_next <= 5
+ * entries behind this range (a word that starts here may run into them; fewer than 5 only at the end of the whole
+ * set); *_map[r] = the state this range hands to the next one when entered in state r, *_map[6 + r] = the words it
+ * then writes.  The caller chains the maps of the ranges in order (state 0 in front of the first) and calls emit with
+ * each range's entry states; the concatenation of the emitted streams is the single-GPU stream, word for word.
+ * emit consumes the plan. */
+int zb_set_encode_plan(const zb_set* s, uint64_t prev_kmer, const uint64_t* next_kmers, const uint32_t* next_counts, int n_next,
+                       zb_encplan** out, uint64_t kmer_map[12], uint64_t count_map[12]);
+int zb_set_encode_emit(zb_encplan* p, int kmer_entry_state, int count_entry_state, zb_words** out);
+int zb_encplan_free(zb_encplan* p);
+
+/* ------------------------------------------------------------------------------------------
+ * host I/O runtime         replaces zotmer/library/file.py:79-123 (openFile: the `gunzip -c` pipe / plain read feeding
+ * the parser) and files.py:65-83 (writeWords) at the device boundary.
+ * zb_stage_input: starts copying `raw` (any host memory: a mapping of the input file, a decompressed buffer, pinned
+ * memory) to `device` and returns at once -- the library's I/O threads move it through a ring of pinned chunks
+ * (memcpy + asynchronous H2D per chunk, several chunks in flight), so the copy of piece i + 1 overlaps the parsing /
+ * extraction of piece i.  `raw` must stay valid until the piece has been fed or freed.
+ * zb_kmerize_feed_staged: zb_kmerize_feed of a staged piece (waits on the device for its copy); consumes it.
+ * zb_host_count_byte: occurrences of `byte` in host memory, on the I/O threads (cutting FASTQ text at record
+ * boundaries -- every 4th newline -- for several GPUs or > 1 GiB pieces, library/reads.py:pieces).
+ * ------------------------------------------------------------------------------------------ */
+int zb_stage_input(int device, const uint8_t* raw, size_t n, zb_staged** out);
+/* the same straight from a file: the I/O threads pread() [offset, offset + n) of `fd` into the pinned chunks (no
+ * mapping, no page-table fill) */
+int zb_stage_fd(int device, int fd, uint64_t offset, size_t n, zb_staged** out);
+int zb_kmerize_feed_staged(zb_kmerizer* h, zb_staged* st, int is_fasta);
+int zb_staged_free(zb_staged* st);
+int zb_host_count_byte(const uint8_t* p, size_t n, int byte, uint64_t* count);
+/* pinned host memory from the library's arena (cudaHostAlloc, cached): destinations of zb_words_fetch / zb_set_fetch */
+int zb_host_alloc(size_t bytes, void** p);
+int zb_host_free(void* p);
 
 /* ------------------------------------------------------------------------------------------
  * diagnostics: stage-level entry points for tests/ and bench.py (kernel isolation and timing).
@@ -197,6 +248,11 @@ int zb_dbg_extract(int device, int k, const uint8_t* codes, size_t n, uint64_t* 
 int zb_dbg_profile(int device, int on, char* report, size_t cap);
 /* CUDA-event timer on the library stream: op 0 records the start, op 1 records the stop and returns ms */
 int zb_dbg_timer(int device, int op, float* ms);
+/* guard bands (ZB_GUARD=1 in the environment when the library is first used): every device block of the library's
+ * allocator has 256 pattern bytes in front and behind; this scans the bands of all live and cached blocks of the
+ * calling thread's context and returns in *n_bad how many blocks have a damaged band (an out-of-bounds store of some
+ * kernel); *n_blocks = blocks scanned.  compute-sanitizer is closed on the GPU pool (profiles/r02_sanitizer.md). */
+int zb_dbg_guard_check(int device, uint64_t* n_blocks, uint64_t* n_bad);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,215 @@
+"""
+GPU tests of the round-2 entry points (pytest -m gpu): device-resident word streams (zb_set_encode_dev, zb_words_*),
+the range-partitioned encoder (zb_set_encode_plan / _emit: several ranges of one sorted set -> one stream, word for word),
+the host I/O runtime (zb_stage_input / zb_stage_fd / zb_kmerize_feed_staged, zb_host_count_byte, zb_words_write_fd) and
+the guard-band allocator that stands in for compute-sanitizer (closed on the GPU pool, profiles/r02_sanitizer.md).
+Everything is compared bit for bit with the oracle (oracle/) or with the single-call path.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from zotmer_b200 import _native
+    assert _native.device_count() >= 1, "no CUDA device"
+    return _native
+
+
+def random_set(rng, n, bits=50, maxcount=70000):
+    ks = np.unique(rng.integers(0, 2 ** bits, n, dtype=np.uint64))
+    # counts with a long tail: most fit 10 bits (six per word), a few need a word of their own
+    cs = rng.integers(1, 60, len(ks), dtype=np.uint32)
+    big = rng.random(len(ks)) < 0.01
+    cs[big] = rng.integers(1, maxcount, int(big.sum()), dtype=np.uint32)
+    return ks, cs
+
+
+@pytest.mark.parametrize("n", [1, 6, 2047, 2048, 2049, 100000, 1300001])
+def test_words_dev_equal_oracle_and_file(nat, n, tmp_path):
+    rng = np.random.default_rng(n)
+    ks, cs = random_set(rng, n)
+    s = nat.KmerSet.from_arrays(ks, cs)
+    w = s.encode_dev()
+    ek, ec = co.encode(ks, True), co.encode(cs.astype(np.uint64), False)
+    assert w.sizes() == (len(ek), len(ec))
+    kw, cw = w.fetch()
+    assert np.array_equal(kw, ek) and np.array_equal(cw, ec)
+    # pinned destinations
+    pk, pc = nat.PinnedArray(len(ek), np.uint64), nat.PinnedArray(len(ec), np.uint64)
+    kw2, cw2 = w.fetch(pk.a, pc.a)
+    assert np.array_equal(kw2, ek) and np.array_equal(cw2, ec)
+    # the I/O threads write both streams into a file behind a header
+    fn = str(tmp_path / "w.bin")
+    with open(fn, "wb") as f:
+        f.write(b"HEAD" * 4)
+        f.flush()
+        w.write_fd(f.fileno(), 16, 16 + 8 * len(ek))
+    blob = open(fn, "rb").read()
+    assert blob[:16] == b"HEAD" * 4
+    assert blob[16:] == ek.astype("<u8").tobytes() + ec.astype("<u8").tobytes()
+    pk.free(); pc.free(); w.free(); s.free()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_range_partitioned_encode(nat, seed):
+    """ranges of one sorted set, encoded separately with halos and chained entry states == the whole-set streams"""
+    rng = np.random.default_rng(100 + seed)
+    n = [40, 5000, 70000, 300000, 13, 2048 * 3][seed]
+    ks, cs = random_set(rng, n, bits=[50, 50, 62, 50, 20, 50][seed])
+    n = len(ks)
+    nr = [4, 3, 8, 2, 7, 5][seed]
+    cuts = np.sort(rng.integers(0, n + 1, nr - 1))
+    if seed == 4:
+        cuts = np.array([0, 1, 1, 3, 4, 4])[:nr - 1]      # empty and one-entry ranges: a word spans several of them
+    bounds = [0] + [int(c) for c in cuts] + [n]
+    ek, ec = co.encode(ks, True), co.encode(cs.astype(np.uint64), False)
+    sets, plans, kmaps, cmaps = [], [], [], []
+    for r in range(nr):
+        a, b = bounds[r], bounds[r + 1]
+        s = nat.KmerSet.from_arrays(ks[a:b], cs[a:b])
+        prev = int(ks[a - 1]) if a > 0 else 0
+        p, km, cm = s.encode_plan(prev, ks[b:b + 5], cs[b:b + 5])
+        sets.append(s); plans.append(p); kmaps.append(km); cmaps.append(cm)
+    kentry, koff, ktot = nat.chain_ranges(kmaps)
+    centry, coff, ctot = nat.chain_ranges(cmaps)
+    assert ktot == len(ek) and ctot == len(ec)
+    kws, cws = [], []
+    for r in range(nr):
+        w = plans[r].emit(kentry[r], centry[r])
+        kw, cw = w.fetch()
+        assert len(kw) == kmaps[r][1][kentry[r]] and len(cw) == cmaps[r][1][centry[r]]
+        kws.append(kw); cws.append(cw)
+        w.free()
+    assert np.array_equal(np.concatenate(kws), ek)
+    assert np.array_equal(np.concatenate(cws), ec)
+    for s in sets:
+        s.free()
+
+
+def test_range_encode_overflow_is_index_error(nat):
+    # a gap of more than 60 bits at a range boundary is still the reference's IndexError (codec64.py:93-99)
+    ks = np.array([5, 7, (1 << 62) + 9], np.uint64)
+    s1 = nat.KmerSet.from_arrays(ks[:2], np.ones(2, np.uint32))
+    s2 = nat.KmerSet.from_arrays(ks[2:], np.ones(1, np.uint32))
+    p1, _, _ = s1.encode_plan(0, ks[2:], np.ones(1, np.uint32))
+    p2, _, _ = s2.encode_plan(int(ks[1]), [], [])
+    p1.emit(0, 0).free()
+    with pytest.raises(IndexError):
+        p2.emit(0, 0)
+
+
+def _fastq(rng, nreads, L=100):
+    g = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 200000)]
+    out = []
+    for i in range(nreads):
+        p = int(rng.integers(0, len(g) - L))
+        out.append(b"@r%d\n%s\n+\n%s\n" % (i, g[p:p + L].tobytes(), b"I" * L))
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("nreads", [1, 300, 60000])
+def test_staged_feed_equals_feed(nat, nreads, tmp_path):
+    rng = np.random.default_rng(nreads)
+    fq = _fastq(rng, nreads)
+    ek, ec, _, enr = co.kmerize(25, [(fq, False)])
+    # from memory (two pieces in flight at once), and from a file descriptor
+    half = fq.rfind(b"\n@", 0, len(fq) // 2) + 1 if nreads > 1 else len(fq)
+    pieces = [fq[:half], fq[half:]] if half and half < len(fq) else [fq]
+    km = nat.Kmerizer(25, 0)
+    staged = [nat.stage_input(p) for p in pieces]
+    for st in staged:
+        km.feed_staged(st, False)
+    s, nr = km.finish()
+    km.close()
+    ks, cs = s.fetch()
+    assert nr == enr and np.array_equal(ks, ek) and np.array_equal(cs, ec)
+    s.free()
+    fn = str(tmp_path / "r.fq")
+    open(fn, "wb").write(b"#" * 37 + fq)
+    with open(fn, "rb") as f:
+        km = nat.Kmerizer(25, 0)
+        km.feed_staged(nat.stage_fd(f.fileno(), 37, len(fq)), False)
+        s, nr = km.finish()
+        km.close()
+    ks, cs = s.fetch()
+    assert nr == enr and np.array_equal(ks, ek) and np.array_equal(cs, ec)
+    s.free()
+    # a staged piece that is never fed can be dropped
+    nat.stage_input(fq).free()
+
+
+def test_host_count_byte(nat):
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 256, 9000001, dtype=np.uint8)
+    assert nat.host_count_byte(a, 10) == int(np.count_nonzero(a == 10))
+    assert nat.host_count_byte(a[:5], 10) == int(np.count_nonzero(a[:5] == 10))
+    assert nat.host_count_byte(b"", 10) == 0
+
+
+GUARD_SCRIPT = r"""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np
+import __graft_entry__ as g
+from zotmer_b200 import _native as nat
+g.smoke()
+rng = np.random.default_rng(9)
+# adversarial sort + count shapes: one value repeated, skewed prefixes, tiny and odd sizes
+for n in (1, 33, 4097, 200001, 1500003):
+    keys = rng.integers(0, 2 ** 50, n, dtype=np.uint64)
+    keys[: n // 3] = keys[0]
+    keys[n // 3: n // 2] &= np.uint64(0xffff)
+    ok, oc, _ = nat.dbg_sort_count(keys, None, 50)
+    u, c = np.unique(keys, return_counts=True)
+    assert np.array_equal(ok, u) and np.array_equal(oc, c.astype(np.uint32))
+sets = [nat.KmerSet.from_arrays(np.unique(rng.integers(0, 2 ** 50, 50000, dtype=np.uint64))) for _ in range(5)]
+nat.merge(sets).free()
+nat.allpairs_abc(sets)
+w = sets[0].encode_dev(); w.fetch(); w.free()
+nb, bad = nat.guard_check(0)
+print("guard: %%d blocks scanned, %%d damaged" %% (nb, bad))
+assert nb > 10 and bad == 0
+"""
+
+
+def test_guard_bands_clean():
+    """the whole smoke pipeline + adversarial shapes with 256-byte pattern bands around every device block: no kernel
+    stores outside its buffers (the stand-in for compute-sanitizer memcheck on this pool)"""
+    env = dict(os.environ, ZB_GUARD="1")
+    r = subprocess.run([sys.executable, "-c", GUARD_SCRIPT % ROOT], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "0 damaged" in r.stdout
+
+
+def test_guard_bands_detect_damage(nat):
+    """the check itself works: without ZB_GUARD the entry point refuses, so a clean report is never vacuous"""
+    if os.environ.get("ZB_GUARD"):
+        pytest.skip("guards are on in this process")
+    with pytest.raises(nat.NativeError):
+        nat.guard_check(0)
+
+
+def test_repeat_determinism(nat):
+    """a shared-memory race in the chained-scan sort, the bucket hash tables or the mirror merge would show up as a run
+    that differs: 20 runs of kmerize+count on the same reads, each compared with the oracle"""
+    rng = np.random.default_rng(77)
+    fq = _fastq(rng, 40000)
+    ek, ec, _, _ = co.kmerize(25, [(fq, False)])
+    for _ in range(20):
+        km = nat.Kmerizer(25, 0)
+        km.feed(fq, False)
+        s, _ = km.finish()
+        km.close()
+        ks, cs = s.fetch()
+        assert np.array_equal(ks, ek) and np.array_equal(cs, ec)
+        s.free()

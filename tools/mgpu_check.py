@@ -54,6 +54,27 @@ for it in range(3):   # several steps: the double-buffered receive side is re-us
         ek, ec, _, _ = co.kmerize(K, [(sh, False) for sh in shards])
         assert np.array_equal(gk[order], ek) and np.array_equal(gc[order], ec), "multi-GPU kmerize differs from the oracle"
 if p2p is not None:
+    # ONE kmerizer streamed through several exchanges (bench.py's human leg, tools/human_scale.py), with a rank that is
+    # late on some steps: a fast peer must not route step s + 2 into a receive buffer whose step-s keys are still being
+    # sorted (the reserve mode had no collective that held peers back)
+    import time
+    km = nat.Kmerizer(K, dev)
+    for it in range(5):
+        km.feed(shards[rank], False)
+        if rank == (it % world) and it % 2 == 1:
+            time.sleep(0.3)
+        p2p.exchange(km)
+    s, nr = km.finish()
+    km.close()
+    ks, cs = s.fetch()
+    s.free()
+    parts = [None] * world
+    dist.all_gather_object(parts, (ks, cs))
+    if rank == 0:
+        gk = np.concatenate([p[0] for p in parts]); gc = np.concatenate([p[1] for p in parts])
+        order = np.argsort(gk)
+        ek, ec, _, _ = co.kmerize(K, [(sh, False) for sh in shards] * 5)
+        assert np.array_equal(gk[order], ek) and np.array_equal(gc[order], ec), "streamed multi-step exchange differs from the oracle"
     p2p.close()
 # all-pairs shards
 rng = np.random.default_rng(1)

@@ -47,6 +47,7 @@ SIGNATURES = {
     "zb_ipc_free": (C.c_int, [C.c_int, vp]),
     "zb_kmerize_adopt_canonical_dev": (C.c_int, [vp, vp, C.c_size_t]),
     "zb_kmerize_add_canonical_dev": (C.c_int, [vp, vp, C.c_size_t]),
+    "zb_kmerize_flush": (C.c_int, [vp]),
     "zb_set_from_host": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.POINTER(vp)]),
     "zb_set_from_device": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.POINTER(vp)]),
     "zb_set_lower_bound": (C.c_int, [vp, vp, C.c_size_t, vp]),
@@ -70,6 +71,23 @@ SIGNATURES = {
     "zb_set_encode": (C.c_int, [vp, vp, C.POINTER(C.c_size_t), vp, C.POINTER(C.c_size_t)]),
     "zb_set_encode_sizes": (C.c_int, [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "zb_set_from_streams": (C.c_int, [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(vp)]),
+    "zb_set_encode_dev": (C.c_int, [vp, C.POINTER(vp)]),
+    "zb_words_sizes": (C.c_int, [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "zb_words_dev_ptrs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
+    "zb_words_fetch": (C.c_int, [vp, vp, vp]),
+    "zb_words_write_fd": (C.c_int, [vp, C.c_int, C.c_uint64, C.c_uint64]),
+    "zb_words_free": (C.c_int, [vp]),
+    "zb_set_encode_plan": (C.c_int, [vp, C.c_uint64, vp, vp, C.c_int, C.POINTER(vp), u64p, u64p]),
+    "zb_set_encode_emit": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+    "zb_encplan_free": (C.c_int, [vp]),
+    "zb_stage_input": (C.c_int, [C.c_int, vp, C.c_size_t, C.POINTER(vp)]),
+    "zb_stage_fd": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_size_t, C.POINTER(vp)]),
+    "zb_kmerize_feed_staged": (C.c_int, [vp, vp, C.c_int]),
+    "zb_staged_free": (C.c_int, [vp]),
+    "zb_host_count_byte": (C.c_int, [vp, C.c_size_t, C.c_int, u64p]),
+    "zb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
+    "zb_host_free": (C.c_int, [vp]),
+    "zb_dbg_guard_check": (C.c_int, [C.c_int, u64p, u64p]),
     "zb_dbg_sort_u64": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "zb_dbg_sort_count": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp, vp,
                                     C.POINTER(C.c_size_t), C.POINTER(C.c_float)]),
@@ -241,6 +259,25 @@ class KmerSet(object):
         _check(lib().zb_project(self.h, int(shift_bits), C.byref(h)))
         return KmerSet(h, self.device)
 
+    def encode_dev(self):
+        """the two packed file streams of the set, left on the device -> Words"""
+        h = vp()
+        _check(lib().zb_set_encode_dev(self.h, C.byref(h)))
+        return Words(h, self.device)
+
+    def encode_plan(self, prev_kmer=0, next_kmers=(), next_counts=()):
+        """first phase of a range-partitioned encode (this set = one range of a longer sorted set):
+        -> (EncodePlan, kmer_map, count_map); map = ([exit state per entry state], [words per entry state])"""
+        nk = np.ascontiguousarray(next_kmers, dtype=np.uint64)
+        nc = np.ascontiguousarray(next_counts, dtype=np.uint32)
+        assert len(nk) == len(nc) <= 5
+        h = vp()
+        km = (C.c_uint64 * 12)()
+        cm = (C.c_uint64 * 12)()
+        _check(lib().zb_set_encode_plan(self.h, int(prev_kmer), _ptr(nk), _ptr(nc), len(nk), C.byref(h), km, cm))
+        return (EncodePlan(h, self), ([int(x) for x in km[:6]], [int(x) for x in km[6:]]),
+                ([int(x) for x in cm[:6]], [int(x) for x in cm[6:]]))
+
     def encode(self):
         """-> (kmer stream words, count stream words) exactly as the reference writes them."""
         nk, nc = C.c_size_t(0), C.c_size_t(0)
@@ -260,6 +297,154 @@ class KmerSet(object):
             self.free()
         except Exception:
             pass
+
+
+class Words(object):
+    """The packed codec64 streams ('kmers' delta-coded, 'counts') of a set, resident on the device."""
+
+    def __init__(self, handle, device):
+        self.h = handle
+        self.device = device
+
+    def sizes(self):
+        nk, nc = C.c_size_t(0), C.c_size_t(0)
+        _check(lib().zb_words_sizes(self.h, C.byref(nk), C.byref(nc)))
+        return nk.value, nc.value
+
+    def dev_ptrs(self):
+        a, b = vp(), vp()
+        _check(lib().zb_words_dev_ptrs(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def fetch(self, out_k=None, out_c=None):
+        """-> (kmer words, count words) on the host; out_k / out_c: preallocated (e.g. pinned) uint64 arrays"""
+        nk, nc = self.sizes()
+        kw = np.empty(nk, np.uint64) if out_k is None else out_k[:nk]
+        cw = np.empty(nc, np.uint64) if out_c is None else out_c[:nc]
+        _check(lib().zb_words_fetch(self.h, _ptr(kw), _ptr(cw)))
+        return kw, cw
+
+    def write_fd(self, fd, kmers_offset, counts_offset):
+        """device -> pinned ring -> pwrite(fd) at the two offsets, on the library's I/O threads"""
+        _check(lib().zb_words_write_fd(self.h, int(fd), int(kmers_offset), int(counts_offset)))
+
+    def free(self):
+        if self.h is not None and self.h.value:
+            lib().zb_words_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class EncodePlan(object):
+    def __init__(self, handle, kset):
+        self.h = handle
+        self.kset = kset      # the plan reads the set again in emit
+
+    def emit(self, kmer_entry_state, count_entry_state):
+        """second phase -> Words; consumes the plan"""
+        h = vp()
+        ph, self.h = self.h, None
+        _check(lib().zb_set_encode_emit(ph, int(kmer_entry_state), int(count_entry_state), C.byref(h)))
+        return Words(h, self.kset.device)
+
+    def __del__(self):
+        try:
+            if self.h is not None and self.h.value:
+                lib().zb_encplan_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def chain_ranges(maps):
+    """maps: per range (exit[6], words[6]) in order -> (entry state per range, word offset per range, total words)
+    (zb_set_encode_plan: state 0 in front of the first range)"""
+    st, off = 0, 0
+    entry, offs = [], []
+    for (ex, wd) in maps:
+        entry.append(st)
+        offs.append(off)
+        off += wd[st]
+        st = ex[st]
+    return entry, offs, off
+
+
+class Staged(object):
+    """input text on its way to the device (zb_stage_input / zb_stage_fd)"""
+
+    def __init__(self, handle, keep=None):
+        self.h = handle
+        self.keep = keep      # the host buffer must outlive the copy
+
+    def free(self):
+        if self.h is not None and self.h.value:
+            lib().zb_staged_free(self.h)
+            self.h = None
+        self.keep = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def stage_input(data, device=0):
+    """start the asynchronous copy of `data` (bytes / memoryview / mmap / uint8 array) to the device -> Staged"""
+    a = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+    h = vp()
+    _check(lib().zb_stage_input(device, _ptr(a), len(a), C.byref(h)))
+    return Staged(h, (a, data))
+
+
+def stage_fd(fd, offset, n, device=0):
+    """the same straight from a file descriptor (pread on the I/O threads)"""
+    h = vp()
+    _check(lib().zb_stage_fd(device, int(fd), int(offset), int(n), C.byref(h)))
+    return Staged(h)
+
+
+def host_count_byte(data, byte):
+    a = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+    n = C.c_uint64(0)
+    _check(lib().zb_host_count_byte(_ptr(a), len(a), int(byte), C.byref(n)))
+    return n.value
+
+
+class PinnedArray(object):
+    """a numpy array over pinned host memory of the library's arena (zb_host_alloc); .a is the array"""
+
+    def __init__(self, n, dtype):
+        dt = np.dtype(dtype)
+        self.p = vp()
+        self.nbytes = max(int(n), 1) * dt.itemsize
+        _check(lib().zb_host_alloc(self.nbytes, C.byref(self.p)))
+        buf = (C.c_uint8 * self.nbytes).from_address(self.p.value)
+        self.a = np.frombuffer(buf, dtype=dt, count=max(int(n), 1))
+
+    def free(self):
+        if self.p is not None and self.p.value:
+            self.a = None
+            lib().zb_host_free(self.p)
+            self.p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def guard_check(device=0):
+    """(blocks scanned, blocks with a damaged guard band); needs ZB_GUARD=1 in the environment"""
+    nb, bad = C.c_uint64(0), C.c_uint64(0)
+    _check(lib().zb_dbg_guard_check(device, C.byref(nb), C.byref(bad)))
+    return nb.value, bad.value
 
 
 def merge(sets):
@@ -336,6 +521,14 @@ class Kmerizer(object):
         if len(a):
             _check(lib().zb_kmerize_feed(self.h, _ptr(a), len(a), 1 if is_fasta else 0))
 
+    def feed_staged(self, staged, is_fasta):
+        """feed a piece started with stage_input / stage_fd (consumes it)"""
+        h, staged.h = staged.h, None
+        try:
+            _check(lib().zb_kmerize_feed_staged(self.h, h, 1 if is_fasta else 0))
+        finally:
+            staged.keep = None
+
     def feed_dev(self, dptr, n, is_fasta):
         _check(lib().zb_kmerize_feed_dev(self.h, vp(dptr), n, 1 if is_fasta else 0))
 
@@ -380,6 +573,10 @@ class Kmerizer(object):
 
     def adopt_canonical_dev(self, dptr, n):
         _check(lib().zb_kmerize_adopt_canonical_dev(self.h, vp(dptr), n))
+
+    def flush(self):
+        """count what is pending / adopted now (an adopted array is free for its owner afterwards)"""
+        _check(lib().zb_kmerize_flush(self.h))
 
     def add_canonical_dev(self, dptr, n):
         _check(lib().zb_kmerize_add_canonical_dev(self.h, vp(dptr), n))

@@ -59,6 +59,8 @@ Ctx* ctx_for(int device) {
     ZB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     ZB_CUDA(cudaHostAlloc((void**)&c->h_scalars, 64 * sizeof(uint64_t), cudaHostAllocMapped));
     ZB_CUDA(cudaHostGetDevicePointer((void**)&c->d_h_scalars, c->h_scalars, 0));
+    ZB_CUDA(cudaHostAlloc((void**)&c->h_big, H_BIG, cudaHostAllocMapped));
+    ZB_CUDA(cudaHostGetDevicePointer((void**)&c->d_h_big, c->h_big, 0));
     g_ctx[key] = c;
     return c;
 }
@@ -92,6 +94,13 @@ __global__ void __launch_bounds__(256) copy_kernel(T* __restrict__ dst, const T*
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) dst[i] = src[i];
 }
 
+cudaError_t read_back_big(Ctx* c, const void* d_src, size_t bytes) {
+    if (bytes > H_BIG || (bytes & 15) || ((uintptr_t)d_src & 15)) return cudaErrorInvalidValue;
+    copy_kernel<uint4><<<(unsigned)div_up(bytes / 16, 256), 256, 0, c->stream>>>((uint4*)c->d_h_big, (const uint4*)d_src, bytes / 16);
+    c->launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t dev_memset(Ctx* c, void* p, int value, size_t bytes) {
     if (bytes == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)std::min<size_t>((size_t)c->sm_count * 8, div_up(std::max<size_t>(bytes / 16, 32), 256));
@@ -112,6 +121,27 @@ cudaError_t dev_copy(Ctx* c, void* dst, const void* src, size_t bytes) {
     else copy_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((uint8_t*)dst, (const uint8_t*)src, n);
     c->launches++;
     return cudaGetLastError();
+}
+
+// ZB_GUARD=1: every block carries GUARD pattern bytes in front and behind (zb_dbg_guard_check scans them).  The pool's
+// compute-sanitizer is closed, so this is how an out-of-bounds store next to a library buffer is caught in the tests.
+static const size_t GUARD = 256;
+static bool guard_on() {
+    static const bool on = [] { const char* e = getenv("ZB_GUARD"); return e && atoi(e) != 0; }();
+    return on;
+}
+static cudaError_t raw_alloc(Ctx* c, void** p, size_t want) {
+    if (!guard_on()) return cudaMalloc(p, want);
+    void* base = nullptr;
+    cudaError_t e = cudaMalloc(&base, want + 2 * GUARD);
+    if (e != cudaSuccess) return e;
+    dev_memset(c, base, 0xA5, GUARD);
+    dev_memset(c, (char*)base + GUARD + want, 0xA5, GUARD);
+    *p = (char*)base + GUARD;
+    return cudaSuccess;
+}
+static void raw_free(void* p) {
+    if (p) cudaFree(guard_on() ? (void*)((char*)p - GUARD) : p);
 }
 
 static size_t round_block(size_t b) {
@@ -153,7 +183,7 @@ void* dalloc(Ctx* c, size_t bytes) {
             for (auto fit = c->free_blocks.begin(); fit != c->free_blocks.end(); ++fit) {
                 if (fit->second == ap.second) {
                     c->cached_bytes -= fit->first;
-                    cudaFree(fit->second);
+                    raw_free(fit->second);
                     c->free_blocks.erase(fit);
                     break;
                 }
@@ -162,15 +192,15 @@ void* dalloc(Ctx* c, size_t bytes) {
         }
     }
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, want);
+    cudaError_t e = raw_alloc(c, &p, want);
     if (e != cudaSuccess) {
         cudaGetLastError();
         cudaStreamSynchronize(c->stream);
-        for (auto& kv : c->free_blocks) cudaFree(kv.second);
+        for (auto& kv : c->free_blocks) raw_free(kv.second);
         c->free_blocks.clear();
         c->freed_at.clear();
         c->cached_bytes = 0;
-        e = cudaMalloc(&p, want);
+        e = raw_alloc(c, &p, want);
     }
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -197,7 +227,7 @@ void dfree(Ctx* c, void* p) {
 
 void dtrim(Ctx* c) {
     std::lock_guard<std::mutex> lk(c->alloc_mu);
-    for (auto& kv : c->free_blocks) cudaFree(kv.second);
+    for (auto& kv : c->free_blocks) raw_free(kv.second);
     c->free_blocks.clear();
     c->freed_at.clear();
     c->cached_bytes = 0;
@@ -347,11 +377,12 @@ static void feed_dev_impl(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is
     extract_codes(h, cd, n_codes);
 }
 
+namespace zb {
 // Large host <-> device copies go out in 64 MiB pieces with at most three of them queued: a copy engine serves the
 // streams of all host threads in the order the transfers were queued, so whatever another thread's step needs from
 // the engine waits for three pieces, not for a whole 315 MB input (measured: with one 315 MB copy queued the other
 // thread's sort + count took 13 ms instead of 6).
-static void copy_chunked(Ctx* c, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+void copy_chunked(Ctx* c, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
     static const size_t piece_mb = [] { const char* e = getenv("ZB_COPY_PIECE_MB"); return e ? (size_t)atoi(e) : (size_t)64; }();
     const size_t piece = piece_mb << 20;   // ZB_COPY_PIECE_MB=0: one unthrottled copy
     if (piece == 0 || bytes <= 2 * piece) {
@@ -375,18 +406,13 @@ static void copy_chunked(Ctx* c, void* dst, const void* src, size_t bytes, cudaM
 // and every step waits for all of them; with a lock around the SM phases as well 8.7 - 9.0 -- the host round trips
 // inside a phase, a dozen few-byte read-backs, then leave the GPU idle).  Locks are never nested; a single-threaded
 // caller never waits.  ZB_ENGINE_LOCKS overrides the policy (bit 0 copy-in, bit 1 SMs, bit 2 copy-out; default 5).
-enum { ENG_H2D = 0, ENG_SM = 1, ENG_D2H = 2 };
-static std::mutex g_engine_mu[64][3];
-static int engine_lock_mask() {
+std::mutex g_engine_mu[64][3];
+int engine_lock_mask() {
     static const int m = [] { const char* e = getenv("ZB_ENGINE_LOCKS"); return e ? atoi(e) : 5; }();
     return m;
 }
-struct EngineLock {
-    std::unique_lock<std::mutex> lk;
-    EngineLock(const Ctx* c, int kind) : lk(g_engine_mu[c->device & 63][kind], std::defer_lock) {
-        if ((engine_lock_mask() >> kind) & 1) lk.lock();
-    }
-};
+
+}  // namespace zb
 
 static zb_set* new_set(Ctx* c, size_t n) {
     zb_set* s = new zb_set();
@@ -396,6 +422,15 @@ static zb_set* new_set(Ctx* c, size_t n) {
     s->cnt.alloc(c, n);
     return s;
 }
+
+// hostio.cu: a staged piece is fed in stream order (the kmerizer's stream already waits for the copies)
+int zb_kmerize_feed_dev_ordered(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is_fasta) {
+    ZB_TRY
+    EngineLock el(h->c, ENG_SM);
+    feed_dev_impl(h, d_raw, n, is_fasta);
+    ZB_CATCH
+}
+zb::Ctx* zb_kmerizer_ctx(zb_kmerizer* h) { return h->c; }
 
 extern "C" {
 
@@ -727,6 +762,15 @@ int zb_kmerize_adopt_canonical_dev(zb_kmerizer* h, uint64_t* d_keys, size_t n) {
     flush_pending(h);          // an earlier adopted array must be consumed before its owner re-uses it
     h->adopted = d_keys;
     h->adopted_n = n;
+    ZB_CATCH
+}
+
+int zb_kmerize_flush(zb_kmerizer* h) {
+    ZB_TRY
+    if (!h) ZB_FAIL(ZB_E_ARG, "null handle");
+    ZB_CUDA(cudaSetDevice(h->c->device));
+    EngineLock el(h->c, ENG_SM);
+    flush_pending(h);
     ZB_CATCH
 }
 
@@ -1230,6 +1274,46 @@ int zb_dbg_extract(int device, int k, const uint8_t* codes, size_t n, uint64_t* 
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     *n_keys = (size_t)c->h_scalars[0];
     if (keys && *n_keys) ZB_CUDA(cudaMemcpy(keys, out.get(), *n_keys * 8, cudaMemcpyDeviceToHost));
+    ZB_CATCH
+}
+
+__global__ void guard_check_kernel(const uint64_t* __restrict__ blocks /*[n][2] = user pointer, size*/, uint32_t n,
+                                   unsigned long long* __restrict__ n_bad) {
+    const uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= n) return;
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(blocks[2 * b]);
+    const uint64_t sz = blocks[2 * b + 1];
+    bool bad = false;
+    for (unsigned i = lane_id(); i < 256; i += 32) bad |= (p[(long long)i - 256] != 0xA5) | (p[sz + i] != 0xA5);
+    if (__any_sync(0xffffffffu, bad) && lane_id() == 0) atomicAdd(n_bad, 1ull);
+}
+
+int zb_dbg_guard_check(int device, uint64_t* n_blocks, uint64_t* n_bad) {
+    ZB_TRY
+    Ctx* c = ctx_for(device);
+    if (n_blocks) *n_blocks = 0;
+    if (n_bad) *n_bad = 0;
+    if (!guard_on()) ZB_FAIL(ZB_E_ARG, "guard bands are off: set ZB_GUARD=1 before the library is first used");
+    std::vector<uint64_t> blocks;
+    {
+        std::lock_guard<std::mutex> lk(c->alloc_mu);
+        for (auto& kv : c->live_blocks) { blocks.push_back((uint64_t)(uintptr_t)kv.first); blocks.push_back(kv.second); }
+        for (auto& kv : c->free_blocks) { blocks.push_back((uint64_t)(uintptr_t)kv.second); blocks.push_back(kv.first); }
+    }
+    const size_t n = blocks.size() / 2;
+    if (n_blocks) *n_blocks = n;
+    if (n == 0) return ZB_OK;
+    uint64_t* d = nullptr;   // outside the guarded allocator: the list must not change while it is scanned
+    ZB_CUDA(cudaMalloc((void**)&d, (blocks.size() + 1) * 8));
+    ZB_CUDA(cudaMemcpyAsync(d + 1, blocks.data(), blocks.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    ZB_CUDA(cudaMemsetAsync(d, 0, 8, c->stream));
+    guard_check_kernel<<<(unsigned)div_up(n, 8), 256, 0, c->stream>>>(d + 1, (uint32_t)n, reinterpret_cast<unsigned long long*>(d));
+    c->launches++;
+    uint64_t bad = 0;
+    ZB_CUDA(cudaMemcpyAsync(&bad, d, 8, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    if (n_bad) *n_bad = bad;
     ZB_CATCH
 }
 

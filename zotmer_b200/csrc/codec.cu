@@ -37,17 +37,27 @@ static constexpr int EN_PER = 8;
 static constexpr int EN_TILE = EN_THREADS * EN_PER;   // 2048 values
 
 // bit lengths of the tile's values (+5 beyond its end) -> sbl[]; group length for a word starting at p -> sJ[p]
+// A stream may be ONE RANGE of a longer one (several GPUs encode consecutive ranges of a sorted set into one file,
+// api: zb_set_encode_plan): `halo` then holds the first n_halo (<= 5) values of the following range -- a word that
+// starts in this range may run into them -- and `first_base` is the value in front of vals[0] (delta only).
+struct EncRange {
+    uint64_t first_base;        // subtracted from vals[0] when delta (0 for a whole stream)
+    uint64_t halo[5];           // values behind vals[n - 1]
+    uint32_t n_halo;
+};
+
 template <typename T>
-__device__ __forceinline__ void enc_prepare(const T* __restrict__ vals, uint64_t n, bool delta, uint64_t base,
+__device__ __forceinline__ void enc_prepare(const T* __restrict__ vals, uint64_t n, bool delta, uint64_t base, const EncRange& rg,
                                             uint8_t* sbl, uint8_t* sJ, uint64_t* sv, unsigned int* err) {
     const unsigned tid = threadIdx.x;
     for (int p = tid; p < EN_TILE + 5; p += EN_THREADS) {
         const uint64_t i = base + p;
         uint64_t v = 0;
         int bl = 255;   // past the end of the data: never fits, so no group runs over the end
-        if (i < n) {
-            const uint64_t x = (uint64_t)vals[i];
-            v = (delta && i > 0) ? x - (uint64_t)vals[i - 1] : x;
+        if (i < n + rg.n_halo) {
+            const uint64_t x = (i < n) ? (uint64_t)vals[i] : rg.halo[i - n];
+            const uint64_t prev = (i == 0) ? rg.first_base : (i <= n) ? (uint64_t)vals[i - 1] : rg.halo[i - n - 1];
+            v = delta ? x - prev : x;
             bl = bitlen64(v);
         }
         sbl[p] = (uint8_t)bl;
@@ -72,12 +82,12 @@ __device__ __forceinline__ void enc_prepare(const T* __restrict__ vals, uint64_t
 
 template <typename T>
 __global__ void __launch_bounds__(EN_THREADS)
-enc_tile_kernel(const T* __restrict__ vals, uint64_t n, int delta, uint32_t* __restrict__ tile_info /*[tiles][6]*/,
+enc_tile_kernel(const T* __restrict__ vals, uint64_t n, int delta, const EncRange rg, uint32_t* __restrict__ tile_info /*[tiles][6]*/,
                 unsigned int* __restrict__ err) {
     __shared__ uint8_t sbl[EN_TILE + 8];
     __shared__ uint8_t sJ[EN_TILE];
     const uint64_t base = (uint64_t)blockIdx.x * EN_TILE;
-    enc_prepare<T>(vals, n, delta != 0, base, sbl, sJ, nullptr, err);
+    enc_prepare<T>(vals, n, delta != 0, base, rg, sbl, sJ, nullptr, err);
     if (threadIdx.x < 6) {
         const int lim = (int)min((uint64_t)EN_TILE, n - base);
         int p = threadIdx.x, cnt = 0;   // entry state r: the next word starts r positions into the tile
@@ -91,9 +101,10 @@ enc_tile_kernel(const T* __restrict__ vals, uint64_t n, int delta, uint32_t* __r
 
 // entry state and first word index of every tile.  One CTA: every thread composes a contiguous chunk of tiles
 // for all six entry states, thread 0 chains the chunks, every thread then replays its chunk.
+// range_map (may be null): [r] = exit state, [6 + r] = number of words, for every entry state r of the whole range
 __global__ void __launch_bounds__(1024)
-enc_scan_kernel(const uint32_t* __restrict__ tile_info, uint32_t tiles, uint8_t* __restrict__ entry,
-                uint64_t* __restrict__ woff, uint64_t* __restrict__ total_words) {
+enc_scan_kernel(const uint32_t* __restrict__ tile_info, uint32_t tiles, uint32_t entry0, uint8_t* __restrict__ entry,
+                uint64_t* __restrict__ woff, uint64_t* __restrict__ total_words, uint64_t* __restrict__ range_map) {
     __shared__ uint8_t c_exit[1024][6];
     __shared__ uint32_t c_cnt[1024][6];   // words in a chunk of tiles (a chunk holds far fewer than 2^32 values)
     __shared__ uint32_t c_state[1024];
@@ -112,8 +123,18 @@ enc_scan_kernel(const uint32_t* __restrict__ tile_info, uint32_t tiles, uint8_t*
         c_cnt[t][r] = cnt;
     }
     __syncthreads();
+    if (t < 6 && range_map) {
+        uint32_t st = t;
+        uint64_t off = 0;
+        for (int i = 0; i < 1024; i++) {
+            off += c_cnt[i][st];
+            st = c_exit[i][st];
+        }
+        range_map[t] = st;
+        range_map[6 + t] = off;
+    }
     if (t == 0) {
-        uint32_t st = 0;
+        uint32_t st = entry0;
         uint64_t off = 0;
         for (int i = 0; i < 1024; i++) {
             c_state[i] = st;
@@ -137,7 +158,7 @@ enc_scan_kernel(const uint32_t* __restrict__ tile_info, uint32_t tiles, uint8_t*
 
 template <typename T>
 __global__ void __launch_bounds__(EN_THREADS)
-enc_emit_kernel(const T* __restrict__ vals, uint64_t n, int delta, const uint8_t* __restrict__ entry,
+enc_emit_kernel(const T* __restrict__ vals, uint64_t n, int delta, const EncRange rg, const uint8_t* __restrict__ entry,
                 const uint64_t* __restrict__ woff, uint64_t* __restrict__ words, unsigned int* __restrict__ err) {
     __shared__ uint8_t sbl[EN_TILE + 8];
     __shared__ uint8_t sJ[EN_TILE];
@@ -147,7 +168,7 @@ enc_emit_kernel(const T* __restrict__ vals, uint64_t n, int delta, const uint8_t
     const unsigned tid = threadIdx.x;
     const uint64_t base = (uint64_t)blockIdx.x * EN_TILE;
     if (tid < EN_TILE / 32) sstart[tid] = 0;
-    enc_prepare<T>(vals, n, delta != 0, base, sbl, sJ, sv, err);
+    enc_prepare<T>(vals, n, delta != 0, base, rg, sbl, sJ, sv, err);
     const int lim = (int)min((uint64_t)EN_TILE, n - base);
     if (tid == 0) {
         int p = entry[blockIdx.x];
@@ -284,28 +305,80 @@ dec_emit_kernel(const uint64_t* __restrict__ words, uint64_t nw, int delta, cons
 }
 
 // ------------------------------------------------------------------------------------------- host side
-// vals (device, n values) -> words (device, capacity n); returns the number of words
+// Encoding in two phases, so that several GPUs can encode consecutive ranges of ONE stream: encode_plan computes the
+// per-tile maps and the range's own map (exit state and word count for each of the six entry states); the caller
+// chains the maps of the ranges on the host and hands every range its true entry state; encode_emit packs the words.
+struct EncodePlan {
+    uint32_t tiles = 0;
+    size_t n = 0;
+    bool delta = false;
+    EncRange rg;
+    DBuf<uint32_t> info;
+    DBuf<uint8_t> entry;
+    DBuf<uint64_t> woff;      // [tiles] word offsets, then [0] total words, [1] error flag, [2..13] range map
+    uint32_t map_exit[6];
+    uint64_t map_words[6];
+};
+
 template <typename T>
-static size_t encode_dev(Ctx* c, const T* d_vals, size_t n, bool delta, uint64_t* d_words) {
-    if (n == 0) return 0;
-    const uint32_t tiles = (uint32_t)div_up(n, EN_TILE);
-    DBuf<uint32_t> info(c, (size_t)tiles * 6);
-    DBuf<uint8_t> entry(c, tiles);
-    DBuf<uint64_t> woff(c, (size_t)tiles + 2);
-    uint64_t* total = woff.get() + tiles;
-    unsigned int* err = reinterpret_cast<unsigned int*>(woff.get() + tiles + 1);
+static void encode_plan(Ctx* c, const T* d_vals, size_t n, bool delta, const EncRange& rg, EncodePlan* p) {
+    p->n = n;
+    p->delta = delta;
+    p->rg = rg;
+    p->tiles = (uint32_t)div_up(n, EN_TILE);
+    if (n == 0) {   // an empty range passes its entry state on
+        for (int r = 0; r < 6; r++) { p->map_exit[r] = r; p->map_words[r] = 0; }
+        return;
+    }
+    p->info.alloc(c, (size_t)p->tiles * 6);
+    p->entry.alloc(c, p->tiles);
+    p->woff.alloc(c, (size_t)p->tiles + 14);
+    uint64_t* total = p->woff.get() + p->tiles;
+    unsigned int* err = reinterpret_cast<unsigned int*>(total + 1);
     ZB_CUDA(dev_memset(c, total, 0, 16));
-    enc_tile_kernel<T><<<tiles, EN_THREADS, 0, c->stream>>>(d_vals, n, delta ? 1 : 0, info.get(), err);
+    enc_tile_kernel<T><<<p->tiles, EN_THREADS, 0, c->stream>>>(d_vals, n, delta ? 1 : 0, rg, p->info.get(), err);
     ZB_LAUNCH_CHECK(c);
-    enc_scan_kernel<<<1, 1024, 0, c->stream>>>(info.get(), tiles, entry.get(), woff.get(), total);
+    enc_scan_kernel<<<1, 1024, 0, c->stream>>>(p->info.get(), p->tiles, 0u, p->entry.get(), p->woff.get(), total, total + 2);
     ZB_LAUNCH_CHECK(c);
-    enc_emit_kernel<T><<<tiles, EN_THREADS, 0, c->stream>>>(d_vals, n, delta ? 1 : 0, entry.get(), woff.get(), d_words, err);
+}
+
+// the range's map (synchronises); only needed when ranges are chained
+static void encode_plan_map(Ctx* c, EncodePlan* p) {
+    if (p->n == 0) return;
+    uint64_t* total = p->woff.get() + p->tiles;
+    ZB_CUDA(read_back(c, total + 2, 96));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < 6; r++) { p->map_exit[r] = (uint32_t)c->h_scalars[r]; p->map_words[r] = c->h_scalars[6 + r]; }
+}
+
+// words (device, capacity n); entry_state = 0 for a whole stream; returns the number of words written
+template <typename T>
+static size_t encode_emit(Ctx* c, const T* d_vals, EncodePlan* p, uint32_t entry_state, uint64_t* d_words) {
+    if (p->n == 0) return 0;
+    uint64_t* total = p->woff.get() + p->tiles;
+    unsigned int* err = reinterpret_cast<unsigned int*>(total + 1);
+    if (entry_state != 0) {   // the plan's scan ran with entry state 0
+        enc_scan_kernel<<<1, 1024, 0, c->stream>>>(p->info.get(), p->tiles, entry_state, p->entry.get(), p->woff.get(), total, nullptr);
+        ZB_LAUNCH_CHECK(c);
+    }
+    enc_emit_kernel<T><<<p->tiles, EN_THREADS, 0, c->stream>>>(d_vals, p->n, p->delta ? 1 : 0, p->rg, p->entry.get(), p->woff.get(), d_words, err);
     ZB_LAUNCH_CHECK(c);
     ZB_CUDA(read_back(c, total, 16));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     if (reinterpret_cast<uint32_t*>(c->h_scalars + 1)[0] != 0)
         ZB_FAIL(ZB_E_RANGE, "codec64: value or k-mer gap needs more than 60 bits (reference: IndexError, codec64.py:93-99)");
     return (size_t)c->h_scalars[0];
+}
+
+// vals (device, n values) -> words (device, capacity n); returns the number of words
+template <typename T>
+static size_t encode_dev(Ctx* c, const T* d_vals, size_t n, bool delta, uint64_t* d_words) {
+    if (n == 0) return 0;
+    EncodePlan p;
+    EncRange rg;
+    memset(&rg, 0, sizeof rg);
+    encode_plan<T>(c, d_vals, n, delta, rg, &p);
+    return encode_emit<T>(c, d_vals, &p, 0, d_words);
 }
 
 struct DecodePlan {
@@ -404,22 +477,161 @@ int zb_set_encode_sizes(const zb_set* s, size_t* n_kmer_words, size_t* n_count_w
 int zb_set_encode(const zb_set* s, uint64_t* kmer_words, size_t* n_kmer_words, uint64_t* count_words, size_t* n_count_words) {
     ZB_TRY
     if (!s || !n_kmer_words || !n_count_words) ZB_FAIL(ZB_E_ARG, "null argument");
-    const zb_set* v = s;
-    Ctx* c = v->c;
-    ZB_CUDA(cudaSetDevice(c->device));
     *n_kmer_words = *n_count_words = 0;
-    if (v->n == 0) return ZB_OK;
+    if (s->n == 0) return ZB_OK;
     if (!kmer_words || !count_words) ZB_FAIL(ZB_E_ARG, "null argument");
-    DBuf<uint64_t> dw(c, v->n);
-    Stage st(c, "encode");
-    size_t nw = encode_dev<uint64_t>(c, v->k.get(), v->n, true, dw.get());
-    ZB_CUDA(cudaMemcpyAsync(kmer_words, dw.get(), nw * 8, cudaMemcpyDeviceToHost, c->stream));
-    *n_kmer_words = nw;
+    zb_words* w = nullptr;
+    if (int rc = zb_set_encode_dev(s, &w)) return rc;
+    *n_kmer_words = w->nk;
+    *n_count_words = w->nc;
+    const int rc = zb_words_fetch(w, kmer_words, count_words);
+    zb_words_free(w);
+    return rc;
+    ZB_CATCH
+}
+
+// the two packed streams of a set, left in HBM: codec64 kernels only, no PCIe traffic
+int zb_set_encode_dev(const zb_set* s, zb_words** out) {
+    ZB_TRY
+    if (!s || !out) ZB_FAIL(ZB_E_ARG, "null argument");
+    Ctx* c = s->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    zb_words* w = new zb_words();
+    w->c = c;
+    try {
+        EngineLock el(c, ENG_SM);
+        Stage st(c, "encode");
+        if (s->n) {
+            // worst case one value per word; the streams are trimmed to their real size afterwards only when that
+            // saves a lot (k-mer gaps of a 10 M set are ~27 bits: two per word; counts: six per word)
+            DBuf<uint64_t> tmp(c, s->n);
+            w->nk = encode_dev<uint64_t>(c, s->k.get(), s->n, true, tmp.get());
+            w->kw.alloc(c, w->nk);
+            ZB_CUDA(dev_copy(c, w->kw.get(), tmp.get(), w->nk * 8));
+            w->nc = encode_dev<uint32_t>(c, s->cnt.get(), s->n, false, tmp.get());
+            w->cw.alloc(c, w->nc);
+            ZB_CUDA(dev_copy(c, w->cw.get(), tmp.get(), w->nc * 8));
+            ZB_CUDA(cudaStreamSynchronize(c->stream));
+        }
+    } catch (...) {
+        delete w;
+        throw;
+    }
+    *out = w;
+    ZB_CATCH
+}
+
+struct zb_encplan {
+    const zb_set* s;
+    EncodePlan pk, pc;
+};
+
+int zb_set_encode_plan(const zb_set* s, uint64_t prev_kmer, const uint64_t* next_kmers, const uint32_t* next_counts, int n_next,
+                       zb_encplan** out, uint64_t kmer_map[12], uint64_t count_map[12]) {
+    ZB_TRY
+    if (!s || !out || !kmer_map || !count_map || n_next < 0 || n_next > 5 || (n_next && (!next_kmers || !next_counts)))
+        ZB_FAIL(ZB_E_ARG, "bad argument");
+    Ctx* c = s->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    zb_encplan* p = new zb_encplan();
+    p->s = s;
+    try {
+        EngineLock el(c, ENG_SM);
+        Stage st(c, "encode");
+        EncRange rk, rc;
+        memset(&rk, 0, sizeof rk);
+        memset(&rc, 0, sizeof rc);
+        rk.first_base = prev_kmer;
+        rk.n_halo = rc.n_halo = (uint32_t)n_next;
+        for (int i = 0; i < n_next; i++) { rk.halo[i] = next_kmers[i]; rc.halo[i] = next_counts[i]; }
+        encode_plan<uint64_t>(c, s->k.get(), s->n, true, rk, &p->pk);
+        encode_plan<uint32_t>(c, s->cnt.get(), s->n, false, rc, &p->pc);
+        encode_plan_map(c, &p->pk);
+        encode_plan_map(c, &p->pc);
+    } catch (...) {
+        delete p;
+        throw;
+    }
+    for (int r = 0; r < 6; r++) {
+        kmer_map[r] = p->pk.map_exit[r]; kmer_map[6 + r] = p->pk.map_words[r];
+        count_map[r] = p->pc.map_exit[r]; count_map[6 + r] = p->pc.map_words[r];
+    }
+    *out = p;
+    ZB_CATCH
+}
+
+int zb_set_encode_emit(zb_encplan* p, int kmer_entry_state, int count_entry_state, zb_words** out) {
+    ZB_TRY
+    if (!p || !out || kmer_entry_state < 0 || kmer_entry_state > 5 || count_entry_state < 0 || count_entry_state > 5)
+        ZB_FAIL(ZB_E_ARG, "bad argument");
+    const zb_set* s = p->s;
+    Ctx* c = s->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    zb_words* w = new zb_words();
+    w->c = c;
+    try {
+        EngineLock el(c, ENG_SM);
+        Stage st(c, "encode");
+        if (s->n) {
+            w->kw.alloc(c, p->pk.map_words[kmer_entry_state] + 1);
+            w->nk = encode_emit<uint64_t>(c, s->k.get(), &p->pk, (uint32_t)kmer_entry_state, w->kw.get());
+            w->cw.alloc(c, p->pc.map_words[count_entry_state] + 1);
+            w->nc = encode_emit<uint32_t>(c, s->cnt.get(), &p->pc, (uint32_t)count_entry_state, w->cw.get());
+            if (w->nk != p->pk.map_words[kmer_entry_state] || w->nc != p->pc.map_words[count_entry_state])
+                ZB_FAIL(ZB_E_CUDA, "codec64: the emitted word count differs from the plan's");
+        }
+    } catch (...) {
+        delete w;
+        delete p;
+        throw;
+    }
+    delete p;
+    *out = w;
+    ZB_CATCH
+}
+
+int zb_encplan_free(zb_encplan* p) {
+    ZB_TRY
+    if (p) {
+        cudaSetDevice(p->s->c->device);
+        delete p;
+    }
+    ZB_CATCH
+}
+
+int zb_words_sizes(const zb_words* w, size_t* n_kmer_words, size_t* n_count_words) {
+    if (!w) { zb::set_error("null argument"); return ZB_E_ARG; }
+    if (n_kmer_words) *n_kmer_words = w->nk;
+    if (n_count_words) *n_count_words = w->nc;
+    return ZB_OK;
+}
+
+int zb_words_dev_ptrs(const zb_words* w, const uint64_t** d_kmer_words, const uint64_t** d_count_words) {
+    if (!w) { zb::set_error("null argument"); return ZB_E_ARG; }
+    if (d_kmer_words) *d_kmer_words = w->kw.get();
+    if (d_count_words) *d_count_words = w->cw.get();
+    return ZB_OK;
+}
+
+int zb_words_fetch(const zb_words* w, uint64_t* kmer_words, uint64_t* count_words) {
+    ZB_TRY
+    if (!w) ZB_FAIL(ZB_E_ARG, "null argument");
+    Ctx* c = w->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    EngineLock el(c, ENG_D2H);
+    Stage st(c, "d2h_words");
+    if (w->nk && kmer_words) copy_chunked(c, kmer_words, w->kw.get(), w->nk * 8, cudaMemcpyDeviceToHost);
+    if (w->nc && count_words) copy_chunked(c, count_words, w->cw.get(), w->nc * 8, cudaMemcpyDeviceToHost);
     ZB_CUDA(cudaStreamSynchronize(c->stream));
-    nw = encode_dev<uint32_t>(c, v->cnt.get(), v->n, false, dw.get());
-    ZB_CUDA(cudaMemcpyAsync(count_words, dw.get(), nw * 8, cudaMemcpyDeviceToHost, c->stream));
-    *n_count_words = nw;
-    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    ZB_CATCH
+}
+
+int zb_words_free(zb_words* w) {
+    ZB_TRY
+    if (w) {
+        cudaSetDevice(w->c->device);
+        delete w;
+    }
     ZB_CATCH
 }
 

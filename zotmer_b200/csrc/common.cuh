@@ -46,6 +46,8 @@ struct Ctx {
     cudaMemPool_t pool = nullptr;
     uint64_t* h_scalars = nullptr;  // pinned, 64 x u64
     uint32_t* d_h_scalars = nullptr;  // the same buffer as the device sees it
+    uint8_t* h_big = nullptr;       // pinned + mapped, H_BIG bytes: read-backs of a few KB (histograms) by a kernel
+    uint8_t* d_h_big = nullptr;
     uint64_t launches = 0;          // kernels launched through this context (bench "gpu_launches")
     // optional per-stage CUDA-event timing (zb_dbg_profile): name, start, stop
     // caching allocator state
@@ -88,6 +90,9 @@ Ctx* ctx_for(int device);
 // threads have in flight on the engine (bench.py's pipelined e2e: the sort + count of one step waited up to 5.7 ms
 // for the 315 MB input copy of the next step).  Synchronise the stream before reading h_scalars.
 cudaError_t read_back(Ctx* c, const void* d_src, size_t bytes);
+// the same for up to H_BIG bytes (a multiple of 16, 16-byte aligned source) into c->h_big
+static const size_t H_BIG = 64 << 10;
+cudaError_t read_back_big(Ctx* c, const void* d_src, size_t bytes);
 // Fill / device-to-device copy done by kernels on the context's stream, for the same reason: cudaMemsetAsync and
 // cudaMemcpyAsync(DeviceToDevice) may be served by a copy engine and then queue behind other threads' bulk transfers.
 cudaError_t dev_memset(Ctx* c, void* p, int value, size_t bytes);

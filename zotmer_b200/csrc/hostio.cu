@@ -1,0 +1,434 @@
+// hostio.cu -- the host side of the device boundary: a small pool of I/O threads with a ring of pinned chunks.
+//
+// The reference feeds its parser from `open(fn)` / a `gunzip -c` pipe (zotmer/library/file.py:79-123) and writes its
+// streams word by word (files.py:65-83).  Here the inputs are hundreds of megabytes that have to cross PCIe, and a
+// plain cudaMemcpy from pageable memory (a mapping of the input file, a decompressed buffer) runs at ~11 GB/s -- one
+// driver thread staging through one bounce buffer (profiles/r01_cli_end_to_end.md: 28 ms for 315 MB, 44 ms for the
+// 203 MB result).  The pool does the same thing on several threads: every worker owns two pinned chunks and one
+// stream per device;
+//   H2D job  : memcpy (or pread) a chunk of the input into a pinned chunk, cudaMemcpyAsync it to its place in the
+//              device buffer, record the chunk's event (the chunk is reused once that event has completed);
+//   D2H job  : cudaMemcpyAsync a chunk of a device array into a pinned chunk, wait, pwrite it at its file offset;
+//   count job: occurrences of a byte in a slice of host memory (record boundaries of FASTQ text).
+// zb_stage_input returns at once; zb_kmerize_feed_staged makes the kmerizer's stream wait for the workers' streams.
+#include <errno.h>
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <map>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <thread>
+
+#include "kernels.h"
+
+namespace zb {
+
+struct IoWorker {
+    int id = 0;
+    uint8_t* slot[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2][64];          // [slot][device], created on first use
+    int pending_dev[2] = {-1, -1};  // device whose event guards the slot, -1 = free
+    cudaStream_t stream[64];        // one per device, created by IoPool::ensure_device
+    int turn = 0;
+};
+
+class IoPool {
+  public:
+    static IoPool& get() {
+        static IoPool* p = new IoPool();   // never destroyed: worker threads may outlive static destruction order
+        return *p;
+    }
+    int nthreads() const { return (int)workers_.size(); }
+    size_t chunk() const { return chunk_; }
+
+    // streams of every worker on `device` exist afterwards
+    void ensure_device(int device) {
+        std::lock_guard<std::mutex> lk(dev_mu_);
+        if (dev_ready_[device & 63]) return;
+        ZB_CUDA(cudaSetDevice(device));
+        for (auto& w : workers_) ZB_CUDA(cudaStreamCreateWithFlags(&w->stream[device & 63], cudaStreamNonBlocking));
+        dev_ready_[device & 63] = true;
+    }
+    cudaStream_t stream_of(int worker, int device) { return workers_[worker]->stream[device & 63]; }
+
+    void submit(std::function<void(IoWorker&)> fn) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            q_.push_back(std::move(fn));
+        }
+        cv_.notify_one();
+    }
+
+  private:
+    IoPool() {
+        int nt = 8;
+        if (const char* e = getenv("ZB_IO_THREADS")) nt = atoi(e);
+        const unsigned hw = std::thread::hardware_concurrency();
+        if (hw && (unsigned)nt > hw) nt = (int)hw;
+        if (nt < 1) nt = 1;
+        if (nt > 32) nt = 32;
+        size_t mb = 4;
+        if (const char* e = getenv("ZB_IO_CHUNK_MB")) mb = (size_t)atoi(e);
+        if (mb < 1) mb = 1;
+        chunk_ = mb << 20;
+        for (int i = 0; i < 64; i++) dev_ready_[i] = false;
+        for (int i = 0; i < nt; i++) {
+            IoWorker* w = new IoWorker();
+            w->id = i;
+            memset(w->ev, 0, sizeof w->ev);
+            memset(w->stream, 0, sizeof w->stream);
+            workers_.push_back(w);
+        }
+        for (auto* w : workers_) threads_.emplace_back([this, w] { run(w); });
+        for (auto& t : threads_) t.detach();
+    }
+
+    void run(IoWorker* w) {
+        while (true) {
+            std::function<void(IoWorker&)> fn;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return !q_.empty(); });
+                fn = std::move(q_.front());
+                q_.pop_front();
+            }
+            fn(*w);
+        }
+    }
+
+    std::vector<IoWorker*> workers_;
+    std::vector<std::thread> threads_;
+    std::deque<std::function<void(IoWorker&)>> q_;
+    std::mutex mu_, dev_mu_;
+    std::condition_variable cv_;
+    bool dev_ready_[64];
+    size_t chunk_;
+};
+
+// a pinned chunk of the worker that is free to be overwritten (waits for the copy that last read it)
+static uint8_t* take_slot(IoWorker& w, size_t chunk, int* which) {
+    const int s = w.turn & 1;
+    w.turn++;
+    if (!w.slot[s]) {
+        if (cudaHostAlloc((void**)&w.slot[s], chunk, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    }
+    if (w.pending_dev[s] >= 0) {
+        cudaSetDevice(w.pending_dev[s]);
+        cudaEventSynchronize(w.ev[s][w.pending_dev[s] & 63]);
+        w.pending_dev[s] = -1;
+    }
+    *which = s;
+    return w.slot[s];
+}
+
+static bool guard_slot(IoWorker& w, int s, int device, cudaStream_t st) {
+    cudaEvent_t& e = w.ev[s][device & 63];
+    if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaEventRecord(e, st) != cudaSuccess) return false;
+    w.pending_dev[s] = device;
+    return true;
+}
+
+// completion of a group of jobs
+struct IoGroup {
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t remaining = 0;
+    uint32_t touched = 0;      // workers that enqueued device work for this group
+    int error = 0;             // errno-like, 0 = ok
+    void done(int worker, int err) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (worker >= 0) touched |= 1u << worker;
+        if (err && !error) error = err;
+        if (--remaining == 0) cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [this] { return remaining == 0; });
+    }
+};
+
+}  // namespace zb
+
+using namespace zb;
+
+struct zb_staged {
+    Ctx* c;
+    DBuf<uint8_t> d;
+    size_t n = 0;
+    IoGroup g;
+    cudaEvent_t ev[32];
+    cudaEvent_t alloc_ev = nullptr;   // the device buffer may be a recycled block still in use on the context's stream
+};
+
+// defined in api.cu: the body of zb_kmerize_feed_dev once the text is (or will be, in stream order) on the device
+int zb_kmerize_feed_dev_ordered(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is_fasta);
+zb::Ctx* zb_kmerizer_ctx(zb_kmerizer* h);
+
+static void stage_jobs(zb_staged* st, const uint8_t* raw, int fd, uint64_t file_off, size_t n) {
+    IoPool& pool = IoPool::get();
+    const size_t chunk = pool.chunk();
+    const size_t nchunks = div_up(n, chunk);
+    const int device = st->c->device;
+    pool.ensure_device(device);
+    uint8_t* dst = st->d.get();
+    ZB_CUDA(cudaEventCreateWithFlags(&st->alloc_ev, cudaEventDisableTiming));
+    ZB_CUDA(cudaEventRecord(st->alloc_ev, st->c->stream));
+    cudaEvent_t alloc_ev = st->alloc_ev;
+    st->g.remaining = nchunks;   // nothing below throws: every counted chunk is submitted
+    for (size_t i = 0; i < nchunks; i++) {
+        const size_t off = i * chunk, len = std::min(chunk, n - off);
+        pool.submit([st, raw, fd, file_off, dst, off, len, device, chunk, alloc_ev](IoWorker& w) {
+            int err = 0, s = 0;
+            uint8_t* slot = take_slot(w, chunk, &s);
+            if (!slot) { st->g.done(-1, ENOMEM); return; }
+            if (raw) {
+                memcpy(slot, raw + off, len);
+            } else {
+                size_t got = 0;
+                while (got < len) {
+                    const ssize_t r = pread(fd, slot + got, len - got, (off_t)(file_off + off + got));
+                    if (r <= 0) { err = r < 0 ? errno : EIO; break; }
+                    got += (size_t)r;
+                }
+            }
+            if (!err) {
+                cudaSetDevice(device);
+                cudaStream_t ws = w.stream[device & 63];
+                if (cudaStreamWaitEvent(ws, alloc_ev, 0) != cudaSuccess ||
+                    cudaMemcpyAsync(dst + off, slot, len, cudaMemcpyHostToDevice, ws) != cudaSuccess || !guard_slot(w, s, device, ws)) err = EIO;
+            }
+            st->g.done(w.id, err);
+        });
+    }
+}
+
+extern "C" {
+
+int zb_stage_input(int device, const uint8_t* raw, size_t n, zb_staged** out) {
+    ZB_TRY
+    if (!out || (n && !raw)) ZB_FAIL(ZB_E_ARG, "null argument");
+    if (n >= ((size_t)1 << 31)) ZB_FAIL(ZB_E_ARG, "stage: piece of %zu bytes; split the input at record boundaries below 2 GiB", n);
+    Ctx* c = ctx_for(device);
+    zb_staged* st = new zb_staged();
+    st->c = c;
+    st->n = n;
+    memset(st->ev, 0, sizeof st->ev);
+    try {
+        st->d.alloc(c, n + 16);
+        if (n) stage_jobs(st, raw, -1, 0, n);
+    } catch (...) {
+        st->g.wait();
+        delete st;
+        throw;
+    }
+    *out = st;
+    ZB_CATCH
+}
+
+int zb_stage_fd(int device, int fd, uint64_t offset, size_t n, zb_staged** out) {
+    ZB_TRY
+    if (!out || fd < 0) ZB_FAIL(ZB_E_ARG, "bad argument");
+    if (n >= ((size_t)1 << 31)) ZB_FAIL(ZB_E_ARG, "stage: piece of %zu bytes; split the input at record boundaries below 2 GiB", n);
+    Ctx* c = ctx_for(device);
+    zb_staged* st = new zb_staged();
+    st->c = c;
+    st->n = n;
+    memset(st->ev, 0, sizeof st->ev);
+    try {
+        st->d.alloc(c, n + 16);
+        if (n) stage_jobs(st, nullptr, fd, offset, n);
+    } catch (...) {
+        st->g.wait();
+        delete st;
+        throw;
+    }
+    *out = st;
+    ZB_CATCH
+}
+
+static void staged_release(zb_staged* st) {
+    st->g.wait();
+    cudaSetDevice(st->c->device);
+    // the workers' copies may still be running: the buffer goes back to the allocator (and may be handed out again on
+    // the context's stream) only after they have finished
+    IoPool& pool = IoPool::get();
+    for (int w = 0; w < pool.nthreads(); w++)
+        if ((st->g.touched >> w) & 1u) cudaStreamSynchronize(pool.stream_of(w, st->c->device));
+    for (int w = 0; w < 32; w++)
+        if (st->ev[w]) cudaEventDestroy(st->ev[w]);
+    if (st->alloc_ev) cudaEventDestroy(st->alloc_ev);
+    delete st;
+}
+
+int zb_staged_free(zb_staged* st) {
+    ZB_TRY
+    if (st) staged_release(st);
+    ZB_CATCH
+}
+
+int zb_kmerize_feed_staged(zb_kmerizer* h, zb_staged* st, int is_fasta) {
+    int rc = ZB_OK;
+    try {
+        if (!h || !st) ZB_FAIL(ZB_E_ARG, "null argument");
+        Ctx* c = zb_kmerizer_ctx(h);
+        if (st->c != c) ZB_FAIL(ZB_E_ARG, "the staged piece belongs to another device context (stage and feed from one thread)");
+        ZB_CUDA(cudaSetDevice(c->device));
+        {
+            Stage stg(c, "h2d_staged");
+            st->g.wait();   // every chunk has been handed to a worker stream
+            if (st->g.error) ZB_FAIL(ZB_E_CUDA, "staging the input failed (%s)", strerror(st->g.error));
+            IoPool& pool = IoPool::get();
+            for (int w = 0; w < pool.nthreads(); w++) {
+                if (!((st->g.touched >> w) & 1u)) continue;
+                if (!st->ev[w]) ZB_CUDA(cudaEventCreateWithFlags(&st->ev[w], cudaEventDisableTiming));
+                ZB_CUDA(cudaEventRecord(st->ev[w], pool.stream_of(w, c->device)));
+                ZB_CUDA(cudaStreamWaitEvent(c->stream, st->ev[w], 0));
+            }
+        }
+        if (st->n) rc = zb_kmerize_feed_dev_ordered(h, st->d.get(), st->n, is_fasta);
+    } catch (const zb::Fail& f) {
+        rc = f.code;
+    } catch (const std::bad_alloc&) {
+        zb::set_error("out of host memory");
+        rc = ZB_E_NOMEM;
+    }
+    if (st) {
+        const std::string keep = zb_last_error();
+        staged_release(st);
+        if (rc != ZB_OK) zb::set_error("%s", keep.c_str());
+    }
+    return rc;
+}
+
+int zb_host_count_byte(const uint8_t* p, size_t n, int byte, uint64_t* count) {
+    ZB_TRY
+    if (!count || (n && !p)) ZB_FAIL(ZB_E_ARG, "null argument");
+    *count = 0;
+    if (n == 0) return ZB_OK;
+    IoPool& pool = IoPool::get();
+    const size_t parts = std::min<size_t>((size_t)pool.nthreads(), div_up(n, (size_t)1 << 20));
+    std::vector<uint64_t> partial(parts, 0);
+    IoGroup g;
+    g.remaining = parts;
+    const size_t per = div_up(n, parts);
+    const uint8_t b = (uint8_t)byte;
+    for (size_t i = 0; i < parts; i++) {
+        const size_t lo = std::min(n, i * per), hi = std::min(n, lo + per);
+        uint64_t* dst = &partial[i];
+        pool.submit([p, lo, hi, b, dst, &g](IoWorker&) {
+            uint64_t cnt = 0;
+            // blocks of 255 x 16 bytes keep the per-byte-lane sums in 8 bits (the compiler vectorises the inner loop)
+            for (size_t i0 = lo; i0 < hi; i0 += 4096) {
+                const size_t i1 = std::min(hi, i0 + 4096);
+                uint32_t c32 = 0;
+                for (size_t j = i0; j < i1; j++) c32 += (p[j] == b);
+                cnt += c32;
+            }
+            *dst = cnt;
+            g.done(-1, 0);
+        });
+    }
+    g.wait();
+    uint64_t tot = 0;
+    for (uint64_t v : partial) tot += v;
+    *count = tot;
+    ZB_CATCH
+}
+
+int zb_words_write_fd(const zb_words* w, int fd, uint64_t kmers_offset, uint64_t counts_offset) {
+    ZB_TRY
+    if (!w || fd < 0) ZB_FAIL(ZB_E_ARG, "bad argument");
+    Ctx* c = w->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));   // the words are complete
+    IoPool& pool = IoPool::get();
+    const int device = c->device;
+    pool.ensure_device(device);
+    const size_t chunk = pool.chunk();
+    struct Part { const uint8_t* src; size_t bytes; uint64_t off; };
+    const Part parts[2] = {{reinterpret_cast<const uint8_t*>(w->kw.get()), w->nk * 8, kmers_offset},
+                           {reinterpret_cast<const uint8_t*>(w->cw.get()), w->nc * 8, counts_offset}};
+    IoGroup g;
+    size_t njobs = 0;
+    for (const Part& p : parts) njobs += div_up(p.bytes, chunk);
+    if (njobs == 0) return ZB_OK;
+    g.remaining = njobs;
+    for (const Part& p : parts) {
+        for (size_t o = 0; o < p.bytes; o += chunk) {
+            const size_t len = std::min(chunk, p.bytes - o);
+            const uint8_t* src = p.src + o;
+            const uint64_t foff = p.off + o;
+            pool.submit([src, len, foff, fd, device, chunk, &g](IoWorker& wk) {
+                int err = 0, s = 0;
+                uint8_t* slot = take_slot(wk, chunk, &s);
+                if (!slot) { g.done(-1, ENOMEM); return; }
+                cudaSetDevice(device);
+                cudaStream_t ws = wk.stream[device & 63];
+                if (cudaMemcpyAsync(slot, src, len, cudaMemcpyDeviceToHost, ws) != cudaSuccess ||
+                    cudaStreamSynchronize(ws) != cudaSuccess) err = EIO;
+                size_t put = 0;
+                while (!err && put < len) {
+                    const ssize_t r = pwrite(fd, slot + put, len - put, (off_t)(foff + put));
+                    if (r <= 0) { err = r < 0 ? errno : EIO; break; }
+                    put += (size_t)r;
+                }
+                g.done(-1, err);
+            });
+        }
+    }
+    g.wait();
+    if (g.error) ZB_FAIL(ZB_E_CUDA, "writing the word streams failed (%s)", strerror(g.error));
+    ZB_CATCH
+}
+
+// ---- pinned host memory (destinations of zb_words_fetch / zb_set_fetch): cudaHostAlloc is slow (~0.3 ms per MB), so
+// released blocks are kept and handed out again
+static std::mutex g_host_mu;
+static std::multimap<size_t, void*> g_host_free;
+static std::map<void*, size_t> g_host_live;
+
+int zb_host_alloc(size_t bytes, void** p) {
+    ZB_TRY
+    if (!p) ZB_FAIL(ZB_E_ARG, "null argument");
+    ctx_for(0);   // fails with ZB_E_NOGPU on a machine without a device
+    const size_t want = std::max<size_t>(4096, (bytes + 4095) & ~(size_t)4095);
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    auto it = g_host_free.lower_bound(want);
+    if (it != g_host_free.end() && it->first <= 2 * want) {
+        *p = it->second;
+        g_host_live[*p] = it->first;
+        g_host_free.erase(it);
+        return ZB_OK;
+    }
+    void* q = nullptr;
+    if (cudaHostAlloc(&q, want, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        for (auto& kv : g_host_free) cudaFreeHost(kv.second);
+        g_host_free.clear();
+        if (cudaHostAlloc(&q, want, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            ZB_FAIL(ZB_E_NOMEM, "out of pinned host memory: %zu bytes requested", want);
+        }
+    }
+    g_host_live[q] = want;
+    *p = q;
+    ZB_CATCH
+}
+
+int zb_host_free(void* p) {
+    ZB_TRY
+    if (!p) return ZB_OK;
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    auto it = g_host_live.find(p);
+    if (it == g_host_live.end()) ZB_FAIL(ZB_E_ARG, "not a pointer of zb_host_alloc");
+    g_host_free.insert({it->second, p});
+    g_host_live.erase(it);
+    ZB_CATCH
+}
+
+}  // extern "C"

@@ -15,6 +15,13 @@ struct zb_set {
     size_t n;
 };
 
+// the handle behind `zb_words*`: the two packed codec64 streams of a set ('kmers' delta-coded, 'counts'), in HBM
+struct zb_words {
+    zb::Ctx* c;
+    zb::DBuf<uint64_t> kw, cw;
+    size_t nk = 0, nc = 0;
+};
+
 // body of every extern "C" entry point: no exception crosses the C boundary
 #define ZB_TRY try {
 #define ZB_CATCH                                   \
@@ -27,6 +34,19 @@ struct zb_set {
     return ZB_OK;
 
 namespace zb {
+
+// ---- api.cu: bulk copies and the per-device engine locks ---------------------------------------
+// Large host <-> device copies in 64 MiB pieces, at most three queued (see api.cu)
+void copy_chunked(Ctx* c, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);
+enum { ENG_H2D = 0, ENG_SM = 1, ENG_D2H = 2 };
+extern std::mutex g_engine_mu[64][3];
+int engine_lock_mask();
+struct EngineLock {
+    std::unique_lock<std::mutex> lk;
+    EngineLock(const Ctx* c, int kind) : lk(g_engine_mu[c->device & 63][kind], std::defer_lock) {
+        if ((engine_lock_mask() >> kind) & 1) lk.lock();
+    }
+};
 
 // ---- sort.cu ---------------------------------------------------------------------------------
 // LSD radix sort ("onesweep": one upfront multi-digit histogram, then one chained-scan scatter

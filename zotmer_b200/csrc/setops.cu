@@ -587,8 +587,9 @@ void set_stats(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, uint64_
     hist->clear();
     if (n == 0) return;
     size_t ovf_cap = std::min<size_t>(n, 1u << 20);
+    Stage st(c, "stats");
     for (int attempt = 0; attempt < 2; attempt++) {
-        DBuf<unsigned long long> d(c, 8 + 2 * HBINS + 1);
+        DBuf<unsigned long long> d(c, 8 + 2 * HBINS + 2);
         DBuf<uint64_t> oidx(c, ovf_cap);
         DBuf<uint32_t> ocnt(c, ovf_cap);
         ZB_CUDA(dev_memset(c, d.get(), 0, (8 + HBINS) * 8));
@@ -598,9 +599,12 @@ void set_stats(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, uint64_
         stats_kernel<<<blocks, 256, 0, c->stream>>>(k, cnt, n, d.get(), d.get() + 8, d.get() + 8 + HBINS,
                                                     d.get() + 8 + 2 * HBINS, oidx.get(), ocnt.get(), ovf_cap);
         ZB_LAUNCH_CHECK(c);
-        std::vector<unsigned long long> h(8 + 2 * HBINS + 1);
-        ZB_CUDA(cudaMemcpyAsync(h.data(), d.get(), h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+        // read back by a kernel into mapped pinned memory: a copy-engine transfer of these 33 KB would queue behind the
+        // bulk copies other host threads have in flight
+        std::vector<unsigned long long> h(8 + 2 * HBINS + 2);
+        ZB_CUDA(read_back_big(c, d.get(), h.size() * 8));
         ZB_CUDA(cudaStreamSynchronize(c->stream));
+        memcpy(h.data(), c->h_big, h.size() * 8);
         const size_t novf = (size_t)h[8 + 2 * HBINS];
         if (novf > ovf_cap) { ovf_cap = novf; continue; }  // rare: rerun with an exact-size list
         for (int q = 0; q < 4; q++) { acgt_w[q] = h[q]; acgt_p[q] = h[4 + q]; *total += h[q]; }

@@ -106,32 +106,43 @@ def p2p_offsets(count_matrix, rank):
 
 class P2PExchange(object):
     """Routing and transfer in ONE kernel (csrc/extract.cu route_p2p_kernel): every rank maps every other rank's
-    receive buffer (CUDA IPC) and the bucketing kernel stores each key straight into its owner's buffer over
-    NVLink.  NCCL is used only for the tiny count matrix (so that ranks agree on their slots) and the barrier that
-    says "all stores have landed".  Two receive buffers alternate, so a fast rank may already fill the next one
-    while a slow rank still reads the current one; the per-step barrier is the only synchronisation.
+    receive buffers (CUDA IPC) and the bucketing kernel stores each key straight into its owner's buffer over
+    NVLink.  NCCL carries only the tiny count matrix (so that ranks agree on their slots) and the all-reduce that says
+    "all stores have landed" (and whether anybody overflowed).
 
-    reserve (ZB_P2P_RESERVE=1 or reserve=True; off by default): no count matrix at all -- every receive buffer ends in
-    a cursor word, and a thread block of the routing kernel reserves its run in the owner's buffer with one system-scope
-    atomic add on that word (over NVLink for a remote owner).  That drops the owner-count pass over the keys, the
-    all-gather and two host round trips from every step; after the barrier the owner reads its own cursor = keys
-    received.  The runs land in timing order, which the owner's sort makes irrelevant.  Measured at N = 2: step 6.46 ->
-    6.37 ms (the kernel waits ~3 us per thread block for its reservation: 0.88 -> 1.07 ms, which eats most of what the
-    dropped pass and round trips save); not measured at N = 8, hence not the default yet (profiles/r01_scaling.md)."""
+    Steps are numbered: exchange(km, seq) uses receive buffer seq % nbuf, and exchanges are issued in the order of their
+    numbers on every rank -- a host thread whose step's turn has not come waits (`_turn`), so several steps can be in
+    flight per rank (one host thread each: the H2D copy / extraction of step s + 1 and the sort of step s - 1 overlap
+    the exchange of step s) while the collectives still match up across ranks.  Why nbuf = steps in flight + 1 is
+    enough: peers store into buffer s % nbuf after the closing all-reduce of step s - 1, which this rank entered only
+    after the thread that runs step s - 1 had finished ITS previous step, s - 1 - inflight, completely (sorted); the
+    buffer's previous user, step s - nbuf, is no later than that.  A single kmerizer that is streamed through many
+    exchanges (tools/human_scale.py, bench.py's human leg) consumes the previously adopted buffer before it enters the
+    closing all-reduce (`consume=True`), so two buffers are enough there as well.
 
-    def __init__(self, nat, dist, rank, world, dev, capacity_keys, reserve=None):
+    reserve (ZB_P2P_RESERVE=1 or reserve=True): no count matrix at all -- every receive buffer ends in a cursor word,
+    and a thread block of the routing kernel reserves its run in the owner's buffer with one system-scope atomic add on
+    that word (over NVLink for a remote owner).  That drops the owner-count pass over the keys, the all-gather and two
+    host round trips from every step; after the closing all-reduce the owner reads its own cursor = keys received.  The
+    runs land in timing order, which the owner's sort makes irrelevant."""
+
+    def __init__(self, nat, dist, rank, world, dev, capacity_keys, reserve=None, nbuf=2):
         import os
+        import threading
         import torch
         self.nat, self.dist, self.rank, self.world, self.dev = nat, dist, rank, world, dev
         self.capacity = int(capacity_keys)
         self.reserve = (os.environ.get("ZB_P2P_RESERVE", "0") == "1") if reserve is None else bool(reserve)
-        self.step = 0
+        self.nbuf = max(2, int(nbuf))
+        self.step = 0                  # next sequence number to be exchanged
+        self._turn = threading.Condition()
         self.bufs = []
         self.route_ms = []
         self.remote_bytes = []
         self.cnt = torch.empty(world, dtype=torch.int64, device="cuda:%d" % dev)
         self.allc = torch.empty(world * world, dtype=torch.int64, device="cuda:%d" % dev)
-        for _ in range(2):
+        self.flag = torch.zeros(1, dtype=torch.int64, device="cuda:%d" % dev)
+        for _ in range(self.nbuf):
             ptr, handle = nat.ipc_alloc(self.capacity * 8 + 256, dev)     # the cursor word sits behind the keys
             _as_tensor(ptr + self.capacity * 8, 1, torch.int64, dev).zero_()
             handles = [None] * world
@@ -141,41 +152,80 @@ class P2PExchange(object):
         torch.cuda.synchronize(dev)
         dist.barrier()
 
-    def _exchange_reserve(self, km):
+    def _landed(self, failed):
+        """closing collective of a step: returns once every rank's stores (and reservations) have completed; raises on
+        EVERY rank when any rank overflowed a receive buffer (a rank that raised alone would leave the others waiting)"""
+        import torch
+        self.flag.fill_(1 if failed else 0)
+        self.dist.all_reduce(self.flag, op=self.dist.ReduceOp.MAX)
+        if int(self.flag.item()):
+            raise RuntimeError("P2PExchange: a receive buffer of %d keys overflowed on some rank" % self.capacity)
+
+    def _exchange_reserve(self, km, seq, consume):
         import time
         import torch
-        own, ptrs = self.bufs[self.step & 1]
+        own, ptrs = self.bufs[seq % self.nbuf]
         t0 = time.perf_counter()
-        sent = km.route_p2p_reserve(ptrs, [p + self.capacity * 8 for p in ptrs], self.capacity)
+        failed = False
+        sent = [0] * self.world
+        try:
+            sent = km.route_p2p_reserve(ptrs, [p + self.capacity * 8 for p in ptrs], self.capacity)
+        except IndexError:           # ZB_E_RANGE: a reservation passed the capacity (nothing was stored out of bounds)
+            failed = True
         self.route_ms.append((time.perf_counter() - t0) * 1e3)
         self.remote_bytes.append(8 * (sum(sent) - sent[self.rank]))
-        self.dist.barrier()          # every rank's stores and reservations have completed
+        if consume:
+            km.flush()               # the buffer adopted in the previous step is sorted before peers may move on
         cur = _as_tensor(own + self.capacity * 8, 1, torch.int64, self.dev)
+        self._landed(failed)         # every rank's stores and reservations have completed
         nrecv = int(cur.item())
-        cur.zero_()                  # for the step after the next one; peers touch it again only after the next barrier
+        cur.zero_()                  # peers touch this buffer's cursor again nbuf steps from now
         torch.cuda.current_stream(self.dev).synchronize()
+        if nrecv > self.capacity:    # cannot happen after a clean _landed; never read past the buffer
+            raise RuntimeError("P2PExchange: cursor %d beyond the capacity %d" % (nrecv, self.capacity))
         km.adopt_canonical_dev(own, nrecv)
-        self.step += 1
 
-    def exchange(self, km):
+    def _exchange_counts(self, km, seq, consume):
+        import time
         import torch
-        if self.reserve:
-            return self._exchange_reserve(km)
         counts = km.bucket_counts(self.world)
         self.cnt.copy_(torch.tensor(counts, dtype=torch.int64))
         self.dist.all_gather_into_tensor(self.allc, self.cnt)
         M = self.allc.view(self.world, self.world).cpu().numpy()
         offs, nrecv = p2p_offsets(M, self.rank)
-        if int(M.sum(axis=0).max()) > self.capacity:
+        if int(M.sum(axis=0).max()) > self.capacity:      # the same matrix on every rank: everybody raises
             raise RuntimeError("P2PExchange: a rank would receive %d keys, capacity is %d" % (int(M.sum(axis=0).max()), self.capacity))
-        own, ptrs = self.bufs[self.step & 1]
-        t0 = __import__("time").perf_counter()
+        own, ptrs = self.bufs[seq % self.nbuf]
+        t0 = time.perf_counter()
         km.route_p2p([ptrs[p] + 8 * offs[p] for p in range(self.world)])
-        self.route_ms.append((__import__("time").perf_counter() - t0) * 1e3)
+        self.route_ms.append((time.perf_counter() - t0) * 1e3)
         self.remote_bytes.append(8 * (sum(counts) - counts[self.rank]))
-        self.dist.barrier()          # every rank's stores have completed
-        km.adopt_canonical_dev(own, nrecv)    # sorted in place by km.finish(); the other buffer takes the next step
-        self.step += 1
+        if consume:
+            km.flush()
+        self._landed(False)          # every rank's stores have completed
+        km.adopt_canonical_dev(own, nrecv)    # sorted in place by km.finish() / the next flush
+
+    def exchange(self, km, seq=None, consume=True):
+        """route km's pending canonical k-mers to their owners and adopt what this rank received.  seq: the step's
+        number (None: the next one -- a single-threaded caller).  consume=False: the caller promises that a step's
+        buffer is sorted (km.finish()) before step seq + nbuf - 1 is exchanged -- one kmerizer per step, at most
+        nbuf - 1 steps in flight."""
+        import torch
+        with self._turn:
+            if seq is None:
+                seq = self.step
+            while self.step != seq:
+                self._turn.wait()
+        torch.cuda.set_device(self.dev)      # collectives below run on this host thread's current device
+        try:
+            if self.reserve:
+                self._exchange_reserve(km, seq, consume)
+            else:
+                self._exchange_counts(km, seq, consume)
+        finally:
+            with self._turn:
+                self.step = seq + 1
+                self._turn.notify_all()
 
     def close(self):
         for (own, ptrs) in self.bufs:
