@@ -9,7 +9,7 @@ from zotmer_b200 import docopt_mini as docopt
 from zotmer_b200 import _native
 from zotmer_b200.library.file import mapBytes
 from zotmer_b200.library.files import writeKmerSet
-from zotmer_b200.library.reads import isFasta, pieces
+from zotmer_b200.library.reads import isFasta, pieces, stagedPieces
 import zotmer_b200.library.kmers as zotk
 from zotmer_b200 import usage
 
@@ -23,13 +23,8 @@ def kmerizeFiles(K, inputs, device=0, verbose=False, baits=None):
     try:
         if baits is not None:
             km.set_baits(baits)
-        for fn in inputs:
-            data = mapBytes(fn)
-            fa = isFasta(fn)
-            if verbose:
-                print('reading %s (%d bytes, %s)' % (fn, len(data), 'FASTA' if fa else 'FASTQ'), file=sys.stderr)
-            for piece in pieces(data, fa):
-                km.feed(piece, fa)
+        for (staged, fa) in stagedPieces(inputs, device, verbose):
+            km.feed_staged(staged, fa)
         return km.finish()
     finally:
         km.close()
@@ -50,21 +45,38 @@ def baitSet(K, fn, device=0):
 
 
 def main(argv):
+    import os
+    import time
+    trace = [] if os.environ.get('ZB_CLI_TRACE') else None
+
+    def mark(what):
+        if trace is not None:
+            trace.append((what, time.perf_counter()))
+
+    mark('start')
     opts = docopt.docopt(__doc__, argv)
 
     verbose = opts['-v']
     K = int(opts['<k>'])
     out = opts['<output>']
 
-    (kset, nr) = kmerizeFiles(K, opts['<input>'], verbose=verbose)
-    st = kset.stats()      # acgt counts EVERY k-mer, before any sub-sampling / capture (kmerize.py:492-493)
+    inputs = opts['<input>']
+    if opts['-C'] is not None and opts['-D'] is None:
+        # capture reads the inputs twice (below); what cannot be read twice (stdin) or is costly to produce twice
+        # (decompressed text) is held in memory after the first read -- the reference reads its input once
+        from zotmer_b200.library.file import readBytes
+        inputs = [(fn, readBytes(fn)) if (fn == '-' or fn.endswith(('.gz', '.bz2'))) else fn for fn in inputs]
+    (kset, nr) = kmerizeFiles(K, inputs, verbose=verbose)
+    mark('read + kmerize + count')
+    st = kset.stats()
+    mark('stats')      # acgt counts EVERY k-mer, before any sub-sampling / capture (kmerize.py:492-493)
 
     if opts['-C'] is not None and opts['-D'] is None:
         # kmerize.py:507-517 (the -D branch comes first in the reference's if / elif chain): whole records are kept
         # when one of their k-mers is a bait.  acgt still covers every record (above), hence the second pass.
         baits = baitSet(K, opts['-C'])
         kset.free()
-        (kset, nr) = kmerizeFiles(K, opts['<input>'], verbose=verbose, baits=baits)
+        (kset, nr) = kmerizeFiles(K, inputs, verbose=verbose, baits=baits)
         baits.free()
         st['hist'] = kset.stats()['hist']
 
@@ -84,7 +96,9 @@ def main(argv):
         h = {}
         for (c, f) in st['hist']:       # first-occurrence order == the reference's dict order (:544-545)
             h[c] = f
+        mark('open output')
         writeKmerSet(z, kset)
+        mark('encode + write streams')
         acgt = st['acgt_weighted']
         n = float(sum(acgt))
         acgt = [c / n for c in acgt]    # ZeroDivisionError on input without k-mers, as :554-555
@@ -94,7 +108,11 @@ def main(argv):
         z.meta['hist'] = h
         z.meta['acgt'] = acgt
         z.meta['reads'] = nr
+    mark('meta + table + close')
     kset.free()
+    if trace is not None:
+        print('zot kmerize phases (ms): ' + ', '.join('%s %.1f' % (trace[i][0], (trace[i][1] - trace[i - 1][1]) * 1e3)
+                                                      for i in range(1, len(trace))), file=sys.stderr)
 
 
 if __name__ == '__main__':

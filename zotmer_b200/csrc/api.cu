@@ -123,93 +123,137 @@ cudaError_t dev_copy(Ctx* c, void* dst, const void* src, size_t bytes) {
     return cudaGetLastError();
 }
 
-// ZB_GUARD=1: every block carries GUARD pattern bytes in front and behind (zb_dbg_guard_check scans them).  The pool's
-// compute-sanitizer is closed, so this is how an out-of-bounds store next to a library buffer is caught in the tests.
+// ZB_GUARD=1: every block carries GUARD pattern bytes in front and behind (checked when the block is released and by
+// zb_dbg_guard_check).  The pool's compute-sanitizer is closed, so this is how an out-of-bounds store next to a library
+// buffer is caught in the tests.
 static const size_t GUARD = 256;
 static bool guard_on() {
     static const bool on = [] { const char* e = getenv("ZB_GUARD"); return e && atoi(e) != 0; }();
     return on;
 }
-static cudaError_t raw_alloc(Ctx* c, void** p, size_t want) {
-    if (!guard_on()) return cudaMalloc(p, want);
-    void* base = nullptr;
-    cudaError_t e = cudaMalloc(&base, want + 2 * GUARD);
-    if (e != cudaSuccess) return e;
-    dev_memset(c, base, 0xA5, GUARD);
-    dev_memset(c, (char*)base + GUARD + want, 0xA5, GUARD);
-    *p = (char*)base + GUARD;
-    return cudaSuccess;
-}
-static void raw_free(void* p) {
-    if (p) cudaFree(guard_on() ? (void*)((char*)p - GUARD) : p);
+
+__global__ void guard_check_kernel(const uint64_t* __restrict__ blocks /*[n][2] = user pointer, size*/, uint32_t n,
+                                   unsigned long long* __restrict__ n_bad) {
+    const uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= n) return;
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(blocks[2 * b]);
+    const uint64_t sz = blocks[2 * b + 1];
+    bool bad = false;
+    for (unsigned i = lane_id(); i < 256; i += 32) bad |= (p[(long long)i - 256] != 0xA5) | (p[sz + i] != 0xA5);
+    if (__any_sync(0xffffffffu, bad) && lane_id() == 0) atomicAdd(n_bad, 1ull);
 }
 
-static size_t round_block(size_t b) {
+// Device memory: a caching allocator per context.  cudaMalloc'ed SEGMENTS are cut into blocks; a request takes the
+// smallest free block that fits and splits off the rest; a released block merges with free neighbours.  Requests
+// below 1 MiB live in their own 2 MiB segments so that scalars never nibble at the gigabyte blocks.  All work of a
+// context is ordered on its one stream, so a block released by the host can be handed out again at once.
+// (History: cudaMallocAsync pools showed 100-600 ms re-mapping stalls between steps; the first in-house version kept
+// whole cudaMalloc blocks in size classes and, when a long kmerize had left 60 GB of them behind, a later small
+// request missed, evicted, and paid 100-170 ms of cudaFree -- inside whatever stage happened to allocate next,
+// bench.py's human leg: "stats 168 ms" for an 8 ms kernel.)
+static const size_t SMALL_LIMIT = (size_t)1 << 20;
+static const size_t SMALL_SEG = (size_t)2 << 20;
+static const size_t MIN_SPLIT = (size_t)1 << 20;     // a large block is split only when the rest is at least this
+
+static size_t round_req(size_t b) {
     if (b < 512) return 512;
-    if (b < ((size_t)1 << 20)) return (b + 511) & ~(size_t)511;
-    // large blocks: multiples of 1/8 of the enclosing power of two (<= 12.5 % slack), at least 2 MiB steps
-    size_t p2 = (size_t)1 << (63 - __builtin_clzll(b));
-    size_t step = std::max<size_t>(p2 >> 3, (size_t)2 << 20);
-    return (b + step - 1) / step * step;
+    return (b + 511) & ~(size_t)511;
+}
+
+static void idx_erase(Ctx* c, Ctx::Seg* sg, size_t off, size_t size) {
+    auto& idx = c->free_idx[sg->small ? 1 : 0];
+    auto rg = idx.equal_range(size);
+    for (auto it = rg.first; it != rg.second; ++it)
+        if (it->second.first == sg && it->second.second == off) { idx.erase(it); return; }
+}
+
+static void seg_release(Ctx* c, Ctx::Seg* sg) {   // a wholly free segment goes back to the driver
+    for (auto& kv : sg->blocks)
+        if (kv.second.free) idx_erase(c, sg, kv.first, kv.second.size);
+    c->cached_bytes -= sg->free_bytes;
+    c->segs.erase(sg->base);
+    cudaFree(sg->base);
+    delete sg;
+}
+
+static void release_free_segments(Ctx* c, size_t down_to) {
+    std::vector<std::pair<uint64_t, Ctx::Seg*>> byage;
+    for (auto& kv : c->segs)
+        if (kv.second->free_bytes == kv.second->size) byage.push_back({kv.second->last_use, kv.second});
+    std::sort(byage.begin(), byage.end());
+    for (auto& ap : byage) {
+        if (c->cached_bytes <= down_to) break;
+        seg_release(c, ap.second);
+    }
 }
 
 void* dalloc(Ctx* c, size_t bytes) {
     std::lock_guard<std::mutex> lk(c->alloc_mu);   // a set may be freed by another thread than the one that made it
-    const size_t want = round_block(bytes);
-    auto it = c->free_blocks.lower_bound(want);
-    if (it != c->free_blocks.end() && it->first <= want + want / 4) {
-        void* p = it->second;
-        const size_t sz = it->first;
-        c->free_blocks.erase(it);
-        c->freed_at.erase(p);
-        c->cached_bytes -= sz;
-        c->live_blocks[p] = sz;
-        c->live_bytes += sz;
-        return p;
-    }
-    // A miss.  A caller whose buffers grow from batch to batch (the running counted set of a long kmerize) leaves a
-    // trail of cached blocks that will never fit again: above the limit, the least recently released ones go back
-    // to the driver (human-scale run: 150 GB were cached, and the first allocation that failed spent 0.8 s freeing them).
-    if (c->cache_limit == 0) {
-        size_t fr = 0, tot = 0;
-        c->cache_limit = (cudaMemGetInfo(&fr, &tot) == cudaSuccess && tot) ? tot / 4 : ((size_t)32 << 30);
-    }
-    if (c->cached_bytes > c->cache_limit) {
-        std::vector<std::pair<uint64_t, void*>> byage;
-        for (auto& kv : c->freed_at) byage.push_back({kv.second, kv.first});
-        std::sort(byage.begin(), byage.end());
-        for (auto& ap : byage) {
-            if (c->cached_bytes <= c->cache_limit / 2) break;
-            for (auto fit = c->free_blocks.begin(); fit != c->free_blocks.end(); ++fit) {
-                if (fit->second == ap.second) {
-                    c->cached_bytes -= fit->first;
-                    raw_free(fit->second);
-                    c->free_blocks.erase(fit);
-                    break;
-                }
-            }
-            c->freed_at.erase(ap.second);
+    const size_t user = round_req(bytes);
+    const size_t want = user + (guard_on() ? 2 * GUARD : 0);
+    const bool small = want < SMALL_LIMIT;
+    auto& idx = c->free_idx[small ? 1 : 0];
+    Ctx::Seg* sg = nullptr;
+    size_t off = 0;
+    auto it = idx.lower_bound(want);
+    if (it != idx.end()) {
+        sg = it->second.first;
+        off = it->second.second;
+        idx.erase(it);
+    } else {
+        // a miss: a new segment.  Above the limit, wholly free segments (least recently used first) go back first.
+        if (c->cache_limit == 0) {
+            size_t fr = 0, tot = 0;
+            c->cache_limit = (cudaMemGetInfo(&fr, &tot) == cudaSuccess && tot) ? tot / 4 : ((size_t)32 << 30);
         }
+        if (c->cached_bytes > c->cache_limit) release_free_segments(c, c->cache_limit / 2);
+        const size_t seg_size = small ? SMALL_SEG : ((want + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1));
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, seg_size);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cudaStreamSynchronize(c->stream);
+            release_free_segments(c, 0);
+            e = cudaMalloc(&p, seg_size);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("out of device memory: %zu bytes requested, %zu live, %zu cached in partly used segments", want, c->live_bytes,
+                      c->cached_bytes);
+            throw Fail{ZB_E_NOMEM};
+        }
+        sg = new Ctx::Seg();
+        sg->base = (char*)p;
+        sg->size = seg_size;
+        sg->small = small;
+        sg->blocks[0] = Ctx::Blk{seg_size, true};
+        sg->free_bytes = seg_size;
+        c->segs[sg->base] = sg;
+        c->cached_bytes += seg_size;
+        off = 0;
     }
-    void* p = nullptr;
-    cudaError_t e = raw_alloc(c, &p, want);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        cudaStreamSynchronize(c->stream);
-        for (auto& kv : c->free_blocks) raw_free(kv.second);
-        c->free_blocks.clear();
-        c->freed_at.clear();
-        c->cached_bytes = 0;
-        e = raw_alloc(c, &p, want);
+    Ctx::Blk& blk = sg->blocks[off];
+    const size_t rest = blk.size - want;
+    if (rest >= (small ? (size_t)512 : MIN_SPLIT)) {
+        blk.size = want;
+        sg->blocks[off + want] = Ctx::Blk{rest, true};
+        idx.insert({rest, {sg, off + want}});
     }
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        set_error("out of device memory: %zu bytes requested, %zu live", want, c->live_bytes);
-        throw Fail{ZB_E_NOMEM};
+    Ctx::Blk& mine = sg->blocks[off];
+    mine.free = false;
+    sg->free_bytes -= mine.size;
+    sg->last_use = ++c->tick;
+    c->cached_bytes -= mine.size;
+    c->live_bytes += mine.size;
+    char* up = sg->base + off;
+    const size_t asked = (bytes + 15) & ~(size_t)15;
+    if (guard_on()) {
+        dev_memset(c, up, 0xA5, GUARD);
+        dev_memset(c, up + GUARD + asked, 0xA5, mine.size - GUARD - asked);   // everything behind the request is band
+        up += GUARD;
     }
-    c->live_blocks[p] = want;
-    c->live_bytes += want;
-    return p;
+    c->live_blocks[up] = Ctx::Live{sg, off, asked};
+    return up;
 }
 
 void dfree(Ctx* c, void* p) {
@@ -217,20 +261,55 @@ void dfree(Ctx* c, void* p) {
     std::lock_guard<std::mutex> lk(c->alloc_mu);
     auto it = c->live_blocks.find(p);
     if (it == c->live_blocks.end()) return;
-    const size_t sz = it->second;
+    Ctx::Seg* sg = it->second.seg;
+    size_t off = it->second.off;
+    const uint64_t span[2] = {(uint64_t)(uintptr_t)p, (uint64_t)it->second.user};
     c->live_blocks.erase(it);
-    c->live_bytes -= sz;
-    c->free_blocks.insert({sz, p});
-    c->freed_at[p] = ++c->tick;
-    c->cached_bytes += sz;
+    if (guard_on()) {
+        // the bands are looked at before the block can be handed out again (stream order); damage is tallied in the context
+        uint64_t* d = nullptr;
+        if (cudaMalloc((void**)&d, 24) == cudaSuccess) {
+            cudaMemsetAsync(d, 0, 8, c->stream);
+            cudaMemcpyAsync(d + 1, span, 16, cudaMemcpyHostToDevice, c->stream);
+            guard_check_kernel<<<1, 32, 0, c->stream>>>(d + 1, 1u, reinterpret_cast<unsigned long long*>(d));
+            uint64_t bad = 0;
+            cudaMemcpyAsync(&bad, d, 8, cudaMemcpyDeviceToHost, c->stream);
+            cudaStreamSynchronize(c->stream);
+            cudaFree(d);
+            c->guard_bad += bad;
+        }
+    }
+    auto bi = sg->blocks.find(off);
+    size_t size = bi->second.size;
+    c->live_bytes -= size;
+    c->cached_bytes += size;
+    sg->free_bytes += size;
+    sg->last_use = ++c->tick;
+    // merge with the free neighbours
+    auto nx = std::next(bi);
+    if (nx != sg->blocks.end() && nx->second.free) {
+        idx_erase(c, sg, nx->first, nx->second.size);
+        size += nx->second.size;
+        sg->blocks.erase(nx);
+    }
+    if (bi != sg->blocks.begin()) {
+        auto pv = std::prev(bi);
+        if (pv->second.free) {
+            idx_erase(c, sg, pv->first, pv->second.size);
+            size += pv->second.size;
+            off = pv->first;
+            sg->blocks.erase(bi);
+            bi = pv;
+        }
+    }
+    bi->second.size = size;
+    bi->second.free = true;
+    c->free_idx[sg->small ? 1 : 0].insert({size, {sg, off}});
 }
 
 void dtrim(Ctx* c) {
     std::lock_guard<std::mutex> lk(c->alloc_mu);
-    for (auto& kv : c->free_blocks) raw_free(kv.second);
-    c->free_blocks.clear();
-    c->freed_at.clear();
-    c->cached_bytes = 0;
+    release_free_segments(c, 0);
 }
 
 }  // namespace zb
@@ -1277,17 +1356,6 @@ int zb_dbg_extract(int device, int k, const uint8_t* codes, size_t n, uint64_t* 
     ZB_CATCH
 }
 
-__global__ void guard_check_kernel(const uint64_t* __restrict__ blocks /*[n][2] = user pointer, size*/, uint32_t n,
-                                   unsigned long long* __restrict__ n_bad) {
-    const uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (b >= n) return;
-    const uint8_t* p = reinterpret_cast<const uint8_t*>(blocks[2 * b]);
-    const uint64_t sz = blocks[2 * b + 1];
-    bool bad = false;
-    for (unsigned i = lane_id(); i < 256; i += 32) bad |= (p[(long long)i - 256] != 0xA5) | (p[sz + i] != 0xA5);
-    if (__any_sync(0xffffffffu, bad) && lane_id() == 0) atomicAdd(n_bad, 1ull);
-}
-
 int zb_dbg_guard_check(int device, uint64_t* n_blocks, uint64_t* n_bad) {
     ZB_TRY
     Ctx* c = ctx_for(device);
@@ -1295,25 +1363,31 @@ int zb_dbg_guard_check(int device, uint64_t* n_blocks, uint64_t* n_bad) {
     if (n_bad) *n_bad = 0;
     if (!guard_on()) ZB_FAIL(ZB_E_ARG, "guard bands are off: set ZB_GUARD=1 before the library is first used");
     std::vector<uint64_t> blocks;
+    uint64_t released_bad = 0, ever = 0;
     {
         std::lock_guard<std::mutex> lk(c->alloc_mu);
-        for (auto& kv : c->live_blocks) { blocks.push_back((uint64_t)(uintptr_t)kv.first); blocks.push_back(kv.second); }
-        for (auto& kv : c->free_blocks) { blocks.push_back((uint64_t)(uintptr_t)kv.second); blocks.push_back(kv.first); }
+        for (auto& kv : c->live_blocks) {
+            blocks.push_back((uint64_t)(uintptr_t)kv.first);
+            blocks.push_back((uint64_t)kv.second.user);
+        }
+        released_bad = c->guard_bad;
+        ever = c->tick;
     }
     const size_t n = blocks.size() / 2;
-    if (n_blocks) *n_blocks = n;
-    if (n == 0) return ZB_OK;
-    uint64_t* d = nullptr;   // outside the guarded allocator: the list must not change while it is scanned
-    ZB_CUDA(cudaMalloc((void**)&d, (blocks.size() + 1) * 8));
-    ZB_CUDA(cudaMemcpyAsync(d + 1, blocks.data(), blocks.size() * 8, cudaMemcpyHostToDevice, c->stream));
-    ZB_CUDA(cudaMemsetAsync(d, 0, 8, c->stream));
-    guard_check_kernel<<<(unsigned)div_up(n, 8), 256, 0, c->stream>>>(d + 1, (uint32_t)n, reinterpret_cast<unsigned long long*>(d));
-    c->launches++;
+    if (n_blocks) *n_blocks = ever;      // allocations + releases seen so far: every release was checked
     uint64_t bad = 0;
-    ZB_CUDA(cudaMemcpyAsync(&bad, d, 8, cudaMemcpyDeviceToHost, c->stream));
-    ZB_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(d);
-    if (n_bad) *n_bad = bad;
+    if (n) {
+        uint64_t* d = nullptr;   // outside the guarded allocator: the list must not change while it is scanned
+        ZB_CUDA(cudaMalloc((void**)&d, (blocks.size() + 1) * 8));
+        ZB_CUDA(cudaMemcpyAsync(d + 1, blocks.data(), blocks.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        ZB_CUDA(cudaMemsetAsync(d, 0, 8, c->stream));
+        guard_check_kernel<<<(unsigned)div_up(n, 8), 256, 0, c->stream>>>(d + 1, (uint32_t)n, reinterpret_cast<unsigned long long*>(d));
+        c->launches++;
+        ZB_CUDA(cudaMemcpyAsync(&bad, d, 8, cudaMemcpyDeviceToHost, c->stream));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(d);
+    }
+    if (n_bad) *n_bad = bad + released_bad;
     ZB_CATCH
 }
 

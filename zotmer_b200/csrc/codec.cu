@@ -9,11 +9,15 @@
 // Encode.  Whether position i starts a word depends on every earlier decision, but only through "how many
 // positions until the next word starts" (0..5): a 6-state machine.  J[i] = the group length the greedy rule
 // gives a word that starts at i depends on v[i..i+5] only (the fit test is monotone in g).
-//   enc_tile_kernel   per 2048-value tile: J[] in shared memory, then six threads walk the tile, one per entry
-//                     state -> (exit state, number of words) for each entry state
+//   enc_tile_kernel   per 2048-value tile: J[] in shared memory; every thread walks its eight positions for each of
+//                     the six entry states (registers only), a block scan composes the threads' maps -> (exit
+//                     state, number of words) of the tile for each entry state
 //   enc_scan_kernel   composes the per-tile maps in order -> entry state and first word index of every tile
-//   enc_emit_kernel   re-derives J[], one thread walks from the tile's real entry state and marks the word
-//                     starts; every start then packs its word
+//   enc_emit_kernel   the same thread maps and scan, now applied to the tile's real entry state: every thread knows
+//                     the state in which the walk reaches it, walks its eight positions and packs the words that
+//                     start there
+// (The first version walked a tile with one thread per entry state: 2048 dependent shared-memory loads each, 3.2 ms
+// for the four streams of one bench step -- the largest stage of the step once both bench arms did the same work.)
 // Decode.  dec_tile_kernel: values and value sum per 512-word tile; dec_scan_kernel: exclusive scan of both;
 // dec_emit_kernel: unpack, add the running sum (undelta), stage in shared memory, write coalesced.
 //
@@ -80,23 +84,95 @@ __device__ __forceinline__ void enc_prepare(const T* __restrict__ vals, uint64_t
     __syncthreads();
 }
 
+// ---- the walk inside a tile, in parallel.  Thread t owns positions [8t, 8t + 8) of the tile (cut at the tile's last
+// value `lim`).  Its map: "the next word starts r positions into my region" (r = 0..5) -> (how many positions past my
+// region's end the next word after it starts, how many words start inside it): six walks of at most eight register
+// steps.  Maps compose associatively -- (a then b)[r] = b[a[r]] -- so an inclusive scan over the threads gives every
+// thread the state in which the walk reaches it for each of the six states in which it may enter the tile.
+// A map is packed as 6 x 3 bits.
+__device__ __forceinline__ uint32_t map_then(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int q = 0; q < 6; q++) r |= ((b >> (3 * ((a >> (3 * q)) & 7u))) & 7u) << (3 * q);
+    return r;
+}
+static constexpr uint32_t MAP_ID = 0 | (1 << 3) | (2 << 6) | (3 << 9) | (4 << 12) | (5 << 15);
+
+struct ThreadWalk {
+    uint32_t map;      // exit state per entry state, 6 x 3 bits
+    uint32_t cnt;      // words started per entry state, 6 x 4 bits
+};
+
+// j8: the group lengths J of the thread's eight positions (one byte each), m = positions of the region that hold data
+__device__ __forceinline__ ThreadWalk thread_walk(uint64_t j8, int m) {
+    ThreadWalk w;
+    w.map = 0;
+    w.cnt = 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        int p = r, c = 0;
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            if (p < m) { p += (int)((j8 >> (8 * p)) & 0xffu); c++; }
+        }
+        w.map |= (uint32_t)(p - m) << (3 * r);
+        w.cnt |= (uint32_t)c << (4 * r);
+    }
+    return w;
+}
+
+// exclusive prefix of the threads' maps over the block (identity for thread 0); *total = the whole tile's map
+__device__ __forceinline__ uint32_t block_map_excl_scan(uint32_t mine, uint32_t* s_warp /*[EN_THREADS / 32]*/, uint32_t* total) {
+    const unsigned l = lane_id(), wid = threadIdx.x >> 5;
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, inc, o);
+        if (l >= (unsigned)o) inc = map_then(prev, inc);
+    }
+    if (l == 31) s_warp[wid] = inc;
+    __syncthreads();
+    uint32_t before = MAP_ID;      // maps of the warps in front of mine
+    uint32_t all = MAP_ID;
+#pragma unroll
+    for (int q = 0; q < EN_THREADS / 32; q++) {
+        const uint32_t wm = s_warp[q];
+        if (q < (int)wid) before = map_then(before, wm);
+        all = map_then(all, wm);
+    }
+    uint32_t excl = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (l == 0) excl = MAP_ID;
+    *total = all;
+    return map_then(before, excl);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(EN_THREADS)
 enc_tile_kernel(const T* __restrict__ vals, uint64_t n, int delta, const EncRange rg, uint32_t* __restrict__ tile_info /*[tiles][6]*/,
                 unsigned int* __restrict__ err) {
     __shared__ uint8_t sbl[EN_TILE + 8];
-    __shared__ uint8_t sJ[EN_TILE];
+    __shared__ __align__(8) uint8_t sJ[EN_TILE];
+    __shared__ uint32_t s_warp[EN_THREADS / 32];
+    __shared__ uint32_t s_cnt[6];
+    const unsigned tid = threadIdx.x;
     const uint64_t base = (uint64_t)blockIdx.x * EN_TILE;
     enc_prepare<T>(vals, n, delta != 0, base, rg, sbl, sJ, nullptr, err);
-    if (threadIdx.x < 6) {
-        const int lim = (int)min((uint64_t)EN_TILE, n - base);
-        int p = threadIdx.x, cnt = 0;   // entry state r: the next word starts r positions into the tile
-        while (p < lim) {
-            p += sJ[p];
-            cnt++;
-        }
-        tile_info[(size_t)blockIdx.x * 6 + threadIdx.x] = (uint32_t)(p - lim) | ((uint32_t)cnt << 8);
+    if (tid < 6) s_cnt[tid] = 0;
+    const int lim = (int)min((uint64_t)EN_TILE, n - base);
+    const int m = max(0, min(EN_PER, lim - (int)tid * EN_PER));
+    const ThreadWalk w = thread_walk(*reinterpret_cast<const uint64_t*>(sJ + tid * EN_PER), m);
+    uint32_t tile_map;
+    const uint32_t excl = block_map_excl_scan(w.map, s_warp, &tile_map);
+    // words of the tile for each of the six entry states: my count in the state in which the walk reaches me
+    uint32_t c6[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) c6[r] = warp_sum((w.cnt >> (4 * ((excl >> (3 * r)) & 7u))) & 15u);
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int r = 0; r < 6; r++) atomicAdd(&s_cnt[r], c6[r]);
     }
+    __syncthreads();
+    if (tid < 6) tile_info[(size_t)blockIdx.x * 6 + tid] = ((tile_map >> (3 * tid)) & 7u) | (s_cnt[tid] << 8);
 }
 
 // entry state and first word index of every tile.  One CTA: every thread composes a contiguous chunk of tiles
@@ -161,38 +237,37 @@ __global__ void __launch_bounds__(EN_THREADS)
 enc_emit_kernel(const T* __restrict__ vals, uint64_t n, int delta, const EncRange rg, const uint8_t* __restrict__ entry,
                 const uint64_t* __restrict__ woff, uint64_t* __restrict__ words, unsigned int* __restrict__ err) {
     __shared__ uint8_t sbl[EN_TILE + 8];
-    __shared__ uint8_t sJ[EN_TILE];
+    __shared__ __align__(8) uint8_t sJ[EN_TILE];
     __shared__ uint64_t sv[EN_TILE + 8];
-    __shared__ uint32_t sstart[EN_TILE / 32];
+    __shared__ uint32_t s_warp[EN_THREADS / 32];
     __shared__ uint32_t s_scan[EN_THREADS / 32 + 1];
     const unsigned tid = threadIdx.x;
     const uint64_t base = (uint64_t)blockIdx.x * EN_TILE;
-    if (tid < EN_TILE / 32) sstart[tid] = 0;
     enc_prepare<T>(vals, n, delta != 0, base, rg, sbl, sJ, sv, err);
     const int lim = (int)min((uint64_t)EN_TILE, n - base);
-    if (tid == 0) {
-        int p = entry[blockIdx.x];
-        while (p < lim) {
-            sstart[p >> 5] |= 1u << (p & 31);
-            p += sJ[p];
-        }
-    }
-    __syncthreads();
-    // thread t owns positions 8t .. 8t+7 = byte t of the start mask
-    const uint32_t mine = (sstart[tid >> 2] >> ((tid & 3) * 8)) & 0xffu;
+    const int m = max(0, min(EN_PER, lim - (int)tid * EN_PER));
+    const uint64_t j8 = *reinterpret_cast<const uint64_t*>(sJ + tid * EN_PER);
+    const ThreadWalk w = thread_walk(j8, m);
+    uint32_t tile_map;
+    const uint32_t excl = block_map_excl_scan(w.map, s_warp, &tile_map);
+    // the state in which the walk from the tile's true entry state reaches this thread; its word starts
+    const int st = (int)((excl >> (3 * (uint32_t)entry[blockIdx.x])) & 7u);
     uint32_t tot;
-    uint32_t rank = block_excl_scan<EN_THREADS, uint32_t, false>(__popc(mine), s_scan, &tot);
-    uint32_t m = mine;
-    while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        const int p = tid * EN_PER + b;
-        const int g = sJ[p];
-        const int wd = cw_width(g);
-        uint64_t word = 0;
-        for (int q = g - 1; q >= 0; q--) word = (word << wd) | sv[p + q];
-        words[woff[blockIdx.x] + rank] = (word << 4) | (uint64_t)g;
-        rank++;
+    uint32_t rank = block_excl_scan<EN_THREADS, uint32_t, false>((w.cnt >> (4 * st)) & 15u, s_scan, &tot);
+    const uint64_t wbase = woff[blockIdx.x];
+    int p = st;
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        if (p < m) {
+            const int g = (int)((j8 >> (8 * p)) & 0xffu);
+            const int wd = cw_width(g);
+            const int q0 = (int)tid * EN_PER + p;
+            uint64_t word = 0;
+            for (int q = g - 1; q >= 0; q--) word = (word << wd) | sv[q0 + q];
+            words[wbase + rank] = (word << 4) | (uint64_t)g;
+            rank++;
+            p += g;
+        }
     }
 }
 
@@ -502,16 +577,19 @@ int zb_set_encode_dev(const zb_set* s, zb_words** out) {
         EngineLock el(c, ENG_SM);
         Stage st(c, "encode");
         if (s->n) {
-            // worst case one value per word; the streams are trimmed to their real size afterwards only when that
-            // saves a lot (k-mer gaps of a 10 M set are ~27 bits: two per word; counts: six per word)
-            DBuf<uint64_t> tmp(c, s->n);
-            w->nk = encode_dev<uint64_t>(c, s->k.get(), s->n, true, tmp.get());
-            w->kw.alloc(c, w->nk);
-            ZB_CUDA(dev_copy(c, w->kw.get(), tmp.get(), w->nk * 8));
-            w->nc = encode_dev<uint32_t>(c, s->cnt.get(), s->n, false, tmp.get());
-            w->cw.alloc(c, w->nc);
-            ZB_CUDA(dev_copy(c, w->cw.get(), tmp.get(), w->nc * 8));
-            ZB_CUDA(cudaStreamSynchronize(c->stream));
+            // plan first (tile maps + scan): it knows the number of words, so the streams are allocated at their real size
+            // (k-mer gaps of a 10 M set are ~27 bits: two per word; counts: six per word)
+            EncRange rg;
+            memset(&rg, 0, sizeof rg);
+            EncodePlan pk, pc;
+            encode_plan<uint64_t>(c, s->k.get(), s->n, true, rg, &pk);
+            encode_plan<uint32_t>(c, s->cnt.get(), s->n, false, rg, &pc);
+            encode_plan_map(c, &pk);
+            encode_plan_map(c, &pc);
+            w->kw.alloc(c, pk.map_words[0] + 1);
+            w->cw.alloc(c, pc.map_words[0] + 1);
+            w->nk = encode_emit<uint64_t>(c, s->k.get(), &pk, 0, w->kw.get());
+            w->nc = encode_emit<uint32_t>(c, s->cnt.get(), &pc, 0, w->cw.get());
         }
     } catch (...) {
         delete w;

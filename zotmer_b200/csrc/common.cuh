@@ -50,13 +50,26 @@ struct Ctx {
     uint8_t* d_h_big = nullptr;
     uint64_t launches = 0;          // kernels launched through this context (bench "gpu_launches")
     // optional per-stage CUDA-event timing (zb_dbg_profile): name, start, stop
-    // caching allocator state
-    std::multimap<size_t, void*> free_blocks;
-    std::unordered_map<void*, size_t> live_blocks;
-    size_t cached_bytes = 0, live_bytes = 0;
-    std::unordered_map<void*, uint64_t> freed_at;   // cached block -> tick of its release (least recently used go first)
+    // caching allocator state (api.cu): segments from cudaMalloc, cut into blocks that are split on demand and merged
+    // with their free neighbours on release
+    struct Seg;
+    struct Blk { size_t size; bool free; };
+    struct Seg {
+        char* base = nullptr;
+        size_t size = 0;
+        bool small = false;                        // segment of the small-block pool
+        std::map<size_t, Blk> blocks;              // offset -> block, covering the segment without gaps
+        size_t free_bytes = 0;
+        uint64_t last_use = 0;
+    };
+    std::map<char*, Seg*> segs;                                        // by base address
+    std::multimap<size_t, std::pair<Seg*, size_t>> free_idx[2];         // [large, small]: size -> (segment, offset)
+    struct Live { Seg* seg; size_t off; size_t user; };                  // user = requested bytes (rounded up to 16)
+    std::unordered_map<void*, Live> live_blocks;                        // user pointer -> its block
+    size_t cached_bytes = 0, live_bytes = 0;      // free / handed-out bytes inside the segments
     uint64_t tick = 0;
-    size_t cache_limit = 0;                        // cached bytes above which a miss evicts old blocks (a quarter of the device)
+    size_t cache_limit = 0;                        // free bytes above which a miss gives wholly free segments back (a quarter of the device)
+    uint64_t guard_bad = 0;                        // blocks released with a damaged guard band (ZB_GUARD=1)
     std::mutex alloc_mu;
     cudaEvent_t copy_ev[3] = {nullptr, nullptr, nullptr};   // bulk host <-> device copies: at most three pieces queued
     bool profile = false;

@@ -58,11 +58,19 @@ def readKmerSet(z, nm=None, counts=True, device=0):
 def writeKmerSet(z, kset, nm=None):
     """files.py:195-217 (writeKmersAndCounts / writeKmersAndCounts2) from a device-resident set."""
     xNm, cNm = _names(nm)
-    kw, cw = kset.encode()
-    with z.add_stream(xNm) as f:
-        writeWords(f, kw)
-    with z.add_stream(cNm) as f:
-        writeWords(f, cw)
+    # codec64 + delta on the device; the packed words then go device -> pinned ring -> pwrite() on the library's I/O
+    # threads, both streams at once, straight to their places in the container (no host copy of the streams in Python)
+    w = kset.encode_dev()
+    try:
+        nk, nc = w.sizes()
+        z._writable()
+        z.fo.flush()
+        at = z._end()
+        w.write_fd(z.fo.fileno(), at, at + 8 * nk)
+        z._record(xNm, at, 8 * nk)
+        z._record(cNm, at + 8 * nk, 8 * nc)
+    finally:
+        w.free()
 
 
 def writeKmersAndCounts2(z, xs, cs, nm=None, device=0):

@@ -40,12 +40,9 @@ def pieces(data, is_fasta, max_piece=MAX_PIECE):
             cut += 1
         else:
             # newline number q (1-based, counted from `start`) ends a record when q % 4 == 0: count the newlines of the
-            # window (64 MiB at a time -- no index array of a gigabyte of text), then step back over the q % 4 newlines
-            # of the incomplete last record
-            import numpy as np
-            total = 0
-            for o in range(start, end, 1 << 26):
-                total += int(np.count_nonzero(np.frombuffer(mv[o:min(o + (1 << 26), end)], dtype=np.uint8) == 10))
+            # window, then step back over the q % 4 newlines of the incomplete last record
+            from zotmer_b200 import _native
+            total = _native.host_count_byte(mv[start:end], 10)      # on the library's I/O threads
             if total < 4:
                 raise ValueError("FASTQ record larger than %d bytes cannot be fed in pieces" % max_piece)
             at = end
@@ -56,3 +53,52 @@ def pieces(data, is_fasta, max_piece=MAX_PIECE):
         start = cut
     if start < n:
         yield mv[start:]
+
+
+def stagedPieces(inputs, device=0, verbose=False, max_piece=MAX_PIECE):
+    """(staged piece, is_fasta) for every record-aligned piece of every input file, in order; the copy of the NEXT piece
+    to the device has already been started (library I/O threads, pinned ring) when a piece is handed out, so reading /
+    copying piece i + 1 overlaps the parsing and extraction of piece i.  A plain file that fits one piece is read by the
+    I/O threads themselves (pread into pinned chunks: no mapping, no Python bytes object); anything else (stdin, .gz /
+    .bz2, files beyond one piece) is staged from host memory."""
+    import os
+    import sys
+    from zotmer_b200 import _native
+    from zotmer_b200.library.file import mapBytes
+
+    def jobs():
+        for fn in inputs:
+            held = None
+            if isinstance(fn, tuple):      # (name, content already in memory): an input that can only be read once
+                fn, held = fn
+            fa = isFasta(fn)
+            plain = held is None and fn != '-' and not fn.endswith(('.gz', '.bz2')) and os.path.isfile(fn)
+            size = os.path.getsize(fn) if plain else -1
+            if verbose:
+                print('reading %s (%s)' % (fn, 'FASTA' if fa else 'FASTQ'), file=sys.stderr)
+            if plain and 0 < size <= max_piece:
+                yield ('fd', fn, size, fa)
+            else:
+                data = held if held is not None else mapBytes(fn)
+                for piece in pieces(data, fa, max_piece):
+                    if len(piece):
+                        yield ('mem', piece, len(piece), fa)
+
+    def start(job):
+        kind, src, n, fa = job
+        if kind == 'fd':
+            f = open(src, 'rb')
+            st = _native.stage_fd(f.fileno(), 0, n, device)
+            st.keep = f            # the descriptor stays open until the piece has been fed
+            return st, fa
+        return _native.stage_input(src, device), fa
+
+    it = jobs()
+    cur = None
+    for job in it:
+        nxt = start(job)
+        if cur is not None:
+            yield cur
+        cur = nxt
+    if cur is not None:
+        yield cur
