@@ -50,6 +50,12 @@ int zb_device_count(int* n);
 /* number of kernels this library has launched on `device` from the calling thread (bench "gpu_launches") */
 int zb_launch_count(int device, uint64_t* n);
 int zb_device_sync(int device);
+/* a few bytes (<= 64 KiB, multiple of 4) between host memory and device memory, moved by a kernel through mapped pinned
+ * memory instead of a copy engine: an engine serves the transfers of all host threads in the order they were queued, so
+ * a 16-byte copy can wait milliseconds behind another thread's 315 MB input (the multi-GPU exchange's count matrix and
+ * flags go this way).  Both return after the transfer has completed. */
+int zb_dev_read_small(int device, const void* d_src, size_t bytes, void* host_dst);
+int zb_dev_write_small(int device, void* d_dst, const void* host_src, size_t bytes);
 /* give the device memory cached by the library (freed sets, scratch) back to the driver */
 int zb_release_cache(int device);
 
@@ -98,6 +104,10 @@ int zb_kmerize_route_p2p(zb_kmerizer* h, int nranks, uint64_t* const* d_dst);
  * whom.  ZB_E_RANGE when a reservation passed capacity_keys (nothing was stored out of bounds). */
 int zb_kmerize_route_p2p_reserve(zb_kmerizer* h, int nranks, uint64_t* const* d_dst, uint64_t* const* d_cursor,
                                  uint64_t capacity_keys, uint64_t* sent_counts);
+/* one process driving several GPUs (the `zot` commands with ZB_GPUS=N): kernels on `device` may then load from and
+ * store to memory of `peer` (NVLink peer mapping, cudaDeviceEnablePeerAccess); buffers from zb_ipc_alloc and the arrays
+ * of sets on `peer` become valid arguments of the *_dev entry points on `device` */
+int zb_peer_enable(int device, int peer);
 /* device buffers that other processes on the node can map (cudaIpc*): alloc/free on the owner, open/close on peers */
 int zb_ipc_alloc(int device, size_t bytes, void** d_ptr, uint8_t handle[64]);
 int zb_ipc_open(int device, const uint8_t handle[64], void** d_ptr);

@@ -29,6 +29,8 @@ SIGNATURES = {
     "zb_launch_count": (C.c_int, [C.c_int, u64p]),
     "zb_device_sync": (C.c_int, [C.c_int]),
     "zb_release_cache": (C.c_int, [C.c_int]),
+    "zb_dev_read_small": (C.c_int, [C.c_int, vp, C.c_size_t, vp]),
+    "zb_dev_write_small": (C.c_int, [C.c_int, vp, vp, C.c_size_t]),
     "zb_kmerize_open": (C.c_int, [C.c_int, C.c_int, C.POINTER(vp)]),
     "zb_kmerize_feed": (C.c_int, [vp, vp, C.c_size_t, C.c_int]),
     "zb_kmerize_feed_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_int]),
@@ -41,6 +43,7 @@ SIGNATURES = {
     "zb_kmerize_bucket_counts": (C.c_int, [vp, C.c_int, u64p]),
     "zb_kmerize_route_p2p": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
     "zb_kmerize_route_p2p_reserve": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.c_uint64, C.POINTER(C.c_uint64)]),
+    "zb_peer_enable": (C.c_int, [C.c_int, C.c_int]),
     "zb_ipc_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]),
     "zb_ipc_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(vp)]),
     "zb_ipc_close": (C.c_int, [C.c_int, vp]),
@@ -143,6 +146,18 @@ def launch_count(device=0):
     n = C.c_uint64(0)
     _check(lib().zb_launch_count(device, C.byref(n)))
     return n.value
+
+
+def dev_read_small(dptr, n, dtype=np.int64, device=0):
+    """n elements of device memory -> numpy array, by a kernel through mapped pinned memory (no copy engine)"""
+    out = np.empty(n, dtype)
+    _check(lib().zb_dev_read_small(device, vp(int(dptr)), out.nbytes, _ptr(out)))
+    return out
+
+
+def dev_write_small(dptr, arr, device=0):
+    a = np.ascontiguousarray(arr)
+    _check(lib().zb_dev_write_small(device, vp(int(dptr)), _ptr(a), a.nbytes))
 
 
 def release_cache(device=0):
@@ -463,6 +478,11 @@ def pairs_abc(sets, I, J):
     out = np.zeros((len(I), 3), np.uint64)
     _check(lib().zb_pairs_abc(len(sets), arr, _ptr(I), _ptr(J), len(I), _ptr(out.reshape(-1)) if len(I) else None))
     return out
+
+
+def peer_enable(device, peer):
+    """kernels on `device` may access memory of `peer` afterwards (one process, several GPUs)"""
+    _check(lib().zb_peer_enable(device, peer))
 
 
 def ipc_alloc(nbytes, device=0):

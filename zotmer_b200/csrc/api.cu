@@ -543,6 +543,30 @@ int zb_release_cache(int device) {
     ZB_CATCH
 }
 
+int zb_dev_read_small(int device, const void* d_src, size_t bytes, void* host_dst) {
+    ZB_TRY
+    if (bytes == 0) return ZB_OK;
+    if (!d_src || !host_dst || bytes > H_BIG || (bytes & 3) || ((uintptr_t)d_src & 3)) ZB_FAIL(ZB_E_ARG, "bad argument");
+    Ctx* c = ctx_for(device);
+    copy_kernel<uint32_t><<<(unsigned)div_up(bytes / 4, 256), 256, 0, c->stream>>>((uint32_t*)c->d_h_big, (const uint32_t*)d_src, bytes / 4);
+    ZB_LAUNCH_CHECK(c);
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(host_dst, c->h_big, bytes);
+    ZB_CATCH
+}
+
+int zb_dev_write_small(int device, void* d_dst, const void* host_src, size_t bytes) {
+    ZB_TRY
+    if (bytes == 0) return ZB_OK;
+    if (!d_dst || !host_src || bytes > H_BIG || (bytes & 3) || ((uintptr_t)d_dst & 3)) ZB_FAIL(ZB_E_ARG, "bad argument");
+    Ctx* c = ctx_for(device);
+    memcpy(c->h_big, host_src, bytes);
+    copy_kernel<uint32_t><<<(unsigned)div_up(bytes / 4, 256), 256, 0, c->stream>>>((uint32_t*)d_dst, (const uint32_t*)c->d_h_big, bytes / 4);
+    ZB_LAUNCH_CHECK(c);
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    ZB_CATCH
+}
+
 int zb_device_sync(int device) {
     ZB_TRY
     ctx_for(device);
@@ -735,10 +759,9 @@ int zb_kmerize_bucket_counts(zb_kmerizer* h, int nranks, uint64_t* bucket_counts
     DBuf<unsigned long long> cnt(c, 64);
     ZB_CUDA(dev_memset(c, cnt.get(), 0, 64 * 8));
     bucket_count(c, h->pending.get(), n, nranks, cnt.get());
-    std::vector<unsigned long long> hc(64, 0);
-    ZB_CUDA(cudaMemcpyAsync(hc.data(), cnt.get(), 64 * 8, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(read_back_big(c, cnt.get(), 64 * 8));      // by a kernel: the copy engines may be busy with other threads' bulk copies
     ZB_CUDA(cudaStreamSynchronize(c->stream));
-    for (int r = 0; r < nranks; r++) bucket_counts[r] = hc[r];
+    for (int r = 0; r < nranks; r++) bucket_counts[r] = reinterpret_cast<const uint64_t*>(c->h_big)[r];
     ZB_CATCH
 }
 
@@ -774,20 +797,36 @@ int zb_kmerize_route_p2p_reserve(zb_kmerizer* h, int nranks, uint64_t* const* d_
         pp.p[r] = (r < nranks) ? d_dst[r] : nullptr;
         pc.p[r] = (r < nranks) ? d_cursor[r] : nullptr;
     }
-    DBuf<unsigned long long> cur(c, 65);      // [0, 64): keys sent per owner; [64]: overflow flag
-    ZB_CUDA(dev_memset(c, cur.get(), 0, 65 * 8));
+    DBuf<unsigned long long> cur(c, 66);      // [0, 64): keys sent per owner; [64]: overflow flag
+    ZB_CUDA(dev_memset(c, cur.get(), 0, 66 * 8));
     {
         Stage st(c, "route_p2p");
         route_p2p(c, h->pending.get(), n, nranks, pp, cur.get(), &pc, capacity_keys, reinterpret_cast<unsigned int*>(cur.get() + 64));
     }
-    std::vector<unsigned long long> hc(65, 0);
-    ZB_CUDA(cudaMemcpyAsync(hc.data(), cur.get(), 65 * 8, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<unsigned long long> hc(66, 0);
+    ZB_CUDA(read_back_big(c, cur.get(), 66 * 8));
     ZB_CUDA(cudaStreamSynchronize(c->stream));   // every store and reservation, local or over NVLink, has completed
+    memcpy(hc.data(), c->h_big, 66 * 8);
     h->pending_upper = 0;
     ZB_CUDA(dev_memset(c, h->d_count.get(), 0, 8));
     if (sent_counts)
         for (int r = 0; r < nranks; r++) sent_counts[r] = hc[r];
     if (hc[64] & 0xffffffffull) ZB_FAIL(ZB_E_RANGE, "route_p2p: a receive buffer of %llu keys overflowed", (unsigned long long)capacity_keys);
+    ZB_CATCH
+}
+
+int zb_peer_enable(int device, int peer) {
+    ZB_TRY
+    ctx_for(device);
+    ctx_for(peer);
+    if (device == peer) return ZB_OK;
+    ZB_CUDA(cudaSetDevice(device));
+    int can = 0;
+    ZB_CUDA(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) ZB_FAIL(ZB_E_CUDA, "device %d cannot map the memory of device %d", device, peer);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+    else ZB_CUDA(e);
     ZB_CATCH
 }
 
