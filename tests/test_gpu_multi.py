@@ -25,3 +25,52 @@ def test_two_rank_kmerize_and_allpairs(mode, k):
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "mgpu_check ok" in r.stdout
+
+
+# ---- one `zot` process, several GPUs (ZB_GPUS, library/devices.py): the file must be the single-GPU file, byte for byte
+CLI_KMERIZE = [(5, "kat6.k5", ["kat6.fa"]), (25, "g1.k25", ["g1.fa"]), (32, "g1.k32", ["g1.fa"]), (8, "r1.k8", ["r1.fq"]),
+               (25, "r1.k25", ["r1.fq"]), (31, "r1.k31", ["r1.fq"]), (25, "mix.k25", ["s0.fa", "r1.fq", "s1.fa"])]
+
+
+@pytest.mark.parametrize("ngpu", [2, 3, 4, 8])
+def test_cli_kmerize_several_gpus_golden_bytes(ngpu, tmp_path, monkeypatch):
+    from zotmer_b200 import _native, cli
+    if _native.device_count() < ngpu:
+        pytest.skip("needs %d GPUs" % ngpu)
+    golden = os.path.join(ROOT, "tests", "golden", "data")
+    monkeypatch.chdir(golden)
+    monkeypatch.setenv("ZB_GPUS", str(ngpu))
+    for k, out, ins in CLI_KMERIZE:
+        o = tmp_path / out
+        cli.main(["kmerize", str(k), str(o)] + ins)
+        with open(os.path.join(golden, out), "rb") as f:
+            assert o.read_bytes() == f.read(), (ngpu, out)
+    # capture (-C) and sub-sampling (-D) on top of the multi-device ranges
+    for args, out in ((["-C", "baits.fa", "25"], "r1_C.k25"), (["-D", "0.3", "-S", "5", "25"], "r1_D03_S5.k25")):
+        o = tmp_path / out
+        cli.main(["kmerize"] + args + [str(o), "r1.fq"])
+        with open(os.path.join(golden, out), "rb") as f:
+            assert o.read_bytes() == f.read(), (ngpu, out)
+
+
+def test_cli_kmerize_two_gpus_equals_one_at_size(tmp_path, monkeypatch):
+    """200,000 reads (30 Mbases): several rounds' worth of keys per device, ranges of ~10 M entries, words that span
+    the range boundary -- the two files must be identical"""
+    import numpy as np
+    from zotmer_b200 import _native, cli
+    from tools import synth
+    if _native.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    g = synth.genome(1500000, seed=9)
+    fq = tmp_path / "reads.fq"
+    synth.fastq_array(g, 200000, seed=10).tofile(str(fq))
+    fa = tmp_path / "genome.fa"
+    fa.write_bytes(synth.fasta_bytes(g))
+    outs = {}
+    for ngpu in (1, 2):
+        monkeypatch.setenv("ZB_GPUS", str(ngpu))
+        o = tmp_path / ("o%d.k25" % ngpu)
+        cli.main(["kmerize", "25", str(o), str(fq), str(fa)])
+        outs[ngpu] = o.read_bytes()
+    assert outs[1] == outs[2]
+    assert len(outs[1]) > 10000000

@@ -66,19 +66,36 @@ def main(argv):
         # (decompressed text) is held in memory after the first read -- the reference reads its input once
         from zotmer_b200.library.file import readBytes
         inputs = [(fn, readBytes(fn)) if (fn == '-' or fn.endswith(('.gz', '.bz2'))) else fn for fn in inputs]
-    (kset, nr) = kmerizeFiles(K, inputs, verbose=verbose)
+    from zotmer_b200.library import devices
+    devs = devices.deviceList()
+    multi = len(devs) > 1     # ZB_GPUS=N: the set then lives on N devices as consecutive key ranges (library/devices.py)
+
+    def kmerizeAll(baits_fn=None):
+        if multi:
+            return devices.kmerizeFilesMulti(K, inputs, devs, verbose=verbose, baits_fn=baits_fn)
+        baits = baitSet(K, baits_fn, devs[0]) if baits_fn is not None else None
+        try:
+            (one, n_) = kmerizeFiles(K, inputs, device=devs[0], verbose=verbose, baits=baits)
+        finally:
+            if baits is not None:
+                baits.free()
+        return [one], n_
+
+    def statsAll(rs):
+        return devices.statsMulti(rs) if multi else rs[0].stats()
+
+    (ranges, nr) = kmerizeAll()
     mark('read + kmerize + count')
-    st = kset.stats()
+    st = statsAll(ranges)
     mark('stats')      # acgt counts EVERY k-mer, before any sub-sampling / capture (kmerize.py:492-493)
 
     if opts['-C'] is not None and opts['-D'] is None:
         # kmerize.py:507-517 (the -D branch comes first in the reference's if / elif chain): whole records are kept
         # when one of their k-mers is a bait.  acgt still covers every record (above), hence the second pass.
-        baits = baitSet(K, opts['-C'])
-        kset.free()
-        (kset, nr) = kmerizeFiles(K, inputs, verbose=verbose, baits=baits)
-        baits.free()
-        st['hist'] = kset.stats()['hist']
+        for r_ in ranges:
+            r_.free()
+        (ranges, nr) = kmerizeAll(opts['-C'])
+        st['hist'] = statsAll(ranges)['hist']
 
     with zotk.kmers(out, 'w') as z:
         if opts['-D'] is not None:
@@ -89,15 +106,19 @@ def main(argv):
             S = 0
             if opts['-S'] is not None:
                 S = int(opts['-S'])
-            kept = kset.sample(d, S, 1)
-            kset.free()
-            kset = kept
-            st['hist'] = kset.stats()['hist']
+            kept = [r_.sample(d, S, 1) for r_ in ranges]
+            for r_ in ranges:
+                r_.free()
+            ranges = kept
+            st['hist'] = statsAll(ranges)['hist']
         h = {}
         for (c, f) in st['hist']:       # first-occurrence order == the reference's dict order (:544-545)
             h[c] = f
         mark('open output')
-        writeKmerSet(z, kset)
+        if multi:
+            devices.writeRangesMulti(z, ranges)
+        else:
+            writeKmerSet(z, ranges[0])
         mark('encode + write streams')
         acgt = st['acgt_weighted']
         n = float(sum(acgt))
@@ -109,7 +130,8 @@ def main(argv):
         z.meta['acgt'] = acgt
         z.meta['reads'] = nr
     mark('meta + table + close')
-    kset.free()
+    for r_ in ranges:
+        r_.free()
     if trace is not None:
         print('zot kmerize phases (ms): ' + ', '.join('%s %.1f' % (trace[i][0], (trace[i][1] - trace[i - 1][1]) * 1e3)
                                                       for i in range(1, len(trace))), file=sys.stderr)

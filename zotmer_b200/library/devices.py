@@ -1,0 +1,263 @@
+"""
+Several GPUs behind ONE `zot` process (ZB_GPUS=N, or all visible devices with ZB_GPUS=all).
+
+The reference is one process, one thread (zotmer/cli.py:45-59); so are the commands here, except that `zot kmerize`
+may spread its work over N devices: one host thread per device (the C ABI releases the GIL, and the library keeps one
+context -- stream, allocator -- per (device, host thread)), NVLink peer mappings between the devices
+(zb_peer_enable), no NCCL and no second process.  The steps, in the order kmerizeFilesMulti runs them:
+
+  1. the input files are cut into record-aligned pieces and dealt out to the devices in ROUNDS of N pieces; a device
+     stages its piece through the pinned ring, parses it and extracts the canonical k-mers (csrc/parse.cu, extract.cu);
+  2. per round, the hash-range exchange of bench.py / multigpu.py, without collectives: the per-owner counts of all
+     devices meet in a Python list (a threading.Barrier is the "all-gather"), every owner allocates its receive buffer
+     at the exact size, route_p2p_kernel stores each key into its owner's buffer over NVLink, a second barrier says
+     that all stores have landed; the owner adopts the buffer and counts it (sort + count, csrc/segsort.cu);
+  3. every device finishes its hash-owned share (mirror + merge: the both-strand set of its k-mers);
+  4. one sorted file needs key RANGES, not hash shares: splitters are quantiles of device 0's share (a uniform sample
+     of all distinct k-mers, since ownership is a hash), every device cuts its sorted share at the splitters
+     (zb_set_lower_bound), device r copies range r of every share out of its peers' memory (zb_set_from_device on a
+     peer pointer) and merges the N sorted runs (zb_merge) -- range r of the final set, no gather to one GPU;
+  5. stats per range, combined on the host (histogram keys in order of first occurrence along the ranges);
+  6. the range-partitioned codec64 encode (zb_set_encode_plan / _emit): every range is encoded where it lives, the
+     six-state maps of the ranges are chained on the host, and all devices write their words into the one output file
+     at once (zb_words_write_fd).  The file is byte-identical to the single-GPU one (tests/test_gpu_multi.py).
+"""
+import os
+import threading
+
+import numpy as np
+
+from zotmer_b200 import _native
+from zotmer_b200.library.reads import isFasta, pieces, MAX_PIECE
+
+
+def deviceList():
+    """devices the commands may use: ZB_GPUS=N -> 0..N-1, ZB_GPUS=all -> every visible device, unset -> device 0"""
+    want = os.environ.get("ZB_GPUS", "1").strip().lower()
+    have = _native.device_count()
+    n = have if want in ("all", "0") else int(want)
+    if n < 1 or n > have:
+        raise SystemExit("ZB_GPUS=%s: this machine has %d CUDA device(s)" % (want, have))
+    return list(range(n))
+
+
+class _Group(object):
+    """N device threads that meet at barriers and share a blackboard"""
+
+    def __init__(self, devs):
+        self.devs = devs
+        self.n = len(devs)
+        self.barrier = threading.Barrier(self.n)
+        self.board = {}
+        self.errors = []
+        for a in devs:
+            for b in devs:
+                if a != b:
+                    _native.peer_enable(a, b)
+
+    def meet(self):
+        self.barrier.wait()
+
+    def run(self, fn):
+        """fn(rank) on one thread per device -> list of results; the first exception of any thread is raised"""
+        out = [None] * self.n
+
+        def body(r):
+            try:
+                out[r] = fn(r)
+            except BaseException as e:      # noqa: B902 -- must release the others from their barriers
+                self.errors.append(e)
+                self.barrier.abort()
+
+        ths = [threading.Thread(target=body, args=(r,)) for r in range(self.n)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if self.errors:
+            first = [e for e in self.errors if not isinstance(e, threading.BrokenBarrierError)]
+            raise (first or self.errors)[0]
+        return out
+
+
+def _pieceRounds(inputs, n, verbose=False):
+    """record-aligned pieces of all inputs, about 1/n of a file each (at most MAX_PIECE), grouped n at a time"""
+    import sys
+    from zotmer_b200.library.file import mapBytes
+    jobs = []
+    for fn in inputs:
+        held = None
+        if isinstance(fn, tuple):
+            fn, held = fn
+        fa = isFasta(fn)
+        data = held if held is not None else mapBytes(fn)
+        if verbose:
+            print('reading %s (%d bytes, %s)' % (fn, len(data), 'FASTA' if fa else 'FASTQ'), file=sys.stderr)
+        if len(data) == 0:
+            continue
+        share = max(1 << 20, min(MAX_PIECE, -(-len(data) // n)))
+        for p in pieces(data, fa, share):
+            if len(p):
+                jobs.append((p, fa))
+    return [jobs[i:i + n] for i in range(0, len(jobs), n)]
+
+
+def mergeHists(hists):
+    """count histograms of consecutive key ranges -> the histogram of the whole set, keys in order of first occurrence"""
+    out = {}
+    for h in hists:
+        for (c, f) in h:
+            out[c] = out.get(c, 0) + f
+    return list(out.items())
+
+
+def kmerizeFilesMulti(K, inputs, devs, verbose=False, baits_fn=None):
+    """-> (list of per-device KmerSets = consecutive key ranges of the both-strand counted set, number of records).
+    baits_fn: FASTA file of bait sequences (`-C`); every device kmerizes it for itself."""
+    g = _Group(devs)
+    n = g.n
+    rounds = _pieceRounds(inputs, n, verbose)
+    nat = _native
+
+    def work(r):
+        dev = devs[r]
+        baits = None
+        if baits_fn is not None:
+            from zotmer_b200.commands.kmerize import baitSet
+            baits = baitSet(K, baits_fn, dev)
+        km = nat.Kmerizer(K, dev)
+        if baits is not None:
+            km.set_baits(baits)
+        bufs = []
+        try:
+            staged = None
+            if rounds and r < len(rounds[0]):
+                staged = nat.stage_input(rounds[0][r][0], dev)
+            for ri, rd in enumerate(rounds):
+                if staged is not None:
+                    km.feed_staged(staged, rd[r][1])
+                    staged = None
+                if ri + 1 < len(rounds) and r < len(rounds[ri + 1]):
+                    staged = nat.stage_input(rounds[ri + 1][r][0], dev)     # copies while this round is exchanged
+                # ---- exchange: counts meet on the board, owners allocate, everybody routes, owners adopt
+                g.board[("cnt", r)] = km.bucket_counts(n)
+                g.meet()
+                M = np.array([g.board[("cnt", s)] for s in range(n)], dtype=np.int64)     # [src][owner]
+                nrecv = int(M[:, r].sum())
+                ptr, _ = nat.ipc_alloc(max(nrecv, 1) * 8 + 256, dev)
+                bufs.append(ptr)
+                g.board[("buf", r)] = ptr
+                g.meet()
+                offs = [int(M[:r, o].sum()) for o in range(n)]
+                km.route_p2p([g.board[("buf", o)] + 8 * offs[o] for o in range(n)])
+                g.meet()                                  # every device's stores have completed
+                km.adopt_canonical_dev(ptr, nrecv)
+                km.flush()                                # counted now: the buffer can go
+                nat.ipc_free(bufs.pop(), dev)
+            share, nr = km.finish()
+        finally:
+            km.close()
+            for p in bufs:
+                nat.ipc_free(p, dev)
+            if baits is not None:
+                baits.free()
+        # ---- key ranges instead of hash shares
+        if r == 0:
+            m = len(share)
+            pos = [(m * q) // n for q in range(1, n)]
+            g.board["split"] = np.array([int(share.slice(p, p + 1).fetch(counts=False)[0]) if m else 0 for p in pos], np.uint64)
+        g.meet()
+        split = g.board["split"]
+        idx = [0] + [int(x) for x in share.lower_bound(split)] + [len(share)]
+        for q in range(1, len(idx)):                      # equal splitters / an empty share: keep the cuts ordered
+            idx[q] = max(idx[q], idx[q - 1])
+        g.board[("share", r)] = (share.dev_ptrs(), idx)
+        g.meet()
+        parts = []
+        for s in range(n):
+            (kp, cp), ix = g.board[("share", s)]
+            b, e = ix[r], ix[r + 1]
+            parts.append(nat.KmerSet.from_device(kp + 8 * b, cp + 4 * b, e - b, dev))     # peer memory -> my memory
+        g.meet()                                          # everybody has copied: the shares can go
+        share.free()
+        mine = nat.merge(parts) if n > 1 else parts[0]
+        for p in parts:
+            if p is not mine:
+                p.free()
+        return mine, nr
+
+    res = g.run(work)
+    return [x[0] for x in res], sum(x[1] for x in res)
+
+
+def statsMulti(ranges):
+    """zb_set_stats of consecutive ranges, combined: acgt tallies add up; the histogram keeps first-occurrence order"""
+    sts = [s.stats() for s in ranges]
+    out = {"acgt_weighted": [sum(st["acgt_weighted"][q] for st in sts) for q in range(4)],
+           "acgt_plain": [sum(st["acgt_plain"][q] for st in sts) for q in range(4)],
+           "total": sum(st["total"] for st in sts), "hist": mergeHists([st["hist"] for st in sts])}
+    return out
+
+
+def writeRangesMulti(z, ranges, nm=None):
+    """the 'kmers' and 'counts' streams of the set whose consecutive key ranges live on several devices, written into the
+    open container `z` exactly as files.writeKmerSet writes a single-device set (files.py:209-217)."""
+    from zotmer_b200.library.files import _names
+    xNm, cNm = _names(nm)
+    n = len(ranges)
+    sizes = [len(s) for s in ranges]
+    # halo of every range: the last k-mer in front of it, the first (up to) five entries behind it
+    heads = []
+    for s in ranges:
+        m = min(5, len(s))
+        if m:
+            h = s.slice(0, m)
+            heads.append(h.fetch())
+            h.free()
+        else:
+            heads.append((np.zeros(0, np.uint64), np.zeros(0, np.uint32)))
+    lasts = []
+    for s in ranges:
+        if len(s):
+            t = s.slice(len(s) - 1, len(s))
+            lasts.append(int(t.fetch(counts=False)[0]))
+            t.free()
+        else:
+            lasts.append(None)
+    plans, kmaps, cmaps = [], [], []
+    prev = 0
+    for r in range(n):
+        nk = np.concatenate([heads[q][0] for q in range(r + 1, n)] + [np.zeros(0, np.uint64)])[:5]
+        nc = np.concatenate([heads[q][1] for q in range(r + 1, n)] + [np.zeros(0, np.uint32)])[:5]
+        p, km, cm = ranges[r].encode_plan(prev, nk, nc)
+        plans.append(p); kmaps.append(km); cmaps.append(cm)
+        if lasts[r] is not None:
+            prev = lasts[r]
+    kentry, koff, ktot = _native.chain_ranges(kmaps)
+    centry, coff, ctot = _native.chain_ranges(cmaps)
+    z._writable()
+    z.fo.flush()
+    at = z._end()
+    fd = z.fo.fileno()
+    errors = []
+
+    def emit(r):
+        try:
+            w = plans[r].emit(kentry[r], centry[r])
+            try:
+                w.write_fd(fd, at + 8 * koff[r], at + 8 * ktot + 8 * coff[r])
+            finally:
+                w.free()
+        except BaseException as e:      # noqa: B902
+            errors.append(e)
+
+    ths = [threading.Thread(target=emit, args=(r,)) for r in range(n)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    if errors:
+        raise errors[0]
+    z._record(xNm, at, 8 * ktot)
+    z._record(cNm, at + 8 * ktot, 8 * ctot)
+    return sum(sizes)
