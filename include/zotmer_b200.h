@@ -190,6 +190,9 @@ int zb_set_encode(const zb_set* s, uint64_t* kmer_words, size_t* n_kmer_words, u
 int zb_set_encode_sizes(const zb_set* s, size_t* n_kmer_words, size_t* n_count_words);
 int zb_set_from_streams(int device, const uint64_t* kmer_words, size_t n_kmer_words,
                         const uint64_t* count_words, size_t n_count_words, zb_set** out);
+/* the same from words that are already in `device` memory */
+int zb_set_from_streams_dev(int device, const uint64_t* d_kmer_words, size_t n_kmer_words,
+                            const uint64_t* d_count_words, size_t n_count_words, zb_set** out);
 /* The same encode with the words LEFT IN HBM (codec64 kernels only): the result is fetched into host memory
  * (zb_words_fetch; pinned destinations copy at full PCIe rate) or written to a file by the library's I/O threads
  * (zb_words_write_fd: device -> pinned ring -> pwrite at the given file offsets, the two streams in parallel) --
@@ -231,6 +234,10 @@ int zb_stage_input(int device, const uint8_t* raw, size_t n, zb_staged** out);
 int zb_stage_fd(int device, int fd, uint64_t offset, size_t n, zb_staged** out);
 int zb_kmerize_feed_staged(zb_kmerizer* h, zb_staged* st, int is_fasta);
 int zb_staged_free(zb_staged* st);
+/* a k-mer set from its two word streams staged with zb_stage_fd / zb_stage_input (count_words may be NULL: all counts
+ * 1) -- readKmersAndCounts, files.py:219-227, without a host copy of the streams; consumes both.  Staging the streams
+ * of file i + 1 before this call for file i overlaps reading and copying with decoding (`zot merge`, `zot dist`). */
+int zb_set_from_staged(zb_staged* kmer_words, zb_staged* count_words, zb_set** out);
 int zb_host_count_byte(const uint8_t* p, size_t n, int byte, uint64_t* count);
 /* pinned host memory from the library's arena (cudaHostAlloc, cached): destinations of zb_words_fetch / zb_set_fetch */
 int zb_host_alloc(size_t bytes, void** p);

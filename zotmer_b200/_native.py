@@ -87,6 +87,8 @@ SIGNATURES = {
     "zb_stage_fd": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_size_t, C.POINTER(vp)]),
     "zb_kmerize_feed_staged": (C.c_int, [vp, vp, C.c_int]),
     "zb_staged_free": (C.c_int, [vp]),
+    "zb_set_from_staged": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "zb_set_from_streams_dev": (C.c_int, [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(vp)]),
     "zb_host_count_byte": (C.c_int, [vp, C.c_size_t, C.c_int, u64p]),
     "zb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
     "zb_host_free": (C.c_int, [vp]),
@@ -200,6 +202,22 @@ class KmerSet(object):
         h = vp()
         _check(lib().zb_set_from_streams(device, _ptr(kw), len(kw), _ptr(cw) if cw is not None else None,
                                          0 if cw is None else len(cw), C.byref(h)))
+        return KmerSet(h, device)
+
+    @staticmethod
+    def from_staged(kmer_words, count_words=None, device=0):
+        """the set whose two word streams were staged with stage_fd / stage_input (consumes them)"""
+        h = vp()
+        kh, kmer_words.h = kmer_words.h, None
+        ch = None
+        if count_words is not None:
+            ch, count_words.h = count_words.h, None
+        try:
+            _check(lib().zb_set_from_staged(kh, ch, C.byref(h)))
+        finally:
+            kmer_words.keep = None
+            if count_words is not None:
+                count_words.keep = None
         return KmerSet(h, device)
 
     def __len__(self):

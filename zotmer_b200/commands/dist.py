@@ -15,7 +15,7 @@ from zotmer_b200 import docopt_mini as docopt
 from zotmer_b200 import usage
 import zotmer_b200.library.dist as formulas
 from zotmer_b200.library.exceptions import MismatchedK
-from zotmer_b200.library.files import readKmerSet
+from zotmer_b200.library.files import readKmerSet, readKmerSetFiles
 from zotmer_b200.library.kmers import kmers
 
 __doc__ = usage.DIST
@@ -97,7 +97,12 @@ def main(argv):
             if z.meta['K'] < K:
                 raise MismatchedK(K, z.meta['K'])
         raise TypeError("cannot unpack non-iterable int object")
-    sets = [projected(K, path) for path in paths]
+    sets = []
+    for (whole, meta) in readKmerSetFiles(paths, counts=False):  # the next files are read and copied meanwhile
+        if meta['K'] < K:
+            raise MismatchedK(K, meta['K'])
+        sets.append(whole.project(2 * (meta['K'] - K)))          # Measure.prep, set form (dist.py:36-49)
+        whole.free()
     abc = _native.allpairs_abc(sets)
     pending = []
     for line in rows(paths, abc, columns):

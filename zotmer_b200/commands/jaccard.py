@@ -14,7 +14,7 @@ from zotmer_b200 import _native
 from zotmer_b200 import docopt_mini as docopt
 from zotmer_b200 import usage
 from zotmer_b200.library.file import readBytes, readFasta
-from zotmer_b200.library.files import readKmerSet
+from zotmer_b200.library.files import readKmerSet, readKmerSetFiles
 from zotmer_b200.library.kmers import kmers
 from zotmer_b200.library.stats import betaQuantile, logBetaSeries
 
@@ -94,10 +94,9 @@ def main(argv):
         return
 
     ks, sets = [], []
-    for path in paths:
-        with kmers(path, 'r') as z:
-            ks.append(z.meta['K'])
-            sets.append(readKmerSet(z, counts=False))
+    for (xs, meta) in readKmerSetFiles(paths, counts=False):     # the next files are read and copied meanwhile
+        ks.append(meta['K'])
+        sets.append(xs)
     firsts = len(paths) if opts['-a'] else 1
     pairs, offender = [], None
     for i in range(firsts):

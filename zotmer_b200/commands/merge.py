@@ -8,7 +8,7 @@ import sys
 from zotmer_b200 import docopt_mini as docopt
 from zotmer_b200 import _native
 from zotmer_b200.library.kmers import kmers
-from zotmer_b200.library.files import readKmerSet, writeKmerSet
+from zotmer_b200.library.files import readKmerSet, readKmerSetFiles, writeKmerSet
 from zotmer_b200 import usage
 
 __doc__ = usage.MERGE
@@ -55,23 +55,15 @@ def main(argv):
 
     K = None
     sets = []
-    for i in range(0, len(inputs), 2):
-        grp = inputs[i:i + 2]
-        zs = [kmers(fn, 'r') for fn in grp]
-        try:
-            # K of the second file of the FIRST pair is never checked (:203-207)
-            if K is None:
-                K = zs[0].meta['K']
-            else:
-                for z0 in zs:
-                    if z0.meta['K'] != K:
-                        print("mismatched K", file=sys.stderr)
-                        sys.exit(1)
-            for z0 in zs:
-                sets.append(readKmerSet(z0))
-        finally:
-            for z0 in zs:
-                z0.close()
+    # the files come in one after the other with the next ones already being read and copied (files.readKmerSetFiles);
+    # K is checked in the reference's order: pair by pair, the second file of the FIRST pair never (:203-207)
+    for i, (xs, meta) in enumerate(readKmerSetFiles(inputs)):
+        sets.append(xs)
+        if i == 0:
+            K = meta['K']
+        elif i >= 2 and meta['K'] != K:
+            print("mismatched K", file=sys.stderr)
+            sys.exit(1)
 
     assert K is not None
 

@@ -855,22 +855,17 @@ int zb_words_free(zb_words* w) {
     ZB_CATCH
 }
 
-int zb_set_from_streams(int device, const uint64_t* kmer_words, size_t n_kmer_words, const uint64_t* count_words,
-                        size_t n_count_words, zb_set** out) {
+// words already on the device (e.g. staged there by the I/O threads) -> set
+int zb_set_from_streams_dev(int device, const uint64_t* d_kmer_words, size_t n_kmer_words, const uint64_t* d_count_words,
+                            size_t n_count_words, zb_set** out) {
     ZB_TRY
-    if (!out || (n_kmer_words && !kmer_words)) ZB_FAIL(ZB_E_ARG, "null argument");
+    if (!out || (n_kmer_words && !d_kmer_words)) ZB_FAIL(ZB_E_ARG, "null argument");
     Ctx* c = ctx_for(device);
     Stage st(c, "decode");
-    DBuf<uint64_t> dkw(c, n_kmer_words), dcw;
-    if (n_kmer_words) ZB_CUDA(cudaMemcpyAsync(dkw.get(), kmer_words, n_kmer_words * 8, cudaMemcpyHostToDevice, c->stream));
-    if (count_words) {
-        dcw.alloc(c, n_count_words);
-        if (n_count_words) ZB_CUDA(cudaMemcpyAsync(dcw.get(), count_words, n_count_words * 8, cudaMemcpyHostToDevice, c->stream));
-    }
     DecodePlan pk, pc;
-    decode_plan(c, dkw.get(), n_kmer_words, &pk);
-    if (count_words) {
-        decode_plan(c, dcw.get(), n_count_words, &pc);
+    decode_plan(c, d_kmer_words, n_kmer_words, &pk);
+    if (d_count_words) {
+        decode_plan(c, d_count_words, n_count_words, &pc);
         if (pc.n != pk.n)
             ZB_FAIL(ZB_E_FORMAT, "k-mer and count streams differ in length (%zu vs %zu)", pk.n, pc.n);   // files.py:182 assert
     }
@@ -882,9 +877,9 @@ int zb_set_from_streams(int device, const uint64_t* kmer_words, size_t n_kmer_wo
         v->k.alloc(c, pk.n);
         v->cnt.alloc(c, pk.n);
         v->n = pk.n;
-        decode_emit<uint64_t>(c, dkw.get(), n_kmer_words, true, &pk, v->k.get());
-        if (count_words) {
-            decode_emit<uint32_t>(c, dcw.get(), n_count_words, false, &pc, v->cnt.get());
+        decode_emit<uint64_t>(c, d_kmer_words, n_kmer_words, true, &pk, v->k.get());
+        if (d_count_words) {
+            decode_emit<uint32_t>(c, d_count_words, n_count_words, false, &pc, v->cnt.get());
         } else if (pk.n) {
             fill_u32(c, v->cnt.get(), pk.n, 1u);
         }
@@ -894,6 +889,21 @@ int zb_set_from_streams(int device, const uint64_t* kmer_words, size_t n_kmer_wo
         throw;
     }
     *out = s;
+    ZB_CATCH
+}
+
+int zb_set_from_streams(int device, const uint64_t* kmer_words, size_t n_kmer_words, const uint64_t* count_words,
+                        size_t n_count_words, zb_set** out) {
+    ZB_TRY
+    if (!out || (n_kmer_words && !kmer_words)) ZB_FAIL(ZB_E_ARG, "null argument");
+    Ctx* c = ctx_for(device);
+    DBuf<uint64_t> dkw(c, n_kmer_words), dcw;
+    if (n_kmer_words) ZB_CUDA(cudaMemcpyAsync(dkw.get(), kmer_words, n_kmer_words * 8, cudaMemcpyHostToDevice, c->stream));
+    if (count_words) {
+        dcw.alloc(c, n_count_words);
+        if (n_count_words) ZB_CUDA(cudaMemcpyAsync(dcw.get(), count_words, n_count_words * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    return zb_set_from_streams_dev(device, dkw.get(), n_kmer_words, count_words ? dcw.get() : nullptr, n_count_words, out);
     ZB_CATCH
 }
 

@@ -305,6 +305,47 @@ int zb_kmerize_feed_staged(zb_kmerizer* h, zb_staged* st, int is_fasta) {
     return rc;
 }
 
+// the kmerizer-independent half of zb_kmerize_feed_staged: the context's stream waits for the piece's copies
+static void staged_wait(zb_staged* st) {
+    Ctx* c = st->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    Stage stg(c, "h2d_staged");
+    st->g.wait();   // every chunk has been handed to a worker stream
+    if (st->g.error) ZB_FAIL(ZB_E_CUDA, "staging the input failed (%s)", strerror(st->g.error));
+    IoPool& pool = IoPool::get();
+    for (int w = 0; w < pool.nthreads(); w++) {
+        if (!((st->g.touched >> w) & 1u)) continue;
+        if (!st->ev[w]) ZB_CUDA(cudaEventCreateWithFlags(&st->ev[w], cudaEventDisableTiming));
+        ZB_CUDA(cudaEventRecord(st->ev[w], pool.stream_of(w, c->device)));
+        ZB_CUDA(cudaStreamWaitEvent(c->stream, st->ev[w], 0));
+    }
+}
+
+int zb_set_from_staged(zb_staged* kmer_words, zb_staged* count_words, zb_set** out) {
+    int rc = ZB_OK;
+    try {
+        if (!kmer_words || !out) ZB_FAIL(ZB_E_ARG, "null argument");
+        if (count_words && count_words->c != kmer_words->c) ZB_FAIL(ZB_E_ARG, "the two streams were staged on different contexts");
+        if ((kmer_words->n & 7) || (count_words && (count_words->n & 7)))
+            ZB_FAIL(ZB_E_FORMAT, "a word stream's length is not a multiple of 8 bytes");     // files.py:58 assert
+        staged_wait(kmer_words);
+        if (count_words) staged_wait(count_words);
+        rc = zb_set_from_streams_dev(kmer_words->c->device, reinterpret_cast<const uint64_t*>(kmer_words->d.get()), kmer_words->n / 8,
+                                     count_words ? reinterpret_cast<const uint64_t*>(count_words->d.get()) : nullptr,
+                                     count_words ? count_words->n / 8 : 0, out);
+    } catch (const zb::Fail& f) {
+        rc = f.code;
+    } catch (const std::bad_alloc&) {
+        zb::set_error("out of host memory");
+        rc = ZB_E_NOMEM;
+    }
+    const std::string keep = zb_last_error();
+    if (kmer_words) staged_release(kmer_words);
+    if (count_words) staged_release(count_words);
+    if (rc != ZB_OK) zb::set_error("%s", keep.c_str());
+    return rc;
+}
+
 int zb_host_count_byte(const uint8_t* p, size_t n, int byte, uint64_t* count) {
     ZB_TRY
     if (!count || (n && !p)) ZB_FAIL(ZB_E_ARG, "null argument");

@@ -96,7 +96,11 @@ def _pieceRounds(inputs, n, verbose=False):
         if len(data) == 0:
             continue
         share = max(1 << 20, min(MAX_PIECE, -(-len(data) // n)))
-        for p in pieces(data, fa, share):
+        try:
+            cut = list(pieces(data, fa, share))
+        except ValueError:      # a record longer than a share (a chromosome): it goes to one device whole
+            cut = list(pieces(data, fa, MAX_PIECE))
+        for p in cut:
             if len(p):
                 jobs.append((p, fa))
     return [jobs[i:i + n] for i in range(0, len(jobs), n)]

@@ -47,12 +47,65 @@ def readKmersAndCounts(z, nm=None, device=0):
     return xs, cs
 
 
+def stageKmerSet(z, nm=None, counts=True, device=0):
+    """start moving the word streams of container `z` to the device (library I/O threads: pread -> pinned ring -> H2D)
+    -> token for finishKmerSet.  `z` must stay open until then."""
+    xNm, cNm = _names(nm)
+    fd = z.fo.fileno()
+    toks = []
+    for name in ((xNm, cNm) if counts else (xNm,)):
+        offset, length = z.toc[name][-1]          # KeyError for a name that is not there (casket.open)
+        assert (length & 7) == 0                  # files.py:58
+        toks.append(_native.stage_fd(fd, offset, length, device))
+    return toks
+
+
+def finishKmerSet(toks, device=0):
+    """decode the staged streams -> _native.KmerSet"""
+    return _native.KmerSet.from_staged(toks[0], toks[1] if len(toks) > 1 else None, device=device)
+
+
 def readKmerSet(z, nm=None, counts=True, device=0):
     """Device-resident form of readKmersAndCounts / readKmers: -> _native.KmerSet"""
-    xNm, cNm = _names(nm)
-    kw = readWords(z.open(xNm))
-    cw = readWords(z.open(cNm)) if counts else None
-    return _native.KmerSet.from_streams(kw, cw, device=device)
+    return finishKmerSet(stageKmerSet(z, nm, counts, device), device)
+
+
+def readKmerSetFiles(paths, counts=True, device=0, ahead=2):
+    """the sets of several k-mer set files, in order: yields (KmerSet, metadata dict).  While one file is decoded the
+    streams of the next `ahead` files are already on their way to the device -- the reference decodes file after file
+    (and `zot dist` re-decodes file j for every pair, dist.py:153-159)."""
+    from zotmer_b200.library.kmers import kmers
+    pending = []
+    it = iter(paths)
+
+    def start():
+        for fn in it:
+            z = kmers(fn, 'r')
+            try:
+                pending.append((z, stageKmerSet(z, None, counts, device)))
+            except BaseException:
+                z.close()
+                raise
+            return True
+        return False
+
+    try:
+        while len(pending) < ahead + 1 and start():
+            pass
+        while pending:
+            z, toks = pending.pop(0)
+            try:
+                s = finishKmerSet(toks, device)
+                meta = dict(z.meta)
+            finally:
+                z.close()
+            start()
+            yield s, meta
+    finally:
+        for (z, toks) in pending:
+            for t in toks:
+                t.free()
+            z.close()
 
 
 def writeKmerSet(z, kset, nm=None):
