@@ -127,6 +127,7 @@ ap_bucket_kernel(const SetRef* __restrict__ sets, int nsets, const uint32_t* __r
     uint8_t* sb = reinterpret_cast<uint8_t*>(acc_w + (two_acc ? 2 : 1) * AB_S * AB_S);   // [AB_CAP] which of the tile's sets an entry came from
     __shared__ uint32_t spre[2 * AB_S + 1];                              // slice starts inside the bucket
     __shared__ uint32_t soff[2 * AB_S];                                  // slice starts inside the sets
+    __shared__ uint32_t s_useful;                                        // useful heads of the bucket (count phase)
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t w0 = W * blockIdx.x / gridDim.x, w1 = W * (blockIdx.x + 1) / gridDim.x;
@@ -211,6 +212,7 @@ ap_bucket_kernel(const SetRef* __restrict__ sets, int nsets, const uint32_t* __r
 #pragma unroll
             for (int j = 0; j < AB_HASH / 4 / AB_THREADS; j++) reinterpret_cast<uint4*>(table)[j * AB_THREADS + tid] = e4;
         }
+        if (tid == 0) s_useful = 0;
         __syncthreads();
         const int m = (int)spre[nT];
         if (m == 0) continue;
@@ -268,14 +270,35 @@ ap_bucket_kernel(const SetRef* __restrict__ sets, int nsets, const uint32_t* __r
         }
         __syncthreads();
 
-        // ---- count: 32 positions per warp step; lane l ends up with "which of these 32 keys are in set l"
-        for (int c0 = (int)warp * 32; c0 < m; c0 += AB_THREADS) {
-            const int q = c0 + (int)lane;
+        // ---- the heads that can contribute to a pair (a key in two sets of a block, or in both blocks) move to the front
+        // of a dense list, in any order -- a pair's count is a sum over keys.  Three entries in four are not heads (a
+        // key of related genomes sits in several of the tile's sets) and a head's position is that of its first entry,
+        // so without this nearly every group of 32 positions held a few heads and was transposed for them: the count
+        // phase was three quarters of the kernel's instructions (profiles/r02_allpairs.md).
+        uint2* cm = reinterpret_cast<uint2*>(sk);                        // [AB_CAP] (mA, mB) of the useful heads; the keys are done with
+#pragma unroll
+        for (int j = 0; j < AB_PER; j++) {
+            const int q = j * AB_THREADS + (int)tid;
             const uint32_t a = (q < m) ? mA[q] : 0u;
             const uint32_t bb = (q < m && two) ? mB[q] : 0u;
             const bool useful = ((flags & AP_WITHIN_A) && (a & (a - 1)) != 0) || ((flags & AP_WITHIN_B) && (bb & (bb - 1)) != 0) ||
                                 ((flags & AP_CROSS) && a != 0 && bb != 0);
-            if (!__any_sync(0xffffffffu, useful)) continue;
+            const unsigned bal = __ballot_sync(0xffffffffu, useful);
+            if (bal) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&s_useful, (uint32_t)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (useful) cm[base + __popc(bal & lanemask_lt())] = make_uint2(a, bb);
+            }
+        }
+        __syncthreads();
+        const int H = (int)s_useful;
+        // ---- count: 32 heads per warp step; lane l ends up with "which of these 32 keys are in set l"
+        for (int c0 = (int)warp * 32; c0 < H; c0 += AB_THREADS) {
+            const int q = c0 + (int)lane;
+            const uint2 ab = (q < H) ? cm[q] : make_uint2(0u, 0u);
+            const uint32_t a = ab.x;
+            const uint32_t bb = ab.y;
             const uint32_t colA = warp_transpose32(a);
             const uint32_t colB = two ? warp_transpose32(bb) : 0u;
             if (flags & (AP_WITHIN_A | AP_WITHIN_B)) {

@@ -225,13 +225,13 @@ __device__ __forceinline__ T block_excl_scan(T v, T* smem, T* total) {
     return r;
 }
 
-// ---- bucket offsets of sorted key arrays: off[b * nsets + i] = first index of set i whose key >> shift is >= b
+// ---- bucket offsets of sorted key arrays: off[b * nsets + i] = first index of set i whose (key - key_base) >> shift is >= b
 // (b = 0 .. nb; `off` zeroed by the caller; blockIdx.y = set).  One streaming pass over the keys: element j closes
 // every bucket between its predecessor's and its own.  Two keys per thread (one 16-byte load), the predecessor of
 // the first one comes from the neighbouring lane.  Ref = any struct with members `k` (sorted u64 keys) and `n`.
 template <typename Ref>
 __device__ __forceinline__ void bucket_offsets_body(const Ref* __restrict__ sets, int nsets, int shift, uint32_t nb,
-                                                    uint32_t* __restrict__ off) {
+                                                    uint32_t* __restrict__ off, uint64_t key_base = 0) {
     const int i = blockIdx.y;
     const uint64_t n = sets[i].n;
     const uint64_t* __restrict__ k = sets[i].k;
@@ -244,29 +244,48 @@ __device__ __forceinline__ void bucket_offsets_body(const Ref* __restrict__ sets
         const bool has0 = 2 * t < n, has1 = 2 * t + 1 < n;
         if (has1 && vec) {
             const uint4 v = ld_stream_v4(k + 2 * t);
-            k0 = ((uint64_t)v.y << 32) | v.x;
-            k1 = ((uint64_t)v.w << 32) | v.z;
+            k0 = (((uint64_t)v.y << 32) | v.x) - key_base;
+            k1 = (((uint64_t)v.w << 32) | v.z) - key_base;
         } else {
-            if (has0) k0 = __ldg(k + 2 * t);
-            if (has1) k1 = __ldg(k + 2 * t + 1);
+            if (has0) k0 = __ldg(k + 2 * t) - key_base;
+            if (has1) k1 = __ldg(k + 2 * t + 1) - key_base;
         }
         uint64_t prev = __shfl_up_sync(0xffffffffu, k1, 1);
-        if (lane == 0 && has0 && t > 0) prev = __ldg(k + 2 * t - 1);
+        if (lane == 0 && has0 && t > 0) prev = __ldg(k + 2 * t - 1) - key_base;
+        // fill tasks: off[b * nsets + i] = val for b in (lo, hi].  Short gaps (the usual case: neighbouring keys in the
+        // same or the next bucket) are written by the thread; a long gap -- the buckets in front of a set's first key,
+        // behind its last one, or an empty stretch of the key space -- is written by the whole warp (one thread took
+        // milliseconds over the hundreds of thousands of empty buckets of a key-range slab)
+        uint64_t lo_[3], hi_[3], val_[3];
+#pragma unroll
+        for (int u = 0; u < 3; u++) { lo_[u] = 0; hi_[u] = 0; val_[u] = 0; }
         if (has0) {
             const uint64_t j = 2 * t;
             const uint64_t cur = (shift < 64) ? (k0 >> shift) : 0ull;
             const uint64_t pb = (shift < 64 && j > 0) ? (prev >> shift) : 0ull;
-            for (uint64_t b = (j > 0) ? pb + 1 : 1; b <= cur; b++) off[b * nsets + i] = (uint32_t)j;   // off[0][i] = 0 already
-            if (j == n - 1)
-                for (uint64_t b = cur + 1; b <= nb; b++) off[b * nsets + i] = (uint32_t)n;
+            lo_[0] = pb; hi_[0] = cur; val_[0] = j;      // (j == 0: buckets 1 .. cur start at 0; off[0][i] = 0 already)
+            if (j == n - 1) { lo_[2] = cur; hi_[2] = nb; val_[2] = n; }
         }
         if (has1) {
             const uint64_t j = 2 * t + 1;
             const uint64_t cur = (shift < 64) ? (k1 >> shift) : 0ull;
             const uint64_t pb = (shift < 64) ? (k0 >> shift) : 0ull;
-            for (uint64_t b = pb + 1; b <= cur; b++) off[b * nsets + i] = (uint32_t)j;
-            if (j == n - 1)
-                for (uint64_t b = cur + 1; b <= nb; b++) off[b * nsets + i] = (uint32_t)n;
+            lo_[1] = pb; hi_[1] = cur; val_[1] = j;
+            if (j == n - 1) { lo_[2] = cur; hi_[2] = nb; val_[2] = n; }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const bool longgap = hi_[u] > lo_[u] + 8;
+            if (!longgap)
+                for (uint64_t bb = lo_[u] + 1; bb <= hi_[u]; bb++) off[bb * nsets + i] = (uint32_t)val_[u];
+            unsigned pend = __ballot_sync(0xffffffffu, longgap);
+            while (pend) {
+                const int src = __ffs(pend) - 1;
+                pend &= pend - 1;
+                const uint64_t glo = __shfl_sync(0xffffffffu, lo_[u], src), ghi = __shfl_sync(0xffffffffu, hi_[u], src);
+                const uint32_t gv = (uint32_t)__shfl_sync(0xffffffffu, val_[u], src);
+                for (uint64_t bb = glo + 1 + lane; bb <= ghi; bb += 32) off[bb * nsets + i] = gv;
+            }
         }
     }
 }

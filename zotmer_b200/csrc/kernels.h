@@ -86,8 +86,11 @@ extern int g_sort_count_mode;  // 0 = auto, 1 = always the classic full LSD sort
 // N-way union of sorted counted sets with the counts summed, one pass over the inputs (key-range buckets merged in
 // shared memory).  merge.py:26-86, :94-163.  Allocates out_k / out_c (n_out entries).  Returns false when the
 // inputs do not suit it (> 1024 of them, key space too skewed for the buckets): the caller falls back to sort_count.
+// key_base / key_bits: every key lies in [key_base, key_base + 2^key_bits) -- a slab of the key space is bucketed by
+// (key - key_base), so that its buckets are all inside the slab.
 bool merge_nway(Ctx* c, const std::vector<const uint64_t*>& ks, const std::vector<const uint32_t*>& cs,
-                const std::vector<size_t>& ns, int key_bits, DBuf<uint64_t>* out_k, DBuf<uint32_t>* out_c, size_t* n_out);
+                const std::vector<size_t>& ns, int key_bits, DBuf<uint64_t>* out_k, DBuf<uint32_t>* out_c, size_t* n_out,
+                uint64_t key_base = 0);
 
 // ---- setops.cu -------------------------------------------------------------------------------
 // Run-length count of a sorted key array (optionally weighted by `w`): distinct keys + counts.

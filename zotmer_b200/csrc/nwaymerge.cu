@@ -49,8 +49,8 @@ struct KCRef {
 // 7.9 ms: nearly every probe misses the TLB.  This reads 8 B per entry, coalesced.)  `off` is zeroed by the caller
 // (rows of empty inputs stay zero).
 __global__ void __launch_bounds__(256)
-bm_offsets_kernel(const KCRef* __restrict__ sets, int nsets, int shift, uint32_t nb, uint32_t* __restrict__ off) {
-    bucket_offsets_body(sets, nsets, shift, nb, off);
+bm_offsets_kernel(const KCRef* __restrict__ sets, int nsets, int shift, uint32_t nb, uint32_t* __restrict__ off, uint64_t key_base) {
+    bucket_offsets_body(sets, nsets, shift, nb, off, key_base);
 }
 
 // start[b] = sum over inputs of off[b][i] (position of bucket b in the virtual concatenation); one warp per bucket
@@ -79,7 +79,7 @@ bm_maxsize_kernel(const uint64_t* __restrict__ start, uint32_t nb, unsigned long
 template <bool BY_SLICE>
 __global__ void __launch_bounds__(BM_THREADS, 2)
 bm_merge_kernel(const KCRef* __restrict__ sets, int nsets, const uint32_t* __restrict__ off, const uint64_t* __restrict__ start,
-                int fine_shift, uint32_t fine_mask, uint64_t* __restrict__ tmp_k, uint32_t* __restrict__ tmp_c,
+                int fine_shift, uint32_t fine_mask, uint64_t key_base, uint64_t* __restrict__ tmp_k, uint32_t* __restrict__ tmp_c,
                 uint32_t* __restrict__ tile_heads, unsigned int* __restrict__ err) {
     extern __shared__ __align__(16) unsigned char bm_raw[];
     uint64_t* sk = reinterpret_cast<uint64_t*>(bm_raw);                  // [BM_CAP] gathered keys
@@ -217,7 +217,7 @@ bm_merge_kernel(const KCRef* __restrict__ sets, int nsets, const uint32_t* __res
 #pragma unroll
     for (int j = 0; j < BM_PER; j++) {
         if ((headbits >> j) & 1u) {
-            const uint32_t d = (uint32_t)(kx[j] >> fine_shift) & fine_mask;
+            const uint32_t d = (uint32_t)((kx[j] - key_base) >> fine_shift) & fine_mask;
             rd[j] = atomicAdd(&hist[d], 1u) | (d << 16);
             wx[j] = wsum[j * BM_THREADS + tid];
         }
@@ -250,7 +250,7 @@ bm_merge_kernel(const KCRef* __restrict__ sets, int nsets, const uint32_t* __res
     const int H = (int)hist[BM_FINE];
     for (int p = (int)tid; p < H; p += BM_THREADS) {
         const uint64_t x = hs[p];
-        const uint32_t d = (uint32_t)(x >> fine_shift) & fine_mask;
+        const uint32_t d = (uint32_t)((x - key_base) >> fine_shift) & fine_mask;
         const int g0 = (int)hist[d], g1 = (int)hist[d + 1];
         int r = 0;
         const int g = g1 - g0;
@@ -296,7 +296,8 @@ bm_compact_kernel(const uint64_t* __restrict__ tmp_k, const uint32_t* __restrict
 }
 
 bool merge_nway(Ctx* c, const std::vector<const uint64_t*>& ks, const std::vector<const uint32_t*>& cs,
-                const std::vector<size_t>& ns, int key_bits, DBuf<uint64_t>* out_k, DBuf<uint32_t>* out_c, size_t* n_out) {
+                const std::vector<size_t>& ns, int key_bits, DBuf<uint64_t>* out_k, DBuf<uint32_t>* out_c, size_t* n_out,
+                uint64_t key_base) {
     const int nsets = (int)ks.size();
     if (nsets < 1 || nsets > BM_MAXSETS) return false;
     size_t total = 0;
@@ -334,7 +335,7 @@ bool merge_nway(Ctx* c, const std::vector<const uint64_t*>& ks, const std::vecto
             size_t nmax = 0;
             for (int i = 0; i < nsets; i++) nmax = std::max(nmax, ns[i]);
             const dim3 grid((unsigned)std::min<size_t>(div_up(nmax, 256 * 2 * 8), 65535), (unsigned)nsets);
-            bm_offsets_kernel<<<grid, 256, 0, c->stream>>>(d_refs.get(), nsets, key_bits - cb, nb, off.get());
+            bm_offsets_kernel<<<grid, 256, 0, c->stream>>>(d_refs.get(), nsets, key_bits - cb, nb, off.get(), key_base);
             ZB_LAUNCH_CHECK(c);
             bm_starts_kernel<<<(unsigned)div_up((size_t)nb + 1, 8), 256, 0, c->stream>>>(off.get(), nsets, nb, start.get());
             ZB_LAUNCH_CHECK(c);
@@ -368,11 +369,11 @@ bool merge_nway(Ctx* c, const std::vector<const uint64_t*>& ks, const std::vecto
         if (nsets >= 16) {
             ZB_CUDA(cudaFuncSetAttribute(bm_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             bm_merge_kernel<true><<<nb, BM_THREADS, smem, c->stream>>>(d_refs.get(), nsets, off.get(), start.get(), fine_shift,
-                                                                       fine_mask, tmp_k.get(), tmp_c.get(), tile_heads.get(), err);
+                                                                       fine_mask, key_base, tmp_k.get(), tmp_c.get(), tile_heads.get(), err);
         } else {
             ZB_CUDA(cudaFuncSetAttribute(bm_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             bm_merge_kernel<false><<<nb, BM_THREADS, smem, c->stream>>>(d_refs.get(), nsets, off.get(), start.get(), fine_shift,
-                                                                        fine_mask, tmp_k.get(), tmp_c.get(), tile_heads.get(), err);
+                                                                        fine_mask, key_base, tmp_k.get(), tmp_c.get(), tile_heads.get(), err);
         }
         ZB_LAUNCH_CHECK(c);
         bm_scan_kernel<<<1, 1024, 0, c->stream>>>(tile_heads.get(), nb, tile_off.get(), totals);
