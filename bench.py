@@ -282,6 +282,7 @@ def mgpu_parity(nat, rank, world, dev):
     for k in (25, 31):
         p2p = multigpu.P2PExchange(nat, dist, rank, world, dev, (READ_LEN - k + 1) * nreads * 2)
         ok = True
+        expect = co.kmerize(k, [(sh, False) for sh in shards])[:2] if rank == 0 else None
         for it in range(3):          # three steps: the receive buffers are reused
             km = nat.Kmerizer(k, dev)
             km.feed(shards[rank], False)
@@ -296,7 +297,7 @@ def mgpu_parity(nat, rank, world, dev):
                 gk = np.concatenate([p[0] for p in parts])
                 gc = np.concatenate([p[1] for p in parts])
                 order = np.argsort(gk, kind="stable")
-                ek, ec, _, _ = co.kmerize(k, [(sh, False) for sh in shards])
+                ek, ec = expect
                 ok = ok and len(np.unique(gk)) == len(gk) and np.array_equal(gk[order], ek) and np.array_equal(gc[order], ec)
         p2p.close()
         flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device="cuda:%d" % dev)
