@@ -96,6 +96,11 @@ int zb_kmerize_take_bucketed_dev(zb_kmerizer* h, int nranks, uint64_t* d_keys, u
  * Returns after all stores have completed; the pending list is empty afterwards. */
 int zb_kmerize_bucket_counts(zb_kmerizer* h, int nranks, uint64_t* bucket_counts);
 int zb_kmerize_route_p2p(zb_kmerizer* h, int nranks, uint64_t* const* d_dst);
+/* zb_kmerize_route_p2p in two halves: _begin launches the routing kernel on a second stream and returns at once, _end
+ * waits for it; in between the caller may count what the PREVIOUS exchange delivered (zb_kmerize_flush), so that the sort
+ * of batch i - 1 runs while batch i's keys travel over NVLink.  Nothing may be fed between the two calls. */
+int zb_kmerize_route_p2p_begin(zb_kmerizer* h, int nranks, uint64_t* const* d_dst);
+int zb_kmerize_route_p2p_end(zb_kmerizer* h);
 /* The same without zb_kmerize_bucket_counts and without any agreement between the ranks beforehand: d_dst[r] is the
  * START of rank r's receive buffer (capacity_keys keys) and d_cursor[r] a u64 word in rank r's memory, zero before the
  * step; every thread block reserves its run with one system-scope atomic add on the owner's word (over NVLink for a

@@ -42,6 +42,8 @@ SIGNATURES = {
     "zb_kmerize_take_bucketed_dev": (C.c_int, [vp, C.c_int, vp, u64p]),
     "zb_kmerize_bucket_counts": (C.c_int, [vp, C.c_int, u64p]),
     "zb_kmerize_route_p2p": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "zb_kmerize_route_p2p_begin": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "zb_kmerize_route_p2p_end": (C.c_int, [vp]),
     "zb_kmerize_route_p2p_reserve": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.c_uint64, C.POINTER(C.c_uint64)]),
     "zb_peer_enable": (C.c_int, [C.c_int, C.c_int]),
     "zb_ipc_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]),
@@ -598,6 +600,14 @@ class Kmerizer(object):
         """write every pending key to dst_ptrs[owner] (device addresses, own or peer memory)"""
         arr = (vp * len(dst_ptrs))(*[vp(int(p)) for p in dst_ptrs])
         _check(lib().zb_kmerize_route_p2p(self.h, len(dst_ptrs), arr))
+
+    def route_p2p_begin(self, dst_ptrs):
+        """route_p2p on the context's second stream; returns at once (route_p2p_end waits)"""
+        arr = (vp * len(dst_ptrs))(*[vp(int(p)) for p in dst_ptrs])
+        _check(lib().zb_kmerize_route_p2p_begin(self.h, len(dst_ptrs), arr))
+
+    def route_p2p_end(self):
+        _check(lib().zb_kmerize_route_p2p_end(self.h))
 
     def route_p2p_reserve(self, dst_ptrs, cursor_ptrs, capacity_keys):
         """write every pending key to its owner's receive buffer (dst_ptrs[owner] = its START), reserving the place with

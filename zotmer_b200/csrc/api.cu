@@ -339,6 +339,8 @@ struct zb_kmerizer {
     const zb_set* baits = nullptr;       // capture mode (`zot kmerize -C`): only records that hold one of these k-mers count
     uint64_t* adopted = nullptr;         // caller-owned key array that stands in for `pending` (multi-GPU receive buffer)
     size_t adopted_n = 0;
+    DBuf<unsigned long long> route_cur;  // cursors of a routing kernel in flight on the side stream (route_p2p_begin / _end)
+    bool routing = false;
 };
 
 static size_t read_pending_count(zb_kmerizer* h) {
@@ -886,6 +888,45 @@ int zb_kmerize_route_p2p(zb_kmerizer* h, int nranks, uint64_t* const* d_dst) {
     ZB_CUDA(cudaStreamSynchronize(c->stream));   // every store, local or over NVLink, has been issued and completed
     h->pending_upper = 0;
     ZB_CUDA(dev_memset(c, h->d_count.get(), 0, 8));
+    ZB_CATCH
+}
+
+// The same in two halves: begin launches the routing kernel on the context's SECOND stream and returns at once, so the
+// caller can count what the previous exchange delivered (zb_kmerize_flush: sort + count on the first stream) while this
+// batch's keys travel over NVLink; end waits for the kernel.  Nothing may be fed between begin and end.
+int zb_kmerize_route_p2p_begin(zb_kmerizer* h, int nranks, uint64_t* const* d_dst) {
+    ZB_TRY
+    if (!h || !d_dst || nranks < 1 || nranks > 64) ZB_FAIL(ZB_E_ARG, "bad argument");
+    if (h->routing) ZB_FAIL(ZB_E_ARG, "a routing kernel is already in flight");
+    Ctx* c = h->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    const size_t n = h->pending_upper ? read_pending_count(h) : 0;
+    if (!c->side) {
+        ZB_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+        ZB_CUDA(cudaEventCreateWithFlags(&c->side_ev, cudaEventDisableTiming));
+    }
+    PeerPtrs pp;
+    for (int r = 0; r < 64; r++) pp.p[r] = (r < nranks) ? d_dst[r] : nullptr;
+    h->route_cur.alloc(c, 64);
+    ZB_CUDA(dev_memset(c, h->route_cur.get(), 0, 64 * 8));
+    ZB_CUDA(cudaEventRecord(c->side_ev, c->stream));          // the keys (and the zeroed cursors) are ready
+    ZB_CUDA(cudaStreamWaitEvent(c->side, c->side_ev, 0));
+    route_p2p(c, h->pending.get(), n, nranks, pp, h->route_cur.get(), nullptr, 0, nullptr, c->side);
+    h->routing = true;
+    h->pending_upper = 0;      // the pending list is spoken for; its buffer is reused only after _end
+    ZB_CUDA(dev_memset(c, h->d_count.get(), 0, 8));
+    ZB_CATCH
+}
+
+int zb_kmerize_route_p2p_end(zb_kmerizer* h) {
+    ZB_TRY
+    if (!h) ZB_FAIL(ZB_E_ARG, "null handle");
+    if (!h->routing) return ZB_OK;
+    Ctx* c = h->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    ZB_CUDA(cudaStreamSynchronize(c->side));   // every store, local or over NVLink, has completed
+    h->routing = false;
+    h->route_cur.release();
     ZB_CATCH
 }
 

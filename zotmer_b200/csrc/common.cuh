@@ -43,6 +43,8 @@ struct Ctx {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;    // second stream of the context (created on first use): a routing kernel that runs beside the sort
+    cudaEvent_t side_ev = nullptr;
     cudaMemPool_t pool = nullptr;
     uint64_t* h_scalars = nullptr;  // pinned, 64 x u64
     uint32_t* d_h_scalars = nullptr;  // the same buffer as the device sees it

@@ -382,15 +382,16 @@ route_p2p_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, Peer
 }
 
 void route_p2p(Ctx* c, const uint64_t* keys, size_t n, int nranks, const PeerPtrs& dst, unsigned long long* d_cursor,
-               const PeerPtrs* rcur, unsigned long long cap, unsigned int* d_err) {
+               const PeerPtrs* rcur, unsigned long long cap, unsigned int* d_err, cudaStream_t stream) {
     if (n == 0) return;
     if (nranks > 64) ZB_FAIL(ZB_E_ARG, "route_p2p: nranks > 64");
+    if (!stream) stream = c->stream;
     if (rcur && g_route_per == 16)
-        route_p2p_kernel<true, 16><<<(unsigned)div_up(n, (size_t)RT_THREADS * 16), RT_THREADS, 0, c->stream>>>(keys, n, nranks, dst, d_cursor, *rcur, cap, d_err);
+        route_p2p_kernel<true, 16><<<(unsigned)div_up(n, (size_t)RT_THREADS * 16), RT_THREADS, 0, stream>>>(keys, n, nranks, dst, d_cursor, *rcur, cap, d_err);
     else if (rcur)
-        route_p2p_kernel<true, 8><<<(unsigned)div_up(n, (size_t)RT_THREADS * 8), RT_THREADS, 0, c->stream>>>(keys, n, nranks, dst, d_cursor, *rcur, cap, d_err);
+        route_p2p_kernel<true, 8><<<(unsigned)div_up(n, (size_t)RT_THREADS * 8), RT_THREADS, 0, stream>>>(keys, n, nranks, dst, d_cursor, *rcur, cap, d_err);
     else
-        route_p2p_kernel<false, 8><<<(unsigned)div_up(n, (size_t)RT_THREADS * 8), RT_THREADS, 0, c->stream>>>(keys, n, nranks, dst, d_cursor, dst, 0ull, nullptr);
+        route_p2p_kernel<false, 8><<<(unsigned)div_up(n, (size_t)RT_THREADS * 8), RT_THREADS, 0, stream>>>(keys, n, nranks, dst, d_cursor, dst, 0ull, nullptr);
     ZB_LAUNCH_CHECK(c);
 }
 

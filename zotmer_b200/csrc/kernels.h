@@ -177,6 +177,7 @@ struct PeerPtrs {
 // rcur != nullptr: reserve mode -- rcur->p[r] is rank r's cursor word (peer memory), a CTA reserves its run there with a
 // system-scope atomic; cap = keys a receive buffer holds, *d_err is raised when a reservation passes it.
 void route_p2p(Ctx* c, const uint64_t* keys, size_t n, int nranks, const PeerPtrs& dst, unsigned long long* d_cursor,
-               const PeerPtrs* rcur = nullptr, unsigned long long cap = 0, unsigned int* d_err = nullptr);
+               const PeerPtrs* rcur = nullptr, unsigned long long cap = 0, unsigned int* d_err = nullptr,
+               cudaStream_t stream = nullptr /* default: the context's stream */);
 
 }  // namespace zb

@@ -204,11 +204,17 @@ class P2PExchange(object):
             raise RuntimeError("P2PExchange: a rank would receive %d keys, capacity is %d" % (int(M.sum(axis=0).max()), self.capacity))
         own, ptrs = self.bufs[seq % self.nbuf]
         t0 = time.perf_counter()
-        km.route_p2p([ptrs[p] + 8 * offs[p] for p in range(self.world)])
+        dst = [ptrs[p] + 8 * offs[p] for p in range(self.world)]
+        if consume:
+            # one kmerizer streamed through many exchanges: this batch's keys travel over NVLink (second stream) while the
+            # batch the previous exchange delivered is sorted and counted (first stream)
+            km.route_p2p_begin(dst)
+            km.flush()
+            km.route_p2p_end()
+        else:
+            km.route_p2p(dst)
         self.route_ms.append((time.perf_counter() - t0) * 1e3)
         self.remote_bytes.append(8 * (sum(counts) - counts[self.rank]))
-        if consume:
-            km.flush()
         self._landed(False)          # every rank's stores have completed
         km.adopt_canonical_dev(own, nrecv)    # sorted in place by km.finish() / the next flush
 
