@@ -435,77 +435,21 @@ static void compact_runs(zb_kmerizer* h) {
     const size_t nr = h->runs.size();
     if (nr <= 1) return;
     Stage st(c, "compact_runs");
-    size_t total = 0, big = 0;
-    for (size_t i = 0; i < nr; i++) {
-        total += h->runs[i].n;
-        if (h->runs[i].n > h->runs[big].n) big = i;
-    }
     size_t fr = 0, tot_mem = 0;
     if (cudaMemGetInfo(&fr, &tot_mem) != cudaSuccess || tot_mem == 0) tot_mem = (size_t)64 << 30;
     const size_t slab_entries = std::max<size_t>((size_t)1 << 24, std::min<size_t>(tot_mem / 16 / 12, ((size_t)1 << 32) - 1));
-    const size_t S = std::max<size_t>(1, div_up(total, slab_entries));
-    // splitters: order statistics of the largest run
-    std::vector<uint64_t> split;
-    for (size_t j = 1; j < S; j++) {
-        const size_t pos = (h->runs[big].n * j) / S;
-        ZB_CUDA(read_back(c, h->runs[big].k.get() + pos, 8));
-        ZB_CUDA(cudaStreamSynchronize(c->stream));
-        split.push_back(c->h_scalars[0]);
-    }
-    std::vector<std::vector<uint64_t>> cut(nr, std::vector<uint64_t>(S + 1, 0));
-    for (size_t i = 0; i < nr; i++) {
-        if (S > 1) lower_bound(c, h->runs[i].k.get(), h->runs[i].n, split.data(), S - 1, cut[i].data() + 1);
-        cut[i][S] = h->runs[i].n;
-        for (size_t j = 1; j <= S; j++) cut[i][j] = std::max(cut[i][j], cut[i][j - 1]);
-    }
-    std::vector<zb_kmerizer::Run> slabs(S);
-    bool ok = true;
-    for (size_t j = 0; j < S && ok; j++) {
-        std::vector<const uint64_t*> ks;
-        std::vector<const uint32_t*> cs;
-        std::vector<size_t> ns;
-        for (size_t i = 0; i < nr; i++) {
-            const size_t b = cut[i][j], e = cut[i][j + 1];
-            if (e > b) { ks.push_back(h->runs[i].k.get() + b); cs.push_back(h->runs[i].c.get() + b); ns.push_back(e - b); }
-        }
-        if (ks.empty()) continue;
-        // the slab's keys lie in [lo, hi]: buckets are cut from (key - lo), so none of them lies outside the slab (bucketed
-        // by the key itself, two thirds of a middle slab's offset table was filled by ONE thread per run: 159 ms of the
-        // human-scale run's 396 ms of compaction)
-        const uint64_t lo = (j == 0) ? 0ull : split[j - 1];
-        const uint64_t top = (2 * h->k >= 64) ? ~0ull : ((1ull << (2 * h->k)) - 1ull);
-        const uint64_t hi = (j + 1 < S) ? split[j] : top;
-        const uint64_t width = hi - lo;
-        const int bits = width ? 64 - __builtin_clzll(width) : 1;
-        ok = merge_nway(c, ks, cs, ns, bits, &slabs[j].k, &slabs[j].c, &slabs[j].n, lo);
-    }
+    std::vector<const uint64_t*> ks;
+    std::vector<const uint32_t*> cs;
+    std::vector<size_t> ns;
+    for (size_t i = 0; i < nr; i++) { ks.push_back(h->runs[i].k.get()); cs.push_back(h->runs[i].c.get()); ns.push_back(h->runs[i].n); }
+    zb_kmerizer::Run r;
+    const bool ok = merge_nway_slabs(c, ks, cs, ns, 2 * h->k, slab_entries, &r.k, &r.c, &r.n);
     if (!ok) {   // key space too skewed for the buckets: fold pairwise instead
-        slabs.clear();
         fold_runs_pairwise(h);
         return;
     }
     ZB_CUDA(cudaStreamSynchronize(c->stream));
-    h->runs.clear();      // the inputs go back to the allocator before the united run is laid out
-    size_t nd = 0;
-    for (auto& sl : slabs) nd += sl.n;
-    zb_kmerizer::Run r;
-    if (S == 1) {
-        r = std::move(slabs[0]);
-    } else {
-        r.n = nd;
-        r.k.alloc(c, nd);
-        r.c.alloc(c, nd);
-        size_t o = 0;
-        for (auto& sl : slabs) {
-            if (sl.n) {
-                ZB_CUDA(dev_copy(c, r.k.get() + o, sl.k.get(), sl.n * 8));
-                ZB_CUDA(dev_copy(c, r.c.get() + o, sl.c.get(), sl.n * 4));
-            }
-            o += sl.n;
-            sl.k.release();
-            sl.c.release();
-        }
-    }
+    h->runs.clear();
     h->runs.push_back(std::move(r));
 }
 
@@ -1210,7 +1154,9 @@ int zb_merge(int nsets, zb_set* const* sets, zb_set** out) {
             bool done = false;
             try {
                 Stage st(c, "merge_nway");
-                done = merge_nway(c, ks, cs, ns, key_bits, &s->k, &s->cnt, &s->n);
+                // slabs of at most 2^27 input entries: the staging stays at 1.6 GB whatever the inputs (64 bacterial
+                // sets = 637 M entries: one 7.6 GB allocation -- 80 - 200 ms of cudaMalloc in a fresh `zot merge` process)
+                done = merge_nway_slabs(c, ks, cs, ns, key_bits, (size_t)1 << 27, &s->k, &s->cnt, &s->n);
             } catch (...) {
                 delete s;
                 throw;

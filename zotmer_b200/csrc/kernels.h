@@ -92,6 +92,11 @@ bool merge_nway(Ctx* c, const std::vector<const uint64_t*>& ks, const std::vecto
                 const std::vector<size_t>& ns, int key_bits, DBuf<uint64_t>* out_k, DBuf<uint32_t>* out_c, size_t* n_out,
                 uint64_t key_base = 0);
 
+// The same slab by slab of the key space: at most ~slab_entries input entries are merged (and staged) at a time.
+bool merge_nway_slabs(Ctx* c, const std::vector<const uint64_t*>& ks, const std::vector<const uint32_t*>& cs,
+                      const std::vector<size_t>& ns, int key_bits, size_t slab_entries, DBuf<uint64_t>* out_k,
+                      DBuf<uint32_t>* out_c, size_t* n_out);
+
 // ---- setops.cu -------------------------------------------------------------------------------
 // Run-length count of a sorted key array (optionally weighted by `w`): distinct keys + counts.
 // Replaces kmerize.py:41-132 (merge with an empty left run) / KmerAccumulator2.flush :412-424.

@@ -396,4 +396,68 @@ bool merge_nway(Ctx* c, const std::vector<const uint64_t*>& ks, const std::vecto
     return true;
 }
 
+// The same, slab by slab of the key space, so that the bucket merge's staging (12 B per input entry of a slab) stays
+// below `slab_entries` entries however large the inputs are: splitters are order statistics of the largest input, every
+// input is cut at them (one lower_bound call per input), the slabs are merged one after the other -- bucketed by
+// (key - slab base), so that no bucket lies outside its slab -- and laid end to end.
+bool merge_nway_slabs(Ctx* c, const std::vector<const uint64_t*>& ks, const std::vector<const uint32_t*>& cs,
+                      const std::vector<size_t>& ns, int key_bits, size_t slab_entries, DBuf<uint64_t>* out_k,
+                      DBuf<uint32_t>* out_c, size_t* n_out) {
+    const size_t nr = ks.size();
+    size_t total = 0, big = 0;
+    for (size_t i = 0; i < nr; i++) {
+        total += ns[i];
+        if (ns[i] > ns[big]) big = i;
+    }
+    const size_t S = std::max<size_t>(1, div_up(total, std::max<size_t>(slab_entries, 1)));
+    if (S == 1) return merge_nway(c, ks, cs, ns, key_bits, out_k, out_c, n_out);
+    std::vector<uint64_t> split;
+    for (size_t j = 1; j < S; j++) {
+        const size_t pos = (ns[big] * j) / S;
+        ZB_CUDA(read_back(c, ks[big] + pos, 8));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+        split.push_back(c->h_scalars[0]);
+    }
+    std::vector<std::vector<uint64_t>> cut(nr, std::vector<uint64_t>(S + 1, 0));
+    for (size_t i = 0; i < nr; i++) {
+        if (ns[i]) lower_bound(c, ks[i], ns[i], split.data(), S - 1, cut[i].data() + 1);
+        cut[i][S] = ns[i];
+        for (size_t j = 1; j <= S; j++) cut[i][j] = std::max(cut[i][j], cut[i][j - 1]);
+    }
+    struct Slab { DBuf<uint64_t> k; DBuf<uint32_t> c; size_t n = 0; };
+    std::vector<Slab> slabs(S);
+    const uint64_t top = (key_bits >= 64) ? ~0ull : ((1ull << key_bits) - 1ull);
+    for (size_t j = 0; j < S; j++) {
+        std::vector<const uint64_t*> sk;
+        std::vector<const uint32_t*> sc;
+        std::vector<size_t> sn;
+        for (size_t i = 0; i < nr; i++) {
+            const size_t b = cut[i][j], e = cut[i][j + 1];
+            if (e > b) { sk.push_back(ks[i] + b); sc.push_back(cs[i] + b); sn.push_back(e - b); }
+        }
+        if (sk.empty()) continue;
+        const uint64_t lo = (j == 0) ? 0ull : split[j - 1];
+        const uint64_t hi = (j + 1 < S) ? split[j] : top;
+        const uint64_t width = hi - lo;
+        const int bits = width ? 64 - __builtin_clzll(width) : 1;
+        if (!merge_nway(c, sk, sc, sn, bits, &slabs[j].k, &slabs[j].c, &slabs[j].n, lo)) return false;
+    }
+    size_t nd = 0;
+    for (auto& sl : slabs) nd += sl.n;
+    out_k->alloc(c, nd);
+    out_c->alloc(c, nd);
+    size_t o = 0;
+    for (auto& sl : slabs) {
+        if (sl.n) {
+            ZB_CUDA(dev_copy(c, out_k->get() + o, sl.k.get(), sl.n * 8));
+            ZB_CUDA(dev_copy(c, out_c->get() + o, sl.c.get(), sl.n * 4));
+        }
+        o += sl.n;
+        sl.k.release();
+        sl.c.release();
+    }
+    *n_out = nd;
+    return true;
+}
+
 }  // namespace zb
