@@ -304,3 +304,44 @@ def test_tools_and_bench_compile():
     import py_compile
     for fn in sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))) + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]:
         py_compile.compile(fn, doraise=True)
+
+
+def test_chain_ranges_and_merge_hists():
+    """host halves of the range-partitioned encode and of the multi-device stats (no GPU needed)"""
+    from zotmer_b200 import _native
+    from zotmer_b200.library import devices
+    # three ranges; maps: entry state -> (exit state, words).  state 0 in front of the first range
+    maps = [([2, 0, 1, 2, 3, 4], [10, 9, 9, 9, 9, 9]), ([0, 1, 2, 3, 4, 5], [0, 0, 0, 0, 0, 0]), ([0, 0, 5, 0, 0, 0], [7, 7, 6, 6, 6, 6])]
+    entry, offs, total = _native.chain_ranges(maps)
+    assert entry == [0, 2, 2] and offs == [0, 10, 10] and total == 16
+    # first-occurrence order along consecutive ranges, frequencies added up
+    h = devices.mergeHists([[(3, 5), (1, 2)], [(1, 1), (7, 4)], [], [(3, 1)]])
+    assert h == [(3, 6), (1, 3), (7, 4)]
+
+
+def test_piece_rounds_are_record_aligned(tmp_path):
+    """ZB_GPUS=N: every input is cut into ~N record-aligned pieces, dealt out N per round; nothing is lost or doubled"""
+    from zotmer_b200.library import devices
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(9000):
+        L = int(rng.integers(30, 400))
+        s = bytes(rng.choice(list(b"ACGTN"), L).tolist())
+        recs.append(b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * L))
+    fq = tmp_path / "a.fq"
+    fq.write_bytes(b"".join(recs))
+    fa = tmp_path / "one_record.fa"     # a single record larger than a share: goes to one device whole
+    fa.write_bytes(b">chr\n" + b"\n".join(bytes(rng.choice(list(b"ACGT"), 80).tolist()) for _ in range(30000)) + b"\n")
+    fb = tmp_path / "many.fa"
+    fb.write_bytes(b"".join(b">s%d\n%s\n" % (i, bytes(rng.choice(list(b"ACGT"), 3000).tolist())) for i in range(900)))
+    rounds = devices._pieceRounds([str(fq), str(fa), str(fb)], 3)
+    assert all(1 <= len(r) <= 3 for r in rounds)
+    flat = [(bytes(p), is_fa) for r in rounds for (p, is_fa) in r]
+    assert b"".join(p for p, f in flat if not f) == fq.read_bytes()
+    assert b"".join(p for p, f in flat if f) == fa.read_bytes() + fb.read_bytes()
+    for p, is_fa in flat:
+        if is_fa:
+            assert p[:1] == b">"
+        else:
+            assert p.count(b"\n") % 4 == 0 and p[:1] == b"@"
+    assert sum(1 for p, f in flat if not f) >= 3 and sum(1 for p, f in flat if f and p.startswith(b">chr")) == 1
