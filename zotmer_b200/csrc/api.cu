@@ -101,6 +101,12 @@ cudaError_t read_back_big(Ctx* c, const void* d_src, size_t bytes) {
     return cudaGetLastError();
 }
 
+void copy_small_to_host(Ctx* c, const void* d_src, size_t host_off, size_t bytes) {
+    if (host_off + bytes > H_BIG || (bytes & 15) || (host_off & 15) || ((uintptr_t)d_src & 15)) ZB_FAIL(ZB_E_ARG, "copy_small_to_host: bad range");
+    copy_kernel<uint4><<<(unsigned)div_up(bytes / 16, 256), 256, 0, c->stream>>>((uint4*)(c->d_h_big + host_off), (const uint4*)d_src, bytes / 16);
+    ZB_LAUNCH_CHECK(c);
+}
+
 cudaError_t dev_memset(Ctx* c, void* p, int value, size_t bytes) {
     if (bytes == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)std::min<size_t>((size_t)c->sm_count * 8, div_up(std::max<size_t>(bytes / 16, 32), 256));

@@ -537,6 +537,9 @@ struct EncodePlan {
     uint64_t map_words[6];
 };
 
+// [0] total words, [1] error flag, [2..13] range map -- behind the word offsets, on a 16-byte boundary
+static inline uint64_t* enc_tail(EncodePlan* p) { return p->woff.get() + (((size_t)p->tiles + 1) & ~(size_t)1); }
+
 template <typename T>
 static void encode_plan(Ctx* c, const T* d_vals, size_t n, bool delta, const EncRange& rg, EncodePlan* p) {
     p->n = n;
@@ -549,8 +552,8 @@ static void encode_plan(Ctx* c, const T* d_vals, size_t n, bool delta, const Enc
     }
     p->info.alloc(c, (size_t)p->tiles * 6);
     p->entry.alloc(c, p->tiles);
-    p->woff.alloc(c, (size_t)p->tiles + 14);
-    uint64_t* total = p->woff.get() + p->tiles;
+    p->woff.alloc(c, (size_t)p->tiles + 16);
+    uint64_t* total = enc_tail(p);
     unsigned int* err = reinterpret_cast<unsigned int*>(total + 1);
     ZB_CUDA(dev_memset(c, total, 0, 16));
     enc_tile_kernel<T><<<p->tiles, EN_THREADS, 0, c->stream>>>(d_vals, n, delta ? 1 : 0, rg, p->info.get(), err);
@@ -562,17 +565,32 @@ static void encode_plan(Ctx* c, const T* d_vals, size_t n, bool delta, const Enc
 // the range's map (synchronises); only needed when ranges are chained
 static void encode_plan_map(Ctx* c, EncodePlan* p) {
     if (p->n == 0) return;
-    uint64_t* total = p->woff.get() + p->tiles;
+    uint64_t* total = enc_tail(p);
     ZB_CUDA(read_back(c, total + 2, 96));
     ZB_CUDA(cudaStreamSynchronize(c->stream));
     for (int r = 0; r < 6; r++) { p->map_exit[r] = (uint32_t)c->h_scalars[r]; p->map_words[r] = c->h_scalars[6 + r]; }
+}
+
+// the same for the two streams of a set with ONE synchronisation (every host round trip of a step is ~15 us of idle GPU)
+static void encode_plan_maps2(Ctx* c, EncodePlan* a, EncodePlan* b) {
+    if (a->n == 0 || b->n == 0) { encode_plan_map(c, a); encode_plan_map(c, b); return; }
+    // the maps sit 16 bytes into 16-byte aligned tails: copy [total, err, map] = 112 bytes of each plan
+    copy_small_to_host(c, enc_tail(a), 0, 112);
+    copy_small_to_host(c, enc_tail(b), 112, 112);
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    const uint64_t* ha = reinterpret_cast<const uint64_t*>(c->h_big);
+    const uint64_t* hb = reinterpret_cast<const uint64_t*>(c->h_big + 112);
+    for (int r = 0; r < 6; r++) {
+        a->map_exit[r] = (uint32_t)ha[2 + r]; a->map_words[r] = ha[8 + r];
+        b->map_exit[r] = (uint32_t)hb[2 + r]; b->map_words[r] = hb[8 + r];
+    }
 }
 
 // words (device, capacity n); entry_state = 0 for a whole stream; returns the number of words written
 template <typename T>
 static size_t encode_emit(Ctx* c, const T* d_vals, EncodePlan* p, uint32_t entry_state, uint64_t* d_words) {
     if (p->n == 0) return 0;
-    uint64_t* total = p->woff.get() + p->tiles;
+    uint64_t* total = enc_tail(p);
     unsigned int* err = reinterpret_cast<unsigned int*>(total + 1);
     if (entry_state != 0) {   // the plan's scan ran with entry state 0
         enc_scan_kernel<<<1, 1024, 0, c->stream>>>(p->info.get(), p->tiles, entry_state, p->entry.get(), p->woff.get(), total, nullptr);
@@ -585,6 +603,27 @@ static size_t encode_emit(Ctx* c, const T* d_vals, EncodePlan* p, uint32_t entry
     if (reinterpret_cast<uint32_t*>(c->h_scalars + 1)[0] != 0)
         ZB_FAIL(ZB_E_RANGE, "codec64: value or k-mer gap needs more than 60 bits (reference: IndexError, codec64.py:93-99)");
     return (size_t)c->h_scalars[0];
+}
+
+// the two streams of a set (entry state 0), emitted back to back with ONE synchronisation
+static void encode_emit2(Ctx* c, const uint64_t* d_k, EncodePlan* pk, uint64_t* kw, size_t* nk, const uint32_t* d_c, EncodePlan* pc,
+                         uint64_t* cw, size_t* nc) {
+    uint64_t* tk = enc_tail(pk);
+    uint64_t* tc = enc_tail(pc);
+    enc_emit_kernel<uint64_t><<<pk->tiles, EN_THREADS, 0, c->stream>>>(d_k, pk->n, 1, pk->rg, pk->entry.get(), pk->woff.get(), kw,
+                                                                      reinterpret_cast<unsigned int*>(tk + 1));
+    ZB_LAUNCH_CHECK(c);
+    enc_emit_kernel<uint32_t><<<pc->tiles, EN_THREADS, 0, c->stream>>>(d_c, pc->n, 0, pc->rg, pc->entry.get(), pc->woff.get(), cw,
+                                                                      reinterpret_cast<unsigned int*>(tc + 1));
+    ZB_LAUNCH_CHECK(c);
+    copy_small_to_host(c, tk, 0, 16);
+    copy_small_to_host(c, tc, 16, 16);
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    const uint64_t* h = reinterpret_cast<const uint64_t*>(c->h_big);
+    if ((uint32_t)h[1] != 0 || (uint32_t)h[3] != 0)
+        ZB_FAIL(ZB_E_RANGE, "codec64: value or k-mer gap needs more than 60 bits (reference: IndexError, codec64.py:93-99)");
+    *nk = (size_t)h[0];
+    *nc = (size_t)h[2];
 }
 
 // vals (device, n values) -> words (device, capacity n); returns the number of words
@@ -726,12 +765,10 @@ int zb_set_encode_dev(const zb_set* s, zb_words** out) {
             EncodePlan pk, pc;
             encode_plan<uint64_t>(c, s->k.get(), s->n, true, rg, &pk);
             encode_plan<uint32_t>(c, s->cnt.get(), s->n, false, rg, &pc);
-            encode_plan_map(c, &pk);
-            encode_plan_map(c, &pc);
+            encode_plan_maps2(c, &pk, &pc);
             w->kw.alloc(c, pk.map_words[0] + 1);
             w->cw.alloc(c, pc.map_words[0] + 1);
-            w->nk = encode_emit<uint64_t>(c, s->k.get(), &pk, 0, w->kw.get());
-            w->nc = encode_emit<uint32_t>(c, s->cnt.get(), &pc, 0, w->cw.get());
+            encode_emit2(c, s->k.get(), &pk, w->kw.get(), &w->nk, s->cnt.get(), &pc, w->cw.get(), &w->nc);
         }
     } catch (...) {
         delete w;

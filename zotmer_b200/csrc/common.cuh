@@ -108,6 +108,8 @@ cudaError_t read_back(Ctx* c, const void* d_src, size_t bytes);
 // the same for up to H_BIG bytes (a multiple of 16, 16-byte aligned source) into c->h_big
 static const size_t H_BIG = 64 << 10;
 cudaError_t read_back_big(Ctx* c, const void* d_src, size_t bytes);
+// `bytes` (multiple of 16, 16-byte aligned source) to c->h_big + host_off; several of these, then ONE synchronisation
+void copy_small_to_host(Ctx* c, const void* d_src, size_t host_off, size_t bytes);
 // Fill / device-to-device copy done by kernels on the context's stream, for the same reason: cudaMemsetAsync and
 // cudaMemcpyAsync(DeviceToDevice) may be served by a copy engine and then queue behind other threads' bulk transfers.
 cudaError_t dev_memset(Ctx* c, void* p, int value, size_t bytes);
