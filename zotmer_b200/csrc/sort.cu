@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(SORT_THREADS, (SORT_ITEMS == 8 ? 3 : (SORT_THR
 onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const uint32_t* __restrict__ vin,
                 uint32_t* __restrict__ vout, uint32_t n, int shift, int bits,
                 const uint32_t* __restrict__ bin_start /*[BINS] global exclusive*/,
-                uint32_t* __restrict__ status /*[tiles][BINS], zeroed*/, uint32_t* __restrict__ ticket) {
+                uint32_t* __restrict__ status /*[tiles][BINS], zeroed*/, uint32_t* __restrict__ ticket, uint64_t uniform_mask) {
     constexpr int SORT_WARPS = SORT_THREADS / 32;
     constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -140,7 +140,14 @@ onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, c
     uint16_t pos[SORT_ITEMS];
     constexpr int PER = (BINS + SORT_THREADS - 1) / SORT_THREADS;  // digits per thread (blocked)
     uint32_t cnt[PER], binst[PER];
-    if (!STABLE) {
+    // A later pass of a sort whose caller accepts any order among keys that agree in the sorted bits (keys-only sorts,
+    // and the top-bit passes in front of the bucket kernels): the input is ordered by the digits already done
+    // (`uniform_mask`), so a tile whose first and last key agree in them holds ONE value of those digits -- 4096
+    // consecutive keys of 125 M nearly always do -- and may rank without regard to arrival order, like a first pass.
+    bool unstable = !STABLE;
+    if (STABLE && uniform_mask != 0 && n_valid > 0)
+        unstable = ((__ldg(kin + tile_base) ^ __ldg(kin + tile_base + n_valid - 1)) & uniform_mask) == 0;
+    if (unstable) {
         // ---- unstable ranking: rank inside (tile, digit) = return value of the atomic
         uint32_t* thist = whist;            // [BINS] counts, then tile-local bin starts
 #pragma unroll
@@ -388,11 +395,15 @@ static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uin
         ZB_CUDA(dev_memset(c, status.get(), 0, (size_t)tiles * BINS * 4));
         Stage st_p(c, vals ? "sort_pass_pairs" : "sort_pass_keys");
         // the first pass has no earlier order to keep: unstable ranking (keys only, or when the caller allows it)
-        const bool stable = !(p == 0 && (!vals || !stable_first)) || g_sort_cfg == 2;
+        const bool any_order = (!vals || !stable_first) && g_sort_cfg != 2;   // ties may come out in any order
+        const bool stable = !(p == 0 && any_order);
+        // bits [lo_bit, shift[p]): the digits the earlier passes have put in order
+        const uint64_t below = (plan.shift[p] >= 64) ? ~0ull : ((1ull << plan.shift[p]) - 1ull);
+        const uint64_t umask = (p > 0 && any_order && g_sort_cfg != 3) ? (below & ~((1ull << lo_bit) - 1ull)) : 0ull;
 #define ZB_ONESWEEP(V, S)                                                                                          \
         onesweep_kernel<BINS, SORT_THREADS, SORT_ITEMS, V, S><<<tiles, SORT_THREADS, sm, c->stream>>>(              \
             kb[cur], kb[cur ^ 1], vals ? vb[cur] : nullptr, vals ? vb[cur ^ 1] : nullptr, (uint32_t)n, plan.shift[p], \
-            plan.bits[p], ghist.get() + (size_t)p * BINS, status.get(), ticket.get() + p)
+            plan.bits[p], ghist.get() + (size_t)p * BINS, status.get(), ticket.get() + p, umask)
         if (vals) { if (stable) ZB_ONESWEEP(true, true); else ZB_ONESWEEP(true, false); }
         else { if (stable) ZB_ONESWEEP(false, true); else ZB_ONESWEEP(false, false); }
 #undef ZB_ONESWEEP
