@@ -350,7 +350,9 @@ def run_ours(args, rank, world, local_rank):
     bases = READS_PER_RANK * READ_LEN
     d_in = torch.from_numpy(fq).to("cuda:%d" % dev)
     with near_gpu(dev):
-        pinned_in = nat.PinnedArray(nbytes, np.uint8)
+        # ZB_PINNED_WC=1: write-combined pinned input (the CPU only writes it; an experiment for hosts where 8 ranks copying
+        # at once are bound by the host side of PCIe)
+        pinned_in = nat.PinnedArray(nbytes, np.uint8, write_combined=os.environ.get("ZB_PINNED_WC", "0") == "1")
         pinned_in.a[:] = fq
     h_in = pinned_in.a
 

@@ -246,6 +246,9 @@ int zb_set_from_staged(zb_staged* kmer_words, zb_staged* count_words, zb_set** o
 int zb_host_count_byte(const uint8_t* p, size_t n, int byte, uint64_t* count);
 /* pinned host memory from the library's arena (cudaHostAlloc, cached): destinations of zb_words_fetch / zb_set_fetch */
 int zb_host_alloc(size_t bytes, void** p);
+/* the same, write-combined (cudaHostAllocWriteCombined): for buffers the CPU only WRITES and the device reads (input
+ * text); PCIe reads of it are not snooped through the CPU caches.  Reading it from the CPU is very slow. */
+int zb_host_alloc_wc(size_t bytes, void** p);
 int zb_host_free(void* p);
 
 /* ------------------------------------------------------------------------------------------

@@ -93,6 +93,7 @@ SIGNATURES = {
     "zb_set_from_streams_dev": (C.c_int, [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(vp)]),
     "zb_host_count_byte": (C.c_int, [vp, C.c_size_t, C.c_int, u64p]),
     "zb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
+    "zb_host_alloc_wc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
     "zb_host_free": (C.c_int, [vp]),
     "zb_dbg_guard_check": (C.c_int, [C.c_int, u64p, u64p]),
     "zb_dbg_sort_u64": (C.c_int, [C.c_int, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
@@ -454,11 +455,12 @@ def host_count_byte(data, byte):
 class PinnedArray(object):
     """a numpy array over pinned host memory of the library's arena (zb_host_alloc); .a is the array"""
 
-    def __init__(self, n, dtype):
+    def __init__(self, n, dtype, write_combined=False):
         dt = np.dtype(dtype)
         self.p = vp()
         self.nbytes = max(int(n), 1) * dt.itemsize
-        _check(lib().zb_host_alloc(self.nbytes, C.byref(self.p)))
+        fn = lib().zb_host_alloc_wc if write_combined else lib().zb_host_alloc
+        _check(fn(self.nbytes, C.byref(self.p)))
         buf = (C.c_uint8 * self.nbytes).from_address(self.p.value)
         self.a = np.frombuffer(buf, dtype=dt, count=max(int(n), 1))
 

@@ -430,36 +430,43 @@ int zb_words_write_fd(const zb_words* w, int fd, uint64_t kmers_offset, uint64_t
 // ---- pinned host memory (destinations of zb_words_fetch / zb_set_fetch): cudaHostAlloc is slow (~0.3 ms per MB), so
 // released blocks are kept and handed out again
 static std::mutex g_host_mu;
-static std::multimap<size_t, void*> g_host_free;
-static std::map<void*, size_t> g_host_live;
+static std::multimap<size_t, void*> g_host_free[2];     // [plain, write-combined]
+static std::map<void*, std::pair<size_t, int>> g_host_live;
 
-int zb_host_alloc(size_t bytes, void** p) {
+static int host_alloc(size_t bytes, int wc, void** p) {
     ZB_TRY
     if (!p) ZB_FAIL(ZB_E_ARG, "null argument");
     ctx_for(0);   // fails with ZB_E_NOGPU on a machine without a device
     const size_t want = std::max<size_t>(4096, (bytes + 4095) & ~(size_t)4095);
+    const unsigned flags = cudaHostAllocPortable | (wc ? cudaHostAllocWriteCombined : 0u);
     std::lock_guard<std::mutex> lk(g_host_mu);
-    auto it = g_host_free.lower_bound(want);
-    if (it != g_host_free.end() && it->first <= 2 * want) {
+    auto& fl = g_host_free[wc ? 1 : 0];
+    auto it = fl.lower_bound(want);
+    if (it != fl.end() && it->first <= 2 * want) {
         *p = it->second;
-        g_host_live[*p] = it->first;
-        g_host_free.erase(it);
+        g_host_live[*p] = {it->first, wc ? 1 : 0};
+        fl.erase(it);
         return ZB_OK;
     }
     void* q = nullptr;
-    if (cudaHostAlloc(&q, want, cudaHostAllocPortable) != cudaSuccess) {
+    if (cudaHostAlloc(&q, want, flags) != cudaSuccess) {
         cudaGetLastError();
-        for (auto& kv : g_host_free) cudaFreeHost(kv.second);
-        g_host_free.clear();
-        if (cudaHostAlloc(&q, want, cudaHostAllocPortable) != cudaSuccess) {
+        for (auto& f : g_host_free) {
+            for (auto& kv : f) cudaFreeHost(kv.second);
+            f.clear();
+        }
+        if (cudaHostAlloc(&q, want, flags) != cudaSuccess) {
             cudaGetLastError();
             ZB_FAIL(ZB_E_NOMEM, "out of pinned host memory: %zu bytes requested", want);
         }
     }
-    g_host_live[q] = want;
+    g_host_live[q] = {want, wc ? 1 : 0};
     *p = q;
     ZB_CATCH
 }
+
+int zb_host_alloc(size_t bytes, void** p) { return host_alloc(bytes, 0, p); }
+int zb_host_alloc_wc(size_t bytes, void** p) { return host_alloc(bytes, 1, p); }
 
 int zb_host_free(void* p) {
     ZB_TRY
@@ -467,7 +474,7 @@ int zb_host_free(void* p) {
     std::lock_guard<std::mutex> lk(g_host_mu);
     auto it = g_host_live.find(p);
     if (it == g_host_live.end()) ZB_FAIL(ZB_E_ARG, "not a pointer of zb_host_alloc");
-    g_host_free.insert({it->second, p});
+    g_host_free[it->second.second].insert({it->second.first, p});
     g_host_live.erase(it);
     ZB_CATCH
 }
