@@ -259,6 +259,8 @@ def finish_step(km, fetch=None):
 def step_device(nat, dev, d_ptr, nbytes, p2p):
     """one step with inputs resident in HBM"""
     km = nat.Kmerizer(K, dev)
+    if p2p is not None:
+        p2p.prepare(km)
     km.feed_dev(d_ptr, nbytes, False)
     if p2p is not None:
         p2p.exchange(km, consume=False)
@@ -284,7 +286,7 @@ def mgpu_parity(nat, rank, world, dev):
         ok = True
         expect = co.kmerize(k, [(sh, False) for sh in shards])[:2] if rank == 0 else None
         for it in range(3):          # three steps: the receive buffers are reused
-            km = nat.Kmerizer(k, dev)
+            km = p2p.prepare(nat.Kmerizer(k, dev))
             km.feed(shards[rank], False)
             p2p.exchange(km)
             s, nr = km.finish()
@@ -402,6 +404,8 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.set_device(dev)
         tr = [threading.get_ident() % 1000, time.perf_counter()] if trace is not None else None
         km = nat.Kmerizer(K, dev)
+        if p2p is not None:
+            p2p.prepare(km)
         km.feed(h_in, False)
         if tr: tr.append(time.perf_counter())
         if p2p is not None:
@@ -468,6 +472,8 @@ def run_ours(args, rank, world, local_rank):
     e2e_ok = (e_res[0], e_res[1], e_res[3], e_res[4]) == (n_full, n_trim, wsz, twsz) and e_res[2]["hist"] == st0["hist"]
     ref_k, ref_c = np.zeros(twsz[0] + 64, np.uint64), np.zeros(twsz[1] + 64, np.uint64)
     km = nat.Kmerizer(K, dev)
+    if p2p is not None:
+        p2p.prepare(km)
     km.feed_dev(d_in.data_ptr(), nbytes, False)
     if p2p is not None:
         p2p.exchange(km, consume=False)
@@ -699,6 +705,8 @@ def bench_human(nat, dev, rank, world):
 
     # warm-up: two batches through a throw-away kmerizer (device allocator, peer mappings, kernel attributes)
     kw = nat.Kmerizer(Kh, dev)
+    if p2p is not None:
+        p2p.prepare(kw)
     for it in range(2):
         codes = make_batch(B, 7 + it)
         kw.feed_codes_dev(codes.data_ptr(), codes.numel(), B)
@@ -714,6 +722,8 @@ def bench_human(nat, dev, rank, world):
 
     nat.dbg_profile(True, dev)
     km = nat.Kmerizer(Kh, dev)
+    if p2p is not None:
+        p2p.prepare(km)
     timed, fed, windows, nb = 0.0, 0, 0, 0
     while fed < nreads:
         b = min(B, nreads - fed)

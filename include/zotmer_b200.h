@@ -87,6 +87,9 @@ int zb_kmerize_close(zb_kmerizer* h);
 /* multi-GPU (hash-range all-to-all): extract canonical k-mers of everything fed so far WITHOUT
  * counting, bucketed by owner = (mix64(kmer) >> 32) * nranks >> 32.  bucket_counts[nranks] (host)
  * receives the sizes; d_keys (device, capacity >= zb_kmerize_pending) the keys grouped by owner. */
+/* the keys this kmerizer extracts from now on will be exchanged among `nranks` GPUs: extraction then also tallies the keys
+ * per owner, and zb_kmerize_bucket_counts(h, nranks) returns the tallies instead of making a pass over the keys (0 = off) */
+int zb_kmerize_set_owners(zb_kmerizer* h, int nranks);
 int zb_kmerize_pending(zb_kmerizer* h, uint64_t* n_keys);
 int zb_kmerize_take_bucketed_dev(zb_kmerizer* h, int nranks, uint64_t* d_keys, uint64_t* bucket_counts);
 /* The same exchange fused into one kernel over NVLink peer memory: zb_kmerize_bucket_counts tells how many of the

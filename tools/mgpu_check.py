@@ -25,6 +25,8 @@ ctx = {"world": world, "rank": rank, "dev": dev, "a2a_ms": [], "a2a_bytes": [],
        "recv": torch.empty(16, dtype=torch.int64, device="cuda:%d" % dev)}
 for it in range(3):   # several steps: the double-buffered receive side is re-used
     km = nat.Kmerizer(K, dev)
+    if p2p is not None and it != 1:
+        p2p.prepare(km)          # owner tallies during extraction (step 1 keeps the counting pass)
     km.feed(shards[rank], False)
     if p2p is not None:
         p2p.exchange(km)
@@ -58,7 +60,7 @@ if p2p is not None:
     # late on some steps: a fast peer must not route step s + 2 into a receive buffer whose step-s keys are still being
     # sorted (the reserve mode had no collective that held peers back)
     import time
-    km = nat.Kmerizer(K, dev)
+    km = p2p.prepare(nat.Kmerizer(K, dev))
     for it in range(5):
         km.feed(shards[rank], False)
         if rank == (it % world) and it % 2 == 1:

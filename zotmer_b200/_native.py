@@ -38,6 +38,7 @@ SIGNATURES = {
     "zb_kmerize_feed_codes_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_uint64]),
     "zb_kmerize_finish": (C.c_int, [vp, C.POINTER(vp), u64p]),
     "zb_kmerize_close": (C.c_int, [vp]),
+    "zb_kmerize_set_owners": (C.c_int, [vp, C.c_int]),
     "zb_kmerize_pending": (C.c_int, [vp, u64p]),
     "zb_kmerize_take_bucketed_dev": (C.c_int, [vp, C.c_int, vp, u64p]),
     "zb_kmerize_bucket_counts": (C.c_int, [vp, C.c_int, u64p]),
@@ -582,6 +583,10 @@ class Kmerizer(object):
 
     def feed_codes_dev(self, dptr, n, n_records):
         _check(lib().zb_kmerize_feed_codes_dev(self.h, vp(dptr), n, n_records))
+
+    def set_owners(self, nranks):
+        """the keys extracted from now on are tallied per owner among `nranks` GPUs (bucket_counts then costs no pass)"""
+        _check(lib().zb_kmerize_set_owners(self.h, int(nranks)))
 
     def pending(self):
         n = C.c_uint64(0)

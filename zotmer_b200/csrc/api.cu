@@ -347,6 +347,9 @@ struct zb_kmerizer {
     size_t adopted_n = 0;
     DBuf<unsigned long long> route_cur;  // cursors of a routing kernel in flight on the side stream (route_p2p_begin / _end)
     bool routing = false;
+    int owners = 0;                      // zb_kmerize_set_owners: extraction tallies the keys per owner among this many GPUs
+    DBuf<unsigned long long> owner_cnt;  // [64] tallies of the pending keys
+    bool owner_cnt_valid = false;        // every pending key came through the tallying extraction
 };
 
 static size_t read_pending_count(zb_kmerizer* h) {
@@ -369,6 +372,16 @@ static void ensure_pending(zb_kmerizer* h, size_t need_total) {
     h->pending_cap = ncap;
 }
 
+// the pending list has been consumed (routed, bucketed or counted): the owner tallies start again
+static void pending_consumed(zb_kmerizer* h) {
+    h->pending_upper = 0;
+    ZB_CUDA(dev_memset(h->c, h->d_count.get(), 0, 8));
+    if (h->owners > 1) {
+        ZB_CUDA(dev_memset(h->c, h->owner_cnt.get(), 0, 64 * 8));
+        h->owner_cnt_valid = true;
+    }
+}
+
 // count the pending canonical keys: one more run
 static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n);
 static void compact_runs(zb_kmerizer* h);
@@ -384,9 +397,9 @@ static void flush_pending(zb_kmerizer* h) {
     }
     if (h->pending_upper == 0) return;
     const size_t n = read_pending_count(h);
-    h->pending_upper = 0;
-    ZB_CUDA(dev_memset(c, h->d_count.get(), 0, 8));
+    pending_consumed(h);
     count_keys(h, h->pending.get(), n);
+    (void)c;
 }
 
 // sort + count `keys` (destroyed) and fold the result into the accumulated run
@@ -472,7 +485,8 @@ static void extract_codes(zb_kmerizer* h, const uint8_t* codes, size_t n_codes) 
         const size_t upper = div_up(len, EXTRACT_TILE) * EXTRACT_TILE;
         ensure_pending(h, h->pending_upper + upper);
         Stage st(c, "extract");
-        extract_canonical(c, h->k, codes + off, len, h->pending.get(), h->d_count.get());
+        extract_canonical(c, h->k, codes + off, len, h->pending.get(), h->d_count.get(), h->owners,
+                          (h->owners > 1 && h->owner_cnt_valid) ? h->owner_cnt.get() : nullptr);
         h->pending_upper += upper;
         off += len;
     }
@@ -661,6 +675,21 @@ int zb_kmerize_set_baits(zb_kmerizer* h, const zb_set* baits) {
     ZB_CATCH
 }
 
+int zb_kmerize_set_owners(zb_kmerizer* h, int nranks) {
+    ZB_TRY
+    if (!h || nranks < 0 || nranks > 64) ZB_FAIL(ZB_E_ARG, "bad argument");
+    Ctx* c = h->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    h->owners = nranks;
+    h->owner_cnt_valid = false;
+    if (nranks > 1) {
+        if (!h->owner_cnt.get()) h->owner_cnt.alloc(c, 64);
+        ZB_CUDA(dev_memset(c, h->owner_cnt.get(), 0, 64 * 8));
+        h->owner_cnt_valid = (h->pending_upper == 0);   // keys extracted before this call were not tallied
+    }
+    ZB_CATCH
+}
+
 int zb_kmerize_feed_dev(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is_fasta) {
     ZB_TRY
     if (!h) ZB_FAIL(ZB_E_ARG, "null handle");
@@ -801,8 +830,7 @@ int zb_kmerize_take_bucketed_dev(zb_kmerizer* h, int nranks, uint64_t* d_keys, u
     if (n && !d_keys) ZB_FAIL(ZB_E_ARG, "null d_keys");
     bucket_scatter(c, h->pending.get(), n, nranks, cnt.get() + 64, d_keys);
     ZB_CUDA(cudaStreamSynchronize(c->stream));
-    h->pending_upper = 0;
-    ZB_CUDA(dev_memset(c, h->d_count.get(), 0, 8));
+    pending_consumed(h);
     ZB_CATCH
 }
 
@@ -811,6 +839,12 @@ int zb_kmerize_bucket_counts(zb_kmerizer* h, int nranks, uint64_t* bucket_counts
     if (!h || !bucket_counts || nranks < 1 || nranks > 64) ZB_FAIL(ZB_E_ARG, "bad argument");
     Ctx* c = h->c;
     ZB_CUDA(cudaSetDevice(c->device));
+    if (h->owners == nranks && h->owner_cnt_valid) {   // tallied while the keys were extracted: no pass over them
+        ZB_CUDA(read_back_big(c, h->owner_cnt.get(), 64 * 8));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int r = 0; r < nranks; r++) bucket_counts[r] = reinterpret_cast<const uint64_t*>(c->h_big)[r];
+        return ZB_OK;
+    }
     const size_t n = h->pending_upper ? read_pending_count(h) : 0;
     DBuf<unsigned long long> cnt(c, 64);
     ZB_CUDA(dev_memset(c, cnt.get(), 0, 64 * 8));
@@ -836,8 +870,7 @@ int zb_kmerize_route_p2p(zb_kmerizer* h, int nranks, uint64_t* const* d_dst) {
         route_p2p(c, h->pending.get(), n, nranks, pp, cur.get());
     }
     ZB_CUDA(cudaStreamSynchronize(c->stream));   // every store, local or over NVLink, has been issued and completed
-    h->pending_upper = 0;
-    ZB_CUDA(dev_memset(c, h->d_count.get(), 0, 8));
+    pending_consumed(h);
     ZB_CATCH
 }
 
@@ -863,8 +896,7 @@ int zb_kmerize_route_p2p_begin(zb_kmerizer* h, int nranks, uint64_t* const* d_ds
     ZB_CUDA(cudaStreamWaitEvent(c->side, c->side_ev, 0));
     route_p2p(c, h->pending.get(), n, nranks, pp, h->route_cur.get(), nullptr, 0, nullptr, c->side);
     h->routing = true;
-    h->pending_upper = 0;      // the pending list is spoken for; its buffer is reused only after _end
-    ZB_CUDA(dev_memset(c, h->d_count.get(), 0, 8));
+    pending_consumed(h);       // the pending list is spoken for; its buffer is reused only after _end
     ZB_CATCH
 }
 
@@ -902,8 +934,7 @@ int zb_kmerize_route_p2p_reserve(zb_kmerizer* h, int nranks, uint64_t* const* d_
     ZB_CUDA(read_back_big(c, cur.get(), 66 * 8));
     ZB_CUDA(cudaStreamSynchronize(c->stream));   // every store and reservation, local or over NVLink, has completed
     memcpy(hc.data(), c->h_big, 66 * 8);
-    h->pending_upper = 0;
-    ZB_CUDA(dev_memset(c, h->d_count.get(), 0, 8));
+    pending_consumed(h);
     if (sent_counts)
         for (int r = 0; r < nranks; r++) sent_counts[r] = hc[r];
     if (hc[64] & 0xffffffffull) ZB_FAIL(ZB_E_RANGE, "route_p2p: a receive buffer of %llu keys overflowed", (unsigned long long)capacity_keys);
@@ -998,6 +1029,7 @@ int zb_kmerize_add_canonical_dev(zb_kmerizer* h, const uint64_t* d_keys, size_t 
         if (have >= h->max_pending) { flush_pending(h); have = 0; }
         const size_t len = std::min(n - off, h->max_pending - have);
         ensure_pending(h, have + len);
+        h->owner_cnt_valid = false;   // these keys were not tallied
         ZB_CUDA(dev_copy(c, h->pending.get() + have, d_keys + off, len * 8));
         const unsigned long long nc = have + len;
         c->h_scalars[8] = nc;

@@ -45,9 +45,23 @@ __device__ __forceinline__ void pack16(uint4 c, uint32_t& w, uint32_t& m) {
     m = m0 | (m1 << 4) | (m2 << 8) | (m3 << 12);
 }
 
+// owner of a canonical k-mer among nranks GPUs (multi-GPU exchange, further down): high bits of an invertible 64-bit mix
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+__device__ __forceinline__ int owner_of(uint64_t key, int nranks) {
+    return (int)__umul64hi(mix64(key), (uint64_t)nranks);
+}
+
+// OWNERS: the kernel also tallies how many of its keys each of `nranks` owners will get (owner_counts[nranks], global), so
+// that the exchange needs no counting pass over the 1 GB of keys afterwards (0.25 ms of every multi-GPU step)
+template <bool OWNERS>
 __global__ void __launch_bounds__(EX_THREADS)
 extract_kernel(int k, const uint8_t* __restrict__ codes, uint64_t* __restrict__ out,
-               unsigned long long* __restrict__ counter) {
+               unsigned long long* __restrict__ counter, int nranks, unsigned long long* __restrict__ owner_counts) {
     __shared__ __align__(128) uint8_t s_codes[EXTRACT_TILE + 32];
     __shared__ uint32_t s_w[EX_THREADS + 2];
     __shared__ uint32_t s_m[EX_THREADS + 2];
@@ -55,8 +69,10 @@ extract_kernel(int k, const uint8_t* __restrict__ codes, uint64_t* __restrict__ 
     __shared__ uint32_t s_scan[EX_THREADS / 32 + 1];
     __shared__ unsigned long long s_base;
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_own[OWNERS ? 64 : 1];
 
     const unsigned tid = threadIdx.x;
+    if (OWNERS && tid < 64) s_own[tid] = 0;
     const uint8_t* src = codes + (size_t)blockIdx.x * EXTRACT_TILE - 32;  // 16-byte aligned by construction
     if (tid == 0) {
         mbar_init(&s_bar, 1);
@@ -116,13 +132,48 @@ extract_kernel(int k, const uint8_t* __restrict__ codes, uint64_t* __restrict__ 
     if (tid == 0) s_base = tot ? atomicAdd(counter, (unsigned long long)tot) : 0ull;
     __syncthreads();
     const unsigned long long base = s_base;
-    for (uint32_t i = tid; i < tot; i += EX_THREADS) out[base + i] = s_keys[i];
+    // up to 8 owners: a thread tallies its ~13 keys in two registers of four 16-bit fields (no atomics, no indexing),
+    // the warp adds them up; more owners: one shared-memory atomic per key
+    uint64_t alo = 0, ahi = 0;
+    for (uint32_t i = tid; i < tot; i += EX_THREADS) {
+        const uint64_t kx = s_keys[i];
+        out[base + i] = kx;
+        if (OWNERS) {
+            const int o = owner_of(kx, nranks);
+            if (nranks <= 8) {
+                const uint64_t one = 1ull << (16 * (o & 3));
+                if (o < 4) alo += one; else ahi += one;
+            } else {
+                atomicAdd(&s_own[o], 1u);
+            }
+        }
+    }
+    if (OWNERS) {
+        if (nranks <= 8) {
+            alo = warp_sum(alo);
+            ahi = warp_sum(ahi);
+            if (lane_id() == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t a = (uint32_t)(alo >> (16 * q)) & 0xffffu, b = (uint32_t)(ahi >> (16 * q)) & 0xffffu;
+                    if (a) atomicAdd(&s_own[q], a);
+                    if (b) atomicAdd(&s_own[4 + q], b);
+                }
+            }
+        }
+        __syncthreads();
+        if ((int)tid < nranks && s_own[tid]) atomicAdd(owner_counts + tid, (unsigned long long)s_own[tid]);
+    }
 }
 
-void extract_canonical(Ctx* c, int k, const uint8_t* codes, size_t n, uint64_t* out, unsigned long long* d_count) {
+void extract_canonical(Ctx* c, int k, const uint8_t* codes, size_t n, uint64_t* out, unsigned long long* d_count, int nranks,
+                       unsigned long long* d_owner_counts) {
     if (n == 0) return;
     const unsigned tiles = (unsigned)div_up(n, EXTRACT_TILE);
-    extract_kernel<<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count);
+    if (nranks > 1 && nranks <= 64 && d_owner_counts)
+        extract_kernel<true><<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count, nranks, d_owner_counts);
+    else
+        extract_kernel<false><<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count, 0, nullptr);
     ZB_LAUNCH_CHECK(c);
 }
 
@@ -244,15 +295,6 @@ void capture_records(Ctx* c, int k, uint8_t* codes, size_t n, const uint64_t* ba
 // multi-GPU routing: owner(key) = floor(mix64(key) * nranks / 2^64) -- the high bits of an
 // invertible 64-bit mix, so ownership is uniform even for low-complexity sequence.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
-    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
-    x ^= x >> 33;
-    return x;
-}
-__device__ __forceinline__ int owner_of(uint64_t key, int nranks) {
-    return (int)__umul64hi(mix64(key), (uint64_t)nranks);
-}
 
 __global__ void __launch_bounds__(256)
 owner_count_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, unsigned long long* __restrict__ counts) {

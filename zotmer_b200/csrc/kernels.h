@@ -165,7 +165,9 @@ void parse_fasta(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n
 // k-mer (min(x, rc x)) of every valid window to out[*d_count ...] (unordered within the batch).
 // basics.py:303-347.
 static const int EXTRACT_TILE = 4096;
-void extract_canonical(Ctx* c, int k, const uint8_t* codes, size_t n, uint64_t* out, unsigned long long* d_count);
+// nranks > 1 with d_owner_counts: also adds to d_owner_counts[o] the number of emitted keys whose owner is o.
+void extract_canonical(Ctx* c, int k, const uint8_t* codes, size_t n, uint64_t* out, unsigned long long* d_count, int nranks = 0,
+                       unsigned long long* d_owner_counts = nullptr);
 // `zot kmerize -C` (kmerize.py:478-483, :507-517): a record is kept, whole, iff one of its k-mers (either strand) is in
 // the bait set; every other record of the code stream (records delimited by code 5, see parse_*) is blanked out.
 // baits: sorted k-mers closed under reverse complement (a both-strand kmerize of the bait FASTA).

@@ -130,6 +130,7 @@ def kmerizeFilesMulti(K, inputs, devs, verbose=False, baits_fn=None):
             from zotmer_b200.commands.kmerize import baitSet
             baits = baitSet(K, baits_fn, dev)
         km = nat.Kmerizer(K, dev)
+        km.set_owners(n)          # extraction tallies the keys per owner: no counting pass before the exchange
         if baits is not None:
             km.set_baits(baits)
         bufs = []

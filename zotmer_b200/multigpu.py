@@ -152,6 +152,12 @@ class P2PExchange(object):
         torch.cuda.synchronize(dev)
         dist.barrier()
 
+    def prepare(self, km):
+        """call on a fresh kmerizer BEFORE it is fed: its extraction then tallies the keys per owner, and the exchange needs
+        no counting pass over them"""
+        km.set_owners(self.world)
+        return km
+
     def _landed(self, failed):
         """closing collective of a step: returns once every rank's stores (and reservations) have completed; raises on
         EVERY rank when any rank overflowed a receive buffer (a rank that raised alone would leave the others waiting)"""
