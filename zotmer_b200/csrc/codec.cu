@@ -307,6 +307,33 @@ __device__ __forceinline__ Comp6 comp_shfl_up(const Comp6& a, int o) {
     for (int q = 0; q < 6; q++) r.c[q] = __shfl_up_sync(0xffffffffu, (unsigned long long)a.c[q], o);
     return r;
 }
+// a tile's record, and the composite of a thread's chunk of tiles, with 32-bit word counts (a chunk holds far fewer than
+// 2^32 values): half the selects and adds of the 64-bit form, which only the scan across the block needs
+struct Comp6s {
+    Map6 s;
+    uint32_t c[6];
+};
+__device__ __forceinline__ uint32_t pick6s(const uint32_t (&c)[6], uint32_t i) {
+    return i == 0 ? c[0] : i == 1 ? c[1] : i == 2 ? c[2] : i == 3 ? c[3] : i == 4 ? c[4] : c[5];
+}
+__device__ __forceinline__ Comp6s comps_of_tile(const uint32_t* __restrict__ info) {
+    Comp6s r;
+    uint32_t v[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) v[q] = info[q];
+    r.s.lo = (v[0] & 0xffu) | ((v[1] & 0xffu) << 8) | ((v[2] & 0xffu) << 16) | ((v[3] & 0xffu) << 24);
+    r.s.hi = (v[4] & 0xffu) | ((v[5] & 0xffu) << 8);
+#pragma unroll
+    for (int q = 0; q < 6; q++) r.c[q] = v[q] >> 8;
+    return r;
+}
+__device__ __forceinline__ Comp6s comps_then(const Comp6s& a, const Comp6s& b) {
+    Comp6s r;
+#pragma unroll
+    for (int q = 0; q < 6; q++) r.c[q] = a.c[q] + pick6s(b.c, map_at(a.s, q));
+    r.s = map_then(a.s, b.s);
+    return r;
+}
 __device__ __forceinline__ Comp6 comp_of_tile(const uint32_t* __restrict__ info) {
     Comp6 r;
     uint32_t v[6];
@@ -319,89 +346,70 @@ __device__ __forceinline__ Comp6 comp_of_tile(const uint32_t* __restrict__ info)
     return r;
 }
 
-// inclusive scan of one composite per lane across the warp
-__device__ __forceinline__ Comp6 comp_warp_incl_scan(Comp6 v) {
-    const unsigned l = lane_id();
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const Comp6 prev = comp_shfl_up(v, o);
-        if (l >= (unsigned)o) v = comp_then(prev, v);
-    }
-    return v;
-}
-__device__ __forceinline__ Comp6 comp_bcast(const Comp6& a, int src) {
-    Comp6 r;
-    r.s.lo = __shfl_sync(0xffffffffu, a.s.lo, src);
-    r.s.hi = __shfl_sync(0xffffffffu, a.s.hi, src);
-#pragma unroll
-    for (int q = 0; q < 6; q++) r.c[q] = __shfl_sync(0xffffffffu, (unsigned long long)a.c[q], src);
-    return r;
-}
-
-// range_map (may be null): [r] = exit state, [6 + r] = number of words, for every entry state r of the whole range.
-// One CTA of EN_SCAN_WARPS warps (16: 128 registers per thread, the composites are 14 registers each); warp w owns a contiguous run of tiles and takes them 32 at a time: one coalesced load of the tile
-// records (the next 32 are requested before these are composed), a warp scan of the composites, the carry.  The 32 warp
-// composites are scanned by warp 0; every warp then replays its run from the state in which the walk from entry0 reaches
-// it, writing each tile's entry state and first word index.
-static constexpr int EN_SCAN_WARPS = 16;
-__global__ void __launch_bounds__(EN_SCAN_WARPS * 32)
+// range_map (may be null): [r] = exit state, [6 + r] = number of words, for every entry state r of the whole range
+__global__ void __launch_bounds__(1024)
 enc_scan_kernel(const uint32_t* __restrict__ tile_info, uint32_t tiles, uint32_t entry0, uint8_t* __restrict__ entry,
                 uint64_t* __restrict__ woff, uint64_t* __restrict__ total_words, uint64_t* __restrict__ range_map) {
-    __shared__ Comp6 s_warp[EN_SCAN_WARPS + 1];
+    __shared__ Comp6 s_warp[33];
     const unsigned t = threadIdx.x, l = t & 31, wid = t >> 5;
-    const uint32_t wchunk = (tiles + EN_SCAN_WARPS - 1) / EN_SCAN_WARPS;
-    const uint32_t t0 = min(tiles, wid * wchunk), t1 = min(tiles, t0 + wchunk);
-    // ---- the warp's composite
-    Comp6 carry = comp_id();
-    {
-        Comp6 nxt = (t0 + l < t1) ? comp_of_tile(tile_info + (size_t)(t0 + l) * 6) : comp_id();
-        for (uint32_t base = t0; base < t1; base += 32) {
-            const Comp6 cur = nxt;
-            const uint32_t tn = base + 32 + l;
-            nxt = (tn < t1) ? comp_of_tile(tile_info + (size_t)tn * 6) : comp_id();
-            const Comp6 inc = comp_warp_incl_scan(cur);
-            carry = comp_then(carry, comp_bcast(inc, 31));
+    const uint32_t chunk = (tiles + 1023) / 1024;
+    const uint32_t t0 = min(tiles, t * chunk), t1 = min(tiles, t0 + chunk);
+    Comp6 mine = comp_id();
+    if (t0 < t1) {   // the next tile's record is requested before this one is composed
+        Comp6s acc = comps_of_tile(tile_info + (size_t)t0 * 6);
+        Comp6s nxt = acc;
+        if (t0 + 1 < t1) nxt = comps_of_tile(tile_info + (size_t)(t0 + 1) * 6);
+        for (uint32_t i = t0 + 1; i < t1; i++) {
+            const Comp6s cur = nxt;
+            if (i + 1 < t1) nxt = comps_of_tile(tile_info + (size_t)(i + 1) * 6);
+            acc = comps_then(acc, cur);
         }
+        mine.s = acc.s;
+#pragma unroll
+        for (int q = 0; q < 6; q++) mine.c[q] = acc.c[q];
     }
-    if (l == 0) s_warp[wid] = carry;
+    // inclusive scan over the block
+    Comp6 inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const Comp6 prev = comp_shfl_up(inc, o);
+        if (l >= (unsigned)o) inc = comp_then(prev, inc);
+    }
+    if (l == 31) s_warp[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        const Comp6 winc = comp_warp_incl_scan(l < EN_SCAN_WARPS ? s_warp[l] : comp_id());
+        Comp6 winc = s_warp[l];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const Comp6 prev = comp_shfl_up(winc, o);
+            if (l >= (unsigned)o) winc = comp_then(prev, winc);
+        }
         Comp6 wex = comp_shfl_up(winc, 1);
         if (l == 0) wex = comp_id();
-        if (l < EN_SCAN_WARPS) s_warp[l] = wex;
-        if (l == 31) s_warp[EN_SCAN_WARPS] = winc;
+        s_warp[l] = wex;
+        if (l == 31) s_warp[32] = winc;
     }
     __syncthreads();
+    Comp6 excl = comp_shfl_up(inc, 1);
+    if (l == 0) excl = comp_id();
+    excl = comp_then(s_warp[wid], excl);
     if (t == 0) {
-        const Comp6 all = s_warp[EN_SCAN_WARPS];
+        const Comp6 all = s_warp[32];
         if (range_map) {
 #pragma unroll
             for (int q = 0; q < 6; q++) { range_map[q] = map_at(all.s, q); range_map[6 + q] = all.c[q]; }
         }
         *total_words = pick6(all.c, entry0);
     }
-    // ---- replay from the state in which the walk from entry0 reaches this warp's run
-    const Comp6 wex = s_warp[wid];
-    uint32_t st = map_at(wex.s, entry0);
-    uint64_t off = pick6(wex.c, entry0);
-    {
-        Comp6 nxt = (t0 + l < t1) ? comp_of_tile(tile_info + (size_t)(t0 + l) * 6) : comp_id();
-        for (uint32_t base = t0; base < t1; base += 32) {
-            const Comp6 cur = nxt;
-            const uint32_t tn = base + 32 + l;
-            nxt = (tn < t1) ? comp_of_tile(tile_info + (size_t)tn * 6) : comp_id();
-            const Comp6 inc = comp_warp_incl_scan(cur);
-            Comp6 ex = comp_shfl_up(inc, 1);
-            if (l == 0) ex = comp_id();
-            if (base + l < t1) {
-                entry[base + l] = (uint8_t)map_at(ex.s, st);
-                woff[base + l] = off + pick6(ex.c, st);
-            }
-            const Comp6 tot = comp_bcast(inc, 31);
-            off += pick6(tot.c, st);
-            st = map_at(tot.s, st);
-        }
+    // replay my chunk from the state in which the walk from entry0 reaches it
+    uint32_t st = map_at(excl.s, entry0);
+    uint64_t off = pick6(excl.c, entry0);
+    for (uint32_t i = t0; i < t1; i++) {
+        const Comp6s ti = comps_of_tile(tile_info + (size_t)i * 6);
+        entry[i] = (uint8_t)st;
+        woff[i] = off;
+        off += pick6s(ti.c, st);
+        st = map_at(ti.s, st);
     }
 }
 
@@ -589,7 +597,7 @@ static void encode_plan(Ctx* c, const T* d_vals, size_t n, bool delta, const Enc
     ZB_CUDA(dev_memset(c, total, 0, 16));
     enc_tile_kernel<T><<<p->tiles, EN_THREADS, 0, c->stream>>>(d_vals, n, delta ? 1 : 0, rg, p->info.get(), err);
     ZB_LAUNCH_CHECK(c);
-    enc_scan_kernel<<<1, EN_SCAN_WARPS * 32, 0, c->stream>>>(p->info.get(), p->tiles, 0u, p->entry.get(), p->woff.get(), total, total + 2);
+    enc_scan_kernel<<<1, 1024, 0, c->stream>>>(p->info.get(), p->tiles, 0u, p->entry.get(), p->woff.get(), total, total + 2);
     ZB_LAUNCH_CHECK(c);
 }
 
@@ -624,7 +632,7 @@ static size_t encode_emit(Ctx* c, const T* d_vals, EncodePlan* p, uint32_t entry
     uint64_t* total = enc_tail(p);
     unsigned int* err = reinterpret_cast<unsigned int*>(total + 1);
     if (entry_state != 0) {   // the plan's scan ran with entry state 0
-        enc_scan_kernel<<<1, EN_SCAN_WARPS * 32, 0, c->stream>>>(p->info.get(), p->tiles, entry_state, p->entry.get(), p->woff.get(), total, nullptr);
+        enc_scan_kernel<<<1, 1024, 0, c->stream>>>(p->info.get(), p->tiles, entry_state, p->entry.get(), p->woff.get(), total, nullptr);
         ZB_LAUNCH_CHECK(c);
     }
     enc_emit_kernel<T><<<p->tiles, EN_THREADS, 0, c->stream>>>(d_vals, p->n, p->delta ? 1 : 0, p->rg, p->entry.get(), p->woff.get(), d_words, err);

@@ -343,7 +343,7 @@ owner_scatter_kernel(const uint64_t* __restrict__ keys, uint64_t n, int nranks, 
 // groups its 2048 keys by owner in shared memory first, so every (CTA, owner) run leaves as consecutive,
 // fully used 128-byte lines.  `cursor[r]` counts what this rank has written to owner r so far.
 static constexpr int RT_THREADS = 256;
-int g_route_per = 8;   // keys per thread of a routing tile in reserve mode (ZB_ROUTE_PER: 8 or 16 = half as many reservations)
+int g_route_per = 8;   // keys per thread of a routing tile (ZB_ROUTE_PER: 8, or 16 = runs twice as long, half as many reservations)
 
 // RESERVE: nobody has told this rank where its runs go -- a CTA reserves its run in the owner's buffer with ONE
 // system-scope atomicAdd on the owner's cursor word (rcur.p[o], in the owner's memory: over NVLink for a remote owner),
@@ -432,6 +432,8 @@ void route_p2p(Ctx* c, const uint64_t* keys, size_t n, int nranks, const PeerPtr
         route_p2p_kernel<true, 16><<<(unsigned)div_up(n, (size_t)RT_THREADS * 16), RT_THREADS, 0, stream>>>(keys, n, nranks, dst, d_cursor, *rcur, cap, d_err);
     else if (rcur)
         route_p2p_kernel<true, 8><<<(unsigned)div_up(n, (size_t)RT_THREADS * 8), RT_THREADS, 0, stream>>>(keys, n, nranks, dst, d_cursor, *rcur, cap, d_err);
+    else if (g_route_per == 16)
+        route_p2p_kernel<false, 16><<<(unsigned)div_up(n, (size_t)RT_THREADS * 16), RT_THREADS, 0, stream>>>(keys, n, nranks, dst, d_cursor, dst, 0ull, nullptr);
     else
         route_p2p_kernel<false, 8><<<(unsigned)div_up(n, (size_t)RT_THREADS * 8), RT_THREADS, 0, stream>>>(keys, n, nranks, dst, d_cursor, dst, 0ull, nullptr);
     ZB_LAUNCH_CHECK(c);
