@@ -19,6 +19,8 @@
 // Algorithmic bytes: 12 B per input entry read + 12 B per output entry staged, re-read and written; the offsets
 // table is 4 B per (bucket, input).  Fallback (skewed keys whose buckets do not fit, > 1024 inputs): the caller
 // uses the weighted sort_count of the concatenation.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -26,15 +28,10 @@
 
 namespace zb {
 
-static constexpr int BM_THREADS = 512;
-static constexpr int BM_PER = 8;
-static constexpr int BM_CAP = BM_THREADS * BM_PER;      // entries of one bucket (all inputs together)
-static constexpr int BM_HASH = 2 * BM_CAP;              // hash slots (load <= 0.5)
-static constexpr int BM_HASH_BITS = 13;
+static constexpr int BM_PER = 8;                        // entries per thread: a bucket holds THREADS x 8 entries of all inputs together
 static constexpr int BM_MAXSETS = 1024;
-static constexpr int BM_SETS_PER = BM_MAXSETS / BM_THREADS;
-static constexpr int BM_FINE = 2048;                    // groups of the in-bucket counting sort (about one distinct key each)
-static constexpr int BM_FINE_BITS = 11;
+// per shape (THREADS = 512 / 256): hash slots 2 x capacity (load <= 0.5), groups of the in-bucket counting sort = THREADS x 4
+int g_merge_cfg = 1;                                    // ZB_MERGE_CFG: 0 = 512 threads, 1 = 256 threads (default, measured)
 #define BM_EMPTY 0xffffffffu
 
 struct KCRef {
@@ -76,11 +73,21 @@ bm_maxsize_kernel(const uint64_t* __restrict__ start, uint32_t nb, unsigned long
 // One CTA per bucket.  Shared memory: keys 32 KB + hash table 32 KB + count sums 16 KB + slice prefixes 8 KB + group
 // sizes 8 KB = 96 KB -> 2 CTAs per SM.
 // BY_SLICE: a warp copies whole slices (few inputs: a thread finds the slice of its entry by bisection instead).
-template <bool BY_SLICE>
-__global__ void __launch_bounds__(BM_THREADS, 2)
+// Two shapes (ZB_MERGE_CFG): THREADS = 512, buckets of <= 4096 entries, 2 CTAs per SM (96 KB each); THREADS = 256, buckets
+// of <= 2048 entries, 4 CTAs per SM (52 KB each) -- four independent CTAs overlap the latency-bound phases (slice offsets,
+// gather) of one bucket with the shared-memory phases of the others better than two do (the same was found for
+// ap_bucket_kernel), at the price of an offset table twice as large.
+template <bool BY_SLICE, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 4)
 bm_merge_kernel(const KCRef* __restrict__ sets, int nsets, const uint32_t* __restrict__ off, const uint64_t* __restrict__ start,
                 int fine_shift, uint32_t fine_mask, uint64_t key_base, uint64_t* __restrict__ tmp_k, uint32_t* __restrict__ tmp_c,
                 uint32_t* __restrict__ tile_heads, unsigned int* __restrict__ err) {
+    constexpr int BM_THREADS = THREADS;
+    constexpr int BM_CAP = THREADS * BM_PER;
+    constexpr int BM_HASH = 2 * BM_CAP;
+    constexpr int BM_HASH_BITS = (THREADS == 512) ? 13 : 12;
+    constexpr int BM_FINE = THREADS * 4;
+    constexpr int BM_SETS_PER = BM_MAXSETS / THREADS;
     extern __shared__ __align__(16) unsigned char bm_raw[];
     uint64_t* sk = reinterpret_cast<uint64_t*>(bm_raw);                  // [BM_CAP] gathered keys
     uint32_t* table = reinterpret_cast<uint32_t*>(sk + BM_CAP);          // [BM_HASH] position of a key's head
@@ -315,6 +322,11 @@ bool merge_nway(Ctx* c, const std::vector<const uint64_t*>& ks, const std::vecto
     ZB_CUDA(cudaMemcpyAsync(d_refs.get(), refs.data(), nsets * sizeof(KCRef), cudaMemcpyHostToDevice, c->stream));
     ZB_CUDA(cudaStreamSynchronize(c->stream));   // `refs` is pageable host memory
 
+    if (const char* e = getenv("ZB_MERGE_CFG")) g_merge_cfg = atoi(e);
+    const int THREADS = (g_merge_cfg == 0) ? 512 : 256;
+    const size_t BM_CAP = (size_t)THREADS * BM_PER;
+    const int BM_FINE = THREADS * 4, BM_FINE_BITS = (THREADS == 512) ? 11 : 10;
+    const size_t BM_HASH = 2 * BM_CAP;
     // buckets: at most 2/3 of the capacity on average; more bits when the largest one does not fit
     int cb = 0;
     while (cb < key_bits && (total >> cb) > (size_t)BM_CAP * 2 / 3) cb++;
@@ -366,15 +378,15 @@ bool merge_nway(Ctx* c, const std::vector<const uint64_t*>& ks, const std::vecto
                         (size_t)(BM_FINE + 1) * 4;
     {
         Stage st(c, "merge_buckets");
-        if (nsets >= 16) {
-            ZB_CUDA(cudaFuncSetAttribute(bm_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            bm_merge_kernel<true><<<nb, BM_THREADS, smem, c->stream>>>(d_refs.get(), nsets, off.get(), start.get(), fine_shift,
-                                                                       fine_mask, key_base, tmp_k.get(), tmp_c.get(), tile_heads.get(), err);
-        } else {
-            ZB_CUDA(cudaFuncSetAttribute(bm_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            bm_merge_kernel<false><<<nb, BM_THREADS, smem, c->stream>>>(d_refs.get(), nsets, off.get(), start.get(), fine_shift,
-                                                                        fine_mask, key_base, tmp_k.get(), tmp_c.get(), tile_heads.get(), err);
-        }
+#define ZB_BM_LAUNCH(SLICE, T)                                                                                                  \
+        do {                                                                                                                    \
+            ZB_CUDA(cudaFuncSetAttribute(bm_merge_kernel<SLICE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+            bm_merge_kernel<SLICE, T><<<nb, T, smem, c->stream>>>(d_refs.get(), nsets, off.get(), start.get(), fine_shift,      \
+                                                                   fine_mask, key_base, tmp_k.get(), tmp_c.get(), tile_heads.get(), err); \
+        } while (0)
+        if (nsets >= 16) { if (THREADS == 512) ZB_BM_LAUNCH(true, 512); else ZB_BM_LAUNCH(true, 256); }
+        else { if (THREADS == 512) ZB_BM_LAUNCH(false, 512); else ZB_BM_LAUNCH(false, 256); }
+#undef ZB_BM_LAUNCH
         ZB_LAUNCH_CHECK(c);
         bm_scan_kernel<<<1, 1024, 0, c->stream>>>(tile_heads.get(), nb, tile_off.get(), totals);
         ZB_LAUNCH_CHECK(c);
