@@ -31,7 +31,7 @@ namespace zb {
 static constexpr int BM_PER = 8;                        // entries per thread: a bucket holds THREADS x 8 entries of all inputs together
 static constexpr int BM_MAXSETS = 1024;
 // per shape (THREADS = 512 / 256): hash slots 2 x capacity (load <= 0.5), groups of the in-bucket counting sort = THREADS x 4
-int g_merge_cfg = 1;                                    // ZB_MERGE_CFG: 0 = 512 threads, 1 = 256 threads (default, measured)
+int g_merge_cfg = 0;                                    // ZB_MERGE_CFG: 0 = 512 threads (default), 1 = 256 threads (measured: slower)
 #define BM_EMPTY 0xffffffffu
 
 struct KCRef {
@@ -73,10 +73,11 @@ bm_maxsize_kernel(const uint64_t* __restrict__ start, uint32_t nb, unsigned long
 // One CTA per bucket.  Shared memory: keys 32 KB + hash table 32 KB + count sums 16 KB + slice prefixes 8 KB + group
 // sizes 8 KB = 96 KB -> 2 CTAs per SM.
 // BY_SLICE: a warp copies whole slices (few inputs: a thread finds the slice of its entry by bisection instead).
-// Two shapes (ZB_MERGE_CFG): THREADS = 512, buckets of <= 4096 entries, 2 CTAs per SM (96 KB each); THREADS = 256, buckets
-// of <= 2048 entries, 4 CTAs per SM (52 KB each) -- four independent CTAs overlap the latency-bound phases (slice offsets,
-// gather) of one bucket with the shared-memory phases of the others better than two do (the same was found for
-// ap_bucket_kernel), at the price of an offset table twice as large.
+// Two shapes (ZB_MERGE_CFG): THREADS = 512, buckets of <= 4096 entries, 2 CTAs per SM (96 KB each) -- the default; THREADS =
+// 256, buckets of <= 2048 entries, 4 CTAs per SM (52 KB each).  Four independent CTAs were what ap_bucket_kernel wanted; here
+// they lose: 64 bacterial sets 18.6 -> 40.0 ms (twice the buckets: offsets 3.1 -> 8.2 ms, buckets 9.4 -> 25.2 ms -- with 64
+// slices per bucket the per-bucket set-up, not the per-entry work, is what doubles), the human-scale compaction 257 -> 282 ms
+// (gpurun_out/r2_test14.log and the run after it).
 template <bool BY_SLICE, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 4)
 bm_merge_kernel(const KCRef* __restrict__ sets, int nsets, const uint32_t* __restrict__ off, const uint64_t* __restrict__ start,
