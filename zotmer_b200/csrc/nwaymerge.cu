@@ -409,6 +409,23 @@ bool merge_nway(Ctx* c, const std::vector<const uint64_t*>& ks, const std::vecto
     return true;
 }
 
+// cut[i * m + j] = first index of input i whose key is >= split[j]: one thread per (input, splitter)
+__global__ void __launch_bounds__(128)
+slab_cuts_kernel(const KCRef* __restrict__ sets, int nsets, const uint64_t* __restrict__ split, int m, uint64_t* __restrict__ cut) {
+    const int i = blockIdx.x;
+    const uint64_t* __restrict__ k = sets[i].k;
+    const uint64_t n = sets[i].n;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const uint64_t x = split[j];
+        uint64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (__ldg(k + mid) < x) lo = mid + 1; else hi = mid;
+        }
+        cut[(size_t)i * m + j] = lo;
+    }
+}
+
 // The same, slab by slab of the key space, so that the bucket merge's staging (12 B per input entry of a slab) stays
 // below `slab_entries` entries however large the inputs are: splitters are order statistics of the largest input, every
 // input is cut at them (one lower_bound call per input), the slabs are merged one after the other -- bucketed by
@@ -431,11 +448,26 @@ bool merge_nway_slabs(Ctx* c, const std::vector<const uint64_t*>& ks, const std:
         ZB_CUDA(cudaStreamSynchronize(c->stream));
         split.push_back(c->h_scalars[0]);
     }
+    // every input is cut at every splitter by ONE kernel (a lower_bound call per input was 64 launches + round trips)
     std::vector<std::vector<uint64_t>> cut(nr, std::vector<uint64_t>(S + 1, 0));
-    for (size_t i = 0; i < nr; i++) {
-        if (ns[i]) lower_bound(c, ks[i], ns[i], split.data(), S - 1, cut[i].data() + 1);
-        cut[i][S] = ns[i];
-        for (size_t j = 1; j <= S; j++) cut[i][j] = std::max(cut[i][j], cut[i][j - 1]);
+    {
+        const int m = (int)(S - 1);
+        std::vector<KCRef> refs(nr);
+        for (size_t i = 0; i < nr; i++) refs[i] = KCRef{ks[i], cs[i], (uint64_t)ns[i]};
+        DBuf<KCRef> d_refs(c, nr);
+        DBuf<uint64_t> d_io(c, (size_t)m + nr * (size_t)m);
+        std::vector<uint64_t> h_cut(nr * (size_t)m);
+        ZB_CUDA(cudaMemcpyAsync(d_refs.get(), refs.data(), nr * sizeof(KCRef), cudaMemcpyHostToDevice, c->stream));
+        ZB_CUDA(cudaMemcpyAsync(d_io.get(), split.data(), (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
+        slab_cuts_kernel<<<(unsigned)nr, 128, 0, c->stream>>>(d_refs.get(), (int)nr, d_io.get(), m, d_io.get() + m);
+        ZB_LAUNCH_CHECK(c);
+        ZB_CUDA(cudaMemcpyAsync(h_cut.data(), d_io.get() + m, h_cut.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < nr; i++) {
+            for (int j = 0; j < m; j++) cut[i][j + 1] = h_cut[i * m + j];
+            cut[i][S] = ns[i];
+            for (size_t j = 1; j <= S; j++) cut[i][j] = std::max(cut[i][j], cut[i][j - 1]);
+        }
     }
     struct Slab { DBuf<uint64_t> k; DBuf<uint32_t> c; size_t n = 0; };
     std::vector<Slab> slabs(S);
