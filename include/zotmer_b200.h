@@ -247,6 +247,30 @@ int zb_staged_free(zb_staged* st);
  * of file i + 1 before this call for file i overlaps reading and copying with decoding (`zot merge`, `zot dist`). */
 int zb_set_from_staged(zb_staged* kmer_words, zb_staged* count_words, zb_set** out);
 int zb_host_count_byte(const uint8_t* p, size_t n, int byte, uint64_t* count);
+/* ------------------------------------------------------------------------------------------
+ * block-compressed input   replaces zotmer/library/file.py:93-97 (`gunzip -c` child + pipe) for files written by
+ * bgzip (BGZF: independent gzip members of <= 64 KiB of text, each with its compressed size in a 'BC' extra field).
+ * The compressed bytes are staged to the device and every member is inflated there by one warp.
+ * zb_bgzf_probe:  ZB_OK iff raw[0, n) is a sequence of BGZF members; their number and the size of the text.
+ * zb_stage_bgzf:  inflates whole members from the front of raw -- as many as fit max_out bytes of text together with
+ *                 the carry (0 = the largest piece the parser takes) -- into a new staged piece on `device`;
+ *                 *n_in_used = compressed bytes consumed.  carry_from / carry_off: the bytes [carry_off, len) of an
+ *                 earlier piece (same device, not yet fed or freed) are copied in front of the inflated text -- the
+ *                 incomplete last record of the previous group.  ZB_E_FORMAT: not BGZF, or a member does not inflate
+ *                 to its recorded size (corrupt file).
+ * zb_staged_cut:  where the text of a staged piece can be cut so that [0, cut) parses like a whole file (FASTQ: after
+ *                 the last newline whose number is a multiple of 4; FASTA: in front of the last '>' that follows a
+ *                 newline); 0 = nowhere.  library/reads.py:pieces on the device.
+ * zb_staged_set_len shortens a piece (to its cut); zb_staged_fetch copies its first n bytes to the host (tests).
+ * ------------------------------------------------------------------------------------------ */
+int zb_bgzf_probe(const uint8_t* raw, size_t n, uint64_t* members, uint64_t* text_bytes);
+int zb_stage_bgzf(int device, const uint8_t* raw, size_t n, uint64_t max_out, zb_staged* carry_from, uint64_t carry_off,
+                  zb_staged** out, uint64_t* n_in_used);
+int zb_staged_cut(zb_staged* st, int is_fasta, uint64_t* cut);
+int zb_staged_len(const zb_staged* st, uint64_t* n);
+int zb_staged_set_len(zb_staged* st, uint64_t n);
+int zb_staged_fetch(zb_staged* st, uint8_t* host, size_t n);
+
 /* pinned host memory from the library's arena (cudaHostAlloc, cached): destinations of zb_words_fetch / zb_set_fetch */
 int zb_host_alloc(size_t bytes, void** p);
 /* the same, write-combined (cudaHostAllocWriteCombined): for buffers the CPU only WRITES and the device reads (input

@@ -213,3 +213,154 @@ def test_repeat_determinism(nat):
         ks, cs = s.fetch()
         assert np.array_equal(ks, ek) and np.array_equal(cs, ec)
         s.free()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# block-compressed input: BGZF members inflated on the device (zb_stage_bgzf, csrc/inflate.cu), record-aligned cuts on
+# the device (zb_staged_cut), `zot kmerize reads.fq.gz`
+# ------------------------------------------------------------------------------------------------------------------
+def _texts():
+    from tools import synth
+    rng = np.random.default_rng(77)
+    g = synth.genome(60000, seed=3)
+    fq = synth.fastq_array(g, 3000, seed=4).reshape(-1).tobytes()
+    fa = synth.fasta_bytes(g)
+    rnd = rng.integers(0, 256, 300000, dtype=np.uint8).tobytes()            # incompressible: stored / near-stored blocks
+    two = rng.choice(np.frombuffer(b"ab", dtype=np.uint8), 200001).tobytes()  # short codes, long matches
+    runs = b"".join(bytes([65 + i % 7]) * int(n) for i, n in enumerate(rng.integers(1, 900, 700)))   # distance < length
+    return {"fastq": fq, "fasta": fa, "random": rnd, "two": two, "runs": runs, "tiny": b"ACGT\n", "empty": b""}
+
+
+@pytest.mark.parametrize("name", ["fastq", "fasta", "random", "two", "runs", "tiny", "empty"])
+def test_bgzf_inflate_on_device_equals_zlib(nat, name):
+    import zlib
+    from tools import synth
+    data = _texts()[name]
+    for (level, block, strategy) in [(6, 65280, 0), (1, 65280, 0), (9, 30000, 0), (0, 65000, 0), (6, 4097, zlib.Z_FIXED),
+                                     (6, 65280, zlib.Z_HUFFMAN_ONLY), (4, 777, 0)]:
+        if len(data) > 300000 and block < 4000:
+            continue
+        z = synth.bgzf_bytes(data, level=level, block=block, strategy=strategy)
+        probe = nat.bgzf_probe(z)
+        assert probe is not None and probe[1] == len(data)
+        st, used = nat.stage_bgzf(z, 0)
+        assert used == len(z) and len(st) == len(data)
+        assert st.fetch() == data, (name, level, block, strategy)
+        st.free()
+
+
+def test_bgzf_groups_and_carry(nat):
+    """a file inflated group by group: every group's text follows the carried tail of the previous piece"""
+    from tools import synth
+    data = _texts()["fastq"]
+    z = synth.bgzf_bytes(data, block=20000)
+    za = np.frombuffer(z, dtype=np.uint8)
+    off, got, prev, prev_cut = 0, b"", None, 0
+    while off < len(z):
+        carried = (len(prev) - prev_cut) if prev is not None else 0
+        st, used = nat.stage_bgzf(za[off:], 0, carried + 70000, prev, prev_cut)
+        assert 0 < used
+        off += used
+        text = st.fetch()
+        if prev is not None:
+            assert text[:carried] == got[len(got) - carried:]
+            got += text[carried:]
+            prev.free()
+        else:
+            got = text
+        prev, prev_cut = st, (len(st) * 2) // 3
+    prev.free()
+    assert got == data
+
+
+def test_bgzf_corrupt_member_is_an_error(nat):
+    from tools import synth
+    data = _texts()["fastq"]
+    z = bytearray(synth.bgzf_bytes(data))
+    z[5000] ^= 0x55
+    z[5001] ^= 0xAA
+    z[5002] ^= 0x0F
+    st = None
+    try:
+        st, _ = nat.stage_bgzf(bytes(z), 0)
+        text = st.fetch()
+    except Exception as e:
+        assert "inflate" in str(e) or "BGZF" in str(e)
+    else:
+        # (a flipped literal inflates to the right size: only the CRC, which `gunzip -c | reader` never waits for, differs)
+        assert len(text) == len(data)
+    if st is not None:
+        st.free()
+    # the library still works afterwards
+    st, _ = nat.stage_bgzf(synth.bgzf_bytes(b"ACGT\n" * 10), 0)
+    assert st.fetch() == b"ACGT\n" * 10
+    st.free()
+
+
+@pytest.mark.parametrize("kind", ["fastq", "fastq_no_final_newline", "fastq_partial", "fasta", "fasta_one_record", "short"])
+def test_staged_cut_equals_host_pieces(nat, kind):
+    from zotmer_b200.library.reads import pieces
+    t = _texts()
+    data = {"fastq": t["fastq"], "fastq_no_final_newline": t["fastq"][:-1], "fastq_partial": t["fastq"][:len(t["fastq"]) - 100],
+            "fasta": t["fasta"] + b">second\nACGT\nAC\n>third x\nGGGG", "fasta_one_record": t["fasta"], "short": b"@r\nAC\n"}[kind]
+    fa = kind.startswith("fasta")
+    st = nat.stage_input(data, 0)
+    cut = st.cut(fa)
+    st.free()
+    if fa:
+        want = data.rfind(b"\n>") + 1
+    else:
+        nl = data.count(b"\n")
+        want = 0
+        if nl >= 4:
+            at = len(data)
+            for _ in range(nl % 4 + 1):
+                at = data.rfind(b"\n", 0, at)
+            want = at + 1
+    assert cut == want
+    if want:
+        # the same boundary the host splitter picks when it has to cut inside this text
+        ps = list(pieces(data, fa, max_piece=len(data) - 1))
+        assert len(ps) >= 2 and len(bytes(ps[0])) <= want
+
+
+@pytest.mark.parametrize("k,group", [(25, None), (25, 200000), (31, 70000)])
+def test_kmerize_bgzf_file_equals_plain(nat, tmp_path, k, group, monkeypatch):
+    """`zot kmerize` of a bgzip'd FASTQ / FASTA (inflated on the device, in groups with carried tails) gives the set of
+    the plain file, which the other tests pin to the oracle"""
+    from tools import synth
+    from zotmer_b200.commands.kmerize import kmerizeFiles
+    from zotmer_b200.library import reads
+    if group:
+        monkeypatch.setattr(reads, "BGZF_GROUP", group)
+    t = _texts()
+    for (name, ext) in (("fastq", ".fq"), ("fasta", ".fa")):
+        data = t[name] if name == "fastq" else t["fasta"] + b">p2 plasmid\n" + t["fasta"][7:5000] + b"\n>p3\nACGTTGCA\n"
+        plain, gz = str(tmp_path / ("x" + ext)), str(tmp_path / ("x" + ext + ".gz"))
+        open(plain, "wb").write(data)
+        open(gz, "wb").write(synth.bgzf_bytes(data, block=30000))
+        before = nat.launch_count(0)
+        (a, na) = kmerizeFiles(k, [gz], 0)
+        assert nat.launch_count(0) > before
+        (b, nb) = kmerizeFiles(k, [plain], 0)
+        ak, ac = a.fetch()
+        bk, bc = b.fetch()
+        assert na == nb and np.array_equal(ak, bk) and np.array_equal(ac, bc)
+        ek, ec, _, enr = co.kmerize(k, [(data, name == "fasta")])
+        assert enr == na and np.array_equal(ak, ek) and np.array_equal(ac, ec)
+        a.free(); b.free()
+
+
+def test_cli_kmerize_bgzf_golden(tmp_path):
+    """the golden k-mer set of r1.fq, from the same reads bgzip'd"""
+    from tools import synth
+    gold = os.path.join(ROOT, "tests", "golden", "data")
+    src = os.path.join(gold, "r1.fq")
+    want = os.path.join(gold, "r1.k25")
+    if not (os.path.exists(src) and os.path.exists(want)):
+        pytest.skip("golden r1.fq / r1.k25 not present")
+    gz = str(tmp_path / "r1.fq.gz")
+    open(gz, "wb").write(synth.bgzf_bytes(open(src, "rb").read(), block=5000))
+    out = str(tmp_path / "o.k25")
+    subprocess.check_call([sys.executable, "-m", "zotmer_b200.cli", "kmerize", "25", out, gz], cwd=ROOT)
+    assert open(out, "rb").read() == open(want, "rb").read()

@@ -345,3 +345,82 @@ def test_piece_rounds_are_record_aligned(tmp_path):
         else:
             assert p.count(b"\n") % 4 == 0 and p[:1] == b"@"
     assert sum(1 for p, f in flat if not f) >= 3 and sum(1 for p, f in flat if f and p.startswith(b">chr")) == 1
+
+
+def test_device_inflater_core_on_the_host_equals_zlib(tmp_path):
+    """zotmer_b200/csrc/inflate_core.cuh (what one warp runs per BGZF member) compiled for the host with one lane:
+    stored / fixed / dynamic blocks, every zlib strategy, multi-block streams with flush points, wrong sizes and
+    corrupt streams (must return an error, never hang or read out of bounds)"""
+    import ctypes
+    import random
+    import zlib
+    so = str(tmp_path / "libzi_host.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "host", "inflate_host.cpp")])
+    L = ctypes.CDLL(so)
+    L.zi_inflate_host.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32]
+    rng = random.Random(1)
+
+    def inflate(comp, n):
+        out = ctypes.create_string_buffer(n + 8)
+        rc = L.zi_inflate_host(comp, len(comp), out, n)
+        return rc, out.raw[:n]
+
+    def check(data, level, strategy, wbits=-15, mem=9):
+        c = zlib.compressobj(level, zlib.DEFLATED, wbits, mem, strategy)
+        comp = c.compress(data) + c.flush()
+        rc, out = inflate(comp, len(data))
+        assert rc == 0 and out == data, (rc, len(data), level, strategy)
+        assert inflate(comp, len(data) + 1)[0] != 0
+        if data:
+            assert inflate(comp, len(data) - 1)[0] != 0
+
+    fq = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, bytes(rng.choice(b"ACGT") for _ in range(150)), b"I" * 150) for i in range(200))
+    cases = [b"", b"a", b"ab" * 10, b"\x00" * 70000, bytes(rng.getrandbits(8) for _ in range(65536)), fq[:65536], b"ACGT" * 16384]
+    for n in [1, 2, 3, 17, 257, 258, 259, 4095, 32768, 65535]:
+        cases.append(bytes(rng.choice(b"ACGTN\n") for _ in range(n)))
+        cases.append(bytes(rng.getrandbits(8) for _ in range(n)))
+        cases.append(bytes(rng.choice(b"ab") for _ in range(n)))
+    for d in cases:
+        for level in (0, 1, 6, 9):
+            for strat in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+                check(d, level, strat)
+    for trial in range(100):
+        c = zlib.compressobj(rng.choice([1, 6, 9]), zlib.DEFLATED, -15, rng.choice([1, 5, 9]),
+                             rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED]))
+        parts, data = [], b""
+        for j in range(rng.randint(1, 6)):
+            al = rng.choice([b"ACGT\n", b"ab", bytes(range(256)), b"ACGTNIIIII@+\n0123456789"])
+            d = bytes(rng.choice(al) for _ in range(rng.choice([0, 1, 10, 300, 5000])))
+            data += d
+            parts.append(c.compress(d))
+            parts.append(c.flush(rng.choice([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH, zlib.Z_NO_FLUSH, zlib.Z_BLOCK])))
+        parts.append(c.flush())
+        comp = b"".join(parts)
+        rc, out = inflate(comp, len(data))
+        assert rc == 0 and out == data
+    c = zlib.compressobj(6, zlib.DEFLATED, -15)
+    base = c.compress(fq[:30000]) + c.flush()
+    rejected = 0
+    for trial in range(1500):
+        b = bytearray(base)
+        for _ in range(rng.randint(1, 4)):
+            b[rng.randrange(len(b))] ^= 1 << rng.randrange(8)
+        if rng.random() < 0.3:
+            b = b[:rng.randrange(1, len(b))]
+        rejected += inflate(bytes(b), 30000)[0] != 0
+    assert rejected > 500
+
+
+def test_bgzf_probe_without_a_device():
+    """BGZF members are recognised from their headers on the host (zb_bgzf_probe); an ordinary .gz is not BGZF"""
+    import gzip
+    from tools import synth
+    from zotmer_b200 import _native as nat
+    from zotmer_b200.library.file import gunzipBytes
+    data = b"@r\nACGT\n+\nIIII\n" * 9000
+    z = synth.bgzf_bytes(data, block=10000)
+    assert gzip.decompress(z) == data and gunzipBytes(z) == data
+    assert nat.bgzf_probe(z) == (len(data) // 10000 + 1 + 1, len(data))
+    assert nat.bgzf_probe(synth.bgzf_bytes(data, eof=False)) == ((len(data) + 65279) // 65280, len(data))
+    assert nat.bgzf_probe(gzip.compress(data)) is None
+    assert nat.bgzf_probe(z[:-1]) is None and nat.bgzf_probe(z + b"\x00" * 40) is None and nat.bgzf_probe(b"") is None

@@ -69,3 +69,22 @@ def mutate(g, rate, seed):
     e = rng.random(len(h)) < rate
     h[e] = ACGT[(np.searchsorted(ACGT, h[e]) + rng.integers(1, 4, int(e.sum()))) & 3]
     return h
+
+
+def bgzf_bytes(data, level=6, block=65280, eof=True, strategy=0):
+    """`data` as bgzip writes it (BGZF, SAM spec 4.1): gzip members of <= 65280 bytes of input, each with a 'BC' extra
+    field holding its total size - 1, closed by the 28-byte empty member."""
+    import struct
+    import zlib
+    out = []
+    pieces = [data[i:i + block] for i in range(0, len(data), block)]
+    if eof:
+        pieces.append(b"")
+    for piece in pieces:
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+        body = c.compress(bytes(piece)) + c.flush()
+        bsize = 12 + 6 + len(body) + 8
+        assert bsize <= 65536
+        out.append(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize - 1) + body +
+                   struct.pack("<II", zlib.crc32(bytes(piece)) & 0xffffffff, len(piece)))
+    return b"".join(out)

@@ -90,6 +90,12 @@ SIGNATURES = {
     "zb_stage_fd": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_size_t, C.POINTER(vp)]),
     "zb_kmerize_feed_staged": (C.c_int, [vp, vp, C.c_int]),
     "zb_staged_free": (C.c_int, [vp]),
+    "zb_bgzf_probe": (C.c_int, [vp, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "zb_stage_bgzf": (C.c_int, [C.c_int, vp, C.c_size_t, C.c_uint64, vp, C.c_uint64, C.POINTER(vp), C.POINTER(C.c_uint64)]),
+    "zb_staged_cut": (C.c_int, [vp, C.c_int, C.POINTER(C.c_uint64)]),
+    "zb_staged_len": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
+    "zb_staged_set_len": (C.c_int, [vp, C.c_uint64]),
+    "zb_staged_fetch": (C.c_int, [vp, vp, C.c_size_t]),
     "zb_set_from_staged": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "zb_set_from_streams_dev": (C.c_int, [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(vp)]),
     "zb_host_count_byte": (C.c_int, [vp, C.c_size_t, C.c_int, u64p]),
@@ -424,6 +430,27 @@ class Staged(object):
             self.h = None
         self.keep = None
 
+    def __len__(self):
+        n = C.c_uint64(0)
+        _check(lib().zb_staged_len(self.h, C.byref(n)))
+        return n.value
+
+    def cut(self, is_fasta):
+        """offset at which the text can be cut at a record boundary (0: nowhere) -- reads.pieces on the device"""
+        n = C.c_uint64(0)
+        _check(lib().zb_staged_cut(self.h, 1 if is_fasta else 0, C.byref(n)))
+        return n.value
+
+    def set_len(self, n):
+        _check(lib().zb_staged_set_len(self.h, int(n)))
+
+    def fetch(self, n=None):
+        """the first n bytes of the piece as it sits on the device (tests)"""
+        n = len(self) if n is None else int(n)
+        out = np.empty(n, dtype=np.uint8)
+        _check(lib().zb_staged_fetch(self.h, _ptr(out), n))
+        return out.tobytes()
+
     def __del__(self):
         try:
             self.free()
@@ -437,6 +464,28 @@ def stage_input(data, device=0):
     h = vp()
     _check(lib().zb_stage_input(device, _ptr(a), len(a), C.byref(h)))
     return Staged(h, (a, data))
+
+
+def bgzf_probe(data):
+    """(members, text bytes) when `data` is a BGZF file (bgzip output: gzip members that carry their own size), else
+    None -- the members are found from their headers, nothing is inflated"""
+    a = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+    if len(a) < 28:
+        return None
+    m, t = C.c_uint64(0), C.c_uint64(0)
+    if lib().zb_bgzf_probe(_ptr(a), len(a), C.byref(m), C.byref(t)) != 0:
+        return None
+    return m.value, t.value
+
+
+def stage_bgzf(data, device=0, max_out=0, carry=None, carry_off=0):
+    """inflate whole BGZF members from the front of `data` ON THE DEVICE into a new staged piece (at most max_out bytes of
+    text, the carried tail of the piece `carry` in front) -> (Staged, compressed bytes consumed)"""
+    a = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+    h, used = vp(), C.c_uint64(0)
+    _check(lib().zb_stage_bgzf(device, _ptr(a), len(a), int(max_out), carry.h if carry is not None else None,
+                               int(carry_off), C.byref(h), C.byref(used)))
+    return Staged(h), used.value
 
 
 def stage_fd(fd, offset, n, device=0):

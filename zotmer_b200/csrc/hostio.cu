@@ -346,6 +346,149 @@ int zb_set_from_staged(zb_staged* kmer_words, zb_staged* count_words, zb_set** o
     return rc;
 }
 
+// ---- block-compressed input (BGZF): members are found on the host, inflated on the device (inflate.cu) -------------
+// Appends the members of raw[0, n) to `tab` until the text would exceed max_out (at least one member is taken).
+// false: raw is not a sequence of BGZF members.
+static bool bgzf_walk(const uint8_t* raw, size_t n, uint64_t max_out, std::vector<BgzfMember>* tab, size_t* used, uint64_t* text) {
+    size_t p = 0;
+    uint64_t out = 0;
+    size_t taken = 0;
+    while (p < n) {
+        if (n - p < 28 || raw[p] != 0x1f || raw[p + 1] != 0x8b || raw[p + 2] != 8 || !(raw[p + 3] & 4)) return false;
+        if (raw[p + 3] & ~4) return false;   // bgzip sets FEXTRA only (no name, comment or header CRC)
+        const size_t xlen = (size_t)raw[p + 10] | ((size_t)raw[p + 11] << 8);
+        if (p + 12 + xlen > n) return false;
+        size_t q = p + 12, bsize = 0;
+        const size_t xend = q + xlen;
+        while (q + 4 <= xend) {
+            const size_t slen = (size_t)raw[q + 2] | ((size_t)raw[q + 3] << 8);
+            if (raw[q] == 'B' && raw[q + 1] == 'C' && slen == 2 && q + 6 <= xend) bsize = ((size_t)raw[q + 4] | ((size_t)raw[q + 5] << 8)) + 1;
+            q += 4 + slen;
+        }
+        if (bsize < xlen + 20 + 2 || p + bsize > n) return false;
+        const uint8_t* t = raw + p + bsize - 4;
+        const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+        if (isize > (1u << 16)) return false;
+        if (taken && out + isize > max_out) break;
+        if (tab) {
+            BgzfMember m;
+            m.src = p + 12 + xlen;
+            m.dst = out;
+            m.clen = (uint32_t)(bsize - xlen - 20);
+            m.isize = isize;
+            tab->push_back(m);
+        }
+        out += isize;
+        taken++;
+        p += bsize;
+    }
+    *used = p;
+    *text = out;
+    return true;
+}
+
+int zb_bgzf_probe(const uint8_t* raw, size_t n, uint64_t* members, uint64_t* text_bytes) {
+    ZB_TRY
+    if (!raw && n) ZB_FAIL(ZB_E_ARG, "null argument");
+    std::vector<BgzfMember> tab;
+    size_t used = 0;
+    uint64_t text = 0;
+    if (n == 0 || !bgzf_walk(raw, n, ~0ull, &tab, &used, &text)) ZB_FAIL(ZB_E_FORMAT, "not a BGZF file");
+    if (members) *members = tab.size();
+    if (text_bytes) *text_bytes = text;
+    ZB_CATCH
+}
+
+int zb_stage_bgzf(int device, const uint8_t* raw, size_t n, uint64_t max_out, zb_staged* carry_from, uint64_t carry_off,
+                  zb_staged** out, uint64_t* n_in_used) {
+    zb_staged* comp = nullptr;
+    zb_staged* res = nullptr;
+    int rc = ZB_OK;
+    try {
+        if (!out || !raw || !n || !n_in_used) ZB_FAIL(ZB_E_ARG, "null argument");
+        Ctx* c = ctx_for(device);
+        if (carry_from && (carry_from->c != c || carry_off > carry_from->n)) ZB_FAIL(ZB_E_ARG, "bad carry");
+        const uint64_t carry_len = carry_from ? carry_from->n - carry_off : 0;
+        const uint64_t limit = ((uint64_t)1 << 31) - 4096;
+        if (max_out == 0 || max_out > limit) max_out = limit;
+        if (carry_len + (1u << 16) > max_out) ZB_FAIL(ZB_E_ARG, "a record of %llu bytes does not fit a piece", (unsigned long long)carry_len);
+        std::vector<BgzfMember> tab;
+        size_t used = 0;
+        uint64_t text = 0;
+        if (!bgzf_walk(raw, n, max_out - carry_len, &tab, &used, &text)) ZB_FAIL(ZB_E_FORMAT, "not a BGZF file");
+        for (auto& m : tab) m.dst += carry_len;
+        // the compressed bytes go through the pinned ring like any input
+        comp = new zb_staged();
+        comp->c = c;
+        comp->n = used;
+        memset(comp->ev, 0, sizeof comp->ev);
+        comp->d.alloc(c, used + 64);
+        stage_jobs(comp, raw, -1, 0, used);
+        res = new zb_staged();
+        res->c = c;
+        res->n = carry_len + text;
+        memset(res->ev, 0, sizeof res->ev);
+        res->d.alloc(c, res->n + 64);
+        DBuf<BgzfMember> d_tab(c, tab.size());
+        DBuf<unsigned int> d_err(c, 4);
+        ZB_CUDA(dev_memset(c, d_err.get(), 0, 16));
+        ZB_CUDA(cudaMemcpyAsync(d_tab.get(), tab.data(), tab.size() * sizeof(BgzfMember), cudaMemcpyHostToDevice, c->stream));
+        if (carry_len) ZB_CUDA(dev_copy(c, res->d.get(), carry_from->d.get() + carry_off, carry_len));
+        staged_wait(comp);
+        bgzf_inflate(c, comp->d.get(), d_tab.get(), (uint32_t)tab.size(), res->d.get(), d_err.get());
+        ZB_CUDA(read_back(c, d_err.get(), 16));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));   // also: `tab` may go out of scope
+        const uint32_t* e = reinterpret_cast<const uint32_t*>(c->h_scalars);
+        if (e[0]) ZB_FAIL(ZB_E_FORMAT, "BGZF member %u of this group does not inflate (code %u; %u members failed)", e[1] - 1, e[2], e[0]);
+        *n_in_used = used;
+    } catch (const zb::Fail& f) {
+        rc = f.code;
+    } catch (const std::bad_alloc&) {
+        zb::set_error("out of host memory");
+        rc = ZB_E_NOMEM;
+    }
+    const std::string keep = rc != ZB_OK ? zb_last_error() : "";
+    if (comp) staged_release(comp);
+    if (rc != ZB_OK) {
+        if (res) staged_release(res);
+        zb::set_error("%s", keep.c_str());
+        return rc;
+    }
+    *out = res;
+    return ZB_OK;
+}
+
+int zb_staged_cut(zb_staged* st, int is_fasta, uint64_t* cut) {
+    ZB_TRY
+    if (!st || !cut) ZB_FAIL(ZB_E_ARG, "null argument");
+    staged_wait(st);
+    *cut = text_cut(st->c, st->d.get(), st->n, is_fasta != 0);
+    ZB_CATCH
+}
+
+int zb_staged_len(const zb_staged* st, uint64_t* n) {
+    ZB_TRY
+    if (!st || !n) ZB_FAIL(ZB_E_ARG, "null argument");
+    *n = st->n;
+    ZB_CATCH
+}
+
+int zb_staged_set_len(zb_staged* st, uint64_t n) {
+    ZB_TRY
+    if (!st || n > st->n) ZB_FAIL(ZB_E_ARG, "bad length");
+    st->n = (size_t)n;
+    ZB_CATCH
+}
+
+int zb_staged_fetch(zb_staged* st, uint8_t* host, size_t n) {
+    ZB_TRY
+    if (!st || (!host && n) || n > st->n) ZB_FAIL(ZB_E_ARG, "bad argument");
+    staged_wait(st);
+    if (n) ZB_CUDA(cudaMemcpyAsync(host, st->d.get(), n, cudaMemcpyDeviceToHost, st->c->stream));
+    ZB_CUDA(cudaStreamSynchronize(st->c->stream));
+    ZB_CATCH
+}
+
 int zb_host_count_byte(const uint8_t* p, size_t n, int byte, uint64_t* count) {
     ZB_TRY
     if (!count || (n && !p)) ZB_FAIL(ZB_E_ARG, "null argument");

@@ -148,6 +148,17 @@ uint64_t allpairs_tiles(int nsets);
 void allpairs_abc(Ctx* c, const std::vector<SetRef>& refs, uint64_t tile_begin, uint64_t tile_end, uint64_t unit_stride,
                   uint64_t* abc_host);
 
+// ---- inflate.cu ------------------------------------------------------------------------------
+// One gzip member of a BGZF file: its raw deflate stream comp[src, src + clen) inflates to out[dst, dst + isize).
+struct BgzfMember {
+    uint64_t src, dst;
+    uint32_t clen, isize;
+};
+// one warp per member; d_err[0] counts the members that failed, [1] = 1 + the first of them, [2] its code
+void bgzf_inflate(Ctx* c, const uint8_t* d_comp, const BgzfMember* d_tab, uint32_t members, uint8_t* d_out, unsigned int* d_err);
+// record-aligned cut of FASTA / FASTQ text on the device (see inflate.cu); 0 = none.  Synchronises.
+uint64_t text_cut(Ctx* c, const uint8_t* d_text, uint64_t n, bool is_fasta);
+
 // ---- parse.cu --------------------------------------------------------------------------------
 // Raw FASTA/FASTQ bytes (device) -> dense base codes (0..3, 4 = break).  `codes` must have room for
 // n + 64 bytes.  Returns number of codes written and the number of records (synchronises).

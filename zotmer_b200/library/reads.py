@@ -78,6 +78,8 @@ def stagedPieces(inputs, device=0, verbose=False, max_piece=MAX_PIECE):
                 print('reading %s (%s)' % (fn, 'FASTA' if fa else 'FASTQ'), file=sys.stderr)
             if plain and 0 < size <= max_piece:
                 yield ('fd', fn, size, fa)
+            elif held is None and fn.endswith('.gz') and os.path.isfile(fn) and _bgzf(fn) is not None:
+                yield ('bgzf', _bgzf(fn), 0, fa)      # block-compressed: inflated on the device, group by group
             else:
                 data = held if held is not None else mapBytes(fn)
                 for piece in pieces(data, fa, max_piece):
@@ -96,9 +98,68 @@ def stagedPieces(inputs, device=0, verbose=False, max_piece=MAX_PIECE):
     it = jobs()
     cur = None
     for job in it:
+        if job[0] == 'bgzf':
+            if cur is not None:
+                yield cur
+                cur = None
+            for st in bgzfPieces(job[1], job[3], device, max_piece):
+                yield st, job[3]
+            continue
         nxt = start(job)
         if cur is not None:
             yield cur
         cur = nxt
     if cur is not None:
         yield cur
+
+
+BGZF_GROUP = 256 << 20   # bytes of text inflated per launch
+
+
+def bgzfPieces(comp, is_fasta, device=0, max_piece=MAX_PIECE, group=None):
+    """Staged pieces of a BGZF file (`comp`: the compressed bytes -- a mapping of the .gz file).  The members are inflated
+    on the device, `group` bytes of text at a time (library zb_stage_bgzf: the compressed bytes cross PCIe, one warp per
+    member); a piece ends at the last record boundary of its group (found on the device, zb_staged_cut) and the
+    incomplete record behind it is carried to the front of the next piece -- what `pieces` does for text in host memory.
+    The inflate of group i + 1 has been issued when piece i is handed out."""
+    import numpy as np
+    from zotmer_b200 import _native
+    group = group or min(BGZF_GROUP, max_piece)
+    a = np.frombuffer(comp, dtype=np.uint8)
+    n, off = len(a), 0
+    st, used = _native.stage_bgzf(a, device, group)
+    off += used
+    while off < n:
+        cut = st.cut(is_fasta)
+        carried = len(st) - cut
+        # cut == 0: one record fills the whole piece so far -- it grows by another group (up to the parser's limit)
+        nxt, used = _native.stage_bgzf(a[off:], device, carried + group, st, cut)
+        off += used
+        if cut:
+            st.set_len(cut)
+            yield st
+        else:
+            st.free()
+        st = nxt
+    yield st
+
+
+_bgzf_cache = {}
+
+
+def _bgzf(fn):
+    """the mapped bytes of `fn` if it is a BGZF file, else None"""
+    import os
+    key = (fn, os.path.getmtime(fn), os.path.getsize(fn))
+    if key not in _bgzf_cache:
+        import mmap
+        from zotmer_b200 import _native
+        _bgzf_cache.clear()
+        res = None
+        if key[2] >= 28:
+            with open(fn, 'rb') as f:
+                m = mmap.mmap(f.fileno(), 0, prot=mmap.PROT_READ)
+            if bytes(m[:4]) == b"\x1f\x8b\x08\x04" and _native.bgzf_probe(m) is not None:
+                res = m
+        _bgzf_cache[key] = res
+    return _bgzf_cache[key]
