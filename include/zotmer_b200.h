@@ -153,8 +153,13 @@ int zb_set_free(zb_set* s);
 int zb_set_stats(const zb_set* s, uint64_t acgt_weighted[4], uint64_t acgt_plain[4], uint64_t* total_count,
                  uint64_t* hist_vals, uint64_t* hist_freqs, size_t hist_cap, size_t* n_hist);
 
-/* N-way union with counts summed -- merge.py:26-86 (merge) + :127-163 (mergeNinto) */
+/* N-way union with counts summed -- merge.py:26-86 (merge) + :127-163 (mergeNinto).
+ * The reference sums Python ints and writes them with codec64 (up to 60 bits): when a sum passes 2^32-1 the result is
+ * a WIDE set -- zb_set_is_wide; its counts come back as u64 through zb_set_fetch_counts64 (zb_set_fetch saturates them
+ * at 2^32-1), zb_set_stats and zb_set_encode* work with the true counts, every other operation on it is ZB_E_RANGE. */
 int zb_merge(int nsets, zb_set* const* sets, zb_set** out);
+int zb_set_is_wide(const zb_set* s, int* wide);
+int zb_set_fetch_counts64(const zb_set* s, uint64_t* counts);   /* any set: its counts as u64 */
 /* keep cmin <= count (and count <= cmax when cmax > 0) -- trim.py:54-62 */
 int zb_trim(const zb_set* s, uint64_t cmin, uint64_t cmax, zb_set** out);
 /* deterministic sub-sampling by k-mer hash, order kept.  mode 0: keep x iff

@@ -70,6 +70,46 @@ def test_merge_file_bytes(zot, tmp_path, out, ins):
     assert o.read_bytes() == rd(out)
 
 
+def test_merge_counts_beyond_u32_file(zot, tmp_path):
+    """`zot merge` of sets whose counts add up past 2^32-1 (the reference adds Python ints, merge.py:145-146, and codec64
+    writes them): the file holds the exact sums, hist / acgt are computed from them"""
+    import numpy as np
+    from oracle import c_oracle as co
+    from oracle import zot_oracle as zo
+    from zotmer_b200.library.kmers import kmers
+    from zotmer_b200.library.files import writeKmersAndCounts2, readWords
+    rng = np.random.default_rng(5)
+    pool = np.unique(rng.integers(0, 2 ** 50, 3000, dtype=np.uint64))
+    sets = []
+    for i in range(3):
+        k = np.sort(rng.choice(pool, 2000, replace=False))
+        k = np.union1d(k, pool[:3])
+        c = rng.integers(1, 50, len(k), dtype=np.uint32)
+        c[np.isin(k, pool[:3])] = np.array([2 ** 32 - 1, 3000000000, 2 ** 31], dtype=np.uint32)
+        sets.append((k, c))
+        with kmers(str(tmp_path / ("w%d.k25" % i)), "w") as z:
+            writeKmersAndCounts2(z, k, c)
+            z.meta["K"] = 25
+            z.meta["kmers"] = "kmers"
+            z.meta["counts"] = "counts"
+    out = tmp_path / "wide.k25"
+    zot("merge", out, *[tmp_path / ("w%d.k25" % i) for i in range(3)])
+    ek, ec = co.merge([(k, c.astype(np.uint64)) for k, c in sets])
+    assert int(ec.max()) == 3 * (2 ** 32 - 1)
+    with kmers(str(out), "r") as z:
+        kw = np.array(readWords(z.open("kmers")), dtype=np.uint64)
+        cw = np.array(readWords(z.open("counts")), dtype=np.uint64)
+        meta = dict(z.meta)
+    assert np.array_equal(kw, co.encode(ek, True)) and np.array_equal(cw, co.encode(ec, False))
+    assert zo.decode([int(w) for w in cw]) == [int(v) for v in ec]
+    want_hist = {}
+    for v in ec:
+        want_hist[int(v)] = want_hist.get(int(v), 0) + 1
+    assert {int(a): b for a, b in meta["hist"].items()} == want_hist
+    tot = float(int(ec.sum()))
+    assert meta["acgt"] == [int(ec[(ek & np.uint64(3)) == np.uint64(b)].sum()) / tot for b in range(4)]
+
+
 def test_merge_behavioural(zot, tmp_path, capsys):
     from zotmer_b200.commands import merge
     with pytest.raises(ZeroDivisionError):

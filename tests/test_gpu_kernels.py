@@ -585,6 +585,46 @@ def test_merge(nat, sizes):
     assert st["acgt_plain"] == [int(((ek & np.uint64(3)) == np.uint64(b)).sum()) for b in range(4)]
 
 
+@pytest.mark.parametrize("route,nsets", [("", 5), ("", 2), ("tree", 3), ("sort", 6), ("", 40)])
+def test_merge_counts_beyond_u32(nat, monkeypatch, route, nsets):
+    """merge.py:56 / :145-146 add Python ints and codec64 carries 60 bits: sums past 2^32-1 come out exact (a WIDE set:
+    u64 counts on fetch, true values in hist / acgt and in the encoded stream), whichever merge route meets them"""
+    if route:
+        monkeypatch.setenv("ZB_MERGE", route)
+    rng = np.random.default_rng(900 + nsets)
+    pool = np.unique(rng.integers(0, 2 ** 50, 60000, dtype=np.uint64))
+    hot = rng.choice(pool, 7, replace=False)          # k-mers every input holds with a huge count
+    sets = []
+    for i in range(nsets):
+        k = np.union1d(np.sort(rng.choice(pool, 20000 + 1000 * (i % 3), replace=False)), hot)
+        c = rng.integers(1, 3000, len(k), dtype=np.uint32)
+        c[np.isin(k, hot)] = rng.integers(2 ** 31, 2 ** 32 - 1, 7, dtype=np.uint64).astype(np.uint32)
+        c[np.isin(k, hot[:1])] = np.uint32(2 ** 32 - 1)
+        if i == 0:
+            c[np.isin(k, hot[1:2])] = np.uint32(2 ** 32 - 2)      # with the 1s below: a sum of exactly 2^32-1 + ...
+        sets.append((k, c))
+    hs = [nat.KmerSet.from_arrays(k, c) for k, c in sets]
+    m = nat.merge(hs)
+    assert m.is_wide()
+    mk, mc = m.fetch()
+    ek, ec = co.merge([(k, c.astype(np.uint64)) for k, c in sets])
+    assert int(ec.max()) > 2 ** 32 and mc.dtype == np.uint64
+    assert np.array_equal(mk, ek) and np.array_equal(mc, ec)
+    st = m.stats()
+    assert st["hist"] == co.hist(ec)
+    assert st["acgt_weighted"] == [int(ec[(ek & np.uint64(3)) == np.uint64(b)].sum()) for b in range(4)]
+    assert st["total"] == int(ec.sum())
+    kw, cw = m.encode()
+    assert np.array_equal(kw, co.encode(ek, True)) and np.array_equal(cw, co.encode(ec, False))
+    with pytest.raises(Exception):
+        m.trim(2)
+    with pytest.raises(Exception):
+        nat.merge([m, hs[0], hs[1]])
+    # sums that stay below 2^32-1 are an ordinary set
+    small = nat.merge(hs[:1] + [nat.KmerSet.from_arrays(sets[0][0][:10], np.ones(10, np.uint32))])
+    assert not small.is_wide()
+
+
 def test_merge_nway_equals_pairwise_tree(nat, monkeypatch):
     """>= 3 inputs are merged bucket by bucket of the key space in shared memory (nwaymerge.cu); it must equal the
     reference-shaped pairwise tree (ZB_MERGE=tree) and the oracle, including counts that add up past 2^16 and empty inputs"""

@@ -64,6 +64,8 @@ SIGNATURES = {
     "zb_set_free": (C.c_int, [vp]),
     "zb_set_stats": (C.c_int, [vp, u64p, u64p, u64p, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "zb_merge": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp)]),
+    "zb_set_is_wide": (C.c_int, [vp, C.POINTER(C.c_int)]),
+    "zb_set_fetch_counts64": (C.c_int, [vp, vp]),
     "zb_trim": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
     "zb_sample": (C.c_int, [vp, C.c_int, C.c_uint64, C.c_double, C.POINTER(vp)]),
     "zb_restrict": (C.c_int, [vp, vp, C.POINTER(vp)]),
@@ -240,10 +242,22 @@ class KmerSet(object):
         n = len(self)
         k = np.empty(n, np.uint64) if out_k is None else out_k[:n]
         c = None
+        if counts and self.is_wide():
+            # a merge whose sums passed 2^32-1 (merge.py:145-146 adds Python ints): the counts come back as u64
+            _check(lib().zb_set_fetch(self.h, _ptr(k), None))
+            c = np.empty(n, np.uint64)
+            _check(lib().zb_set_fetch_counts64(self.h, _ptr(c)))
+            return k, c
         if counts:
             c = np.empty(n, np.uint32) if out_c is None else out_c[:n]
         _check(lib().zb_set_fetch(self.h, _ptr(k), _ptr(c) if counts else None))
         return (k, c) if counts else k
+
+    def is_wide(self):
+        """True when some count exceeds 2^32-1 (only a merge produces such a set)"""
+        w = C.c_int(0)
+        _check(lib().zb_set_is_wide(self.h, C.byref(w)))
+        return bool(w.value)
 
     def dev_ptrs(self):
         a, b = vp(), vp()

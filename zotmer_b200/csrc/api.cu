@@ -553,6 +553,11 @@ int engine_lock_mask() {
 
 }  // namespace zb
 
+// ZB_E_RANGE for a set with counts beyond 2^32-1
+static void no_wide(const zb_set* s, const char* what) {
+    if (s && s->wide.get()) ZB_FAIL(ZB_E_RANGE, "%s: the set holds counts beyond 2^32-1 (only merge output, stats, encode and fetch handle them)", what);
+}
+
 static zb_set* new_set(Ctx* c, size_t n) {
     zb_set* s = new zb_set();
     s->c = c;
@@ -1086,6 +1091,7 @@ int zb_set_lower_bound(const zb_set* s, const uint64_t* probes, size_t m, uint64
 int zb_set_slice(const zb_set* s, size_t begin, size_t end, zb_set** out) {
     ZB_TRY
     if (!s || !out || begin > end || end > s->n) ZB_FAIL(ZB_E_ARG, "bad slice");
+    no_wide(s, "slice");
     Ctx* c = s->c;
     ZB_CUDA(cudaSetDevice(c->device));
     zb_set* r = new_set(c, end - begin);
@@ -1140,9 +1146,30 @@ int zb_set_stats(const zb_set* s, uint64_t acgt_weighted[4], uint64_t acgt_plain
     ZB_CUDA(cudaSetDevice(c->device));
     uint64_t aw[4], ap[4], tot;
     std::vector<std::pair<uint64_t, uint64_t>> hist;
+    std::vector<uint64_t> first;
     {
         EngineLock el(c, ENG_SM);
-        set_stats(c, s->k.get(), s->cnt.get(), s->n, aw, ap, &tot, &hist);
+        set_stats(c, s->k.get(), s->cnt.get(), s->n, aw, ap, &tot, &hist, &first);
+    }
+    if (s->wide.get()) {
+        // the entries the kernel saw as 2^32-1 are exactly the listed ones: their bin goes, their true values come in
+        struct E { uint64_t first, val, freq; };
+        std::vector<E> es;
+        for (size_t i = 0; i < hist.size(); i++)
+            if (hist[i].first != 0xffffffffull) es.push_back(E{first[i], hist[i].first, hist[i].second});
+        std::map<uint64_t, E> add;
+        for (size_t i = 0; i < s->exc_idx.size(); i++) {
+            const uint64_t v = s->exc_val[i];
+            auto it = add.find(v);
+            if (it == add.end()) add[v] = E{s->exc_idx[i], v, 1};   // exc_idx ascends: the first one seen is the first position
+            else it->second.freq++;
+            aw[s->exc_key[i] & 3] += v - 0xffffffffull;
+            tot += v - 0xffffffffull;
+        }
+        for (auto& kv : add) es.push_back(kv.second);
+        std::sort(es.begin(), es.end(), [](const E& a, const E& b) { return a.first < b.first; });
+        hist.clear();
+        for (auto& e : es) hist.push_back({e.val, e.freq});
     }
     for (int q = 0; q < 4; q++) {
         if (acgt_weighted) acgt_weighted[q] = aw[q];
@@ -1159,13 +1186,17 @@ int zb_set_stats(const zb_set* s, uint64_t acgt_weighted[4], uint64_t acgt_plain
     ZB_CATCH
 }
 
-int zb_merge(int nsets, zb_set* const* sets, zb_set** out) {
+// one input of a merge: a set's arrays, or the same keys with other counts (the 16-bit planes of the wide route)
+struct MergeIn {
+    struct K { const uint64_t* p; const uint64_t* get() const { return p; } } k;
+    struct C { const uint32_t* p; const uint32_t* get() const { return p; } } cnt;
+    size_t n;
+    Ctx* c;
+};
+
+static int merge_core(int nsets, const MergeIn* const* sets, zb_set** out) {
     ZB_TRY
-    if (nsets < 1 || !sets || !out) ZB_FAIL(ZB_E_ARG, "bad argument");
     Ctx* c = sets[0]->c;
-    ZB_CUDA(cudaSetDevice(c->device));
-    for (int i = 0; i < nsets; i++)
-        if (!sets[i] || sets[i]->c != c) ZB_FAIL(ZB_E_ARG, "sets must live on one device");
     size_t total = 0;
     for (int i = 0; i < nsets; i++) total += sets[i]->n;
     const char* mm = getenv("ZB_MERGE");
@@ -1263,9 +1294,164 @@ tree:
     ZB_CATCH
 }
 
+// ---- counts beyond 2^32-1 ------------------------------------------------------------------------------------------
+// The reference sums Python ints (merge.py:56, :145-146) and codec64 carries up to 60 bits, so a merge of very deep
+// sets may hold counts that no u32 array can.  Every merge kernel reports such a sum (ZB_E_RANGE); zb_merge then
+// merges the inputs twice more with the low and the high 16 bits of every count as the counts -- each of those sums
+// fits 32 bits for up to 65,536 inputs -- and adds the two results up in 64 bits.
+__global__ void __launch_bounds__(256) count_plane_kernel(const uint32_t* __restrict__ c, size_t n, int shift, uint32_t* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = (c[i] >> shift) & 0xffffu;
+}
+__global__ void __launch_bounds__(256) count_join_kernel(uint32_t* __restrict__ lo_sat, const uint32_t* __restrict__ hi, size_t n,
+                                                         uint64_t* __restrict__ wide, unsigned long long* __restrict__ n_exc,
+                                                         uint64_t* __restrict__ exc_idx, uint64_t exc_cap) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const uint64_t v = (uint64_t)lo_sat[i] + ((uint64_t)hi[i] << 16);
+        wide[i] = v;
+        lo_sat[i] = v >= 0xffffffffull ? 0xffffffffu : (uint32_t)v;
+        if (v >= 0xffffffffull) {
+            const unsigned long long s = atomicAdd(n_exc, 1ull);
+            if (s < exc_cap) exc_idx[s] = i;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) exc_gather_kernel(const uint64_t* __restrict__ idx, size_t m, const uint64_t* __restrict__ k,
+                                                         const uint64_t* __restrict__ wide, uint64_t* __restrict__ out /*[2m]*/) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < m) { out[i] = k[idx[i]]; out[m + i] = wide[idx[i]]; }
+}
+
+
+static int merge_wide(int nsets, zb_set* const* sets, zb_set** out) {
+    ZB_TRY
+    Ctx* c = sets[0]->c;
+    if (nsets > 65536) ZB_FAIL(ZB_E_RANGE, "k-mer count exceeds 2^32-1 in a merge of more than 65,536 sets");
+    size_t total = 0;
+    for (int i = 0; i < nsets; i++) total += sets[i]->n;
+    DBuf<uint32_t> plane(c, total);
+    std::vector<MergeIn> in(nsets);
+    std::vector<const MergeIn*> ptr(nsets);
+    zb_set* part[2] = {nullptr, nullptr};
+    try {
+        for (int p = 0; p < 2; p++) {
+            size_t off = 0;
+            for (int i = 0; i < nsets; i++) {
+                const size_t n = sets[i]->n;
+                if (n) {
+                    const unsigned blocks = (unsigned)std::min<size_t>((size_t)c->sm_count * 8, div_up(n, 256));
+                    count_plane_kernel<<<blocks, 256, 0, c->stream>>>(sets[i]->cnt.get(), n, 16 * p, plane.get() + off);
+                    ZB_LAUNCH_CHECK(c);
+                }
+                in[i].k.p = sets[i]->k.get();
+                in[i].cnt.p = plane.get() + off;
+                in[i].n = n;
+                in[i].c = c;
+                ptr[i] = &in[i];
+                off += n;
+            }
+            if (int rc = merge_core(nsets, ptr.data(), &part[p])) throw zb::Fail{rc};
+        }
+        zb_set* r = part[0];
+        if (part[1]->n != r->n) ZB_FAIL(ZB_E_CUDA, "merge: the two count planes disagree (%zu vs %zu keys)", r->n, part[1]->n);
+        r->wide.alloc(c, r->n);
+        size_t cap = 1 << 16;
+        DBuf<unsigned long long> nexc(c, 2);
+        DBuf<uint64_t> eidx;
+        size_t m = 0;
+        // (the join is idempotent on cnt only the first time: a second attempt re-reads the planes, so keep them apart)
+        DBuf<uint32_t> lo_keep(c, r->n);
+        ZB_CUDA(dev_copy(c, lo_keep.get(), r->cnt.get(), r->n * 4));
+        for (int attempt = 0; attempt < 2; attempt++) {
+            eidx.alloc(c, cap);
+            ZB_CUDA(dev_memset(c, nexc.get(), 0, 16));
+            if (attempt) ZB_CUDA(dev_copy(c, r->cnt.get(), lo_keep.get(), r->n * 4));
+            const unsigned blocks = (unsigned)std::min<size_t>((size_t)c->sm_count * 8, div_up(std::max<size_t>(r->n, 1), 256));
+            count_join_kernel<<<blocks, 256, 0, c->stream>>>(r->cnt.get(), part[1]->cnt.get(), r->n, r->wide.get(), nexc.get(), eidx.get(), cap);
+            ZB_LAUNCH_CHECK(c);
+            ZB_CUDA(read_back(c, nexc.get(), 8));
+            ZB_CUDA(cudaStreamSynchronize(c->stream));
+            m = (size_t)c->h_scalars[0];
+            if (m <= cap) break;
+            cap = m;
+        }
+        r->exc_idx.resize(m);
+        r->exc_key.resize(m);
+        r->exc_val.resize(m);
+        if (m) {
+            ZB_CUDA(cudaMemcpy(r->exc_idx.data(), eidx.get(), m * 8, cudaMemcpyDeviceToHost));
+            std::sort(r->exc_idx.begin(), r->exc_idx.end());
+            ZB_CUDA(cudaMemcpy(eidx.get(), r->exc_idx.data(), m * 8, cudaMemcpyHostToDevice));
+            DBuf<uint64_t> kv(c, 2 * m);
+            exc_gather_kernel<<<(unsigned)div_up(m, 256), 256, 0, c->stream>>>(eidx.get(), m, r->k.get(), r->wide.get(), kv.get());
+            ZB_LAUNCH_CHECK(c);
+            std::vector<uint64_t> h(2 * m);
+            ZB_CUDA(cudaMemcpyAsync(h.data(), kv.get(), 2 * m * 8, cudaMemcpyDeviceToHost, c->stream));
+            ZB_CUDA(cudaStreamSynchronize(c->stream));
+            for (size_t i = 0; i < m; i++) { r->exc_key[i] = h[i]; r->exc_val[i] = h[m + i]; }
+        }
+        zb_set_free(part[1]);
+        part[1] = nullptr;
+        *out = r;
+    } catch (...) {
+        if (part[0]) zb_set_free(part[0]);
+        if (part[1]) zb_set_free(part[1]);
+        throw;
+    }
+    ZB_CATCH
+}
+
+int zb_merge(int nsets, zb_set* const* sets, zb_set** out) {
+    ZB_TRY
+    if (nsets < 1 || !sets || !out) ZB_FAIL(ZB_E_ARG, "bad argument");
+    for (int i = 0; i < nsets; i++)
+        if (!sets[i] || sets[i]->c != sets[0]->c) ZB_FAIL(ZB_E_ARG, "sets must live on one device");
+    Ctx* c = sets[0]->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    std::vector<MergeIn> in(nsets);
+    std::vector<const MergeIn*> ptr(nsets);
+    for (int i = 0; i < nsets; i++) {
+        no_wide(sets[i], "merge input");
+        in[i].k.p = sets[i]->k.get();
+        in[i].cnt.p = sets[i]->cnt.get();
+        in[i].n = sets[i]->n;
+        in[i].c = c;
+        ptr[i] = &in[i];
+    }
+    const int rc = merge_core(nsets, ptr.data(), out);
+    if (rc != ZB_E_RANGE) return rc;
+    return merge_wide(nsets, sets, out);
+    ZB_CATCH
+}
+
+int zb_set_is_wide(const zb_set* s, int* wide) {
+    if (!s || !wide) { zb::set_error("null argument"); return ZB_E_ARG; }
+    *wide = s->wide.get() ? 1 : 0;
+    return ZB_OK;
+}
+
+int zb_set_fetch_counts64(const zb_set* s, uint64_t* counts) {
+    ZB_TRY
+    if (!s || (s->n && !counts)) ZB_FAIL(ZB_E_ARG, "null argument");
+    Ctx* c = s->c;
+    ZB_CUDA(cudaSetDevice(c->device));
+    if (s->n == 0) return ZB_OK;
+    EngineLock el(c, ENG_D2H);
+    if (s->wide.get()) {
+        copy_chunked(c, counts, s->wide.get(), s->n * 8, cudaMemcpyDeviceToHost);
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+        std::vector<uint32_t> t(s->n);
+        copy_chunked(c, t.data(), s->cnt.get(), s->n * 4, cudaMemcpyDeviceToHost);
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < s->n; i++) counts[i] = t[i];
+    }
+    ZB_CATCH
+}
+
 int zb_trim(const zb_set* s, uint64_t cmin, uint64_t cmax, zb_set** out) {
     ZB_TRY
     if (!s || !out) ZB_FAIL(ZB_E_ARG, "null argument");
+    no_wide(s, "trim");
     Ctx* c = s->c;
     ZB_CUDA(cudaSetDevice(c->device));
     zb_set* r = new_set(c, s->n);
@@ -1279,6 +1465,7 @@ int zb_trim(const zb_set* s, uint64_t cmin, uint64_t cmax, zb_set** out) {
 int zb_sample(const zb_set* s, int mode, uint64_t seed, double p, zb_set** out) {
     ZB_TRY
     if (!s || !out || mode < 0 || mode > 1) ZB_FAIL(ZB_E_ARG, "bad argument");
+    no_wide(s, "sample");
     Ctx* c = s->c;
     ZB_CUDA(cudaSetDevice(c->device));
     zb_set* r = new_set(c, s->n);
@@ -1292,6 +1479,7 @@ int zb_restrict(const zb_set* s, const zb_set* ref, zb_set** out) {
     ZB_TRY
     if (!s || !ref || !out) ZB_FAIL(ZB_E_ARG, "null argument");
     if (s->c != ref->c) ZB_FAIL(ZB_E_ARG, "sets must live on one device");
+    no_wide(s, "restrict");
     Ctx* c = s->c;
     ZB_CUDA(cudaSetDevice(c->device));
     zb_set* r = new_set(c, s->n);

@@ -801,6 +801,15 @@ int zb_set_encode_dev(const zb_set* s, zb_words** out) {
             // (k-mer gaps of a 10 M set are ~27 bits: two per word; counts: six per word)
             EncRange rg;
             memset(&rg, 0, sizeof rg);
+            if (s->wide.get()) {
+                // counts beyond 2^32-1 (a merge of very deep sets): both streams through the 64-bit encoder, one after the other
+                w->kw.alloc(c, s->n);
+                w->cw.alloc(c, s->n);
+                w->nk = encode_dev<uint64_t>(c, s->k.get(), s->n, true, w->kw.get());
+                w->nc = encode_dev<uint64_t>(c, s->wide.get(), s->n, false, w->cw.get());
+                *out = w;
+                return ZB_OK;
+            }
             EncodePlan pk, pc;
             encode_plan<uint64_t>(c, s->k.get(), s->n, true, rg, &pk);
             encode_plan<uint32_t>(c, s->cnt.get(), s->n, false, rg, &pc);
@@ -827,6 +836,7 @@ int zb_set_encode_plan(const zb_set* s, uint64_t prev_kmer, const uint64_t* next
     ZB_TRY
     if (!s || !out || !kmer_map || !count_map || n_next < 0 || n_next > 5 || (n_next && (!next_kmers || !next_counts)))
         ZB_FAIL(ZB_E_ARG, "bad argument");
+    if (s->wide.get()) ZB_FAIL(ZB_E_RANGE, "a set with counts beyond 2^32-1 is encoded in one piece (zb_set_encode_dev)");
     Ctx* c = s->c;
     ZB_CUDA(cudaSetDevice(c->device));
     zb_encplan* p = new zb_encplan();

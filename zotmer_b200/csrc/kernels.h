@@ -13,6 +13,11 @@ struct zb_set {
     zb::DBuf<uint64_t> k;
     zb::DBuf<uint32_t> cnt;
     size_t n;
+    // A merge whose sums pass 2^32-1 (merge.py:145-146 adds Python ints) gives a WIDE set: `wide` holds every count as
+    // u64 (what the encoder writes), cnt holds min(count, 2^32-1), and the few entries with cnt == 2^32-1 are listed with
+    // their true counts (ascending position).  Empty for every other set.
+    zb::DBuf<uint64_t> wide;
+    std::vector<uint64_t> exc_idx, exc_key, exc_val;
 };
 
 // the handle behind `zb_words*`: the two packed codec64 streams of a set ('kmers' delta-coded, 'counts'), in HBM
@@ -123,7 +128,8 @@ size_t restrict_pairs(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, 
 size_t project_keys(Ctx* c, const uint64_t* k, size_t n, int shift, uint64_t* ok);
 // Histogram of counts in first-occurrence order + acgt tallies.  kmerize.py:544-545, merge.py:158-159.
 void set_stats(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, uint64_t acgt_w[4], uint64_t acgt_p[4],
-               uint64_t* total, std::vector<std::pair<uint64_t, uint64_t>>* hist_first_order);
+               uint64_t* total, std::vector<std::pair<uint64_t, uint64_t>>* hist_first_order,
+               std::vector<uint64_t>* first_idx = nullptr /* position of the first entry with each count value */);
 void fill_u32(Ctx* c, uint32_t* p, size_t n, uint32_t v);
 void lower_bound(Ctx* c, const uint64_t* keys, size_t n, const uint64_t* h_probe, size_t m, uint64_t* h_idx);
 // Intersection / difference cardinalities for a batch of pairs.  library/dist.py:241-265.

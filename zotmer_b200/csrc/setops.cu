@@ -595,10 +595,11 @@ stats_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt
 }
 
 void set_stats(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, uint64_t acgt_w[4], uint64_t acgt_p[4],
-               uint64_t* total, std::vector<std::pair<uint64_t, uint64_t>>* hist) {
+               uint64_t* total, std::vector<std::pair<uint64_t, uint64_t>>* hist, std::vector<uint64_t>* first_idx) {
     for (int q = 0; q < 4; q++) acgt_w[q] = acgt_p[q] = 0;
     *total = 0;
     hist->clear();
+    if (first_idx) first_idx->clear();
     if (n == 0) return;
     size_t ovf_cap = std::min<size_t>(n, 1u << 20);
     Stage st(c, "stats");
@@ -643,7 +644,10 @@ void set_stats(Ctx* c, const uint64_t* k, const uint32_t* cnt, size_t n, uint64_
             }
         }
         std::sort(es.begin(), es.end(), [](const E& a, const E& b) { return a.first < b.first; });
-        for (auto& e : es) hist->push_back({e.val, e.freq});
+        for (auto& e : es) {
+            hist->push_back({e.val, e.freq});
+            if (first_idx) first_idx->push_back(e.first);
+        }
         return;
     }
     ZB_FAIL(ZB_E_CUDA, "set_stats: overflow list kept growing");
