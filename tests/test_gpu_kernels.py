@@ -646,13 +646,14 @@ def test_merge_nway_equals_pairwise_tree(nat, monkeypatch):
     assert np.array_equal(ak, bk) and np.array_equal(ac, bc)
     ek, ec = co.merge([(k, c.astype(np.uint64)) for k, c in sets])
     assert np.array_equal(ak, ek) and np.array_equal(ac.astype(np.uint64), ec)
-    # a sum beyond 2^32-1 is an error on both paths (the reference's array('I') would overflow)
+    # a sum beyond 2^32-1 comes out exact on every path (merge.py:145-146 adds Python ints; test_merge_counts_beyond_u32)
     big = [nat.KmerSet.from_arrays(np.array([7, 9], np.uint64), np.array([2 ** 31, 1], np.uint32)) for _ in range(4)]
     for mode in (None, "sort", "tree"):
         if mode:
             monkeypatch.setenv("ZB_MERGE", mode)
-        with pytest.raises(IndexError):
-            nat.merge(big)
+        w = nat.merge(big)
+        wk, wc = w.fetch()
+        assert w.is_wide() and wk.tolist() == [7, 9] and wc.tolist() == [2 ** 33, 4]
 
 
 def _merge_all_modes(nat, monkeypatch, sets):
