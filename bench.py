@@ -400,13 +400,16 @@ def run_ours(args, rank, world, local_rank):
 
     trace = [] if os.environ.get("ZB_E2E_TRACE") else None
 
-    def step_e2e(seq, out):
+    def feed_plain(km):
+        km.feed(h_in, False)
+
+    def step_e2e(seq, out, feed=feed_plain):
         torch.cuda.set_device(dev)
         tr = [threading.get_ident() % 1000, time.perf_counter()] if trace is not None else None
         km = nat.Kmerizer(K, dev)
         if p2p is not None:
             p2p.prepare(km)
-        km.feed(h_in, False)
+        feed(km)
         if tr: tr.append(time.perf_counter())
         if p2p is not None:
             p2p.exchange(km, seq=seq, consume=False)
@@ -417,56 +420,65 @@ def run_ours(args, rank, world, local_rank):
             trace.append(tr)
         return r
 
-    warm = min(args.warmup, 2)
-    total_steps = inflight * warm + args.steps
-    base_seq = p2p.step if p2p is not None else 0
-    gate = threading.Barrier(inflight + 1)     # everybody is warm
-    go = threading.Barrier(inflight + 1)       # the per-stage profile has been reset: the timed region starts
-    results = [None] * inflight
-    errors = []
+    def run_e2e(feed):
+        """`args.steps` timed steps (after warm-up) kept `inflight` at a time -> (ms per step, stage profile, result of the
+        last step of one thread, its output buffers)"""
+        warm = min(args.warmup, 2)
+        total_steps = inflight * warm + args.steps
+        base_seq = p2p.step if p2p is not None else 0
+        gate = threading.Barrier(inflight + 1)     # everybody is warm
+        go = threading.Barrier(inflight + 1)       # the per-stage profile has been reset: the timed region starts
+        results = [None] * inflight
+        errors = []
 
-    def worker(i):
-        try:
-            out = make_out()
-            # step numbers: thread i runs i, i + inflight, ... -- the same assignment on every rank
-            seqs = list(range(i, total_steps, inflight))
-            for s_ in seqs[:warm]:
-                step_e2e(base_seq + s_, out)
-            gate.wait()
-            go.wait()
-            r = None
-            for s_ in seqs[warm:]:
-                r = step_e2e(base_seq + s_, out)
-            results[i] = (r, out)
-        except BaseException as e:   # pragma: no cover
-            errors.append(e)
-            for b_ in (gate, go):
-                try:
-                    b_.abort()
-                except Exception:
-                    pass
+        def worker(i):
+            try:
+                out = make_out()
+                # step numbers: thread i runs i, i + inflight, ... -- the same assignment on every rank
+                seqs = list(range(i, total_steps, inflight))
+                for s_ in seqs[:warm]:
+                    step_e2e(base_seq + s_, out, feed)
+                gate.wait()
+                go.wait()
+                r = None
+                for s_ in seqs[warm:]:
+                    r = step_e2e(base_seq + s_, out, feed)
+                results[i] = (r, out)
+            except BaseException as e:   # pragma: no cover
+                errors.append(e)
+                for b_ in (gate, go):
+                    try:
+                        b_.abort()
+                    except Exception:
+                        pass
 
-    nat.dbg_profile(True, dev)
-    ths = [threading.Thread(target=worker, args=(i,)) for i in range(inflight)]
-    for t_ in ths:
-        t_.start()
-    e0 = time.perf_counter()
-    try:
-        gate.wait()
-        barrier()                    # all ranks are warm
-        nat.dbg_profile(True, dev)   # drop the warm-up stages (no worker touches the library between the two barriers)
-        go.wait()
+        nat.dbg_profile(True, dev)
+        ths = [threading.Thread(target=worker, args=(i,)) for i in range(inflight)]
+        for t_ in ths:
+            t_.start()
         e0 = time.perf_counter()
-    except threading.BrokenBarrierError:
-        pass
-    for t_ in ths:
-        t_.join()
-    if errors:
-        raise errors[0]
-    barrier()
-    e2e_ms = (time.perf_counter() - e0) * 1e3 / args.steps
-    e_prof = nat.dbg_profile(False, dev)
-    (e_res, e_out) = [r for r in results if r is not None][0]
+        try:
+            gate.wait()
+            barrier()                    # all ranks are warm
+            nat.dbg_profile(True, dev)   # drop the warm-up stages (no worker touches the library between the two barriers)
+            go.wait()
+            e0 = time.perf_counter()
+        except threading.BrokenBarrierError:
+            pass
+        for t_ in ths:
+            t_.join()
+        if errors:
+            raise errors[0]
+        barrier()
+        ms = (time.perf_counter() - e0) * 1e3 / args.steps
+        pr = nat.dbg_profile(False, dev)
+        outs = [r for r in results if r is not None]
+        for (_, o) in outs[1:]:
+            for b_ in o:
+                b_.free()
+        return (ms, pr) + outs[0]
+
+    (e2e_ms, e_prof, e_res, e_out) = run_e2e(feed_plain)
     clocks = sampler.stop() if rank == 0 else None     # sampled over both timed regions (device-resident and e2e)
     # what the timed e2e steps fetched must be the streams a fresh device-resident step produces (sizes, histogram, words)
     e2e_ok = (e_res[0], e_res[1], e_res[3], e_res[4]) == (n_full, n_trim, wsz, twsz) and e_res[2]["hist"] == st0["hist"]
@@ -498,6 +510,49 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(tl, op=dist.ReduceOp.SUM)
         launches = int(tl[0])
         e2e_ok = int(tl[1]) == world
+    # ---------------- the same end-to-end step fed from BLOCK-COMPRESSED input (what `zot kmerize reads.fq.gz` does for a
+    # bgzip'd file): the compressed bytes cross PCIe, every gzip member is inflated by one warp on the device
+    # (csrc/inflate.cu), the text never exists on the host.  Informational: the headline `e2e` stays the plain-text one.
+    bgzf = None
+    if not args.no_bgzf:
+        from concurrent.futures import ThreadPoolExecutor
+        from tools import synth
+        t0 = time.perf_counter()
+        raw = fq.tobytes()
+        chunk = 65280 * 64
+        with ThreadPoolExecutor(min(16, os.cpu_count() or 4)) as ex:
+            parts = list(ex.map(lambda o: synth.bgzf_bytes(raw[o:o + chunk], level=6, eof=False), range(0, len(raw), chunk)))
+        z = b"".join(parts) + synth.bgzf_bytes(b"")
+        del raw, parts
+        t_comp = time.perf_counter() - t0
+        pin_z = nat.PinnedArray(len(z), np.uint8)
+        pin_z.a[:] = np.frombuffer(z, dtype=np.uint8)
+
+        def feed_bgzf(km):
+            st, _ = nat.stage_bgzf(pin_z.a, dev)
+            km.feed_staged(st, False)
+
+        (g_ms, g_prof, g_res, g_out) = run_e2e(feed_bgzf)
+        g_ok = (g_res[0], g_res[1], g_res[3], g_res[4]) == (n_full, n_trim, wsz, twsz) and g_res[2]["hist"] == st0["hist"] and \
+            np.array_equal(g_out[0].a[:twsz[0]], e_out[0].a[:twsz[0]]) and np.array_equal(g_out[1].a[:twsz[1]], e_out[1].a[:twsz[1]])
+        zbytes = len(z)
+        if world > 1:
+            tg = torch.tensor([g_ms, 0.0 if g_ok else 1.0, float(zbytes)], dtype=torch.float64, device="cuda:%d" % dev)
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            g_ms, g_ok, zbytes = float(tg[0]), float(tg[1]) == 0.0, int(tg[2])
+        bgzf = {"value": bases * world / (g_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": g_ms, "steps_in_flight": inflight,
+                "h2d_bytes_per_step": int(zbytes), "d2h_bytes_per_step": int(8 * sum(twsz)),
+                "inflate_ms_per_step": round(g_prof.get("inflate", (0.0, 0))[0] / args.steps, 3),
+                "result_check": "ok" if g_ok else "MISMATCH",
+                "input": "the rank's FASTQ as BGZF (bgzip framing, zlib level 6: %d -> %d bytes, %.1f s to compress, not timed) in "
+                         "pinned host memory; inflated on the device, one warp per member" % (nbytes, len(z), t_comp)}
+        if rank == 0:
+            print("e2e from BGZF (%d in flight) %.2f ms/step; stage ms/step: %s" % (
+                inflight, g_ms, {k: round(v[0] / args.steps, 3) for k, v in g_prof.items()}), file=sys.stderr)
+        for b_ in g_out:
+            b_.free()
+        pin_z.free()
+        del z
     keys_per_step = stage_keys(nat, dev, d_in, nbytes)
     if p2p is not None:
         p2p.close()
@@ -568,6 +623,8 @@ def run_ours(args, rank, world, local_rank):
         "result": {"distinct_kmers": int(n_full), "after_trim": int(n_trim), "kmer_words": int(wsz[0]), "count_words": int(wsz[1]),
                    "trimmed_kmer_words": int(twsz[0]), "trimmed_count_words": int(twsz[1])},
     }
+    if bgzf is not None:
+        line["e2e_bgzf"] = bgzf
     if parity is not None:
         line["mgpu_parity"] = parity
     if route_ms_dev and "route_p2p" in prof:
@@ -1014,6 +1071,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pairs", action="store_true", help="skip the set-pairs/s measurement (configs[3])")
     ap.add_argument("--no-human", action="store_true", help="skip the human-scale k=31 measurement (configs[4])")
+    ap.add_argument("--no-bgzf", action="store_true", help="skip the end-to-end step fed from block-compressed input")
     ap.add_argument("--no-cli", action="store_true", help="skip the command-level measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -15,7 +15,8 @@ static constexpr int INF_WARPS = 8;
 __global__ void __launch_bounds__(INF_WARPS * 32)
 bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfMember* __restrict__ tab, uint32_t members, uint8_t* out,
                     unsigned int* __restrict__ err /*[0] failures, [1] 1 + first failing member, [2] its code*/) {
-    __shared__ zinf::Scratch scratch[INF_WARPS];
+    extern __shared__ __align__(16) unsigned char inf_raw[];
+    zinf::Scratch* scratch = reinterpret_cast<zinf::Scratch*>(inf_raw);   // [INF_WARPS], 6.5 KB each
     const uint32_t m = blockIdx.x * INF_WARPS + (threadIdx.x >> 5);
     if (m >= members) return;
     const BgzfMember t = tab[m];
@@ -33,7 +34,9 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfMember* __restri
 void bgzf_inflate(Ctx* c, const uint8_t* d_comp, const BgzfMember* d_tab, uint32_t members, uint8_t* d_out, unsigned int* d_err) {
     if (members == 0) return;
     Stage st(c, "inflate");
-    bgzf_inflate_kernel<<<(unsigned)div_up(members, INF_WARPS), INF_WARPS * 32, 0, c->stream>>>(d_comp, d_tab, members, d_out, d_err);
+    const int smem = (int)(INF_WARPS * sizeof(zinf::Scratch));   // 52 KB: four CTAs = 32 warps per SM
+    ZB_CUDA(cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    bgzf_inflate_kernel<<<(unsigned)div_up(members, INF_WARPS), INF_WARPS * 32, smem, c->stream>>>(d_comp, d_tab, members, d_out, d_err);
     ZB_LAUNCH_CHECK(c);
 }
 
