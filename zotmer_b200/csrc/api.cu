@@ -350,6 +350,11 @@ struct zb_kmerizer {
     int owners = 0;                      // zb_kmerize_set_owners: extraction tallies the keys per owner among this many GPUs
     DBuf<unsigned long long> owner_cnt;  // [64] tallies of the pending keys
     bool owner_cnt_valid = false;        // every pending key came through the tallying extraction
+    // digit histograms of the pending keys, tallied by the extraction for the plan the coming sort is EXPECTED to use
+    // (chosen from the size of the first piece of a batch; the sort checks it against its real plan)
+    SortPre pre;
+    DBuf<uint32_t> pre_hist;             // [4][256]
+    bool pre_on = false;                 // every pending key is in pre_hist
 };
 
 static size_t read_pending_count(zb_kmerizer* h) {
@@ -375,6 +380,7 @@ static void ensure_pending(zb_kmerizer* h, size_t need_total) {
 // the pending list has been consumed (routed, bucketed or counted): the owner tallies start again
 static void pending_consumed(zb_kmerizer* h) {
     h->pending_upper = 0;
+    h->pre_on = false;
     ZB_CUDA(dev_memset(h->c, h->d_count.get(), 0, 8));
     if (h->owners > 1) {
         ZB_CUDA(dev_memset(h->c, h->owner_cnt.get(), 0, 64 * 8));
@@ -383,7 +389,7 @@ static void pending_consumed(zb_kmerizer* h) {
 }
 
 // count the pending canonical keys: one more run
-static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n);
+static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n, const SortPre* pre = nullptr);
 static void compact_runs(zb_kmerizer* h);
 
 static void flush_pending(zb_kmerizer* h) {
@@ -397,19 +403,20 @@ static void flush_pending(zb_kmerizer* h) {
     }
     if (h->pending_upper == 0) return;
     const size_t n = read_pending_count(h);
+    const bool pre_on = h->pre_on;
     pending_consumed(h);
-    count_keys(h, h->pending.get(), n);
+    count_keys(h, h->pending.get(), n, pre_on ? &h->pre : nullptr);
     (void)c;
 }
 
 // sort + count `keys` (destroyed) and fold the result into the accumulated run
-static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n) {
+static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n, const SortPre* pre) {
     Ctx* c = h->c;
     if (n == 0) return;
     // sort + count in one go (segsort.cu): distinct canonical keys -> `dk`, counts -> `dc`
     DBuf<uint64_t> tmp(c, n), dk(c, n);
     DBuf<uint32_t> dc(c, n);
-    const size_t nd = sort_count(c, keys, tmp.get(), nullptr, nullptr, n, 2 * h->k, dk.get(), dc.get());
+    const size_t nd = sort_count(c, keys, tmp.get(), nullptr, nullptr, n, 2 * h->k, dk.get(), dc.get(), false, pre);
     tmp.release();
     // the run at its real size (sort_count's outputs are sized for n distinct keys)
     zb_kmerizer::Run r;
@@ -473,7 +480,13 @@ static void compact_runs(zb_kmerizer* h) {
 }
 
 // extraction of a parsed code stream (device buffer with 32-byte front pad and tile tail pad)
-static void extract_codes(zb_kmerizer* h, const uint8_t* codes, size_t n_codes) {
+static bool extract_hist_on() {
+    static const bool on = [] { const char* e = getenv("ZB_EXTRACT_HIST"); return !e || atoi(e) != 0; }();
+    return on;
+}
+
+// keys_hint: how many keys the caller expects these codes to give (0: unknown) -- only used to pick the digit plan
+static void extract_codes(zb_kmerizer* h, const uint8_t* codes, size_t n_codes, size_t keys_hint = 0) {
     Ctx* c = h->c;
     size_t off = 0;
     while (off < n_codes) {
@@ -484,9 +497,21 @@ static void extract_codes(zb_kmerizer* h, const uint8_t* codes, size_t n_codes) 
         // a slice may overshoot into the next tile: bound by whole tiles
         const size_t upper = div_up(len, EXTRACT_TILE) * EXTRACT_TILE;
         ensure_pending(h, h->pending_upper + upper);
+        if (h->pending_upper == 0 && h->owners <= 1 && extract_hist_on()) {
+            // a new batch: the sort that will count it takes its digit histograms from the extraction, for the plan
+            // that fits the number of keys this piece is expected to give
+            const size_t expect = (keys_hint && len == n_codes) ? keys_hint : len;
+            h->pre_on = sort_count_plan(expect, 2 * h->k, &h->pre);
+            if (h->pre_on) {
+                if (!h->pre_hist.get()) h->pre_hist.alloc(c, 4 * 256);
+                h->pre.d_hist = h->pre_hist.get();
+                ZB_CUDA(dev_memset(c, h->pre_hist.get(), 0, 4 * 256 * 4));
+            }
+        }
+        if (h->owners > 1) h->pre_on = false;   // the tallying extraction for several owners keeps no digit histograms
         Stage st(c, "extract");
         extract_canonical(c, h->k, codes + off, len, h->pending.get(), h->d_count.get(), h->owners,
-                          (h->owners > 1 && h->owner_cnt_valid) ? h->owner_cnt.get() : nullptr);
+                          (h->owners > 1 && h->owner_cnt_valid) ? h->owner_cnt.get() : nullptr, h->pre_on ? &h->pre : nullptr);
         h->pending_upper += upper;
         off += len;
     }
@@ -513,7 +538,9 @@ static void feed_dev_impl(zb_kmerizer* h, const uint8_t* d_raw, size_t n, int is
     const size_t padded = div_up(n_codes, EXTRACT_TILE) * EXTRACT_TILE + 32;
     ZB_CUDA(dev_memset(c, cd + n_codes, 4, padded - n_codes));
     if (h->baits) capture_records(c, h->k, cd, n_codes, h->baits->k.get(), h->baits->n);
-    extract_codes(h, cd, n_codes);
+    // every record of L bases gives L - k + 1 windows and one break code (fewer where it holds other letters)
+    const uint64_t lost = n_rec * (uint64_t)h->k;
+    extract_codes(h, cd, n_codes, n_codes > lost ? (size_t)(n_codes - lost) : 1);
 }
 
 namespace zb {
@@ -1035,6 +1062,7 @@ int zb_kmerize_add_canonical_dev(zb_kmerizer* h, const uint64_t* d_keys, size_t 
         const size_t len = std::min(n - off, h->max_pending - have);
         ensure_pending(h, have + len);
         h->owner_cnt_valid = false;   // these keys were not tallied
+        h->pre_on = false;
         ZB_CUDA(dev_copy(c, h->pending.get() + have, d_keys + off, len * 8));
         const unsigned long long nc = have + len;
         c->h_scalars[8] = nc;

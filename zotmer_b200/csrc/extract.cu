@@ -58,10 +58,19 @@ __device__ __forceinline__ int owner_of(uint64_t key, int nranks) {
 
 // OWNERS: the kernel also tallies how many of its keys each of `nranks` owners will get (owner_counts[nranks], global), so
 // that the exchange needs no counting pass over the 1 GB of keys afterwards (0.25 ms of every multi-GPU step)
-template <bool OWNERS>
+// HIST: the kernel also tallies the digits the coming sort will look at (SortPre: up to 4 digits of at most 8 bits) in
+// shared memory and adds them to hist[passes][256] -- the sort then needs no pass over the keys for its histograms
+struct ExHist {
+    int passes;
+    int shift[4];
+    uint32_t mask[4];
+    uint32_t* hist;
+};
+
+template <bool OWNERS, bool HIST>
 __global__ void __launch_bounds__(EX_THREADS)
 extract_kernel(int k, const uint8_t* __restrict__ codes, uint64_t* __restrict__ out,
-               unsigned long long* __restrict__ counter, int nranks, unsigned long long* __restrict__ owner_counts) {
+               unsigned long long* __restrict__ counter, int nranks, unsigned long long* __restrict__ owner_counts, const ExHist eh) {
     __shared__ __align__(128) uint8_t s_codes[EXTRACT_TILE + 32];
     __shared__ uint32_t s_w[EX_THREADS + 2];
     __shared__ uint32_t s_m[EX_THREADS + 2];
@@ -70,9 +79,14 @@ extract_kernel(int k, const uint8_t* __restrict__ codes, uint64_t* __restrict__ 
     __shared__ unsigned long long s_base;
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_own[OWNERS ? 64 : 1];
+    __shared__ uint32_t s_hist[HIST ? 4 * 256 : 1];
 
     const unsigned tid = threadIdx.x;
     if (OWNERS && tid < 64) s_own[tid] = 0;
+    if (HIST) {
+#pragma unroll
+        for (int p = 0; p < 4; p++) s_hist[p * 256 + tid] = 0;
+    }
     const uint8_t* src = codes + (size_t)blockIdx.x * EXTRACT_TILE - 32;  // 16-byte aligned by construction
     if (tid == 0) {
         mbar_init(&s_bar, 1);
@@ -138,6 +152,11 @@ extract_kernel(int k, const uint8_t* __restrict__ codes, uint64_t* __restrict__ 
     for (uint32_t i = tid; i < tot; i += EX_THREADS) {
         const uint64_t kx = s_keys[i];
         out[base + i] = kx;
+        if (HIST) {
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                if (p < eh.passes) atomicAdd(&s_hist[p * 256 + ((uint32_t)(kx >> eh.shift[p]) & eh.mask[p])], 1u);
+        }
         if (OWNERS) {
             const int o = owner_of(kx, nranks);
             if (nranks <= 8) {
@@ -145,6 +164,16 @@ extract_kernel(int k, const uint8_t* __restrict__ codes, uint64_t* __restrict__ 
                 if (o < 4) alo += one; else ahi += one;
             } else {
                 atomicAdd(&s_own[o], 1u);
+            }
+        }
+    }
+    if (HIST) {
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            if (p < eh.passes) {
+                const uint32_t v = s_hist[p * 256 + tid];
+                if (v) atomicAdd(eh.hist + p * 256 + tid, v);
             }
         }
     }
@@ -167,13 +196,25 @@ extract_kernel(int k, const uint8_t* __restrict__ codes, uint64_t* __restrict__ 
 }
 
 void extract_canonical(Ctx* c, int k, const uint8_t* codes, size_t n, uint64_t* out, unsigned long long* d_count, int nranks,
-                       unsigned long long* d_owner_counts) {
+                       unsigned long long* d_owner_counts, const SortPre* pre) {
     if (n == 0) return;
     const unsigned tiles = (unsigned)div_up(n, EXTRACT_TILE);
-    if (nranks > 1 && nranks <= 64 && d_owner_counts)
-        extract_kernel<true><<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count, nranks, d_owner_counts);
-    else
-        extract_kernel<false><<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count, 0, nullptr);
+    ExHist eh;
+    memset(&eh, 0, sizeof eh);
+    if (nranks > 1 && nranks <= 64 && d_owner_counts) {
+        extract_kernel<true, false><<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count, nranks, d_owner_counts, eh);
+    } else if (pre && pre->d_hist && pre->passes >= 1 && pre->passes <= 4) {
+        eh.passes = pre->passes;
+        for (int p = 0; p < pre->passes; p++) {
+            if (pre->bits[p] > 8) ZB_FAIL(ZB_E_ARG, "extract: digits wider than 8 bits");
+            eh.shift[p] = pre->shift[p];
+            eh.mask[p] = (1u << pre->bits[p]) - 1u;
+        }
+        eh.hist = pre->d_hist;
+        extract_kernel<false, true><<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count, 0, nullptr, eh);
+    } else {
+        extract_kernel<false, false><<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count, 0, nullptr, eh);
+    }
     ZB_LAUNCH_CHECK(c);
 }
 

@@ -62,8 +62,19 @@ int radix_sort(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, s
 // Same, but only the bits [lo_bit, lo_bit + nbits) take part (stable): the first stage of sort_count.
 // stable_first = false: equal keys may come out in any order even when a payload is attached (keys-only sorts
 // always take that liberty: it is unobservable) -- the first pass then ranks with one atomic per key.
+// Digit histograms gathered while the keys were PRODUCED (extract.cu tallies them on the way out), so that the sort
+// does not have to read the keys once more for them (sort_hist_kernel: 1 GB and 0.24 ms of a bench step).  The plan is
+// chosen before the number of keys is known; the sort uses the histograms only when its own plan turns out the same.
+struct SortPre {
+    int passes = 0;
+    int shift[4] = {0, 0, 0, 0};
+    int bits[4] = {0, 0, 0, 0};
+    uint32_t* d_hist = nullptr;   // [passes][256] counts; consumed (scanned in place) by the sort that uses them
+};
+// digits of an LSD sort of the bits [lo_bit, lo_bit + nbits) with at most maxbits per pass, lowest first
+int sort_digit_plan(int lo_bit, int nbits, int maxbits, int* shift, int* bits, int max_passes);
 int radix_sort_range(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int lo_bit, int nbits,
-                     bool stable_first = true);
+                     bool stable_first = true, const SortPre* pre = nullptr);
 extern int g_sort_max_bits;
 extern int g_sort_cfg;   // onesweep CTA shape, see sort.cu  // digit width cap (8..11), tunable from bench via ZB_SORT_BITS
 
@@ -77,7 +88,9 @@ extern int g_sort_cfg;   // onesweep CTA shape, see sort.cu  // digit width cap 
 // distinct = true: the caller guarantees that no key occurs twice (v0 is then a payload that is carried along);
 // a violation is detected and reported as ZB_E_ARG.
 size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
-                  uint64_t* out_k, uint32_t* out_c, bool distinct = false);
+                  uint64_t* out_k, uint32_t* out_c, bool distinct = false, const SortPre* pre = nullptr);
+// the digit plan sort_count's bucket route will use for n keys of key_bits bits (false: none -- tiny inputs, wide digits)
+bool sort_count_plan(size_t n, int key_bits, SortPre* plan);
 // The both-strand set of kmerize: the sorted canonical counted set (ck, cc, n) united with its nm mirrored pairs
 // (mk, mc: distinct, disjoint from ck, unordered; destroyed, mk2 / mc2 are scratch) into out_k / out_c (n + nm entries).
 // Returns false when the key space is too skewed for its buckets; M is then still complete in mk/mc (which_out = 0) or
@@ -183,8 +196,9 @@ void parse_fasta(Ctx* c, const uint8_t* raw, size_t n, uint8_t* codes, size_t* n
 // basics.py:303-347.
 static const int EXTRACT_TILE = 4096;
 // nranks > 1 with d_owner_counts: also adds to d_owner_counts[o] the number of emitted keys whose owner is o.
+// pre: also adds the keys' digits to pre->d_hist (see SortPre).
 void extract_canonical(Ctx* c, int k, const uint8_t* codes, size_t n, uint64_t* out, unsigned long long* d_count, int nranks = 0,
-                       unsigned long long* d_owner_counts = nullptr);
+                       unsigned long long* d_owner_counts = nullptr, const SortPre* pre = nullptr);
 // `zot kmerize -C` (kmerize.py:478-483, :507-517): a record is kept, whole, iff one of its k-mers (either strand) is in
 // the bait set; every other record of the code stream (records delimited by code 5, see parse_*) is blanked out.
 // baits: sorted k-mers closed under reverse complement (a both-strand kmerize of the bait FASTA).

@@ -751,17 +751,32 @@ __global__ void big_bucket_ranges_kernel(const uint32_t* __restrict__ big_list, 
     big_len[i] = start[b + 1] - start[b];
 }
 
-static size_t sort_count_buckets(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
-                                 uint64_t* out_k, uint32_t* out_c, bool distinct) {
-    const bool weighted = (v0 != nullptr);
+// top key bits the LSD passes of the bucket route put in order: buckets of at most ~BC_CAP / 2 keys on average
+static int bucket_top_bits(size_t n, int key_bits) {
     int cb = 0;
     while (cb < key_bits && (n >> cb) > (size_t)BC_CAP / 2) cb++;
+    return cb;
+}
+
+bool sort_count_plan(size_t n, int key_bits, SortPre* plan) {
+    if (key_bits < 1) key_bits = 1;
+    if (key_bits > 64) key_bits = 64;
+    const int cb = bucket_top_bits(n, key_bits);
+    if (cb == 0 || g_sort_max_bits > 8 || g_sort_count_mode != 0) return false;
+    plan->passes = sort_digit_plan(key_bits - cb, cb, 8, plan->shift, plan->bits, 4);
+    return plan->passes > 0;
+}
+
+static size_t sort_count_buckets(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
+                                 uint64_t* out_k, uint32_t* out_c, bool distinct, const SortPre* pre) {
+    const bool weighted = (v0 != nullptr);
+    const int cb = bucket_top_bits(n, key_bits);
     const uint32_t nb = 1u << cb;
     const int shift = key_bits - cb;
     int which = 0;
     if (cb > 0) {
         Stage st(c, "sort");
-        which = radix_sort_range(c, k0, k1, v0, v1, n, shift, cb, false);
+        which = radix_sort_range(c, k0, k1, v0, v1, n, shift, cb, false, pre);
     }
     const uint64_t* sk = which ? k1 : k0;
     const uint32_t* sv = weighted ? (which ? v1 : v0) : nullptr;
@@ -1025,7 +1040,7 @@ bool merge_mirrored(Ctx* c, const uint64_t* ck, const uint32_t* cc, size_t n, ui
 // g_sort_count_mode (ZB_SORT_COUNT): 0 = bucket route (weighted sums: segment route), 1 = classic full sort +
 // reduce-by-key, 2 = segment route
 size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits,
-                  uint64_t* out_k, uint32_t* out_c, bool distinct) {
+                  uint64_t* out_k, uint32_t* out_c, bool distinct, const SortPre* pre) {
     if (n == 0) return 0;
     if (distinct && !v0) ZB_FAIL(ZB_E_ARG, "sort_count: distinct mode needs a payload");
     if (key_bits < 1) key_bits = 1;
@@ -1036,7 +1051,7 @@ size_t sort_count(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1
     const bool aligned = (((uintptr_t)k0 | (uintptr_t)k1) & 15) == 0;
     if (g_sort_count_mode == 2 || weighted_sum || !aligned)
         return sort_count_segsort(c, k0, k1, v0, v1, n, key_bits, out_k, out_c, distinct);
-    return sort_count_buckets(c, k0, k1, v0, v1, n, key_bits, out_k, out_c, distinct);
+    return sort_count_buckets(c, k0, k1, v0, v1, n, key_bits, out_k, out_c, distinct, pre);
 }
 
 }  // namespace zb

@@ -337,32 +337,42 @@ static size_t onesweep_smem(bool vals) {
     return (size_t)SORT_TILE * 8 + (vals ? (size_t)SORT_TILE * 4 : 0) + (size_t)SORT_WARPS * BINS * 4 + BINS * 4;
 }
 
+int sort_digit_plan(int lo_bit, int nbits, int maxbits, int* shift, int* bits, int max_passes) {
+    int passes = (nbits + maxbits - 1) / maxbits;
+    if (passes < 1) passes = 1;
+    if (passes > max_passes) return -passes;
+    int base = nbits / passes, rem = nbits % passes, sh = lo_bit;
+    for (int p = 0; p < passes; p++) {
+        bits[p] = base + (p < rem ? 1 : 0);
+        if (bits[p] < 1) bits[p] = 1;
+        shift[p] = sh;
+        sh += bits[p];
+    }
+    return passes;
+}
+
 template <int BINS, int SORT_THREADS, int SORT_ITEMS>
 static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int lo_bit,
-                           int key_bits, int maxbits, bool stable_first) {
+                           int key_bits, int maxbits, bool stable_first, const SortPre* pre) {
     SortPlan plan;
-    plan.passes = (key_bits + maxbits - 1) / maxbits;
-    if (plan.passes < 1) plan.passes = 1;
-    if (plan.passes > MAX_PASSES) ZB_FAIL(ZB_E_ARG, "radix_sort: %d passes needed (max %d)", plan.passes, MAX_PASSES);
-    {
-        int base = key_bits / plan.passes, rem = key_bits % plan.passes, sh = lo_bit;
-        for (int p = 0; p < plan.passes; p++) {
-            plan.bits[p] = base + (p < rem ? 1 : 0);
-            if (plan.bits[p] < 1) plan.bits[p] = 1;
-            plan.shift[p] = sh;
-            sh += plan.bits[p];
-        }
-    }
+    plan.passes = sort_digit_plan(lo_bit, key_bits, maxbits, plan.shift, plan.bits, MAX_PASSES);
+    if (plan.passes < 0) ZB_FAIL(ZB_E_ARG, "radix_sort: %d passes needed (max %d)", -plan.passes, MAX_PASSES);
+    // histograms that came with the keys (extract.cu) are used when they were taken for exactly this plan
+    bool have_hist = pre && pre->d_hist && BINS == 256 && pre->passes == plan.passes;
+    for (int p = 0; have_hist && p < plan.passes; p++) have_hist = pre->shift[p] == plan.shift[p] && pre->bits[p] == plan.bits[p];
     constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     const bool vals = (v0 != nullptr);
     const uint32_t tiles = (uint32_t)div_up(n, SORT_TILE);
     DBuf<uint32_t> ghist(c, (size_t)plan.passes * BINS);
     DBuf<uint32_t> status(c, (size_t)tiles * BINS);
     DBuf<uint32_t> ticket(c, MAX_PASSES);
-    ZB_CUDA(dev_memset(c, ghist.get(), 0, (size_t)plan.passes * BINS * 4));
     ZB_CUDA(dev_memset(c, ticket.get(), 0, MAX_PASSES * 4));
-
-    {
+    if (have_hist) {
+        ZB_CUDA(dev_copy(c, ghist.get(), pre->d_hist, (size_t)plan.passes * BINS * 4));
+        sort_scan_kernel<BINS><<<plan.passes, (BINS > 1024 ? 1024 : BINS), 0, c->stream>>>(ghist.get());
+        ZB_LAUNCH_CHECK(c);
+    } else {
+        ZB_CUDA(dev_memset(c, ghist.get(), 0, (size_t)plan.passes * BINS * 4));
         Stage st_h(c, "sort_hist");
         int blocks = (int)std::min<size_t>((size_t)c->sm_count * 4, div_up(n, 512 * 2 * 4));
         if (blocks < 1) blocks = 1;
@@ -414,7 +424,7 @@ static int radix_sort_impl(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uin
 }
 
 int radix_sort_range(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int lo_bit, int nbits,
-                     bool stable_first) {
+                     bool stable_first, const SortPre* pre) {
     if (n == 0) return 0;
     if (n >= (1ull << 30)) ZB_FAIL(ZB_E_ARG, "radix_sort: n=%zu exceeds 2^30 keys per batch", n);
     if (lo_bit < 0) lo_bit = 0;
@@ -422,11 +432,11 @@ int radix_sort_range(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t*
     if (nbits < 1) nbits = 1;
     if (lo_bit + nbits > 64) nbits = 64 - lo_bit;
     int mb = g_sort_max_bits;
-    if (mb <= 8 && g_sort_cfg == 1) return radix_sort_impl<256, 512, 8>(c, k0, k1, v0, v1, n, lo_bit, nbits, 8, stable_first);
-    if (mb <= 8) return radix_sort_impl<256, 256, 16>(c, k0, k1, v0, v1, n, lo_bit, nbits, 8, stable_first);
-    if (mb == 9) return radix_sort_impl<512, 512, 16>(c, k0, k1, v0, v1, n, lo_bit, nbits, 9, stable_first);
-    if (mb == 10) return radix_sort_impl<1024, 512, 16>(c, k0, k1, v0, v1, n, lo_bit, nbits, 10, stable_first);
-    return radix_sort_impl<2048, 512, 16>(c, k0, k1, v0, v1, n, lo_bit, nbits, 11, stable_first);
+    if (mb <= 8 && g_sort_cfg == 1) return radix_sort_impl<256, 512, 8>(c, k0, k1, v0, v1, n, lo_bit, nbits, 8, stable_first, pre);
+    if (mb <= 8) return radix_sort_impl<256, 256, 16>(c, k0, k1, v0, v1, n, lo_bit, nbits, 8, stable_first, pre);
+    if (mb == 9) return radix_sort_impl<512, 512, 16>(c, k0, k1, v0, v1, n, lo_bit, nbits, 9, stable_first, nullptr);
+    if (mb == 10) return radix_sort_impl<1024, 512, 16>(c, k0, k1, v0, v1, n, lo_bit, nbits, 10, stable_first, nullptr);
+    return radix_sort_impl<2048, 512, 16>(c, k0, k1, v0, v1, n, lo_bit, nbits, 11, stable_first, nullptr);
 }
 
 int radix_sort(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, size_t n, int key_bits) {
