@@ -486,11 +486,7 @@ bc_bounds_kernel(const uint64_t* __restrict__ keys, uint64_t n, int shift, uint3
 // Persistent: a CTA takes buckets blockIdx.x, + gridDim.x, ... and, while it works on one, the TMA engine copies
 // the keys of its next one into the other half of a double buffer (one cp.async.bulk per bucket, completion on an
 // mbarrier) -- the first version loaded a bucket with plain loads and then spent 34 % of its time waiting for them.
-// DENSE (MODE 0): a key that becomes the head of its value appends its table slot to a list, and the phases that follow
-// the dedupe walk that list -- ~300 heads among the ~1,900 keys of a bucket at 30x coverage -- instead of every
-// thread's item slots, where nearly every warp found a head in every slot and ran the head path for 16 % of its lanes
-// (profiles/r01_ncu_bucket_count.txt: a quarter of the kernel's instructions).
-template <int MODE, bool DENSE>
+template <int MODE>
 __global__ void __launch_bounds__(BC_THREADS, 2)
 bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ w, const uint64_t* __restrict__ start,
                     uint32_t nb, int shift, int fine_shift, uint32_t fine_mask, uint64_t* __restrict__ tmp_k,
@@ -502,8 +498,6 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
     uint32_t* table = reinterpret_cast<uint32_t*>(buf0 + 2 * (BC_CAP + 2));   // [BC_HASH]
     uint32_t* hist = table + BC_HASH;                                    // [BC_FINE + 1]
     uint64_t* hs = reinterpret_cast<uint64_t*>(table);                   // [BC_CAP] heads grouped by fine digit (after the dedupe)
-    uint16_t* hl = reinterpret_cast<uint16_t*>(hist + BC_FINE + 2);      // [BC_CAP] table slots of the heads, in arrival order (DENSE)
-    __shared__ uint32_t s_nh;
     __shared__ uint32_t s_scan[BC_THREADS / 32 + 1];
     __shared__ uint32_t s_sub[16];
     __shared__ uint32_t s_cnt;
@@ -588,7 +582,6 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
             }
 #pragma unroll
             for (int j = 0; j < FINE / BC_THREADS; j++) hist[j * BC_THREADS + tid] = 0;
-            if (DENSE && tid == 0) s_nh = 0;
             uint64_t kx[BC_PER];
             uint32_t wx[BC_PER];
             int m;
@@ -662,11 +655,7 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
                         uint32_t h = (uint32_t)((x * 0x9E3779B97F4A7C15ull) >> (64 - BC_HASH_BITS));
                         while (true) {
                             const uint32_t old = atomicCAS(&table[h], SS_EMPTY, (uint32_t)q | 0x10000u);
-                            if (old == SS_EMPTY) {
-                                if (DENSE) hl[atomicAdd(&s_nh, 1u)] = (uint16_t)h;
-                                else { headbits |= 1u << j; wx[j] = h; }
-                                break;
-                            }
+                            if (old == SS_EMPTY) { headbits |= 1u << j; wx[j] = h; break; }
                             if (sk[old & 0xffffu] == x) { atomicAdd(&table[h], 0x10000u); break; }
                             h = (h + 1) & (BC_HASH - 1);
                         }
@@ -677,26 +666,6 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
 
             // ---- heads: counting sort by the next key bits (rank inside a group = arrival order, fixed up below)
             uint32_t rd[BC_PER];
-            int hn = jn;   // item slots that may hold a head
-            if (DENSE) {
-                // the heads come from the list: slot u of a thread is head number u * BC_THREADS + tid
-                const int nh = (int)s_nh;
-                hn = (nh + BC_THREADS - 1) / BC_THREADS;
-                headbits = 0;
-#pragma unroll
-                for (int u = 0; u < BC_PER; u++) {
-                    if (u >= hn) break;
-                    const int p = u * BC_THREADS + (int)tid;
-                    if (p < nh) {
-                        const uint32_t e = table[hl[p]];
-                        kx[u] = sk[e & 0xffffu];
-                        wx[u] = e >> 16;
-                        headbits |= 1u << u;
-                        const uint32_t d = (uint32_t)(kx[u] >> fine_shift) & fine_mask;
-                        rd[u] = atomicAdd(&hist[d], 1u) | (d << 16);
-                    }
-                }
-            } else {
 #pragma unroll
             for (int j = 0; j < BC_PER; j++) {
                 if (j >= jn) break;
@@ -705,7 +674,6 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
                     rd[j] = atomicAdd(&hist[d], 1u) | (d << 16);
                     if (!DISTINCT) wx[j] = table[wx[j]] >> 16;
                 }
-            }
             }
             __syncthreads();
             {   // exclusive scan of the group sizes
@@ -723,7 +691,7 @@ bucket_count_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < BC_PER; j++) {
-                if (j >= hn) break;
+                if (j >= jn) break;
                 if ((headbits >> j) & 1u) {
                     const uint32_t p = hist[rd[j] >> 16] + (rd[j] & 0xffffu);
                     hs[p] = kx[j];
@@ -825,8 +793,7 @@ static size_t sort_count_buckets(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v
     uint64_t* totals = tile_off.get() + nb;                                          // [0] distinct, [1] big buckets
     unsigned int* err = reinterpret_cast<unsigned int*>(totals + 2);
     ZB_CUDA(dev_memset(c, totals, 0, 32));
-    const size_t smem = (size_t)2 * (BC_CAP + 2) * 8 + (size_t)BC_HASH * 4 + (size_t)(BC_FINE + 2) * 4 + (size_t)BC_CAP * 2;
-    static const bool dense = [] { const char* e = getenv("ZB_BC_DENSE"); return !e || atoi(e) != 0; }();
+    const size_t smem = (size_t)2 * (BC_CAP + 2) * 8 + (size_t)BC_HASH * 4 + (size_t)(BC_FINE + 1) * 4;
     const unsigned grid = (unsigned)std::min<size_t>(nb, (size_t)c->sm_count * 2);   // persistent: 2 CTAs per SM
     {
         Stage st(c, "segcount");
@@ -834,17 +801,13 @@ static size_t sort_count_buckets(Ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v
         ZB_LAUNCH_CHECK(c);
         unsigned long long* bign = reinterpret_cast<unsigned long long*>(totals + 1);
         if (distinct) {
-            ZB_CUDA(cudaFuncSetAttribute(bucket_count_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            bucket_count_kernel<2, false><<<grid, BC_THREADS, smem, c->stream>>>(sk, sv, start.get(), nb, shift, fine_shift, fine_mask, tmp_k.get(),
-                                                                               tmp_c.get(), tile_heads.get(), bign, big_list.get(), err);
-        } else if (dense) {
-            ZB_CUDA(cudaFuncSetAttribute(bucket_count_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            bucket_count_kernel<0, true><<<grid, BC_THREADS, smem, c->stream>>>(sk, nullptr, start.get(), nb, shift, fine_shift, fine_mask, tmp_k.get(),
-                                                                              tmp_c.get(), tile_heads.get(), bign, big_list.get(), err);
+            ZB_CUDA(cudaFuncSetAttribute(bucket_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            bucket_count_kernel<2><<<grid, BC_THREADS, smem, c->stream>>>(sk, sv, start.get(), nb, shift, fine_shift, fine_mask, tmp_k.get(),
+                                                                        tmp_c.get(), tile_heads.get(), bign, big_list.get(), err);
         } else {
-            ZB_CUDA(cudaFuncSetAttribute(bucket_count_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            bucket_count_kernel<0, false><<<grid, BC_THREADS, smem, c->stream>>>(sk, nullptr, start.get(), nb, shift, fine_shift, fine_mask, tmp_k.get(),
-                                                                               tmp_c.get(), tile_heads.get(), bign, big_list.get(), err);
+            ZB_CUDA(cudaFuncSetAttribute(bucket_count_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            bucket_count_kernel<0><<<grid, BC_THREADS, smem, c->stream>>>(sk, nullptr, start.get(), nb, shift, fine_shift, fine_mask, tmp_k.get(),
+                                                                        tmp_c.get(), tile_heads.get(), bign, big_list.get(), err);
         }
         ZB_LAUNCH_CHECK(c);
         segscan_kernel<<<1, 1024, 0, c->stream>>>(tile_heads.get(), nb, tile_off.get(), totals);
