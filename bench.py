@@ -10,7 +10,11 @@ Headline workload (`value`, `e2e`): BASELINE.json configs[1] -- synthetic 30x 15
 the hot path over the whole read set of a rank, doing what `zot kmerize` + `zot trim` do up to the file write (and what
 the reference arm does on the CPU): parse, extract both strands, sort, count, count histogram + acgt tallies, codec64
 (+ delta) encode of the counted set, trim, codec64 encode of the trimmed set -- all through the C ABI.
-  value : FASTQ text already resident in HBM (zb_kmerize_feed_dev), results left in HBM; CUDA events.
+  value : FASTQ text already resident in HBM (zb_kmerize_feed_dev), results left in HBM; CUDA events.  Measured twice over
+          the same K steps: one after the other on one stream (`one_in_flight`: the region the per-stage times and the
+          `roofline` of the kernels come from), and with several steps in flight, one host thread and one stream each --
+          the host round trips of a step and, at N > 1, its exchange over NVLink then run under the kernels of the others.
+          `value` is the faster of the two (`steps_in_flight` says which); every step does the whole work either way.
   e2e   : FASTQ text in pinned HOST memory (zb_kmerize_feed), the encoded word streams of the trimmed set fetched into
           pinned host memory (zb_words_fetch) -- the bytes `zot trim` would write -- H2D and D2H inside the timed region;
           several steps in flight (one host thread each), at N > 1 as well: exchanges are issued in step order.
@@ -18,6 +22,8 @@ N > 1 (weak scaling): every rank kmerizes its own 1M-read shard, routes each can
 bits of a 64-bit mix) with one fused routing kernel that stores into the owner's buffer over NVLink peer memory, and
 sorts / counts / trims its disjoint share.  Before anything is timed the ranks run a small multi-GPU kmerize (k = 25 and
 k = 31) and compare the union of their shares with the oracle, bit for bit (`mgpu_parity`).
+  e2e_bgzf : the e2e step fed from the same reads as a bgzip'd file (BGZF) in pinned host memory: the compressed bytes
+          cross PCIe and are inflated on the device (informational; `e2e` and the reference arm read plain text).
 Further objects of the JSON line (each skippable): `human` = configs[4]'s per-GPU shape (375 Mbp of genome, 75 M reads,
 k = 31; reads generated on the device); `pairs` = configs[3] (all pairs of 1,000 sets, 499,500 pairs); `cli` = the
 `zot kmerize` command itself, FASTQ file in -> k-mer set file out, wall clock.
@@ -330,7 +336,7 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     p2p = None
     parity = None
-    inflight = int(os.environ.get("ZB_E2E_INFLIGHT", 4 if world == 1 else 3))
+    inflight = int(os.environ.get("ZB_E2E_INFLIGHT", 6))   # measured: r3_bench6_f*.json (N = 1), r3_bench_n2_f*.json (N = 2)
     if world > 1:
         import torch.distributed as dist
         from zotmer_b200 import multigpu
