@@ -123,6 +123,7 @@ cudaError_t dev_copy(Ctx* c, void* dst, const void* src, size_t bytes);
 void* dalloc(Ctx* c, size_t bytes);
 void dfree(Ctx* c, void* p);
 void dtrim(Ctx* c);  // give every cached block back to the driver
+void dshrink(Ctx* c, void* p, size_t bytes);  // keep the first `bytes` of a block, free the rest (no copy)
 
 // RAII device buffer bound to a context's stream/pool
 template <typename T>
@@ -142,6 +143,7 @@ struct DBuf {
     ~DBuf() { release(); }
     void release() { if (p) { dfree(c, p); p = nullptr; n = 0; } }
     void alloc(Ctx* c_, size_t n_) { release(); c = c_; n = n_; p = (T*)dalloc(c, n * sizeof(T)); }
+    void shrink(size_t n_) { if (p && n_ < n) { dshrink(c, p, n_ * sizeof(T)); n = n_; } }
     T* get() const { return p; }
 };
 
