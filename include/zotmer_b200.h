@@ -275,6 +275,14 @@ int zb_staged_cut(zb_staged* st, int is_fasta, uint64_t* cut);
 int zb_staged_len(const zb_staged* st, uint64_t* n);
 int zb_staged_set_len(zb_staged* st, uint64_t n);
 int zb_staged_fetch(zb_staged* st, uint8_t* host, size_t n);
+/* Several devices inflate one BGZF file (library/devices.py): zb_bgzf_groups cuts the file into runs of whole members of
+ * at most max_text bytes of text (starts[i] = compressed offset of group i; *n_groups may exceed cap: call again);
+ * every device inflates its group with zb_stage_bgzf, then, in file order, puts the incomplete record the previous
+ * group left behind in front of its text (zb_stage_concat: host prefix + a staged piece -> a new piece, consumes the
+ * piece), finds its own cut (zb_staged_cut) and hands the bytes behind it on (zb_staged_fetch_range). */
+int zb_bgzf_groups(const uint8_t* raw, size_t n, uint64_t max_text, uint64_t* starts, size_t cap, size_t* n_groups);
+int zb_stage_concat(int device, const uint8_t* prefix, size_t prefix_len, zb_staged* body, zb_staged** out);
+int zb_staged_fetch_range(zb_staged* st, uint64_t off, uint8_t* host, size_t n);
 
 /* pinned host memory from the library's arena (cudaHostAlloc, cached): destinations of zb_words_fetch / zb_set_fetch */
 int zb_host_alloc(size_t bytes, void** p);

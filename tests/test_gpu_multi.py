@@ -74,3 +74,39 @@ def test_cli_kmerize_two_gpus_equals_one_at_size(tmp_path, monkeypatch):
         outs[ngpu] = o.read_bytes()
     assert outs[1] == outs[2]
     assert len(outs[1]) > 10000000
+
+
+@pytest.mark.parametrize("ngpu", [2, 4])
+def test_cli_kmerize_bgzf_on_several_gpus(ngpu, tmp_path, monkeypatch):
+    """block-compressed inputs on several GPUs: every device inflates a run of members, the incomplete record behind a
+    run's last record boundary is handed to the device that holds the next run (library/devices.py:_stageBgzfGroup);
+    the file is the golden one / the one a single GPU writes from the plain text"""
+    from zotmer_b200 import _native, cli
+    from zotmer_b200.library import reads
+    from tools import synth
+    if _native.device_count() < ngpu:
+        pytest.skip("needs %d GPUs" % ngpu)
+    golden = os.path.join(ROOT, "tests", "golden", "data")
+    monkeypatch.setenv("ZB_GPUS", str(ngpu))
+    for k, out, src in ((25, "r1.k25", "r1.fq"), (31, "r1.k31", "r1.fq"), (25, "g1.k25", "g1.fa")):
+        data = open(os.path.join(golden, src), "rb").read()
+        for block in (700, 65280):
+            gz = tmp_path / (src + ".gz")
+            gz.write_bytes(synth.bgzf_bytes(data, block=block))
+            o = tmp_path / out
+            cli.main(["kmerize", str(k), str(o), str(gz)])
+            with open(os.path.join(golden, out), "rb") as f:
+                assert o.read_bytes() == f.read(), (ngpu, out, block)
+    # at size: several rounds of groups per device (1 MiB of text per group), FASTQ + FASTA + a plain file in one call
+    g = synth.genome(1200000, seed=21)
+    fq = synth.fastq_array(g, 60000, seed=22).reshape(-1).tobytes()
+    fa = synth.fasta_bytes(g) + b">p2 x\n" + synth.fasta_bytes(synth.genome(300000, seed=23))[6:]
+    (tmp_path / "a.fq").write_bytes(fq)
+    (tmp_path / "a.fq.gz").write_bytes(synth.bgzf_bytes(fq, block=40000))
+    (tmp_path / "b.fa").write_bytes(fa)
+    (tmp_path / "b.fa.gz").write_bytes(synth.bgzf_bytes(fa))
+    monkeypatch.setattr(reads, "BGZF_GROUP", 1 << 20)
+    cli.main(["kmerize", "25", str(tmp_path / "z.k25"), str(tmp_path / "a.fq.gz"), str(tmp_path / "b.fa.gz"), str(tmp_path / "a.fq")])
+    monkeypatch.setenv("ZB_GPUS", "1")
+    cli.main(["kmerize", "25", str(tmp_path / "p.k25"), str(tmp_path / "a.fq"), str(tmp_path / "b.fa"), str(tmp_path / "a.fq")])
+    assert (tmp_path / "z.k25").read_bytes() == (tmp_path / "p.k25").read_bytes()

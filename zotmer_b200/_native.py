@@ -98,6 +98,9 @@ SIGNATURES = {
     "zb_staged_len": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
     "zb_staged_set_len": (C.c_int, [vp, C.c_uint64]),
     "zb_staged_fetch": (C.c_int, [vp, vp, C.c_size_t]),
+    "zb_bgzf_groups": (C.c_int, [vp, C.c_size_t, C.c_uint64, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "zb_stage_concat": (C.c_int, [C.c_int, vp, C.c_size_t, vp, C.POINTER(vp)]),
+    "zb_staged_fetch_range": (C.c_int, [vp, C.c_uint64, vp, C.c_size_t]),
     "zb_set_from_staged": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "zb_set_from_streams_dev": (C.c_int, [C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(vp)]),
     "zb_host_count_byte": (C.c_int, [vp, C.c_size_t, C.c_int, u64p]),
@@ -465,6 +468,12 @@ class Staged(object):
         _check(lib().zb_staged_fetch(self.h, _ptr(out), n))
         return out.tobytes()
 
+    def fetch_range(self, off, n):
+        """bytes [off, off + n) of the piece (the incomplete record behind a cut)"""
+        out = np.empty(int(n), dtype=np.uint8)
+        _check(lib().zb_staged_fetch_range(self.h, int(off), _ptr(out), int(n)))
+        return out.tobytes()
+
     def __del__(self):
         try:
             self.free()
@@ -500,6 +509,28 @@ def stage_bgzf(data, device=0, max_out=0, carry=None, carry_off=0):
     _check(lib().zb_stage_bgzf(device, _ptr(a), len(a), int(max_out), carry.h if carry is not None else None,
                                int(carry_off), C.byref(h), C.byref(used)))
     return Staged(h), used.value
+
+
+def bgzf_groups(data, max_text):
+    """compressed offsets at which runs of whole BGZF members of at most max_text bytes of text start"""
+    a = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+    cap = 1024
+    while True:
+        starts = np.zeros(cap, dtype=np.uint64)
+        n = C.c_size_t(0)
+        _check(lib().zb_bgzf_groups(_ptr(a), len(a), int(max_text), _ptr(starts), cap, C.byref(n)))
+        if n.value <= cap:
+            return [int(x) for x in starts[:n.value]]
+        cap = n.value
+
+
+def stage_concat(prefix, body, device=0):
+    """host bytes `prefix` + the staged piece `body` (consumed) -> a new Staged on the same device"""
+    a = np.frombuffer(prefix, dtype=np.uint8) if len(prefix) else None
+    h = vp()
+    bh, body.h = body.h, None
+    _check(lib().zb_stage_concat(device, _ptr(a), len(prefix), bh, C.byref(h)))
+    return Staged(h)
 
 
 def stage_fd(fd, offset, n, device=0):

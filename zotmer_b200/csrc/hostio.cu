@@ -458,6 +458,68 @@ int zb_stage_bgzf(int device, const uint8_t* raw, size_t n, uint64_t max_out, zb
     return ZB_OK;
 }
 
+int zb_bgzf_groups(const uint8_t* raw, size_t n, uint64_t max_text, uint64_t* starts, size_t cap, size_t* n_groups) {
+    ZB_TRY
+    if (!raw || !n || !n_groups || (cap && !starts)) ZB_FAIL(ZB_E_ARG, "null argument");
+    if (max_text < (1u << 16)) max_text = 1u << 16;
+    size_t off = 0, g = 0;
+    while (off < n) {
+        size_t used = 0;
+        uint64_t text = 0;
+        if (!bgzf_walk(raw + off, n - off, max_text, nullptr, &used, &text) || used == 0) ZB_FAIL(ZB_E_FORMAT, "not a BGZF file");
+        if (g < cap) starts[g] = off;
+        g++;
+        off += used;
+    }
+    *n_groups = g;
+    ZB_CATCH
+}
+
+// prefix (host bytes) + the text of `body` (same device; consumed) as one new piece: the incomplete record that the
+// previous group of members left behind, in front of this group's text
+int zb_stage_concat(int device, const uint8_t* prefix, size_t prefix_len, zb_staged* body, zb_staged** out) {
+    int rc = ZB_OK;
+    zb_staged* res = nullptr;
+    try {
+        if (!body || !out || (prefix_len && !prefix)) ZB_FAIL(ZB_E_ARG, "null argument");
+        Ctx* c = ctx_for(device);
+        if (body->c != c) ZB_FAIL(ZB_E_ARG, "the piece belongs to another device context");
+        if (prefix_len + body->n >= ((size_t)1 << 31)) ZB_FAIL(ZB_E_ARG, "a piece of %zu bytes", prefix_len + body->n);
+        staged_wait(body);
+        res = new zb_staged();
+        res->c = c;
+        res->n = prefix_len + body->n;
+        memset(res->ev, 0, sizeof res->ev);
+        res->d.alloc(c, res->n + 64);
+        if (prefix_len) ZB_CUDA(cudaMemcpyAsync(res->d.get(), prefix, prefix_len, cudaMemcpyHostToDevice, c->stream));
+        if (body->n) ZB_CUDA(dev_copy(c, res->d.get() + prefix_len, body->d.get(), body->n));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));   // `prefix` may go out of scope
+    } catch (const zb::Fail& f) {
+        rc = f.code;
+    } catch (const std::bad_alloc&) {
+        zb::set_error("out of host memory");
+        rc = ZB_E_NOMEM;
+    }
+    const std::string keep = rc != ZB_OK ? zb_last_error() : "";
+    if (body) staged_release(body);
+    if (rc != ZB_OK) {
+        if (res) staged_release(res);
+        zb::set_error("%s", keep.c_str());
+        return rc;
+    }
+    *out = res;
+    return ZB_OK;
+}
+
+int zb_staged_fetch_range(zb_staged* st, uint64_t off, uint8_t* host, size_t n) {
+    ZB_TRY
+    if (!st || (!host && n) || off > st->n || n > st->n - off) ZB_FAIL(ZB_E_ARG, "bad argument");
+    staged_wait(st);
+    if (n) ZB_CUDA(cudaMemcpyAsync(host, st->d.get() + off, n, cudaMemcpyDeviceToHost, st->c->stream));
+    ZB_CUDA(cudaStreamSynchronize(st->c->stream));
+    ZB_CATCH
+}
+
 int zb_staged_cut(zb_staged* st, int is_fasta, uint64_t* cut) {
     ZB_TRY
     if (!st || !cut) ZB_FAIL(ZB_E_ARG, "null argument");

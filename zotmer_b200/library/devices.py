@@ -80,6 +80,67 @@ class _Group(object):
         return out
 
 
+class _BgzfGroup(object):
+    """a run of whole members of a block-compressed file: inflated on the device that gets it (library zb_stage_bgzf);
+    its text starts with the rest of the record the previous group ended in (`first`: nothing to wait for) and the
+    record it ends in is completed by the next group (`last`: nothing to hand on)"""
+
+    def __init__(self, comp, job, first, last):
+        self.comp, self.job, self.first, self.last = comp, job, first, last
+        self.tail = None                    # bytes behind this group's last record boundary, for the next group
+        self.done = threading.Event()
+
+    def __len__(self):
+        return len(self.comp)
+
+
+def _bgzfJobs(fn, fa, n, jobs):
+    """groups of members of the BGZF file `fn` appended to `jobs`; False if it is not BGZF"""
+    import os
+    from zotmer_b200.library.reads import _bgzf, BGZF_GROUP
+    if not (fn.endswith('.gz') and os.path.isfile(fn)):
+        return False
+    comp = _bgzf(fn)
+    if comp is None:
+        return False
+    a = np.frombuffer(comp, dtype=np.uint8)
+    (_, text) = _native.bgzf_probe(a)
+    if text == 0:
+        return True
+    share = max(1 << 20, min(BGZF_GROUP, -(-text // n)))
+    starts = _native.bgzf_groups(a, share) + [len(a)]
+    for i in range(len(starts) - 1):
+        jobs.append((_BgzfGroup(a[starts[i]:starts[i + 1]], len(jobs), i == 0, i == len(starts) - 2), fa))
+    return True
+
+
+def _stageBgzfGroup(grp, prev, fa, dev, errors):
+    """the staged piece of a group (None: it holds no record boundary): inflate, put the previous group's leftover in
+    front, cut at the last record boundary and hand the bytes behind it on.  `prev`: the group before it in the file."""
+    nat = _native
+    st, _ = nat.stage_bgzf(grp.comp, dev)
+    if not grp.first:
+        while not prev.done.wait(0.05):
+            if errors:
+                st.free()
+                raise RuntimeError("another device failed")
+        if prev.tail:
+            st = nat.stage_concat(prev.tail, st, dev)
+        prev.tail = None
+    try:
+        if grp.last:
+            return st
+        cut = st.cut(fa)
+        grp.tail = st.fetch_range(cut, len(st) - cut)
+        if cut == 0:
+            st.free()
+            return None
+        st.set_len(cut)
+        return st
+    finally:
+        grp.done.set()
+
+
 def _pieceRounds(inputs, n, verbose=False):
     """record-aligned pieces of all inputs, about 1/n of a file each (at most MAX_PIECE), grouped n at a time"""
     import sys
@@ -90,6 +151,10 @@ def _pieceRounds(inputs, n, verbose=False):
         if isinstance(fn, tuple):
             fn, held = fn
         fa = isFasta(fn)
+        if held is None and _bgzfJobs(fn, fa, n, jobs):
+            if verbose:
+                print('reading %s (block-compressed, %s): inflated on the devices' % (fn, 'FASTA' if fa else 'FASTQ'), file=sys.stderr)
+            continue
         data = held if held is not None else mapBytes(fn)
         if verbose:
             print('reading %s (%d bytes, %s)' % (fn, len(data), 'FASTA' if fa else 'FASTQ'), file=sys.stderr)
@@ -121,6 +186,7 @@ def kmerizeFilesMulti(K, inputs, devs, verbose=False, baits_fn=None):
     g = _Group(devs)
     n = g.n
     rounds = _pieceRounds(inputs, n, verbose)
+    flat = [job for rd in rounds for job in rd]     # a BGZF group finds the group before it here
     nat = _native
 
     def work(r):
@@ -134,16 +200,25 @@ def kmerizeFilesMulti(K, inputs, devs, verbose=False, baits_fn=None):
         if baits is not None:
             km.set_baits(baits)
         bufs = []
+
+        def stage(ri):
+            """the piece of this device in round ri on its way to the device"""
+            src = rounds[ri][r][0]
+            if isinstance(src, _BgzfGroup):
+                prev = flat[src.job - 1][0] if not src.first else None
+                return _stageBgzfGroup(src, prev, rounds[ri][r][1], dev, g.errors)
+            return nat.stage_input(src, dev)
+
         try:
             staged = None
             if rounds and r < len(rounds[0]):
-                staged = nat.stage_input(rounds[0][r][0], dev)
+                staged = stage(0)
             for ri, rd in enumerate(rounds):
                 if staged is not None:
                     km.feed_staged(staged, rd[r][1])
                     staged = None
                 if ri + 1 < len(rounds) and r < len(rounds[ri + 1]):
-                    staged = nat.stage_input(rounds[ri + 1][r][0], dev)     # copies while this round is exchanged
+                    staged = stage(ri + 1)     # copies (or inflates) while this round is exchanged
                 # ---- exchange: counts meet on the board, owners allocate, everybody routes, owners adopt
                 g.board[("cnt", r)] = km.bucket_counts(n)
                 g.meet()
