@@ -424,3 +424,16 @@ def test_bgzf_probe_without_a_device():
     assert nat.bgzf_probe(synth.bgzf_bytes(data, eof=False)) == ((len(data) + 65279) // 65280, len(data))
     assert nat.bgzf_probe(gzip.compress(data)) is None
     assert nat.bgzf_probe(z[:-1]) is None and nat.bgzf_probe(z + b"\x00" * 40) is None and nat.bgzf_probe(b"") is None
+    # runs of whole members for several devices (zb_bgzf_groups): they tile the file, each holds <= max_text bytes of text
+    for max_text in (10000, 35000, 70000, 10 ** 9):
+        starts = nat.bgzf_groups(z, max_text)
+        assert starts[0] == 0 and starts == sorted(set(starts))
+        total = 0
+        for a, b in zip(starts, starts[1:] + [len(z)]):
+            m, t = nat.bgzf_probe(z[a:b])
+            assert m >= 1 and (t <= max(max_text, 65536) or m == 1)
+            assert gzip.decompress(z[a:b]) == data[total:total + t]
+            total += t
+        assert total == len(data)
+    with pytest.raises(Exception):
+        nat.bgzf_groups(gzip.compress(data), 70000)
