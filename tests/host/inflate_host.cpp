@@ -13,7 +13,7 @@ extern "C" int zi_inflate_host(const uint8_t* src, uint32_t clen, uint8_t* out, 
     const int skew = (int)(clen % 4);
     memcpy(buf + 8 + skew, src, clen);
     zinf::Scratch* S = (zinf::Scratch*)calloc(1, sizeof(zinf::Scratch));
-    const int rc = zinf::inflate_member<1>(0, buf + 8 + skew, clen, out, isize, S);
+    const int rc = zinf::inflate_member<1>(0, 1u, buf + 8 + skew, clen, out, isize, S);
     free(S);
     free(buf);
     return rc;

@@ -10,20 +10,26 @@
 
 namespace zb {
 
-static constexpr int INF_WARPS = 8;
+static constexpr int INF_THREADS = 256;
 
-__global__ void __launch_bounds__(INF_WARPS * 32)
+// W lanes inflate one member: a whole warp (W = 32), or an aligned half / quarter of one (W = 16 / 8: the groups of a
+// warp then run their serial decodes in the same issue slots wherever they take the same branch -- ZB_INFLATE_W)
+template <int W>
+__global__ void __launch_bounds__(INF_THREADS)
 bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfMember* __restrict__ tab, uint32_t members, uint8_t* out,
                     unsigned int* __restrict__ err /*[0] failures, [1] 1 + first failing member, [2] its code*/) {
     extern __shared__ __align__(16) unsigned char inf_raw[];
-    zinf::Scratch* scratch = reinterpret_cast<zinf::Scratch*>(inf_raw);   // [INF_WARPS], 6.5 KB each
-    const uint32_t m = blockIdx.x * INF_WARPS + (threadIdx.x >> 5);
+    zinf::Scratch* scratch = reinterpret_cast<zinf::Scratch*>(inf_raw);   // [INF_THREADS / W], 6.5 KB each
+    constexpr int GROUPS = INF_THREADS / W;
+    const uint32_t grp = threadIdx.x / W;
+    const uint32_t m = blockIdx.x * GROUPS + grp;
     if (m >= members) return;
     const BgzfMember t = tab[m];
     if (t.isize == 0 && t.clen <= 2) return;   // the empty member that ends a BGZF file
-    const int rc = zinf::inflate_member<32>((int)(threadIdx.x & 31), comp + t.src, t.clen, out + t.dst, t.isize,
-                                            &scratch[threadIdx.x >> 5]);
-    if (rc != zinf::ZI_OK && (threadIdx.x & 31) == 0) {
+    const int lane = (int)(threadIdx.x % W);
+    const uint32_t smask = (W == 32) ? 0xffffffffu : (((1u << W) - 1u) << ((threadIdx.x & 31u) / W * W));
+    const int rc = zinf::inflate_member<W>(lane, smask, comp + t.src, t.clen, out + t.dst, t.isize, &scratch[grp]);
+    if (rc != zinf::ZI_OK && lane == 0) {
         if (atomicAdd(&err[0], 1u) == 0) {
             err[1] = m + 1;
             err[2] = (unsigned)rc;
@@ -31,13 +37,22 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfMember* __restri
     }
 }
 
+template <int W>
+static void launch_inflate(Ctx* c, const uint8_t* d_comp, const BgzfMember* d_tab, uint32_t members, uint8_t* d_out, unsigned int* d_err) {
+    constexpr int GROUPS = INF_THREADS / W;
+    const int smem = (int)(GROUPS * sizeof(zinf::Scratch));   // W = 32: 52 KB, four CTAs = 32 warps = 32 members per SM
+    ZB_CUDA(cudaFuncSetAttribute(bgzf_inflate_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    bgzf_inflate_kernel<W><<<(unsigned)div_up(members, GROUPS), INF_THREADS, smem, c->stream>>>(d_comp, d_tab, members, d_out, d_err);
+    ZB_LAUNCH_CHECK(c);
+}
+
 void bgzf_inflate(Ctx* c, const uint8_t* d_comp, const BgzfMember* d_tab, uint32_t members, uint8_t* d_out, unsigned int* d_err) {
     if (members == 0) return;
+    static const int w = [] { const char* e = getenv("ZB_INFLATE_W"); return e ? atoi(e) : 32; }();
     Stage st(c, "inflate");
-    const int smem = (int)(INF_WARPS * sizeof(zinf::Scratch));   // 52 KB: four CTAs = 32 warps per SM
-    ZB_CUDA(cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    bgzf_inflate_kernel<<<(unsigned)div_up(members, INF_WARPS), INF_WARPS * 32, smem, c->stream>>>(d_comp, d_tab, members, d_out, d_err);
-    ZB_LAUNCH_CHECK(c);
+    if (w == 16) launch_inflate<16>(c, d_comp, d_tab, members, d_out, d_err);
+    else if (w == 8) launch_inflate<8>(c, d_comp, d_tab, members, d_out, d_err);
+    else launch_inflate<32>(c, d_comp, d_tab, members, d_out, d_err);
 }
 
 // ------------------------------------------------------------------------------- record-aligned cut

@@ -20,7 +20,7 @@
 //   * lanes synchronise only when a match reads bytes written since the last synchronisation (`vis`).
 //
 // The same source compiles for the host with W = 1 (tests/host/inflate_host.cpp checks it against zlib without a
-// GPU); ZI_SYNC() is __syncwarp() on the device.
+// GPU); ZI_SYNC(smask) is __syncwarp() on the device.
 #pragma once
 #include <stdint.h>
 
@@ -30,9 +30,9 @@
 #define ZI_HD inline
 #endif
 #ifdef __CUDA_ARCH__
-#define ZI_SYNC() __syncwarp()
+#define ZI_SYNC(m) __syncwarp(m)
 #else
-#define ZI_SYNC() do { } while (0)
+#define ZI_SYNC(m) do { (void)(m); } while (0)
 #endif
 
 namespace zinf {
@@ -154,8 +154,8 @@ ZI_HD int slow_decode(uint32_t bits, int maxlen, const uint16_t* cnt, const uint
 // then fills its share of the 2^tbits table entries.  KIND 0: literal/length entries, 1: distance entries, 2: the
 // code-length alphabet (u16 entries).  false: the lengths over-subscribe the code space.
 template <int W, int KIND>
-ZI_HD bool build(int lane, const uint8_t* lens, int n, uint16_t* cnt, uint16_t* sym, void* tab, int tbits, int* flag) {
-    ZI_SYNC();   // lens[] written by lane 0
+ZI_HD bool build(int lane, uint32_t smask, const uint8_t* lens, int n, uint16_t* cnt, uint16_t* sym, void* tab, int tbits, int* flag) {
+    ZI_SYNC(smask);   // lens[] written by lane 0
     if (lane == 0) {
         int c[16], offs[16];
         for (int i = 0; i < 16; i++) c[i] = 0;
@@ -175,7 +175,7 @@ ZI_HD bool build(int lane, const uint8_t* lens, int n, uint16_t* cnt, uint16_t* 
         for (int i = 0; i < 16; i++) cnt[i] = (uint16_t)c[i];
         *flag = ok;
     }
-    ZI_SYNC();
+    ZI_SYNC(smask);
     if (!*flag) return false;
     for (int e = lane; e < (1 << tbits); e += W) {
         int l = 0;
@@ -184,7 +184,7 @@ ZI_HD bool build(int lane, const uint8_t* lens, int n, uint16_t* cnt, uint16_t* 
         else if (KIND == 1) reinterpret_cast<uint32_t*>(tab)[e] = (s < 0) ? 0u : dist_entry(s, l);
         else reinterpret_cast<uint16_t*>(tab)[e] = (s < 0) ? (uint16_t)0 : (uint16_t)((l << 9) | s);
     }
-    ZI_SYNC();
+    ZI_SYNC(smask);
     return true;
 }
 
@@ -208,12 +208,13 @@ ZI_HD void flush_literals(int lane, uint8_t* out, uint32_t& lit0, uint32_t pos, 
     }
 }
 
-// Inflate the raw deflate stream src[0, clen) into out[0, isize).  W lanes (a power of two) call this together with
-// identical arguments and their own `lane`; the result code is the same in every lane.  Reads up to 16 bytes past
+// Inflate the raw deflate stream src[0, clen) into out[0, isize).  W lanes (a power of two: a warp, or an aligned part
+// of one -- `smask` names the lanes of the group for its synchronisations) call this together with identical arguments
+// and their own `lane` (0 .. W - 1); the result code is the same in every lane.  Reads up to 16 bytes past
 // src + clen (never uses them) and may write up to W bytes past out + isize when the stream is corrupt (the caller
 // keeps that much slack behind the last member and rejects the whole group on any error).
 template <int W>
-ZI_HD int inflate_member(int lane, const uint8_t* src, uint32_t clen, uint8_t* out, uint32_t isize, Scratch* S) {
+ZI_HD int inflate_member(int lane, uint32_t smask, const uint8_t* src, uint32_t clen, uint8_t* out, uint32_t isize, Scratch* S) {
     Bits b;
     const uint8_t* const in_end = src + clen + 16;
     b.init(src, in_end);
@@ -243,7 +244,7 @@ ZI_HD int inflate_member(int lane, const uint8_t* src, uint32_t clen, uint8_t* o
         if (type == 1) {
             nlit = 288;
             ndist = 30;
-            ZI_SYNC();   // nobody still reads the previous block's lengths
+            ZI_SYNC(smask);   // nobody still reads the previous block's lengths
             for (int s = lane; s < 288; s += W) S->lens[s] = (uint8_t)(s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8)));
             for (int s = lane; s < 30; s += W) S->lens[288 + s] = 5;
         } else {
@@ -251,15 +252,15 @@ ZI_HD int inflate_member(int lane, const uint8_t* src, uint32_t clen, uint8_t* o
             ndist = (int)b.take(5) + 1;
             const int ncode = (int)b.take(4) + 4;
             if (nlit > 286 || ndist > 30) return ZI_E_HEADER;
-            ZI_SYNC();
+            ZI_SYNC(smask);
             if (lane == 0)
                 for (int i = 0; i < 19; i++) S->clens[i] = 0;
-            ZI_SYNC();
+            ZI_SYNC(smask);
             for (int i = 0; i < ncode; i++) {
                 const uint32_t v = b.take(3);
                 if (lane == 0) S->clens[clen_order(i)] = (uint8_t)v;
             }
-            if (!build<W, 2>(lane, S->clens, 19, S->ccnt, S->csym, S->ctab, CBITS, &S->flag)) return ZI_E_CODE;
+            if (!build<W, 2>(lane, smask, S->clens, 19, S->ccnt, S->csym, S->ctab, CBITS, &S->flag)) return ZI_E_CODE;
             int i = 0, prev = -1;
             const int total = nlit + ndist;
             while (i < total) {
@@ -291,11 +292,11 @@ ZI_HD int inflate_member(int lane, const uint8_t* src, uint32_t clen, uint8_t* o
                 i += rep;
                 prev = val;
             }
-            ZI_SYNC();
+            ZI_SYNC(smask);
             if (S->lens[256] == 0) return ZI_E_HEADER;   // no end-of-block code
         }
-        if (!build<W, 0>(lane, S->lens, nlit, S->lcnt, S->lsym, S->ltab, LBITS, &S->flag)) return ZI_E_CODE;
-        if (!build<W, 1>(lane, S->lens + nlit, ndist, S->dcnt, S->dsym, S->dtab, DBITS, &S->flag)) return ZI_E_CODE;
+        if (!build<W, 0>(lane, smask, S->lens, nlit, S->lcnt, S->lsym, S->ltab, LBITS, &S->flag)) return ZI_E_CODE;
+        if (!build<W, 1>(lane, smask, S->lens + nlit, ndist, S->dcnt, S->dsym, S->dtab, DBITS, &S->flag)) return ZI_E_CODE;
 
         for (;;) {
             uint32_t win = b.window();
@@ -342,7 +343,7 @@ ZI_HD int inflate_member(int lane, const uint8_t* src, uint32_t clen, uint8_t* o
             flush_literals<W>(lane, out, lit0, pos, mine);
             const uint32_t from0 = pos - dist;
             if (from0 + (dist < len ? dist : len) > vis) {   // the source holds bytes stored since the last synchronisation
-                ZI_SYNC();
+                ZI_SYNC(smask);
                 vis = pos;
             }
             {
@@ -362,7 +363,7 @@ ZI_HD int inflate_member(int lane, const uint8_t* src, uint32_t clen, uint8_t* o
         }
     } while (!last);
     flush_literals<W>(lane, out, lit0, pos, mine);
-    ZI_SYNC();
+    ZI_SYNC(smask);
     if (pos != isize) return ZI_E_OUT;
     if (b.bit_pos(src) > (uint64_t)clen * 8u) return ZI_E_IN;
     return ZI_OK;
