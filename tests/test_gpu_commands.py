@@ -108,6 +108,14 @@ def test_merge_counts_beyond_u32_file(zot, tmp_path):
     assert {int(a): b for a, b in meta["hist"].items()} == want_hist
     tot = float(int(ec.sum()))
     assert meta["acgt"] == [int(ec[(ek & np.uint64(3)) == np.uint64(b)].sum()) / tot for b in range(4)]
+    # the file is an input like any other: merged once more with its own inputs
+    out2 = tmp_path / "wide2.k25"
+    zot("merge", out2, out, tmp_path / "w0.k25", tmp_path / "w1.k25")
+    e2k, e2c = co.merge([(ek, ec)] + [(k, c.astype(np.uint64)) for k, c in sets[:2]])
+    with kmers(str(out2), "r") as z:
+        kw2 = np.array(readWords(z.open("kmers")), dtype=np.uint64)
+        cw2 = np.array(readWords(z.open("counts")), dtype=np.uint64)
+    assert np.array_equal(kw2, co.encode(e2k, True)) and np.array_equal(cw2, co.encode(e2c, False))
 
 
 def test_merge_behavioural(zot, tmp_path, capsys):

@@ -618,8 +618,18 @@ def test_merge_counts_beyond_u32(nat, monkeypatch, route, nsets):
     assert np.array_equal(kw, co.encode(ek, True)) and np.array_equal(cw, co.encode(ec, False))
     with pytest.raises(Exception):
         m.trim(2)
-    with pytest.raises(Exception):
-        nat.merge([m, hs[0], hs[1]])
+    # the streams read back are the same wide set (files.py:219-227 decodes Python ints)
+    back = nat.KmerSet.from_streams(kw, cw)
+    bk, bc = back.fetch()
+    assert back.is_wide() and np.array_equal(bk, ek) and np.array_equal(bc, ec) and back.stats()["hist"] == st["hist"]
+    # and a wide set is an input like any other: four 16-bit planes instead of two
+    m2 = nat.merge([back, hs[0], hs[1]])
+    k2, c2 = m2.fetch()
+    e2k, e2c = co.merge([(ek, ec), (sets[0][0], sets[0][1].astype(np.uint64)), (sets[1][0], sets[1][1].astype(np.uint64))])
+    assert m2.is_wide() and np.array_equal(k2, e2k) and np.array_equal(c2, e2c)
+    assert m2.stats()["hist"] == co.hist(e2c)
+    w2k, w2c = m2.encode()
+    assert np.array_equal(w2k, co.encode(e2k, True)) and np.array_equal(w2c, co.encode(e2c, False))
     # sums that stay below 2^32-1 are an ordinary set
     small = nat.merge(hs[:1] + [nat.KmerSet.from_arrays(sets[0][0][:10], np.ones(10, np.uint32))])
     assert not small.is_wide()

@@ -1355,16 +1355,23 @@ tree:
 // sets may hold counts that no u32 array can.  Every merge kernel reports such a sum (ZB_E_RANGE); zb_merge then
 // merges the inputs twice more with the low and the high 16 bits of every count as the counts -- each of those sums
 // fits 32 bits for up to 65,536 inputs -- and adds the two results up in 64 bits.
-__global__ void __launch_bounds__(256) count_plane_kernel(const uint32_t* __restrict__ c, size_t n, int shift, uint32_t* __restrict__ out) {
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = (c[i] >> shift) & 0xffffu;
+// plane p of a count: bits [16 p, 16 p + 16), from the u32 counts or from the u64 counts of a wide input
+__global__ void __launch_bounds__(256) count_plane_kernel(const uint32_t* __restrict__ c, const uint64_t* __restrict__ w, size_t n, int shift,
+                                                          uint32_t* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        out[i] = w ? (uint32_t)(w[i] >> shift) & 0xffffu : (shift < 32 ? (c[i] >> shift) & 0xffffu : 0u);
 }
-__global__ void __launch_bounds__(256) count_join_kernel(uint32_t* __restrict__ lo_sat, const uint32_t* __restrict__ hi, size_t n,
-                                                         uint64_t* __restrict__ wide, unsigned long long* __restrict__ n_exc,
-                                                         uint64_t* __restrict__ exc_idx, uint64_t exc_cap) {
+__global__ void __launch_bounds__(256) wide_add_plane_kernel(uint64_t* __restrict__ wide, const uint32_t* __restrict__ plane, size_t n, int shift,
+                                                             int first) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        wide[i] = (first ? 0ull : wide[i]) + ((uint64_t)plane[i] << shift);
+}
+// cnt = min(wide, 2^32-1); the entries that reach 2^32-1 are listed
+__global__ void __launch_bounds__(256) wide_sat_kernel(const uint64_t* __restrict__ wide, size_t n, uint32_t* __restrict__ cnt,
+                                                       unsigned long long* __restrict__ n_exc, uint64_t* __restrict__ exc_idx, uint64_t exc_cap) {
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-        const uint64_t v = (uint64_t)lo_sat[i] + ((uint64_t)hi[i] << 16);
-        wide[i] = v;
-        lo_sat[i] = v >= 0xffffffffull ? 0xffffffffu : (uint32_t)v;
+        const uint64_t v = wide[i];
+        cnt[i] = v >= 0xffffffffull ? 0xffffffffu : (uint32_t)v;
         if (v >= 0xffffffffull) {
             const unsigned long long s = atomicAdd(n_exc, 1ull);
             if (s < exc_cap) exc_idx[s] = i;
@@ -1377,25 +1384,70 @@ __global__ void __launch_bounds__(256) exc_gather_kernel(const uint64_t* __restr
     if (i < m) { out[i] = k[idx[i]]; out[m + i] = wide[idx[i]]; }
 }
 
+}  // extern "C"
+
+// r->k (n keys) and r->wide (their counts as u64) are in place: the saturated u32 counts and the list of the entries
+// that reach 2^32-1 follow.  Also used by the decoder for a file that holds such counts (codec.cu).
+void zb_set_finish_wide(zb_set* r) {
+    Ctx* c = r->c;
+    if (!r->cnt.get() || r->cnt.n < r->n) r->cnt.alloc(c, r->n);
+    size_t cap = 1 << 16, m = 0;
+    DBuf<unsigned long long> nexc(c, 2);
+    DBuf<uint64_t> eidx;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        eidx.alloc(c, cap);
+        ZB_CUDA(dev_memset(c, nexc.get(), 0, 16));
+        const unsigned blocks = (unsigned)std::min<size_t>((size_t)c->sm_count * 8, div_up(std::max<size_t>(r->n, 1), 256));
+        wide_sat_kernel<<<blocks, 256, 0, c->stream>>>(r->wide.get(), r->n, r->cnt.get(), nexc.get(), eidx.get(), cap);
+        ZB_LAUNCH_CHECK(c);
+        ZB_CUDA(read_back(c, nexc.get(), 8));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+        m = (size_t)c->h_scalars[0];
+        if (m <= cap) break;
+        cap = m;
+    }
+    r->exc_idx.resize(m);
+    r->exc_key.resize(m);
+    r->exc_val.resize(m);
+    if (m) {
+        ZB_CUDA(cudaMemcpy(r->exc_idx.data(), eidx.get(), m * 8, cudaMemcpyDeviceToHost));
+        std::sort(r->exc_idx.begin(), r->exc_idx.end());
+        ZB_CUDA(cudaMemcpy(eidx.get(), r->exc_idx.data(), m * 8, cudaMemcpyHostToDevice));
+        DBuf<uint64_t> kv(c, 2 * m);
+        exc_gather_kernel<<<(unsigned)div_up(m, 256), 256, 0, c->stream>>>(eidx.get(), m, r->k.get(), r->wide.get(), kv.get());
+        ZB_LAUNCH_CHECK(c);
+        std::vector<uint64_t> h(2 * m);
+        ZB_CUDA(cudaMemcpyAsync(h.data(), kv.get(), 2 * m * 8, cudaMemcpyDeviceToHost, c->stream));
+        ZB_CUDA(cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < m; i++) { r->exc_key[i] = h[i]; r->exc_val[i] = h[m + i]; }
+    } else {
+        r->wide.release();   // every count fits 32 bits after all: an ordinary set
+    }
+}
+
+extern "C" {
 
 static int merge_wide(int nsets, zb_set* const* sets, zb_set** out) {
     ZB_TRY
     Ctx* c = sets[0]->c;
     if (nsets > 65536) ZB_FAIL(ZB_E_RANGE, "k-mer count exceeds 2^32-1 in a merge of more than 65,536 sets");
     size_t total = 0;
-    for (int i = 0; i < nsets; i++) total += sets[i]->n;
+    bool wide_in = false;
+    for (int i = 0; i < nsets; i++) { total += sets[i]->n; wide_in = wide_in || sets[i]->wide.get() != nullptr; }
+    const int planes = wide_in ? 4 : 2;     // 16-bit planes of the inputs' counts (codec64 carries at most 60 bits)
     DBuf<uint32_t> plane(c, total);
     std::vector<MergeIn> in(nsets);
     std::vector<const MergeIn*> ptr(nsets);
-    zb_set* part[2] = {nullptr, nullptr};
+    zb_set* r = nullptr;
+    zb_set* part = nullptr;
     try {
-        for (int p = 0; p < 2; p++) {
+        for (int p = 0; p < planes; p++) {
             size_t off = 0;
             for (int i = 0; i < nsets; i++) {
                 const size_t n = sets[i]->n;
                 if (n) {
                     const unsigned blocks = (unsigned)std::min<size_t>((size_t)c->sm_count * 8, div_up(n, 256));
-                    count_plane_kernel<<<blocks, 256, 0, c->stream>>>(sets[i]->cnt.get(), n, 16 * p, plane.get() + off);
+                    count_plane_kernel<<<blocks, 256, 0, c->stream>>>(sets[i]->cnt.get(), sets[i]->wide.get(), n, 16 * p, plane.get() + off);
                     ZB_LAUNCH_CHECK(c);
                 }
                 in[i].k.p = sets[i]->k.get();
@@ -1405,52 +1457,31 @@ static int merge_wide(int nsets, zb_set* const* sets, zb_set** out) {
                 ptr[i] = &in[i];
                 off += n;
             }
-            if (int rc = merge_core(nsets, ptr.data(), &part[p])) throw zb::Fail{rc};
+            if (int rc = merge_core(nsets, ptr.data(), &part)) throw zb::Fail{rc};
+            if (p == 0) {
+                r = part;
+                part = nullptr;
+                r->wide.alloc(c, r->n);
+            } else if (part->n != r->n) {
+                ZB_FAIL(ZB_E_CUDA, "merge: the count planes disagree (%zu vs %zu keys)", r->n, part->n);
+            }
+            const zb_set* src = p == 0 ? r : part;
+            if (r->n) {
+                const unsigned blocks = (unsigned)std::min<size_t>((size_t)c->sm_count * 8, div_up(r->n, 256));
+                wide_add_plane_kernel<<<blocks, 256, 0, c->stream>>>(r->wide.get(), src->cnt.get(), r->n, 16 * p, p == 0 ? 1 : 0);
+                ZB_LAUNCH_CHECK(c);
+            }
+            if (part) {
+                ZB_CUDA(cudaStreamSynchronize(c->stream));
+                zb_set_free(part);
+                part = nullptr;
+            }
         }
-        zb_set* r = part[0];
-        if (part[1]->n != r->n) ZB_FAIL(ZB_E_CUDA, "merge: the two count planes disagree (%zu vs %zu keys)", r->n, part[1]->n);
-        r->wide.alloc(c, r->n);
-        size_t cap = 1 << 16;
-        DBuf<unsigned long long> nexc(c, 2);
-        DBuf<uint64_t> eidx;
-        size_t m = 0;
-        // (the join is idempotent on cnt only the first time: a second attempt re-reads the planes, so keep them apart)
-        DBuf<uint32_t> lo_keep(c, r->n);
-        ZB_CUDA(dev_copy(c, lo_keep.get(), r->cnt.get(), r->n * 4));
-        for (int attempt = 0; attempt < 2; attempt++) {
-            eidx.alloc(c, cap);
-            ZB_CUDA(dev_memset(c, nexc.get(), 0, 16));
-            if (attempt) ZB_CUDA(dev_copy(c, r->cnt.get(), lo_keep.get(), r->n * 4));
-            const unsigned blocks = (unsigned)std::min<size_t>((size_t)c->sm_count * 8, div_up(std::max<size_t>(r->n, 1), 256));
-            count_join_kernel<<<blocks, 256, 0, c->stream>>>(r->cnt.get(), part[1]->cnt.get(), r->n, r->wide.get(), nexc.get(), eidx.get(), cap);
-            ZB_LAUNCH_CHECK(c);
-            ZB_CUDA(read_back(c, nexc.get(), 8));
-            ZB_CUDA(cudaStreamSynchronize(c->stream));
-            m = (size_t)c->h_scalars[0];
-            if (m <= cap) break;
-            cap = m;
-        }
-        r->exc_idx.resize(m);
-        r->exc_key.resize(m);
-        r->exc_val.resize(m);
-        if (m) {
-            ZB_CUDA(cudaMemcpy(r->exc_idx.data(), eidx.get(), m * 8, cudaMemcpyDeviceToHost));
-            std::sort(r->exc_idx.begin(), r->exc_idx.end());
-            ZB_CUDA(cudaMemcpy(eidx.get(), r->exc_idx.data(), m * 8, cudaMemcpyHostToDevice));
-            DBuf<uint64_t> kv(c, 2 * m);
-            exc_gather_kernel<<<(unsigned)div_up(m, 256), 256, 0, c->stream>>>(eidx.get(), m, r->k.get(), r->wide.get(), kv.get());
-            ZB_LAUNCH_CHECK(c);
-            std::vector<uint64_t> h(2 * m);
-            ZB_CUDA(cudaMemcpyAsync(h.data(), kv.get(), 2 * m * 8, cudaMemcpyDeviceToHost, c->stream));
-            ZB_CUDA(cudaStreamSynchronize(c->stream));
-            for (size_t i = 0; i < m; i++) { r->exc_key[i] = h[i]; r->exc_val[i] = h[m + i]; }
-        }
-        zb_set_free(part[1]);
-        part[1] = nullptr;
+        zb_set_finish_wide(r);
         *out = r;
     } catch (...) {
-        if (part[0]) zb_set_free(part[0]);
-        if (part[1]) zb_set_free(part[1]);
+        if (r) zb_set_free(r);
+        if (part) zb_set_free(part);
         throw;
     }
     ZB_CATCH
@@ -1465,14 +1496,16 @@ int zb_merge(int nsets, zb_set* const* sets, zb_set** out) {
     ZB_CUDA(cudaSetDevice(c->device));
     std::vector<MergeIn> in(nsets);
     std::vector<const MergeIn*> ptr(nsets);
+    bool wide_in = false;
     for (int i = 0; i < nsets; i++) {
-        no_wide(sets[i], "merge input");
+        wide_in = wide_in || sets[i]->wide.get() != nullptr;
         in[i].k.p = sets[i]->k.get();
         in[i].cnt.p = sets[i]->cnt.get();
         in[i].n = sets[i]->n;
         in[i].c = c;
         ptr[i] = &in[i];
     }
+    if (wide_in) return merge_wide(nsets, sets, out);   // the saturated u32 counts of a wide input must not be added up
     const int rc = merge_core(nsets, ptr.data(), out);
     if (rc != ZB_E_RANGE) return rc;
     return merge_wide(nsets, sets, out);

@@ -965,7 +965,16 @@ int zb_set_from_streams_dev(int device, const uint64_t* d_kmer_words, size_t n_k
         v->n = pk.n;
         decode_emit<uint64_t>(c, d_kmer_words, n_kmer_words, true, &pk, v->k.get());
         if (d_count_words) {
-            decode_emit<uint32_t>(c, d_count_words, n_count_words, false, &pc, v->cnt.get());
+            try {
+                decode_emit<uint32_t>(c, d_count_words, n_count_words, false, &pc, v->cnt.get());
+            } catch (const zb::Fail& f) {
+                if (f.code != ZB_E_RANGE) throw;
+                // counts beyond 2^32-1 (the file of a merge of very deep sets, merge.py:145-146): a WIDE set
+                ZB_CUDA(dev_memset(c, pc.coff.get() + pc.tiles + 1, 0, 4));
+                v->wide.alloc(c, pk.n);
+                decode_emit<uint64_t>(c, d_count_words, n_count_words, false, &pc, v->wide.get());
+                zb_set_finish_wide(v);
+            }
         } else if (pk.n) {
             fill_u32(c, v->cnt.get(), pk.n, 1u);
         }

@@ -27,6 +27,9 @@ struct zb_words {
     size_t nk = 0, nc = 0;
 };
 
+// api.cu: r->k and r->wide are filled -> the saturated u32 counts and the list of entries >= 2^32-1 (an ordinary set if none)
+void zb_set_finish_wide(zb_set* r);
+
 // body of every extern "C" entry point: no exception crosses the C boundary
 #define ZB_TRY try {
 #define ZB_CATCH                                   \
