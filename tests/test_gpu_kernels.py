@@ -394,12 +394,16 @@ def test_kmerize_fasta_vs_c_oracle(nat, k):
     assert s.stats()["acgt_weighted"] == eacgt
 
 
-def test_kmerize_batched_flush(nat, monkeypatch):
-    """small ZB_MAX_PENDING forces several sort+count+merge rounds; the result must not change"""
+@pytest.mark.parametrize("max_runs", [None, 3, 8])
+def test_kmerize_batched_flush(nat, monkeypatch, max_runs):
+    """small ZB_MAX_PENDING forces several sort+count rounds; the runs are united at the end (default: they fit the
+    memory budget) or every max_runs batches; the result must not change"""
     rng = np.random.default_rng(7)
     genome = rnd_dna(rng, 50000)
     fq = make_fastq(rng, genome, 8000, 100)
     monkeypatch.setenv("ZB_MAX_PENDING", "65536")
+    if max_runs:
+        monkeypatch.setenv("ZB_MAX_RUNS", str(max_runs))
     s, nr = run_kmerize(nat, 21, [(fq, False), (fq[:len(fq) // 2 - (len(fq) // 2) % 1], False)])
     monkeypatch.delenv("ZB_MAX_PENDING")
     ks, cc = s.fetch()

@@ -365,7 +365,11 @@ struct zb_kmerizer {
     // the human-scale read set: more than half of that run's time, profiles/r02_human_scale.md.)
     struct Run { DBuf<uint64_t> k; DBuf<uint32_t> c; size_t n = 0; };
     std::vector<Run> runs;
-    size_t max_runs = 8;
+    // Runs pile up until they hold `run_budget` bytes (a share of the device's memory: every compaction re-reads and
+    // re-writes what has been accumulated so far, so the fewer the better -- human-scale shape on one B200: 10.5 / 14.9 /
+    // 17.3 Gbases/s with a compaction every 5 / 8 / 13 batches, gpurun_out/r3_human_r*.json) or there are max_runs of them.
+    size_t max_runs = 256;
+    size_t run_budget = 0;               // bytes; 0 = not yet asked (ZB_RUN_BUDGET_PCT of the device's memory, default 35)
     DBuf<uint64_t> acc_k;                // the one run left by compact_runs at finish
     DBuf<uint32_t> acc_c;
     size_t acc_n = 0;
@@ -456,7 +460,16 @@ static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n, const SortPre* 
     r.k = std::move(dk);
     r.c = std::move(dc);
     h->runs.push_back(std::move(r));
-    if (h->runs.size() >= h->max_runs) compact_runs(h);
+    if (h->run_budget == 0) {
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess || tot == 0) tot = (size_t)64 << 30;
+        int pct = 35;
+        if (const char* e = getenv("ZB_RUN_BUDGET_PCT")) pct = std::min(80, std::max(1, atoi(e)));
+        h->run_budget = tot / 100 * (size_t)pct;
+    }
+    size_t held = 0;
+    for (const auto& q : h->runs) held += q.n * 12;
+    if (h->runs.size() >= h->max_runs || (h->runs.size() > 1 && held > h->run_budget)) compact_runs(h);
 }
 
 // the pairwise fold of the first version: merge path + reduce-by-key, run after run (fallback for key spaces too
