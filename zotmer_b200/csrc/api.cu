@@ -422,10 +422,11 @@ static void pending_consumed(zb_kmerizer* h) {
 }
 
 // count the pending canonical keys: one more run
-static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n, const SortPre* pre = nullptr);
+static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n, const SortPre* pre = nullptr, bool last = false);
 static void compact_runs(zb_kmerizer* h);
 
-static void flush_pending(zb_kmerizer* h) {
+// last: no batch follows (zb_kmerize_finish)
+static void flush_pending(zb_kmerizer* h, bool last = false) {
     Ctx* c = h->c;
     if (h->adopted) {
         uint64_t* keys = h->adopted;
@@ -438,12 +439,12 @@ static void flush_pending(zb_kmerizer* h) {
     const size_t n = read_pending_count(h);
     const bool pre_on = h->pre_on;
     pending_consumed(h);
-    count_keys(h, h->pending.get(), n, pre_on ? &h->pre : nullptr);
+    count_keys(h, h->pending.get(), n, pre_on ? &h->pre : nullptr, last);
     (void)c;
 }
 
 // sort + count `keys` (destroyed) and fold the result into the accumulated run
-static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n, const SortPre* pre) {
+static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n, const SortPre* pre, bool last) {
     Ctx* c = h->c;
     if (n == 0) return;
     // sort + count in one go (segsort.cu): distinct canonical keys -> `dk`, counts -> `dc`
@@ -451,14 +452,26 @@ static void count_keys(zb_kmerizer* h, uint64_t* keys, size_t n, const SortPre* 
     DBuf<uint32_t> dc(c, n);
     const size_t nd = sort_count(c, keys, tmp.get(), nullptr, nullptr, n, 2 * h->k, dk.get(), dc.get(), false, pre);
     tmp.release();
-    // the run at its real size: sort_count's outputs are sized for n distinct keys; what lies behind the nd that came out
-    // goes back to the allocator (no copy -- this used to be 0.08 ms of every bench step and 1.2 ms of every human-scale batch)
+    // the run at its real size (sort_count's outputs are sized for n distinct keys).  The last batch of a kmerizer keeps the
+    // buffers and gives what lies behind its nd entries back to the allocator (no copy: 0.08 ms of a bench step).  A batch in
+    // the middle of a long input copies its run into buffers of its own instead: shrunk blocks pin their segments, the
+    // 3 GB buffers of the NEXT batch then find no free block of their size, and a cudaMalloc per batch costs far more than
+    // the copy (human-scale shape with 17 runs held: 1.8 s instead of 0.65, gpurun_out/r3_human_b35.json).
     zb_kmerizer::Run r;
     r.n = nd;
-    dk.shrink(nd);
-    dc.shrink(nd);
-    r.k = std::move(dk);
-    r.c = std::move(dc);
+    if (last) {
+        dk.shrink(nd);
+        dc.shrink(nd);
+        r.k = std::move(dk);
+        r.c = std::move(dc);
+    } else {
+        r.k.alloc(c, nd);
+        r.c.alloc(c, nd);
+        ZB_CUDA(dev_copy(c, r.k.get(), dk.get(), nd * 8));
+        ZB_CUDA(dev_copy(c, r.c.get(), dc.get(), nd * 4));
+        dk.release();
+        dc.release();
+    }
     h->runs.push_back(std::move(r));
     if (h->run_budget == 0) {
         size_t fr = 0, tot = 0;
@@ -814,7 +827,7 @@ int zb_kmerize_finish(zb_kmerizer* h, zb_set** result, uint64_t* n_records) {
     Ctx* c = h->c;
     ZB_CUDA(cudaSetDevice(c->device));
     EngineLock el(c, ENG_SM);
-    flush_pending(h);
+    flush_pending(h, true);
     h->pending.release();
     h->pending_cap = 0;
     compact_runs(h);
