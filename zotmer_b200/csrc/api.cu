@@ -365,10 +365,12 @@ struct zb_kmerizer {
     // the human-scale read set: more than half of that run's time, profiles/r02_human_scale.md.)
     struct Run { DBuf<uint64_t> k; DBuf<uint32_t> c; size_t n = 0; };
     std::vector<Run> runs;
-    // Runs pile up until they hold `run_budget` bytes (a share of the device's memory: every compaction re-reads and
-    // re-writes what has been accumulated so far, so the fewer the better -- human-scale shape on one B200: 10.5 / 14.9 /
-    // 17.3 Gbases/s with a compaction every 5 / 8 / 13 batches, gpurun_out/r3_human_r*.json) or there are max_runs of them.
-    size_t max_runs = 256;
+    // Runs pile up until there are max_runs of them or they hold `run_budget` bytes (a share of the device's memory).
+    // Every compaction re-reads and re-writes what has been accumulated so far, so few of them is better -- human-scale
+    // shape on one B200: 10.5 / 14.9 / 17.3 Gbases/s with a compaction every 5 / 8 / 13 batches (gpurun_out/r3_human_r*.json)
+    // -- but one merge of all 25 runs at the end is no better than two of 13 (16.5, r3_human_c55.json: the slices a bucket
+    // gets from each input become short).
+    size_t max_runs = 13;
     size_t run_budget = 0;               // bytes; 0 = not yet asked (ZB_RUN_BUDGET_PCT of the device's memory, default 35)
     DBuf<uint64_t> acc_k;                // the one run left by compact_runs at finish
     DBuf<uint32_t> acc_c;
