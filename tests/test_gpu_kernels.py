@@ -986,9 +986,11 @@ def test_codec_set_streams_and_errors(nat):
     bad[len(bad) // 2] = (bad[len(bad) // 2] & ~np.uint64(15)) | np.uint64(9)
     with pytest.raises(AssertionError):                                    # unknown tag (codec64.py:128)
         nat.decode_stream(bad, True)
-    big = co.encode(np.array([5, 2 ** 32, 7], np.uint64), False)           # a count beyond u32
-    with pytest.raises(IndexError):
-        nat.KmerSet.from_streams(co.encode(np.array([1, 2, 3], np.uint64), True), big)
+    big = co.encode(np.array([5, 2 ** 32, 7], np.uint64), False)           # a count beyond u32: a wide set (merge.py:145-146)
+    w = nat.KmerSet.from_streams(co.encode(np.array([1, 2, 3], np.uint64), True), big)
+    wk, wc = w.fetch()
+    assert w.is_wide() and wk.tolist() == [1, 2, 3] and wc.tolist() == [5, 2 ** 32, 7]
+    assert w.stats()["hist"] == [(5, 1), (2 ** 32, 1), (7, 1)] and np.array_equal(w.encode()[1], big)
     wide = np.array([1, 2 ** 62], np.uint64)                               # gap > 60 bits
     with pytest.raises(IndexError):
         nat.encode_stream(wide, True)
