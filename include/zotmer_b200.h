@@ -157,7 +157,8 @@ int zb_set_stats(const zb_set* s, uint64_t acgt_weighted[4], uint64_t acgt_plain
  * The reference sums Python ints and writes them with codec64 (up to 60 bits): when a sum passes 2^32-1 the result is
  * a WIDE set -- zb_set_is_wide; its counts come back as u64 through zb_set_fetch_counts64 (zb_set_fetch saturates them
  * at 2^32-1), zb_set_stats and zb_set_encode* work with the true counts, zb_set_from_streams* gives a wide set for
- * streams that hold such counts and zb_merge takes wide inputs; trim / sample / restrict / slice of one are ZB_E_RANGE. */
+ * streams that hold such counts, zb_merge takes wide inputs, and trim / sample / restrict / slice of one keep the true
+ * counts of what they keep (trim thresholds beyond 2^32-1 on a wide set: ZB_E_RANGE). */
 int zb_merge(int nsets, zb_set* const* sets, zb_set** out);
 int zb_set_is_wide(const zb_set* s, int* wide);
 int zb_set_fetch_counts64(const zb_set* s, uint64_t* counts);   /* any set: its counts as u64 */

@@ -620,8 +620,20 @@ def test_merge_counts_beyond_u32(nat, monkeypatch, route, nsets):
     assert st["total"] == int(ec.sum())
     kw, cw = m.encode()
     assert np.array_equal(kw, co.encode(ek, True)) and np.array_equal(cw, co.encode(ec, False))
+    # subsets of a wide set keep the true counts of what they keep (trim.py:54-62 compares Python ints)
+    t = m.trim(3)
+    tk, tc = t.fetch()
+    xk, xc = co.trim(ek, ec, 3, 0)
+    assert t.is_wide() and np.array_equal(tk, xk) and np.array_equal(tc, xc) and t.stats()["hist"] == co.hist(xc)
+    t2 = m.trim(1, 1000)                       # the upper cutoff drops every huge count: an ordinary set again
+    t2k, t2c = t2.fetch()
+    x2k, x2c = co.trim(ek, ec, 1, 1000)
+    assert not t2.is_wide() and np.array_equal(t2k, x2k) and np.array_equal(t2c.astype(np.uint64), x2c)
     with pytest.raises(Exception):
-        m.trim(2)
+        m.trim(1, 2 ** 33)                     # thresholds beyond 2^32-1 on such a set are not supported
+    sl = m.slice(5, len(ek) - 5)
+    sk, sc = sl.fetch()
+    assert np.array_equal(sk, ek[5:-5]) and np.array_equal(sc.astype(np.uint64), ec[5:-5])
     # the streams read back are the same wide set (files.py:219-227 decodes Python ints)
     back = nat.KmerSet.from_streams(kw, cw)
     bk, bc = back.fetch()

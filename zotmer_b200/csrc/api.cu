@@ -636,6 +636,9 @@ int engine_lock_mask() {
 
 }  // namespace zb
 
+// true counts of a wide set's entries that survive in a subset of it (defined with the wide-set code further down)
+static void zb_set_carry_wide(const zb_set* in, zb_set* out);
+
 // ZB_E_RANGE for a set with counts beyond 2^32-1
 static void no_wide(const zb_set* s, const char* what) {
     if (s && s->wide.get()) ZB_FAIL(ZB_E_RANGE, "%s: the set holds counts beyond 2^32-1 (only merge output, stats, encode and fetch handle them)", what);
@@ -1175,7 +1178,6 @@ int zb_set_lower_bound(const zb_set* s, const uint64_t* probes, size_t m, uint64
 int zb_set_slice(const zb_set* s, size_t begin, size_t end, zb_set** out) {
     ZB_TRY
     if (!s || !out || begin > end || end > s->n) ZB_FAIL(ZB_E_ARG, "bad slice");
-    no_wide(s, "slice");
     Ctx* c = s->c;
     ZB_CUDA(cudaSetDevice(c->device));
     zb_set* r = new_set(c, end - begin);
@@ -1183,6 +1185,7 @@ int zb_set_slice(const zb_set* s, size_t begin, size_t end, zb_set** out) {
         ZB_CUDA(dev_copy(c, r->k.get(), s->k.get() + begin, (end - begin) * 8));
         ZB_CUDA(dev_copy(c, r->cnt.get(), s->cnt.get() + begin, (end - begin) * 4));
         ZB_CUDA(cudaStreamSynchronize(c->stream));
+        zb_set_carry_wide(s, r);
     }
     *out = r;
     ZB_CATCH
@@ -1453,6 +1456,67 @@ void zb_set_finish_wide(zb_set* r) {
     }
 }
 
+__global__ void __launch_bounds__(256) widen_kernel(const uint32_t* __restrict__ c, size_t n, uint64_t* __restrict__ w) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) w[i] = c[i];
+}
+__global__ void __launch_bounds__(256) gather_keys_kernel(const uint64_t* __restrict__ idx, size_t m, const uint64_t* __restrict__ k, size_t n,
+                                                          uint64_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < m) out[i] = idx[i] < n ? k[idx[i]] : ~0ull;
+}
+__global__ void __launch_bounds__(256) patch_wide_kernel(uint64_t* __restrict__ w, const uint64_t* __restrict__ idx_val /*[2m]*/, size_t m) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < m) w[idx_val[i]] = idx_val[m + i];
+}
+
+// `out` holds a subset of the entries of `in` (trim, sample, restrict, slice: the counts travel unchanged).  If `in` is
+// wide, the entries of `out` whose u32 count is saturated get their true counts back: the few of them are looked up by
+// key in the list of `in`.  lo / hi (hi = 0: none): the count range a trim kept -- a listed entry that the saturated
+// count let through although its true count is outside (thresholds beyond 2^32-1) cannot be taken out again here.
+static void carry_wide(const zb_set* in, zb_set* out, uint64_t lo = 0, uint64_t hi = 0) {
+    if (!in->wide.get()) return;
+    Ctx* c = in->c;
+    const size_t m = in->exc_key.size();
+    for (size_t i = 0; i < m; i++) {
+        const uint64_t v = in->exc_val[i];
+        const bool want = v >= lo && (hi == 0 || v <= hi);
+        const bool got = 0xffffffffull >= lo && (hi == 0 || 0xffffffffull <= hi);
+        if (want != got) ZB_FAIL(ZB_E_RANGE, "trim: count thresholds beyond 2^32-1 on a set that holds such counts");
+    }
+    if (out->n == 0 || m == 0) return;
+    std::vector<uint64_t> idx(m), keys(m);
+    lower_bound(c, out->k.get(), out->n, in->exc_key.data(), m, idx.data());
+    DBuf<uint64_t> d(c, 2 * m);
+    ZB_CUDA(cudaMemcpyAsync(d.get(), idx.data(), m * 8, cudaMemcpyHostToDevice, c->stream));
+    gather_keys_kernel<<<(unsigned)div_up(m, 256), 256, 0, c->stream>>>(d.get(), m, out->k.get(), out->n, d.get() + m);
+    ZB_LAUNCH_CHECK(c);
+    ZB_CUDA(cudaMemcpyAsync(keys.data(), d.get() + m, m * 8, cudaMemcpyDeviceToHost, c->stream));
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<uint64_t> iv;
+    for (size_t i = 0; i < m; i++) {
+        if (idx[i] < out->n && keys[i] == in->exc_key[i]) {
+            out->exc_idx.push_back(idx[i]);
+            out->exc_key.push_back(in->exc_key[i]);
+            out->exc_val.push_back(in->exc_val[i]);
+        }
+    }
+    const size_t kept = out->exc_idx.size();
+    if (kept == 0) return;
+    out->wide.alloc(c, out->n);
+    const unsigned blocks = (unsigned)std::min<size_t>((size_t)c->sm_count * 8, div_up(out->n, 256));
+    widen_kernel<<<blocks, 256, 0, c->stream>>>(out->cnt.get(), out->n, out->wide.get());
+    ZB_LAUNCH_CHECK(c);
+    iv.resize(2 * kept);
+    for (size_t i = 0; i < kept; i++) { iv[i] = out->exc_idx[i]; iv[kept + i] = out->exc_val[i]; }
+    DBuf<uint64_t> div_(c, 2 * kept);
+    ZB_CUDA(cudaMemcpyAsync(div_.get(), iv.data(), 2 * kept * 8, cudaMemcpyHostToDevice, c->stream));
+    patch_wide_kernel<<<(unsigned)div_up(kept, 256), 256, 0, c->stream>>>(out->wide.get(), div_.get(), kept);
+    ZB_LAUNCH_CHECK(c);
+    ZB_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+static void zb_set_carry_wide(const zb_set* in, zb_set* out) { carry_wide(in, out); }
+
 extern "C" {
 
 static int merge_wide(int nsets, zb_set* const* sets, zb_set** out) {
@@ -1568,13 +1632,18 @@ int zb_set_fetch_counts64(const zb_set* s, uint64_t* counts) {
 int zb_trim(const zb_set* s, uint64_t cmin, uint64_t cmax, zb_set** out) {
     ZB_TRY
     if (!s || !out) ZB_FAIL(ZB_E_ARG, "null argument");
-    no_wide(s, "trim");
     Ctx* c = s->c;
     ZB_CUDA(cudaSetDevice(c->device));
     zb_set* r = new_set(c, s->n);
-    EngineLock el(c, ENG_SM);
-    Stage st(c, "trim");
-    r->n = trim_pairs(c, s->k.get(), s->cnt.get(), s->n, cmin, cmax, r->k.get(), r->cnt.get());
+    try {
+        EngineLock el(c, ENG_SM);
+        Stage st(c, "trim");
+        r->n = trim_pairs(c, s->k.get(), s->cnt.get(), s->n, cmin, cmax, r->k.get(), r->cnt.get());
+        carry_wide(s, r, cmin, cmax);
+    } catch (...) {
+        delete r;
+        throw;
+    }
     *out = r;
     ZB_CATCH
 }
@@ -1582,12 +1651,17 @@ int zb_trim(const zb_set* s, uint64_t cmin, uint64_t cmax, zb_set** out) {
 int zb_sample(const zb_set* s, int mode, uint64_t seed, double p, zb_set** out) {
     ZB_TRY
     if (!s || !out || mode < 0 || mode > 1) ZB_FAIL(ZB_E_ARG, "bad argument");
-    no_wide(s, "sample");
     Ctx* c = s->c;
     ZB_CUDA(cudaSetDevice(c->device));
     zb_set* r = new_set(c, s->n);
-    Stage st(c, "sample");
-    r->n = sample_pairs(c, s->k.get(), s->cnt.get(), s->n, mode, seed, p, r->k.get(), r->cnt.get());
+    try {
+        Stage st(c, "sample");
+        r->n = sample_pairs(c, s->k.get(), s->cnt.get(), s->n, mode, seed, p, r->k.get(), r->cnt.get());
+        carry_wide(s, r);
+    } catch (...) {
+        delete r;
+        throw;
+    }
     *out = r;
     ZB_CATCH
 }
@@ -1596,12 +1670,17 @@ int zb_restrict(const zb_set* s, const zb_set* ref, zb_set** out) {
     ZB_TRY
     if (!s || !ref || !out) ZB_FAIL(ZB_E_ARG, "null argument");
     if (s->c != ref->c) ZB_FAIL(ZB_E_ARG, "sets must live on one device");
-    no_wide(s, "restrict");
     Ctx* c = s->c;
     ZB_CUDA(cudaSetDevice(c->device));
     zb_set* r = new_set(c, s->n);
-    Stage st(c, "restrict");
-    r->n = restrict_pairs(c, s->k.get(), s->cnt.get(), s->n, ref->k.get(), ref->n, r->k.get(), r->cnt.get());
+    try {
+        Stage st(c, "restrict");
+        r->n = restrict_pairs(c, s->k.get(), s->cnt.get(), s->n, ref->k.get(), ref->n, r->k.get(), r->cnt.get());
+        carry_wide(s, r);
+    } catch (...) {
+        delete r;
+        throw;
+    }
     *out = r;
     ZB_CATCH
 }
