@@ -437,3 +437,91 @@ def test_bgzf_probe_without_a_device():
         assert total == len(data)
     with pytest.raises(Exception):
         nat.bgzf_groups(gzip.compress(data), 70000)
+
+
+def test_bgzf_groups_handed_from_device_to_device(tmp_path, monkeypatch):
+    """library/devices.py: the runs of members of a block-compressed file are dealt out to the devices; every device
+    puts the leftover of the previous run in front of its text, cuts at its last record boundary and hands the rest on.
+    The device calls (inflate, concat, cut) are stood in for by host code here; the threads, the order of the hand-over
+    and the cuts are the real ones.  (The multi-GPU tests that run this on devices need more than one GPU.)"""
+    import gzip
+    import threading
+    from tools import synth
+    from zotmer_b200.library import devices, reads
+
+    class FakeStaged(object):
+        def __init__(self, data):
+            self.data = bytes(data)
+
+        def __len__(self):
+            return len(self.data)
+
+        def cut(self, fa):
+            d = self.data
+            if fa:
+                return d.rfind(b"\n>") + 1
+            nl = d.count(b"\n")
+            if nl < 4:
+                return 0
+            at = len(d)
+            for _ in range(nl % 4 + 1):
+                at = d.rfind(b"\n", 0, at)
+            return at + 1
+
+        def fetch_range(self, off, n):
+            return self.data[off:off + n]
+
+        def set_len(self, n):
+            self.data = self.data[:n]
+
+        def free(self):
+            self.data = b""
+
+    class FakeNative(object):
+        bgzf_probe = staticmethod(devices._native.bgzf_probe)
+        bgzf_groups = staticmethod(devices._native.bgzf_groups)
+
+        @staticmethod
+        def stage_bgzf(comp, dev):
+            return FakeStaged(gzip.decompress(bytes(comp))), len(comp)
+
+        @staticmethod
+        def stage_concat(prefix, body, dev):
+            return FakeStaged(bytes(prefix) + body.data)
+
+    monkeypatch.setattr(devices, "_native", FakeNative)
+    monkeypatch.setattr(reads, "BGZF_GROUP", 1 << 20)
+    g = synth.genome(400000, seed=31)
+    fq = synth.fastq_array(g, 12000, seed=32).reshape(-1).tobytes()[:-1]            # no final newline
+    big = synth.genome(2600000, seed=34)        # one record longer than two runs: they hold no record boundary
+    fa = synth.fasta_bytes(g) + b">p2\n" + synth.fasta_bytes(big)[6:] + b">p3\n" + synth.fasta_bytes(synth.genome(90000, seed=33))[6:] + b">p4\nACGT"
+    for name, text, is_fa in (("a.fq.gz", fq, False), ("b.fa.gz", fa, True)):
+        fn = tmp_path / name
+        fn.write_bytes(synth.bgzf_bytes(text, block=50000))
+        for n in (2, 3, 8):
+            jobs = []
+            assert devices._bgzfJobs(str(fn), is_fa, n, jobs) and len(jobs) >= 2
+            out = [None] * len(jobs)
+            errors = []
+
+            def work(j):
+                grp = jobs[j][0]
+                try:
+                    st = devices._stageBgzfGroup(grp, jobs[j - 1][0] if not grp.first else None, is_fa, j % n, errors)
+                    out[j] = st.data if st is not None else b""
+                except BaseException as e:      # noqa: B902
+                    errors.append(e)
+
+            # rounds of n jobs, the devices of a round at once, later rounds' threads started before earlier ones end
+            ths = [threading.Thread(target=work, args=(j,)) for j in reversed(range(len(jobs)))]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            assert not errors, errors
+            assert b"".join(out) == text
+            for piece in out[:-1]:
+                if is_fa:
+                    assert piece == b"" or (piece[:1] == b">" and piece[-1:] == b"\n")
+                else:
+                    assert piece.count(b"\n") % 4 == 0 and (piece == b"" or piece[-1:] == b"\n")
