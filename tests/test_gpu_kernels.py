@@ -630,7 +630,7 @@ def test_merge_counts_beyond_u32(nat, monkeypatch, route, nsets):
     x2k, x2c = co.trim(ek, ec, 1, 1000)
     assert not t2.is_wide() and np.array_equal(t2k, x2k) and np.array_equal(t2c.astype(np.uint64), x2c)
     with pytest.raises(Exception):
-        m.trim(1, 2 ** 33)                     # thresholds beyond 2^32-1 on such a set are not supported
+        m.trim(1, 2 ** 32 + 5)                 # a cutoff beyond 2^32-1 that would have to drop a saturated entry: not supported
     sl = m.slice(5, len(ek) - 5)
     sk, sc = sl.fetch()
     assert np.array_equal(sk, ek[5:-5]) and np.array_equal(sc.astype(np.uint64), ec[5:-5])
