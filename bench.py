@@ -645,10 +645,7 @@ def run_ours(args, rank, world, local_rank):
                           "note": "the same K steps one after the other on one stream (CUDA events on that stream): the region "
                                   "`roofline` and its per-stage times are measured in"},
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64", "data": "synthetic",
-        "config": dict(workload_config(world), steps_in_flight=in_flight_dev,
-                       pipelining="%d steps in flight, one host thread and stream each; every step does the whole work "
-                                  "(`one_in_flight` = the same steps one after the other)" % in_flight_dev),
+        "dtype": "u64", "data": "synthetic", "config": workload_config(world),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(8 * sum(twsz)),
                 "ms_per_step": e2e_ms, "steps_in_flight": inflight,
                 "result": "the two codec64 word streams of the trimmed set (what `zot trim` writes) in pinned host memory + count "
