@@ -364,3 +364,30 @@ def test_cli_kmerize_bgzf_golden(tmp_path):
     out = str(tmp_path / "o.k25")
     subprocess.check_call([sys.executable, "-m", "zotmer_b200.cli", "kmerize", "25", out, gz], cwd=ROOT)
     assert open(out, "rb").read() == open(want, "rb").read()
+
+
+def test_stage_input_from_pinned_memory(nat):
+    """a source that is pinned already is copied from where it lies (no trip through the pinned ring): same bytes, same set"""
+    data = _texts()["fastq"]
+    pin = nat.PinnedArray(len(data), np.uint8)
+    pin.a[:] = np.frombuffer(data, dtype=np.uint8)
+    st = nat.stage_input(pin.a, 0)
+    assert st.fetch() == data
+    st.free()
+    km = nat.Kmerizer(25, 0)
+    km.feed_staged(nat.stage_input(pin.a, 0), False)
+    a, na = km.finish()
+    km.close()
+    km = nat.Kmerizer(25, 0)
+    km.feed_staged(nat.stage_input(data, 0), False)
+    b, nb = km.finish()
+    km.close()
+    ak, ac = a.fetch()
+    bk, bc = b.fetch()
+    assert na == nb and np.array_equal(ak, bk) and np.array_equal(ac, bc)
+    z = __import__("tools.synth", fromlist=["x"]).bgzf_bytes(data)
+    pz = nat.PinnedArray(len(z), np.uint8)
+    pz.a[:] = np.frombuffer(z, dtype=np.uint8)
+    st, used = nat.stage_bgzf(pz.a, 0)
+    assert used == len(z) and st.fetch() == data
+    st.free(); pin.free(); pz.free()

@@ -179,9 +179,26 @@ static void stage_jobs(zb_staged* st, const uint8_t* raw, int fd, uint64_t file_
     ZB_CUDA(cudaEventCreateWithFlags(&st->alloc_ev, cudaEventDisableTiming));
     ZB_CUDA(cudaEventRecord(st->alloc_ev, st->c->stream));
     cudaEvent_t alloc_ev = st->alloc_ev;
+    // a source that is pinned already (zb_host_alloc, cudaHostAlloc, cudaHostRegister) is copied from where it lies
+    bool pinned = false;
+    if (raw) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, raw) == cudaSuccess) pinned = pa.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
     st->g.remaining = nchunks;   // nothing below throws: every counted chunk is submitted
     for (size_t i = 0; i < nchunks; i++) {
         const size_t off = i * chunk, len = std::min(chunk, n - off);
+        if (pinned) {
+            pool.submit([st, raw, dst, off, len, device, alloc_ev](IoWorker& w) {
+                cudaSetDevice(device);
+                cudaStream_t ws = w.stream[device & 63];
+                const bool ok = cudaStreamWaitEvent(ws, alloc_ev, 0) == cudaSuccess &&
+                                cudaMemcpyAsync(dst + off, raw + off, len, cudaMemcpyHostToDevice, ws) == cudaSuccess;
+                st->g.done(w.id, ok ? 0 : EIO);
+            });
+            continue;
+        }
         pool.submit([st, raw, fd, file_off, dst, off, len, device, chunk, alloc_ev](IoWorker& w) {
             int err = 0, s = 0;
             uint8_t* slot = take_slot(w, chunk, &s);
