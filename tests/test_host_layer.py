@@ -355,14 +355,26 @@ def test_device_inflater_core_on_the_host_equals_zlib(tmp_path):
     import random
     import zlib
     so = str(tmp_path / "libzi_host.so")
-    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "host", "inflate_host.cpp")])
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-pthread", "-o", so, os.path.join(ROOT, "tests", "host", "inflate_host.cpp")])
     L = ctypes.CDLL(so)
     L.zi_inflate_host.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32]
+    L.zi_inflate_host_lanes.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32]
     rng = random.Random(1)
+    lanes = [0]
 
     def inflate(comp, n):
-        out = ctypes.create_string_buffer(n + 8)
+        """one lane, and -- every few calls -- 2, 4 or 8 lanes on as many threads with a real barrier (the lanes' protocol:
+        parked literals, two-literal entries, shared copies, synchronisation on overlap); both must agree"""
+        out = ctypes.create_string_buffer(n + 72)
         rc = L.zi_inflate_host(comp, len(comp), out, n)
+        lanes[0] += 1
+        if lanes[0] % 3 == 0:
+            w = (2, 4, 8)[(lanes[0] // 3) % 3]
+            out2 = ctypes.create_string_buffer(n + 72)
+            rc2 = L.zi_inflate_host_lanes(w, comp, len(comp), out2, n)
+            assert (rc2 == 0) == (rc == 0), (rc, rc2, w)
+            if rc == 0:
+                assert out2.raw[:n] == out.raw[:n], w
         return rc, out.raw[:n]
 
     def check(data, level, strategy, wbits=-15, mem=9):

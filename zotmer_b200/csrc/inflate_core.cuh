@@ -31,6 +31,8 @@
 #endif
 #ifdef __CUDA_ARCH__
 #define ZI_SYNC(m) __syncwarp(m)
+#elif defined(ZI_HOST_SYNC)
+#define ZI_SYNC(m) do { (void)(m); ZI_HOST_SYNC(); } while (0)   // host test with several "lanes" on threads: a real barrier
 #else
 #define ZI_SYNC(m) do { (void)(m); } while (0)
 #endif
@@ -54,7 +56,12 @@ enum {
 
 // Table entries (u32).  bits 0-3: code length (0 = not in the table: a longer code, or no code at all);
 // bits 4-7: extra bits; bits 8-9: kind; bits 16-31: the literal, the length base or the distance base.
+// A literal entry may hold TWO literals (K_TWO set: bits 0-3 = both code lengths together, second literal in bits
+// 24-31) when both codes fit the table index -- text is mostly literals of 3 - 5 bits between short matches
+// (3.7 literals per match in FASTQ at level 6), and the second one then costs a few instructions instead of a
+// whole trip through the loop.
 enum { K_LIT = 0, K_LEN = 1, K_END = 2, K_BAD = 3 };
+static constexpr uint32_t K_TWO = 1u << 10;
 
 ZI_HD uint32_t lit_entry(int sym, int len) {
     if (sym < 256) return (uint32_t)len | (K_LIT << 8) | ((uint32_t)sym << 16);
@@ -180,8 +187,15 @@ ZI_HD bool build(int lane, uint32_t smask, const uint8_t* lens, int n, uint16_t*
     for (int e = lane; e < (1 << tbits); e += W) {
         int l = 0;
         const int s = slow_decode((uint32_t)e, tbits, cnt, sym, &l);
-        if (KIND == 0) reinterpret_cast<uint32_t*>(tab)[e] = (s < 0) ? 0u : lit_entry(s, l);
-        else if (KIND == 1) reinterpret_cast<uint32_t*>(tab)[e] = (s < 0) ? 0u : dist_entry(s, l);
+        if (KIND == 0) {
+            uint32_t ent = (s < 0) ? 0u : lit_entry(s, l);
+            if (W >= 2 && s >= 0 && s < 256 && l < tbits) {   // a second literal in the bits behind the first?
+                int l2 = 0;
+                const int s2 = slow_decode((uint32_t)e >> l, tbits - l, cnt, sym, &l2);
+                if (s2 >= 0 && s2 < 256) ent = (uint32_t)(l + l2) | (K_LIT << 8) | K_TWO | ((uint32_t)s << 16) | ((uint32_t)s2 << 24);
+            }
+            reinterpret_cast<uint32_t*>(tab)[e] = ent;
+        } else if (KIND == 1) reinterpret_cast<uint32_t*>(tab)[e] = (s < 0) ? 0u : dist_entry(s, l);
         else reinterpret_cast<uint16_t*>(tab)[e] = (s < 0) ? (uint16_t)0 : (uint16_t)((l << 9) | s);
     }
     ZI_SYNC(smask);
@@ -211,7 +225,7 @@ ZI_HD void flush_literals(int lane, uint8_t* out, uint32_t& lit0, uint32_t pos, 
 // Inflate the raw deflate stream src[0, clen) into out[0, isize).  W lanes (a power of two: a warp, or an aligned part
 // of one -- `smask` names the lanes of the group for its synchronisations) call this together with identical arguments
 // and their own `lane` (0 .. W - 1); the result code is the same in every lane.  Reads up to 16 bytes past
-// src + clen (never uses them) and may write up to W bytes past out + isize when the stream is corrupt (the caller
+// src + clen (never uses them) and may write up to W + 1 bytes past out + isize when the stream is corrupt (the caller
 // keeps that much slack behind the last member and rejects the whole group on any error).
 template <int W>
 ZI_HD int inflate_member(int lane, uint32_t smask, const uint8_t* src, uint32_t clen, uint8_t* out, uint32_t isize, Scratch* S) {
@@ -310,12 +324,14 @@ ZI_HD int inflate_member(int lane, uint32_t smask, const uint8_t* src, uint32_t 
             const uint32_t kind = (e >> 8) & 3u;
             if (kind == K_LIT) {
                 b.drop(e & 15u);
-                if (pos - lit0 >= (uint32_t)W) {
+                const uint32_t two = (e >> 10) & 1u;
+                if (pos - lit0 + two >= (uint32_t)W) {   // the run in the registers is full
                     flush_literals<W>(lane, out, lit0, pos, mine);
                     if (pos > isize) return ZI_E_OUT;
                 }
                 if (((pos ^ (uint32_t)lane) & (uint32_t)(W - 1)) == 0) mine = e >> 16;
-                pos++;
+                if (two && (((pos + 1u) ^ (uint32_t)lane) & (uint32_t)(W - 1)) == 0) mine = e >> 24;
+                pos += 1u + two;
                 continue;
             }
             if (kind != K_LEN) {
@@ -349,7 +365,9 @@ ZI_HD int inflate_member(int lane, uint32_t smask, const uint8_t* src, uint32_t 
             {
                 const uint8_t* from = out + from0;
                 uint8_t* to = out + pos;
-                if (dist >= len) {
+                if (len <= (uint32_t)W) {      // the common case: every lane at most one byte
+                    if ((uint32_t)lane < len) to[lane] = from[dist >= len ? (uint32_t)lane : (dist == 1 ? 0u : (uint32_t)lane % dist)];
+                } else if (dist >= len) {
                     for (uint32_t j = (uint32_t)lane; j < len; j += W) to[j] = from[j];
                 } else if (dist == 1) {
                     const uint8_t v = from[0];
