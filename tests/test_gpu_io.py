@@ -391,3 +391,24 @@ def test_stage_input_from_pinned_memory(nat):
     st, used = nat.stage_bgzf(pz.a, 0)
     assert used == len(z) and st.fetch() == data
     st.free(); pin.free(); pz.free()
+
+
+@pytest.mark.parametrize("k", [25, 31])
+def test_kmerize_fasta_record_longer_than_a_piece(nat, k):
+    """a chromosome that does not fit a feed piece is cut inside (library/reads.py:splitPieces): same set, same record count"""
+    from tools import synth
+    from zotmer_b200.library.reads import stagedPieces
+    g = synth.genome(400000, seed=41)
+    fa = synth.fasta_bytes(g) + b">p2\n" + synth.fasta_bytes(synth.genome(90000, seed=42), width=100000)[6:] + b">p3\nACGTTGCA\n"
+    km = nat.Kmerizer(k, 0)
+    fake = pieces_fed = 0
+    for (st, is_fa) in stagedPieces([("x.fa", fa)], 0, max_piece=70000, k=k):
+        fake += getattr(st, "fake_records", 0)
+        pieces_fed += 1
+        km.feed_staged(st, is_fa)
+    s, nr = km.finish()
+    km.close()
+    assert pieces_fed >= 6 and fake >= 4
+    ks, cs = s.fetch()
+    ek, ec, _, enr = co.kmerize(k, [(fa, True)])
+    assert nr - fake == enr == 3 and np.array_equal(ks, ek) and np.array_equal(cs, ec)

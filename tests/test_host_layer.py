@@ -537,3 +537,59 @@ def test_bgzf_groups_handed_from_device_to_device(tmp_path, monkeypatch):
                     assert piece == b"" or (piece[:1] == b">" and piece[-1:] == b"\n")
                 else:
                     assert piece.count(b"\n") % 4 == 0 and (piece == b"" or piece[-1:] == b"\n")
+
+
+def test_long_fasta_records_are_cut_inside():
+    """library/reads.py:splitPieces -- a FASTA record longer than a piece is cut after a line (or inside a line longer than
+    the piece); the next piece starts with an empty header + the k - 1 characters before the cut.  Feeding the pieces
+    must give the k-mers, counts and (after subtracting the extra headers) records of the whole file: oracle on both
+    sides, with the reference's line rules (indented headers, '>' and blanks inside lines, CRLF, blank lines, text
+    before the first header)."""
+    import random
+    from oracle import c_oracle as co
+    from zotmer_b200.library.reads import splitPieces
+
+    def rnd_fasta(rng, nrec, maxlen, linelens, weird):
+        out = []
+        if weird and rng.random() < 0.3:
+            out.append(b"ACGTACGTAAAA junk before the first header\n")
+        for r in range(nrec):
+            out.append(b">rec%d some text\n" % r if not (weird and rng.random() < 0.2) else b"  >indented header\n")
+            L = rng.randrange(0, maxlen)
+            seq = bytes(rng.choice(b"ACGT" if rng.random() < 0.97 else b"NnRY") for _ in range(L))
+            i = 0
+            while i < L:
+                w = rng.choice(linelens)
+                line = seq[i:i + w]
+                i += w
+                if weird and rng.random() < 0.1:
+                    line = b"  " + line + b" \t"
+                if weird and rng.random() < 0.05 and len(line) > 4:
+                    line = line[:2] + b" " + line[2:]
+                if weird and rng.random() < 0.02 and len(line) > 4:
+                    line = line[:3] + b">" + line[3:]
+                out.append(line + (b"\r\n" if weird and rng.random() < 0.1 else b"\n"))
+                if weird and rng.random() < 0.03:
+                    out.append(b"\n")
+        data = b"".join(out)
+        return data[:-1] if rng.random() < 0.5 and data.endswith(b"\n") else data
+
+    rng = random.Random(11)
+    done = 0
+    for trial in range(260):
+        data = rnd_fasta(rng, rng.randint(1, 4), rng.choice([50, 400, 3000]), rng.choice([[60], [7, 13], [100000], [1, 2, 3]]), trial % 2 == 1)
+        k = rng.choice([1, 2, 5, 16, 25, 31, 32])
+        mp = rng.choice([40, 97, 300, 1000])
+        if len(data) <= mp:
+            continue
+        ps = list(splitPieces(data, True, k, mp))
+        assert b"".join(bytes(v) for _, v, _ in ps) == data and all(len(v) <= mp for _, v, _ in ps)
+        fake = sum(f for _, _, f in ps)
+        ek, ec, _, enr = co.kmerize(k, [(data, True)])
+        gk, gc, _, gnr = co.kmerize(k, [(pre + bytes(v), True) for pre, v, _ in ps])
+        assert np.array_equal(ek, gk) and np.array_equal(ec, gc) and gnr - fake == enr, (trial, k, mp)
+        done += 1
+    assert done > 150
+    # FASTQ and short inputs go through `pieces` unchanged
+    fq = b"@r\nACGT\n+\nIIII\n" * 50
+    assert [(p, bytes(v), f) for p, v, f in splitPieces(fq, False, 25, 100)] == [(b"", bytes(v), 0) for v in __import__("zotmer_b200.library.reads", fromlist=["x"]).pieces(fq, False, 100)]

@@ -23,9 +23,13 @@ def kmerizeFiles(K, inputs, device=0, verbose=False, baits=None):
     try:
         if baits is not None:
             km.set_baits(baits)
-        for (staged, fa) in stagedPieces(inputs, device, verbose):
+        fake = 0
+        # capture mode keeps or drops whole records: a record is then never cut inside
+        for (staged, fa) in stagedPieces(inputs, device, verbose, k=K if baits is None else None):
+            fake += getattr(staged, 'fake_records', 0)
             km.feed_staged(staged, fa)
-        return km.finish()
+        (s, nr) = km.finish()
+        return s, nr - fake
     finally:
         km.close()
 

@@ -55,12 +55,119 @@ def pieces(data, is_fasta, max_piece=MAX_PIECE):
         yield mv[start:]
 
 
-def stagedPieces(inputs, device=0, verbose=False, max_piece=MAX_PIECE):
+_WS = b" \t\n\r\x0b\x0c"      # what py2's strip() removes (file.py:24,30)
+
+
+def _isHeaderAt(data, at, lo):
+    """data[at] == '>': is it the first non-blank byte of its line (readFasta's test for a header, file.py:24-26)?"""
+    j = at - 1
+    while j >= lo and data[j:j + 1] != b"\n":
+        if data[j:j + 1] not in (b" ", b"\t", b"\r", b"\x0b", b"\x0c"):
+            return False
+        j -= 1
+    return True
+
+
+def _headerIn(data, lo, hi):
+    """does data[lo:hi] hold a header line?"""
+    at = data.find(b">", lo, hi)
+    while at >= 0:
+        if _isHeaderAt(data, at, lo):
+            return True
+        at = data.find(b">", at + 1, hi)
+    return False
+
+
+def _seqTail(region, m, starts_line):
+    """the last m characters of the sequence readFasta has joined so far when it has read `region` (a stretch of a
+    record's lines; starts_line: it begins at the start of a line).  None if the region ends in a header line."""
+    lines = region.split(b"\n")
+    seq = []
+    header = False
+    for i, l in enumerate(lines):
+        t = l.strip(_WS) if (i > 0 or starts_line) else l.rstrip(_WS)
+        if i == len(lines) - 1 and l and l[-1:] not in (b" ", b"\t", b"\r", b"\x0b", b"\x0c"):
+            t = l.lstrip(_WS) if (i > 0 or starts_line) else l       # the line goes on behind the cut: nothing trails yet
+        if (i > 0 or starts_line) and t[:1] == b">":
+            seq = []
+            header = True
+            continue
+        header = False
+        seq.append(t)
+    if header:
+        return None
+    joined = b"".join(seq[-(m + 2):]) if m else b""
+    if len(joined) < m:
+        joined = b"".join(seq)
+    return joined[max(0, len(joined) - m):] if m else b""
+
+
+def splitPieces(data, is_fasta, k, max_piece=MAX_PIECE):
+    """`pieces` that never gives up on a long FASTA record: -> (prefix, piece, fake).  A record that fills a whole window
+    is cut inside (after a line, or inside a line that is itself longer than the window); the next piece then starts
+    with `prefix` = an empty header line + the last k - 1 characters of the sequence so far, so that exactly the
+    windows that span the cut are seen there (the reference streams a record of any length, file.py:19-36).  `fake` = 1
+    for such a piece: it adds a record that is not one."""
+    n = len(data)
+    if n <= max_piece or not is_fasta:
+        for p in pieces(data, is_fasta, max_piece):
+            yield (b"", p, 0)
+        return
+    mv = memoryview(data)
+    start = 0
+    prefix, fake = b"", 0
+    in_record = False          # a header line lies before `start`
+    look = max(4096, 64 * k)
+    while n - start > max_piece:
+        end = start + max_piece
+        cut = data.rfind(b"\n>", start + 1, end)
+        if cut > start:
+            cut += 1
+            yield (prefix, mv[start:cut], fake)
+            prefix, fake, start, in_record = b"", 0, cut, True
+            continue
+        nl = data.rfind(b"\n", start + 1, end)
+        if nl > start:
+            p, midline = nl + 1, False
+        else:
+            p, midline = end, True
+            # not next to white space (it would become leading / trailing and vanish) and not in front of a '>' (it would
+            # become the first byte of a line: a header)
+            while p > start + 2 and (data[p - 1:p] in (b" ", b"\t", b"\r", b"\x0b", b"\x0c") or
+                                     data[p:p + 1] in (b" ", b"\t", b"\r", b"\x0b", b"\x0c", b">")):
+                p -= 1
+        in_record = in_record or _headerIn(data, start, p)
+        yield (prefix, mv[start:p], fake)
+        if in_record:
+            lo = max(start, p - look)
+            region = bytes(mv[lo:p])
+            starts_line = lo == start or data[lo - 1:lo] == b"\n"
+            if lo == start and prefix:
+                region, starts_line = prefix + region, True
+            tail = _seqTail(region, k - 1, starts_line)
+            if tail is None:
+                # the cut follows a header line: that header opens an empty record in the piece just given out, and
+                # the sequence needs a header of its own here
+                prefix, fake = b">\n", 1
+            else:
+                if tail[:1] == b">":        # a '>' from inside a line must not open the line here (any letter that is
+                    tail = b"-" + tail      # no base does in front of it: no window starts there)
+                prefix, fake = b">\n" + tail + (b"" if midline else b"\n"), 1
+        else:
+            prefix, fake = b"", 0
+        start = p
+    if start < n:
+        yield (prefix, mv[start:], fake)
+
+
+def stagedPieces(inputs, device=0, verbose=False, max_piece=MAX_PIECE, k=None):
     """(staged piece, is_fasta) for every record-aligned piece of every input file, in order; the copy of the NEXT piece
     to the device has already been started (library I/O threads, pinned ring) when a piece is handed out, so reading /
     copying piece i + 1 overlaps the parsing and extraction of piece i.  A plain file that fits one piece is read by the
     I/O threads themselves (pread into pinned chunks: no mapping, no Python bytes object); anything else (stdin, .gz /
-    .bz2, files beyond one piece) is staged from host memory."""
+    .bz2, files beyond one piece) is staged from host memory.  k: the k-mer length, for callers that count k-mers -- a
+    FASTA record longer than a piece is then cut inside instead of refused; such a piece counts one record too many
+    (`fake_records` of the staged piece)."""
     import os
     import sys
     from zotmer_b200 import _native
@@ -82,9 +189,16 @@ def stagedPieces(inputs, device=0, verbose=False, max_piece=MAX_PIECE):
                 yield ('bgzf', _bgzf(fn), 0, fa)      # block-compressed: inflated on the device, group by group
             else:
                 data = held if held is not None else mapBytes(fn)
-                for piece in pieces(data, fa, max_piece):
-                    if len(piece):
-                        yield ('mem', piece, len(piece), fa)
+                if k is not None:
+                    # a FASTA record longer than a piece is cut inside (splitPieces): the piece behind the cut starts with
+                    # an empty header line and the k - 1 characters in front of the cut
+                    for (prefix, piece, fake) in splitPieces(data, fa, k, max_piece):
+                        if len(piece):
+                            yield ('mem', (prefix, piece, fake), len(piece), fa)
+                else:
+                    for piece in pieces(data, fa, max_piece):
+                        if len(piece):
+                            yield ('mem', piece, len(piece), fa)
 
     def start(job):
         kind, src, n, fa = job
@@ -92,6 +206,15 @@ def stagedPieces(inputs, device=0, verbose=False, max_piece=MAX_PIECE):
             f = open(src, 'rb')
             st = _native.stage_fd(f.fileno(), 0, n, device)
             st.keep = f            # the descriptor stays open until the piece has been fed
+            return st, fa
+        if isinstance(src, tuple):
+            (prefix, piece, fake) = src
+            st = _native.stage_input(piece, device)
+            if prefix:
+                keep = st.keep
+                st = _native.stage_concat(prefix, st, device)     # waits for the copy of `piece`
+                st.keep = keep
+            st.fake_records = fake
             return st, fa
         return _native.stage_input(src, device), fa
 
