@@ -345,6 +345,21 @@ def test_piece_rounds_are_record_aligned(tmp_path):
         else:
             assert p.count(b"\n") % 4 == 0 and p[:1] == b"@"
     assert sum(1 for p, f in flat if not f) >= 3 and sum(1 for p, f in flat if f and p.startswith(b">chr")) == 1
+    # with the k-mer length known the long record is spread over the devices: cut inside, prefix + piece per cut
+    from oracle import c_oracle as co
+    rounds = devices._pieceRounds([str(fa)], 3, k=25)
+    jobs = [j for r in rounds for j in r]
+    assert len(jobs) >= 3
+    texts, fake = [], 0
+    for (src, is_fa) in jobs:
+        if isinstance(src, tuple):
+            texts.append(src[0] + bytes(src[1]))
+            fake += src[2]
+        else:
+            texts.append(bytes(src))
+    ek, ec, _, enr = co.kmerize(25, [(fa.read_bytes(), True)])
+    gk, gc, _, gnr = co.kmerize(25, [(t, True) for t in texts])
+    assert np.array_equal(ek, gk) and np.array_equal(ec, gc) and gnr - fake == enr == 1
 
 
 def test_device_inflater_core_on_the_host_equals_zlib(tmp_path):

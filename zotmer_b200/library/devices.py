@@ -144,8 +144,10 @@ def _stageBgzfGroup(grp, prev, fa, dev, errors):
         grp.done.set()
 
 
-def _pieceRounds(inputs, n, verbose=False):
-    """record-aligned pieces of all inputs, about 1/n of a file each (at most MAX_PIECE), grouped n at a time"""
+def _pieceRounds(inputs, n, verbose=False, k=None):
+    """record-aligned pieces of all inputs, about 1/n of a file each (at most MAX_PIECE), grouped n at a time.
+    k: the k-mer length when a FASTA record longer than a share may be cut inside (reads.splitPieces: a chromosome is then
+    spread over the devices like any other input); such a piece is a (prefix, piece, extra records) triple."""
     import sys
     from zotmer_b200.library.file import mapBytes
     jobs = []
@@ -164,6 +166,12 @@ def _pieceRounds(inputs, n, verbose=False):
         if len(data) == 0:
             continue
         share = max(1 << 20, min(MAX_PIECE, -(-len(data) // n)))
+        if k is not None and fa:
+            from zotmer_b200.library.reads import splitPieces
+            for t in splitPieces(data, fa, k, share):
+                if len(t[1]):
+                    jobs.append((t if (t[0] or t[2]) else t[1], fa))
+            continue
         try:
             cut = list(pieces(data, fa, share))
         except ValueError:      # a record longer than a share (a chromosome): it goes to one device whole
@@ -188,8 +196,10 @@ def kmerizeFilesMulti(K, inputs, devs, verbose=False, baits_fn=None):
     baits_fn: FASTA file of bait sequences (`-C`); every device kmerizes it for itself."""
     g = _Group(devs)
     n = g.n
-    rounds = _pieceRounds(inputs, n, verbose)
+    # capture mode keeps or drops whole records: a record is then never cut inside
+    rounds = _pieceRounds(inputs, n, verbose, k=K if baits_fn is None else None)
     flat = [job for rd in rounds for job in rd]     # a BGZF group finds the group before it here
+    fake = sum(job[0][2] for job in flat if isinstance(job[0], tuple))   # headers that splitPieces put in front of cut records
     nat = _native
 
     def work(r):
@@ -210,6 +220,9 @@ def kmerizeFilesMulti(K, inputs, devs, verbose=False, baits_fn=None):
             if isinstance(src, _BgzfGroup):
                 prev = flat[src.job - 1][0] if not src.first else None
                 return _stageBgzfGroup(src, prev, rounds[ri][r][1], dev, g.errors)
+            if isinstance(src, tuple):             # the piece behind a cut inside a record: its prefix goes in front
+                st = nat.stage_input(src[1], dev)
+                return nat.stage_concat(src[0], st, dev) if src[0] else st
             return nat.stage_input(src, dev)
 
         try:
@@ -270,7 +283,7 @@ def kmerizeFilesMulti(K, inputs, devs, verbose=False, baits_fn=None):
         return mine, nr
 
     res = g.run(work)
-    return [x[0] for x in res], sum(x[1] for x in res)
+    return [x[0] for x in res], sum(x[1] for x in res) - fake
 
 
 def statsMulti(ranges):
