@@ -8,7 +8,8 @@ context -- stream, allocator -- per (device, host thread)), NVLink peer mappings
 
   1. the input files are cut into record-aligned pieces and dealt out to the devices in ROUNDS of N pieces; a device
      stages its piece through the pinned ring, parses it and extracts the canonical k-mers (csrc/parse.cu, extract.cu).
-     A block-compressed file (BGZF) is dealt out as runs of whole gzip members instead: a device inflates its run itself
+     A FASTA record longer than a device's share (a chromosome) is cut inside (reads.splitPieces) and spread over the
+     devices.  A block-compressed file (BGZF) is dealt out as runs of whole gzip members instead: a device inflates its run itself
      (csrc/inflate.cu) and the incomplete record behind a run's last record boundary travels to the device that holds
      the next run (_stageBgzfGroup);
   2. per round, the hash-range exchange of bench.py / multigpu.py, without collectives: the per-owner counts of all
