@@ -412,3 +412,35 @@ def test_kmerize_fasta_record_longer_than_a_piece(nat, k):
     ks, cs = s.fetch()
     ek, ec, _, enr = co.kmerize(k, [(fa, True)])
     assert nr - fake == enr == 3 and np.array_equal(ks, ek) and np.array_equal(cs, ec)
+
+
+def test_kmerize_bgzf_with_a_damaged_member_stops_where_gunzip_stops(nat, tmp_path, monkeypatch):
+    """file.py:93-97 pipes `gunzip -c` and never looks at its exit status: what was written before the damaged member
+    is processed, the rest is not.  Same here: the group that fails on the device is inflated on the host up to the damage."""
+    from tools import synth
+    from zotmer_b200.commands.kmerize import kmerizeFiles
+    from zotmer_b200.library import reads
+    from zotmer_b200.library.file import gunzipBytes
+    data = _texts()["fastq"]
+    z = bytearray(synth.bgzf_bytes(data, block=30000))
+    members = []
+    p = 0
+    while p < len(z):
+        bsize = (z[p + 16] | (z[p + 17] << 8)) + 1
+        members.append((p, bsize))
+        p += bsize
+    assert len(members) > 12
+    for victim, group in ((1, None), (9, 70000), (len(members) - 2, 200000)):
+        zz = bytearray(z)
+        (mp, bs) = members[victim]
+        zz[mp + 40:mp + 90] = b"\xff" * 50          # inside the member's deflate stream
+        want = gunzipBytes(bytes(zz))
+        assert 0 < len(want) < len(data) and data.startswith(want)
+        gz = tmp_path / ("bad%d.fq.gz" % victim)
+        gz.write_bytes(bytes(zz))
+        monkeypatch.setattr(reads, "BGZF_GROUP", group or reads.BGZF_GROUP)
+        (a, na) = kmerizeFiles(25, [str(gz)], 0)
+        ak, ac = a.fetch()
+        ek, ec, _, enr = co.kmerize(25, [(want, False)])
+        assert na == enr and np.array_equal(ak, ek) and np.array_equal(ac, ec), victim
+        a.free()
