@@ -67,7 +67,10 @@ struct ExHist {
     uint32_t* hist;
 };
 
-template <bool OWNERS, bool HIST>
+// HIST: 0 = no histograms; 2 / 3 = exactly that many digits, all in the upper 32 bits of the key (the top-bit passes of a
+// k >= 17 batch: one 32-bit shift per digit, no predicates); 4 = the general form (up to 4 digits anywhere in the key).
+// The tallies were 22 % of this kernel's instructions in the general form (profiles/r02_ncu_extract_hist.txt).
+template <bool OWNERS, int HIST>
 __global__ void __launch_bounds__(EX_THREADS)
 extract_kernel(int k, const uint8_t* __restrict__ codes, uint64_t* __restrict__ out,
                unsigned long long* __restrict__ counter, int nranks, unsigned long long* __restrict__ owner_counts, const ExHist eh) {
@@ -152,7 +155,11 @@ extract_kernel(int k, const uint8_t* __restrict__ codes, uint64_t* __restrict__ 
     for (uint32_t i = tid; i < tot; i += EX_THREADS) {
         const uint64_t kx = s_keys[i];
         out[base + i] = kx;
-        if (HIST) {
+        if (HIST == 2 || HIST == 3) {
+            const uint32_t hi = (uint32_t)(kx >> 32);
+#pragma unroll
+            for (int p = 0; p < HIST; p++) atomicAdd(&s_hist[p * 256 + ((hi >> (eh.shift[p] - 32)) & eh.mask[p])], 1u);
+        } else if (HIST) {
 #pragma unroll
             for (int p = 0; p < 4; p++)
                 if (p < eh.passes) atomicAdd(&s_hist[p * 256 + ((uint32_t)(kx >> eh.shift[p]) & eh.mask[p])], 1u);
@@ -202,7 +209,7 @@ void extract_canonical(Ctx* c, int k, const uint8_t* codes, size_t n, uint64_t* 
     ExHist eh;
     memset(&eh, 0, sizeof eh);
     if (nranks > 1 && nranks <= 64 && d_owner_counts) {
-        extract_kernel<true, false><<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count, nranks, d_owner_counts, eh);
+        extract_kernel<true, 0><<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count, nranks, d_owner_counts, eh);
     } else if (pre && pre->d_hist && pre->passes >= 1 && pre->passes <= 4) {
         eh.passes = pre->passes;
         for (int p = 0; p < pre->passes; p++) {
@@ -211,9 +218,13 @@ void extract_canonical(Ctx* c, int k, const uint8_t* codes, size_t n, uint64_t* 
             eh.mask[p] = (1u << pre->bits[p]) - 1u;
         }
         eh.hist = pre->d_hist;
-        extract_kernel<false, true><<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count, 0, nullptr, eh);
+        bool upper = true;
+        for (int p = 0; p < pre->passes; p++) upper = upper && pre->shift[p] >= 32;
+        if (upper && pre->passes == 2) extract_kernel<false, 2><<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count, 0, nullptr, eh);
+        else if (upper && pre->passes == 3) extract_kernel<false, 3><<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count, 0, nullptr, eh);
+        else extract_kernel<false, 4><<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count, 0, nullptr, eh);
     } else {
-        extract_kernel<false, false><<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count, 0, nullptr, eh);
+        extract_kernel<false, 0><<<tiles, EX_THREADS, 0, c->stream>>>(k, codes, out, d_count, 0, nullptr, eh);
     }
     ZB_LAUNCH_CHECK(c);
 }
