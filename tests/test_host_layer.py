@@ -608,3 +608,90 @@ def test_long_fasta_records_are_cut_inside():
     # FASTQ and short inputs go through `pieces` unchanged
     fq = b"@r\nACGT\n+\nIIII\n" * 50
     assert [(p, bytes(v), f) for p, v, f in splitPieces(fq, False, 25, 100)] == [(b"", bytes(v), 0) for v in __import__("zotmer_b200.library.reads", fromlist=["x"]).pieces(fq, False, 100)]
+
+
+def test_bgzf_pieces_groups_carry_and_damage(monkeypatch):
+    """library/reads.py:bgzfPieces with the device calls stood in for by host code: groups of members, the incomplete
+    record carried to the next piece, a record that fills several groups, and a damaged member (the input ends where
+    `gunzip -c` would have stopped writing, file.py:93-97)"""
+    import gzip
+    from tools import synth
+    from zotmer_b200.library import reads
+    from zotmer_b200.library.file import gunzipBytes
+    from zotmer_b200 import _native as real_nat
+
+    class FakeStaged(object):
+        def __init__(self, data):
+            self.data = bytes(data)
+
+        def __len__(self):
+            return len(self.data)
+
+        def cut(self, fa):
+            d = self.data
+            if fa:
+                return d.rfind(b"\n>") + 1
+            nl = d.count(b"\n")
+            if nl < 4:
+                return 0
+            at = len(d)
+            for _ in range(nl % 4 + 1):
+                at = d.rfind(b"\n", 0, at)
+            return at + 1
+
+        def fetch_range(self, off, n):
+            return self.data[off:off + n]
+
+        def set_len(self, n):
+            self.data = self.data[:n]
+
+        def free(self):
+            self.data = b""
+
+    class FakeNative(object):
+        @staticmethod
+        def stage_bgzf(data, device=0, max_out=0, carry=None, carry_off=0):
+            nat = real_nat
+            a = bytes(data)
+            head = carry.data[carry_off:] if carry is not None else b""
+            # whole members while the text fits max_out (at least one), as zb_stage_bgzf takes them
+            starts = nat.bgzf_groups(a, 65536)
+            text, used = b"", 0
+            for s0, s1 in zip(starts, starts[1:] + [len(a)]):
+                try:
+                    t = gzip.decompress(a[s0:s1])
+                except Exception:
+                    raise AssertionError("BGZF member does not inflate")
+                if used and max_out and len(head) + len(text) + len(t) > max_out:
+                    break
+                text += t
+                used = s1
+            return FakeStaged(head + text), used
+
+        @staticmethod
+        def stage_input(data, device=0):
+            return FakeStaged(bytes(data))
+
+    import zotmer_b200
+    monkeypatch.setattr(zotmer_b200, "_native", FakeNative, raising=False)
+    g = synth.genome(300000, seed=51)
+    fq = synth.fastq_array(g, 4000, seed=52).reshape(-1).tobytes()
+    fa = synth.fasta_bytes(g) + b">p2\nACGT\nAC\n>p3 x\nGGGG"
+    for text, is_fa in ((fq, False), (fa, True)):
+        z = synth.bgzf_bytes(text, block=20000)
+        for group in (70000, 150000, 10 ** 9):
+            out = [st.data for st in reads.bgzfPieces(z, is_fa, 0, group=group)]
+            assert b"".join(out) == text
+            for piece in out[:-1]:
+                assert piece[-1:] == b"\n" and (piece[:1] == b">" if is_fa else piece.count(b"\n") % 4 == 0)
+    # a damaged member in the third group
+    z = bytearray(synth.bgzf_bytes(fq, block=20000))
+    p, k = 0, 0
+    while k < 9:
+        p += (z[p + 16] | (z[p + 17] << 8)) + 1
+        k += 1
+    z[p + 40:p + 90] = b"\xff" * 50
+    want = gunzipBytes(bytes(z))
+    assert 0 < len(want) < len(fq)
+    out = b"".join(st.data for st in reads.bgzfPieces(bytes(z), False, 0, group=70000))
+    assert out == want
